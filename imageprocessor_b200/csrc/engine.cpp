@@ -1,0 +1,1222 @@
+// engine.cpp -- libipgpu.so host engine + C ABI (include/ipgpu.h).
+//
+// One submission queue and two service threads per device (a batcher that turns
+// queued tickets into one launch sequence on a free lane, and a completer that
+// retires lanes in order); `lanes_per_device` lanes, each a CUDA stream with its
+// own device arena and pinned parameter blob, so the H2D of batch k+1, the kernels
+// of batch k and the D2H of batch k-1 overlap.  Images shard by ticket across
+// devices; there is no cross-device exchange, hence no collective.
+//
+// The drop-in boundary is processor.ImageProcessor.Process
+// (internal/usecase/processor/image_processor.go:39): the Go side keeps decode,
+// parameter parsing, geometry, glyph rasterisation, encode and SaveProcessed and
+// calls ipg_submit/ipg_wait where it called resizeImage / cropAndResize /
+// addTextWatermark.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ipgpu.h"
+#include "ipg_device.h"
+#include "kernels.h"
+#include "plan.h"
+
+namespace ipg {
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+static std::string cuda_msg(const char *what, cudaError_t e)
+{
+    return std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+}
+#define IPG_CU(call)                                                      \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) throw std::runtime_error(cuda_msg(#call, e__)); \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int plane_count(int layout) { return layout >= IPG_LAYOUT_YCBCR444 ? 3 : 1; }
+static void plane_dims(int layout, int plane, int w, int h, int *pw_bytes, int *ph)
+{
+    if (plane == 0) {
+        *pw_bytes = (layout == IPG_LAYOUT_RGBA8 || layout == IPG_LAYOUT_NRGBA8) ? w * 4 : w;
+        *ph = h;
+        return;
+    }
+    int cw = w, ch = h; // image.NewYCbCr chroma sizes
+    if (layout == IPG_LAYOUT_YCBCR422 || layout == IPG_LAYOUT_YCBCR420) cw = (w + 1) / 2;
+    if (layout == IPG_LAYOUT_YCBCR420 || layout == IPG_LAYOUT_YCBCR440) ch = (h + 1) / 2;
+    *pw_bytes = cw;
+    *ph = ch;
+}
+
+// ---------------------------------------------------------------------------------
+// pinned memory: caller-visible allocations (registry) and an internal staging pool
+// ---------------------------------------------------------------------------------
+class PinnedRegistry {
+public:
+    void add(void *p, size_t n)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        map_[(uintptr_t)p] = n;
+    }
+    bool remove(void *p)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        return map_.erase((uintptr_t)p) > 0;
+    }
+    bool contains(const void *p, size_t n)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = map_.upper_bound((uintptr_t)p);
+        if (it == map_.begin()) return false;
+        --it;
+        return (uintptr_t)p + n <= it->first + it->second;
+    }
+    std::vector<void *> drain()
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        std::vector<void *> v;
+        for (auto &kv : map_) v.push_back((void *)kv.first);
+        map_.clear();
+        return v;
+    }
+
+private:
+    std::mutex mu_;
+    std::map<uintptr_t, size_t> map_;
+};
+
+// First-fit pool over one pinned slab; alloc blocks until space is free.
+class StagingPool {
+public:
+    bool init(size_t bytes)
+    {
+        if (cudaHostAlloc((void **)&base_, bytes, cudaHostAllocPortable) != cudaSuccess) return false;
+        size_ = bytes;
+        free_[0] = bytes;
+        return true;
+    }
+    void destroy()
+    {
+        if (base_) cudaFreeHost(base_);
+        base_ = nullptr;
+    }
+    size_t size() const { return size_; }
+    uint8_t *alloc(size_t n, const std::atomic<bool> &stop)
+    {
+        n = align_up(std::max<size_t>(n, 1), 256);
+        if (n > size_) return nullptr;
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            for (auto it = free_.begin(); it != free_.end(); ++it) {
+                if (it->second >= n) {
+                    size_t off = it->first, rem = it->second - n;
+                    free_.erase(it);
+                    if (rem) free_[off + n] = rem;
+                    used_[off] = n;
+                    return base_ + off;
+                }
+            }
+            if (stop.load()) return nullptr;
+            cv_.wait_for(lk, std::chrono::milliseconds(50));
+        }
+    }
+    void release(uint8_t *p)
+    {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu_);
+        size_t off = (size_t)(p - base_);
+        auto u = used_.find(off);
+        if (u == used_.end()) return;
+        size_t n = u->second;
+        used_.erase(u);
+        auto nx = free_.lower_bound(off);
+        if (nx != free_.end() && off + n == nx->first) {
+            n += nx->second;
+            nx = free_.erase(nx);
+        }
+        if (nx != free_.begin()) {
+            auto pv = std::prev(nx);
+            if (pv->first + pv->second == off) {
+                pv->second += n;
+                cv_.notify_all();
+                return;
+            }
+        }
+        free_[off] = n;
+        cv_.notify_all();
+    }
+
+private:
+    uint8_t *base_ = nullptr;
+    size_t size_ = 0;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::map<size_t, size_t> free_, used_;
+};
+
+// ---------------------------------------------------------------------------------
+// tickets
+// ---------------------------------------------------------------------------------
+struct GlyphRec {
+    ipg_glyph g;
+    std::vector<uint8_t> mask; // owned copy, tight stride = mask_w
+};
+
+struct OpRec {
+    int kind = 0;
+    int dw = 0, dh = 0;
+    int rx = 0, ry = 0, rw = 0, rh = 0;
+    uint8_t color[4] = {0, 0, 0, 0};
+    std::vector<GlyphRec> glyphs;
+    void *dst = nullptr;
+    int dst_stride = 0;
+    int dst_mem = 0;
+    uint8_t *stage = nullptr; // staging for a non-pinned host dst (tight rows)
+    uint8_t *dev_out = nullptr;
+    size_t dev_pitch = 0;
+};
+
+struct Ticket {
+    uint64_t id = 0;
+    int dev = 0;
+    ipg_image_desc src{};
+    uint8_t *src_stage[3] = {nullptr, nullptr, nullptr};
+    std::vector<OpRec> ops;
+    size_t dev_bytes = 0; // arena bytes this ticket needs
+    size_t cost = 0;      // for device selection
+    std::mutex mu;
+    std::condition_variable cv;
+    bool done = false;
+    int status = IPG_OK;
+    std::string err;
+};
+using TicketP = std::shared_ptr<Ticket>;
+
+// ---------------------------------------------------------------------------------
+// lanes, devices, context
+// ---------------------------------------------------------------------------------
+struct Batch {
+    std::vector<TicketP> tickets;
+    int lane = -1;
+    bool failed = false;
+    std::string err;
+    int n_kernels = 0;
+    uint64_t h2d = 0, d2h = 0;
+    uint64_t exact_fallbacks = 0;
+    bool has_fix = false;
+};
+
+struct Lane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t done = nullptr;
+    uint8_t *arena = nullptr;
+    size_t arena_bytes = 0;
+    uint8_t *param_host = nullptr; // pinned
+    size_t param_cap = 0;
+    uint32_t *fix_count_host = nullptr; // pinned, 1 word
+    bool busy = false;
+};
+
+struct Ctx;
+struct Device {
+    Ctx *ctx = nullptr;
+    int index = 0;
+    int cuda_id = 0;
+    std::vector<Lane> lanes;
+    std::mutex mu;
+    std::condition_variable cv_q, cv_lane, cv_idle;
+    std::deque<TicketP> queue;
+    std::deque<std::unique_ptr<Batch>> inflight;
+    std::atomic<uint64_t> outstanding{0};
+    std::thread batcher, completer;
+    StagingPool staging;
+};
+
+struct Ctx {
+    ipg_config cfg{};
+    std::vector<std::unique_ptr<Device>> devs;
+    std::atomic<bool> stop{false};
+    std::atomic<uint64_t> next_id{1};
+    std::mutex tmu;
+    std::unordered_map<uint64_t, TicketP> tickets;
+    PinnedRegistry pinned;
+    // stats
+    std::atomic<uint64_t> s_done{0}, s_batches{0}, s_kernels{0}, s_h2d{0}, s_d2h{0}, s_fix{0}, s_fallback{0}, s_staged{0};
+    std::mutex smu;
+    double s_stream_ms = 0, s_fix_ms = 0, s_other_ms = 0;
+};
+
+} // namespace ipg
+
+struct ipg_ctx : ipg::Ctx {};
+
+namespace ipg {
+
+// bump allocator over a lane's device arena
+struct Arena {
+    uint8_t *base;
+    size_t cap, off = 0;
+    uint8_t *take(size_t n, size_t a = 256)
+    {
+        size_t o = align_up(off, a);
+        if (o + n > cap) return nullptr;
+        off = o + n;
+        return base + o;
+    }
+};
+
+// host-side image of the parameter blob with the matching device base address
+struct Blob {
+    uint8_t *host;
+    uint8_t *dev;
+    size_t cap, off = 0;
+    bool overflow = false;
+    std::unordered_map<const void *, size_t> seen;
+    template <typename T> T *dptr(size_t o) const { return (T *)(dev + o); }
+    size_t put(const void *data, size_t bytes, size_t a = 16)
+    {
+        size_t o = align_up(off, a);
+        if (o + bytes > cap) {
+            overflow = true;
+            return 0;
+        }
+        if (bytes) memcpy(host + o, data, bytes);
+        off = o + bytes;
+        return o;
+    }
+    template <typename T> const T *put_vec(const std::vector<T> &v)
+    {
+        auto it = seen.find((const void *)v.data());
+        if (it != seen.end()) return dptr<const T>(it->second);
+        size_t o = put(v.data(), v.size() * sizeof(T), 16);
+        seen[(const void *)v.data()] = o;
+        return dptr<const T>(o);
+    }
+    size_t reserve(size_t bytes, size_t a = 16)
+    {
+        size_t o = align_up(off, a);
+        if (o + bytes > cap) {
+            overflow = true;
+            return 0;
+        }
+        off = o + bytes;
+        return o;
+    }
+};
+
+static AxisExact pack_axis(Blob &b, const AxisPlan &p)
+{
+    AxisExact a;
+    a.off = b.put_vec(p.off);
+    a.first = b.put_vec(p.first);
+    a.inv = b.put_vec(p.inv);
+    a.inv_ffff = b.put_vec(p.inv_ffff);
+    a.w = b.put_vec(p.w);
+    return a;
+}
+
+static size_t ticket_device_bytes(const Ticket &t)
+{
+    size_t n = 0;
+    if (t.src.memspace == IPG_MEM_HOST) {
+        for (int p = 0; p < plane_count(t.src.layout); p++) {
+            int wb, ph;
+            plane_dims(t.src.layout, p, t.src.width, t.src.height, &wb, &ph);
+            n += align_up((size_t)wb, 256) * (size_t)ph + 256;
+        }
+    }
+    for (auto &op : t.ops) {
+        if (op.dst_mem == IPG_MEM_HOST) n += align_up((size_t)std::max(op.dw, 0) * 4, 256) * (size_t)std::max(op.dh, 0) + 256;
+        for (auto &g : op.glyphs) n += align_up(g.mask.size(), 256) + 256;
+        n += 4096;
+    }
+    return n + 4096;
+}
+
+// Build and enqueue one batch on a lane.  Throws std::runtime_error on failure.
+static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
+{
+    IPG_CU(cudaSetDevice(d.cuda_id));
+    cudaStream_t st = L.st;
+    Arena arena{L.arena, L.arena_bytes};
+    uint8_t *blob_dev = arena.take(L.param_cap, 256);
+    if (!blob_dev) throw std::runtime_error("device arena smaller than the parameter blob");
+    Blob blob{L.param_host, blob_dev, L.param_cap};
+
+    std::vector<StreamJob> sjobs;
+    std::vector<StreamItem> sitems;
+    std::vector<ExactJob> fixjobs;    // one per stream target (EXACT mode)
+    std::vector<ExactJob> xjobs;      // whole-output fp64 jobs
+    std::vector<ExactItem> xitems;
+    std::vector<WmJob> wjobs;
+    std::vector<WmItem> witems;
+    struct Readback { uint8_t *dev; size_t pitch; void *host; size_t hstride; size_t row_bytes; int rows; };
+    std::vector<Readback> readbacks;
+    int max_nt = 0;
+    bool any_wm = false, any_check = false;
+    uint64_t fix_px = 0;
+    const int precision = c.cfg.precision;
+
+    // band count: aim for >= ~2 waves of CTAs over the whole batch
+    size_t est_ctas = 0;
+    for (auto &tp : B.tickets) est_ctas += (size_t)(tp->src.width + 479) / 480;
+    int bands_hint = (int)std::min<size_t>(32, std::max<size_t>(1, (1400 + est_ctas - 1) / std::max<size_t>(est_ctas, 1)));
+
+    for (auto &tp : B.tickets) {
+        Ticket &t = *tp;
+        // ---- source view on the device
+        SrcView sv{};
+        sv.w = t.src.width;
+        sv.h = t.src.height;
+        sv.layout = t.src.layout;
+        const uint8_t *dp[3] = {nullptr, nullptr, nullptr};
+        int ds[3] = {0, 0, 0};
+        for (int p = 0; p < plane_count(t.src.layout); p++) {
+            int wb, ph;
+            plane_dims(t.src.layout, p, t.src.width, t.src.height, &wb, &ph);
+            if (t.src.memspace == IPG_MEM_DEVICE) {
+                dp[p] = (const uint8_t *)t.src.plane[p];
+                ds[p] = t.src.stride[p];
+            } else {
+                size_t pitch = align_up((size_t)wb, 256);
+                uint8_t *dv = arena.take(pitch * (size_t)ph);
+                if (!dv) throw std::runtime_error("device arena exhausted (source)");
+                const void *hp = t.src_stage[p] ? (const void *)t.src_stage[p] : t.src.plane[p];
+                size_t hs = t.src_stage[p] ? (size_t)wb : (size_t)t.src.stride[p];
+                IPG_CU(cudaMemcpy2DAsync(dv, pitch, hp, hs, (size_t)wb, (size_t)ph, cudaMemcpyHostToDevice, st));
+                B.h2d += (uint64_t)wb * (uint64_t)ph;
+                dp[p] = dv;
+                ds[p] = (int)pitch;
+            }
+        }
+        sv.p0 = dp[0]; sv.p1 = dp[1]; sv.p2 = dp[2];
+        sv.s0 = ds[0]; sv.s1 = ds[1]; sv.s2 = ds[2];
+
+        // ---- destinations on the device
+        for (auto &op : t.ops) {
+            op.dev_out = nullptr;
+            if (op.dw <= 0 || op.dh <= 0) continue;
+            if (op.dst_mem == IPG_MEM_DEVICE) {
+                op.dev_out = (uint8_t *)op.dst;
+                op.dev_pitch = (size_t)op.dst_stride;
+            } else {
+                size_t pitch = align_up((size_t)op.dw * 4, 256);
+                op.dev_out = arena.take(pitch * (size_t)op.dh);
+                if (!op.dev_out) throw std::runtime_error("device arena exhausted (destination)");
+                op.dev_pitch = pitch;
+                void *hp = op.stage ? (void *)op.stage : op.dst;
+                size_t hs = op.stage ? (size_t)op.dw * 4 : (size_t)op.dst_stride;
+                readbacks.push_back({op.dev_out, pitch, hp, hs, (size_t)op.dw * 4, op.dh});
+            }
+        }
+
+        // ---- watermark descriptors
+        auto make_wm = [&](OpRec &op) -> WatermarkD {
+            WatermarkD w{};
+            w.dst = op.dev_out;
+            w.dst_stride = (int)op.dev_pitch;
+            w.sr = op.color[0] * 0x101u; w.sg = op.color[1] * 0x101u;
+            w.sb = op.color[2] * 0x101u; w.sa = op.color[3] * 0x101u;
+            std::vector<GlyphD> gd;
+            int bx0 = INT32_MAX, by0 = INT32_MAX, bx1 = INT32_MIN, by1 = INT32_MIN;
+            for (auto &g : op.glyphs) {
+                if (g.g.x0 >= g.g.x1 || g.g.y0 >= g.g.y1) continue;
+                const size_t o = blob.put(g.mask.data(), g.mask.size(), 16); // masks ride in the blob
+                GlyphD x{};
+                x.x0 = g.g.x0; x.y0 = g.g.y0; x.x1 = g.g.x1; x.y1 = g.g.y1;
+                x.mp_x = g.g.mp_x; x.mp_y = g.g.mp_y;
+                x.mask_stride = g.g.mask_w;
+                x.mask = blob.dptr<const uint8_t>(o);
+                gd.push_back(x);
+                bx0 = std::min(bx0, x.x0); by0 = std::min(by0, x.y0);
+                bx1 = std::max(bx1, x.x1); by1 = std::max(by1, x.y1);
+            }
+            w.n_glyphs = (int)gd.size();
+            if (gd.empty()) { bx0 = by0 = bx1 = by1 = 0; }
+            size_t o = blob.put(gd.data(), gd.size() * sizeof(GlyphD), 16);
+            w.glyphs = blob.dptr<const GlyphD>(o);
+            w.bx0 = bx0; w.by0 = by0; w.bx1 = bx1; w.by1 = by1;
+            return w;
+        };
+
+        auto add_exact = [&](OpRec &op, std::vector<ExactJob> &vec) -> int {
+            ExactJob j{};
+            j.src = sv;
+            j.two_stage = op.kind == IPG_OP_THUMB_CROP;
+            if (op.kind == IPG_OP_THUMB_CROP) { j.rect_x = op.rx; j.rect_y = op.ry; }
+            const int sw = op.kind == IPG_OP_THUMB_CROP ? op.rw : sv.w;
+            const int sh = op.kind == IPG_OP_THUMB_CROP ? op.rh : sv.h;
+            j.dw = op.dw; j.dh = op.dh;
+            j.dst = op.dev_out; j.dst_stride = (int)op.dev_pitch;
+            j.ax = pack_axis(blob, *get_axis_plan(op.dw, sw));
+            j.ay = pack_axis(blob, *get_axis_plan(op.dh, sh));
+            vec.push_back(j);
+            return (int)vec.size() - 1;
+        };
+        auto add_exact_whole = [&](OpRec &op) {
+            int ji = add_exact(op, xjobs);
+            for (int ty = 0; ty < (op.dh + 7) / 8; ty++)
+                for (int tx = 0; tx < (op.dw + 31) / 32; tx++) xitems.push_back(ExactItem{ji, tx, ty, 0});
+        };
+
+        // ---- classify ops
+        std::vector<OpRec *> res, wms;
+        for (auto &op : t.ops) {
+            if (op.dw <= 0 || op.dh <= 0) continue;
+            (op.kind == IPG_OP_WATERMARK ? wms : res).push_back(&op);
+        }
+        const bool streamable = precision != IPG_PRECISION_REFERENCE && sv.layout == L_RGBA8 &&
+                                (sv.s0 % 4) == 0 && ((size_t)sv.p0 % 4) == 0;
+        size_t wi = 0;
+        if (streamable) {
+            size_t ri = 0;
+            while (ri < res.size() || wi < wms.size()) {
+                // greedily take up to two resample targets + one watermark per pass over the source
+                OpRec *tg[2] = {nullptr, nullptr};
+                int nt = 0;
+                StreamTargetSpec spec[2];
+                while (ri < res.size() && nt < 2) {
+                    OpRec *op = res[ri];
+                    StreamTargetSpec s{0, 0, sv.w, sv.h, op->dw, op->dh};
+                    if (op->kind == IPG_OP_THUMB_CROP) s = StreamTargetSpec{op->rx, op->ry, op->rw, op->rh, op->dw, op->dh};
+                    spec[nt] = s;
+                    tg[nt++] = op;
+                    ri++;
+                }
+                OpRec *wm = wi < wms.size() ? wms[wi] : nullptr;
+                std::shared_ptr<const StreamGeom> geom;
+                if (nt > 0 || wm) geom = get_stream_geom(sv.w, sv.h, spec, nt, wm != nullptr, bands_hint, 257.0);
+                if (!geom && nt == 2) { // retry the targets one at a time
+                    ri -= 1;
+                    nt = 1;
+                    tg[1] = nullptr;
+                    geom = get_stream_geom(sv.w, sv.h, spec, 1, wm != nullptr, bands_hint, 257.0);
+                }
+                if (!geom) {
+                    if (nt == 1) { add_exact_whole(*tg[0]); B.exact_fallbacks++; }
+                    if (nt == 0 && wm) break; // cannot happen (wm-only always streams); fall to k_watermark
+                    continue;
+                }
+                if (wm) wi++;
+                StreamJob j{};
+                j.src = sv;
+                j.n_targets = nt;
+                j.has_wm = wm != nullptr;
+                j.tile_w = geom->tile_w;
+                j.n_tiles = geom->n_tiles;
+                j.n_bands = geom->n_bands;
+                j.band_y = blob.put_vec(geom->band_y);
+                j.band_yend = blob.put_vec(geom->band_yend);
+                for (int k = 0; k < nt; k++) {
+                    const StreamTargetGeom &tgm = geom->t[k];
+                    StreamTarget &o = j.t[k];
+                    o.dst = tg[k]->dev_out;
+                    o.dst_stride = (int)tg[k]->dev_pitch;
+                    o.dw = tg[k]->dw; o.dh = tg[k]->dh;
+                    o.rect_x = spec[k].rect_x; o.rect_y = spec[k].rect_y;
+                    o.two_stage = tg[k]->kind == IPG_OP_THUMB_CROP;
+                    o.fix_d = tgm.fix_d;
+                    o.xoff = blob.put_vec(tgm.ax->off);
+                    o.xfirst = blob.put_vec(tgm.ax->first);
+                    o.xw = blob.put_vec(tgm.xw);
+                    o.tile_ox = blob.put_vec(tgm.tile_ox);
+                    o.rows = blob.put_vec(tgm.rows);
+                    o.band_rec_off = blob.put_vec(tgm.band_rec_off);
+                    o.band_tend = blob.put_vec(tgm.band_tend);
+                    o.exact_job = -1;
+                    if (precision == IPG_PRECISION_EXACT) {
+                        o.exact_job = add_exact(*tg[k], fixjobs);
+                        fix_px += (uint64_t)o.dw * (uint64_t)o.dh;
+                    }
+                    if (o.two_stage && !t.src.opaque_hint) j.check_premul = 1;
+                }
+                if (wm) j.wm = make_wm(*wm);
+                max_nt = std::max(max_nt, nt);
+                any_wm |= wm != nullptr;
+                any_check |= j.check_premul != 0;
+                const int ji = (int)sjobs.size();
+                sjobs.push_back(j);
+                for (auto it : geom->items) {
+                    it.job = ji;
+                    sitems.push_back(it);
+                }
+            }
+        } else {
+            for (auto *op : res) {
+                add_exact_whole(*op);
+                if (precision != IPG_PRECISION_REFERENCE) B.exact_fallbacks++;
+            }
+        }
+        for (; wi < wms.size(); wi++) {
+            WmJob j{};
+            j.src = sv;
+            j.wm = make_wm(*wms[wi]);
+            const int ji = (int)wjobs.size();
+            wjobs.push_back(j);
+            for (int y = 0; y < sv.h; y += WM_ROWS) witems.push_back(WmItem{ji, y});
+        }
+    }
+
+    // ---- fix list (EXACT mode)
+    FixList fix{nullptr, nullptr, 0};
+    if (!fixjobs.empty()) {
+        uint64_t cap = std::min<uint64_t>(fix_px / 8 + 4096, 8u << 20);
+        uint8_t *cnt = arena.take(256);
+        uint8_t *ent = arena.take((size_t)cap * sizeof(FixEntry));
+        if (!cnt || !ent) throw std::runtime_error("device arena exhausted (fix list)");
+        fix.count = (uint32_t *)cnt;
+        fix.entries = (FixEntry *)ent;
+        fix.capacity = (uint32_t)cap;
+        IPG_CU(cudaMemsetAsync(cnt, 0, 4, st));
+        B.has_fix = true;
+    }
+
+    // ---- parameter blob upload
+    const StreamJob *d_sjobs = blob.dptr<const StreamJob>(blob.put(sjobs.data(), sjobs.size() * sizeof(StreamJob), 16));
+    const StreamItem *d_sitems = blob.dptr<const StreamItem>(blob.put(sitems.data(), sitems.size() * sizeof(StreamItem), 16));
+    const ExactJob *d_fixjobs = blob.dptr<const ExactJob>(blob.put(fixjobs.data(), fixjobs.size() * sizeof(ExactJob), 16));
+    const ExactJob *d_xjobs = blob.dptr<const ExactJob>(blob.put(xjobs.data(), xjobs.size() * sizeof(ExactJob), 16));
+    const ExactItem *d_xitems = blob.dptr<const ExactItem>(blob.put(xitems.data(), xitems.size() * sizeof(ExactItem), 16));
+    const WmJob *d_wjobs = blob.dptr<const WmJob>(blob.put(wjobs.data(), wjobs.size() * sizeof(WmJob), 16));
+    const WmItem *d_witems = blob.dptr<const WmItem>(blob.put(witems.data(), witems.size() * sizeof(WmItem), 16));
+    if (blob.overflow) throw std::runtime_error("parameter blob overflow (batch too heterogeneous); lower max_batch");
+    IPG_CU(cudaMemcpyAsync(blob_dev, L.param_host, blob.off, cudaMemcpyHostToDevice, st));
+    B.h2d += blob.off;
+
+    // ---- kernels
+    IPG_CU(cudaEventRecord(L.ev[0], st));
+    if (!sitems.empty()) {
+        IPG_CU(launch_stream(d_sjobs, d_sitems, (int)sitems.size(), max_nt, any_wm, any_check, fix, st));
+        B.n_kernels++;
+    }
+    IPG_CU(cudaEventRecord(L.ev[1], st));
+    if (!fixjobs.empty()) {
+        IPG_CU(launch_exact_fix(d_fixjobs, (int)fixjobs.size(), fix, st));
+        B.n_kernels++;
+    }
+    IPG_CU(cudaEventRecord(L.ev[2], st));
+    if (!xitems.empty()) {
+        IPG_CU(launch_exact_tiles(d_xjobs, d_xitems, (int)xitems.size(), st));
+        B.n_kernels++;
+    }
+    if (!witems.empty()) {
+        IPG_CU(launch_watermark(d_wjobs, d_witems, (int)witems.size(), st));
+        B.n_kernels++;
+    }
+    IPG_CU(cudaEventRecord(L.ev[3], st));
+
+    // ---- read back
+    if (B.has_fix) IPG_CU(cudaMemcpyAsync(L.fix_count_host, fix.count, 4, cudaMemcpyDeviceToHost, st));
+    for (auto &r : readbacks) {
+        IPG_CU(cudaMemcpy2DAsync(r.host, r.hstride, r.dev, r.pitch, r.row_bytes, (size_t)r.rows, cudaMemcpyDeviceToHost, st));
+        B.d2h += (uint64_t)r.row_bytes * (uint64_t)r.rows;
+    }
+    IPG_CU(cudaEventRecord(L.done, st));
+}
+
+static void finish_ticket(Ctx &c, Device &d, const TicketP &t, int status, const std::string &err)
+{
+    for (int p = 0; p < 3; p++) {
+        if (t->src_stage[p]) d.staging.release(t->src_stage[p]);
+        t->src_stage[p] = nullptr;
+    }
+    {
+        std::lock_guard<std::mutex> lk(t->mu);
+        t->status = status;
+        t->err = err;
+        t->done = true;
+    }
+    t->cv.notify_all();
+    d.outstanding.fetch_sub(t->cost);
+    c.s_done++;
+}
+
+static void batcher_main(Ctx *c, Device *d)
+{
+    cudaSetDevice(d->cuda_id);
+    for (;;) {
+        std::unique_ptr<Batch> B(new Batch);
+        int lane = -1;
+        {
+            std::unique_lock<std::mutex> lk(d->mu);
+            d->cv_q.wait(lk, [&] { return c->stop.load() || !d->queue.empty(); });
+            if (c->stop.load() && d->queue.empty()) return;
+            // a free lane first: tickets keep arriving while we wait for one
+            d->cv_lane.wait(lk, [&] {
+                for (auto &L : d->lanes)
+                    if (!L.busy) return true;
+                return c->stop.load();
+            });
+            for (size_t i = 0; i < d->lanes.size(); i++)
+                if (!d->lanes[i].busy) { lane = (int)i; break; }
+            if (lane < 0) return;
+            // short window to let concurrent submitters fill the batch
+            if ((int)d->queue.size() < c->cfg.max_batch && c->cfg.batch_window_us > 0) {
+                d->cv_q.wait_for(lk, std::chrono::microseconds(c->cfg.batch_window_us),
+                                 [&] { return (int)d->queue.size() >= c->cfg.max_batch || c->stop.load(); });
+            }
+            Lane &L = d->lanes[lane];
+            size_t budget = L.arena_bytes - L.param_cap - (64u << 20);
+            size_t used = 0;
+            while (!d->queue.empty() && (int)B->tickets.size() < c->cfg.max_batch) {
+                TicketP &t = d->queue.front();
+                if (!B->tickets.empty() && used + t->dev_bytes > budget) break;
+                used += t->dev_bytes;
+                B->tickets.push_back(t);
+                d->queue.pop_front();
+            }
+            L.busy = true;
+            B->lane = lane;
+        }
+        try {
+            launch_batch(*c, *d, d->lanes[lane], *B);
+        } catch (const std::exception &e) {
+            B->failed = true;
+            B->err = e.what();
+            cudaGetLastError();
+        }
+        {
+            std::lock_guard<std::mutex> lk(d->mu);
+            d->inflight.push_back(std::move(B));
+        }
+        d->cv_idle.notify_all();
+    }
+}
+
+static void completer_main(Ctx *c, Device *d)
+{
+    cudaSetDevice(d->cuda_id);
+    for (;;) {
+        std::unique_ptr<Batch> B;
+        {
+            std::unique_lock<std::mutex> lk(d->mu);
+            d->cv_idle.wait(lk, [&] { return !d->inflight.empty() || c->stop.load(); });
+            if (d->inflight.empty()) {
+                if (c->stop.load()) return;
+                continue;
+            }
+            B = std::move(d->inflight.front());
+            d->inflight.pop_front();
+        }
+        Lane &L = d->lanes[B->lane];
+        int status = IPG_OK;
+        std::string err;
+        if (B->failed) {
+            cudaStreamSynchronize(L.st);
+            status = IPG_ERR_CUDA;
+            err = B->err;
+            if (err.find("arena") != std::string::npos || err.find("blob") != std::string::npos) status = IPG_ERR_NOMEM;
+        } else {
+            cudaError_t e = cudaEventSynchronize(L.done);
+            if (e != cudaSuccess) {
+                status = IPG_ERR_CUDA;
+                err = cuda_msg("batch execution", e);
+            } else {
+                float a = 0, b = 0, o = 0;
+                cudaEventElapsedTime(&a, L.ev[0], L.ev[1]);
+                cudaEventElapsedTime(&b, L.ev[1], L.ev[2]);
+                cudaEventElapsedTime(&o, L.ev[2], L.ev[3]);
+                std::lock_guard<std::mutex> lk(c->smu);
+                c->s_stream_ms += a;
+                c->s_fix_ms += b;
+                c->s_other_ms += o;
+            }
+            if (B->has_fix && status == IPG_OK) c->s_fix += *L.fix_count_host;
+            c->s_batches++;
+            c->s_kernels += (uint64_t)B->n_kernels;
+            c->s_h2d += B->h2d;
+            c->s_d2h += B->d2h;
+            c->s_fallback += B->exact_fallbacks;
+        }
+        for (auto &t : B->tickets) finish_ticket(*c, *d, t, status, err);
+        {
+            std::lock_guard<std::mutex> lk(d->mu);
+            L.busy = false;
+        }
+        d->cv_lane.notify_all();
+        d->cv_idle.notify_all();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+static int validate(const ipg_image_desc *src, const ipg_op *ops, int n_ops)
+{
+    if (!src || !ops || n_ops <= 0) return fail(IPG_ERR_INVALID, "null source/ops or n_ops <= 0");
+    if (src->layout < IPG_LAYOUT_RGBA8 || src->layout > IPG_LAYOUT_YCBCR440) return fail(IPG_ERR_INVALID, "unknown source layout");
+    if (src->width <= 0 || src->height <= 0) return fail(IPG_ERR_INVALID, "source image is empty");
+    if ((int64_t)src->width * src->height > (int64_t)1 << 30) return fail(IPG_ERR_INVALID, "source image too large");
+    for (int p = 0; p < plane_count(src->layout); p++) {
+        int wb, ph;
+        plane_dims(src->layout, p, src->width, src->height, &wb, &ph);
+        if (!src->plane[p]) return fail(IPG_ERR_INVALID, "source plane pointer is null");
+        if (src->stride[p] < wb) return fail(IPG_ERR_INVALID, "source stride smaller than a row");
+    }
+    if (src->memspace != IPG_MEM_HOST && src->memspace != IPG_MEM_DEVICE) return fail(IPG_ERR_INVALID, "bad source memspace");
+    if (src->memspace == IPG_MEM_DEVICE && src->layout <= IPG_LAYOUT_NRGBA8 && ((src->stride[0] & 3) || ((uintptr_t)src->plane[0] & 3)))
+        return fail(IPG_ERR_INVALID, "device RGBA source must be 4-byte aligned");
+    for (int i = 0; i < n_ops; i++) {
+        const ipg_op &o = ops[i];
+        if (o.kind != IPG_OP_RESIZE && o.kind != IPG_OP_THUMB_CROP && o.kind != IPG_OP_WATERMARK)
+            return fail(IPG_ERR_INVALID, "unsupported operation kind");
+        if (o.dst_w > 65536 || o.dst_h > 65536) return fail(IPG_ERR_INVALID, "destination too large");
+        if (o.kind == IPG_OP_WATERMARK && (o.dst_w != src->width || o.dst_h != src->height))
+            return fail(IPG_ERR_INVALID, "watermark destination must have the source size");
+        if (o.dst_w > 0 && o.dst_h > 0) {
+            if (!o.dst) return fail(IPG_ERR_INVALID, "destination pointer is null");
+            if (o.dst_stride < o.dst_w * 4) return fail(IPG_ERR_INVALID, "destination stride smaller than a row");
+            if (o.dst_memspace == IPG_MEM_DEVICE && ((o.dst_stride & 3) || ((uintptr_t)o.dst & 3)))
+                return fail(IPG_ERR_INVALID, "device destination must be 4-byte aligned");
+        }
+        if (o.kind == IPG_OP_THUMB_CROP) {
+            if (o.rect_w <= 0 || o.rect_h <= 0 || o.rect_x < 0 || o.rect_y < 0 || o.rect_x + o.rect_w > src->width ||
+                o.rect_y + o.rect_h > src->height)
+                return fail(IPG_ERR_INVALID, "crop rectangle outside the source");
+        }
+        if (o.kind == IPG_OP_WATERMARK) {
+            if (o.n_glyphs < 0 || (o.n_glyphs > 0 && !o.glyphs)) return fail(IPG_ERR_INVALID, "bad glyph list");
+            for (int g = 0; g < o.n_glyphs; g++) {
+                const ipg_glyph &G = o.glyphs[g];
+                if (G.x0 >= G.x1 || G.y0 >= G.y1) continue; // dr.Empty(): nothing drawn
+                if (G.x0 < 0 || G.y0 < 0 || G.x1 > src->width || G.y1 > src->height)
+                    return fail(IPG_ERR_INVALID, "glyph rectangle must be clipped to the image");
+                if (!G.mask || G.mask_w <= 0 || G.mask_h <= 0 || G.mask_stride < G.mask_w)
+                    return fail(IPG_ERR_INVALID, "bad glyph mask");
+                if (G.mp_x < 0 || G.mp_y < 0 || G.mp_x + (G.x1 - G.x0) > G.mask_w || G.mp_y + (G.y1 - G.y0) > G.mask_h)
+                    return fail(IPG_ERR_INVALID, "glyph rectangle exceeds its mask");
+            }
+        }
+    }
+    return IPG_OK;
+}
+
+static int submit_impl(Ctx *c, int dev_index, const ipg_image_desc *src, const ipg_op *ops, int n_ops, ipg_ticket *out)
+{
+    if (!c || !out) return fail(IPG_ERR_INVALID, "null context or ticket pointer");
+    if (c->stop.load()) return fail(IPG_ERR_SHUTDOWN, "context is shutting down");
+    int rc = validate(src, ops, n_ops);
+    if (rc) return rc;
+    bool any_device_mem = src->memspace == IPG_MEM_DEVICE;
+    for (int i = 0; i < n_ops; i++) any_device_mem |= ops[i].dst_memspace == IPG_MEM_DEVICE;
+    if (dev_index < 0 && any_device_mem) return fail(IPG_ERR_INVALID, "device-resident buffers need ipg_submit_on");
+    if (dev_index >= (int)c->devs.size()) return fail(IPG_ERR_INVALID, "device index out of range");
+    if (dev_index < 0) { // least outstanding work
+        uint64_t best = UINT64_MAX;
+        for (size_t i = 0; i < c->devs.size(); i++) {
+            uint64_t o = c->devs[i]->outstanding.load();
+            if (o < best) { best = o; dev_index = (int)i; }
+        }
+    }
+    Device &d = *c->devs[dev_index];
+
+    auto t = std::make_shared<Ticket>();
+    t->dev = dev_index;
+    t->src = *src;
+    t->ops.resize((size_t)n_ops);
+    for (int i = 0; i < n_ops; i++) {
+        const ipg_op &o = ops[i];
+        OpRec &r = t->ops[i];
+        r.kind = o.kind; r.dw = o.dst_w; r.dh = o.dst_h;
+        r.rx = o.rect_x; r.ry = o.rect_y; r.rw = o.rect_w; r.rh = o.rect_h;
+        memcpy(r.color, o.color, 4);
+        r.dst = o.dst; r.dst_stride = o.dst_stride; r.dst_mem = o.dst_memspace;
+        if (o.kind == IPG_OP_WATERMARK) {
+            for (int g = 0; g < o.n_glyphs; g++) {
+                const ipg_glyph &G = o.glyphs[g];
+                GlyphRec gr;
+                gr.g = G;
+                if (G.x0 < G.x1 && G.y0 < G.y1) {
+                    gr.mask.resize((size_t)G.mask_w * (size_t)G.mask_h);
+                    for (int y = 0; y < G.mask_h; y++)
+                        memcpy(gr.mask.data() + (size_t)y * G.mask_w, G.mask + (size_t)y * G.mask_stride, (size_t)G.mask_w);
+                }
+                gr.g.mask = nullptr;
+                r.glyphs.push_back(std::move(gr));
+            }
+        }
+    }
+    // caller memory that is not ours is copied now (cgo: no retained pointers)
+    if (src->memspace == IPG_MEM_HOST) {
+        for (int p = 0; p < plane_count(src->layout); p++) {
+            int wb, ph;
+            plane_dims(src->layout, p, src->width, src->height, &wb, &ph);
+            size_t span = (size_t)src->stride[p] * (size_t)(ph - 1) + (size_t)wb;
+            if (c->pinned.contains(src->plane[p], span)) continue;
+            uint8_t *s = d.staging.alloc((size_t)wb * (size_t)ph, c->stop);
+            if (!s) {
+                for (int q = 0; q < p; q++) d.staging.release(t->src_stage[q]);
+                return fail(IPG_ERR_NOMEM, "image larger than the pinned staging pool (raise lane_pinned_bytes or decode into ipg_alloc_pinned memory)");
+            }
+            for (int y = 0; y < ph; y++)
+                memcpy(s + (size_t)y * wb, (const uint8_t *)src->plane[p] + (size_t)y * src->stride[p], (size_t)wb);
+            t->src_stage[p] = s;
+            c->s_staged++;
+        }
+    }
+    for (auto &r : t->ops) {
+        if (r.dst_mem != IPG_MEM_HOST || r.dw <= 0 || r.dh <= 0) continue;
+        size_t span = (size_t)r.dst_stride * (size_t)(r.dh - 1) + (size_t)r.dw * 4;
+        if (c->pinned.contains(r.dst, span)) continue;
+        r.stage = d.staging.alloc((size_t)r.dw * 4 * (size_t)r.dh, c->stop);
+        if (!r.stage) {
+            for (auto &q : t->ops) { d.staging.release(q.stage); q.stage = nullptr; }
+            for (int p = 0; p < 3; p++) d.staging.release(t->src_stage[p]);
+            return fail(IPG_ERR_NOMEM, "output larger than the pinned staging pool");
+        }
+    }
+    t->dev_bytes = ticket_device_bytes(*t);
+    t->cost = (size_t)src->width * (size_t)src->height * 4 + 65536;
+    if (t->dev_bytes + d.lanes[0].param_cap + (64u << 20) > d.lanes[0].arena_bytes) {
+        for (auto &q : t->ops) { d.staging.release(q.stage); q.stage = nullptr; }
+        for (int p = 0; p < 3; p++) d.staging.release(t->src_stage[p]);
+        return fail(IPG_ERR_NOMEM, "image does not fit a lane's device arena (raise lane_device_bytes)");
+    }
+    t->id = c->next_id.fetch_add(1);
+    {
+        std::lock_guard<std::mutex> lk(c->tmu);
+        c->tickets[t->id] = t;
+    }
+    d.outstanding.fetch_add(t->cost);
+    {
+        std::lock_guard<std::mutex> lk(d.mu);
+        d.queue.push_back(t);
+    }
+    d.cv_q.notify_all();
+    *out = t->id;
+    return IPG_OK;
+}
+
+static int wait_impl(Ctx *c, ipg_ticket id, int timeout_ms)
+{
+    if (!c) return fail(IPG_ERR_INVALID, "null context");
+    TicketP t;
+    {
+        std::lock_guard<std::mutex> lk(c->tmu);
+        auto it = c->tickets.find(id);
+        if (it == c->tickets.end()) return fail(IPG_ERR_INVALID, "unknown or already consumed ticket");
+        t = it->second;
+    }
+    {
+        std::unique_lock<std::mutex> lk(t->mu);
+        if (timeout_ms < 0) {
+            t->cv.wait(lk, [&] { return t->done; });
+        } else if (!t->cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return t->done; })) {
+            return fail(IPG_ERR_TIMEOUT, "timed out waiting for ticket");
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(c->tmu);
+        if (c->tickets.erase(id) == 0) return fail(IPG_ERR_INVALID, "ticket consumed by another waiter");
+    }
+    Device &d = *c->devs[t->dev];
+    for (auto &r : t->ops) {
+        if (!r.stage) continue;
+        if (t->status == IPG_OK) {
+            for (int y = 0; y < r.dh; y++)
+                memcpy((uint8_t *)r.dst + (size_t)y * r.dst_stride, r.stage + (size_t)y * r.dw * 4, (size_t)r.dw * 4);
+            c->s_staged++;
+        }
+        d.staging.release(r.stage);
+        r.stage = nullptr;
+    }
+    if (t->status != IPG_OK) return fail(t->status, t->err);
+    return IPG_OK;
+}
+
+static void destroy_impl(Ctx *c)
+{
+    if (!c) return;
+    c->stop.store(true);
+    for (auto &dp : c->devs) {
+        Device &d = *dp;
+        d.cv_q.notify_all();
+        d.cv_lane.notify_all();
+        d.cv_idle.notify_all();
+        if (d.batcher.joinable()) d.batcher.join();
+        // let the completer retire what is in flight
+        for (;;) {
+            {
+                std::lock_guard<std::mutex> lk(d.mu);
+                if (d.inflight.empty()) break;
+            }
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        }
+        d.cv_idle.notify_all();
+        if (d.completer.joinable()) d.completer.join();
+        // anything still queued never ran
+        for (auto &t : d.queue) finish_ticket(*c, d, t, IPG_ERR_SHUTDOWN, "context destroyed");
+        d.queue.clear();
+        cudaSetDevice(d.cuda_id);
+        for (auto &L : d.lanes) {
+            if (L.st) cudaStreamSynchronize(L.st);
+            for (auto &e : L.ev) if (e) cudaEventDestroy(e);
+            if (L.done) cudaEventDestroy(L.done);
+            if (L.arena) cudaFree(L.arena);
+            if (L.param_host) cudaFreeHost(L.param_host);
+            if (L.fix_count_host) cudaFreeHost(L.fix_count_host);
+            if (L.st) cudaStreamDestroy(L.st);
+        }
+        d.staging.destroy();
+    }
+    for (void *p : c->pinned.drain()) cudaFreeHost(p);
+    delete static_cast<ipg_ctx *>(c);
+}
+
+} // namespace ipg
+
+// =================================================================================
+// C ABI
+// =================================================================================
+using namespace ipg;
+
+extern "C" {
+
+int ipg_abi_version(void) { return IPG_ABI_VERSION; }
+const char *ipg_last_error(void) { return g_err.c_str(); }
+
+int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
+{
+    if (!out) return fail(IPG_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(IPG_ERR_NO_DEVICE, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                           (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    }
+    ipg_ctx *c = nullptr;
+    try {
+        c = new ipg_ctx;
+        ipg_config k{};
+        if (cfg) memcpy(&k, cfg, std::min<size_t>(sizeof k, cfg->struct_size ? cfg->struct_size : sizeof k));
+        if (k.precision < IPG_PRECISION_EXACT || k.precision > IPG_PRECISION_REFERENCE) k.precision = IPG_PRECISION_EXACT;
+        if (k.lanes_per_device <= 0) k.lanes_per_device = 3;
+        if (k.lanes_per_device > 16) k.lanes_per_device = 16;
+        if (k.max_batch <= 0) k.max_batch = 16;
+        if (!cfg || k.batch_window_us < 0) k.batch_window_us = 200;
+        if (k.lane_device_bytes == 0) k.lane_device_bytes = 1ull << 30;
+        if (k.lane_pinned_bytes == 0) k.lane_pinned_bytes = 256ull << 20;
+        c->cfg = k;
+        std::vector<int> ids;
+        if (device_ids && n > 0) ids.assign(device_ids, device_ids + n);
+        else for (int i = 0; i < count; i++) ids.push_back(i);
+        for (size_t i = 0; i < ids.size(); i++) {
+            if (ids[i] < 0 || ids[i] >= count) throw std::runtime_error("device id out of range");
+            cudaDeviceProp prop;
+            IPG_CU(cudaGetDeviceProperties(&prop, ids[i]));
+            if (prop.major < 10)
+                throw std::runtime_error(std::string("device ") + prop.name + " is not sm_100-class; this library is built for sm_100a only");
+            std::unique_ptr<Device> d(new Device);
+            d->ctx = c;
+            d->index = (int)i;
+            d->cuda_id = ids[i];
+            IPG_CU(cudaSetDevice(ids[i]));
+            d->lanes.resize((size_t)k.lanes_per_device);
+            const size_t param_cap = 32u << 20;
+            if (k.lane_device_bytes < param_cap + (128u << 20)) throw std::runtime_error("lane_device_bytes too small (< 160 MiB)");
+            for (auto &L : d->lanes) {
+                IPG_CU(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+                for (auto &ev : L.ev) IPG_CU(cudaEventCreate(&ev));
+                IPG_CU(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+                L.arena_bytes = (size_t)k.lane_device_bytes;
+                IPG_CU(cudaMalloc((void **)&L.arena, L.arena_bytes));
+                L.param_cap = param_cap;
+                IPG_CU(cudaHostAlloc((void **)&L.param_host, L.param_cap, cudaHostAllocPortable));
+                IPG_CU(cudaHostAlloc((void **)&L.fix_count_host, 64, cudaHostAllocPortable));
+            }
+            if (!d->staging.init((size_t)k.lane_pinned_bytes * (size_t)k.lanes_per_device))
+                throw std::runtime_error("pinned staging allocation failed");
+            c->devs.push_back(std::move(d));
+        }
+        for (auto &d : c->devs) {
+            d->batcher = std::thread(batcher_main, c, d.get());
+            d->completer = std::thread(completer_main, c, d.get());
+        }
+    } catch (const std::exception &ex) {
+        std::string m = ex.what();
+        if (c) destroy_impl(c);
+        cudaGetLastError();
+        return fail(IPG_ERR_CUDA, m);
+    }
+    *out = c;
+    return IPG_OK;
+}
+
+void ipg_destroy(ipg_ctx *ctx) { destroy_impl(ctx); }
+
+int ipg_device_count(const ipg_ctx *ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+void *ipg_alloc_pinned(ipg_ctx *ctx, size_t bytes)
+{
+    if (!ctx || bytes == 0) { fail(IPG_ERR_INVALID, "null context or zero size"); return nullptr; }
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); fail(IPG_ERR_NOMEM, cuda_msg("cudaHostAlloc", e)); return nullptr; }
+    ctx->pinned.add(p, bytes);
+    return p;
+}
+
+void ipg_free_pinned(ipg_ctx *ctx, void *p)
+{
+    if (!ctx || !p) return;
+    if (ctx->pinned.remove(p)) cudaFreeHost(p);
+}
+
+void *ipg_alloc_device(ipg_ctx *ctx, int device_index, size_t bytes)
+{
+    if (!ctx || device_index < 0 || device_index >= (int)ctx->devs.size() || bytes == 0) {
+        fail(IPG_ERR_INVALID, "bad context/device/size");
+        return nullptr;
+    }
+    cudaSetDevice(ctx->devs[device_index]->cuda_id);
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); fail(IPG_ERR_NOMEM, cuda_msg("cudaMalloc", e)); return nullptr; }
+    return p;
+}
+
+void ipg_free_device(ipg_ctx *ctx, int device_index, void *p)
+{
+    if (!ctx || !p || device_index < 0 || device_index >= (int)ctx->devs.size()) return;
+    cudaSetDevice(ctx->devs[device_index]->cuda_id);
+    cudaFree(p);
+}
+
+int ipg_copy_to_device(ipg_ctx *ctx, int device_index, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx || device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(IPG_ERR_INVALID, "bad context/device");
+    cudaSetDevice(ctx->devs[device_index]->cuda_id);
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(IPG_ERR_CUDA, cuda_msg("cudaMemcpy H2D", e)); }
+    return IPG_OK;
+}
+
+int ipg_copy_from_device(ipg_ctx *ctx, int device_index, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx || device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(IPG_ERR_INVALID, "bad context/device");
+    cudaSetDevice(ctx->devs[device_index]->cuda_id);
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(IPG_ERR_CUDA, cuda_msg("cudaMemcpy D2H", e)); }
+    return IPG_OK;
+}
+
+int ipg_submit(ipg_ctx *ctx, const ipg_image_desc *src, const ipg_op *ops, int n_ops, ipg_ticket *ticket)
+{
+    try {
+        return submit_impl(ctx, -1, src, ops, n_ops, ticket);
+    } catch (const std::exception &e) {
+        return fail(IPG_ERR_INTERNAL, e.what());
+    }
+}
+
+int ipg_submit_on(ipg_ctx *ctx, int device_index, const ipg_image_desc *src, const ipg_op *ops, int n_ops,
+                  ipg_ticket *ticket)
+{
+    if (device_index < 0) return fail(IPG_ERR_INVALID, "device index out of range");
+    try {
+        return submit_impl(ctx, device_index, src, ops, n_ops, ticket);
+    } catch (const std::exception &e) {
+        return fail(IPG_ERR_INTERNAL, e.what());
+    }
+}
+
+int ipg_wait(ipg_ctx *ctx, ipg_ticket ticket, int timeout_ms)
+{
+    try {
+        return wait_impl(ctx, ticket, timeout_ms);
+    } catch (const std::exception &e) {
+        return fail(IPG_ERR_INTERNAL, e.what());
+    }
+}
+
+int ipg_flush(ipg_ctx *ctx)
+{
+    if (!ctx) return fail(IPG_ERR_INVALID, "null context");
+    for (auto &dp : ctx->devs) {
+        Device &d = *dp;
+        std::unique_lock<std::mutex> lk(d.mu);
+        d.cv_lane.wait(lk, [&] {
+            if (!d.queue.empty() || !d.inflight.empty()) return false;
+            for (auto &L : d.lanes)
+                if (L.busy) return false;
+            return true;
+        });
+    }
+    return IPG_OK;
+}
+
+int ipg_get_stats(ipg_ctx *ctx, ipg_stats *out)
+{
+    if (!ctx || !out) return fail(IPG_ERR_INVALID, "null argument");
+    memset(out, 0, sizeof *out);
+    out->tickets_done = ctx->s_done.load();
+    out->batches = ctx->s_batches.load();
+    out->kernels_launched = ctx->s_kernels.load();
+    out->bytes_h2d = ctx->s_h2d.load();
+    out->bytes_d2h = ctx->s_d2h.load();
+    out->exact_fixups = ctx->s_fix.load();
+    out->exact_fallbacks = ctx->s_fallback.load();
+    out->staged_copies = ctx->s_staged.load();
+    std::lock_guard<std::mutex> lk(ctx->smu);
+    out->stream_kernel_ms = ctx->s_stream_ms;
+    out->fix_kernel_ms = ctx->s_fix_ms;
+    out->other_kernel_ms = ctx->s_other_ms;
+    out->kernel_ms = ctx->s_stream_ms + ctx->s_fix_ms + ctx->s_other_ms;
+    return IPG_OK;
+}
+
+/* internal/usecase/processor/operations/resize.go:63-72 */
+void ipg_keep_aspect_dims(int ow, int oh, int w, int h, int *nw, int *nh)
+{
+    const double wr = (double)w / (double)ow;
+    const double hr = (double)h / (double)oh;
+    const double ratio = wr < hr ? wr : hr; // math.Min (no NaNs here)
+    *nw = (int)((double)ow * ratio);
+    *nh = (int)((double)oh * ratio);
+}
+
+/* operations/thumbnail.go:52-63 */
+void ipg_thumb_fit_dims(int ow, int oh, int size, int *nw, int *nh)
+{
+    if (ow > oh) {
+        *nh = size;
+        *nw = (int)((double)ow * (double)size / (double)oh);
+    } else {
+        *nw = size;
+        *nh = (int)((double)oh * (double)size / (double)ow);
+    }
+}
+
+/* operations/thumbnail.go:115-127 */
+void ipg_crop_square(int ow, int oh, int *cx, int *cy, int *cs)
+{
+    if (ow > oh) {
+        *cs = oh; *cx = (ow - oh) / 2; *cy = 0;
+    } else {
+        *cs = ow; *cx = 0; *cy = (oh - ow) / 2;
+    }
+}
+
+} // extern "C"

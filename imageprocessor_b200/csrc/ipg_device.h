@@ -1,0 +1,115 @@
+// ipg_device.h -- structs shared by the host engine and the sm_100a kernels.
+// Everything here is plain-old-data living in the per-batch parameter blob that
+// the engine uploads once per launch sequence; pointers are device pointers.
+#pragma once
+#include <stdint.h>
+
+namespace ipg {
+
+enum Layout : int32_t {
+    L_RGBA8 = 0, L_NRGBA8 = 1, L_GRAY8 = 2,
+    L_YCBCR444 = 3, L_YCBCR422 = 4, L_YCBCR420 = 5, L_YCBCR440 = 6,
+};
+
+struct SrcView {
+    const uint8_t *p0, *p1, *p2; // device planes
+    int32_t s0, s1, s2;          // strides (bytes)
+    int32_t w, h;
+    int32_t layout;
+};
+
+// One axis of x/image's distrib in reference (float64) form, CSR by output index.
+struct AxisExact {
+    const int32_t *off;     // [n+1] tap offsets
+    const int32_t *first;   // [n]   first source coord (relative to the source rect)
+    const double *inv;      // [n]   invTotalWeight
+    const double *inv_ffff; // [n]   invTotalWeight / 0xffff
+    const double *w;        // [off[n]] unnormalised tent weights
+};
+
+// A resample evaluated in fp64, reference operation order (whole image or the
+// pixels a stream kernel flagged as ambiguous).
+struct ExactJob {
+    SrcView src;
+    int32_t rect_x, rect_y;   // source rectangle origin
+    int32_t two_stage;        // cropAndResize: samples are the 8-bit cropped RGBA
+    int32_t dw, dh;
+    int32_t dst_stride;
+    uint8_t *dst;
+    AxisExact ax, ay;
+};
+
+struct ExactItem { int32_t job; int32_t tile_x, tile_y; int32_t pad; };
+
+// Output pixel flagged by a stream kernel for fp64 re-evaluation.
+struct FixEntry { int32_t job; int32_t x, y; };
+struct FixList {
+    FixEntry *entries;
+    uint32_t *count;     // device counter (entries appended, may exceed capacity)
+    uint32_t capacity;
+};
+
+// Streaming (vertical-first, fp32) resample plan ---------------------------------
+// One record per source row a band walks: row contributes w_a to the lowest
+// still-open output row and w_b to the next one; emit>=0: the lowest open row is
+// complete after this source row and is output row `emit`.
+struct RowRec { float wa, wb; int32_t emit; int32_t pad; };
+
+struct StreamTarget {
+    uint8_t *dst;
+    int32_t dst_stride;
+    int32_t dw, dh;
+    int32_t rect_x, rect_y;      // source rect origin (crop)
+    int32_t two_stage;           // samples clamped to alpha (8-bit crop stage) first
+    int32_t exact_job;           // ExactJob index used for fix-ups
+    int32_t fix_d;               // ambiguity half-width, 1/256 of a 16-bit step
+    const int32_t *xoff;         // [dw+1]
+    const int32_t *xfirst;       // [dw]   relative to rect_x
+    const float *xw;             // normalised fp32 weights (sum 1)
+    const int32_t *tile_ox;      // [n_tiles+1] output columns owned by each column tile
+    const RowRec *rows;          // per-band records, concatenated
+    const int32_t *band_rec_off; // [n_bands] first record of each band
+    const int32_t *band_tend;    // [n_bands] one past the last source row that contributes
+};
+
+struct GlyphD {
+    int32_t x0, y0, x1, y1;
+    int32_t mp_x, mp_y, mask_stride, pad;
+    const uint8_t *mask; // device
+};
+
+struct WatermarkD {
+    uint8_t *dst;
+    int32_t dst_stride;
+    int32_t n_glyphs;
+    const GlyphD *glyphs;
+    int32_t bx0, by0, bx1, by1;  // union of glyph rects
+    uint32_t sr, sg, sb, sa;     // Uniform.RGBA(): c * 0x101
+};
+
+enum { STREAM_THREADS = 128, STREAM_PX = 4, STREAM_COLS = STREAM_THREADS * STREAM_PX };
+
+struct StreamJob {
+    SrcView src;
+    int32_t n_targets;
+    int32_t has_wm;
+    int32_t tile_w;            // source columns owned per tile (multiple of 4)
+    int32_t n_tiles, n_bands;
+    int32_t check_premul;      // RGBA8 source, alpha unknown, a two_stage target exists
+    const int32_t *band_y;     // [n_bands+1] owned source rows of each band
+    const int32_t *band_yend;  // [n_bands]   one past the last row the band must read
+    StreamTarget t[2];
+    WatermarkD wm;
+};
+
+struct StreamItem { int32_t job; int16_t tile, band; };
+
+// Standalone convert/copy + watermark blend (any layout) -------------------------
+struct WmJob {
+    SrcView src;
+    WatermarkD wm;
+};
+struct WmItem { int32_t job; int32_t row0; };  // WM_ROWS rows per item
+enum { WM_ROWS = 8 };
+
+} // namespace ipg

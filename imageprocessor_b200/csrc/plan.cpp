@@ -1,0 +1,257 @@
+// plan.cpp -- see plan.h.  Compiled with -ffp-contract=off: the tables must equal
+// what Go/amd64 computes for golang.org/x/image v0.33.0 draw/scale.go newDistrib.
+#include "plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace ipg {
+
+static std::shared_ptr<const AxisPlan> build_axis(int32_t dn, int32_t sn)
+{
+    auto p = std::make_shared<AxisPlan>();
+    p->dn = dn;
+    p->sn = sn;
+    p->off.assign((size_t)dn + 1, 0);
+    p->first.assign((size_t)dn, 0);
+    p->inv.assign((size_t)dn, 0.0);
+    p->inv_ffff.assign((size_t)dn, 0.0);
+
+    // BiLinear: Support = 1, At(t) = 1 - t.  When shrinking, the support is
+    // widened by the scale and the kernel argument shrunk by it.
+    const double scale = (double)sn / (double)dn;
+    double half_width = 1.0, arg_scale = 1.0;
+    if (scale > 1) {
+        half_width *= scale;
+        arg_scale = 1 / scale;
+    }
+    for (int32_t x = 0; x < dn; x++) {
+        const double center = ((double)x + 0.5) * scale - 0.5;
+        int32_t i = (int32_t)std::floor(center - half_width);
+        if (i < 0) i = 0;
+        int32_t j = (int32_t)std::ceil(center + half_width);
+        if (j > sn) {
+            j = sn;
+            if (j < i) j = i;
+        }
+        double total = 0.0;
+        int32_t kept_first = -1, kept_last = -1, kept = 0;
+        for (int32_t coord = i; coord < j; coord++) {
+            const double t = std::fabs((center - (double)coord) * arg_scale);
+            if (t >= 1.0) continue;
+            const double wt = 1 - t;
+            if (wt == 0) continue;
+            total += wt;
+            p->w.push_back(wt);
+            if (kept_first < 0) kept_first = coord;
+            kept_last = coord;
+            kept++;
+        }
+        if (kept > 0 && kept_last - kept_first + 1 != kept) p->contiguous = false;
+        p->first[x] = kept_first < 0 ? 0 : kept_first;
+        p->off[(size_t)x + 1] = (int32_t)p->w.size();
+        total = 1 / total;
+        p->inv[x] = total;
+        p->inv_ffff[x] = total / 0xffff;
+        p->max_taps = std::max(p->max_taps, kept);
+    }
+    return p;
+}
+
+std::shared_ptr<const AxisPlan> get_axis_plan(int dn, int sn)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, std::shared_ptr<const AxisPlan>> cache;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find({dn, sn});
+        if (it != cache.end()) return it->second;
+    }
+    auto p = build_axis(dn, sn);
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[{dn, sn}] = p;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------
+
+static bool build_target(StreamGeom &g, int ti, const StreamTargetSpec &s, double sample_scale)
+{
+    StreamTargetGeom &t = g.t[ti];
+    t.ax = get_axis_plan(s.dw, s.rect_w);
+    t.ay = get_axis_plan(s.dh, s.rect_h);
+    const AxisPlan &ax = *t.ax, &ay = *t.ay;
+    if (!ax.contiguous || !ay.contiguous) return false;
+
+    // horizontal: normalised fp32 weights
+    t.xw.resize(ax.w.size());
+    for (int32_t ox = 0; ox < s.dw; ox++)
+        for (int32_t k = ax.off[ox]; k < ax.off[ox + 1]; k++) t.xw[k] = (float)(ax.w[k] * ax.inv[ox]);
+
+    // the streaming vertical pass keeps two output rows open: first/last source
+    // rows of consecutive outputs must both be strictly increasing and row a+2
+    // must start after row a ended.
+    auto last = [&](int32_t oy) { return ay.first[oy] + (ay.off[oy + 1] - ay.off[oy]) - 1; };
+    for (int32_t oy = 0; oy < s.dh; oy++) {
+        if (ay.off[oy + 1] == ay.off[oy]) return false;
+        if (oy + 1 < s.dh && (ay.first[oy + 1] < ay.first[oy] || last(oy + 1) <= last(oy))) return false;
+        if (oy + 2 < s.dh && ay.first[oy + 2] <= last(oy)) return false;
+    }
+
+    // column tiles: an output column belongs to the tile holding its first tap
+    t.tile_ox.assign((size_t)g.n_tiles + 1, s.dw);
+    {
+        int32_t ox = 0;
+        for (int32_t tile = 0; tile < g.n_tiles; tile++) {
+            t.tile_ox[tile] = ox;
+            const int32_t cx1 = (tile + 1) * g.tile_w;
+            while (ox < s.dw && ax.first[ox] + s.rect_x < cx1) {
+                const int32_t lastcol = ax.first[ox] + s.rect_x + (ax.off[ox + 1] - ax.off[ox]) - 1;
+                if (lastcol >= tile * g.tile_w + STREAM_COLS) return false; // halo too small
+                ox++;
+            }
+        }
+        t.tile_ox[g.n_tiles] = ox;
+        if (ox != s.dw) return false;
+    }
+
+    // row bands: an output row belongs to the band holding its first source row
+    t.band_rec_off.assign((size_t)g.n_bands, 0);
+    t.band_tend.assign((size_t)g.n_bands, 0);
+    int32_t oy = 0;
+    for (int32_t b = 0; b < g.n_bands; b++) {
+        const int32_t Y0 = g.band_y[b], Y1 = g.band_y[b + 1];
+        const int32_t oyA = oy;
+        while (oy < s.dh && ay.first[oy] + s.rect_y < Y1) oy++;
+        const int32_t oyB = oy;
+        t.band_rec_off[b] = (int32_t)t.rows.size();
+        int32_t tend = Y0;
+        if (oyB > oyA) tend = last(oyB - 1) + s.rect_y + 1;
+        t.band_tend[b] = tend;
+        int32_t a = oyA;
+        for (int32_t ys = Y0; ys < tend; ys++) {
+            const int32_t yr = ys - s.rect_y;
+            RowRec r{0.f, 0.f, -1, 0};
+            auto weight = [&](int32_t o) -> float {
+                if (o >= oyB || yr < ay.first[o] || yr > last(o)) return 0.f;
+                const int32_t k = ay.off[o] + (yr - ay.first[o]);
+                return (float)(ay.w[k] * ay.inv[o] * sample_scale);
+            };
+            r.wa = weight(a);
+            r.wb = weight(a + 1);
+            if (a + 2 < oyB && yr >= ay.first[a + 2]) return false;
+            if (a < oyB && last(a) == yr) {
+                r.emit = a;
+                a++;
+                if (a < oyB && last(a) == yr) return false;
+            }
+            t.rows.push_back(r);
+        }
+        if (a != oyB) return false;
+    }
+    if (oy != s.dh) return false;
+
+    // |fp32 - exact| <= (taps_x + taps_y + 3) units of 1/256 of a 16-bit step
+    // (DESIGN.md "certified fp32"); 25 % margin on top.
+    t.fix_d = (int32_t)std::ceil(1.25 * (double)(ax.max_taps + ay.max_taps + 4));
+    return true;
+}
+
+static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const StreamTargetSpec *targets, int n_targets,
+                                                      bool has_wm, int n_bands, double sample_scale)
+{
+    auto g = std::make_shared<StreamGeom>();
+    g->W = W;
+    g->H = H;
+    g->n_targets = n_targets;
+    g->has_wm = has_wm;
+
+    int max_taps_x = 1;
+    double max_scale_y = 1.0;
+    for (int i = 0; i < n_targets; i++) {
+        const StreamTargetSpec &s = targets[i];
+        if (s.dw <= 0 || s.dh <= 0 || s.rect_w <= 0 || s.rect_h <= 0) return nullptr;
+        if (s.rect_h < s.dh) return nullptr; // vertical upscale: many open rows -> k_exact
+        auto ax = get_axis_plan(s.dw, s.rect_w);
+        max_taps_x = std::max(max_taps_x, ax->max_taps);
+        max_scale_y = std::max(max_scale_y, (double)s.rect_h / (double)s.dh);
+    }
+    const int tile_w_max = ((STREAM_COLS - (max_taps_x - 1)) / STREAM_PX) * STREAM_PX;
+    if (tile_w_max < 64) return nullptr;
+    g->n_tiles = (W + tile_w_max - 1) / tile_w_max;
+    g->tile_w = (((W + g->n_tiles - 1) / g->n_tiles) + STREAM_PX - 1) / STREAM_PX * STREAM_PX;
+    if (g->tile_w > tile_w_max) g->tile_w = tile_w_max;
+    g->n_tiles = (W + g->tile_w - 1) / g->tile_w;
+
+    // bands: at least ~8 vertical supports tall so the re-read tail stays small
+    const int min_rows = std::max(32, (int)std::ceil(16.0 * max_scale_y));
+    n_bands = std::max(1, std::min(n_bands, H / min_rows));
+    if (n_bands < 1) n_bands = 1;
+    g->n_bands = n_bands;
+    g->band_y.resize((size_t)n_bands + 1);
+    for (int b = 0; b <= n_bands; b++) g->band_y[b] = (int32_t)((int64_t)H * b / n_bands);
+
+    for (int i = 0; i < n_targets; i++)
+        if (!build_target(*g, i, targets[i], sample_scale)) return nullptr;
+
+    g->band_yend.resize((size_t)n_bands);
+    for (int b = 0; b < n_bands; b++) {
+        int32_t e = has_wm ? g->band_y[b + 1] : g->band_y[b];
+        for (int i = 0; i < n_targets; i++) e = std::max(e, g->t[i].band_tend[b]);
+        if (e > H) return nullptr;
+        g->band_yend[b] = e;
+    }
+    for (int b = 0; b < n_bands; b++) {
+        for (int tile = 0; tile < g->n_tiles; tile++) {
+            bool work = has_wm;
+            for (int i = 0; i < n_targets && !work; i++)
+                work = g->t[i].band_tend[b] > g->band_y[b] && g->t[i].tile_ox[tile + 1] > g->t[i].tile_ox[tile];
+            if (work && g->band_yend[b] > g->band_y[b]) g->items.push_back(StreamItem{0, (int16_t)tile, (int16_t)b});
+        }
+    }
+    return g;
+}
+
+namespace {
+struct GeomKey {
+    int W, H, n_targets, has_wm, n_bands;
+    long long scale_bits;
+    StreamTargetSpec t[2];
+    bool operator<(const GeomKey &o) const
+    {
+        auto tup = [](const GeomKey &k) {
+            return std::make_tuple(k.W, k.H, k.n_targets, k.has_wm, k.n_bands, k.scale_bits, k.t[0].rect_x, k.t[0].rect_y,
+                                   k.t[0].rect_w, k.t[0].rect_h, k.t[0].dw, k.t[0].dh, k.t[1].rect_x, k.t[1].rect_y,
+                                   k.t[1].rect_w, k.t[1].rect_h, k.t[1].dw, k.t[1].dh);
+        };
+        return tup(*this) < tup(o);
+    }
+};
+} // namespace
+
+std::shared_ptr<const StreamGeom> get_stream_geom(int W, int H, const StreamTargetSpec *targets, int n_targets,
+                                                  bool has_wm, int n_bands_hint, double sample_scale)
+{
+    static std::mutex mu;
+    static std::map<GeomKey, std::shared_ptr<const StreamGeom>> cache; // value may be nullptr (infeasible)
+    GeomKey key{};
+    key.W = W; key.H = H; key.n_targets = n_targets; key.has_wm = has_wm; key.n_bands = n_bands_hint;
+    key.scale_bits = (long long)(sample_scale * 65536.0);
+    for (int i = 0; i < n_targets && i < 2; i++) key.t[i] = targets[i];
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) return it->second;
+    }
+    auto g = (n_targets <= 2) ? build_stream(W, H, targets, n_targets, has_wm, n_bands_hint, sample_scale) : nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 1024) cache.clear();
+    cache[key] = g;
+    return g;
+}
+
+} // namespace ipg

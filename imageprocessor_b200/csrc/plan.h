@@ -1,0 +1,67 @@
+// plan.h -- host-side planning: per-axis weight tables exactly as x/image's
+// newDistrib builds them (float64, same operation order), and the derived
+// streaming plan (column tiles, row bands, per-row records) for k_stream.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <vector>
+
+#include "ipg_device.h"
+
+namespace ipg {
+
+// x/image v0.33.0 draw/scale.go newDistrib for BiLinear (Support 1, At(t)=1-t),
+// CSR by output index.  Taps of one output are a contiguous run of source coords.
+struct AxisPlan {
+    int32_t dn = 0, sn = 0;
+    int32_t max_taps = 0;
+    std::vector<int32_t> off;    // [dn+1]
+    std::vector<int32_t> first;  // [dn]
+    std::vector<double> inv;     // [dn] 1/sum(w)
+    std::vector<double> inv_ffff;// [dn] inv/0xffff
+    std::vector<double> w;       // unnormalised weights
+    bool contiguous = true;      // taps of each output are consecutive coords
+};
+
+std::shared_ptr<const AxisPlan> get_axis_plan(int dn, int sn); // cached, thread-safe
+
+struct StreamTargetSpec {
+    int32_t rect_x, rect_y, rect_w, rect_h;
+    int32_t dw, dh;
+    bool operator==(const StreamTargetSpec &o) const
+    {
+        return rect_x == o.rect_x && rect_y == o.rect_y && rect_w == o.rect_w && rect_h == o.rect_h &&
+               dw == o.dw && dh == o.dh;
+    }
+};
+
+struct StreamTargetGeom {
+    std::shared_ptr<const AxisPlan> ax, ay;
+    std::vector<float> xw;            // normalised fp32 horizontal weights
+    std::vector<int32_t> tile_ox;     // [n_tiles+1]
+    std::vector<RowRec> rows;         // per-band records
+    std::vector<int32_t> band_rec_off;// [n_bands]
+    std::vector<int32_t> band_tend;   // [n_bands] one past last source row with a contribution
+    int32_t fix_d = 0;
+};
+
+// Everything k_stream needs that depends only on geometry (not on pointers).
+struct StreamGeom {
+    int32_t W = 0, H = 0;
+    int32_t n_targets = 0;
+    bool has_wm = false;
+    int32_t tile_w = 0, n_tiles = 0, n_bands = 0;
+    std::vector<int32_t> band_y;    // [n_bands+1]
+    std::vector<int32_t> band_yend; // [n_bands]
+    StreamTargetGeom t[2];
+    std::vector<StreamItem> items;  // (tile, band) pairs that have work; job index left 0
+};
+
+// Returns nullptr when the geometry cannot stream (upscale in y, more than two
+// output rows open at once, support wider than a slab, ...): caller uses k_exact.
+// `sample_scale` maps source samples to the 16-bit scale (257 for 8-bit RGBA).
+std::shared_ptr<const StreamGeom> get_stream_geom(int W, int H, const StreamTargetSpec *targets,
+                                                  int n_targets, bool has_wm, int n_bands_hint,
+                                                  double sample_scale);
+
+} // namespace ipg

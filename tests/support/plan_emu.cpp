@@ -1,0 +1,105 @@
+// plan_emu.cpp -- TEST-ONLY host mirror of k_stream's control flow.
+//
+// Links the product's host planner (imageprocessor_b200/csrc/plan.cpp) and walks
+// its tables exactly as the CUDA kernel does (same tile/band ownership, same fp32
+// fmaf order, same quantiser and ambiguity test), so the planner logic and the
+// "certified fp32" error bound can be checked on a CPU-only box.  Never shipped,
+// never linked into libipgpu.so; used by tests/test_plan_host.py only.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../imageprocessor_b200/csrc/plan.h"
+
+using namespace ipg;
+
+static inline int quant16(float v, int D, bool &amb)
+{
+    const int T = (int)std::floor(std::fmaf(v, 256.0f, 128.0f));
+    const int out = std::min(T >> 16, 255);
+    const int lo = std::min(std::max(T - D, 0) >> 16, 255);
+    const int hi = std::min((T + D) >> 16, 255);
+    amb |= (lo != hi);
+    return std::max(out, 0);
+}
+
+extern "C" int planemu_axis(int dn, int sn, int32_t *off, int32_t *first, double *w, double *inv, int *max_taps)
+{
+    auto p = get_axis_plan(dn, sn);
+    if (off) memcpy(off, p->off.data(), p->off.size() * 4);
+    if (first) memcpy(first, p->first.data(), p->first.size() * 4);
+    if (w) memcpy(w, p->w.data(), p->w.size() * 8);
+    if (inv) memcpy(inv, p->inv.data(), p->inv.size() * 8);
+    if (max_taps) *max_taps = p->max_taps;
+    return (int)p->w.size();
+}
+
+// specs: 6 ints per target {rect_x, rect_y, rect_w, rect_h, dw, dh}.
+// flags[t]: dw*dh bytes, 1 where the kernel would queue an fp64 fix-up.
+// info: {n_tiles, n_bands, tile_w, n_items, rows_read}
+extern "C" int planemu_run(const uint8_t *src, int stride, int W, int H, int n_targets, const int *specs,
+                           const int *two_stage, uint8_t **dsts, uint8_t **flags, int bands_hint, int *info)
+{
+    StreamTargetSpec sp[2];
+    for (int t = 0; t < n_targets; t++)
+        sp[t] = StreamTargetSpec{specs[6 * t], specs[6 * t + 1], specs[6 * t + 2], specs[6 * t + 3], specs[6 * t + 4], specs[6 * t + 5]};
+    auto g = get_stream_geom(W, H, sp, n_targets, false, bands_hint, 257.0);
+    if (!g) return -1;
+    long rows_read = 0;
+    for (const StreamItem &it : g->items) {
+        const int tile = it.tile, band = it.band;
+        const int cx0 = tile * g->tile_w;
+        const int ys0 = g->band_y[band], yend = g->band_yend[band];
+        std::vector<float> acc_a[2], acc_b[2];
+        int tend[2] = {ys0, ys0};
+        for (int t = 0; t < n_targets; t++) {
+            acc_a[t].assign((size_t)STREAM_COLS * 4, 0.f);
+            acc_b[t].assign((size_t)STREAM_COLS * 4, 0.f);
+            if (g->t[t].tile_ox[tile + 1] > g->t[t].tile_ox[tile]) tend[t] = g->t[t].band_tend[band];
+        }
+        for (int ys = ys0; ys < yend; ys++) {
+            rows_read++;
+            for (int t = 0; t < n_targets; t++) {
+                if (ys >= tend[t]) continue;
+                const StreamTargetGeom &tg = g->t[t];
+                const RowRec r = tg.rows[(size_t)tg.band_rec_off[band] + (size_t)(ys - ys0)];
+                for (int e = 0; e < STREAM_COLS; e++) {
+                    const int c = cx0 + e;
+                    uint8_t px[4] = {0, 0, 0, 0};
+                    if (c < W) memcpy(px, src + (size_t)ys * stride + (size_t)c * 4, 4);
+                    if (two_stage[t]) for (int k = 0; k < 3; k++) px[k] = std::min(px[k], px[3]);
+                    for (int k = 0; k < 4; k++) {
+                        float &a = acc_a[t][(size_t)e * 4 + k], &b = acc_b[t][(size_t)e * 4 + k];
+                        a = std::fmaf((float)px[k], r.wa, a);
+                        b = std::fmaf((float)px[k], r.wb, b);
+                    }
+                }
+                if (r.emit >= 0) {
+                    std::vector<float> row = acc_a[t];
+                    acc_a[t] = acc_b[t];
+                    std::fill(acc_b[t].begin(), acc_b[t].end(), 0.f);
+                    const int oy = r.emit;
+                    for (int ox = tg.tile_ox[tile]; ox < tg.tile_ox[tile + 1]; ox++) {
+                        const int k0 = tg.ax->off[ox], n = tg.ax->off[ox + 1] - k0;
+                        const int e0 = tg.ax->first[ox] + sp[t].rect_x - cx0;
+                        if (e0 < 0 || e0 + n > STREAM_COLS) return -2;
+                        float s[4] = {0, 0, 0, 0};
+                        for (int k = 0; k < n; k++)
+                            for (int ch = 0; ch < 4; ch++) s[ch] = std::fmaf(row[(size_t)(e0 + k) * 4 + ch], tg.xw[k0 + k], s[ch]);
+                        for (int ch = 0; ch < 3; ch++) s[ch] = std::fmin(s[ch], s[3]);
+                        bool amb = false;
+                        uint8_t *d = dsts[t] + ((size_t)oy * sp[t].dw + ox) * 4;
+                        for (int ch = 0; ch < 4; ch++) d[ch] = (uint8_t)quant16(s[ch], tg.fix_d, amb);
+                        if (flags && flags[t]) flags[t][(size_t)oy * sp[t].dw + ox] += amb ? 1 : 16; // 16: written once
+                    }
+                }
+            }
+        }
+    }
+    if (info) {
+        info[0] = g->n_tiles; info[1] = g->n_bands; info[2] = g->tile_w;
+        info[3] = (int)g->items.size(); info[4] = (int)std::min<long>(rows_read, 2147483647L);
+    }
+    return 0;
+}

@@ -1,0 +1,104 @@
+"""CPU tests of the product's host planner (imageprocessor_b200/csrc/plan.cpp).
+
+tests/support/plan_emu.cpp walks the planner's tables exactly as k_stream does
+(same ownership rules, fp32 fmaf order, quantiser, ambiguity window).  Checked here:
+  * the axis tables equal the oracle's newDistrib restatement bit for bit;
+  * every output pixel is produced exactly once (tile/band ownership is a partition);
+  * "certified fp32": every byte NOT flagged for the fp64 fix-up already equals the
+    fp64 oracle, flagged bytes are within 1, and few pixels are flagged.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.util import rgba_random
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SUP = os.path.join(HERE, "support")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-C", SUP, "-s", "libplan_emu.so"])
+    L = C.CDLL(os.path.join(SUP, "libplan_emu.so"))
+    L.planemu_axis.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5
+    L.planemu_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    return L
+
+
+def run_emu(L, a, specs, two_stage, bands_hint=4):
+    h, w = a.shape[:2]
+    n = len(specs)
+    sp = np.array(specs, np.int32).reshape(-1)
+    ts = np.array(two_stage, np.int32)
+    dsts = [np.zeros((s[5], s[4], 4), np.uint8) for s in specs]
+    flags = [np.zeros((s[5], s[4]), np.uint8) for s in specs]
+    dp = (C.c_void_p * n)(*[d.ctypes.data for d in dsts])
+    fp = (C.c_void_p * n)(*[f.ctypes.data for f in flags])
+    info = np.zeros(5, np.int32)
+    rc = L.planemu_run(a.ctypes.data, a.strides[0], w, h, n, sp.ctypes.data, ts.ctypes.data, dp, fp,
+                       bands_hint, info.ctypes.data)
+    return rc, dsts, flags, info
+
+
+@pytest.mark.parametrize("dn,sn", [(1024, 4000), (768, 3000), (200, 3000), (1023, 1002), (767, 147), (7, 7), (1, 5000), (300, 301)])
+def test_axis_tables_equal_oracle(emu, oracle, dn, sn):
+    st, co, w, inv = oracle.distrib(dn, sn)
+    off = np.zeros(dn + 1, np.int32); first = np.zeros(dn, np.int32)
+    ww = np.zeros(len(w), np.float64); iv = np.zeros(dn, np.float64); mt = C.c_int()
+    n = emu.planemu_axis(dn, sn, off.ctypes.data, first.ctypes.data, ww.ctypes.data, iv.ctypes.data, C.byref(mt))
+    assert n == len(w)
+    assert np.array_equal(off, st)
+    assert np.array_equal(first, co[st[:-1]])
+    assert np.array_equal(ww.view(np.uint64), w.view(np.uint64))          # bit-identical doubles
+    assert np.array_equal(iv.view(np.uint64), inv.view(np.uint64))
+    assert mt.value == int(np.diff(st).max())
+    assert abs((w[st[0]:st[1]] * inv[0]).sum() - 1) < 1e-12
+
+
+@pytest.mark.parametrize("w,h,rw,rh,size,bands", [
+    (400, 300, 102, 76, 20, 1), (1000, 750, 256, 192, 50, 4), (1203, 899, 300, 224, 64, 7),
+    (2000, 1500, 1024, 768, 200, 3), (600, 800, 1024, 768, 200, 2), (1601, 1201, 640, 480, 100, 5),
+])
+@pytest.mark.parametrize("alpha", ["opaque", "raw"])
+def test_stream_plan_certified_fp32(emu, oracle, w, h, rw, rh, size, bands, alpha):
+    a = rgba_random(w, h, w * 31 + h, alpha)
+    nw, nh = oracle.keep_aspect_dims(w, h, rw, rh)
+    cx, cy, cs = oracle.crop_square(w, h)
+    specs = [(0, 0, w, h, nw, nh), (cx, cy, cs, cs, size, size)]
+    rc, dsts, flags, info = run_emu(emu, a, specs, [0, 1], bands)
+    if nh > h:   # vertical upscale cannot stream; the engine falls back to k_exact
+        assert rc == -1
+        return
+    assert rc == 0
+    R = oracle.Raster.rgba(a)
+    refs = [oracle.resize_image(R, nw, nh), oracle.crop_and_resize(R, size)]
+    for d, f, ref in zip(dsts, flags, refs):
+        assert np.all((f == 16) | (f == 1)), "each output pixel written exactly once"
+        amb = f == 1
+        diff = np.abs(d.astype(int) - ref.astype(int)).max(axis=2)
+        assert diff[~amb].max(initial=0) == 0, "an unflagged byte differs from the fp64 oracle"
+        assert diff.max(initial=0) <= 1
+        assert amb.mean() < 0.03
+
+
+def test_stream_plan_rejects_what_it_cannot_do(emu):
+    a = rgba_random(64, 48, 1)
+    rc, *_ = run_emu(emu, a, [(0, 0, 64, 48, 200, 150)], [0])     # upscale
+    assert rc == -1
+    a = rgba_random(40000, 4, 2)
+    rc, *_ = run_emu(emu, a, [(0, 0, 40000, 4, 40, 1)], [0])      # 1000-tap rows: wider than a slab
+    assert rc == -1
+
+
+def test_single_target_and_identity(emu, oracle):
+    a = rgba_random(500, 333, 9, "raw")
+    rc, dsts, flags, info = run_emu(emu, a, [(0, 0, 500, 333, 500, 333)], [0], 3)   # 1:1
+    assert rc == 0
+    ref = oracle.resize_image(oracle.Raster.rgba(a), 500, 333)
+    amb = flags[0] == 1
+    assert np.array_equal(dsts[0][~amb], ref[~amb])
