@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec for resize(1024x768 keep-aspect) + thumbnail(200 crop) +
+watermark on a batch of 12 MP RGBA images (BASELINE.json metric / configs[1..2]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+  python bench.py --impl reference [...]                        # restated reference CPU path
+  torchrun ... bench.py --gpus N ...                            # one rank per GPU, images shard by rank
+
+One step = one pass of the hot path over the whole batch (256 images per GPU).
+`value`  : device-resident inputs/outputs, device clock from the first kernel start to
+           the last kernel end of the K timed steps (CUDA events on the launching streams).
+`e2e`    : the same K steps through the C ABI with pinned HOST buffers: H2D of every
+           source and D2H of every result inside the timed region.
+`roofline`: k_stream's algorithmic bytes per launch / its mean launch duration, against
+           the measured HBM copy peak (MEASURED_PEAKS.json).
+`cpu_baseline`: oracle/ (C restatement of the reference algorithm) on the host cores.
+Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W_IMG, H_IMG = 4000, 3000
+RW, RH, THUMB = 1024, 768, 200
+WM_TEXT, WM_OPACITY, WM_COLOR = "© ImageProcessor", 0.5, "255,255,255"
+METRIC = "images/sec resize+thumb+watermark, 12MP batch"
+# algorithmic bytes per 12 MP RGBA image, source read once
+BYTES_PER_IMAGE = W_IMG * H_IMG * 4 + RW * RH * 4 + THUMB * THUMB * 4 + W_IMG * H_IMG * 4
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per k_stream launch from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 8:
+                    continue
+                try:
+                    sm.append(float(p[0])); mx.append(float(p[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, p[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------------
+def make_host_image(seed):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 256, (H_IMG, W_IMG, 4), dtype=np.uint8)
+    a[..., 3] = 255
+    return a
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path: Go cannot be built here, so
+    this is oracle/ (C restatement, float64 scalar, fresh temp buffers, one image per
+    thread) on all host cores, on a bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from imageprocessor_b200 import glyphs as G
+    O.build()
+    cores = os.cpu_count() or 1
+    n = env_int("IPG_BENCH_REF_IMAGES", cores)
+    imgs = [make_host_image(1000 + i) for i in range(min(n, 4))]
+    rasters = [O.Raster.rgba(imgs[i % len(imgs)]) for i in range(n)]
+    gl = [O.Glyph(g.x0, g.y0, g.x1, g.y1, g.mask, g.mp_x, g.mp_y)
+          for g in G.layout_watermark(W_IMG, H_IMG, WM_TEXT)]
+    col, _ = G.parse_color(WM_COLOR, WM_OPACITY)
+    for _ in range(min(args.warmup, 1)):
+        O.bench_batch(rasters[:cores], cores, 7, RW, RH, True, THUMB, col, gl)
+    secs = 0.0
+    for _ in range(args.steps):
+        s, _ = O.bench_batch(rasters, cores, 7, RW, RH, True, THUMB, col, gl)
+        secs += s
+    value = n * args.steps / secs
+    sample = f"{n} images per step (one per host thread), {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, n),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "restated reference CPU path (C), not the Go build"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, images_per_gpu):
+    return {
+        "workload": "BASELINE configs[2]: batch of 12MP (4000x3000) synthetic RGBA images, "
+                    "resize 1024x768 keep-aspect + thumbnail 200 crop + watermark '(c) ImageProcessor'",
+        "images_per_gpu_per_step": images_per_gpu, "image": f"{W_IMG}x{H_IMG} RGBA8", "ops": "resize+thumb+watermark",
+        "sharding": f"by image, {n_gpus} rank(s), no collective",
+        "l2_policy": "inputs larger than L2 (each step streams >= 12 GB of distinct sources per GPU)",
+        "precision": "EXACT (fp32 stream + fp64 fix-up: byte-identical to the fp64 reference algorithm)",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=env_int("IPG_BENCH_IMAGES", 256), help="images per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = env_int("RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import imageprocessor_b200 as ip
+    from imageprocessor_b200 import _lib as L
+    from imageprocessor_b200 import glyphs as G
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n_img = args.images
+    lib = L.load()
+    eng = ip.Engine(devices=[local_rank], precision=ip.PRECISION_EXACT, lanes_per_device=3,
+                    max_batch=env_int("IPG_BENCH_MAX_BATCH", 32), batch_window_us=100)
+    ctx = eng._ctx
+
+    # ---- synthetic sources, resident in HBM (seeded per image; A=255)
+    gen = torch.Generator(device=dev)
+    srcs = []
+    for i in range(n_img):
+        gen.manual_seed(1000 + rank * n_img + i)
+        t = torch.randint(0, 256, (H_IMG, W_IMG, 4), dtype=torch.uint8, device=dev, generator=gen)
+        t[..., 3] = 255
+        srcs.append(t)
+    nw, nh = ip.keep_aspect_dims(W_IMG, H_IMG, RW, RH)
+    cx, cy, cs = ip.crop_square(W_IMG, H_IMG)
+    out_r = torch.empty((n_img, nh, nw, 4), dtype=torch.uint8, device=dev)
+    out_t = torch.empty((n_img, THUMB, THUMB, 4), dtype=torch.uint8, device=dev)
+    out_w = torch.empty((n_img, H_IMG, W_IMG, 4), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    glyph_list = G.layout_watermark(W_IMG, H_IMG, WM_TEXT, "bottom-right", 36.0)
+    color, _ = G.parse_color(WM_COLOR, WM_OPACITY)
+    garr = (L.Glyph * len(glyph_list))()
+    gkeep = []
+    for j, g in enumerate(glyph_list):
+        m = np.ascontiguousarray(g.mask, np.uint8)
+        gkeep.append(m)
+        garr[j].x0, garr[j].y0, garr[j].x1, garr[j].y1 = g.x0, g.y0, g.x1, g.y1
+        garr[j].mp_x, garr[j].mp_y = g.mp_x, g.mp_y
+        garr[j].mask_w, garr[j].mask_h, garr[j].mask_stride = m.shape[1], m.shape[0], m.strides[0]
+        garr[j].mask = m.ctypes.data
+
+    def make_ops(dst_r, dst_t, dst_w, memspace):
+        ops = (L.Op * 3)()
+        ops[0].kind, ops[0].dst_w, ops[0].dst_h = L.OP_RESIZE, nw, nh
+        ops[0].dst, ops[0].dst_stride, ops[0].dst_memspace = dst_r, nw * 4, memspace
+        ops[1].kind, ops[1].dst_w, ops[1].dst_h = L.OP_THUMB_CROP, THUMB, THUMB
+        ops[1].rect_x, ops[1].rect_y, ops[1].rect_w, ops[1].rect_h = cx, cy, cs, cs
+        ops[1].dst, ops[1].dst_stride, ops[1].dst_memspace = dst_t, THUMB * 4, memspace
+        ops[2].kind, ops[2].dst_w, ops[2].dst_h = L.OP_WATERMARK, W_IMG, H_IMG
+        for k in range(4):
+            ops[2].color[k] = color[k]
+        ops[2].n_glyphs, ops[2].glyphs = len(glyph_list), garr
+        ops[2].dst, ops[2].dst_stride, ops[2].dst_memspace = dst_w, W_IMG * 4, memspace
+        return ops
+
+    def make_desc(ptr, memspace):
+        d = L.ImageDesc()
+        d.layout, d.memspace, d.width, d.height = L.RGBA8, memspace, W_IMG, H_IMG
+        d.plane[0] = ptr
+        d.stride[0] = W_IMG * 4
+        d.opaque_hint = 0   # *image.RGBA: alpha unknown to the caller, as in the reference
+        return d
+
+    dev_descs = [make_desc(srcs[i].data_ptr(), L.MEM_DEVICE) for i in range(n_img)]
+    dev_ops = [make_ops(out_r[i].data_ptr(), out_t[i].data_ptr(), out_w[i].data_ptr(), L.MEM_DEVICE) for i in range(n_img)]
+    tids = (C.c_uint64 * n_img)()
+    tid_ref = [C.cast(C.byref(tids, 8 * i), C.POINTER(C.c_uint64)) for i in range(n_img)]
+    submit_on, wait = lib.ipg_submit_on, lib.ipg_wait
+
+    def step_device():
+        for i in range(n_img):
+            rc = submit_on(ctx, 0, C.byref(dev_descs[i]), dev_ops[i], 3, tid_ref[i])
+            if rc:
+                L.check(rc)
+        for i in range(n_img):
+            rc = wait(ctx, tids[i], -1)
+            if rc:
+                L.check(rc)
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    eng.reset_stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_device()
+    eng.flush()
+    barrier()
+    wall_dev = time.perf_counter() - t0
+    clocks = sampler.stop()
+    st = eng.stats()
+    span_s = max_over_ranks(st["kernel_span_ms"] / 1e3)
+    total_images = sum_over_ranks(float(n_img * args.steps))
+    value = total_images / span_s
+    launches = int(sum_over_ranks(float(st["kernels_launched"])))
+    stream_launches = st["batches"]
+    stream_ms_per_launch = st["stream_kernel_ms"] / max(stream_launches, 1)
+    imgs_per_launch = n_img * args.steps / max(stream_launches, 1)
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_IMAGE * imgs_per_launch / (stream_ms_per_launch * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    roofline = {
+        "bound": "hbm", "kernel": "k_stream<2,wm,check>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "peak_source": peak_src,
+        "frac_of_nominal_8TBs": achieved / 8000.0,
+        "algorithmic_bytes_per_image": BYTES_PER_IMAGE, "images_per_launch": imgs_per_launch,
+        "ms_per_launch": stream_ms_per_launch,
+        "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+        "traffic_note": traffic.get("note") if traffic else "no ncu --set full capture committed yet",
+        "kernel_share_of_step": st["stream_kernel_ms"] / max(st["kernel_ms"], 1e-9),
+        "fix_kernel_ms_per_step": st["fix_kernel_ms"] / args.steps,
+        "exact_fixups_per_image": st["exact_fixups"] / max(n_img * args.steps, 1),
+    }
+
+    # ---- verification of the timed outputs against the oracle (rank 0, one image)
+    verified = None
+    if rank == 0 and not args.no_verify:
+        from oracle import oracle as O
+        a = srcs[0].cpu().numpy()
+        R = O.Raster.rgba(a)
+        ok_r = np.array_equal(out_r[0].cpu().numpy(), O.resize_image(R, nw, nh))
+        ok_t = np.array_equal(out_t[0].cpu().numpy(), O.crop_and_resize(R, THUMB))
+        ogl = [O.Glyph(g.x0, g.y0, g.x1, g.y1, g.mask, g.mp_x, g.mp_y) for g in glyph_list]
+        ok_w = np.array_equal(out_w[0].cpu().numpy(), O.watermark(R, color, ogl))
+        verified = {"resize_bit_exact": bool(ok_r), "thumb_bit_exact": bool(ok_t), "watermark_bit_exact": bool(ok_w)}
+
+    # ---- end to end through the C ABI with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        n_slots = min(env_int("IPG_BENCH_HOST_SLOTS", 24), n_img)
+        src_bytes = W_IMG * H_IMG * 4
+        pins = []
+        h_descs, h_ops = [], []
+        for s in range(n_slots):
+            p_in = eng.alloc_pinned(src_bytes)
+            p_in.array[:] = srcs[s].cpu().numpy().reshape(-1)
+            p_r, p_t, p_w = eng.alloc_pinned(nw * nh * 4), eng.alloc_pinned(THUMB * THUMB * 4), eng.alloc_pinned(src_bytes)
+            pins += [p_in, p_r, p_t, p_w]
+            h_descs.append(make_desc(p_in.ptr, L.MEM_HOST))
+            h_ops.append(make_ops(p_r.ptr, p_t.ptr, p_w.ptr, L.MEM_HOST))
+        submit = lib.ipg_submit_on
+
+        def step_host():
+            for i in range(n_img):
+                s = i % n_slots
+                if i >= n_slots:          # bounded in flight: slot s is free once its previous ticket is done
+                    rc = wait(ctx, tids[i - n_slots], -1)
+                    if rc:
+                        L.check(rc)
+                rc = submit(ctx, 0, C.byref(h_descs[s]), h_ops[s], 3, tid_ref[i])
+                if rc:
+                    L.check(rc)
+            for i in range(max(n_img - n_slots, 0), n_img):
+                rc = wait(ctx, tids[i], -1)
+                if rc:
+                    L.check(rc)
+
+        del out_w
+        torch.cuda.empty_cache()
+        for _ in range(max(1, min(args.warmup, 3))):
+            step_host()
+        barrier()
+        eng.reset_stats()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        eng.flush()
+        barrier()
+        wall = max_over_ranks(time.perf_counter() - t0)
+        st2 = eng.stats()
+        e2e = {
+            "value": total_images / wall, "unit": "images/s",
+            "h2d_bytes_per_step": int(st2["bytes_h2d"] / args.steps), "d2h_bytes_per_step": int(st2["bytes_d2h"] / args.steps),
+            "timing": "host wall clock around K steps (barrier + flush both sides), max over ranks",
+            "device_span_s": st2["batch_span_ms"] / 1e3,
+            "h2d_GBps": st2["bytes_h2d"] / wall / 1e9, "d2h_GBps": st2["bytes_d2h"] / wall / 1e9,
+            "host_buffers": f"{n_slots} pinned slots per rank (ipg_alloc_pinned), zero staging copies: {st2['staged_copies'] == 0}",
+            "verified_slot0": None,
+        }
+        if rank == 0 and not args.no_verify:
+            from oracle import oracle as O
+            a = pins[0].array.reshape(H_IMG, W_IMG, 4)
+            e2e["verified_slot0"] = bool(np.array_equal(pins[1].array.reshape(nh, nw, 4),
+                                                        O.resize_image(O.Raster.rgba(a), nw, nh)))
+        for p in pins:
+            p.free()
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        n_s = env_int("IPG_BENCH_CPU_IMAGES", cores)
+        host_imgs = [srcs[i % n_img].cpu().numpy() for i in range(min(n_s, 4))]
+        rasters = [O.Raster.rgba(host_imgs[i % len(host_imgs)]) for i in range(n_s)]
+        ogl = [O.Glyph(g.x0, g.y0, g.x1, g.y1, g.mask, g.mp_x, g.mp_y) for g in glyph_list]
+        secs, _ = O.bench_batch(rasters, cores, 7, RW, RH, True, THUMB, color, ogl)
+        cpu = {"value": n_s / secs, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"{n_s} images of the same workload, one per host thread, one pass ({secs:.1f} s)",
+               "note": "restated reference CPU path (C, float64 scalar), not the Go build"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * span_s / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world, n_img),
+            "timing": "CUDA events on the launching streams: first kernel start -> last kernel end, max over ranks",
+            "wall_ms_per_step": 1e3 * wall_dev / args.steps,
+            "hbm_GBps": value * BYTES_PER_IMAGE / 1e9 / world,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": e2e, "verified": verified,
+            "host": {"nproc": os.cpu_count()},
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

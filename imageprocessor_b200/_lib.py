@@ -60,7 +60,8 @@ class Stats(C.Structure):
                 ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64), ("exact_fixups", C.c_uint64),
                 ("exact_fallbacks", C.c_uint64), ("staged_copies", C.c_uint64),
                 ("kernel_ms", C.c_double), ("stream_kernel_ms", C.c_double),
-                ("fix_kernel_ms", C.c_double), ("other_kernel_ms", C.c_double)]
+                ("fix_kernel_ms", C.c_double), ("other_kernel_ms", C.c_double),
+                ("kernel_span_ms", C.c_double), ("batch_span_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -71,7 +72,7 @@ EXPORTS = [
     "ipg_init", "ipg_destroy", "ipg_device_count", "ipg_last_error", "ipg_abi_version",
     "ipg_alloc_pinned", "ipg_free_pinned", "ipg_alloc_device", "ipg_free_device",
     "ipg_copy_to_device", "ipg_copy_from_device", "ipg_submit", "ipg_submit_on", "ipg_wait",
-    "ipg_flush", "ipg_get_stats", "ipg_keep_aspect_dims", "ipg_thumb_fit_dims", "ipg_crop_square",
+    "ipg_flush", "ipg_get_stats", "ipg_reset_stats", "ipg_keep_aspect_dims", "ipg_thumb_fit_dims", "ipg_crop_square",
 ]
 
 _lib = None
@@ -110,6 +111,7 @@ def load():
     L.ipg_wait.argtypes = [vp, C.c_uint64, C.c_int]
     L.ipg_flush.argtypes = [vp]
     L.ipg_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.ipg_reset_stats.argtypes = [vp]
     L.ipg_keep_aspect_dims.argtypes = [C.c_int] * 4 + [ip, ip]
     L.ipg_keep_aspect_dims.restype = None
     L.ipg_thumb_fit_dims.argtypes = [C.c_int] * 3 + [ip, ip]

@@ -230,7 +230,8 @@ struct Batch {
 struct Lane {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t done = nullptr;
+    cudaEvent_t begin = nullptr; // before the batch's first H2D
+    cudaEvent_t done = nullptr;  // after its last D2H
     uint8_t *arena = nullptr;
     size_t arena_bytes = 0;
     uint8_t *param_host = nullptr; // pinned
@@ -252,6 +253,9 @@ struct Device {
     std::atomic<uint64_t> outstanding{0};
     std::thread batcher, completer;
     StagingPool staging;
+    // device-time spans since the last ipg_reset_stats, in ms after `epoch`
+    cudaEvent_t epoch = nullptr;
+    double k_first = 1e300, k_last = -1, b_first = 1e300, b_last = -1;
 };
 
 struct Ctx {
@@ -360,6 +364,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
 {
     IPG_CU(cudaSetDevice(d.cuda_id));
     cudaStream_t st = L.st;
+    IPG_CU(cudaEventRecord(L.begin, st));
     Arena arena{L.arena, L.arena_bytes};
     uint8_t *blob_dev = arena.take(L.param_cap, 256);
     if (!blob_dev) throw std::runtime_error("device arena smaller than the parameter blob");
@@ -372,10 +377,12 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     std::vector<ExactItem> xitems;
     std::vector<WmJob> wjobs;
     std::vector<WmItem> witems;
+    std::vector<WatermarkD> blends;   // every watermark of the batch that has glyphs
+    std::vector<BlendItem> bitems;
     struct Readback { uint8_t *dev; size_t pitch; void *host; size_t hstride; size_t row_bytes; int rows; };
     std::vector<Readback> readbacks;
     int max_nt = 0;
-    bool any_wm = false, any_check = false;
+    bool any_wm = false, all_tma = true;
     uint64_t fix_px = 0;
     const int precision = c.cfg.precision;
 
@@ -458,6 +465,12 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
             size_t o = blob.put(gd.data(), gd.size() * sizeof(GlyphD), 16);
             w.glyphs = blob.dptr<const GlyphD>(o);
             w.bx0 = bx0; w.by0 = by0; w.bx1 = bx1; w.by1 = by1;
+            if (w.n_glyphs > 0) {
+                const int bi = (int)blends.size();
+                blends.push_back(w);
+                for (int ty = 0; ty < (by1 - by0 + 7) / 8; ty++)
+                    for (int tx = 0; tx < (bx1 - bx0 + 31) / 32; tx++) bitems.push_back(BlendItem{bi, tx, ty});
+            }
             return w;
         };
 
@@ -545,6 +558,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                     o.rows = blob.put_vec(tgm.rows);
                     o.band_rec_off = blob.put_vec(tgm.band_rec_off);
                     o.band_tend = blob.put_vec(tgm.band_tend);
+                    o.band_oy = blob.put_vec(tgm.band_oy);
                     o.exact_job = -1;
                     if (precision == IPG_PRECISION_EXACT) {
                         o.exact_job = add_exact(*tg[k], fixjobs);
@@ -555,7 +569,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 if (wm) j.wm = make_wm(*wm);
                 max_nt = std::max(max_nt, nt);
                 any_wm |= wm != nullptr;
-                any_check |= j.check_premul != 0;
+                all_tma &= (((size_t)sv.p0 | (size_t)sv.s0) & 15) == 0; // rows bulk-copyable
                 const int ji = (int)sjobs.size();
                 sjobs.push_back(j);
                 for (auto it : geom->items) {
@@ -601,6 +615,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     const ExactItem *d_xitems = blob.dptr<const ExactItem>(blob.put(xitems.data(), xitems.size() * sizeof(ExactItem), 16));
     const WmJob *d_wjobs = blob.dptr<const WmJob>(blob.put(wjobs.data(), wjobs.size() * sizeof(WmJob), 16));
     const WmItem *d_witems = blob.dptr<const WmItem>(blob.put(witems.data(), witems.size() * sizeof(WmItem), 16));
+    const WatermarkD *d_blends = blob.dptr<const WatermarkD>(blob.put(blends.data(), blends.size() * sizeof(WatermarkD), 16));
+    const BlendItem *d_bitems = blob.dptr<const BlendItem>(blob.put(bitems.data(), bitems.size() * sizeof(BlendItem), 16));
     if (blob.overflow) throw std::runtime_error("parameter blob overflow (batch too heterogeneous); lower max_batch");
     IPG_CU(cudaMemcpyAsync(blob_dev, L.param_host, blob.off, cudaMemcpyHostToDevice, st));
     B.h2d += blob.off;
@@ -608,7 +624,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     // ---- kernels
     IPG_CU(cudaEventRecord(L.ev[0], st));
     if (!sitems.empty()) {
-        IPG_CU(launch_stream(d_sjobs, d_sitems, (int)sitems.size(), max_nt, any_wm, any_check, fix, st));
+        IPG_CU(launch_stream(d_sjobs, d_sitems, (int)sitems.size(), max_nt, any_wm, all_tma, fix, st));
         B.n_kernels++;
     }
     IPG_CU(cudaEventRecord(L.ev[1], st));
@@ -623,6 +639,10 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     }
     if (!witems.empty()) {
         IPG_CU(launch_watermark(d_wjobs, d_witems, (int)witems.size(), st));
+        B.n_kernels++;
+    }
+    if (!bitems.empty()) {
+        IPG_CU(launch_blend(d_blends, d_bitems, (int)bitems.size(), st));
         B.n_kernels++;
     }
     IPG_CU(cudaEventRecord(L.ev[3], st));
@@ -738,10 +758,21 @@ static void completer_main(Ctx *c, Device *d)
                 cudaEventElapsedTime(&a, L.ev[0], L.ev[1]);
                 cudaEventElapsedTime(&b, L.ev[1], L.ev[2]);
                 cudaEventElapsedTime(&o, L.ev[2], L.ev[3]);
+                float t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+                cudaEventElapsedTime(&t0, d->epoch, L.begin);
+                cudaEventElapsedTime(&t1, d->epoch, L.ev[0]);
+                cudaEventElapsedTime(&t2, d->epoch, L.ev[3]);
+                cudaEventElapsedTime(&t3, d->epoch, L.done);
                 std::lock_guard<std::mutex> lk(c->smu);
                 c->s_stream_ms += a;
                 c->s_fix_ms += b;
                 c->s_other_ms += o;
+                if (B->n_kernels > 0) {
+                    d->k_first = std::min(d->k_first, (double)t1);
+                    d->k_last = std::max(d->k_last, (double)t2);
+                }
+                d->b_first = std::min(d->b_first, (double)t0);
+                d->b_last = std::max(d->b_last, (double)t3);
             }
             if (B->has_fix && status == IPG_OK) c->s_fix += *L.fix_count_host;
             c->s_batches++;
@@ -971,12 +1002,14 @@ static void destroy_impl(Ctx *c)
         for (auto &L : d.lanes) {
             if (L.st) cudaStreamSynchronize(L.st);
             for (auto &e : L.ev) if (e) cudaEventDestroy(e);
+            if (L.begin) cudaEventDestroy(L.begin);
             if (L.done) cudaEventDestroy(L.done);
             if (L.arena) cudaFree(L.arena);
             if (L.param_host) cudaFreeHost(L.param_host);
             if (L.fix_count_host) cudaFreeHost(L.fix_count_host);
             if (L.st) cudaStreamDestroy(L.st);
         }
+        if (d.epoch) cudaEventDestroy(d.epoch);
         d.staging.destroy();
     }
     for (void *p : c->pinned.drain()) cudaFreeHost(p);
@@ -1039,7 +1072,8 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
             for (auto &L : d->lanes) {
                 IPG_CU(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
                 for (auto &ev : L.ev) IPG_CU(cudaEventCreate(&ev));
-                IPG_CU(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+                IPG_CU(cudaEventCreate(&L.begin));
+                IPG_CU(cudaEventCreate(&L.done));
                 L.arena_bytes = (size_t)k.lane_device_bytes;
                 IPG_CU(cudaMalloc((void **)&L.arena, L.arena_bytes));
                 L.param_cap = param_cap;
@@ -1048,6 +1082,9 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
             }
             if (!d->staging.init((size_t)k.lane_pinned_bytes * (size_t)k.lanes_per_device))
                 throw std::runtime_error("pinned staging allocation failed");
+            IPG_CU(cudaEventCreate(&d->epoch));
+            IPG_CU(cudaEventRecord(d->epoch, d->lanes[0].st));
+            IPG_CU(cudaEventSynchronize(d->epoch));
             c->devs.push_back(std::move(d));
         }
         for (auto &d : c->devs) {
@@ -1184,6 +1221,29 @@ int ipg_get_stats(ipg_ctx *ctx, ipg_stats *out)
     out->fix_kernel_ms = ctx->s_fix_ms;
     out->other_kernel_ms = ctx->s_other_ms;
     out->kernel_ms = ctx->s_stream_ms + ctx->s_fix_ms + ctx->s_other_ms;
+    for (auto &d : ctx->devs) {
+        if (d->k_last >= 0) out->kernel_span_ms = std::max(out->kernel_span_ms, d->k_last - d->k_first);
+        if (d->b_last >= 0) out->batch_span_ms = std::max(out->batch_span_ms, d->b_last - d->b_first);
+    }
+    return IPG_OK;
+}
+
+int ipg_reset_stats(ipg_ctx *ctx)
+{
+    if (!ctx) return fail(IPG_ERR_INVALID, "null context");
+    int rc = ipg_flush(ctx);
+    if (rc) return rc;
+    ctx->s_done = 0; ctx->s_batches = 0; ctx->s_kernels = 0; ctx->s_h2d = 0; ctx->s_d2h = 0;
+    ctx->s_fix = 0; ctx->s_fallback = 0; ctx->s_staged = 0;
+    std::lock_guard<std::mutex> lk(ctx->smu);
+    ctx->s_stream_ms = ctx->s_fix_ms = ctx->s_other_ms = 0;
+    for (auto &d : ctx->devs) {
+        cudaSetDevice(d->cuda_id);
+        cudaEventRecord(d->epoch, d->lanes[0].st);
+        cudaEventSynchronize(d->epoch);
+        d->k_first = d->b_first = 1e300;
+        d->k_last = d->b_last = -1;
+    }
     return IPG_OK;
 }
 

@@ -70,6 +70,7 @@ struct StreamTarget {
     const RowRec *rows;          // per-band records, concatenated
     const int32_t *band_rec_off; // [n_bands] first record of each band
     const int32_t *band_tend;    // [n_bands] one past the last source row that contributes
+    const int32_t *band_oy;      // [n_bands+1] first output row owned by each band
 };
 
 struct GlyphD {
@@ -87,7 +88,17 @@ struct WatermarkD {
     uint32_t sr, sg, sb, sa;     // Uniform.RGBA(): c * 0x101
 };
 
-enum { STREAM_THREADS = 128, STREAM_PX = 4, STREAM_COLS = STREAM_THREADS * STREAM_PX };
+// k_stream CTA: 4 vertical-pass warps (128 threads x 4 px = one 512-column slab), 1 TMA
+// producer warp, 2 horizontal-pass warps.
+enum {
+    STREAM_THREADS = 128, STREAM_PX = 4, STREAM_COLS = STREAM_THREADS * STREAM_PX,
+    STREAM_GROUP = 4,           // source rows per ring stage / TMA barrier phase (8 KB)
+    STREAM_STAGES = 5,          // source ring depth in stages
+    STREAM_XSLOTS = 3,          // vertically-filtered rows awaiting the horizontal pass (8 KB each)
+    STREAM_XTHREADS = 64,
+    STREAM_XREG = 3,            // outputs per X thread whose tap tables live in registers
+    STREAM_CTA = STREAM_THREADS + 32 + STREAM_XTHREADS,
+};
 
 struct StreamJob {
     SrcView src;
@@ -110,6 +121,7 @@ struct WmJob {
     WatermarkD wm;
 };
 struct WmItem { int32_t job; int32_t row0; };  // WM_ROWS rows per item
+struct BlendItem { int32_t wm; int32_t tile_x, tile_y; }; // 32x8 px of a watermark's glyph box
 enum { WM_ROWS = 8 };
 
 } // namespace ipg

@@ -145,20 +145,72 @@ k_exact_tiles(const ExactJob *__restrict__ jobs, const ExactItem *__restrict__ i
     *(uchar4 *)(J.dst + (size_t)oy * J.dst_stride + (size_t)ox * 4) = o;
 }
 
-__global__ void __launch_bounds__(128)
+// Warp-cooperative variant for the fix-up list: lanes take the contributing source
+// rows round-robin and run their horizontal sums (each sum still sequential, unfused,
+// in tap order); lanes 0..3 then run the vertical sum of one channel each in row
+// order.  Same operations in the same order per value as exact_pixel, ~30x less
+// latency for the 29x29-tap thumbnail pixels.
+enum { FIX_THREADS = 128, FIX_MAX_ROWS = 96 };
+
+__device__ void exact_pixel_warp(const ExactJob &J, int ox, int oy, double (*tmp)[4])
+{
+    const int lane = threadIdx.x & 31;
+    const int kx0 = __ldg(J.ax.off + ox), nx = __ldg(J.ax.off + ox + 1) - kx0;
+    const int ky0 = __ldg(J.ay.off + oy), ny = __ldg(J.ay.off + oy + 1) - ky0;
+    if (ny > FIX_MAX_ROWS) { // cannot stage: one lane does it alone
+        if (lane == 0) *(uchar4 *)(J.dst + (size_t)oy * J.dst_stride + (size_t)ox * 4) = exact_pixel(J, ox, oy);
+        __syncwarp();
+        return;
+    }
+    const int x0 = __ldg(J.ax.first + ox) + J.rect_x;
+    const int y0 = __ldg(J.ay.first + oy) + J.rect_y;
+    const double ifx = __ldg(J.ax.inv_ffff + ox);
+    for (int j = lane; j < ny; j += 32) {
+        double xr = 0, xg = 0, xb = 0, xa = 0;
+        bool const_alpha = false;
+        for (int k = 0; k < nx; k++) {
+            uint32_t p[4];
+            const_alpha = sample16(J.src, x0 + k, y0 + j, p);
+            if (J.two_stage) { to_cropped_rgba16(p); const_alpha = false; }
+            const double w = __ldg(J.ax.w + kx0 + k);
+            xr = __dadd_rn(xr, __dmul_rn((double)p[0], w));
+            xg = __dadd_rn(xg, __dmul_rn((double)p[1], w));
+            xb = __dadd_rn(xb, __dmul_rn((double)p[2], w));
+            xa = __dadd_rn(xa, __dmul_rn((double)p[3], w));
+        }
+        tmp[j][0] = __dmul_rn(xr, ifx);
+        tmp[j][1] = __dmul_rn(xg, ifx);
+        tmp[j][2] = __dmul_rn(xb, ifx);
+        tmp[j][3] = const_alpha ? 1.0 : __dmul_rn(xa, ifx);
+    }
+    __syncwarp();
+    double p = 0;
+    if (lane < 4) {
+        for (int j = 0; j < ny; j++) p = __dadd_rn(p, __dmul_rn(tmp[j][lane], __ldg(J.ay.w + ky0 + j)));
+    }
+    const double pa = __shfl_sync(0xffffffffu, p, 3);
+    if (lane < 4) {
+        if (p > pa) p = pa;
+        const uint32_t q = ftou(__dmul_rn(p, __ldg(J.ay.inv + oy))) >> 8;
+        J.dst[(size_t)oy * J.dst_stride + (size_t)ox * 4 + lane] = (unsigned char)q;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(FIX_THREADS)
 k_exact_fix(const ExactJob *__restrict__ jobs, int n_jobs, FixList fix)
 {
+    __shared__ double tmp[FIX_THREADS / 32][FIX_MAX_ROWS][4];
     const uint32_t cnt = *fix.count;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     if (cnt <= fix.capacity) {
-        for (uint32_t i = tid; i < cnt; i += nthr) {
+        const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+        for (uint32_t i = wid; i < cnt; i += nw) {
             const FixEntry e = fix.entries[i];
-            const ExactJob &J = jobs[e.job];
-            const uchar4 o = exact_pixel(J, e.x, e.y);
-            *(uchar4 *)(J.dst + (size_t)e.y * J.dst_stride + (size_t)e.x * 4) = o;
+            exact_pixel_warp(jobs[e.job], e.x, e.y, tmp[threadIdx.x >> 5]);
         }
     } else {
         // the list overflowed: entries were dropped, so redo every stream target whole
+        const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
         for (int j = 0; j < n_jobs; j++) {
             const ExactJob &J = jobs[j];
             const uint32_t npx = (uint32_t)J.dw * (uint32_t)J.dh;
@@ -244,7 +296,7 @@ k_watermark(const WmJob *__restrict__ jobs, const WmItem *__restrict__ items)
             uint32_t o[4];
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                o[j] = (x + j < W) ? blend_if_inside(draw_src_px(J.src, x + j, y), x + j, y, J.wm) : 0u;
+                o[j] = (x + j < W) ? draw_src_px(J.src, x + j, y) : 0u;
             if (x + 4 <= W && ((J.wm.dst_stride | (int)(size_t)J.wm.dst) & 15) == 0) {
                 *(uint4 *)(drow + (size_t)x * 4) = make_uint4(o[0], o[1], o[2], o[3]);
             } else {
@@ -254,30 +306,120 @@ k_watermark(const WmJob *__restrict__ jobs, const WmItem *__restrict__ items)
     }
 }
 
+// Ordered glyph blend, in place on the watermark destination, over the union box of
+// the glyph rectangles only (~300x45 px): one thread per pixel walks the glyphs in string
+// order, exactly like freetype's one-DrawMask-per-rune sequence.  Runs after the kernel
+// that produced the full-frame copy/conversion, on the same stream.
+__global__ void __launch_bounds__(256)
+k_blend(const WatermarkD *__restrict__ wms, const BlendItem *__restrict__ items)
+{
+    const BlendItem it = items[blockIdx.x];
+    const WatermarkD &wm = wms[it.wm];
+    const int x = wm.bx0 + it.tile_x * 32 + (threadIdx.x & 31);
+    const int y = wm.by0 + it.tile_y * 8 + (threadIdx.x >> 5);
+    if (x >= wm.bx1 || y >= wm.by1) return;
+    uint32_t *p = (uint32_t *)(wm.dst + (size_t)y * wm.dst_stride) + x;
+    const uint32_t d = *p;
+    const uint32_t o = glyph_over_px(d, x, y, wm);
+    if (o != d) *p = o;
+}
+
 // ---------------------------------------------------------------------------------
 // k_stream: vertical-first fp32 streaming resample
 //
-// CTA = 128 threads x 4 source pixels = a 512-column slab; it owns `tile_w` of those
-// columns, the rest is the right halo the widest horizontal support needs.  The CTA
-// walks the source rows of its band once, top to bottom.  Per source row each thread
-// converts its 4 RGBA pixels to fp32 once and multiply-adds them into the (at most)
-// two output rows the row contributes to, per target: a tent of half-width `scale`
-// centred every `scale` rows covers each source row exactly twice.  When a source
-// row completes an output row (RowRec.emit), the CTA parks that vertically-filtered
-// row in shared memory (XOR-swizzled float4 slots: conflict-free stores, <=2-way
-// gathers), and threads 0..n_owned-1 run the horizontal gather, quantise with the
-// reference's ftou()>>8, flag bytes too close to a quantiser step for the fp64
-// fix-up, and store uchar4 (coalesced).
-// Source bytes are read from HBM exactly once for resize + thumbnail + watermark.
+// CTA = 4 consumer warps (128 threads x 4 source pixels = a 512-column slab) + 1
+// producer warp.  The CTA owns `tile_w` of the slab's columns; the rest is the right
+// halo the widest horizontal support needs.  It walks the source rows of its band
+// once, top to bottom:
+//
+//   producer   one elected thread streams the slab's rows HBM -> shared memory with
+//              TMA bulk copies (cp.async.bulk, 2 KB per row) into a ring of
+//              STREAM_STAGES rows, paced by full/empty mbarriers.  This is what keeps
+//              tens of KB per SM in flight; a register prefetch of one row left the
+//              kernel latency-bound at ~1 TB/s.
+//   consumers  wait for a row, LDS.128 their 4 pixels (conflict-free), release the
+//              stage, convert bytes to fp32 once (PRMT into 2^23+b, FADD: the I2F.U8
+//              the compiler would pick runs on the quarter-rate XU pipe) and
+//              multiply-add them into the (at most) two output rows the source row
+//              contributes to, per target: a tent of half-width `scale` centred every
+//              `scale` rows covers each source row exactly twice.  The watermark copy
+//              (with its glyph blend) leaves from the same registers.
+//   emit       when a source row completes an output row (RowRec.emit) the consumers
+//              park that vertically-filtered row in shared memory (XOR-swizzled float4
+//              slots: conflict-free stores, <=2-way gathers), meet at a 128-thread
+//              named barrier, and threads 0..n_owned-1 run the horizontal gather,
+//              quantise with the reference's ftou()>>8, flag bytes too close to a
+//              quantiser step for the fp64 fix-up, and store uchar4 (coalesced).
+//
+// Source bytes cross HBM exactly once for resize + thumbnail + watermark.
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ int swz(int e) { return e ^ ((e >> 3) & 7); }
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    // try_wait suspends the thread in hardware up to the hint (ns) and wakes on completion
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+}
+// Same, for roles that are not on the critical path (producer waiting for a free stage,
+// X warps waiting for a parked row): sleep between probes so the spin does not steal
+// issue slots from the V warps and the other CTAs' producers.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity)
+{
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        __nanosleep(128);
+    }
+}
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"r"((int)STREAM_THREADS) : "memory"); }
+
+// uint8 -> fp32 on the ALU + FMA pipes: 0x4B0000bb is 2^23 + b exactly.
+template <int K> __device__ __forceinline__ float byte_f32(uint32_t q)
+{
+    return __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7540 + K)) - 8388608.0f;
+}
 __device__ __forceinline__ void unpack_px(uint32_t q, float *v)
 {
-    v[0] = (float)(q & 0xff);
-    v[1] = (float)((q >> 8) & 0xff);
-    v[2] = (float)((q >> 16) & 0xff);
-    v[3] = (float)(q >> 24);
+    v[0] = byte_f32<0>(q);
+    v[1] = byte_f32<1>(q);
+    v[2] = byte_f32<2>(q);
+    v[3] = byte_f32<3>(q);
 }
 
 __device__ __forceinline__ uint32_t clamp_to_alpha(uint32_t q)
@@ -287,12 +429,10 @@ __device__ __forceinline__ uint32_t clamp_to_alpha(uint32_t q)
     return r | (g << 8) | (b << 16) | (a << 24);
 }
 
-__device__ __forceinline__ uint4 load_px4(const uint8_t *row, int c, int W, bool vec)
+__device__ __forceinline__ uint4 load_px4(const uint8_t *row, int c, int W)
 {
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (c + 4 <= W && vec) {
-        v = __ldcs((const uint4 *)(row + (size_t)c * 4)); // streaming: read once
-    } else if (c < W) {
+    if (c < W) {
         const uint32_t *p = (const uint32_t *)row + c;
         v.x = __ldg(p);
         if (c + 1 < W) v.y = __ldg(p + 1);
@@ -302,102 +442,262 @@ __device__ __forceinline__ uint4 load_px4(const uint8_t *row, int c, int W, bool
     return v;
 }
 
-__device__ __forceinline__ int quant16(float v, int D, bool &amb)
+__device__ __forceinline__ uint32_t quant16(float v, uint32_t D, uint32_t span, bool &amb)
 {
-    // t = v + 0.5 in 16.8 fixed point; out byte = floor(t) >> 8 = T >> 16.
-    const int T = __float2int_rd(fmaf(v, 256.0f, 128.0f));
-    const int out = min(T >> 16, 255);
-    const int lo = min(max(T - D, 0) >> 16, 255);
-    const int hi = min((T + D) >> 16, 255);
-    amb |= (lo != hi);
-    return max(out, 0);
+    // t = v + 0.5 in 16.8 fixed point (T < 2^24 because v <= 65535): the output byte is
+    // floor(t) >> 8 = T >> 16.  The byte is ambiguous when T lies within D of a multiple
+    // of 65536: (low16 - D) mod 2^32 >= 65536 - 2D  (span = 65536 - 2D).
+    const uint32_t T = (uint32_t)min(__float2int_rd(fmaf(v, 256.0f, 128.0f)), 0xffffff);
+    amb |= ((T & 0xffffu) - D) >= span;
+    return T >> 16;
 }
 
-__device__ __forceinline__ void xpass(const StreamTarget &t, int tile, int oy, int cx0,
-                                      const float4 *__restrict__ buf, const FixList &fix)
+struct __align__(128) StreamSmem {
+    uint4 ring[STREAM_STAGES][STREAM_GROUP][STREAM_THREADS]; // source rows, 2 KB each; a stage = STREAM_GROUP rows
+    float4 rowbuf[STREAM_XSLOTS][STREAM_COLS];   // vertically filtered rows, XOR-swizzled slots
+    uint64_t full[STREAM_STAGES], empty[STREAM_STAGES];
+    uint64_t xfull[STREAM_XSLOTS], xempty[STREAM_XSLOTS];
+    int32_t xmeta[STREAM_XSLOTS][2];             // {target, output row} of each parked row
+};
+
+// ---- X warps ---------------------------------------------------------------------
+// What an X thread needs of one target, copied out of the job so that its global
+// stores cannot force reloads.
+struct XTarget {
+    uint8_t *dst;
+    const float *xw;
+    const int32_t *xoff, *xfirst;
+    int dst_stride, ox0, n_own, ebase; // ebase = rect_x - cx0
+    int exact_job;
+    uint32_t D, span;
+    // first STREAM_XREG outputs of this thread, cached: first smem slot, weight offset, tap count
+    int e0[STREAM_XREG], k0[STREAM_XREG], n[STREAM_XREG];
+};
+
+__device__ __forceinline__ void xtarget_load(XTarget &x, const StreamTarget &t, int tile, int cx0, int xt)
 {
-    const int ox0 = __ldg(t.tile_ox + tile);
-    const int n_own = __ldg(t.tile_ox + tile + 1) - ox0;
-    for (int j = threadIdx.x; j < n_own; j += STREAM_THREADS) {
-        const int ox = ox0 + j;
-        const int k0 = __ldg(t.xoff + ox);
-        const int n = __ldg(t.xoff + ox + 1) - k0;
-        const int e0 = __ldg(t.xfirst + ox) + t.rect_x - cx0;
-        float r = 0.f, g = 0.f, b = 0.f, a = 0.f;
-        for (int k = 0; k < n; k++) {
-            const float w = __ldg(t.xw + k0 + k);
-            const float4 q = buf[swz(e0 + k)];
-            r = fmaf(q.x, w, r); g = fmaf(q.y, w, g);
-            b = fmaf(q.z, w, b); a = fmaf(q.w, w, a);
-        }
-        r = fminf(r, a); g = fminf(g, a); b = fminf(b, a);
-        bool amb = false;
-        uchar4 o;
-        o.x = (unsigned char)quant16(r, t.fix_d, amb);
-        o.y = (unsigned char)quant16(g, t.fix_d, amb);
-        o.z = (unsigned char)quant16(b, t.fix_d, amb);
-        o.w = (unsigned char)quant16(a, t.fix_d, amb);
-        *(uchar4 *)(t.dst + (size_t)oy * t.dst_stride + (size_t)ox * 4) = o;
-        if (amb && fix.capacity) {
-            const uint32_t idx = atomicAdd(fix.count, 1u);
-            if (idx < fix.capacity) fix.entries[idx] = FixEntry{t.exact_job, ox, oy};
+    x.dst = t.dst; x.dst_stride = t.dst_stride;
+    x.xw = t.xw; x.xoff = t.xoff; x.xfirst = t.xfirst;
+    x.ox0 = __ldg(t.tile_ox + tile);
+    x.n_own = __ldg(t.tile_ox + tile + 1) - x.ox0;
+    x.ebase = t.rect_x - cx0;
+    x.exact_job = t.exact_job;
+    x.D = (uint32_t)t.fix_d;
+    x.span = 65536u - 2u * x.D;
+#pragma unroll
+    for (int i = 0; i < STREAM_XREG; i++) {
+        const int j = xt + i * STREAM_XTHREADS;
+        x.e0[i] = x.k0[i] = x.n[i] = 0;
+        if (j < x.n_own) {
+            const int ox = x.ox0 + j;
+            x.k0[i] = __ldg(t.xoff + ox);
+            x.n[i] = __ldg(t.xoff + ox + 1) - x.k0[i];
+            x.e0[i] = __ldg(t.xfirst + ox) + x.ebase;
         }
     }
 }
 
-template <int NT, bool WM, bool CHECK>
-__global__ void __launch_bounds__(STREAM_THREADS, (NT == 2 ? 3 : 4))
-k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ items, FixList fix)
+// One output pixel of the horizontal pass; FFMA2 carries (r,g) and (b,a) as packed pairs.
+__device__ __forceinline__ void xpixel(const XTarget &x, int ox, int oy, int e0, int k0, int n,
+                                       const float4 *__restrict__ buf, const FixList &fix)
 {
-    __shared__ float4 rowbuf[2][STREAM_COLS];
+    const float *__restrict__ wp = x.xw + k0;
+    float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
+#pragma unroll 4
+    for (int k = 0; k < n; k++) {
+        const float w = __ldg(wp + k);
+        const float4 q = buf[swz(e0 + k)];
+        const float2 ww = make_float2(w, w);
+        rg = __ffma2_rn(make_float2(q.x, q.y), ww, rg);
+        ba = __ffma2_rn(make_float2(q.z, q.w), ww, ba);
+    }
+    const float a = ba.y;
+    const float r = fminf(rg.x, a), g = fminf(rg.y, a), b = fminf(ba.x, a);
+    bool amb = false;
+    const uint32_t o = quant16(r, x.D, x.span, amb) | (quant16(g, x.D, x.span, amb) << 8) |
+                       (quant16(b, x.D, x.span, amb) << 16) | (quant16(a, x.D, x.span, amb) << 24);
+    *(uint32_t *)(x.dst + (size_t)oy * x.dst_stride + (size_t)ox * 4) = o;
+    if (amb && fix.capacity) {
+        const uint32_t idx = atomicAdd(fix.count, 1u);
+        if (idx < fix.capacity) fix.entries[idx] = FixEntry{x.exact_job, ox, oy};
+    }
+}
 
-    const StreamItem it = items[blockIdx.x];
-    const StreamJob &J = jobs[it.job];
-    const int tile = it.tile, band = it.band;
-    const int W = J.src.w;
-    const int cx0 = tile * J.tile_w;
-    const int c = cx0 + (int)threadIdx.x * STREAM_PX;
-    const int ys0 = __ldg(J.band_y + band), ys1 = __ldg(J.band_y + band + 1);
-    const int yend = __ldg(J.band_yend + band);
-    const int stride = J.src.s0;
-    const bool vec = (((size_t)J.src.p0 | (size_t)stride) & 15) == 0;
+__device__ __forceinline__ void xpass(const XTarget &x, int oy, int xt, const float4 *__restrict__ buf,
+                                      const FixList &fix)
+{
+#pragma unroll
+    for (int i = 0; i < STREAM_XREG; i++) {
+        const int j = xt + i * STREAM_XTHREADS;
+        if (j < x.n_own) xpixel(x, x.ox0 + j, oy, x.e0[i], x.k0[i], x.n[i], buf, fix);
+    }
+    for (int j = xt + STREAM_XREG * STREAM_XTHREADS; j < x.n_own; j += STREAM_XTHREADS) { // mild downscales only
+        const int ox = x.ox0 + j;
+        const int k0 = __ldg(x.xoff + ox);
+        xpixel(x, ox, oy, __ldg(x.xfirst + ox) + x.ebase, k0, __ldg(x.xoff + ox + 1) - k0, buf, fix);
+    }
+}
 
-    float acc_a[NT > 0 ? NT : 1][16], acc_b[NT > 0 ? NT : 1][16];
-    const RowRec *rec[NT > 0 ? NT : 1];
-    int tend[NT > 0 ? NT : 1]; // rows >= tend[T] contribute nothing to target T in this (tile, band)
+// ---- V warps ---------------------------------------------------------------------
+// Per-target streaming state of one V thread (4 source pixels): two accumulator sets
+// that swap roles at every emitted row (no register shuffling).  RGB of the 4 pixels is
+// 12 floats = 6 packed pairs for FFMA2.  Alpha is materialised lazily: while a warp has
+// only met opaque pixels (alpha 255) every pixel's alpha sum is the same fmaf chain, so
+// it is carried as two warp-uniform scalars (`sa`) and the V loop runs its ALPHA=false
+// instantiation; the first non-opaque row copies the scalars into the per-pixel lanes
+// (bit-identical to having accumulated them all along) and the warp continues in the
+// ALPHA=true instantiation.
+struct VState {
+    float2 rgb[2][6];
+    float2 al[2][2];
+    float sa[2];
+    int par;            // set `par` belongs to the lowest open output row
+    const RowRec *rec;  // this band's records, indexed by row - ys0
+    int tend;           // rows >= tend contribute nothing in this (tile, band)
+    bool clamp;         // two_stage target: clamp channels to alpha on non-opaque rows
+};
+
+__device__ __forceinline__ float2 magic2(uint32_t qa, int ka, uint32_t qb, int kb)
+{
+    // two bytes -> (2^23 + b) bit patterns; the caller subtracts 2^23 with one FADD2
+    return make_float2(__uint_as_float(__byte_perm(qa, 0x4B000000u, 0x7540 + ka)),
+                       __uint_as_float(__byte_perm(qb, 0x4B000000u, 0x7540 + kb)));
+}
+__device__ __forceinline__ void unpack_rgb(const uint4 &c, float2 *vp)
+{
+    const float2 m = make_float2(-8388608.0f, -8388608.0f);
+    vp[0] = __fadd2_rn(magic2(c.x, 0, c.x, 1), m);
+    vp[1] = __fadd2_rn(magic2(c.x, 2, c.y, 0), m);
+    vp[2] = __fadd2_rn(magic2(c.y, 1, c.y, 2), m);
+    vp[3] = __fadd2_rn(magic2(c.z, 0, c.z, 1), m);
+    vp[4] = __fadd2_rn(magic2(c.z, 2, c.w, 0), m);
+    vp[5] = __fadd2_rn(magic2(c.w, 1, c.w, 2), m);
+}
+__device__ __forceinline__ void unpack_alpha(const uint4 &c, float2 *va)
+{
+    const float2 m = make_float2(-8388608.0f, -8388608.0f);
+    va[0] = __fadd2_rn(magic2(c.x, 3, c.y, 3), m);
+    va[1] = __fadd2_rn(magic2(c.z, 3, c.w, 3), m);
+}
+
+template <int SET, bool ALPHA>
+__device__ __forceinline__ void park_row(VState &S, float4 *buf, int tid)
+{
+    const int base = (tid * 4) & ~7, key = (tid >> 1) & 7, lo = (tid & 1) * 4; // swz(4*tid + j)
+    const float2 *g = S.rgb[SET];
+    const float a0 = ALPHA ? S.al[SET][0].x : S.sa[SET], a1 = ALPHA ? S.al[SET][0].y : S.sa[SET];
+    const float a2 = ALPHA ? S.al[SET][1].x : S.sa[SET], a3 = ALPHA ? S.al[SET][1].y : S.sa[SET];
+    buf[base | ((lo + 0) ^ key)] = make_float4(g[0].x, g[0].y, g[1].x, a0);
+    buf[base | ((lo + 1) ^ key)] = make_float4(g[1].y, g[2].x, g[2].y, a1);
+    buf[base | ((lo + 2) ^ key)] = make_float4(g[3].x, g[3].y, g[4].x, a2);
+    buf[base | ((lo + 3) ^ key)] = make_float4(g[4].y, g[5].x, g[5].y, a3);
+#pragma unroll
+    for (int i = 0; i < 6; i++) S.rgb[SET][i] = make_float2(0.f, 0.f);
+    if (ALPHA) S.al[SET][0] = S.al[SET][1] = make_float2(0.f, 0.f);
+    else S.sa[SET] = 0.f;
+}
+
+struct VCursor {  // parked-row slot position of a V warp
+    int xs; uint32_t xph;
+    int emits;
+};
+
+// Vertical multiply-adds of one source row into every target, and the hand-off of
+// completed output rows to the X warps.
+template <int NT, bool ALPHA>
+__device__ __forceinline__ void v_row(VState *S, const uint4 &cur, int ys, int ys0, int tid, StreamSmem &sm, VCursor &C)
+{
+    float2 vp[6], va[2];
+    unpack_rgb(cur, vp);
+    if (ALPHA) unpack_alpha(cur, va);
 #pragma unroll
     for (int T = 0; T < NT; T++) {
+        if (ys >= S[T].tend) continue; // CTA-uniform
+        const int4 rr = __ldg((const int4 *)(S[T].rec + (ys - ys0)));
+        const float wa = __int_as_float(rr.x), wb = __int_as_float(rr.y);
+        const float w0 = S[T].par ? wb : wa, w1 = S[T].par ? wa : wb;
+        const float2 w00 = make_float2(w0, w0), w11 = make_float2(w1, w1);
+        if (!ALPHA) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) { acc_a[T][i] = 0.f; acc_b[T][i] = 0.f; }
-        rec[T] = nullptr;
-        tend[T] = ys0;
-        if (T < J.n_targets && __ldg(J.t[T].tile_ox + tile + 1) > __ldg(J.t[T].tile_ox + tile)) {
-            rec[T] = J.t[T].rows + __ldg(J.t[T].band_rec_off + band);
-            tend[T] = __ldg(J.t[T].band_tend + band);
+            for (int i = 0; i < 6; i++) {
+                S[T].rgb[0][i] = __ffma2_rn(vp[i], w00, S[T].rgb[0][i]);
+                S[T].rgb[1][i] = __ffma2_rn(vp[i], w11, S[T].rgb[1][i]);
+            }
+            S[T].sa[0] = fmaf(255.0f, w0, S[T].sa[0]);
+            S[T].sa[1] = fmaf(255.0f, w1, S[T].sa[1]);
+        } else {
+            float2 up[6];
+            if (S[T].clamp) {
+                // cropAndResize quantises to premultiplied RGBA8 first: channels clamp to alpha
+                const uint4 cc = make_uint4(clamp_to_alpha(cur.x), clamp_to_alpha(cur.y), clamp_to_alpha(cur.z),
+                                            clamp_to_alpha(cur.w));
+                unpack_rgb(cc, up);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 6; i++) up[i] = vp[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                S[T].rgb[0][i] = __ffma2_rn(up[i], w00, S[T].rgb[0][i]);
+                S[T].rgb[1][i] = __ffma2_rn(up[i], w11, S[T].rgb[1][i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                S[T].al[0][i] = __ffma2_rn(va[i], w00, S[T].al[0][i]);
+                S[T].al[1][i] = __ffma2_rn(va[i], w11, S[T].al[1][i]);
+            }
+        }
+        if (rr.z >= 0) { // CTA-uniform: this source row completes output row rr.z
+            if (C.emits >= STREAM_XSLOTS) mbar_wait(&sm.xempty[C.xs], C.xph);
+            if (S[T].par == 0) park_row<0, ALPHA>(S[T], sm.rowbuf[C.xs], tid);
+            else               park_row<1, ALPHA>(S[T], sm.rowbuf[C.xs], tid);
+            S[T].par ^= 1;
+            if (tid == 0) { sm.xmeta[C.xs][0] = T; sm.xmeta[C.xs][1] = rr.z; }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&sm.xfull[C.xs]);
+            C.emits++;
+            if (++C.xs == STREAM_XSLOTS) { C.xs = 0; C.xph ^= 1; }
         }
     }
+}
 
-    const uint8_t *row = J.src.p0 + (size_t)ys0 * stride;
-    uint4 cur = load_px4(row, c, W, vec);
-    int emits = 0;
-    const bool own_col = (int)threadIdx.x * STREAM_PX < J.tile_w && c < W;
+// What a V thread needs for the fused watermark copy, held in registers (the copy's
+// global stores would otherwise force the job struct to be re-read every row).
+struct VWm {
+    uint8_t *dst;
+    int stride, ys1;
+    bool on, vec;
+};
 
-    for (int ys = ys0; ys < yend; ys++) {
-        row += stride;
+// Rows k0..nr-1 of one ring stage (or, without TMA, of global memory).  ALPHA=false is
+// the all-opaque-so-far instantiation: it returns the index of the first row holding a
+// non-opaque pixel (that row is not processed), or -1 when the group is done.
+template <int NT, bool WM, bool TMA, bool ALPHA>
+__device__ __forceinline__ int v_group(VState *S, StreamSmem &sm, VCursor &C, const VWm &M, int stage, int k0, int nr,
+                                       int ysg, int ys0, int tid, int c, int W, bool edge, const uint8_t *grow, int stride)
+{
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (k0 < nr) cur = TMA ? sm.ring[stage][k0][tid] : load_px4(grow + (size_t)k0 * stride, c, W);
+#pragma unroll
+    for (int k = 0; k < STREAM_GROUP; k++) {
+        if (k < k0 || k >= nr) continue;
         uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (ys + 1 < yend) nxt = load_px4(row, c, W, vec);
-
-        if (WM && J.has_wm && ys < ys1 && own_col) {
-            uint4 o = cur;
-            const WatermarkD &wm = J.wm;
-            if (ys >= wm.by0 && ys < wm.by1 && c + 4 > wm.bx0 && c < wm.bx1) {
-                o.x = blend_if_inside(o.x, c, ys, wm);
-                o.y = blend_if_inside(o.y, c + 1, ys, wm);
-                o.z = blend_if_inside(o.z, c + 2, ys, wm);
-                o.w = blend_if_inside(o.w, c + 3, ys, wm);
-            }
-            uint8_t *d = wm.dst + (size_t)ys * wm.dst_stride + (size_t)c * 4;
-            if (c + 4 <= W && (((size_t)wm.dst | (size_t)wm.dst_stride) & 15) == 0) {
+        if (k + 1 < nr) nxt = TMA ? sm.ring[stage][k + 1][tid] : load_px4(grow + (size_t)(k + 1) * stride, c, W);
+        const int ys = ysg + k;
+        if (edge) { // columns past the image edge read as opaque black (they feed no output)
+            if (c >= W) cur.x = 0xff000000u;
+            if (c + 1 >= W) cur.y = 0xff000000u;
+            if (c + 2 >= W) cur.z = 0xff000000u;
+            cur.w = 0xff000000u;
+        }
+        if (NT > 0 && !ALPHA) {
+            const uint32_t m = min(min(cur.x, cur.y), min(cur.z, cur.w));
+            if (__any_sync(0xffffffffu, m < 0xff000000u)) return k;
+        }
+        if (WM && M.on && ys < M.ys1) {
+            const uint4 o = cur; // draw.Draw(Src) of an *image.RGBA is a copy; k_blend adds the glyphs
+            uint8_t *d = M.dst + (size_t)ys * M.stride + (size_t)c * 4;
+            if (M.vec) {
                 __stcs((uint4 *)d, o);
             } else {
                 ((uint32_t *)d)[0] = o.x;
@@ -406,83 +706,199 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
                 if (c + 3 < W) ((uint32_t *)d)[3] = o.w;
             }
         }
+        if (NT > 0) v_row<NT, ALPHA>(S, cur, ys, ys0, tid, sm, C);
+        cur = nxt;
+    }
+    return -1;
+}
 
-        if (NT > 0) {
-            float v[16];
-            unpack_px(cur.x, v); unpack_px(cur.y, v + 4);
-            unpack_px(cur.z, v + 8); unpack_px(cur.w, v + 12);
-            bool slow = false;
-            if (CHECK && J.check_premul) {
-                const uint32_t m = min(min(cur.x, cur.y), min(cur.z, cur.w));
-                slow = __any_sync(0xffffffffu, m < 0xff000000u);
-            }
-#pragma unroll
-            for (int T = 0; T < NT; T++) {
-                if (ys >= tend[T]) continue; // CTA-uniform
-                const int4 rr = __ldg((const int4 *)(rec[T] + (ys - ys0)));
-                const float wa = __int_as_float(rr.x), wb = __int_as_float(rr.y);
-                if (CHECK && slow && J.t[T].two_stage) {
-                    float vc[16];
-                    unpack_px(clamp_to_alpha(cur.x), vc); unpack_px(clamp_to_alpha(cur.y), vc + 4);
-                    unpack_px(clamp_to_alpha(cur.z), vc + 8); unpack_px(clamp_to_alpha(cur.w), vc + 12);
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        acc_a[T][i] = fmaf(vc[i], wa, acc_a[T][i]);
-                        acc_b[T][i] = fmaf(vc[i], wb, acc_b[T][i]);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        acc_a[T][i] = fmaf(v[i], wa, acc_a[T][i]);
-                        acc_b[T][i] = fmaf(v[i], wb, acc_b[T][i]);
-                    }
-                }
-                if (rr.z >= 0) { // CTA-uniform: this source row completes output row rr.z
-                    float4 *buf = rowbuf[emits & 1];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        buf[swz((int)threadIdx.x * 4 + j)] =
-                            make_float4(acc_a[T][4 * j], acc_a[T][4 * j + 1], acc_a[T][4 * j + 2], acc_a[T][4 * j + 3]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; i++) { acc_a[T][i] = acc_b[T][i]; acc_b[T][i] = 0.f; }
-                    __syncthreads();
-                    xpass(J.t[T], tile, rr.z, cx0, buf, fix);
-                    emits++;
-                }
+// TMA: rows are 16-byte aligned (base and stride), so they can be bulk-copied.
+// Otherwise (caller-provided device memory with an odd stride) the V warps LDG.
+template <int NT, bool WM, bool TMA>
+__global__ void __launch_bounds__(STREAM_CTA, 2)
+k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ items, FixList fix)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    StreamSmem &sm = *reinterpret_cast<StreamSmem *>(smem_raw);
+
+    const StreamItem it = items[blockIdx.x];
+    const StreamJob &J = jobs[it.job];
+    const int tile = it.tile, band = it.band;
+    const int W = J.src.w;
+    const int cx0 = tile * J.tile_w;
+    const int ys0 = __ldg(J.band_y + band), ys1 = __ldg(J.band_y + band + 1);
+    const int yend = __ldg(J.band_yend + band);
+    const int stride = J.src.s0;
+    const int warp = threadIdx.x >> 5;
+    const int ngroups = (yend - ys0 + STREAM_GROUP - 1) / STREAM_GROUP;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STREAM_STAGES; s++) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], STREAM_THREADS / 32);
+        }
+        for (int s = 0; s < STREAM_XSLOTS; s++) {
+            mbar_init(&sm.xfull[s], STREAM_THREADS / 32);
+            mbar_init(&sm.xempty[s], STREAM_XTHREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == STREAM_THREADS / 32) {
+        // ===== producer warp: one lane streams the slab's rows HBM -> smem ring, =====
+        // ===== STREAM_GROUP rows (8 KB) per stage and per barrier phase           =====
+        if (TMA && (threadIdx.x & 31) == 0) {
+            const uint32_t row_bytes = (uint32_t)(((min(STREAM_COLS, W - cx0) * 4) + 15) & ~15);
+            const uint8_t *g = J.src.p0 + (size_t)ys0 * stride + (size_t)cx0 * 4;
+            int s = 0;
+            uint32_t ph = 1; // first pass over the ring: slots are free
+            for (int i = 0; i < ngroups; i++) {
+                if (i >= STREAM_STAGES) mbar_wait_relaxed(&sm.empty[s], ph);
+                const int nr = min(STREAM_GROUP, yend - ys0 - i * STREAM_GROUP);
+                mbar_arrive_expect_tx(&sm.full[s], row_bytes * (uint32_t)nr);
+                for (int k = 0; k < nr; k++, g += stride) tma_load_1d(&sm.ring[s][k][0], g, row_bytes, &sm.full[s]);
+                if (++s == STREAM_STAGES) { s = 0; ph ^= 1; }
             }
         }
-        cur = nxt;
+        return;
+    }
+
+    if (warp > STREAM_THREADS / 32) {
+        // ===== X warps: horizontal pass + quantise + store of every parked row =====
+        if (NT == 0) return;
+        const int xt = (int)threadIdx.x - (STREAM_THREADS + 32);
+        XTarget X0, X1;
+        int total = 0;
+        X0.n_own = X1.n_own = 0;
+        if (J.n_targets > 0) {
+            xtarget_load(X0, J.t[0], tile, cx0, xt);
+            if (X0.n_own > 0) total += __ldg(J.t[0].band_oy + band + 1) - __ldg(J.t[0].band_oy + band);
+        }
+        if (NT > 1 && J.n_targets > 1) {
+            xtarget_load(X1, J.t[1], tile, cx0, xt);
+            if (X1.n_own > 0) total += __ldg(J.t[1].band_oy + band + 1) - __ldg(J.t[1].band_oy + band);
+        }
+        int s = 0;
+        uint32_t ph = 0;
+        for (int e = 0; e < total; e++) {
+            mbar_wait_relaxed(&sm.xfull[s], ph);
+            const int T = sm.xmeta[s][0], oy = sm.xmeta[s][1];
+            if (NT == 1 || T == 0) xpass(X0, oy, xt, sm.rowbuf[s], fix);
+            else                   xpass(X1, oy, xt, sm.rowbuf[s], fix);
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&sm.xempty[s]);
+            if (++s == STREAM_XSLOTS) { s = 0; ph ^= 1; }
+        }
+        return;
+    }
+
+    // ===== V warps: vertical pass =====
+    const int tid = (int)threadIdx.x;
+    const int c = cx0 + tid * STREAM_PX;
+    VState S[NT > 0 ? NT : 1];
+#pragma unroll
+    for (int T = 0; T < NT; T++) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) S[T].rgb[k][i] = make_float2(0.f, 0.f);
+            S[T].al[k][0] = S[T].al[k][1] = make_float2(0.f, 0.f);
+            S[T].sa[k] = 0.f;
+        }
+        S[T].par = 0;
+        S[T].rec = nullptr;
+        S[T].tend = ys0;
+        S[T].clamp = false;
+        if (T < J.n_targets && __ldg(J.t[T].tile_ox + tile + 1) > __ldg(J.t[T].tile_ox + tile)) {
+            S[T].rec = J.t[T].rows + __ldg(J.t[T].band_rec_off + band);
+            S[T].tend = __ldg(J.t[T].band_tend + band);
+            S[T].clamp = J.t[T].two_stage != 0;
+        }
+    }
+    VWm M;
+    M.on = WM && J.has_wm && tid * STREAM_PX < J.tile_w && c < W;
+    M.dst = WM ? J.wm.dst : nullptr;
+    M.stride = WM ? J.wm.dst_stride : 0;
+    M.ys1 = ys1;
+    M.vec = WM && c + 4 <= W && (((size_t)M.dst | (size_t)M.stride) & 15) == 0;
+    const bool edge = c + 4 > W; // at most one V thread per row holds a partial or empty pixel group
+    const uint8_t *grow = J.src.p0 + (size_t)ys0 * stride;
+    VCursor C{0, 1u, 0};
+    int rs = 0;
+    uint32_t rph = 0;
+
+    auto acquire = [&]() { if (TMA) mbar_wait(&sm.full[rs], rph); };
+    auto release = [&]() {
+        if (TMA) {
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&sm.empty[rs]);
+            if (++rs == STREAM_STAGES) { rs = 0; rph ^= 1; }
+        }
+    };
+
+    int g = 0, kres = -1;
+    // phase 1: every pixel this warp has met so far is opaque
+    for (; g < ngroups; g++) {
+        const int nr = min(STREAM_GROUP, yend - ys0 - g * STREAM_GROUP);
+        acquire();
+        kres = v_group<NT, WM, TMA, false>(S, sm, C, M, rs, 0, nr, ys0 + g * STREAM_GROUP, ys0, tid, c, W, edge,
+                                           grow + (size_t)g * STREAM_GROUP * stride, stride);
+        if (kres >= 0) break;
+        release();
+    }
+    // phase 2: per-pixel alpha lanes, seeded from the scalar chains
+    if (NT > 0 && kres >= 0) {
+#pragma unroll
+        for (int T = 0; T < NT; T++)
+#pragma unroll
+            for (int k = 0; k < 2; k++) S[T].al[k][0] = S[T].al[k][1] = make_float2(S[T].sa[k], S[T].sa[k]);
+        for (; g < ngroups; g++) {
+            const int nr = min(STREAM_GROUP, yend - ys0 - g * STREAM_GROUP);
+            if (kres < 0) acquire();
+            v_group<NT, WM, TMA, true>(S, sm, C, M, rs, kres < 0 ? 0 : kres, nr, ys0 + g * STREAM_GROUP, ys0, tid, c, W,
+                                       edge, grow + (size_t)g * STREAM_GROUP * stride, stride);
+            kres = -1;
+            release();
+        }
     }
 }
 
-int stream_smem_bytes() { return (int)(2 * STREAM_COLS * sizeof(float4)); }
+int stream_smem_bytes() { return (int)sizeof(StreamSmem); }
 
-template <int NT, bool WM, bool CHECK>
+template <int NT, bool WM, bool TMA>
 static cudaError_t launch_stream_t(const StreamJob *jobs, const StreamItem *items, int n, FixList fix, cudaStream_t st)
 {
-    k_stream<NT, WM, CHECK><<<n, STREAM_THREADS, 0, st>>>(jobs, items, fix);
+    static bool configured = false; // per instantiation; benign race (idempotent attribute)
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_stream<NT, WM, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(StreamSmem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_stream<NT, WM, TMA><<<n, STREAM_CTA, sizeof(StreamSmem), st>>>(jobs, items, fix);
     return cudaGetLastError();
 }
 
+template <bool TMA>
+static cudaError_t launch_stream_a(const StreamJob *jobs, const StreamItem *items, int n_items, int max_targets,
+                                   bool any_wm, FixList fix, cudaStream_t st)
+{
+    switch (max_targets) {
+    case 0: return any_wm ? launch_stream_t<0, true, TMA>(jobs, items, n_items, fix, st) : cudaSuccess;
+    case 1: return any_wm ? launch_stream_t<1, true, TMA>(jobs, items, n_items, fix, st)
+                          : launch_stream_t<1, false, TMA>(jobs, items, n_items, fix, st);
+    default: return any_wm ? launch_stream_t<2, true, TMA>(jobs, items, n_items, fix, st)
+                           : launch_stream_t<2, false, TMA>(jobs, items, n_items, fix, st);
+    }
+}
+
 cudaError_t launch_stream(const StreamJob *jobs, const StreamItem *items, int n_items, int max_targets,
-                          bool any_wm, bool any_check, FixList fix, cudaStream_t st)
+                          bool any_wm, bool tma, FixList fix, cudaStream_t st)
 {
     if (n_items <= 0) return cudaSuccess;
-#define IPG_DISPATCH(NT)                                                                          \
-    if (any_wm) {                                                                                 \
-        return any_check ? launch_stream_t<NT, true, true>(jobs, items, n_items, fix, st)         \
-                         : launch_stream_t<NT, true, false>(jobs, items, n_items, fix, st);       \
-    } else {                                                                                      \
-        return any_check ? launch_stream_t<NT, false, true>(jobs, items, n_items, fix, st)        \
-                         : launch_stream_t<NT, false, false>(jobs, items, n_items, fix, st);      \
-    }
-    switch (max_targets) {
-    case 0: if (!any_wm) return cudaSuccess; return launch_stream_t<0, true, false>(jobs, items, n_items, fix, st);
-    case 1: IPG_DISPATCH(1)
-    default: IPG_DISPATCH(2)
-    }
-#undef IPG_DISPATCH
+    return tma ? launch_stream_a<true>(jobs, items, n_items, max_targets, any_wm, fix, st)
+               : launch_stream_a<false>(jobs, items, n_items, max_targets, any_wm, fix, st);
 }
 
 cudaError_t launch_exact_tiles(const ExactJob *jobs, const ExactItem *items, int n_items, cudaStream_t st)
@@ -495,7 +911,14 @@ cudaError_t launch_exact_tiles(const ExactJob *jobs, const ExactItem *items, int
 cudaError_t launch_exact_fix(const ExactJob *jobs, int n_jobs, FixList fix, cudaStream_t st)
 {
     if (!fix.capacity || n_jobs <= 0) return cudaSuccess;
-    k_exact_fix<<<148 * 4, 128, 0, st>>>(jobs, n_jobs, fix);
+    k_exact_fix<<<148 * 4, FIX_THREADS, 0, st>>>(jobs, n_jobs, fix);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_blend(const WatermarkD *wms, const BlendItem *items, int n_items, cudaStream_t st)
+{
+    if (n_items <= 0) return cudaSuccess;
+    k_blend<<<n_items, 256, 0, st>>>(wms, items);
     return cudaGetLastError();
 }
 

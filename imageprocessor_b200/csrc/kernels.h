@@ -7,7 +7,7 @@ namespace ipg {
 
 // Streaming fp32 resample (+ fused watermark copy/blend): one CTA per StreamItem.
 cudaError_t launch_stream(const StreamJob *jobs, const StreamItem *items, int n_items,
-                          int max_targets, bool any_wm, bool any_check, FixList fix,
+                          int max_targets, bool any_wm, bool tma, FixList fix,
                           cudaStream_t st);
 
 // fp64 reference-order resample of whole outputs: one CTA per 32x8 output tile.
@@ -17,7 +17,10 @@ cudaError_t launch_exact_tiles(const ExactJob *jobs, const ExactItem *items, int
 // fp64 re-evaluation of the pixels a stream kernel flagged (count read on device).
 cudaError_t launch_exact_fix(const ExactJob *jobs, int n_jobs, FixList fix, cudaStream_t st);
 
-// draw.Draw(Src) convert/copy + ordered glyph blend for any layout.
+// Ordered glyph blend in place over each watermark's glyph box (after the copy/convert).
+cudaError_t launch_blend(const WatermarkD *wms, const BlendItem *items, int n_items, cudaStream_t st);
+
+// draw.Draw(Src) convert/copy for any layout (glyphs follow in launch_blend).
 cudaError_t launch_watermark(const WmJob *jobs, const WmItem *items, int n_items, cudaStream_t st);
 
 int stream_smem_bytes();

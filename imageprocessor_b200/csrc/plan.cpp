@@ -122,12 +122,14 @@ static bool build_target(StreamGeom &g, int ti, const StreamTargetSpec &s, doubl
     // row bands: an output row belongs to the band holding its first source row
     t.band_rec_off.assign((size_t)g.n_bands, 0);
     t.band_tend.assign((size_t)g.n_bands, 0);
+    t.band_oy.assign((size_t)g.n_bands + 1, s.dh);
     int32_t oy = 0;
     for (int32_t b = 0; b < g.n_bands; b++) {
         const int32_t Y0 = g.band_y[b], Y1 = g.band_y[b + 1];
         const int32_t oyA = oy;
         while (oy < s.dh && ay.first[oy] + s.rect_y < Y1) oy++;
         const int32_t oyB = oy;
+        t.band_oy[b] = oyA;
         t.band_rec_off[b] = (int32_t)t.rows.size();
         int32_t tend = Y0;
         if (oyB > oyA) tend = last(oyB - 1) + s.rect_y + 1;

@@ -42,6 +42,7 @@ struct StreamTargetGeom {
     std::vector<RowRec> rows;         // per-band records
     std::vector<int32_t> band_rec_off;// [n_bands]
     std::vector<int32_t> band_tend;   // [n_bands] one past last source row with a contribution
+    std::vector<int32_t> band_oy;     // [n_bands+1] first output row owned by each band
     int32_t fix_d = 0;
 };
 

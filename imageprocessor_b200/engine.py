@@ -256,6 +256,9 @@ class Engine:
     def flush(self) -> None:
         L.check(self._lib.ipg_flush(self._ctx))
 
+    def reset_stats(self) -> None:
+        L.check(self._lib.ipg_reset_stats(self._ctx))
+
     def stats(self) -> dict:
         s = L.Stats()
         L.check(self._lib.ipg_get_stats(self._ctx, C.byref(s)))

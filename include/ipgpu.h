@@ -164,6 +164,10 @@ typedef struct {
     double stream_kernel_ms;      /* k_stream (fp32 resample + watermark copy) */
     double fix_kernel_ms;         /* k_exact_fix                               */
     double other_kernel_ms;       /* k_exact_tiles + k_watermark               */
+    /* device-clock spans since ipg_reset_stats (max over devices): first kernel start ->
+     * last kernel end, and first batch H2D start -> last batch D2H end */
+    double kernel_span_ms;
+    double batch_span_ms;
 } ipg_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -201,6 +205,8 @@ IPG_API int ipg_flush(ipg_ctx *ctx);
 
 /* ---- introspection ------------------------------------------------------- */
 IPG_API int ipg_get_stats(ipg_ctx *ctx, ipg_stats *out);
+/* ipg_flush, then zero the counters and restart the device-time spans. */
+IPG_API int ipg_reset_stats(ipg_ctx *ctx);
 
 /* ---- host-side helpers with the reference's arithmetic ------------------- */
 /* resize.go:63-72 */

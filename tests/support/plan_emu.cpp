@@ -16,12 +16,9 @@ using namespace ipg;
 
 static inline int quant16(float v, int D, bool &amb)
 {
-    const int T = (int)std::floor(std::fmaf(v, 256.0f, 128.0f));
-    const int out = std::min(T >> 16, 255);
-    const int lo = std::min(std::max(T - D, 0) >> 16, 255);
-    const int hi = std::min((T + D) >> 16, 255);
-    amb |= (lo != hi);
-    return std::max(out, 0);
+    const uint32_t T = (uint32_t)std::min((int)std::floor(std::fmaf(v, 256.0f, 128.0f)), 0xffffff);
+    amb |= ((T & 0xffffu) - (uint32_t)D) >= (65536u - 2u * (uint32_t)D);
+    return (int)(T >> 16);
 }
 
 extern "C" int planemu_axis(int dn, int sn, int32_t *off, int32_t *first, double *w, double *inv, int *max_taps)
