@@ -88,8 +88,8 @@ struct WatermarkD {
     uint32_t sr, sg, sb, sa;     // Uniform.RGBA(): c * 0x101
 };
 
-// k_stream CTA: 4 vertical-pass warps (128 threads x 4 px = one 512-column slab), 1 TMA
-// producer warp, 2 horizontal-pass warps.
+// k_stream CTA: 4 vertical-pass warps (128 threads x 4 px = one 512-column slab) and 2
+// horizontal-pass warps.  The V warps refill the TMA ring themselves (last one out).
 enum {
     STREAM_THREADS = 128, STREAM_PX = 4, STREAM_COLS = STREAM_THREADS * STREAM_PX,
     STREAM_GROUP = 4,           // source rows per ring stage / TMA barrier phase (8 KB)
@@ -97,7 +97,8 @@ enum {
     STREAM_XSLOTS = 3,          // vertically-filtered rows awaiting the horizontal pass (8 KB each)
     STREAM_XTHREADS = 64,
     STREAM_XREG = 3,            // outputs per X thread whose tap tables live in registers
-    STREAM_CTA = STREAM_THREADS + 32 + STREAM_XTHREADS,
+    STREAM_XTAPS = 8,           // ... and, when every one has at most this many taps, the weights too
+    STREAM_CTA = STREAM_THREADS + STREAM_XTHREADS,
 };
 
 struct StreamJob {

@@ -431,7 +431,7 @@ __device__ __forceinline__ uint32_t clamp_to_alpha(uint32_t q)
 
 __device__ __forceinline__ uint4 load_px4(const uint8_t *row, int c, int W)
 {
-    uint4 v = make_uint4(0, 0, 0, 0);
+    uint4 v = make_uint4(0xff000000u, 0xff000000u, 0xff000000u, 0xff000000u); // past the edge: opaque black
     if (c < W) {
         const uint32_t *p = (const uint32_t *)row + c;
         v.x = __ldg(p);
@@ -455,14 +455,18 @@ __device__ __forceinline__ uint32_t quant16(float v, uint32_t D, uint32_t span, 
 struct __align__(128) StreamSmem {
     uint4 ring[STREAM_STAGES][STREAM_GROUP][STREAM_THREADS]; // source rows, 2 KB each; a stage = STREAM_GROUP rows
     float4 rowbuf[STREAM_XSLOTS][STREAM_COLS];   // vertically filtered rows, XOR-swizzled slots
-    uint64_t full[STREAM_STAGES], empty[STREAM_STAGES];
+    uint64_t full[STREAM_STAGES];                // TMA completion of a stage
     uint64_t xfull[STREAM_XSLOTS], xempty[STREAM_XSLOTS];
+    uint32_t released[STREAM_STAGES];            // V warps done with a stage; the last one refills it
     int32_t xmeta[STREAM_XSLOTS][2];             // {target, output row} of each parked row
 };
 
 // ---- X warps ---------------------------------------------------------------------
 // What an X thread needs of one target, copied out of the job so that its global
-// stores cannot force reloads.
+// stores cannot force reloads.  The first STREAM_XREG outputs of the thread keep their
+// tap tables in registers; when all of them have at most STREAM_XTAPS taps (`cached`)
+// the weights live in registers too and the taps run branch-free (weight 0 past the
+// end adds exactly nothing).
 struct XTarget {
     uint8_t *dst;
     const float *xw;
@@ -470,8 +474,9 @@ struct XTarget {
     int dst_stride, ox0, n_own, ebase; // ebase = rect_x - cx0
     int exact_job;
     uint32_t D, span;
-    // first STREAM_XREG outputs of this thread, cached: first smem slot, weight offset, tap count
+    bool cached;
     int e0[STREAM_XREG], k0[STREAM_XREG], n[STREAM_XREG];
+    float w[STREAM_XREG][STREAM_XTAPS];
 };
 
 __device__ __forceinline__ void xtarget_load(XTarget &x, const StreamTarget &t, int tile, int cx0, int xt)
@@ -484,6 +489,7 @@ __device__ __forceinline__ void xtarget_load(XTarget &x, const StreamTarget &t, 
     x.exact_job = t.exact_job;
     x.D = (uint32_t)t.fix_d;
     x.span = 65536u - 2u * x.D;
+    bool small = true;
 #pragma unroll
     for (int i = 0; i < STREAM_XREG; i++) {
         const int j = xt + i * STREAM_XTHREADS;
@@ -494,10 +500,31 @@ __device__ __forceinline__ void xtarget_load(XTarget &x, const StreamTarget &t, 
             x.n[i] = __ldg(t.xoff + ox + 1) - x.k0[i];
             x.e0[i] = __ldg(t.xfirst + ox) + x.ebase;
         }
+        small &= x.n[i] <= STREAM_XTAPS;
+    }
+    x.cached = __all_sync(0xffffffffu, small);
+#pragma unroll
+    for (int i = 0; i < STREAM_XREG; i++)
+#pragma unroll
+        for (int k = 0; k < STREAM_XTAPS; k++)
+            x.w[i][k] = (x.cached && k < x.n[i]) ? __ldg(t.xw + x.k0[i] + k) : 0.f;
+}
+
+__device__ __forceinline__ void xfinish(const XTarget &x, int ox, int oy, float2 rg, float2 ba, const FixList &fix)
+{
+    const float a = ba.y;
+    const float r = fminf(rg.x, a), g = fminf(rg.y, a), b = fminf(ba.x, a);
+    bool amb = false;
+    const uint32_t o = quant16(r, x.D, x.span, amb) | (quant16(g, x.D, x.span, amb) << 8) |
+                       (quant16(b, x.D, x.span, amb) << 16) | (quant16(a, x.D, x.span, amb) << 24);
+    *(uint32_t *)(x.dst + (size_t)oy * x.dst_stride + (size_t)ox * 4) = o;
+    if (amb && fix.capacity) {
+        const uint32_t idx = atomicAdd(fix.count, 1u);
+        if (idx < fix.capacity) fix.entries[idx] = FixEntry{x.exact_job, ox, oy};
     }
 }
 
-// One output pixel of the horizontal pass; FFMA2 carries (r,g) and (b,a) as packed pairs.
+// One output pixel, taps and weights from memory; FFMA2 carries (r,g) and (b,a) pairs.
 __device__ __forceinline__ void xpixel(const XTarget &x, int ox, int oy, int e0, int k0, int n,
                                        const float4 *__restrict__ buf, const FixList &fix)
 {
@@ -511,25 +538,33 @@ __device__ __forceinline__ void xpixel(const XTarget &x, int ox, int oy, int e0,
         rg = __ffma2_rn(make_float2(q.x, q.y), ww, rg);
         ba = __ffma2_rn(make_float2(q.z, q.w), ww, ba);
     }
-    const float a = ba.y;
-    const float r = fminf(rg.x, a), g = fminf(rg.y, a), b = fminf(ba.x, a);
-    bool amb = false;
-    const uint32_t o = quant16(r, x.D, x.span, amb) | (quant16(g, x.D, x.span, amb) << 8) |
-                       (quant16(b, x.D, x.span, amb) << 16) | (quant16(a, x.D, x.span, amb) << 24);
-    *(uint32_t *)(x.dst + (size_t)oy * x.dst_stride + (size_t)ox * 4) = o;
-    if (amb && fix.capacity) {
-        const uint32_t idx = atomicAdd(fix.count, 1u);
-        if (idx < fix.capacity) fix.entries[idx] = FixEntry{x.exact_job, ox, oy};
-    }
+    xfinish(x, ox, oy, rg, ba, fix);
 }
 
 __device__ __forceinline__ void xpass(const XTarget &x, int oy, int xt, const float4 *__restrict__ buf,
                                       const FixList &fix)
 {
+    if (x.cached) {
 #pragma unroll
-    for (int i = 0; i < STREAM_XREG; i++) {
-        const int j = xt + i * STREAM_XTHREADS;
-        if (j < x.n_own) xpixel(x, x.ox0 + j, oy, x.e0[i], x.k0[i], x.n[i], buf, fix);
+        for (int i = 0; i < STREAM_XREG; i++) {
+            const int j = xt + i * STREAM_XTHREADS;
+            if (j >= x.n_own) break;
+            float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < STREAM_XTAPS; k++) {
+                const float4 q = buf[swz(min(x.e0[i] + k, STREAM_COLS - 1))];
+                const float2 ww = make_float2(x.w[i][k], x.w[i][k]);
+                rg = __ffma2_rn(make_float2(q.x, q.y), ww, rg);
+                ba = __ffma2_rn(make_float2(q.z, q.w), ww, ba);
+            }
+            xfinish(x, x.ox0 + j, oy, rg, ba, fix);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < STREAM_XREG; i++) {
+            const int j = xt + i * STREAM_XTHREADS;
+            if (j < x.n_own) xpixel(x, x.ox0 + j, oy, x.e0[i], x.k0[i], x.n[i], buf, fix);
+        }
     }
     for (int j = xt + STREAM_XREG * STREAM_XTHREADS; j < x.n_own; j += STREAM_XTHREADS) { // mild downscales only
         const int ox = x.ox0 + j;
@@ -603,9 +638,10 @@ struct VCursor {  // parked-row slot position of a V warp
 };
 
 // Vertical multiply-adds of one source row into every target, and the hand-off of
-// completed output rows to the X warps.
+// completed output rows to the X warp.  rr[T] is this row's record (prefetched).
 template <int NT, bool ALPHA>
-__device__ __forceinline__ void v_row(VState *S, const uint4 &cur, int ys, int ys0, int tid, StreamSmem &sm, VCursor &C)
+__device__ __forceinline__ void v_row(VState *S, const uint4 &cur, const int4 *rr, int ys, int tid, StreamSmem &sm,
+                                      VCursor &C)
 {
     float2 vp[6], va[2];
     unpack_rgb(cur, vp);
@@ -613,8 +649,10 @@ __device__ __forceinline__ void v_row(VState *S, const uint4 &cur, int ys, int y
 #pragma unroll
     for (int T = 0; T < NT; T++) {
         if (ys >= S[T].tend) continue; // CTA-uniform
-        const int4 rr = __ldg((const int4 *)(S[T].rec + (ys - ys0)));
-        const float wa = __int_as_float(rr.x), wb = __int_as_float(rr.y);
+        const float wa = __int_as_float(rr[T].x), wb = __int_as_float(rr[T].y);
+        // keep the record's unused 4th word allocated until here: if the compiler recycled that
+        // register early, every row would stall on a write-after-write against the in-flight LDG.128
+        asm volatile("" ::"r"(rr[T].w));
         const float w0 = S[T].par ? wb : wa, w1 = S[T].par ? wa : wb;
         const float2 w00 = make_float2(w0, w0), w11 = make_float2(w1, w1);
         if (!ALPHA) {
@@ -647,12 +685,12 @@ __device__ __forceinline__ void v_row(VState *S, const uint4 &cur, int ys, int y
                 S[T].al[1][i] = __ffma2_rn(va[i], w11, S[T].al[1][i]);
             }
         }
-        if (rr.z >= 0) { // CTA-uniform: this source row completes output row rr.z
+        if (rr[T].z >= 0) { // CTA-uniform: this source row completes output row rr.z
             if (C.emits >= STREAM_XSLOTS) mbar_wait(&sm.xempty[C.xs], C.xph);
             if (S[T].par == 0) park_row<0, ALPHA>(S[T], sm.rowbuf[C.xs], tid);
             else               park_row<1, ALPHA>(S[T], sm.rowbuf[C.xs], tid);
             S[T].par ^= 1;
-            if (tid == 0) { sm.xmeta[C.xs][0] = T; sm.xmeta[C.xs][1] = rr.z; }
+            if (tid == 0) { sm.xmeta[C.xs][0] = T; sm.xmeta[C.xs][1] = rr[T].z; }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&sm.xfull[C.xs]);
             C.emits++;
@@ -674,26 +712,32 @@ struct VWm {
 // non-opaque pixel (that row is not processed), or -1 when the group is done.
 template <int NT, bool WM, bool TMA, bool ALPHA>
 __device__ __forceinline__ int v_group(VState *S, StreamSmem &sm, VCursor &C, const VWm &M, int stage, int k0, int nr,
-                                       int ysg, int ys0, int tid, int c, int W, bool edge, const uint8_t *grow, int stride)
+                                       int ysg, int tid, int c, int W, const uint8_t *grow, int stride)
 {
     uint4 cur = make_uint4(0, 0, 0, 0);
-    if (k0 < nr) cur = TMA ? sm.ring[stage][k0][tid] : load_px4(grow + (size_t)k0 * stride, c, W);
+    int4 rr[NT > 0 ? NT : 1];
+    if (k0 < nr) {
+        cur = TMA ? sm.ring[stage][k0][tid] : load_px4(grow + (size_t)k0 * stride, c, W);
 #pragma unroll
-    for (int k = 0; k < STREAM_GROUP; k++) {
-        if (k < k0 || k >= nr) continue;
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (k + 1 < nr) nxt = TMA ? sm.ring[stage][k + 1][tid] : load_px4(grow + (size_t)(k + 1) * stride, c, W);
+        for (int T = 0; T < NT; T++)
+            rr[T] = (ysg + k0 < S[T].tend) ? __ldg((const int4 *)S[T].rec) : make_int4(0, 0, -1, 0);
+    }
+#pragma unroll 1
+    for (int k = k0; k < nr; k++) {
         const int ys = ysg + k;
-        if (edge) { // columns past the image edge read as opaque black (they feed no output)
-            if (c >= W) cur.x = 0xff000000u;
-            if (c + 1 >= W) cur.y = 0xff000000u;
-            if (c + 2 >= W) cur.z = 0xff000000u;
-            cur.w = 0xff000000u;
-        }
         if (NT > 0 && !ALPHA) {
             const uint32_t m = min(min(cur.x, cur.y), min(cur.z, cur.w));
             if (__any_sync(0xffffffffu, m < 0xff000000u)) return k;
         }
+        // software pipeline: next row's pixels and records are requested before this row's math
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        int4 rn[NT > 0 ? NT : 1];
+#pragma unroll
+        for (int T = 0; T < NT; T++) {
+            if (ys < S[T].tend) S[T].rec++;
+            rn[T] = (ys + 1 < S[T].tend) ? __ldg((const int4 *)S[T].rec) : make_int4(0, 0, -1, 0);
+        }
+        if (k + 1 < nr) nxt = TMA ? sm.ring[stage][k + 1][tid] : load_px4(grow + (size_t)(k + 1) * stride, c, W);
         if (WM && M.on && ys < M.ys1) {
             const uint4 o = cur; // draw.Draw(Src) of an *image.RGBA is a copy; k_blend adds the glyphs
             uint8_t *d = M.dst + (size_t)ys * M.stride + (size_t)c * 4;
@@ -706,8 +750,10 @@ __device__ __forceinline__ int v_group(VState *S, StreamSmem &sm, VCursor &C, co
                 if (c + 3 < W) ((uint32_t *)d)[3] = o.w;
             }
         }
-        if (NT > 0) v_row<NT, ALPHA>(S, cur, ys, ys0, tid, sm, C);
+        if (NT > 0) v_row<NT, ALPHA>(S, cur, rr, ys, tid, sm, C);
         cur = nxt;
+#pragma unroll
+        for (int T = 0; T < NT; T++) rr[T] = rn[T];
     }
     return -1;
 }
@@ -715,7 +761,7 @@ __device__ __forceinline__ int v_group(VState *S, StreamSmem &sm, VCursor &C, co
 // TMA: rows are 16-byte aligned (base and stride), so they can be bulk-copied.
 // Otherwise (caller-provided device memory with an odd stride) the V warps LDG.
 template <int NT, bool WM, bool TMA>
-__global__ void __launch_bounds__(STREAM_CTA, 2)
+__global__ void __launch_bounds__(STREAM_CTA, (NT == 2 ? 2 : 3))
 k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ items, FixList fix)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -731,11 +777,23 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     const int stride = J.src.s0;
     const int warp = threadIdx.x >> 5;
     const int ngroups = (yend - ys0 + STREAM_GROUP - 1) / STREAM_GROUP;
+    const int tid = (int)threadIdx.x;
+    const int c = cx0 + tid * STREAM_PX;
+    const uint32_t row_bytes = (uint32_t)(((min(STREAM_COLS, W - cx0) * 4) + 15) & ~15);
+    const uint8_t *gsrc = J.src.p0 + (size_t)ys0 * stride + (size_t)cx0 * 4;
 
-    if (threadIdx.x == 0) {
+    // One TMA transaction group: STREAM_GROUP rows (8 KB) HBM -> ring stage, one barrier phase.
+    auto refill = [&](int group, int stage) {
+        const int nr = min(STREAM_GROUP, yend - ys0 - group * STREAM_GROUP);
+        mbar_arrive_expect_tx(&sm.full[stage], row_bytes * (uint32_t)nr);
+        const uint8_t *g = gsrc + (size_t)group * STREAM_GROUP * stride;
+        for (int k = 0; k < nr; k++, g += stride) tma_load_1d(&sm.ring[stage][k][0], g, row_bytes, &sm.full[stage]);
+    };
+
+    if (tid == 0) {
         for (int s = 0; s < STREAM_STAGES; s++) {
             mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], STREAM_THREADS / 32);
+            sm.released[s] = 0;
         }
         for (int s = 0; s < STREAM_XSLOTS; s++) {
             mbar_init(&sm.xfull[s], STREAM_THREADS / 32);
@@ -743,31 +801,23 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // slab columns past the image edge are never written by TMA: park opaque black there
+    // so they neither look transparent nor feed anything (no output taps them)
+    if (TMA && tid < STREAM_THREADS && c >= W) {
+        for (int s = 0; s < STREAM_STAGES; s++)
+            for (int k = 0; k < STREAM_GROUP; k++)
+                sm.ring[s][k][tid] = make_uint4(0xff000000u, 0xff000000u, 0xff000000u, 0xff000000u);
+    }
     __syncthreads();
-
-    if (warp == STREAM_THREADS / 32) {
-        // ===== producer warp: one lane streams the slab's rows HBM -> smem ring, =====
-        // ===== STREAM_GROUP rows (8 KB) per stage and per barrier phase           =====
-        if (TMA && (threadIdx.x & 31) == 0) {
-            const uint32_t row_bytes = (uint32_t)(((min(STREAM_COLS, W - cx0) * 4) + 15) & ~15);
-            const uint8_t *g = J.src.p0 + (size_t)ys0 * stride + (size_t)cx0 * 4;
-            int s = 0;
-            uint32_t ph = 1; // first pass over the ring: slots are free
-            for (int i = 0; i < ngroups; i++) {
-                if (i >= STREAM_STAGES) mbar_wait_relaxed(&sm.empty[s], ph);
-                const int nr = min(STREAM_GROUP, yend - ys0 - i * STREAM_GROUP);
-                mbar_arrive_expect_tx(&sm.full[s], row_bytes * (uint32_t)nr);
-                for (int k = 0; k < nr; k++, g += stride) tma_load_1d(&sm.ring[s][k][0], g, row_bytes, &sm.full[s]);
-                if (++s == STREAM_STAGES) { s = 0; ph ^= 1; }
-            }
-        }
-        return;
+    if (TMA && tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int g = 0; g < min(STREAM_STAGES, ngroups); g++) refill(g, g); // prologue: fill the ring
     }
 
-    if (warp > STREAM_THREADS / 32) {
+    if (warp >= STREAM_THREADS / 32) {
         // ===== X warps: horizontal pass + quantise + store of every parked row =====
         if (NT == 0) return;
-        const int xt = (int)threadIdx.x - (STREAM_THREADS + 32);
+        const int xt = tid - STREAM_THREADS;
         XTarget X0, X1;
         int total = 0;
         X0.n_own = X1.n_own = 0;
@@ -782,20 +832,18 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
         int s = 0;
         uint32_t ph = 0;
         for (int e = 0; e < total; e++) {
-            mbar_wait_relaxed(&sm.xfull[s], ph);
+            mbar_wait(&sm.xfull[s], ph);
             const int T = sm.xmeta[s][0], oy = sm.xmeta[s][1];
             if (NT == 1 || T == 0) xpass(X0, oy, xt, sm.rowbuf[s], fix);
             else                   xpass(X1, oy, xt, sm.rowbuf[s], fix);
             __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(&sm.xempty[s]);
+            if ((tid & 31) == 0) mbar_arrive(&sm.xempty[s]);
             if (++s == STREAM_XSLOTS) { s = 0; ph ^= 1; }
         }
         return;
     }
 
     // ===== V warps: vertical pass =====
-    const int tid = (int)threadIdx.x;
-    const int c = cx0 + tid * STREAM_PX;
     VState S[NT > 0 ? NT : 1];
 #pragma unroll
     for (int T = 0; T < NT; T++) {
@@ -822,17 +870,28 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     M.stride = WM ? J.wm.dst_stride : 0;
     M.ys1 = ys1;
     M.vec = WM && c + 4 <= W && (((size_t)M.dst | (size_t)M.stride) & 15) == 0;
-    const bool edge = c + 4 > W; // at most one V thread per row holds a partial or empty pixel group
     const uint8_t *grow = J.src.p0 + (size_t)ys0 * stride;
     VCursor C{0, 1u, 0};
     int rs = 0;
     uint32_t rph = 0;
 
     auto acquire = [&]() { if (TMA) mbar_wait(&sm.full[rs], rph); };
-    auto release = [&]() {
+    // Consumer-driven refill: the last of the four V warps to finish a stage re-arms it
+    // with the group STREAM_STAGES ahead.  No producer warp, no polling.
+    auto release = [&](int group) {
         if (TMA) {
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&sm.empty[rs]);
+            if ((tid & 31) == 0) {
+                __threadfence_block();
+                if (atomicAdd(&sm.released[rs], 1u) == STREAM_THREADS / 32 - 1) {
+                    sm.released[rs] = 0;
+                    __threadfence_block();
+                    if (group + STREAM_STAGES < ngroups) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        refill(group + STREAM_STAGES, rs);
+                    }
+                }
+            }
             if (++rs == STREAM_STAGES) { rs = 0; rph ^= 1; }
         }
     };
@@ -842,10 +901,10 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     for (; g < ngroups; g++) {
         const int nr = min(STREAM_GROUP, yend - ys0 - g * STREAM_GROUP);
         acquire();
-        kres = v_group<NT, WM, TMA, false>(S, sm, C, M, rs, 0, nr, ys0 + g * STREAM_GROUP, ys0, tid, c, W, edge,
+        kres = v_group<NT, WM, TMA, false>(S, sm, C, M, rs, 0, nr, ys0 + g * STREAM_GROUP, tid, c, W,
                                            grow + (size_t)g * STREAM_GROUP * stride, stride);
         if (kres >= 0) break;
-        release();
+        release(g);
     }
     // phase 2: per-pixel alpha lanes, seeded from the scalar chains
     if (NT > 0 && kres >= 0) {
@@ -856,10 +915,10 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
         for (; g < ngroups; g++) {
             const int nr = min(STREAM_GROUP, yend - ys0 - g * STREAM_GROUP);
             if (kres < 0) acquire();
-            v_group<NT, WM, TMA, true>(S, sm, C, M, rs, kres < 0 ? 0 : kres, nr, ys0 + g * STREAM_GROUP, ys0, tid, c, W,
-                                       edge, grow + (size_t)g * STREAM_GROUP * stride, stride);
+            v_group<NT, WM, TMA, true>(S, sm, C, M, rs, kres < 0 ? 0 : kres, nr, ys0 + g * STREAM_GROUP, tid, c, W,
+                                       grow + (size_t)g * STREAM_GROUP * stride, stride);
             kres = -1;
-            release();
+            release(g);
         }
     }
 }
@@ -911,7 +970,7 @@ cudaError_t launch_exact_tiles(const ExactJob *jobs, const ExactItem *items, int
 cudaError_t launch_exact_fix(const ExactJob *jobs, int n_jobs, FixList fix, cudaStream_t st)
 {
     if (!fix.capacity || n_jobs <= 0) return cudaSuccess;
-    k_exact_fix<<<148 * 4, FIX_THREADS, 0, st>>>(jobs, n_jobs, fix);
+    k_exact_fix<<<148 * 16, FIX_THREADS, 0, st>>>(jobs, n_jobs, fix); // 64 resident warps per SM hide the fp64/LDG latency
     return cudaGetLastError();
 }
 

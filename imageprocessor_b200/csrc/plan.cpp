@@ -158,8 +158,8 @@ static bool build_target(StreamGeom &g, int ti, const StreamTargetSpec &s, doubl
     if (oy != s.dh) return false;
 
     // |fp32 - exact| <= (taps_x + taps_y + 3) units of 1/256 of a 16-bit step
-    // (DESIGN.md "certified fp32"); 25 % margin on top.
-    t.fix_d = (int32_t)std::ceil(1.25 * (double)(ax.max_taps + ay.max_taps + 4));
+    // (DESIGN.md "certified fp32"); +3 units of margin on top.
+    t.fix_d = ax.max_taps + ay.max_taps + 6;
     return true;
 }
 
