@@ -350,7 +350,13 @@ def main():
     # ---- end to end through the C ABI with pinned host buffers
     e2e = None
     if not args.no_e2e:
-        n_slots = min(env_int("IPG_BENCH_HOST_SLOTS", 24), n_img)
+        # a separate context tuned for the PCIe-bound path: smaller batches, more lanes, so
+        # the H2D of one batch overlaps the D2H of another
+        eng.close()
+        eng = ip.Engine(devices=[local_rank], precision=ip.PRECISION_EXACT, lanes_per_device=4,
+                        max_batch=env_int("IPG_BENCH_E2E_BATCH", 8), batch_window_us=100)
+        ctx = eng._ctx
+        n_slots = min(env_int("IPG_BENCH_HOST_SLOTS", 64), n_img)
         src_bytes = W_IMG * H_IMG * 4
         pins = []
         h_descs, h_ops = [], []

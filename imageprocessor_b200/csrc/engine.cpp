@@ -18,6 +18,8 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -230,8 +232,9 @@ struct Batch {
 struct Lane {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t begin = nullptr; // before the batch's first H2D
-    cudaEvent_t done = nullptr;  // after its last D2H
+    cudaEvent_t begin = nullptr;    // before the batch's first H2D (upload stream)
+    cudaEvent_t uploaded = nullptr; // after its last H2D (upload stream)
+    cudaEvent_t done = nullptr;     // after its last D2H (download stream)
     uint8_t *arena = nullptr;
     size_t arena_bytes = 0;
     uint8_t *param_host = nullptr; // pinned
@@ -254,7 +257,12 @@ struct Device {
     std::thread batcher, completer;
     StagingPool staging;
     // device-time spans since the last ipg_reset_stats, in ms after `epoch`
+    // One upload and one download stream per device, shared by the lanes in batch order:
+    // with a copy stream per lane the driver maps several lanes onto one copy engine and an
+    // H2D queues behind another lane's D2H; two dedicated streams always run both directions.
+    cudaStream_t up = nullptr, down = nullptr;
     cudaEvent_t epoch = nullptr;
+    cudaEvent_t last_compute = nullptr; // end-of-kernels event of the most recent batch (owned by its lane)
     double k_first = 1e300, k_last = -1, b_first = 1e300, b_last = -1;
 };
 
@@ -266,6 +274,7 @@ struct Ctx {
     std::mutex tmu;
     std::unordered_map<uint64_t, TicketP> tickets;
     PinnedRegistry pinned;
+    bool trace = false; // IPG_TRACE=1: per-batch device timeline on stderr
     // stats
     std::atomic<uint64_t> s_done{0}, s_batches{0}, s_kernels{0}, s_h2d{0}, s_d2h{0}, s_fix{0}, s_fallback{0}, s_staged{0};
     std::mutex smu;
@@ -348,11 +357,11 @@ static size_t ticket_device_bytes(const Ticket &t)
         for (int p = 0; p < plane_count(t.src.layout); p++) {
             int wb, ph;
             plane_dims(t.src.layout, p, t.src.width, t.src.height, &wb, &ph);
-            n += align_up((size_t)wb, 256) * (size_t)ph + 256;
+            n += (align_up((size_t)wb, 256) + 256) * (size_t)ph + 256;
         }
     }
     for (auto &op : t.ops) {
-        if (op.dst_mem == IPG_MEM_HOST) n += align_up((size_t)std::max(op.dw, 0) * 4, 256) * (size_t)std::max(op.dh, 0) + 256;
+        if (op.dst_mem == IPG_MEM_HOST) n += (align_up((size_t)std::max(op.dw, 0) * 4, 256) + 256) * (size_t)std::max(op.dh, 0) + 256;
         for (auto &g : op.glyphs) n += align_up(g.mask.size(), 256) + 256;
         n += 4096;
     }
@@ -363,8 +372,10 @@ static size_t ticket_device_bytes(const Ticket &t)
 static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
 {
     IPG_CU(cudaSetDevice(d.cuda_id));
-    cudaStream_t st = L.st;
-    IPG_CU(cudaEventRecord(L.begin, st));
+    cudaStream_t st = L.st;       // kernels
+    cudaStream_t up = d.up;       // host -> device
+    cudaStream_t down = d.down;   // device -> host
+    IPG_CU(cudaEventRecord(L.begin, up));
     Arena arena{L.arena, L.arena_bytes};
     uint8_t *blob_dev = arena.take(L.param_cap, 256);
     if (!blob_dev) throw std::runtime_error("device arena smaller than the parameter blob");
@@ -407,12 +418,17 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 dp[p] = (const uint8_t *)t.src.plane[p];
                 ds[p] = t.src.stride[p];
             } else {
-                size_t pitch = align_up((size_t)wb, 256);
-                uint8_t *dv = arena.take(pitch * (size_t)ph);
-                if (!dv) throw std::runtime_error("device arena exhausted (source)");
                 const void *hp = t.src_stage[p] ? (const void *)t.src_stage[p] : t.src.plane[p];
                 size_t hs = t.src_stage[p] ? (size_t)wb : (size_t)t.src.stride[p];
-                IPG_CU(cudaMemcpy2DAsync(dv, pitch, hp, hs, (size_t)wb, (size_t)ph, cudaMemcpyHostToDevice, st));
+                // keep the host stride as device pitch when rows stay 16-byte aligned: one linear DMA
+                const bool linear = (hs % 16) == 0 && hs < (size_t)wb + 256;
+                size_t pitch = linear ? hs : align_up((size_t)wb, 256);
+                uint8_t *dv = arena.take(pitch * (size_t)ph);
+                if (!dv) throw std::runtime_error("device arena exhausted (source)");
+                if (linear)
+                    IPG_CU(cudaMemcpyAsync(dv, hp, hs * (size_t)(ph - 1) + (size_t)wb, cudaMemcpyHostToDevice, up));
+                else
+                    IPG_CU(cudaMemcpy2DAsync(dv, pitch, hp, hs, (size_t)wb, (size_t)ph, cudaMemcpyHostToDevice, up));
                 B.h2d += (uint64_t)wb * (uint64_t)ph;
                 dp[p] = dv;
                 ds[p] = (int)pitch;
@@ -429,12 +445,13 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 op.dev_out = (uint8_t *)op.dst;
                 op.dev_pitch = (size_t)op.dst_stride;
             } else {
-                size_t pitch = align_up((size_t)op.dw * 4, 256);
+                void *hp = op.stage ? (void *)op.stage : op.dst;
+                size_t hs = op.stage ? (size_t)op.dw * 4 : (size_t)op.dst_stride;
+                const bool linear = (hs % 16) == 0 && hs < (size_t)op.dw * 4 + 256;
+                size_t pitch = linear ? hs : align_up((size_t)op.dw * 4, 256);
                 op.dev_out = arena.take(pitch * (size_t)op.dh);
                 if (!op.dev_out) throw std::runtime_error("device arena exhausted (destination)");
                 op.dev_pitch = pitch;
-                void *hp = op.stage ? (void *)op.stage : op.dst;
-                size_t hs = op.stage ? (size_t)op.dw * 4 : (size_t)op.dst_stride;
                 readbacks.push_back({op.dev_out, pitch, hp, hs, (size_t)op.dw * 4, op.dh});
             }
         }
@@ -618,10 +635,15 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     const WatermarkD *d_blends = blob.dptr<const WatermarkD>(blob.put(blends.data(), blends.size() * sizeof(WatermarkD), 16));
     const BlendItem *d_bitems = blob.dptr<const BlendItem>(blob.put(bitems.data(), bitems.size() * sizeof(BlendItem), 16));
     if (blob.overflow) throw std::runtime_error("parameter blob overflow (batch too heterogeneous); lower max_batch");
-    IPG_CU(cudaMemcpyAsync(blob_dev, L.param_host, blob.off, cudaMemcpyHostToDevice, st));
+    IPG_CU(cudaMemcpyAsync(blob_dev, L.param_host, blob.off, cudaMemcpyHostToDevice, up));
     B.h2d += blob.off;
+    IPG_CU(cudaEventRecord(L.uploaded, up));
+    IPG_CU(cudaStreamWaitEvent(st, L.uploaded, 0));
 
-    // ---- kernels
+    // ---- kernels.  Compute sections of different lanes run one after another (each kernel
+    // already fills the GPU; overlapping them only makes them evict each other), while the
+    // copies of the other lanes overlap with them.
+    if (d.last_compute) IPG_CU(cudaStreamWaitEvent(st, d.last_compute, 0));
     IPG_CU(cudaEventRecord(L.ev[0], st));
     if (!sitems.empty()) {
         IPG_CU(launch_stream(d_sjobs, d_sitems, (int)sitems.size(), max_nt, any_wm, all_tma, fix, st));
@@ -646,14 +668,19 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
         B.n_kernels++;
     }
     IPG_CU(cudaEventRecord(L.ev[3], st));
+    d.last_compute = L.ev[3];
 
     // ---- read back
-    if (B.has_fix) IPG_CU(cudaMemcpyAsync(L.fix_count_host, fix.count, 4, cudaMemcpyDeviceToHost, st));
+    IPG_CU(cudaStreamWaitEvent(down, L.ev[3], 0));
+    if (B.has_fix) IPG_CU(cudaMemcpyAsync(L.fix_count_host, fix.count, 4, cudaMemcpyDeviceToHost, down));
     for (auto &r : readbacks) {
-        IPG_CU(cudaMemcpy2DAsync(r.host, r.hstride, r.dev, r.pitch, r.row_bytes, (size_t)r.rows, cudaMemcpyDeviceToHost, st));
+        if (r.pitch == r.hstride)
+            IPG_CU(cudaMemcpyAsync(r.host, r.dev, r.pitch * (size_t)(r.rows - 1) + r.row_bytes, cudaMemcpyDeviceToHost, down));
+        else
+            IPG_CU(cudaMemcpy2DAsync(r.host, r.hstride, r.dev, r.pitch, r.row_bytes, (size_t)r.rows, cudaMemcpyDeviceToHost, down));
         B.d2h += (uint64_t)r.row_bytes * (uint64_t)r.rows;
     }
-    IPG_CU(cudaEventRecord(L.done, st));
+    IPG_CU(cudaEventRecord(L.done, down));
 }
 
 static void finish_ticket(Ctx &c, Device &d, const TicketP &t, int status, const std::string &err)
@@ -744,7 +771,7 @@ static void completer_main(Ctx *c, Device *d)
         int status = IPG_OK;
         std::string err;
         if (B->failed) {
-            cudaStreamSynchronize(L.st);
+            cudaDeviceSynchronize();
             status = IPG_ERR_CUDA;
             err = B->err;
             if (err.find("arena") != std::string::npos || err.find("blob") != std::string::npos) status = IPG_ERR_NOMEM;
@@ -763,6 +790,9 @@ static void completer_main(Ctx *c, Device *d)
                 cudaEventElapsedTime(&t1, d->epoch, L.ev[0]);
                 cudaEventElapsedTime(&t2, d->epoch, L.ev[3]);
                 cudaEventElapsedTime(&t3, d->epoch, L.done);
+                if (c->trace)
+                    fprintf(stderr, "[ipg trace] dev %d lane %d tickets %zu: begin %.3f ms, kernels %.3f..%.3f ms, done %.3f ms (h2d %.1f MB, d2h %.1f MB)\n",
+                            d->index, B->lane, B->tickets.size(), t0, t1, t2, t3, B->h2d / 1e6, B->d2h / 1e6);
                 std::lock_guard<std::mutex> lk(c->smu);
                 c->s_stream_ms += a;
                 c->s_fix_ms += b;
@@ -1003,12 +1033,15 @@ static void destroy_impl(Ctx *c)
             if (L.st) cudaStreamSynchronize(L.st);
             for (auto &e : L.ev) if (e) cudaEventDestroy(e);
             if (L.begin) cudaEventDestroy(L.begin);
+            if (L.uploaded) cudaEventDestroy(L.uploaded);
             if (L.done) cudaEventDestroy(L.done);
             if (L.arena) cudaFree(L.arena);
             if (L.param_host) cudaFreeHost(L.param_host);
             if (L.fix_count_host) cudaFreeHost(L.fix_count_host);
             if (L.st) cudaStreamDestroy(L.st);
         }
+        if (d.up) { cudaStreamSynchronize(d.up); cudaStreamDestroy(d.up); }
+        if (d.down) { cudaStreamSynchronize(d.down); cudaStreamDestroy(d.down); }
         if (d.epoch) cudaEventDestroy(d.epoch);
         d.staging.destroy();
     }
@@ -1052,6 +1085,7 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
         if (k.lane_device_bytes == 0) k.lane_device_bytes = 1ull << 30;
         if (k.lane_pinned_bytes == 0) k.lane_pinned_bytes = 256ull << 20;
         c->cfg = k;
+        c->trace = getenv("IPG_TRACE") && atoi(getenv("IPG_TRACE")) != 0;
         std::vector<int> ids;
         if (device_ids && n > 0) ids.assign(device_ids, device_ids + n);
         else for (int i = 0; i < count; i++) ids.push_back(i);
@@ -1073,6 +1107,7 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
                 IPG_CU(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
                 for (auto &ev : L.ev) IPG_CU(cudaEventCreate(&ev));
                 IPG_CU(cudaEventCreate(&L.begin));
+                IPG_CU(cudaEventCreateWithFlags(&L.uploaded, cudaEventDisableTiming));
                 IPG_CU(cudaEventCreate(&L.done));
                 L.arena_bytes = (size_t)k.lane_device_bytes;
                 IPG_CU(cudaMalloc((void **)&L.arena, L.arena_bytes));
@@ -1082,6 +1117,8 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
             }
             if (!d->staging.init((size_t)k.lane_pinned_bytes * (size_t)k.lanes_per_device))
                 throw std::runtime_error("pinned staging allocation failed");
+            IPG_CU(cudaStreamCreateWithFlags(&d->up, cudaStreamNonBlocking));
+            IPG_CU(cudaStreamCreateWithFlags(&d->down, cudaStreamNonBlocking));
             IPG_CU(cudaEventCreate(&d->epoch));
             IPG_CU(cudaEventRecord(d->epoch, d->lanes[0].st));
             IPG_CU(cudaEventSynchronize(d->epoch));
