@@ -353,7 +353,9 @@ static AxisExact pack_axis(Blob &b, const AxisPlan &p)
 static size_t ticket_device_bytes(const Ticket &t)
 {
     size_t n = 0;
-    if (t.src.memspace == IPG_MEM_HOST) {
+    if (t.src.memspace == IPG_MEM_HOST ||
+        (t.src.layout == IPG_LAYOUT_RGBA8 &&
+         ((((uintptr_t)t.src.plane[0]) | (uintptr_t)t.src.stride[0] | ((uintptr_t)t.src.width * 4)) & 15))) {
         for (int p = 0; p < plane_count(t.src.layout); p++) {
             int wb, ph;
             plane_dims(t.src.layout, p, t.src.width, t.src.height, &wb, &ph);
@@ -393,7 +395,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     struct Readback { uint8_t *dev; size_t pitch; void *host; size_t hstride; size_t row_bytes; int rows; };
     std::vector<Readback> readbacks;
     int max_nt = 0;
-    bool any_wm = false, all_tma = true;
+    bool any_wm = false;
     uint64_t fix_px = 0;
     const int precision = c.cfg.precision;
 
@@ -417,6 +419,16 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
             if (t.src.memspace == IPG_MEM_DEVICE) {
                 dp[p] = (const uint8_t *)t.src.plane[p];
                 ds[p] = t.src.stride[p];
+                if (t.src.layout == IPG_LAYOUT_RGBA8 && precision != IPG_PRECISION_REFERENCE &&
+                    ((((uintptr_t)dp[p]) | (uintptr_t)ds[p] | (uintptr_t)wb) & 15)) {
+                    // k_stream moves rows with TMA bulk copies (16-byte granular): re-pitch once
+                    size_t pitch = align_up((size_t)wb, 256);
+                    uint8_t *dv = arena.take(pitch * (size_t)ph);
+                    if (!dv) throw std::runtime_error("device arena exhausted (re-pitched source)");
+                    IPG_CU(cudaMemcpy2DAsync(dv, pitch, dp[p], (size_t)ds[p], (size_t)wb, (size_t)ph, cudaMemcpyDeviceToDevice, up));
+                    dp[p] = dv;
+                    ds[p] = (int)pitch;
+                }
             } else {
                 const void *hp = t.src_stage[p] ? (const void *)t.src_stage[p] : t.src.plane[p];
                 size_t hs = t.src_stage[p] ? (size_t)wb : (size_t)t.src.stride[p];
@@ -559,6 +571,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 j.n_bands = geom->n_bands;
                 j.band_y = blob.put_vec(geom->band_y);
                 j.band_yend = blob.put_vec(geom->band_yend);
+                j.grec = blob.put_vec(geom->grec);
+                j.band_grec_off = blob.put_vec(geom->band_grec_off);
                 for (int k = 0; k < nt; k++) {
                     const StreamTargetGeom &tgm = geom->t[k];
                     StreamTarget &o = j.t[k];
@@ -586,7 +600,6 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 if (wm) j.wm = make_wm(*wm);
                 max_nt = std::max(max_nt, nt);
                 any_wm |= wm != nullptr;
-                all_tma &= (((size_t)sv.p0 | (size_t)sv.s0) & 15) == 0; // rows bulk-copyable
                 const int ji = (int)sjobs.size();
                 sjobs.push_back(j);
                 for (auto it : geom->items) {
@@ -646,7 +659,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     if (d.last_compute) IPG_CU(cudaStreamWaitEvent(st, d.last_compute, 0));
     IPG_CU(cudaEventRecord(L.ev[0], st));
     if (!sitems.empty()) {
-        IPG_CU(launch_stream(d_sjobs, d_sitems, (int)sitems.size(), max_nt, any_wm, all_tma, fix, st));
+        IPG_CU(launch_stream(d_sjobs, d_sitems, (int)sitems.size(), max_nt, any_wm, fix, st));
         B.n_kernels++;
     }
     IPG_CU(cudaEventRecord(L.ev[1], st));

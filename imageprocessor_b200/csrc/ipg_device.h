@@ -55,6 +55,21 @@ struct FixList {
 // complete after this source row and is output row `emit`.
 struct RowRec { float wa, wb; int32_t emit; int32_t pad; };
 
+// What the kernel actually consumes: the RowRecs of STREAM_GROUP consecutive source rows
+// of one target, re-expressed per accumulator SET (the two open output rows live in two
+// register sets that swap roles at every emitted row; the host resolves that parity), plus
+// the alpha sums an all-opaque image would have accumulated (so the opaque fast path does
+// no alpha arithmetic at all).  One block of n_targets GroupRecs per (band, group) rides
+// into shared memory with the group's source rows in the same TMA transaction.
+struct GroupRow { float w0, w1;    // weight of this source row for accumulator set 0 / 1
+                  float sa0, sa1; };// fmaf(255, w, .) chains of set 0 / 1 after this row (before an emit clears it)
+struct GroupRec {
+    GroupRow row[4];               // STREAM_GROUP rows
+    int32_t emit[4];               // -1, or (output row << 1 | set): the row completes that set
+    float seed0, seed1;            // the two alpha chains entering the group
+    int32_t pad[2];
+};
+
 struct StreamTarget {
     uint8_t *dst;
     int32_t dst_stride;
@@ -88,17 +103,21 @@ struct WatermarkD {
     uint32_t sr, sg, sb, sa;     // Uniform.RGBA(): c * 0x101
 };
 
-// k_stream CTA: 4 vertical-pass warps (128 threads x 4 px = one 512-column slab) and 2
-// horizontal-pass warps.  The V warps refill the TMA ring themselves (last one out).
+// k_stream CTA: 4 vertical-pass warps (128 threads x 4 px = one 512-column slab), one
+// producer warp (one elected lane drives the TMA ring: bulk loads of source rows + group
+// records, bulk stores of the watermark copy straight out of the ring) and 2
+// horizontal-pass warps.
 enum {
     STREAM_THREADS = 128, STREAM_PX = 4, STREAM_COLS = STREAM_THREADS * STREAM_PX,
     STREAM_GROUP = 4,           // source rows per ring stage / TMA barrier phase (8 KB)
-    STREAM_STAGES = 5,          // source ring depth in stages
+    STREAM_STAGES_2T = 8,       // ring depth, two-target instantiation (2 CTAs per SM)
+    STREAM_STAGES_1T = 5,       // ring depth otherwise (3 CTAs per SM)
     STREAM_XSLOTS = 3,          // vertically-filtered rows awaiting the horizontal pass (8 KB each)
+    STREAM_PTHREADS = 32,       // producer warp
     STREAM_XTHREADS = 64,
     STREAM_XREG = 3,            // outputs per X thread whose tap tables live in registers
     STREAM_XTAPS = 8,           // ... and, when every one has at most this many taps, the weights too
-    STREAM_CTA = STREAM_THREADS + STREAM_XTHREADS,
+    STREAM_CTA = STREAM_THREADS + STREAM_PTHREADS + STREAM_XTHREADS,
 };
 
 struct StreamJob {
@@ -110,6 +129,8 @@ struct StreamJob {
     int32_t check_premul;      // RGBA8 source, alpha unknown, a two_stage target exists
     const int32_t *band_y;     // [n_bands+1] owned source rows of each band
     const int32_t *band_yend;  // [n_bands]   one past the last row the band must read
+    const GroupRec *grec;      // [groups of all bands][n_targets]
+    const int32_t *band_grec_off; // [n_bands] first group of each band
     StreamTarget t[2];
     WatermarkD wm;
 };

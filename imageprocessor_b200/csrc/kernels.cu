@@ -327,31 +327,33 @@ k_blend(const WatermarkD *__restrict__ wms, const BlendItem *__restrict__ items)
 // ---------------------------------------------------------------------------------
 // k_stream: vertical-first fp32 streaming resample
 //
-// CTA = 4 consumer warps (128 threads x 4 source pixels = a 512-column slab) + 1
-// producer warp.  The CTA owns `tile_w` of the slab's columns; the rest is the right
-// halo the widest horizontal support needs.  It walks the source rows of its band
-// once, top to bottom:
+// CTA = 4 V warps (128 threads x 4 source pixels = a 512-column slab) + 1 producer warp
+// + 2 X warps.  The CTA owns `tile_w` of the slab's columns; the rest is the right halo
+// the widest horizontal support needs.  It walks the source rows of its band once, top
+// to bottom, in groups of STREAM_GROUP rows:
 //
-//   producer   one elected thread streams the slab's rows HBM -> shared memory with
-//              TMA bulk copies (cp.async.bulk, 2 KB per row) into a ring of
-//              STREAM_STAGES rows, paced by full/empty mbarriers.  This is what keeps
-//              tens of KB per SM in flight; a register prefetch of one row left the
-//              kernel latency-bound at ~1 TB/s.
-//   consumers  wait for a row, LDS.128 their 4 pixels (conflict-free), release the
-//              stage, convert bytes to fp32 once (PRMT into 2^23+b, FADD: the I2F.U8
-//              the compiler would pick runs on the quarter-rate XU pipe) and
-//              multiply-add them into the (at most) two output rows the source row
-//              contributes to, per target: a tent of half-width `scale` centred every
-//              `scale` rows covers each source row exactly twice.  The watermark copy
-//              (with its glyph blend) leaves from the same registers.
-//   emit       when a source row completes an output row (RowRec.emit) the consumers
-//              park that vertically-filtered row in shared memory (XOR-swizzled float4
-//              slots: conflict-free stores, <=2-way gathers), meet at a 128-thread
-//              named barrier, and threads 0..n_owned-1 run the horizontal gather,
-//              quantise with the reference's ftou()>>8, flag bytes too close to a
-//              quantiser step for the fp64 fix-up, and store uchar4 (coalesced).
-//
-// Source bytes cross HBM exactly once for resize + thumbnail + watermark.
+//   producer   one elected lane drives a ring of STAGES stages with TMA bulk copies
+//              (cp.async.bulk, SASS UBLKCP): per group, the rows (2 KB each) and the
+//              group's records land in one stage under one mbarrier phase.  For the
+//              watermark copy the same lane bulk-STORES the owned columns of the landed
+//              rows straight from the ring to the destination (draw.Draw(Src) of an
+//              *image.RGBA is a copy): the copy costs no SM instructions and the source
+//              crosses HBM once for resize + thumbnail + watermark.  A stage is refilled
+//              once the V warps released it (`empty` mbarrier) and its store has read it
+//              (bulk-group wait).
+//   V warps    wait for a stage, LDS.128 their 4 pixels of each of the 4 rows, convert
+//              bytes to fp32 once (PRMT into 2^23+b, FADD2: the I2F.U8 the compiler would
+//              pick runs on the quarter-rate XU pipe) and FFMA2 them into the two
+//              accumulator sets of each target: a tent of half-width `scale` centred every
+//              `scale` rows covers each source row exactly twice.  Weights arrive per SET
+//              (the host resolved which set is which open output row).  While a warp has
+//              only met opaque pixels its alpha sums are the host-computed chains in the
+//              records, so the fast path carries no alpha arithmetic.
+//   emit       when a source row completes an output row the V warps park that
+//              vertically-filtered row in shared memory (XOR-swizzled float4 slots:
+//              conflict-free stores, <=2-way gathers) and signal the X warps, which run
+//              the horizontal gather, quantise with the reference's ftou()>>8, flag bytes
+//              too close to a quantiser step for the fp64 fix-up, and store uchar4.
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ int swz(int e) { return e ^ ((e >> 3) & 7); }
 
@@ -382,23 +384,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
 }
-// Same, for roles that are not on the critical path (producer waiting for a free stage,
-// X warps waiting for a parked row): sleep between probes so the spin does not steal
-// issue slots from the V warps and the other CTAs' producers.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity)
-{
-    for (;;) {
-        uint32_t ok;
-        asm volatile(
-            "{\n"
-            ".reg .pred P1;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, P1;\n"
-            "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (ok) return;
-        __nanosleep(128);
-    }
-}
 // TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
 {
@@ -407,39 +392,25 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"r"((int)STREAM_THREADS) : "memory"); }
-
-// uint8 -> fp32 on the ALU + FMA pipes: 0x4B0000bb is 2^23 + b exactly.
-template <int K> __device__ __forceinline__ float byte_f32(uint32_t q)
+// TMA 1-D bulk copy shared -> global, tracked by the issuing thread's bulk async-group.
+__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes)
 {
-    return __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7540 + K)) - 8388608.0f;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
 }
-__device__ __forceinline__ void unpack_px(uint32_t q, float *v)
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read()
 {
-    v[0] = byte_f32<0>(q);
-    v[1] = byte_f32<1>(q);
-    v[2] = byte_f32<2>(q);
-    v[3] = byte_f32<3>(q);
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t clamp_to_alpha(uint32_t q)
 {
     uint32_t a = q >> 24;
     uint32_t r = min(q & 0xff, a), g = min((q >> 8) & 0xff, a), b = min((q >> 16) & 0xff, a);
     return r | (g << 8) | (b << 16) | (a << 24);
-}
-
-__device__ __forceinline__ uint4 load_px4(const uint8_t *row, int c, int W)
-{
-    uint4 v = make_uint4(0xff000000u, 0xff000000u, 0xff000000u, 0xff000000u); // past the edge: opaque black
-    if (c < W) {
-        const uint32_t *p = (const uint32_t *)row + c;
-        v.x = __ldg(p);
-        if (c + 1 < W) v.y = __ldg(p + 1);
-        if (c + 2 < W) v.z = __ldg(p + 2);
-        if (c + 3 < W) v.w = __ldg(p + 3);
-    }
-    return v;
 }
 
 __device__ __forceinline__ uint32_t quant16(float v, uint32_t D, uint32_t span, bool &amb)
@@ -452,12 +423,17 @@ __device__ __forceinline__ uint32_t quant16(float v, uint32_t D, uint32_t span, 
     return T >> 16;
 }
 
-struct __align__(128) StreamSmem {
-    uint4 ring[STREAM_STAGES][STREAM_GROUP][STREAM_THREADS]; // source rows, 2 KB each; a stage = STREAM_GROUP rows
+struct __align__(16) StreamStage {
+    uint4 rows[STREAM_GROUP][STREAM_THREADS]; // source rows of the slab, 2 KB each
+    GroupRec rec[2];                          // this group's records, one per target
+};
+
+template <int STAGES> struct __align__(128) StreamSmem {
+    StreamStage stage[STAGES];
     float4 rowbuf[STREAM_XSLOTS][STREAM_COLS];   // vertically filtered rows, XOR-swizzled slots
-    uint64_t full[STREAM_STAGES];                // TMA completion of a stage
+    uint64_t full[STAGES];                       // TMA completion of a stage
+    uint64_t empty[STAGES];                      // the 4 V warps are done with a stage
     uint64_t xfull[STREAM_XSLOTS], xempty[STREAM_XSLOTS];
-    uint32_t released[STREAM_STAGES];            // V warps done with a stage; the last one refills it
     int32_t xmeta[STREAM_XSLOTS][2];             // {target, output row} of each parked row
 };
 
@@ -574,22 +550,12 @@ __device__ __forceinline__ void xpass(const XTarget &x, int oy, int xt, const fl
 }
 
 // ---- V warps ---------------------------------------------------------------------
-// Per-target streaming state of one V thread (4 source pixels): two accumulator sets
-// that swap roles at every emitted row (no register shuffling).  RGB of the 4 pixels is
-// 12 floats = 6 packed pairs for FFMA2.  Alpha is materialised lazily: while a warp has
-// only met opaque pixels (alpha 255) every pixel's alpha sum is the same fmaf chain, so
-// it is carried as two warp-uniform scalars (`sa`) and the V loop runs its ALPHA=false
-// instantiation; the first non-opaque row copies the scalars into the per-pixel lanes
-// (bit-identical to having accumulated them all along) and the warp continues in the
-// ALPHA=true instantiation.
-struct VState {
+// Per-target accumulators of one V thread (4 source pixels): two sets, one per open
+// output row.  RGB of the 4 pixels is 12 floats = 6 packed pairs for FFMA2; the per-pixel
+// alpha lanes exist only in the ALPHA instantiation.
+struct VAcc {
     float2 rgb[2][6];
     float2 al[2][2];
-    float sa[2];
-    int par;            // set `par` belongs to the lowest open output row
-    const RowRec *rec;  // this band's records, indexed by row - ys0
-    int tend;           // rows >= tend contribute nothing in this (tile, band)
-    bool clamp;         // two_stage target: clamp channels to alpha on non-opaque rows
 };
 
 __device__ __forceinline__ float2 magic2(uint32_t qa, int ka, uint32_t qb, int kb)
@@ -615,13 +581,15 @@ __device__ __forceinline__ void unpack_alpha(const uint4 &c, float2 *va)
     va[1] = __fadd2_rn(magic2(c.z, 3, c.w, 3), m);
 }
 
+// Hand one completed, vertically-filtered row (accumulator set SET) to the X warps and
+// clear the set.  `sa` is the opaque alpha chain value (ALPHA=false).
 template <int SET, bool ALPHA>
-__device__ __forceinline__ void park_row(VState &S, float4 *buf, int tid)
+__device__ __forceinline__ void park_row(VAcc &S, float sa, float4 *buf, int tid)
 {
     const int base = (tid * 4) & ~7, key = (tid >> 1) & 7, lo = (tid & 1) * 4; // swz(4*tid + j)
     const float2 *g = S.rgb[SET];
-    const float a0 = ALPHA ? S.al[SET][0].x : S.sa[SET], a1 = ALPHA ? S.al[SET][0].y : S.sa[SET];
-    const float a2 = ALPHA ? S.al[SET][1].x : S.sa[SET], a3 = ALPHA ? S.al[SET][1].y : S.sa[SET];
+    const float a0 = ALPHA ? S.al[SET][0].x : sa, a1 = ALPHA ? S.al[SET][0].y : sa;
+    const float a2 = ALPHA ? S.al[SET][1].x : sa, a3 = ALPHA ? S.al[SET][1].y : sa;
     buf[base | ((lo + 0) ^ key)] = make_float4(g[0].x, g[0].y, g[1].x, a0);
     buf[base | ((lo + 1) ^ key)] = make_float4(g[1].y, g[2].x, g[2].y, a1);
     buf[base | ((lo + 2) ^ key)] = make_float4(g[3].x, g[3].y, g[4].x, a2);
@@ -629,7 +597,6 @@ __device__ __forceinline__ void park_row(VState &S, float4 *buf, int tid)
 #pragma unroll
     for (int i = 0; i < 6; i++) S.rgb[SET][i] = make_float2(0.f, 0.f);
     if (ALPHA) S.al[SET][0] = S.al[SET][1] = make_float2(0.f, 0.f);
-    else S.sa[SET] = 0.f;
 }
 
 struct VCursor {  // parked-row slot position of a V warp
@@ -637,135 +604,72 @@ struct VCursor {  // parked-row slot position of a V warp
     int emits;
 };
 
-// Vertical multiply-adds of one source row into every target, and the hand-off of
-// completed output rows to the X warp.  rr[T] is this row's record (prefetched).
-template <int NT, bool ALPHA>
-__device__ __forceinline__ void v_row(VState *S, const uint4 &cur, const int4 *rr, int ys, int tid, StreamSmem &sm,
-                                      VCursor &C)
+// The four source rows of one ring stage into every active target.
+template <int NT, bool ALPHA, typename SM>
+__device__ __forceinline__ void v_group(VAcc *S, const uint4 *px, const StreamStage &stg, SM &sm, VCursor &C,
+                                        const bool *act, const bool *clampt, int tid)
 {
-    float2 vp[6], va[2];
-    unpack_rgb(cur, vp);
-    if (ALPHA) unpack_alpha(cur, va);
 #pragma unroll
-    for (int T = 0; T < NT; T++) {
-        if (ys >= S[T].tend) continue; // CTA-uniform
-        const float wa = __int_as_float(rr[T].x), wb = __int_as_float(rr[T].y);
-        // keep the record's unused 4th word allocated until here: if the compiler recycled that
-        // register early, every row would stall on a write-after-write against the in-flight LDG.128
-        asm volatile("" ::"r"(rr[T].w));
-        const float w0 = S[T].par ? wb : wa, w1 = S[T].par ? wa : wb;
-        const float2 w00 = make_float2(w0, w0), w11 = make_float2(w1, w1);
-        if (!ALPHA) {
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                S[T].rgb[0][i] = __ffma2_rn(vp[i], w00, S[T].rgb[0][i]);
-                S[T].rgb[1][i] = __ffma2_rn(vp[i], w11, S[T].rgb[1][i]);
-            }
-            S[T].sa[0] = fmaf(255.0f, w0, S[T].sa[0]);
-            S[T].sa[1] = fmaf(255.0f, w1, S[T].sa[1]);
-        } else {
-            float2 up[6];
-            if (S[T].clamp) {
-                // cropAndResize quantises to premultiplied RGBA8 first: channels clamp to alpha
-                const uint4 cc = make_uint4(clamp_to_alpha(cur.x), clamp_to_alpha(cur.y), clamp_to_alpha(cur.z),
-                                            clamp_to_alpha(cur.w));
-                unpack_rgb(cc, up);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 6; i++) up[i] = vp[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                S[T].rgb[0][i] = __ffma2_rn(up[i], w00, S[T].rgb[0][i]);
-                S[T].rgb[1][i] = __ffma2_rn(up[i], w11, S[T].rgb[1][i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                S[T].al[0][i] = __ffma2_rn(va[i], w00, S[T].al[0][i]);
-                S[T].al[1][i] = __ffma2_rn(va[i], w11, S[T].al[1][i]);
-            }
-        }
-        if (rr[T].z >= 0) { // CTA-uniform: this source row completes output row rr.z
-            if (C.emits >= STREAM_XSLOTS) mbar_wait(&sm.xempty[C.xs], C.xph);
-            if (S[T].par == 0) park_row<0, ALPHA>(S[T], sm.rowbuf[C.xs], tid);
-            else               park_row<1, ALPHA>(S[T], sm.rowbuf[C.xs], tid);
-            S[T].par ^= 1;
-            if (tid == 0) { sm.xmeta[C.xs][0] = T; sm.xmeta[C.xs][1] = rr[T].z; }
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&sm.xfull[C.xs]);
-            C.emits++;
-            if (++C.xs == STREAM_XSLOTS) { C.xs = 0; C.xph ^= 1; }
-        }
-    }
-}
-
-// What a V thread needs for the fused watermark copy, held in registers (the copy's
-// global stores would otherwise force the job struct to be re-read every row).
-struct VWm {
-    uint8_t *dst;
-    int stride, ys1;
-    bool on, vec;
-};
-
-// Rows k0..nr-1 of one ring stage (or, without TMA, of global memory).  ALPHA=false is
-// the all-opaque-so-far instantiation: it returns the index of the first row holding a
-// non-opaque pixel (that row is not processed), or -1 when the group is done.
-template <int NT, bool WM, bool TMA, bool ALPHA>
-__device__ __forceinline__ int v_group(VState *S, StreamSmem &sm, VCursor &C, const VWm &M, int stage, int k0, int nr,
-                                       int ysg, int tid, int c, int W, const uint8_t *grow, int stride)
-{
-    uint4 cur = make_uint4(0, 0, 0, 0);
-    int4 rr[NT > 0 ? NT : 1];
-    if (k0 < nr) {
-        cur = TMA ? sm.ring[stage][k0][tid] : load_px4(grow + (size_t)k0 * stride, c, W);
-#pragma unroll
-        for (int T = 0; T < NT; T++)
-            rr[T] = (ysg + k0 < S[T].tend) ? __ldg((const int4 *)S[T].rec) : make_int4(0, 0, -1, 0);
-    }
-#pragma unroll 1
-    for (int k = k0; k < nr; k++) {
-        const int ys = ysg + k;
-        if (NT > 0 && !ALPHA) {
-            const uint32_t m = min(min(cur.x, cur.y), min(cur.z, cur.w));
-            if (__any_sync(0xffffffffu, m < 0xff000000u)) return k;
-        }
-        // software pipeline: next row's pixels and records are requested before this row's math
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        int4 rn[NT > 0 ? NT : 1];
+    for (int k = 0; k < STREAM_GROUP; k++) {
+        float2 vp[6], va[2];
+        unpack_rgb(px[k], vp);
+        if (ALPHA) unpack_alpha(px[k], va);
 #pragma unroll
         for (int T = 0; T < NT; T++) {
-            if (ys < S[T].tend) S[T].rec++;
-            rn[T] = (ys + 1 < S[T].tend) ? __ldg((const int4 *)S[T].rec) : make_int4(0, 0, -1, 0);
-        }
-        if (k + 1 < nr) nxt = TMA ? sm.ring[stage][k + 1][tid] : load_px4(grow + (size_t)(k + 1) * stride, c, W);
-        if (WM && M.on && ys < M.ys1) {
-            const uint4 o = cur; // draw.Draw(Src) of an *image.RGBA is a copy; k_blend adds the glyphs
-            uint8_t *d = M.dst + (size_t)ys * M.stride + (size_t)c * 4;
-            if (M.vec) {
-                __stcs((uint4 *)d, o);
+            if (!act[T]) continue; // CTA-uniform
+            const float4 r = *reinterpret_cast<const float4 *>(&stg.rec[T].row[k]); // LDS.128 broadcast
+            const float2 w00 = make_float2(r.x, r.x), w11 = make_float2(r.y, r.y);
+            if (!ALPHA) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    S[T].rgb[0][i] = __ffma2_rn(vp[i], w00, S[T].rgb[0][i]);
+                    S[T].rgb[1][i] = __ffma2_rn(vp[i], w11, S[T].rgb[1][i]);
+                }
             } else {
-                ((uint32_t *)d)[0] = o.x;
-                if (c + 1 < W) ((uint32_t *)d)[1] = o.y;
-                if (c + 2 < W) ((uint32_t *)d)[2] = o.z;
-                if (c + 3 < W) ((uint32_t *)d)[3] = o.w;
+                float2 up[6];
+                if (clampt[T]) {
+                    // cropAndResize quantises to premultiplied RGBA8 first: channels clamp to alpha
+                    const uint4 cc = make_uint4(clamp_to_alpha(px[k].x), clamp_to_alpha(px[k].y),
+                                                clamp_to_alpha(px[k].z), clamp_to_alpha(px[k].w));
+                    unpack_rgb(cc, up);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 6; i++) up[i] = vp[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    S[T].rgb[0][i] = __ffma2_rn(up[i], w00, S[T].rgb[0][i]);
+                    S[T].rgb[1][i] = __ffma2_rn(up[i], w11, S[T].rgb[1][i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    S[T].al[0][i] = __ffma2_rn(va[i], w00, S[T].al[0][i]);
+                    S[T].al[1][i] = __ffma2_rn(va[i], w11, S[T].al[1][i]);
+                }
+            }
+            const int e = stg.rec[T].emit[k];
+            if (e >= 0) { // CTA-uniform: this source row completes output row e>>1, held in set e&1
+                if (C.emits >= STREAM_XSLOTS) mbar_wait(&sm.xempty[C.xs], C.xph);
+                if (e & 1) park_row<1, ALPHA>(S[T], r.w, sm.rowbuf[C.xs], tid);
+                else       park_row<0, ALPHA>(S[T], r.z, sm.rowbuf[C.xs], tid);
+                if (tid == 0) { sm.xmeta[C.xs][0] = T; sm.xmeta[C.xs][1] = e >> 1; }
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&sm.xfull[C.xs]);
+                C.emits++;
+                if (++C.xs == STREAM_XSLOTS) { C.xs = 0; C.xph ^= 1; }
             }
         }
-        if (NT > 0) v_row<NT, ALPHA>(S, cur, rr, ys, tid, sm, C);
-        cur = nxt;
-#pragma unroll
-        for (int T = 0; T < NT; T++) rr[T] = rn[T];
     }
-    return -1;
 }
 
-// TMA: rows are 16-byte aligned (base and stride), so they can be bulk-copied.
-// Otherwise (caller-provided device memory with an odd stride) the V warps LDG.
-template <int NT, bool WM, bool TMA>
+template <int NT, bool WM>
 __global__ void __launch_bounds__(STREAM_CTA, (NT == 2 ? 2 : 3))
 k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ items, FixList fix)
 {
+    constexpr int STAGES = NT == 2 ? STREAM_STAGES_2T : STREAM_STAGES_1T;
+    using Smem = StreamSmem<STAGES>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    StreamSmem &sm = *reinterpret_cast<StreamSmem *>(smem_raw);
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
     const StreamItem it = items[blockIdx.x];
     const StreamJob &J = jobs[it.job];
@@ -780,20 +684,15 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     const int tid = (int)threadIdx.x;
     const int c = cx0 + tid * STREAM_PX;
     const uint32_t row_bytes = (uint32_t)(((min(STREAM_COLS, W - cx0) * 4) + 15) & ~15);
-    const uint8_t *gsrc = J.src.p0 + (size_t)ys0 * stride + (size_t)cx0 * 4;
-
-    // One TMA transaction group: STREAM_GROUP rows (8 KB) HBM -> ring stage, one barrier phase.
-    auto refill = [&](int group, int stage) {
-        const int nr = min(STREAM_GROUP, yend - ys0 - group * STREAM_GROUP);
-        mbar_arrive_expect_tx(&sm.full[stage], row_bytes * (uint32_t)nr);
-        const uint8_t *g = gsrc + (size_t)group * STREAM_GROUP * stride;
-        for (int k = 0; k < nr; k++, g += stride) tma_load_1d(&sm.ring[stage][k][0], g, row_bytes, &sm.full[stage]);
-    };
+    // watermark copy: owned columns of the band's own rows; by TMA when 16-byte granular
+    const bool has_wm = WM && J.has_wm;
+    const uint32_t wm_bytes = (uint32_t)(min(J.tile_w, W - cx0) * 4);
+    const bool wm_tma = has_wm && (wm_bytes & 15) == 0 && ((((size_t)J.wm.dst) | (size_t)J.wm.dst_stride) & 15) == 0;
 
     if (tid == 0) {
-        for (int s = 0; s < STREAM_STAGES; s++) {
+        for (int s = 0; s < STAGES; s++) {
             mbar_init(&sm.full[s], 1);
-            sm.released[s] = 0;
+            mbar_init(&sm.empty[s], STREAM_THREADS / 32);
         }
         for (int s = 0; s < STREAM_XSLOTS; s++) {
             mbar_init(&sm.xfull[s], STREAM_THREADS / 32);
@@ -803,21 +702,61 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     }
     // slab columns past the image edge are never written by TMA: park opaque black there
     // so they neither look transparent nor feed anything (no output taps them)
-    if (TMA && tid < STREAM_THREADS && c >= W) {
-        for (int s = 0; s < STREAM_STAGES; s++)
+    if (tid < STREAM_THREADS && c >= W) {
+        for (int s = 0; s < STAGES; s++)
             for (int k = 0; k < STREAM_GROUP; k++)
-                sm.ring[s][k][tid] = make_uint4(0xff000000u, 0xff000000u, 0xff000000u, 0xff000000u);
+                sm.stage[s].rows[k][tid] = make_uint4(0xff000000u, 0xff000000u, 0xff000000u, 0xff000000u);
     }
     __syncthreads();
-    if (TMA && tid == 0) {
+
+    if (warp == STREAM_THREADS / 32) {
+        // ===== producer: one lane drives the ring =====
+        if ((tid & 31) != 0) return;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int g = 0; g < min(STREAM_STAGES, ngroups); g++) refill(g, g); // prologue: fill the ring
+        const uint8_t *gsrc = J.src.p0 + (size_t)ys0 * stride + (size_t)cx0 * 4;
+        const uint8_t *grec = (const uint8_t *)(J.grec + (size_t)__ldg(J.band_grec_off + band) * (size_t)J.n_targets);
+        const uint32_t rec_bytes = (uint32_t)(NT > 0 ? J.n_targets * (int)sizeof(GroupRec) : 0);
+        uint8_t *wdst = has_wm ? J.wm.dst + (size_t)ys0 * J.wm.dst_stride + (size_t)cx0 * 4 : nullptr;
+        const int wm_stride = has_wm ? J.wm.dst_stride : 0;
+        auto refill = [&](int group, int stage) {
+            const int nr = min(STREAM_GROUP, yend - ys0 - group * STREAM_GROUP);
+            StreamStage &st = sm.stage[stage];
+            mbar_arrive_expect_tx(&sm.full[stage], row_bytes * (uint32_t)nr + rec_bytes);
+            const uint8_t *g = gsrc + (size_t)group * STREAM_GROUP * stride;
+            for (int k = 0; k < nr; k++, g += stride) tma_load_1d(&st.rows[k][0], g, row_bytes, &sm.full[stage]);
+            if (rec_bytes) tma_load_1d(&st.rec[0], grec + (size_t)group * rec_bytes, rec_bytes, &sm.full[stage]);
+        };
+        for (int g = 0; g < min(STAGES, ngroups); g++) refill(g, g); // prologue: fill the ring
+        int s = 0, sp = 0;        // stage of group g / of group g-1
+        uint32_t ph = 0, php = 0; // their phases
+        for (int g = 0; g < ngroups; g++) {
+            if (wm_tma) {
+                const int nw = min(STREAM_GROUP, ys1 - ys0 - g * STREAM_GROUP); // rows of this group the band owns
+                if (nw > 0) {
+                    mbar_wait(&sm.full[s], ph);
+                    uint8_t *d = wdst + (size_t)g * STREAM_GROUP * wm_stride;
+                    for (int k = 0; k < nw; k++, d += wm_stride) tma_store_1d(d, &sm.stage[s].rows[k][0], wm_bytes);
+                }
+                tma_store_commit(); // one (possibly empty) bulk group per ring group keeps the wait count uniform
+            }
+            if (g >= 1) {
+                if (g - 1 + STAGES < ngroups) {
+                    mbar_wait(&sm.empty[sp], php);            // V warps are done with group g-1
+                    if (wm_tma) tma_store_wait_read<1>();     // ... and so is its store (all but group g's)
+                    refill(g - 1 + STAGES, sp);
+                }
+                if (++sp == STAGES) { sp = 0; php ^= 1; }
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        if (wm_tma) tma_store_wait_all(); // shared memory must outlive the reads
+        return;
     }
 
-    if (warp >= STREAM_THREADS / 32) {
+    if (warp > STREAM_THREADS / 32) {
         // ===== X warps: horizontal pass + quantise + store of every parked row =====
         if (NT == 0) return;
-        const int xt = tid - STREAM_THREADS;
+        const int xt = tid - STREAM_THREADS - STREAM_PTHREADS;
         XTarget X0, X1;
         int total = 0;
         X0.n_own = X1.n_own = 0;
@@ -844,7 +783,8 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     }
 
     // ===== V warps: vertical pass =====
-    VState S[NT > 0 ? NT : 1];
+    VAcc S[NT > 0 ? NT : 1];
+    bool act[NT > 0 ? NT : 1], clampt[NT > 0 ? NT : 1];
 #pragma unroll
     for (int T = 0; T < NT; T++) {
 #pragma unroll
@@ -852,112 +792,101 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
 #pragma unroll
             for (int i = 0; i < 6; i++) S[T].rgb[k][i] = make_float2(0.f, 0.f);
             S[T].al[k][0] = S[T].al[k][1] = make_float2(0.f, 0.f);
-            S[T].sa[k] = 0.f;
         }
-        S[T].par = 0;
-        S[T].rec = nullptr;
-        S[T].tend = ys0;
-        S[T].clamp = false;
-        if (T < J.n_targets && __ldg(J.t[T].tile_ox + tile + 1) > __ldg(J.t[T].tile_ox + tile)) {
-            S[T].rec = J.t[T].rows + __ldg(J.t[T].band_rec_off + band);
-            S[T].tend = __ldg(J.t[T].band_tend + band);
-            S[T].clamp = J.t[T].two_stage != 0;
-        }
+        act[T] = T < J.n_targets && __ldg(J.t[T].tile_ox + tile + 1) > __ldg(J.t[T].tile_ox + tile) &&
+                 __ldg(J.t[T].band_tend + band) > ys0;
+        clampt[T] = T < J.n_targets && J.t[T].two_stage != 0;
     }
-    VWm M;
-    M.on = WM && J.has_wm && tid * STREAM_PX < J.tile_w && c < W;
-    M.dst = WM ? J.wm.dst : nullptr;
-    M.stride = WM ? J.wm.dst_stride : 0;
-    M.ys1 = ys1;
-    M.vec = WM && c + 4 <= W && (((size_t)M.dst | (size_t)M.stride) & 15) == 0;
-    const uint8_t *grow = J.src.p0 + (size_t)ys0 * stride;
+    // fallback watermark copy by the V warps when the rows are not 16-byte granular
+    const bool wm_v = has_wm && !wm_tma && tid * STREAM_PX < J.tile_w && c < W;
+    uint8_t *wm_dst = has_wm ? J.wm.dst : nullptr;
+    const int wm_stride = has_wm ? J.wm.dst_stride : 0;
     VCursor C{0, 1u, 0};
     int rs = 0;
     uint32_t rph = 0;
+    bool alpha_mode = false;
 
-    auto acquire = [&]() { if (TMA) mbar_wait(&sm.full[rs], rph); };
-    // Consumer-driven refill: the last of the four V warps to finish a stage re-arms it
-    // with the group STREAM_STAGES ahead.  No producer warp, no polling.
-    auto release = [&](int group) {
-        if (TMA) {
-            __syncwarp();
-            if ((tid & 31) == 0) {
-                __threadfence_block();
-                if (atomicAdd(&sm.released[rs], 1u) == STREAM_THREADS / 32 - 1) {
-                    sm.released[rs] = 0;
-                    __threadfence_block();
-                    if (group + STREAM_STAGES < ngroups) {
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        refill(group + STREAM_STAGES, rs);
+    for (int g = 0; g < ngroups; g++) {
+        mbar_wait(&sm.full[rs], rph);
+        const StreamStage &stg = sm.stage[rs];
+        uint4 px[STREAM_GROUP];
+#pragma unroll
+        for (int k = 0; k < STREAM_GROUP; k++) px[k] = stg.rows[k][tid];
+        const int nr = yend - ys0 - g * STREAM_GROUP;
+        if (nr < STREAM_GROUP) { // band tail: rows past the end are stale ring contents (their weights are 0)
+#pragma unroll
+            for (int k = 1; k < STREAM_GROUP; k++)
+                if (k >= nr) px[k] = make_uint4(0xff000000u, 0xff000000u, 0xff000000u, 0xff000000u);
+        }
+        if (WM && wm_v) {
+#pragma unroll
+            for (int k = 0; k < STREAM_GROUP; k++) {
+                const int ys = ys0 + g * STREAM_GROUP + k;
+                if (ys < ys1) {
+                    uint32_t *d = (uint32_t *)(wm_dst + (size_t)ys * wm_stride + (size_t)c * 4);
+                    d[0] = px[k].x;
+                    if (c + 1 < W) d[1] = px[k].y;
+                    if (c + 2 < W) d[2] = px[k].z;
+                    if (c + 3 < W) d[3] = px[k].w;
+                }
+            }
+        }
+        if (NT > 0) {
+            if (!alpha_mode) {
+                uint32_t m = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < STREAM_GROUP; k++) m = min(m, min(min(px[k].x, px[k].y), min(px[k].z, px[k].w)));
+                if (__any_sync(0xffffffffu, m < 0xff000000u)) {
+                    // first non-opaque pixel this warp meets: materialise the per-pixel alpha lanes
+                    // from the chains entering this group (bit-identical to having carried them)
+                    alpha_mode = true;
+#pragma unroll
+                    for (int T = 0; T < NT; T++) {
+                        const float s0 = stg.rec[T].seed0, s1 = stg.rec[T].seed1;
+                        S[T].al[0][0] = S[T].al[0][1] = make_float2(s0, s0);
+                        S[T].al[1][0] = S[T].al[1][1] = make_float2(s1, s1);
                     }
                 }
             }
-            if (++rs == STREAM_STAGES) { rs = 0; rph ^= 1; }
+            if (!alpha_mode) v_group<NT, false>(S, px, stg, sm, C, act, clampt, tid);
+            else             v_group<NT, true>(S, px, stg, sm, C, act, clampt, tid);
         }
-    };
-
-    int g = 0, kres = -1;
-    // phase 1: every pixel this warp has met so far is opaque
-    for (; g < ngroups; g++) {
-        const int nr = min(STREAM_GROUP, yend - ys0 - g * STREAM_GROUP);
-        acquire();
-        kres = v_group<NT, WM, TMA, false>(S, sm, C, M, rs, 0, nr, ys0 + g * STREAM_GROUP, tid, c, W,
-                                           grow + (size_t)g * STREAM_GROUP * stride, stride);
-        if (kres >= 0) break;
-        release(g);
-    }
-    // phase 2: per-pixel alpha lanes, seeded from the scalar chains
-    if (NT > 0 && kres >= 0) {
-#pragma unroll
-        for (int T = 0; T < NT; T++)
-#pragma unroll
-            for (int k = 0; k < 2; k++) S[T].al[k][0] = S[T].al[k][1] = make_float2(S[T].sa[k], S[T].sa[k]);
-        for (; g < ngroups; g++) {
-            const int nr = min(STREAM_GROUP, yend - ys0 - g * STREAM_GROUP);
-            if (kres < 0) acquire();
-            v_group<NT, WM, TMA, true>(S, sm, C, M, rs, kres < 0 ? 0 : kres, nr, ys0 + g * STREAM_GROUP, tid, c, W,
-                                       grow + (size_t)g * STREAM_GROUP * stride, stride);
-            kres = -1;
-            release(g);
-        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&sm.empty[rs]);
+        if (++rs == STAGES) { rs = 0; rph ^= 1; }
     }
 }
 
-int stream_smem_bytes() { return (int)sizeof(StreamSmem); }
+int stream_smem_bytes() { return (int)sizeof(StreamSmem<STREAM_STAGES_2T>); }
 
-template <int NT, bool WM, bool TMA>
+template <int NT, bool WM>
 static cudaError_t launch_stream_t(const StreamJob *jobs, const StreamItem *items, int n, FixList fix, cudaStream_t st)
 {
+    constexpr int STAGES = NT == 2 ? STREAM_STAGES_2T : STREAM_STAGES_1T;
     static bool configured = false; // per instantiation; benign race (idempotent attribute)
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_stream<NT, WM, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(StreamSmem));
+        cudaError_t e = cudaFuncSetAttribute(k_stream<NT, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(StreamSmem<STAGES>));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_stream<NT, WM, TMA><<<n, STREAM_CTA, sizeof(StreamSmem), st>>>(jobs, items, fix);
+    k_stream<NT, WM><<<n, STREAM_CTA, sizeof(StreamSmem<STAGES>), st>>>(jobs, items, fix);
     return cudaGetLastError();
 }
 
-template <bool TMA>
-static cudaError_t launch_stream_a(const StreamJob *jobs, const StreamItem *items, int n_items, int max_targets,
-                                   bool any_wm, FixList fix, cudaStream_t st)
-{
-    switch (max_targets) {
-    case 0: return any_wm ? launch_stream_t<0, true, TMA>(jobs, items, n_items, fix, st) : cudaSuccess;
-    case 1: return any_wm ? launch_stream_t<1, true, TMA>(jobs, items, n_items, fix, st)
-                          : launch_stream_t<1, false, TMA>(jobs, items, n_items, fix, st);
-    default: return any_wm ? launch_stream_t<2, true, TMA>(jobs, items, n_items, fix, st)
-                           : launch_stream_t<2, false, TMA>(jobs, items, n_items, fix, st);
-    }
-}
-
+// Rows must be bulk-copyable (16-byte aligned base and stride): the engine re-pitches
+// anything else into its arena first.
 cudaError_t launch_stream(const StreamJob *jobs, const StreamItem *items, int n_items, int max_targets,
-                          bool any_wm, bool tma, FixList fix, cudaStream_t st)
+                          bool any_wm, FixList fix, cudaStream_t st)
 {
     if (n_items <= 0) return cudaSuccess;
-    return tma ? launch_stream_a<true>(jobs, items, n_items, max_targets, any_wm, fix, st)
-               : launch_stream_a<false>(jobs, items, n_items, max_targets, any_wm, fix, st);
+    switch (max_targets) {
+    case 0: return any_wm ? launch_stream_t<0, true>(jobs, items, n_items, fix, st) : cudaSuccess;
+    case 1: return any_wm ? launch_stream_t<1, true>(jobs, items, n_items, fix, st)
+                          : launch_stream_t<1, false>(jobs, items, n_items, fix, st);
+    default: return any_wm ? launch_stream_t<2, true>(jobs, items, n_items, fix, st)
+                           : launch_stream_t<2, false>(jobs, items, n_items, fix, st);
+    }
 }
 
 cudaError_t launch_exact_tiles(const ExactJob *jobs, const ExactItem *items, int n_items, cudaStream_t st)

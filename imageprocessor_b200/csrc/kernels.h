@@ -6,9 +6,9 @@
 namespace ipg {
 
 // Streaming fp32 resample (+ fused watermark copy/blend): one CTA per StreamItem.
+// Source rows must be 16-byte aligned (base and stride): they are moved by TMA bulk copies.
 cudaError_t launch_stream(const StreamJob *jobs, const StreamItem *items, int n_items,
-                          int max_targets, bool any_wm, bool tma, FixList fix,
-                          cudaStream_t st);
+                          int max_targets, bool any_wm, FixList fix, cudaStream_t st);
 
 // fp64 reference-order resample of whole outputs: one CTA per 32x8 output tile.
 cudaError_t launch_exact_tiles(const ExactJob *jobs, const ExactItem *items, int n_items,

@@ -207,6 +207,45 @@ static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const Stream
         if (e > H) return nullptr;
         g->band_yend[b] = e;
     }
+    // Group records: the RowRecs re-expressed per accumulator set (parity resolved here), with
+    // the opaque-alpha chains the kernel's fast path reads instead of computing.
+    g->band_grec_off.resize((size_t)n_bands);
+    for (int b = 0; b < n_bands; b++) {
+        const int32_t Y0 = g->band_y[b];
+        const int32_t ng = (g->band_yend[b] - Y0 + STREAM_GROUP - 1) / STREAM_GROUP;
+        const size_t base = g->grec.size() / (size_t)std::max(n_targets, 1);
+        g->band_grec_off[b] = (int32_t)base;
+        if (n_targets == 0) continue;
+        g->grec.resize((base + (size_t)ng) * (size_t)n_targets);
+        for (int i = 0; i < n_targets; i++) {
+            const StreamTargetGeom &t = g->t[i];
+            int par = 0;
+            float sa[2] = {0.f, 0.f};
+            for (int32_t gi = 0; gi < ng; gi++) {
+                GroupRec &G = g->grec[(base + (size_t)gi) * (size_t)n_targets + (size_t)i];
+                G.seed0 = sa[0];
+                G.seed1 = sa[1];
+                G.pad[0] = G.pad[1] = 0;
+                for (int k = 0; k < STREAM_GROUP; k++) {
+                    const int32_t ys = Y0 + gi * STREAM_GROUP + k;
+                    RowRec r{0.f, 0.f, -1, 0};
+                    if (ys < t.band_tend[b]) r = t.rows[(size_t)t.band_rec_off[b] + (size_t)(ys - Y0)];
+                    float w[2];
+                    w[par] = r.wa;
+                    w[par ^ 1] = r.wb;
+                    sa[0] = std::fmaf(255.0f, w[0], sa[0]);
+                    sa[1] = std::fmaf(255.0f, w[1], sa[1]);
+                    G.row[k] = GroupRow{w[0], w[1], sa[0], sa[1]};
+                    G.emit[k] = -1;
+                    if (r.emit >= 0) {
+                        G.emit[k] = (r.emit << 1) | par;
+                        sa[par] = 0.f;
+                        par ^= 1;
+                    }
+                }
+            }
+        }
+    }
     for (int b = 0; b < n_bands; b++) {
         for (int tile = 0; tile < g->n_tiles; tile++) {
             bool work = has_wm;

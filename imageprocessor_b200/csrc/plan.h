@@ -55,6 +55,8 @@ struct StreamGeom {
     std::vector<int32_t> band_y;    // [n_bands+1]
     std::vector<int32_t> band_yend; // [n_bands]
     StreamTargetGeom t[2];
+    std::vector<GroupRec> grec;         // [groups of all bands][n_targets]: what k_stream consumes
+    std::vector<int32_t> band_grec_off; // [n_bands] first group of each band
     std::vector<StreamItem> items;  // (tile, band) pairs that have work; job index left 0
 };
 

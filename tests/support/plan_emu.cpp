@@ -44,51 +44,68 @@ extern "C" int planemu_run(const uint8_t *src, int stride, int W, int H, int n_t
     auto g = get_stream_geom(W, H, sp, n_targets, false, bands_hint, 257.0);
     if (!g) return -1;
     long rows_read = 0;
+    bool opaque_src = true; // then every column's alpha chain must equal the record's precomputed one
+    for (int y = 0; y < H && opaque_src; y++)
+        for (int x = 0; x < W; x++)
+            if (src[(size_t)y * stride + (size_t)x * 4 + 3] != 255) { opaque_src = false; break; }
     for (const StreamItem &it : g->items) {
         const int tile = it.tile, band = it.band;
         const int cx0 = tile * g->tile_w;
         const int ys0 = g->band_y[band], yend = g->band_yend[band];
-        std::vector<float> acc_a[2], acc_b[2];
-        int tend[2] = {ys0, ys0};
+        // two accumulator sets per target, exactly as the kernel's VAcc; weights and emits come
+        // from the GroupRec tables the kernel consumes (parity already resolved by the planner)
+        std::vector<float> acc[2][2];
+        bool act[2] = {false, false};
         for (int t = 0; t < n_targets; t++) {
-            acc_a[t].assign((size_t)STREAM_COLS * 4, 0.f);
-            acc_b[t].assign((size_t)STREAM_COLS * 4, 0.f);
-            if (g->t[t].tile_ox[tile + 1] > g->t[t].tile_ox[tile]) tend[t] = g->t[t].band_tend[band];
+            acc[t][0].assign((size_t)STREAM_COLS * 4, 0.f);
+            acc[t][1].assign((size_t)STREAM_COLS * 4, 0.f);
+            act[t] = g->t[t].tile_ox[tile + 1] > g->t[t].tile_ox[tile] && g->t[t].band_tend[band] > ys0;
         }
-        for (int ys = ys0; ys < yend; ys++) {
-            rows_read++;
-            for (int t = 0; t < n_targets; t++) {
-                if (ys >= tend[t]) continue;
-                const StreamTargetGeom &tg = g->t[t];
-                const RowRec r = tg.rows[(size_t)tg.band_rec_off[band] + (size_t)(ys - ys0)];
-                for (int e = 0; e < STREAM_COLS; e++) {
-                    const int c = cx0 + e;
-                    uint8_t px[4] = {0, 0, 0, 0};
-                    if (c < W) memcpy(px, src + (size_t)ys * stride + (size_t)c * 4, 4);
-                    if (two_stage[t]) for (int k = 0; k < 3; k++) px[k] = std::min(px[k], px[3]);
-                    for (int k = 0; k < 4; k++) {
-                        float &a = acc_a[t][(size_t)e * 4 + k], &b = acc_b[t][(size_t)e * 4 + k];
-                        a = std::fmaf((float)px[k], r.wa, a);
-                        b = std::fmaf((float)px[k], r.wb, b);
+        const int ngroups = (yend - ys0 + STREAM_GROUP - 1) / STREAM_GROUP;
+        for (int gi = 0; gi < ngroups; gi++) {
+            for (int k = 0; k < STREAM_GROUP; k++) {
+                const int ys = ys0 + gi * STREAM_GROUP + k;
+                if (ys < yend) rows_read++;
+                for (int t = 0; t < n_targets; t++) {
+                    if (!act[t]) continue;
+                    const StreamTargetGeom &tg = g->t[t];
+                    const GroupRec &G = g->grec[((size_t)g->band_grec_off[band] + (size_t)gi) * (size_t)n_targets + (size_t)t];
+                    const GroupRow r = G.row[k];
+                    if (ys >= yend && (r.w0 != 0.f || r.w1 != 0.f || G.emit[k] >= 0)) return -3; // padding rows must be inert
+                    for (int e = 0; e < STREAM_COLS; e++) {
+                        const int c = cx0 + e;
+                        uint8_t px[4] = {0, 0, 0, 255};
+                        if (c < W && ys < yend) memcpy(px, src + (size_t)ys * stride + (size_t)c * 4, 4);
+                        if (two_stage[t]) for (int q = 0; q < 3; q++) px[q] = std::min(px[q], px[3]);
+                        for (int q = 0; q < 4; q++) {
+                            float &a = acc[t][0][(size_t)e * 4 + q], &b = acc[t][1][(size_t)e * 4 + q];
+                            a = std::fmaf((float)px[q], r.w0, a);
+                            b = std::fmaf((float)px[q], r.w1, b);
+                        }
                     }
-                }
-                if (r.emit >= 0) {
-                    std::vector<float> row = acc_a[t];
-                    acc_a[t] = acc_b[t];
-                    std::fill(acc_b[t].begin(), acc_b[t].end(), 0.f);
-                    const int oy = r.emit;
-                    for (int ox = tg.tile_ox[tile]; ox < tg.tile_ox[tile + 1]; ox++) {
-                        const int k0 = tg.ax->off[ox], n = tg.ax->off[ox + 1] - k0;
-                        const int e0 = tg.ax->first[ox] + sp[t].rect_x - cx0;
-                        if (e0 < 0 || e0 + n > STREAM_COLS) return -2;
-                        float s[4] = {0, 0, 0, 0};
-                        for (int k = 0; k < n; k++)
-                            for (int ch = 0; ch < 4; ch++) s[ch] = std::fmaf(row[(size_t)(e0 + k) * 4 + ch], tg.xw[k0 + k], s[ch]);
-                        for (int ch = 0; ch < 3; ch++) s[ch] = std::fmin(s[ch], s[3]);
-                        bool amb = false;
-                        uint8_t *d = dsts[t] + ((size_t)oy * sp[t].dw + ox) * 4;
-                        for (int ch = 0; ch < 4; ch++) d[ch] = (uint8_t)quant16(s[ch], tg.fix_d, amb);
-                        if (flags && flags[t]) flags[t][(size_t)oy * sp[t].dw + ox] += amb ? 1 : 16; // 16: written once
+                    // the opaque fast path takes alpha from the record instead of the accumulators
+                    if (opaque_src) {
+                        for (int e = 0; e < STREAM_COLS; e++) {
+                            if (acc[t][0][(size_t)e * 4 + 3] != r.sa0 || acc[t][1][(size_t)e * 4 + 3] != r.sa1) return -4;
+                        }
+                    }
+                    if (G.emit[k] >= 0) {
+                        const int set = G.emit[k] & 1, oy = G.emit[k] >> 1;
+                        std::vector<float> row = acc[t][set];
+                        std::fill(acc[t][set].begin(), acc[t][set].end(), 0.f);
+                        for (int ox = tg.tile_ox[tile]; ox < tg.tile_ox[tile + 1]; ox++) {
+                            const int k0 = tg.ax->off[ox], n = tg.ax->off[ox + 1] - k0;
+                            const int e0 = tg.ax->first[ox] + sp[t].rect_x - cx0;
+                            if (e0 < 0 || e0 + n > STREAM_COLS) return -2;
+                            float s[4] = {0, 0, 0, 0};
+                            for (int kk = 0; kk < n; kk++)
+                                for (int ch = 0; ch < 4; ch++) s[ch] = std::fmaf(row[(size_t)(e0 + kk) * 4 + ch], tg.xw[k0 + kk], s[ch]);
+                            for (int ch = 0; ch < 3; ch++) s[ch] = std::fmin(s[ch], s[3]);
+                            bool amb = false;
+                            uint8_t *d = dsts[t] + ((size_t)oy * sp[t].dw + ox) * 4;
+                            for (int ch = 0; ch < 4; ch++) d[ch] = (uint8_t)quant16(s[ch], tg.fix_d, amb);
+                            if (flags && flags[t]) flags[t][(size_t)oy * sp[t].dw + ox] += amb ? 1 : 16; // 16: written once
+                        }
                     }
                 }
             }
