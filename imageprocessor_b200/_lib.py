@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libipgpu.so")
+LIB_PATH = os.environ.get("IPG_LIB_PATH") or os.path.join(_HERE, "libipgpu.so")  # env: kernel experiments only
 
 # ipg_status
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_TIMEOUT, ERR_NO_DEVICE, ERR_SHUTDOWN, ERR_INTERNAL = 0, -1, -2, -3, -4, -5, -6, -7

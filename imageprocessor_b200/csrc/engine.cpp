@@ -567,6 +567,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 j.n_targets = nt;
                 j.has_wm = wm != nullptr;
                 j.tile_w = geom->tile_w;
+                j.warp_stride = geom->warp_stride;
+                j.slab_cols = geom->slab_cols;
                 j.n_tiles = geom->n_tiles;
                 j.n_bands = geom->n_bands;
                 j.band_y = blob.put_vec(geom->band_y);
@@ -586,6 +588,9 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                     o.xfirst = blob.put_vec(tgm.ax->first);
                     o.xw = blob.put_vec(tgm.xw);
                     o.tile_ox = blob.put_vec(tgm.tile_ox);
+                    o.local = tgm.local ? 1 : 0;
+                    o.warp_ox = tgm.local ? blob.put_vec(tgm.warp_ox) : nullptr;
+                    o.tile_parts = blob.put_vec(tgm.tile_parts);
                     o.rows = blob.put_vec(tgm.rows);
                     o.band_rec_off = blob.put_vec(tgm.band_rec_off);
                     o.band_tend = blob.put_vec(tgm.band_tend);

@@ -82,6 +82,11 @@ struct StreamTarget {
     const int32_t *xfirst;       // [dw]   relative to rect_x
     const float *xw;             // normalised fp32 weights (sum 1)
     const int32_t *tile_ox;      // [n_tiles+1] output columns owned by each column tile
+    int32_t local;               // 1: narrow support, each V warp runs its own horizontal pass
+    const int32_t *warp_ox;      // local: [n_tiles*4+1] output columns owned by each (tile, warp)
+    const int32_t *tile_parts;   // [n_tiles] horizontal-pass form of the tile: 0 = generic loops; P >= 1 =
+                                 // "cached": every output is split over P adjacent V threads, each holding
+                                 // at most STREAM_XTAPS interleaved taps (local targets: P == 1)
     const RowRec *rows;          // per-band records, concatenated
     const int32_t *band_rec_off; // [n_bands] first record of each band
     const int32_t *band_tend;    // [n_bands] one past the last source row that contributes
@@ -103,21 +108,37 @@ struct WatermarkD {
     uint32_t sr, sg, sb, sa;     // Uniform.RGBA(): c * 0x101
 };
 
-// k_stream CTA: 4 vertical-pass warps (128 threads x 4 px = one 512-column slab), one
-// producer warp (one elected lane drives the TMA ring: bulk loads of source rows + group
-// records, bulk stores of the watermark copy straight out of the ring) and 2
-// horizontal-pass warps.
+// occupancy knobs (overridable for experiments: make EXTRA=-DIPG_CTAS_2T=2 ...)
+#ifndef IPG_CTAS_2T
+#define IPG_CTAS_2T 2
+#endif
+#ifndef IPG_STAGES_2T
+#define IPG_STAGES_2T 8
+#endif
+#ifndef IPG_CTAS_1T
+#define IPG_CTAS_1T 3
+#endif
+#ifndef IPG_STAGES_1T
+#define IPG_STAGES_1T 5
+#endif
+
+// k_stream CTA: 4 V warps + one producer warp (one elected lane drives the TMA ring: bulk
+// loads of source rows + group records, bulk stores of the watermark copy straight out of
+// the ring).  Each V warp covers 128 source columns (32 lanes x 4 px); consecutive warps
+// start `warp_stride` <= 128 columns apart, so a warp sees the right halo of its own
+// outputs and runs the horizontal pass of narrow-support ("local") targets on its own,
+// one output per lane, with no cross-warp hand-off.  Wide-support targets (the 15:1
+// thumbnail) park their rows CTA-wide and meet at a 128-thread named barrier instead.
 enum {
-    STREAM_THREADS = 128, STREAM_PX = 4, STREAM_COLS = STREAM_THREADS * STREAM_PX,
-    STREAM_GROUP = 4,           // source rows per ring stage / TMA barrier phase (8 KB)
-    STREAM_STAGES_2T = 8,       // ring depth, two-target instantiation (2 CTAs per SM)
-    STREAM_STAGES_1T = 5,       // ring depth otherwise (3 CTAs per SM)
-    STREAM_XSLOTS = 3,          // vertically-filtered rows awaiting the horizontal pass (8 KB each)
+    STREAM_THREADS = 128, STREAM_PX = 4, STREAM_WARP_COLS = 32 * STREAM_PX,
+    STREAM_COLS = STREAM_THREADS * STREAM_PX, // widest slab (warp_stride == 128)
+    STREAM_GROUP = 4,           // source rows per ring stage / TMA barrier phase (<= 8 KB)
     STREAM_PTHREADS = 32,       // producer warp
-    STREAM_XTHREADS = 64,
-    STREAM_XREG = 3,            // outputs per X thread whose tap tables live in registers
-    STREAM_XTAPS = 8,           // ... and, when every one has at most this many taps, the weights too
-    STREAM_CTA = STREAM_THREADS + STREAM_PTHREADS + STREAM_XTHREADS,
+    STREAM_CTA = STREAM_THREADS + STREAM_PTHREADS,
+    STREAM_XTAPS = 8,           // local targets: taps per output kept in registers
+    STREAM_LOCAL_MAX_HALO = 16, // a target is local when its widest support - 1 fits this overlap
+    STREAM_STAGES_2T = IPG_STAGES_2T, STREAM_CTAS_2T = IPG_CTAS_2T,   // ring depth / CTAs per SM, two-target instantiation
+    STREAM_STAGES_1T = IPG_STAGES_1T, STREAM_CTAS_1T = IPG_CTAS_1T,   // ... otherwise
 };
 
 struct StreamJob {
@@ -125,6 +146,8 @@ struct StreamJob {
     int32_t n_targets;
     int32_t has_wm;
     int32_t tile_w;            // source columns owned per tile (multiple of 4)
+    int32_t warp_stride;       // columns between the first columns of consecutive V warps (multiple of 4)
+    int32_t slab_cols;         // 3 * warp_stride + 128: columns a CTA loads per row
     int32_t n_tiles, n_bands;
     int32_t check_premul;      // RGBA8 source, alpha unknown, a two_stage target exists
     const int32_t *band_y;     // [n_bands+1] owned source rows of each band

@@ -327,20 +327,20 @@ k_blend(const WatermarkD *__restrict__ wms, const BlendItem *__restrict__ items)
 // ---------------------------------------------------------------------------------
 // k_stream: vertical-first fp32 streaming resample
 //
-// CTA = 4 V warps (128 threads x 4 source pixels = a 512-column slab) + 1 producer warp
-// + 2 X warps.  The CTA owns `tile_w` of the slab's columns; the rest is the right halo
-// the widest horizontal support needs.  It walks the source rows of its band once, top
-// to bottom, in groups of STREAM_GROUP rows:
+// CTA = 4 V warps + 1 producer warp.  Each V warp covers 128 source columns (32 lanes x
+// 4 px); consecutive warps start `warp_stride` columns apart, so the CTA's slab is
+// 3 * warp_stride + 128 columns wide and the CTA owns `tile_w` of them (the rest is the
+// right halo the widest horizontal support needs).  The CTA walks the source rows of its
+// band once, top to bottom, in groups of STREAM_GROUP rows:
 //
 //   producer   one elected lane drives a ring of STAGES stages with TMA bulk copies
-//              (cp.async.bulk, SASS UBLKCP): per group, the rows (2 KB each) and the
-//              group's records land in one stage under one mbarrier phase.  For the
-//              watermark copy the same lane bulk-STORES the owned columns of the landed
-//              rows straight from the ring to the destination (draw.Draw(Src) of an
-//              *image.RGBA is a copy): the copy costs no SM instructions and the source
-//              crosses HBM once for resize + thumbnail + watermark.  A stage is refilled
-//              once the V warps released it (`empty` mbarrier) and its store has read it
-//              (bulk-group wait).
+//              (cp.async.bulk, SASS UBLKCP): per group, the rows and the group's records
+//              land in one stage under one mbarrier phase.  For the watermark copy the
+//              same lane bulk-STORES the owned columns of the landed rows straight from
+//              the ring to the destination (draw.Draw(Src) of an *image.RGBA is a copy):
+//              the copy costs no SM instructions and the source crosses HBM once for
+//              resize + thumbnail + watermark.  A stage is refilled once the V warps
+//              released it (`empty` mbarrier) and its store has read it (bulk-group wait).
 //   V warps    wait for a stage, LDS.128 their 4 pixels of each of the 4 rows, convert
 //              bytes to fp32 once (PRMT into 2^23+b, FADD2: the I2F.U8 the compiler would
 //              pick runs on the quarter-rate XU pipe) and FFMA2 them into the two
@@ -349,11 +349,15 @@ k_blend(const WatermarkD *__restrict__ wms, const BlendItem *__restrict__ items)
 //              (the host resolved which set is which open output row).  While a warp has
 //              only met opaque pixels its alpha sums are the host-computed chains in the
 //              records, so the fast path carries no alpha arithmetic.
-//   emit       when a source row completes an output row the V warps park that
-//              vertically-filtered row in shared memory (XOR-swizzled float4 slots:
-//              conflict-free stores, <=2-way gathers) and signal the X warps, which run
-//              the horizontal gather, quantise with the reference's ftou()>>8, flag bytes
-//              too close to a quantiser step for the fp64 fix-up, and store uchar4.
+//   emit       when a source row completes an output row of a LOCAL target (narrow
+//              horizontal support: the resize) each V warp parks its 128 filtered columns
+//              in its private shared-memory strip and, after a __syncwarp, every lane
+//              gathers one output pixel (taps in registers), quantises with the
+//              reference's ftou()>>8, flags bytes too close to a quantiser step for the
+//              fp64 fix-up and stores uchar4: no cross-warp hand-off at all.  For a SHARED
+//              target (wide support: the 15:1 thumbnail, one emit per ~15 rows) the four
+//              warps park into a CTA-wide double-buffered row, meet at a 128-thread named
+//              barrier, and split the outputs among all 128 threads.
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ int swz(int e) { return e ^ ((e >> 3) & 7); }
 
@@ -405,6 +409,7 @@ template <int N> __device__ __forceinline__ void tma_store_wait_read()
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void vwarps_bar() { asm volatile("bar.sync 1, %0;" ::"r"((int)STREAM_THREADS) : "memory"); }
 
 __device__ __forceinline__ uint32_t clamp_to_alpha(uint32_t q)
 {
@@ -424,88 +429,75 @@ __device__ __forceinline__ uint32_t quant16(float v, uint32_t D, uint32_t span, 
 }
 
 struct __align__(16) StreamStage {
-    uint4 rows[STREAM_GROUP][STREAM_THREADS]; // source rows of the slab, 2 KB each
+    uint4 rows[STREAM_GROUP][STREAM_THREADS]; // source rows of the slab (slab_cols * 4 bytes used)
     GroupRec rec[2];                          // this group's records, one per target
 };
 
-template <int STAGES> struct __align__(128) StreamSmem {
+// Per-thread horizontal-pass table of a target in "cached" form (StreamTarget::tile_parts):
+// every output is split over P adjacent V threads, each owning at most STREAM_XTAPS taps
+// e0, e0 + P, e0 + 2P, ...  Lives in shared memory, not registers: the emit code exists
+// once for all targets and the accumulators keep the register file.
+template <int NT> struct XTab {
+    int32_t ox[NT][STREAM_THREADS];              // output column, or -1 when the thread has none
+    int32_t e0[NT][STREAM_THREADS];              // element of xbuf[T] holding its first tap
+    float w[NT][STREAM_XTAPS][STREAM_THREADS];   // its weights, 0 past the end
+};
+template <> struct XTab<0> {};
+
+#ifndef IPG_ROW_UNROLL
+#define IPG_ROW_UNROLL 4
+#endif
+constexpr int kRowUnroll = IPG_ROW_UNROLL; // rows of a group unrolled in the V loop
+enum { STREAM_XBUF = STREAM_COLS + 64 }; // padded: zero-weight taps past an output's support read finite data
+
+// What the horizontal pass needs of a target, copied to shared memory once per CTA.
+struct XInfo {
+    uint8_t *dst;
+    int32_t dst_stride, exact_job;
+    uint32_t D;
+    int32_t local, parts, pad;
+};
+
+template <int NT, int STAGES> struct __align__(128) StreamSmem {
     StreamStage stage[STAGES];
-    float4 rowbuf[STREAM_XSLOTS][STREAM_COLS];   // vertically filtered rows, XOR-swizzled slots
+    float4 xbuf[NT > 0 ? NT : 1][STREAM_XBUF];   // vertically filtered row of each target, XOR-swizzled:
+                                                 // local target: four private 128-column warp strips;
+                                                 // shared target: the CTA's slab
+    XTab<NT> xt;
     uint64_t full[STAGES];                       // TMA completion of a stage
     uint64_t empty[STAGES];                      // the 4 V warps are done with a stage
-    uint64_t xfull[STREAM_XSLOTS], xempty[STREAM_XSLOTS];
-    int32_t xmeta[STREAM_XSLOTS][2];             // {target, output row} of each parked row
+    XInfo xi[2];                                 // per target; parts = tile_parts of this CTA's tile
+};
+template <int NT> struct StreamCfg {
+    static constexpr int STAGES = NT == 2 ? STREAM_STAGES_2T : STREAM_STAGES_1T;
+    static constexpr int CTAS_PER_SM = NT == 2 ? STREAM_CTAS_2T : STREAM_CTAS_1T;
+    using Smem = StreamSmem<NT, STAGES>;
 };
 
-// ---- X warps ---------------------------------------------------------------------
-// What an X thread needs of one target, copied out of the job so that its global
-// stores cannot force reloads.  The first STREAM_XREG outputs of the thread keep their
-// tap tables in registers; when all of them have at most STREAM_XTAPS taps (`cached`)
-// the weights live in registers too and the taps run branch-free (weight 0 past the
-// end adds exactly nothing).
-struct XTarget {
-    uint8_t *dst;
-    const float *xw;
-    const int32_t *xoff, *xfirst;
-    int dst_stride, ox0, n_own, ebase; // ebase = rect_x - cx0
-    int exact_job;
-    uint32_t D, span;
-    bool cached;
-    int e0[STREAM_XREG], k0[STREAM_XREG], n[STREAM_XREG];
-    float w[STREAM_XREG][STREAM_XTAPS];
-};
-
-__device__ __forceinline__ void xtarget_load(XTarget &x, const StreamTarget &t, int tile, int cx0, int xt)
-{
-    x.dst = t.dst; x.dst_stride = t.dst_stride;
-    x.xw = t.xw; x.xoff = t.xoff; x.xfirst = t.xfirst;
-    x.ox0 = __ldg(t.tile_ox + tile);
-    x.n_own = __ldg(t.tile_ox + tile + 1) - x.ox0;
-    x.ebase = t.rect_x - cx0;
-    x.exact_job = t.exact_job;
-    x.D = (uint32_t)t.fix_d;
-    x.span = 65536u - 2u * x.D;
-    bool small = true;
-#pragma unroll
-    for (int i = 0; i < STREAM_XREG; i++) {
-        const int j = xt + i * STREAM_XTHREADS;
-        x.e0[i] = x.k0[i] = x.n[i] = 0;
-        if (j < x.n_own) {
-            const int ox = x.ox0 + j;
-            x.k0[i] = __ldg(t.xoff + ox);
-            x.n[i] = __ldg(t.xoff + ox + 1) - x.k0[i];
-            x.e0[i] = __ldg(t.xfirst + ox) + x.ebase;
-        }
-        small &= x.n[i] <= STREAM_XTAPS;
-    }
-    x.cached = __all_sync(0xffffffffu, small);
-#pragma unroll
-    for (int i = 0; i < STREAM_XREG; i++)
-#pragma unroll
-        for (int k = 0; k < STREAM_XTAPS; k++)
-            x.w[i][k] = (x.cached && k < x.n[i]) ? __ldg(t.xw + x.k0[i] + k) : 0.f;
-}
-
-__device__ __forceinline__ void xfinish(const XTarget &x, int ox, int oy, float2 rg, float2 ba, const FixList &fix)
+// ---- horizontal pass ---------------------------------------------------------------
+template <typename TI>
+__device__ __forceinline__ void xfinish(const TI &t, uint32_t D, int ox, int oy, float2 rg, float2 ba, const FixList &fix)
 {
     const float a = ba.y;
     const float r = fminf(rg.x, a), g = fminf(rg.y, a), b = fminf(ba.x, a);
     bool amb = false;
-    const uint32_t o = quant16(r, x.D, x.span, amb) | (quant16(g, x.D, x.span, amb) << 8) |
-                       (quant16(b, x.D, x.span, amb) << 16) | (quant16(a, x.D, x.span, amb) << 24);
-    *(uint32_t *)(x.dst + (size_t)oy * x.dst_stride + (size_t)ox * 4) = o;
+    const uint32_t span = 65536u - 2u * D;
+    const uint32_t o = quant16(r, D, span, amb) | (quant16(g, D, span, amb) << 8) |
+                       (quant16(b, D, span, amb) << 16) | (quant16(a, D, span, amb) << 24);
+    *(uint32_t *)(t.dst + (size_t)oy * t.dst_stride + (size_t)ox * 4) = o;
     if (amb && fix.capacity) {
         const uint32_t idx = atomicAdd(fix.count, 1u);
-        if (idx < fix.capacity) fix.entries[idx] = FixEntry{x.exact_job, ox, oy};
+        if (idx < fix.capacity) fix.entries[idx] = FixEntry{t.exact_job, ox, oy};
     }
 }
 
-// One output pixel, taps and weights from memory; FFMA2 carries (r,g) and (b,a) pairs.
-__device__ __forceinline__ void xpixel(const XTarget &x, int ox, int oy, int e0, int k0, int n,
-                                       const float4 *__restrict__ buf, const FixList &fix)
+// One output pixel: n taps of a parked row starting at element e0, weights from L1.
+// FFMA2 carries the (r,g) and (b,a) pairs; taps in order, exactly as the emulator.
+__device__ __forceinline__ void xgather(const float *__restrict__ wp, int e0, int n, const float4 *__restrict__ buf,
+                                        float2 &rg, float2 &ba)
 {
-    const float *__restrict__ wp = x.xw + k0;
-    float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
+    rg = make_float2(0.f, 0.f);
+    ba = make_float2(0.f, 0.f);
 #pragma unroll 4
     for (int k = 0; k < n; k++) {
         const float w = __ldg(wp + k);
@@ -514,49 +506,73 @@ __device__ __forceinline__ void xpixel(const XTarget &x, int ox, int oy, int e0,
         rg = __ffma2_rn(make_float2(q.x, q.y), ww, rg);
         ba = __ffma2_rn(make_float2(q.z, q.w), ww, ba);
     }
-    xfinish(x, ox, oy, rg, ba, fix);
 }
 
-__device__ __forceinline__ void xpass(const XTarget &x, int oy, int xt, const float4 *__restrict__ buf,
-                                      const FixList &fix)
+// Horizontal pass of the row the V warps just parked for target T (runtime value: this
+// code exists once).  Local target: warp-private, one __syncwarp on each side.  Shared
+// target: all 128 V threads, one named barrier on each side.
+template <int NT, typename SM>
+__device__ __noinline__ void xpass(const StreamJob &J, SM &sm, int T, int oy, int tile, int cx0, int vtid, const FixList &fix)
 {
-    if (x.cached) {
+    const XInfo xi = sm.xi[T];
+    const int warp = vtid >> 5, lane = vtid & 31;
+    const bool local = xi.local != 0;
+    const int P = xi.parts;
+    const float4 *buf = sm.xbuf[T];
+    if (local) __syncwarp(); else vwarps_bar(); // the row is parked
+    if (P > 0) {
+        // cached form: this thread's taps and weights come from the shared-memory table
+        const int ox = sm.xt.ox[T][vtid];
+        const int e0 = sm.xt.e0[T][vtid];
+        float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
+        if (ox >= 0) {
 #pragma unroll
-        for (int i = 0; i < STREAM_XREG; i++) {
-            const int j = xt + i * STREAM_XTHREADS;
-            if (j >= x.n_own) break;
-            float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < STREAM_XTAPS; k++) {
-                const float4 q = buf[swz(min(x.e0[i] + k, STREAM_COLS - 1))];
-                const float2 ww = make_float2(x.w[i][k], x.w[i][k]);
+            for (int k = 0; k < STREAM_XTAPS; k++) { // weight 0 past the end adds exactly nothing (the buffer is padded and finite)
+                const float w = sm.xt.w[T][k][vtid];
+                const float4 q = buf[swz(e0 + k * P)];
+                const float2 ww = make_float2(w, w);
                 rg = __ffma2_rn(make_float2(q.x, q.y), ww, rg);
                 ba = __ffma2_rn(make_float2(q.z, q.w), ww, ba);
             }
-            xfinish(x, x.ox0 + j, oy, rg, ba, fix);
         }
+        for (int off = 1; off < P; off <<= 1) { // butterfly over the P threads of an output (P divides 32)
+            rg.x += __shfl_xor_sync(0xffffffffu, rg.x, off);
+            rg.y += __shfl_xor_sync(0xffffffffu, rg.y, off);
+            ba.x += __shfl_xor_sync(0xffffffffu, ba.x, off);
+            ba.y += __shfl_xor_sync(0xffffffffu, ba.y, off);
+        }
+        if (ox >= 0 && (vtid & (P - 1)) == 0) xfinish(xi, xi.D, ox, oy, rg, ba, fix);
     } else {
-#pragma unroll
-        for (int i = 0; i < STREAM_XREG; i++) {
-            const int j = xt + i * STREAM_XTHREADS;
-            if (j < x.n_own) xpixel(x, x.ox0 + j, oy, x.e0[i], x.k0[i], x.n[i], buf, fix);
+        const StreamTarget &t = J.t[T];
+        int ox0, n_own, ebase = t.rect_x - cx0, j0 = vtid, step = STREAM_THREADS;
+        if (local) { // strips sit at their slab position: warp * 128 + (column - warp * warp_stride)
+            ox0 = __ldg(t.warp_ox + tile * 4 + warp);
+            n_own = __ldg(t.warp_ox + tile * 4 + warp + 1) - ox0;
+            ebase += warp * (STREAM_WARP_COLS - J.warp_stride);
+            j0 = lane;
+            step = 32;
+        } else {
+            ox0 = __ldg(t.tile_ox + tile);
+            n_own = __ldg(t.tile_ox + tile + 1) - ox0;
+        }
+        for (int j = j0; j < n_own; j += step) {
+            const int ox = ox0 + j;
+            const int k0 = __ldg(t.xoff + ox);
+            float2 rg, ba;
+            xgather(t.xw + k0, __ldg(t.xfirst + ox) + ebase, __ldg(t.xoff + ox + 1) - k0, buf, rg, ba);
+            xfinish(xi, xi.D, ox, oy, rg, ba, fix);
         }
     }
-    for (int j = xt + STREAM_XREG * STREAM_XTHREADS; j < x.n_own; j += STREAM_XTHREADS) { // mild downscales only
-        const int ox = x.ox0 + j;
-        const int k0 = __ldg(x.xoff + ox);
-        xpixel(x, ox, oy, __ldg(x.xfirst + ox) + x.ebase, k0, __ldg(x.xoff + ox + 1) - k0, buf, fix);
-    }
+    if (local) __syncwarp(); else vwarps_bar(); // the buffer is reused by the next emit
 }
 
-// ---- V warps ---------------------------------------------------------------------
+// ---- vertical pass -------------------------------------------------------------------
 // Per-target accumulators of one V thread (4 source pixels): two sets, one per open
 // output row.  RGB of the 4 pixels is 12 floats = 6 packed pairs for FFMA2; the per-pixel
 // alpha lanes exist only in the ALPHA instantiation.
-struct VAcc {
-    float2 rgb[2][6];
-    float2 al[2][2];
-};
+template <bool ALPHA> struct VAcc;
+template <> struct VAcc<false> { float2 rgb[2][6]; };
+template <> struct VAcc<true> { float2 rgb[2][6]; float2 al[2][2]; };
 
 __device__ __forceinline__ float2 magic2(uint32_t qa, int ka, uint32_t qb, int kb)
 {
@@ -581,93 +597,141 @@ __device__ __forceinline__ void unpack_alpha(const uint4 &c, float2 *va)
     va[1] = __fadd2_rn(magic2(c.z, 3, c.w, 3), m);
 }
 
-// Hand one completed, vertically-filtered row (accumulator set SET) to the X warps and
-// clear the set.  `sa` is the opaque alpha chain value (ALPHA=false).
+// Park one completed, vertically-filtered row (accumulator set SET) at elements
+// 4*slot .. 4*slot+3 of `buf` (XOR-swizzled) and clear the set.  `sa` is the opaque alpha
+// chain value (ALPHA=false).
 template <int SET, bool ALPHA>
-__device__ __forceinline__ void park_row(VAcc &S, float sa, float4 *buf, int tid)
+__device__ __forceinline__ void park_row(VAcc<ALPHA> &S, float sa, float4 *buf, int slot)
 {
-    const int base = (tid * 4) & ~7, key = (tid >> 1) & 7, lo = (tid & 1) * 4; // swz(4*tid + j)
+    const int base = (slot * 4) & ~7, key = (slot >> 1) & 7, lo = (slot & 1) * 4; // swz(4*slot + j)
     const float2 *g = S.rgb[SET];
-    const float a0 = ALPHA ? S.al[SET][0].x : sa, a1 = ALPHA ? S.al[SET][0].y : sa;
-    const float a2 = ALPHA ? S.al[SET][1].x : sa, a3 = ALPHA ? S.al[SET][1].y : sa;
+    float a0 = sa, a1 = sa, a2 = sa, a3 = sa;
+    if constexpr (ALPHA) { a0 = S.al[SET][0].x; a1 = S.al[SET][0].y; a2 = S.al[SET][1].x; a3 = S.al[SET][1].y; }
     buf[base | ((lo + 0) ^ key)] = make_float4(g[0].x, g[0].y, g[1].x, a0);
     buf[base | ((lo + 1) ^ key)] = make_float4(g[1].y, g[2].x, g[2].y, a1);
     buf[base | ((lo + 2) ^ key)] = make_float4(g[3].x, g[3].y, g[4].x, a2);
     buf[base | ((lo + 3) ^ key)] = make_float4(g[4].y, g[5].x, g[5].y, a3);
 #pragma unroll
     for (int i = 0; i < 6; i++) S.rgb[SET][i] = make_float2(0.f, 0.f);
-    if (ALPHA) S.al[SET][0] = S.al[SET][1] = make_float2(0.f, 0.f);
+    if constexpr (ALPHA) S.al[SET][0] = S.al[SET][1] = make_float2(0.f, 0.f);
 }
 
-struct VCursor {  // parked-row slot position of a V warp
-    int xs; uint32_t xph;
-    int emits;
+// What a V thread carries through the row loop besides its accumulators.
+struct VCtx {
+    int tile, cx0, vtid;
+    int slot;        // this thread's 4-pixel slot within the slab (index into a ring row)
+    int pslot[2];    // where it parks its 4 columns of target T (strip slot if local, slab slot if shared)
+    bool act[2], clampt[2];
+    // target 0 in its common form (local, one output per lane, <= STREAM_XTAPS taps): the horizontal
+    // pass runs inline with the taps in registers; every other case goes through xpass()
+    bool x0_inline;
+    int x0_ox;               // output column of this lane, or -1
+    const float4 *x0_tap;    // address of its first tap in xbuf[0] when no swizzle step is crossed ... see x0_off
+    int x0_e0;
+    float x0_w[STREAM_XTAPS];
+    // fallback watermark copy
+    bool wm_v;
+    uint8_t *wm_dst;
+    int wm_stride, c, W, ys1;
 };
 
-// The four source rows of one ring stage into every active target.
-template <int NT, bool ALPHA, typename SM>
-__device__ __forceinline__ void v_group(VAcc *S, const uint4 *px, const StreamStage &stg, SM &sm, VCursor &C,
-                                        const bool *act, const bool *clampt, int tid)
+// The source rows of one ring stage into every active target; rows are taken one at a
+// time (the next one is requested before this one's math) so the code stays small.
+template <int NT, bool WM, bool ALPHA, typename SM>
+__device__ __forceinline__ void v_rows(VAcc<ALPHA> *S, const StreamJob &J, const StreamStage &stg, SM &sm, const VCtx &C,
+                                       int ys_first, int nr, const FixList &fix)
 {
-#pragma unroll
+    uint4 cur = stg.rows[0][C.slot];
+#pragma unroll kRowUnroll
     for (int k = 0; k < STREAM_GROUP; k++) {
-        float2 vp[6], va[2];
-        unpack_rgb(px[k], vp);
-        if (ALPHA) unpack_alpha(px[k], va);
+        const uint4 nxt = stg.rows[(k + 1) & (STREAM_GROUP - 1)][C.slot];
+        // band tail: rows past the end are stale ring contents (their weights are 0)
+        if (k >= nr) cur = make_uint4(0xff000000u, 0xff000000u, 0xff000000u, 0xff000000u);
+        if (WM && C.wm_v && ys_first + k < C.ys1) {
+            uint32_t *d = (uint32_t *)(C.wm_dst + (size_t)(ys_first + k) * C.wm_stride + (size_t)C.c * 4);
+            d[0] = cur.x;
+            if (C.c + 1 < C.W) d[1] = cur.y;
+            if (C.c + 2 < C.W) d[2] = cur.z;
+            if (C.c + 3 < C.W) d[3] = cur.w;
+        }
+        if constexpr (NT > 0) {
+            float2 vp[6], va[2];
+            unpack_rgb(cur, vp);
+            if (ALPHA) unpack_alpha(cur, va);
+            int pending = 0, oyv[NT > 0 ? NT : 1];
 #pragma unroll
-        for (int T = 0; T < NT; T++) {
-            if (!act[T]) continue; // CTA-uniform
-            const float4 r = *reinterpret_cast<const float4 *>(&stg.rec[T].row[k]); // LDS.128 broadcast
-            const float2 w00 = make_float2(r.x, r.x), w11 = make_float2(r.y, r.y);
-            if (!ALPHA) {
+            for (int T = 0; T < NT; T++) {
+                if (!C.act[T]) continue; // CTA-uniform
+                const float4 r = *reinterpret_cast<const float4 *>(&stg.rec[T].row[k]); // LDS.128 broadcast
+                const float2 w00 = make_float2(r.x, r.x), w11 = make_float2(r.y, r.y);
+                if constexpr (!ALPHA) {
 #pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    S[T].rgb[0][i] = __ffma2_rn(vp[i], w00, S[T].rgb[0][i]);
-                    S[T].rgb[1][i] = __ffma2_rn(vp[i], w11, S[T].rgb[1][i]);
-                }
-            } else {
-                float2 up[6];
-                if (clampt[T]) {
-                    // cropAndResize quantises to premultiplied RGBA8 first: channels clamp to alpha
-                    const uint4 cc = make_uint4(clamp_to_alpha(px[k].x), clamp_to_alpha(px[k].y),
-                                                clamp_to_alpha(px[k].z), clamp_to_alpha(px[k].w));
-                    unpack_rgb(cc, up);
+                    for (int i = 0; i < 6; i++) {
+                        S[T].rgb[0][i] = __ffma2_rn(vp[i], w00, S[T].rgb[0][i]);
+                        S[T].rgb[1][i] = __ffma2_rn(vp[i], w11, S[T].rgb[1][i]);
+                    }
                 } else {
+                    float2 up[6];
+                    if (C.clampt[T]) {
+                        // cropAndResize quantises to premultiplied RGBA8 first: channels clamp to alpha
+                        const uint4 cc = make_uint4(clamp_to_alpha(cur.x), clamp_to_alpha(cur.y), clamp_to_alpha(cur.z),
+                                                    clamp_to_alpha(cur.w));
+                        unpack_rgb(cc, up);
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 6; i++) up[i] = vp[i];
+                        for (int i = 0; i < 6; i++) up[i] = vp[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; i++) {
+                        S[T].rgb[0][i] = __ffma2_rn(up[i], w00, S[T].rgb[0][i]);
+                        S[T].rgb[1][i] = __ffma2_rn(up[i], w11, S[T].rgb[1][i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        S[T].al[0][i] = __ffma2_rn(va[i], w00, S[T].al[0][i]);
+                        S[T].al[1][i] = __ffma2_rn(va[i], w11, S[T].al[1][i]);
+                    }
                 }
+                const int e = stg.rec[T].emit[k];
+                oyv[T] = e >> 1;
+                if (e >= 0) { // CTA-uniform: this source row completes output row e>>1, held in set e&1
+                    if (e & 1) park_row<1, ALPHA>(S[T], r.w, sm.xbuf[T], C.pslot[T]);
+                    else       park_row<0, ALPHA>(S[T], r.z, sm.xbuf[T], C.pslot[T]);
+                    if (T == 0 && C.x0_inline) {
+                        __syncwarp();
+                        if (C.x0_ox >= 0) {
+                            const float4 *buf = sm.xbuf[0];
+                            float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    S[T].rgb[0][i] = __ffma2_rn(up[i], w00, S[T].rgb[0][i]);
-                    S[T].rgb[1][i] = __ffma2_rn(up[i], w11, S[T].rgb[1][i]);
-                }
-#pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    S[T].al[0][i] = __ffma2_rn(va[i], w00, S[T].al[0][i]);
-                    S[T].al[1][i] = __ffma2_rn(va[i], w11, S[T].al[1][i]);
+                            for (int q = 0; q < STREAM_XTAPS; q++) { // weight 0 past the end adds exactly nothing
+                                const float4 v = buf[swz(C.x0_e0 + q)];
+                                const float2 ww = make_float2(C.x0_w[q], C.x0_w[q]);
+                                rg = __ffma2_rn(make_float2(v.x, v.y), ww, rg);
+                                ba = __ffma2_rn(make_float2(v.z, v.w), ww, ba);
+                            }
+                            xfinish(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
+                        }
+                        __syncwarp(); // the strip is reused by the next emit
+                    } else {
+                        pending |= 1 << T;
+                    }
                 }
             }
-            const int e = stg.rec[T].emit[k];
-            if (e >= 0) { // CTA-uniform: this source row completes output row e>>1, held in set e&1
-                if (C.emits >= STREAM_XSLOTS) mbar_wait(&sm.xempty[C.xs], C.xph);
-                if (e & 1) park_row<1, ALPHA>(S[T], r.w, sm.rowbuf[C.xs], tid);
-                else       park_row<0, ALPHA>(S[T], r.z, sm.rowbuf[C.xs], tid);
-                if (tid == 0) { sm.xmeta[C.xs][0] = T; sm.xmeta[C.xs][1] = e >> 1; }
-                __syncwarp();
-                if ((tid & 31) == 0) mbar_arrive(&sm.xfull[C.xs]);
-                C.emits++;
-                if (++C.xs == STREAM_XSLOTS) { C.xs = 0; C.xph ^= 1; }
+            if (pending & 1) xpass<NT>(J, sm, 0, oyv[0], C.tile, C.cx0, C.vtid, fix);
+            if constexpr (NT > 1) {
+                if (pending & 2) xpass<NT>(J, sm, 1, oyv[1], C.tile, C.cx0, C.vtid, fix);
             }
         }
+        cur = nxt;
     }
 }
 
 template <int NT, bool WM>
-__global__ void __launch_bounds__(STREAM_CTA, (NT == 2 ? 2 : 3))
+__global__ void __launch_bounds__(STREAM_CTA, StreamCfg<NT>::CTAS_PER_SM)
 k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ items, FixList fix)
 {
-    constexpr int STAGES = NT == 2 ? STREAM_STAGES_2T : STREAM_STAGES_1T;
-    using Smem = StreamSmem<STAGES>;
+    constexpr int STAGES = StreamCfg<NT>::STAGES;
+    using Smem = typename StreamCfg<NT>::Smem;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
@@ -682,8 +746,10 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     const int warp = threadIdx.x >> 5;
     const int ngroups = (yend - ys0 + STREAM_GROUP - 1) / STREAM_GROUP;
     const int tid = (int)threadIdx.x;
-    const int c = cx0 + tid * STREAM_PX;
-    const uint32_t row_bytes = (uint32_t)(((min(STREAM_COLS, W - cx0) * 4) + 15) & ~15);
+    const int ws = J.warp_stride;
+    const int slot = (warp & 3) * (ws >> 2) + (tid & 31); // this thread's 4-pixel slot within the slab
+    const int c = cx0 + slot * STREAM_PX;
+    const uint32_t row_bytes = (uint32_t)(((min(J.slab_cols, W - cx0) * 4) + 15) & ~15);
     // watermark copy: owned columns of the band's own rows; by TMA when 16-byte granular
     const bool has_wm = WM && J.has_wm;
     const uint32_t wm_bytes = (uint32_t)(min(J.tile_w, W - cx0) * 4);
@@ -694,10 +760,6 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
             mbar_init(&sm.full[s], 1);
             mbar_init(&sm.empty[s], STREAM_THREADS / 32);
         }
-        for (int s = 0; s < STREAM_XSLOTS; s++) {
-            mbar_init(&sm.xfull[s], STREAM_THREADS / 32);
-            mbar_init(&sm.xempty[s], STREAM_XTHREADS / 32);
-        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // slab columns past the image edge are never written by TMA: park opaque black there
@@ -705,7 +767,41 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     if (tid < STREAM_THREADS && c >= W) {
         for (int s = 0; s < STAGES; s++)
             for (int k = 0; k < STREAM_GROUP; k++)
-                sm.stage[s].rows[k][tid] = make_uint4(0xff000000u, 0xff000000u, 0xff000000u, 0xff000000u);
+                sm.stage[s].rows[k][slot] = make_uint4(0xff000000u, 0xff000000u, 0xff000000u, 0xff000000u);
+    }
+    // horizontal-pass tables of the targets whose tile is in cached form, one entry per V thread
+    if constexpr (NT > 0) {
+        if (tid < STREAM_THREADS) {
+#pragma unroll
+            for (int T = 0; T < NT; T++) {
+                if (T >= J.n_targets) continue;
+                const StreamTarget &t = J.t[T];
+                const int P = __ldg(t.tile_parts + tile);
+                if (tid == 0) sm.xi[T] = XInfo{t.dst, t.dst_stride, t.exact_job, (uint32_t)t.fix_d, t.local, P, 0};
+                for (int e = tid; e < STREAM_XBUF; e += STREAM_THREADS) sm.xbuf[T][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (P == 0) continue;
+                int ox = -1, e0 = 0, k0 = 0, n = 0, part = 0;
+                if (t.local) { // one output per lane of the owning warp; strip w sits at elements [128 w, 128 w + 128)
+                    const int ox0 = __ldg(t.warp_ox + tile * 4 + warp);
+                    if ((tid & 31) < __ldg(t.warp_ox + tile * 4 + warp + 1) - ox0) ox = ox0 + (tid & 31);
+                    if (ox >= 0) e0 = __ldg(t.xfirst + ox) + t.rect_x - cx0 + warp * (STREAM_WARP_COLS - ws);
+                } else {       // P adjacent threads per output of the tile
+                    const int ox0 = __ldg(t.tile_ox + tile);
+                    part = tid & (P - 1);
+                    if (tid / P < __ldg(t.tile_ox + tile + 1) - ox0) ox = ox0 + tid / P;
+                    if (ox >= 0) e0 = __ldg(t.xfirst + ox) + t.rect_x - cx0 + part;
+                }
+                if (ox >= 0) {
+                    k0 = __ldg(t.xoff + ox);
+                    n = __ldg(t.xoff + ox + 1) - k0;
+                }
+                sm.xt.ox[T][tid] = ox;
+                sm.xt.e0[T][tid] = e0;
+#pragma unroll
+                for (int k = 0; k < STREAM_XTAPS; k++)
+                    sm.xt.w[T][k][tid] = (ox >= 0 && part + k * P < n) ? __ldg(t.xw + k0 + part + k * P) : 0.f;
+            }
+        }
     }
     __syncthreads();
 
@@ -753,124 +849,108 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
         return;
     }
 
-    if (warp > STREAM_THREADS / 32) {
-        // ===== X warps: horizontal pass + quantise + store of every parked row =====
-        if (NT == 0) return;
-        const int xt = tid - STREAM_THREADS - STREAM_PTHREADS;
-        XTarget X0, X1;
-        int total = 0;
-        X0.n_own = X1.n_own = 0;
-        if (J.n_targets > 0) {
-            xtarget_load(X0, J.t[0], tile, cx0, xt);
-            if (X0.n_own > 0) total += __ldg(J.t[0].band_oy + band + 1) - __ldg(J.t[0].band_oy + band);
-        }
-        if (NT > 1 && J.n_targets > 1) {
-            xtarget_load(X1, J.t[1], tile, cx0, xt);
-            if (X1.n_own > 0) total += __ldg(J.t[1].band_oy + band + 1) - __ldg(J.t[1].band_oy + band);
-        }
-        int s = 0;
-        uint32_t ph = 0;
-        for (int e = 0; e < total; e++) {
-            mbar_wait(&sm.xfull[s], ph);
-            const int T = sm.xmeta[s][0], oy = sm.xmeta[s][1];
-            if (NT == 1 || T == 0) xpass(X0, oy, xt, sm.rowbuf[s], fix);
-            else                   xpass(X1, oy, xt, sm.rowbuf[s], fix);
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&sm.xempty[s]);
-            if (++s == STREAM_XSLOTS) { s = 0; ph ^= 1; }
-        }
-        return;
+    // ===== V warps: vertical pass, and the horizontal pass of every row they complete =====
+    VCtx C;
+    C.tile = tile; C.cx0 = cx0; C.vtid = tid; C.slot = slot;
+    C.c = c; C.W = W; C.ys1 = ys1;
+#pragma unroll
+    for (int T = 0; T < 2; T++) {
+        C.act[T] = T < NT && T < J.n_targets && __ldg(J.t[T].tile_ox + tile + 1) > __ldg(J.t[T].tile_ox + tile) &&
+                   __ldg(J.t[T].band_tend + band) > ys0;
+        C.clampt[T] = T < NT && T < J.n_targets && J.t[T].two_stage != 0;
+        C.pslot[T] = (T < NT && T < J.n_targets && J.t[T].local) ? tid : slot;
     }
-
-    // ===== V warps: vertical pass =====
-    VAcc S[NT > 0 ? NT : 1];
-    bool act[NT > 0 ? NT : 1], clampt[NT > 0 ? NT : 1];
+    C.x0_inline = false;
+    C.x0_ox = -1;
+    C.x0_e0 = 0;
+    C.x0_tap = nullptr;
 #pragma unroll
-    for (int T = 0; T < NT; T++) {
+    for (int k = 0; k < STREAM_XTAPS; k++) C.x0_w[k] = 0.f;
+    if constexpr (NT > 0) {
+        if (C.act[0] && sm.xi[0].local && sm.xi[0].parts == 1) {
+            C.x0_inline = true;
+            C.x0_ox = sm.xt.ox[0][tid];
+            C.x0_e0 = sm.xt.e0[0][tid];
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-#pragma unroll
-            for (int i = 0; i < 6; i++) S[T].rgb[k][i] = make_float2(0.f, 0.f);
-            S[T].al[k][0] = S[T].al[k][1] = make_float2(0.f, 0.f);
+            for (int k = 0; k < STREAM_XTAPS; k++) C.x0_w[k] = sm.xt.w[0][k][tid];
         }
-        act[T] = T < J.n_targets && __ldg(J.t[T].tile_ox + tile + 1) > __ldg(J.t[T].tile_ox + tile) &&
-                 __ldg(J.t[T].band_tend + band) > ys0;
-        clampt[T] = T < J.n_targets && J.t[T].two_stage != 0;
     }
     // fallback watermark copy by the V warps when the rows are not 16-byte granular
-    const bool wm_v = has_wm && !wm_tma && tid * STREAM_PX < J.tile_w && c < W;
-    uint8_t *wm_dst = has_wm ? J.wm.dst : nullptr;
-    const int wm_stride = has_wm ? J.wm.dst_stride : 0;
-    VCursor C{0, 1u, 0};
-    int rs = 0;
-    uint32_t rph = 0;
-    bool alpha_mode = false;
+    C.wm_v = has_wm && !wm_tma && c < min(W, cx0 + J.tile_w) &&
+             (warp == 3 || (tid & 31) * STREAM_PX < ws); // overlapped columns: the right-hand warp writes them
+    C.wm_dst = has_wm ? J.wm.dst : nullptr;
+    C.wm_stride = has_wm ? J.wm.dst_stride : 0;
 
-    for (int g = 0; g < ngroups; g++) {
-        mbar_wait(&sm.full[rs], rph);
-        const StreamStage &stg = sm.stage[rs];
-        uint4 px[STREAM_GROUP];
+    VAcc<false> S[NT > 0 ? NT : 1];
 #pragma unroll
-        for (int k = 0; k < STREAM_GROUP; k++) px[k] = stg.rows[k][tid];
-        const int nr = yend - ys0 - g * STREAM_GROUP;
-        if (nr < STREAM_GROUP) { // band tail: rows past the end are stale ring contents (their weights are 0)
+    for (int T = 0; T < NT; T++)
 #pragma unroll
-            for (int k = 1; k < STREAM_GROUP; k++)
-                if (k >= nr) px[k] = make_uint4(0xff000000u, 0xff000000u, 0xff000000u, 0xff000000u);
-        }
-        if (WM && wm_v) {
+        for (int k = 0; k < 2; k++)
 #pragma unroll
-            for (int k = 0; k < STREAM_GROUP; k++) {
-                const int ys = ys0 + g * STREAM_GROUP + k;
-                if (ys < ys1) {
-                    uint32_t *d = (uint32_t *)(wm_dst + (size_t)ys * wm_stride + (size_t)c * 4);
-                    d[0] = px[k].x;
-                    if (c + 1 < W) d[1] = px[k].y;
-                    if (c + 2 < W) d[2] = px[k].z;
-                    if (c + 3 < W) d[3] = px[k].w;
-                }
-            }
-        }
-        if (NT > 0) {
-            if (!alpha_mode) {
-                uint32_t m = 0xffffffffu;
-#pragma unroll
-                for (int k = 0; k < STREAM_GROUP; k++) m = min(m, min(min(px[k].x, px[k].y), min(px[k].z, px[k].w)));
-                if (__any_sync(0xffffffffu, m < 0xff000000u)) {
-                    // first non-opaque pixel this warp meets: materialise the per-pixel alpha lanes
-                    // from the chains entering this group (bit-identical to having carried them)
-                    alpha_mode = true;
-#pragma unroll
-                    for (int T = 0; T < NT; T++) {
-                        const float s0 = stg.rec[T].seed0, s1 = stg.rec[T].seed1;
-                        S[T].al[0][0] = S[T].al[0][1] = make_float2(s0, s0);
-                        S[T].al[1][0] = S[T].al[1][1] = make_float2(s1, s1);
-                    }
-                }
-            }
-            if (!alpha_mode) v_group<NT, false>(S, px, stg, sm, C, act, clampt, tid);
-            else             v_group<NT, true>(S, px, stg, sm, C, act, clampt, tid);
-        }
+            for (int i = 0; i < 6; i++) S[T].rgb[k][i] = make_float2(0.f, 0.f);
+    int rs = 0, g = 0;
+    uint32_t rph = 0;
+    auto advance = [&]() {
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&sm.empty[rs]);
         if (++rs == STAGES) { rs = 0; rph ^= 1; }
+    };
+
+    // phase 1: every pixel this warp has met so far is opaque -- alpha comes from the records
+    bool switch_alpha = false;
+    for (; g < ngroups; g++) {
+        mbar_wait(&sm.full[rs], rph);
+        const StreamStage &stg = sm.stage[rs];
+        const int nr = yend - ys0 - g * STREAM_GROUP;
+        if (NT > 0) {
+            uint32_t m = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < STREAM_GROUP; k++) {
+                const uint4 q = stg.rows[k][slot];
+                if (k < nr) m = min(m, min(min(q.x, q.y), min(q.z, q.w)));
+            }
+            if (__any_sync(0xffffffffu, m < 0xff000000u)) { switch_alpha = true; break; }
+        }
+        v_rows<NT, WM, false>(S, J, stg, sm, C, ys0 + g * STREAM_GROUP, nr, fix);
+        advance();
+    }
+    if constexpr (NT > 0) {
+        if (!switch_alpha) return;
+        // phase 2: first non-opaque pixel this warp meets: materialise the per-pixel alpha lanes from the
+        // chains entering this group (bit-identical to having carried them all along)
+        VAcc<true> A[NT];
+#pragma unroll
+        for (int T = 0; T < NT; T++) {
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+#pragma unroll
+                for (int i = 0; i < 6; i++) A[T].rgb[k][i] = S[T].rgb[k][i];
+            const float s0 = sm.stage[rs].rec[T].seed0, s1 = sm.stage[rs].rec[T].seed1;
+            A[T].al[0][0] = A[T].al[0][1] = make_float2(s0, s0);
+            A[T].al[1][0] = A[T].al[1][1] = make_float2(s1, s1);
+        }
+        for (; g < ngroups; g++) {
+            mbar_wait(&sm.full[rs], rph); // (already complete for the group that triggered the switch)
+            v_rows<NT, WM, true>(A, J, sm.stage[rs], sm, C, ys0 + g * STREAM_GROUP, yend - ys0 - g * STREAM_GROUP, fix);
+            advance();
+        }
     }
 }
 
-int stream_smem_bytes() { return (int)sizeof(StreamSmem<STREAM_STAGES_2T>); }
+int stream_smem_bytes() { return (int)sizeof(StreamCfg<2>::Smem); }
 
 template <int NT, bool WM>
 static cudaError_t launch_stream_t(const StreamJob *jobs, const StreamItem *items, int n, FixList fix, cudaStream_t st)
 {
-    constexpr int STAGES = NT == 2 ? STREAM_STAGES_2T : STREAM_STAGES_1T;
+    using Smem = typename StreamCfg<NT>::Smem;
     static bool configured = false; // per instantiation; benign race (idempotent attribute)
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_stream<NT, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(StreamSmem<STAGES>));
+                                             (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_stream<NT, WM><<<n, STREAM_CTA, sizeof(StreamSmem<STAGES>), st>>>(jobs, items, fix);
+    k_stream<NT, WM><<<n, STREAM_CTA, sizeof(Smem), st>>>(jobs, items, fix);
     return cudaGetLastError();
 }
 

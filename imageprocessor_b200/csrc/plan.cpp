@@ -111,12 +111,55 @@ static bool build_target(StreamGeom &g, int ti, const StreamTargetSpec &s, doubl
             const int32_t cx1 = (tile + 1) * g.tile_w;
             while (ox < s.dw && ax.first[ox] + s.rect_x < cx1) {
                 const int32_t lastcol = ax.first[ox] + s.rect_x + (ax.off[ox + 1] - ax.off[ox]) - 1;
-                if (lastcol >= tile * g.tile_w + STREAM_COLS) return false; // halo too small
+                if (lastcol >= tile * g.tile_w + g.slab_cols) return false; // halo too small
                 ox++;
             }
         }
         t.tile_ox[g.n_tiles] = ox;
         if (ox != s.dw) return false;
+    }
+    // local targets: within a tile, an output column belongs to the V warp whose owned range
+    // [w * warp_stride, (w + 1) * warp_stride) (the last warp: up to tile_w) holds its first tap;
+    // all its taps must lie inside that warp's 128 loaded columns
+    t.warp_ox.clear();
+    if (t.local) {
+        t.warp_ox.assign((size_t)g.n_tiles * 4 + 1, s.dw);
+        int32_t ox = 0;
+        for (int32_t tile = 0; tile < g.n_tiles; tile++) {
+            for (int32_t w = 0; w < 4; w++) {
+                t.warp_ox[(size_t)tile * 4 + w] = ox;
+                const int32_t c0 = tile * g.tile_w + w * g.warp_stride;
+                const int32_t c1 = w < 3 ? std::min(c0 + g.warp_stride, (tile + 1) * g.tile_w) : (tile + 1) * g.tile_w;
+                while (ox < t.tile_ox[tile + 1] && ax.first[ox] + s.rect_x < c1) {
+                    const int32_t firstcol = ax.first[ox] + s.rect_x;
+                    const int32_t lastcol = firstcol + (ax.off[ox + 1] - ax.off[ox]) - 1;
+                    if (firstcol < c0 || lastcol >= c0 + STREAM_WARP_COLS) return false;
+                    ox++;
+                }
+            }
+            if (ox != t.tile_ox[tile + 1]) return false;
+        }
+        t.warp_ox[(size_t)g.n_tiles * 4] = ox;
+    }
+
+    // horizontal-pass form per tile (see StreamTarget::tile_parts)
+    t.tile_parts.assign((size_t)g.n_tiles, 0);
+    for (int32_t tile = 0; tile < g.n_tiles; tile++) {
+        const int32_t o0 = t.tile_ox[tile], o1 = t.tile_ox[tile + 1];
+        int32_t maxn = 0;
+        for (int32_t ox = o0; ox < o1; ox++) maxn = std::max(maxn, ax.off[ox + 1] - ax.off[ox]);
+        if (o1 == o0) continue;
+        if (t.local) {
+            bool ok = maxn <= STREAM_XTAPS;
+            for (int32_t w = 0; w < 4 && ok; w++)
+                ok = t.warp_ox[(size_t)tile * 4 + w + 1] - t.warp_ox[(size_t)tile * 4 + w] <= 32;
+            t.tile_parts[tile] = ok ? 1 : 0;
+        } else {
+            for (int32_t P = 1; P <= 32; P <<= 1) {
+                if ((o1 - o0) * P > STREAM_THREADS) break;
+                if ((maxn + P - 1) / P <= STREAM_XTAPS) { t.tile_parts[tile] = P; break; }
+            }
+        }
     }
 
     // row bands: an output row belongs to the band holding its first source row
@@ -172,7 +215,7 @@ static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const Stream
     g->n_targets = n_targets;
     g->has_wm = has_wm;
 
-    int max_taps_x = 1;
+    int max_taps_x = 1, local_halo = 0;
     double max_scale_y = 1.0;
     for (int i = 0; i < n_targets; i++) {
         const StreamTargetSpec &s = targets[i];
@@ -181,8 +224,14 @@ static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const Stream
         auto ax = get_axis_plan(s.dw, s.rect_w);
         max_taps_x = std::max(max_taps_x, ax->max_taps);
         max_scale_y = std::max(max_scale_y, (double)s.rect_h / (double)s.dh);
+        // narrow horizontal support: every V warp filters its own columns (no hand-off)
+        g->t[i].local = ax->max_taps - 1 <= STREAM_LOCAL_MAX_HALO;
+        if (g->t[i].local) local_halo = std::max(local_halo, ax->max_taps - 1);
     }
-    const int tile_w_max = ((STREAM_COLS - (max_taps_x - 1)) / STREAM_PX) * STREAM_PX;
+    // consecutive V warps overlap by the local halo, rounded up to the 4-pixel thread granule
+    g->warp_stride = STREAM_WARP_COLS - (local_halo + STREAM_PX - 1) / STREAM_PX * STREAM_PX;
+    g->slab_cols = 3 * g->warp_stride + STREAM_WARP_COLS;
+    const int tile_w_max = ((g->slab_cols - (max_taps_x - 1)) / STREAM_PX) * STREAM_PX;
     if (tile_w_max < 64) return nullptr;
     g->n_tiles = (W + tile_w_max - 1) / tile_w_max;
     g->tile_w = (((W + g->n_tiles - 1) / g->n_tiles) + STREAM_PX - 1) / STREAM_PX * STREAM_PX;

@@ -39,6 +39,9 @@ struct StreamTargetGeom {
     std::shared_ptr<const AxisPlan> ax, ay;
     std::vector<float> xw;            // normalised fp32 horizontal weights
     std::vector<int32_t> tile_ox;     // [n_tiles+1]
+    bool local = false;               // horizontal pass per V warp (narrow support)
+    std::vector<int32_t> warp_ox;     // local: [n_tiles*4+1]
+    std::vector<int32_t> tile_parts;  // [n_tiles] 0 = generic, P >= 1 = cached with P threads per output
     std::vector<RowRec> rows;         // per-band records
     std::vector<int32_t> band_rec_off;// [n_bands]
     std::vector<int32_t> band_tend;   // [n_bands] one past last source row with a contribution
@@ -52,6 +55,7 @@ struct StreamGeom {
     int32_t n_targets = 0;
     bool has_wm = false;
     int32_t tile_w = 0, n_tiles = 0, n_bands = 0;
+    int32_t warp_stride = STREAM_WARP_COLS, slab_cols = STREAM_COLS;
     std::vector<int32_t> band_y;    // [n_bands+1]
     std::vector<int32_t> band_yend; // [n_bands]
     StreamTargetGeom t[2];

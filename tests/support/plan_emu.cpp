@@ -96,10 +96,30 @@ extern "C" int planemu_run(const uint8_t *src, int stride, int W, int H, int n_t
                         for (int ox = tg.tile_ox[tile]; ox < tg.tile_ox[tile + 1]; ox++) {
                             const int k0 = tg.ax->off[ox], n = tg.ax->off[ox + 1] - k0;
                             const int e0 = tg.ax->first[ox] + sp[t].rect_x - cx0;
-                            if (e0 < 0 || e0 + n > STREAM_COLS) return -2;
-                            float s[4] = {0, 0, 0, 0};
-                            for (int kk = 0; kk < n; kk++)
-                                for (int ch = 0; ch < 4; ch++) s[ch] = std::fmaf(row[(size_t)(e0 + kk) * 4 + ch], tg.xw[k0 + kk], s[ch]);
+                            if (e0 < 0 || e0 + n > g->slab_cols) return -2;
+                            // horizontal sum in the kernel's order: P threads per output, each over
+                            // its interleaved taps in order, then an xor-butterfly of the partial sums
+                            const int P = std::max(tg.tile_parts[tile], 1);
+                            if (tg.local) { // must lie inside the owning warp's 128 loaded columns
+                                int w = 0;
+                                while (w < 3 && ox >= tg.warp_ox[(size_t)tile * 4 + w + 1]) w++;
+                                if (ox < tg.warp_ox[(size_t)tile * 4 + w] || e0 < w * g->warp_stride ||
+                                    e0 + n > w * g->warp_stride + STREAM_WARP_COLS) return -5;
+                            }
+                            float part[32][4];
+                            for (int pp = 0; pp < P; pp++)
+                                for (int ch = 0; ch < 4; ch++) {
+                                    float a = 0.f;
+                                    for (int kk = pp; kk < n; kk += P) a = std::fmaf(row[(size_t)(e0 + kk) * 4 + ch], tg.xw[k0 + kk], a);
+                                    part[pp][ch] = a;
+                                }
+                            for (int off = 1; off < P; off <<= 1) {
+                                float nx[32][4];
+                                for (int pp = 0; pp < P; pp++)
+                                    for (int ch = 0; ch < 4; ch++) nx[pp][ch] = part[pp][ch] + part[pp ^ off][ch];
+                                memcpy(part, nx, sizeof nx);
+                            }
+                            float s[4] = {part[0][0], part[0][1], part[0][2], part[0][3]};
                             for (int ch = 0; ch < 3; ch++) s[ch] = std::fmin(s[ch], s[3]);
                             bool amb = false;
                             uint8_t *d = dsts[t] + ((size_t)oy * sp[t].dw + ox) * 4;
