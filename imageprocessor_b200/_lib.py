@@ -74,6 +74,11 @@ EXPORTS = [
     "ipg_copy_to_device", "ipg_copy_from_device", "ipg_submit", "ipg_submit_on", "ipg_wait",
     "ipg_flush", "ipg_get_stats", "ipg_reset_stats", "ipg_keep_aspect_dims", "ipg_thumb_fit_dims", "ipg_crop_square",
 ]
+# ... and include/ipgpu_host.h
+HOST_EXPORTS = [
+    "iph_processor_new", "iph_processor_free", "iph_process", "iph_process_batch", "iph_free", "iph_last_error",
+    "iph_parse_color", "iph_watermark_height_px", "iph_watermark_anchor", "iph_generate_path", "iph_content_type",
+]
 
 _lib = None
 

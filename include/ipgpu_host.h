@@ -14,6 +14,9 @@
  *                      Thumbnailer.Process / cropAndResize  operations/thumbnail.go:25-132
  *                      Watermarker.Process / addTextWatermark / parseColor
  *                                                           operations/watermark.go:40-190
+ *                      freetype.Context.DrawString / glyph  golang/freetype@e2365dfdc4a0 freetype.go
+ *                      (pen movement, kerning, the (glyph, quarter-pixel) mask cache, the
+ *                       per-rune DrawMask rectangle with mask point (0, dr.Min.Y - glyphRect.Min.Y))
  *   iph_process_batch  Worker.processWorker / processMessage internal/worker/worker.go:112-234,
  *                      reshaped to take a batch of decoded images (the one loop the GPU
  *                      path changes): all tickets are submitted, then awaited.
@@ -39,7 +42,7 @@ typedef struct iph_processor iph_processor;
 /* *image.Alpha mask of one rune plus its placement, as truetype/raster produce it for
  * freetype.Context.glyph(): mask bounds offset by (off_x, off_y) from the integer pen. */
 typedef struct {
-    int32_t advance_26_6;      /* advance width, fixed.Int26_6 */
+    int32_t advance_26_6;      /* Font.HMetric(scale, index).AdvanceWidth: what DrawString moves the pen by */
     int32_t off_x, off_y;      /* mask origin relative to (pen.X>>6, pen.Y>>6) */
     int32_t mask_w, mask_h, mask_stride;
     const uint8_t *mask;       /* valid until the next glyph_mask call on this user */
@@ -58,20 +61,25 @@ typedef struct {
     /* truetype.Face.GlyphAdvance(rune): returns 0 and the advance, or non-zero if the face
      * lacks the rune (then it adds nothing to the width, watermark.go:110-115). */
     int (*glyph_advance)(void *user, uint32_t rune, double font_size, int32_t *advance_26_6);
-    /* freetype.Context.glyph(index, p): mask at sub-pixel (fx, fy) = (p.X & 63, p.Y & 63). */
+    /* freetype.Context.rasterize(index, fx, fy): mask at sub-pixel (fx, fy) = (p.X & 63, p.Y & 63). */
     int (*glyph_mask)(void *user, uint32_t rune, double font_size, int fx, int fy, iph_glyph *out);
+    /* Font.Kern(scale, prev, index), 26.6; may be NULL (no kerning). */
+    int32_t (*kern)(void *user, uint32_t prev_rune, uint32_t rune, double font_size);
 } iph_callbacks;
 
+/* ctx may be NULL for host-only use (parameter handling, paths, JSON): raster work then
+ * fails with "no raster engine" -- there is no CPU fallback. */
 IPG_API iph_processor *iph_processor_new(ipg_ctx *ctx, const iph_callbacks *cb);
 IPG_API void iph_processor_free(iph_processor *p);
 
 /* ImageProcessor.Process on an already decoded image.  task_json is the broker message
  * value (ProcessingTask); decoded_format what image.Decode returned ("jpeg", "png", "gif").
+ * img == NULL stands for a failed image.Decode (decode_error = its message, may be NULL).
  * *result_json receives the ProcessingResult marshalled as encoding/json would (free with
  * iph_free).  Returns 0 when Process returns a nil error, -1 otherwise; like the reference
  * a populated result comes back in both cases and the error text is in iph_last_error(). */
 IPG_API int iph_process(iph_processor *p, const char *task_json, const ipg_image_desc *img,
-                        const char *decoded_format, char **result_json);
+                        const char *decoded_format, const char *decode_error, char **result_json);
 
 /* The batching processWorker: n messages with their decoded images.  Every task's raster
  * work is submitted before any is awaited, so the engine coalesces them into batched

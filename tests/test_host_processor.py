@@ -1,0 +1,226 @@
+"""The host layer (include/ipgpu_host.h) against the reference's own behaviour:
+processor.ImageProcessor.Process (internal/usecase/processor/image_processor.go:39-182),
+the three operations' parameter handling (operations/resize.go:26-59, thumbnail.go:25-46,
+watermark.go:40-60,159-190) and the task/result schema (internal/domain/task.go:3-23).
+
+not gpu: everything that happens before/after the raster call.
+gpu    : Process end to end; stored objects compared byte for byte with the oracle.
+"""
+import json
+
+import numpy as np
+import pytest
+
+from imageprocessor_b200 import processor as P
+from tests.util import rgba_random
+
+CANONICAL_OPS = [   # internal/http-server/handler/image/image.go:222-277
+    {"Type": "thumbnail", "Parameters": {"size": 200, "crop_to_fit": True}},
+    {"Type": "resize", "Parameters": {"width": 1024, "height": 768, "keep_aspect": True}},
+    {"Type": "watermark", "Parameters": {"text": "© ImageProcessor", "opacity": 0.5, "position": "bottom-right"}},
+]
+
+
+def task(ops, fmt="", image_id="img-1"):
+    # usecase/image/image.go:85-93: no json tags, so the keys are the Go field names
+    return {"ID": "task-1", "ImageID": image_id, "OriginalPath": "original/2024/01/01/1.jpg", "Bucket": "images",
+            "Operations": ops, "Format": fmt}
+
+
+# ---- host-only ------------------------------------------------------------------------
+def test_parse_color_matches_reference_rules():
+    assert P.parse_color("255,255,255", 0.5) == (0, (255, 255, 255, 127))      # uint8(255*0.5) truncates
+    assert P.parse_color(" 10, 300 , -5 ", 1.0) == (0, (10, 255, 0, 255))      # spaces stripped, clamped
+    assert P.parse_color("1,2,3,40", 0.5) == (0, (1, 2, 3, 40))                # explicit alpha wins
+    assert P.parse_color("1,2,3,x", 0.25) == (0, (1, 2, 3, 63))                # bad alpha -> opacity
+    assert P.parse_color("red", 0.5) == (-1, (0, 0, 0, 127))                   # caller falls back to black
+    assert P.parse_color("1,2", 0.5)[0] == -1 and P.parse_color("1,2,3,4,5", 0.5)[0] == -1
+    assert P.parse_color("1.5,2,3", 0.5)[0] == -1                              # strconv.Atoi rejects floats
+
+
+def test_watermark_geometry():
+    assert P.watermark_height_px(36) == 44 and P.watermark_height_px(12) == 15
+    W, H, w, h = 4000, 3000, 300, 44
+    assert P.watermark_anchor("bottom-right", W, H, w, h) == (3680, 2980)
+    assert P.watermark_anchor("top-left", W, H, w, h) == (20, 64)
+    assert P.watermark_anchor("top-right", W, H, w, h) == (3680, 64)
+    assert P.watermark_anchor("top-center", W, H, w, h) == (1850, 64)
+    assert P.watermark_anchor("bottom-left", W, H, w, h) == (20, 2980)
+    assert P.watermark_anchor("bottom-center", W, H, w, h) == (1850, 2980)
+    assert P.watermark_anchor("center", W, H, w, h) == (1850, 1522)
+    assert P.watermark_anchor("nonsense", W, H, w, h) == (3680, 2980)
+    assert P.watermark_anchor("center", 100, 30, 301, 44) == (-100, 37)         # Go '/' truncates toward zero
+
+
+def test_generate_path_and_content_type():
+    gp = P.generate_path
+    assert gp("abc", "resize", "jpeg", {"width": 1024, "height": 768}) == "processed/resize/abc/1024x768.jpeg"
+    assert gp("abc", "resize", "png", {}) == "processed/resize/abc/0x0.png"                 # requested, not actual, dims
+    assert gp("abc", "thumbnail", "jpeg", {"size": 150}) == "processed/thumbnails/abc/150.jpeg"
+    assert gp("abc", "thumbnail", "gif", {}) == "processed/thumbnails/abc/200.gif"          # DefaultThumbnailSize
+    assert gp("abc", "watermark", "jpeg", {}) == "processed/watermarked/abc/watermarked.jpeg"
+    assert gp("abc", "Rotate", "png", {}) == "processed/rotate/abc/processed.png"
+    ct = P.content_type
+    assert ct("a/b.jpg") == ct("a/b.JPEG") == "image/jpeg" and ct("x.png") == "image/png" and ct("x.gif") == "image/gif"
+    assert ct("x.webp") == "image/webp" and ct("x.bmp") == "image/bmp" and ct("x.tif") == "image/tiff"
+    assert ct("noext") == "image/jpeg" and ct("dir.png/file") == "image/jpeg"
+
+
+def test_process_parameter_errors_without_a_device():
+    """Errors raised before any raster work: same strings, same partial result as the reference."""
+    from imageprocessor_b200 import Image
+    repo = P.MemoryFileRepo()
+    ip_ = P.ImageProcessor(None, repo)
+    img = Image.from_rgba(rgba_random(64, 48, 1))
+    res, err = ip_.process(task([{"Type": "resize", "Parameters": {"height": 10}}]), img)
+    assert err == "operation resize failed: failed to process operation resize: width parameter is required and must be a number"
+    assert res == {"ID": "task-1", "ImageID": "img-1", "Status": "failed", "ProcessedPaths": {},
+                   "Error": "Operation resize failed: failed to process operation resize: width parameter is required and must be a number"}
+    res, err = ip_.process(task([{"Type": "resize", "Parameters": {"width": 10, "height": 0}}]), img)
+    assert err.endswith("width and height must be positive numbers")
+    res, err = ip_.process(task([{"Type": "thumbnail", "Parameters": {"size": -3}}]), img)
+    assert err.endswith("size must be a positive number")
+    res, err = ip_.process(task([{"Type": "rotate", "Parameters": {}}]), img)
+    assert err == "operation rotate failed: unsupported operation type: rotate"          # not wrapped by applyOperation
+    assert res["Error"] == "Operation rotate failed: unsupported operation type: rotate"
+    res, err = ip_.process(task(CANONICAL_OPS), None, decode_error="image: unknown format")
+    assert err == "failed to decode image: image: unknown format" and res["Status"] == "failed"
+    assert res["Error"] == "Failed to decode image: image: unknown format"
+    res, err = ip_.process("{not json", img)
+    assert err.startswith("failed to unmarshal task")
+    res, err = ip_.process(task([]), img)                                             # no operations: completed, nothing saved
+    assert err is None and res["Status"] == "completed" and res["ProcessedPaths"] == {}
+    # raster work without an engine must fail loudly, never fall back
+    res, err = ip_.process(task(CANONICAL_OPS[:1]), img)
+    assert "no raster engine" in err and res["Status"] == "failed"
+    assert repo.objects == {}
+    ip_.close()
+
+
+def test_result_json_is_encoding_json_shaped():
+    from imageprocessor_b200 import Image
+    ip_ = P.ImageProcessor(None, P.MemoryFileRepo())
+    t = task([{"Type": "rotate", "Parameters": {}}], image_id='a<b>&"c ')
+    ip_.process(t, Image.from_rgba(rgba_random(8, 8, 1)))
+    raw = ip_.last_result_json
+    assert raw.startswith('{"ID":"task-1","ImageID":"a\\u003cb\\u003e\\u0026\\"c\\u2028","Status":"failed","ProcessedPaths":{},"Error":')
+    assert json.loads(raw)["ImageID"] == 'a<b>&"c '
+    ip_.close()
+
+
+# ---- end to end on the GPU --------------------------------------------------------------
+def go_drawstring_layout(face, text, size, W, H, px, py):
+    """freetype.Context.DrawString restated for the oracle side of the test (26.6 pen, the
+    (rune, quarter-pixel) mask cache, per-rune clipped rectangle with mask point (0, dy))."""
+    pen_x, pen_y = px * 64, py * 64
+    cache, out = {}, []
+    for ch in text:
+        r = ord(ch)
+        ix, fx, iy, fy = pen_x >> 6, pen_x & 63, pen_y >> 6, pen_y & 63
+        key = (r, fx // 16, fy // 64)
+        if key not in cache:
+            cache[key] = face.mask(r, size, fx, fy)
+        adv, ox, oy, m = cache[key]
+        if m.size:
+            gx0, gy0 = ix + ox, iy + oy
+            x0, y0, x1, y1 = max(gx0, 0), max(gy0, 0), min(gx0 + m.shape[1], W), min(gy0 + m.shape[0], H)
+            if x0 < x1 and y0 < y1:
+                out.append((x0, y0, min(x1, x0 + m.shape[1]), y1, m, 0, y0 - gy0))
+        pen_x += adv
+    return out
+
+
+@pytest.mark.gpu
+def test_process_canonical_task_matches_oracle(engines, oracle):
+    import imageprocessor_b200 as ip
+    w, h = 1600, 1200
+    a = rgba_random(w, h, 77)
+    repo = P.MemoryFileRepo()
+    proc = P.ImageProcessor(engines(ip.PRECISION_EXACT), repo, encode=P.raw_encode)
+    res, err = proc.process(task(CANONICAL_OPS), ip.Image.from_rgba(a), "jpeg")
+    assert err is None
+    assert res == {"ID": "task-1", "ImageID": "img-1", "Status": "completed", "Error": "", "ProcessedPaths": {
+        "thumbnail": "processed/thumbnails/img-1/200.jpeg",
+        "resize": "processed/resize/img-1/1024x768.jpeg",
+        "watermark": "processed/watermarked/img-1/watermarked.jpeg"}}
+    assert {k: v[1] for k, v in repo.objects.items()} == {p: "image/jpeg" for p in res["ProcessedPaths"].values()}
+    R = oracle.Raster.rgba(a)
+    nw, nh = oracle.keep_aspect_dims(w, h, 1024, 768)
+    fmt, got = P.raw_decode(repo.objects["processed/resize/img-1/1024x768.jpeg"][0])
+    assert fmt == "jpeg" and np.array_equal(got, oracle.resize_image(R, nw, nh))
+    _, got = P.raw_decode(repo.objects["processed/thumbnails/img-1/200.jpeg"][0])
+    assert np.array_equal(got, oracle.crop_and_resize(R, 200))
+    # watermark: same glyph source on both sides (PilFace), blend bit-exact
+    face = proc.face
+    text = "© ImageProcessor"
+    width_px = (sum(face.advance_26_6(ord(c), 36.0) for c in text) + 63) >> 6
+    px, py = oracle.watermark_anchor("bottom-right", w, h, width_px, oracle.watermark_height_px(36.0))
+    gl = go_drawstring_layout(face, text, 36.0, w, h, px, py)
+    _, got = P.raw_decode(repo.objects["processed/watermarked/img-1/watermarked.jpeg"][0])
+    want = oracle.watermark(R, (255, 255, 255, 127), [oracle.Glyph(*g) for g in gl])
+    assert np.array_equal(got, want) and not np.array_equal(got, a)
+    proc.close()
+
+
+@pytest.mark.gpu
+def test_process_formats_fit_thumbnail_and_failure_isolation(engines, oracle):
+    import imageprocessor_b200 as ip
+    a = rgba_random(900, 600, 5)
+    repo = P.MemoryFileRepo()
+    proc = P.ImageProcessor(engines(ip.PRECISION_EXACT), repo, encode=P.raw_encode)
+    img = ip.Image.from_rgba(a)
+    # png source, no target format: keeps png; non-crop thumbnail is fit-short-side (thumbnail.go:52-63)
+    ops = [{"Type": "thumbnail", "Parameters": {"size": 100}}, {"Type": "resize", "Parameters": {"width": 300, "height": 300}}]
+    res, err = proc.process(task(ops), img, "png")
+    assert err is None and res["ProcessedPaths"] == {"thumbnail": "processed/thumbnails/img-1/100.png",
+                                                      "resize": "processed/resize/img-1/300x300.png"}
+    fmt, got = P.raw_decode(repo.objects["processed/thumbnails/img-1/100.png"][0])
+    assert fmt == "png" and got.shape[:2] == (100, 150)
+    assert np.array_equal(got, oracle.resize_image(oracle.Raster.rgba(a), 150, 100))
+    _, got = P.raw_decode(repo.objects["processed/resize/img-1/300x300.png"][0])
+    assert np.array_equal(got, oracle.resize_image(oracle.Raster.rgba(a), 300, 300))   # keep_aspect absent: stretched
+    # webp target -> jpeg; watermark of a gif -> jpeg (resize.go:88-90, watermark.go:73-75)
+    res, err = proc.process(task([{"Type": "resize", "Parameters": {"width": 90, "height": 60}}], fmt="webp"), img, "png")
+    assert res["ProcessedPaths"]["resize"].endswith("90x60.jpeg")
+    res, err = proc.process(task([{"Type": "watermark", "Parameters": {}}, {"Type": "thumbnail", "Parameters": {}}]), img, "gif")
+    assert res["ProcessedPaths"] == {"watermark": "processed/watermarked/img-1/watermarked.jpeg",
+                                     "thumbnail": "processed/thumbnails/img-1/200.gif"}
+    # Process stops at the first failing operation; what came before stays saved (image_processor.go:64-75)
+    repo.objects.clear()
+    ops = [{"Type": "thumbnail", "Parameters": {"size": 32, "crop_to_fit": True}}, {"Type": "resize", "Parameters": {"width": "x"}},
+           {"Type": "watermark", "Parameters": {}}]
+    res, err = proc.process(task(ops), img, "jpeg")
+    assert err.startswith("operation resize failed") and res["Status"] == "failed"
+    assert res["ProcessedPaths"] == {"thumbnail": "processed/thumbnails/img-1/32.jpeg"} and list(repo.objects) == ["processed/thumbnails/img-1/32.jpeg"]
+    # SaveProcessed failure
+    repo.fail_on = "resize"
+    res, err = proc.process(task([{"Type": "resize", "Parameters": {"width": 10, "height": 10}}]), img, "jpeg")
+    assert err.startswith("failed to save processed image") and res["Error"].startswith("Failed to save processed image")
+    repo.fail_on = None
+    proc.close()
+
+
+@pytest.mark.gpu
+def test_process_batch_is_the_batching_worker_loop(engines, oracle):
+    import imageprocessor_b200 as ip
+    e = engines(ip.PRECISION_EXACT)
+    repo = P.MemoryFileRepo()
+    proc = P.ImageProcessor(e, repo, encode=P.raw_encode)
+    imgs = [rgba_random(640 + 16 * k, 480 + 8 * k, 200 + k) for k in range(6)]
+    tasks = [task(CANONICAL_OPS[:2], image_id=f"im{k}") for k in range(6)]
+    tasks[3] = task([{"Type": "resize", "Parameters": {}}], image_id="im3")        # one bad message among good ones
+    b0 = e.stats()["batches"]
+    out = proc.process_batch(tasks, [ip.Image.from_rgba(a) for a in imgs], ["jpeg"] * 6)
+    assert e.stats()["batches"] - b0 < 5          # tickets were coalesced, not one launch sequence per image
+    for k, ((res, err), a) in enumerate(zip(out, imgs)):
+        if k == 3:
+            assert err and res["Status"] == "failed" and res["ProcessedPaths"] == {}
+            continue
+        assert err is None and res["Status"] == "completed"
+        h, w = a.shape[:2]
+        nw, nh = oracle.keep_aspect_dims(w, h, 1024, 768)
+        _, got = P.raw_decode(repo.objects[f"processed/resize/im{k}/1024x768.jpeg"][0])
+        assert np.array_equal(got, oracle.resize_image(oracle.Raster.rgba(a), nw, nh))
+        _, got = P.raw_decode(repo.objects[f"processed/thumbnails/im{k}/200.jpeg"][0])
+        assert np.array_equal(got, oracle.crop_and_resize(oracle.Raster.rgba(a), 200))
+    proc.close()
