@@ -17,9 +17,12 @@
  *   - operations/thumbnail.go:48-64,114-132   (fit dims, cropAndResize)
  *   - operations/watermark.go:86-157,159-190  (draw.Draw Src, DrawString,
  *                                              parseColor, clamp)
- * It is pinned instead by known-answer tests derived from the formulae and by
- * an independent cross-check (torch antialiased bilinear in fp64 + the x/image
- * quantiser); see tests/test_oracle_*.py and oracle/verify_with_go/.
+ * It is pinned instead by fixtures computed with independent code (PyTorch's
+ * antialiased bilinear in float64 + the x/image quantiser; big-int
+ * drawGlyphOver; hand-derived geometry): tests/golden/make_golden.py ->
+ * tests/golden/golden_v1.npz, checked by tests/test_golden.py.
+ * oracle/verify_with_go/ regenerates them from the real reference
+ * dependencies the first time a Go toolchain is available.
  */
 #ifndef IP_ORACLE_H
 #define IP_ORACLE_H

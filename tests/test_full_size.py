@@ -1,0 +1,74 @@
+"""BASELINE.json's full sizes on the GPU: the 12 MP and 8K configurations against the oracle
+(a few seconds of CPU each), plus size-independent properties of the path."""
+import numpy as np
+import pytest
+
+import imageprocessor_b200 as ip
+from imageprocessor_b200 import glyphs as G
+from tests.util import rgba_random, rgba_gradient
+
+pytestmark = pytest.mark.gpu
+
+
+def full_pipeline(e, a, text="© ImageProcessor"):
+    h, w = a.shape[:2]
+    nw, nh = ip.keep_aspect_dims(w, h, 1024, 768)
+    cx, cy, cs = ip.crop_square(w, h)
+    gl = G.layout_watermark(w, h, text)
+    col, _ = G.parse_color("255,255,255", 0.5)
+    out = e.run(ip.Image.from_rgba(a), [ip.OpSpec.resize(nw, nh), ip.OpSpec.thumb_crop((cx, cy, cs, cs), 200),
+                                          ip.OpSpec.watermark(w, h, col, gl)])
+    return out, (nw, nh), gl, col
+
+
+@pytest.mark.parametrize("w,h,gen", [(4000, 3000, "random"), (4000, 3000, "gradient"), (7680, 4320, "random"), (3000, 4000, "random")])
+def test_baseline_sizes_bit_exact(engines, oracle, w, h, gen):
+    a = rgba_random(w, h, 1000) if gen == "random" else rgba_gradient(w, h)
+    e = engines(ip.PRECISION_EXACT, lane_device_bytes=2 << 30)
+    f0 = e.stats()["exact_fallbacks"]
+    out, (nw, nh), gl, col = full_pipeline(e, a)
+    assert e.stats()["exact_fallbacks"] == f0, "the streaming kernel must take these geometries"
+    assert (nw, nh) == {(4000, 3000): (1024, 768), (7680, 4320): (1024, 576), (3000, 4000): (576, 768)}[(w, h)]
+    R = oracle.Raster.rgba(a)
+    assert np.array_equal(out[0], oracle.resize_image(R, nw, nh))
+    assert np.array_equal(out[1], oracle.crop_and_resize(R, 200))
+    og = [oracle.Glyph(g.x0, g.y0, g.x1, g.y1, g.mask, g.mp_x, g.mp_y) for g in gl]
+    assert np.array_equal(out[2], oracle.watermark(R, col, og))
+
+
+def test_fast_mode_12mp_within_one_and_mismatch_fraction(engines, oracle):
+    a = rgba_random(4000, 3000, 1001)
+    out, (nw, nh), *_ = full_pipeline(engines(ip.PRECISION_FAST), a)
+    R = oracle.Raster.rgba(a)
+    for got, want in ((out[0], oracle.resize_image(R, nw, nh)), (out[1], oracle.crop_and_resize(R, 200))):
+        d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+        frac = float((d > 0).mean())
+        print(f"fast mode mismatch fraction {frac:.2e}")
+        assert d.max() <= 1 and frac < 1e-3          # north_star tolerance: max |diff| <= 1, fraction reported
+
+
+def test_properties_at_full_size(engines):
+    e = engines(ip.PRECISION_EXACT, lane_device_bytes=2 << 30)
+    # a constant image stays that constant through both resamplers; the watermark only touches its glyph box
+    a = np.empty((3000, 4000, 4), np.uint8)
+    a[...] = (37, 201, 90, 255)
+    out, (nw, nh), gl, col = full_pipeline(e, a)
+    assert (out[0] == a[0, 0]).all() and (out[1] == a[0, 0]).all()
+    x0, y0 = min(g.x0 for g in gl), min(g.y0 for g in gl)
+    x1, y1 = max(g.x1 for g in gl), max(g.y1 for g in gl)
+    outside = np.ones(a.shape[:2], bool)
+    outside[y0:y1, x0:x1] = False
+    assert np.array_equal(out[2][outside], a[outside]) and not np.array_equal(out[2][y0:y1, x0:x1], a[y0:y1, x0:x1])
+    # 1:1 resize is the identity on valid premultiplied input; transparent images stay transparent
+    b = rgba_random(1024, 768, 5, "premul")
+    assert np.array_equal(e.run(ip.Image.from_rgba(b), [ip.OpSpec.resize(1024, 768)])[0], b)
+    z = np.zeros((1200, 1600, 4), np.uint8)
+    o = e.run(ip.Image.from_rgba(z), [ip.OpSpec.resize(1024, 768), ip.OpSpec.thumb_crop((200, 0, 1200, 1200), 200)])
+    assert not o[0].any() and not o[1].any()
+    # linearity of the filter up to the quantiser: resize(255 - a) == 255 - resize(a) within 1 on opaque input
+    c = rgba_random(2000, 1500, 6)
+    inv = c.copy()
+    inv[..., :3] = 255 - c[..., :3]
+    r1 = e.run(ip.Image.from_rgba(c), [ip.OpSpec.resize(512, 384)])[0].astype(np.int16)
+    r2 = e.run(ip.Image.from_rgba(inv), [ip.OpSpec.resize(512, 384)])[0].astype(np.int16)
+    assert np.abs((255 - r1[..., :3]) - r2[..., :3]).max() <= 1
