@@ -33,7 +33,7 @@ class IpgError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("precision", C.c_int32), ("lanes_per_device", C.c_int32),
-                ("max_batch", C.c_int32), ("batch_window_us", C.c_int32), ("reserved0", C.c_int32),
+                ("max_batch", C.c_int32), ("batch_window_us", C.c_int32), ("fuse_targets", C.c_int32),
                 ("lane_device_bytes", C.c_uint64), ("lane_pinned_bytes", C.c_uint64)]
 
 

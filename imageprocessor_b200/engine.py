@@ -134,7 +134,7 @@ class Engine:
 
     def __init__(self, devices: Optional[Sequence[int]] = None, precision: int = L.PRECISION_EXACT,
                  lanes_per_device: int = 3, max_batch: int = 16, batch_window_us: int = 200,
-                 lane_device_bytes: int = 0, lane_pinned_bytes: int = 0):
+                 lane_device_bytes: int = 0, lane_pinned_bytes: int = 0, fuse_targets: int = 0):
         lib = L.load()
         cfg = L.Config()
         cfg.struct_size = C.sizeof(L.Config)
@@ -142,6 +142,7 @@ class Engine:
         cfg.lanes_per_device = lanes_per_device
         cfg.max_batch = max_batch
         cfg.batch_window_us = batch_window_us
+        cfg.fuse_targets = fuse_targets
         cfg.lane_device_bytes = lane_device_bytes
         cfg.lane_pinned_bytes = lane_pinned_bytes
         ctx = C.c_void_p()

@@ -21,10 +21,11 @@ def full_pipeline(e, a, text="© ImageProcessor"):
     return out, (nw, nh), gl, col
 
 
-@pytest.mark.parametrize("w,h,gen", [(4000, 3000, "random"), (4000, 3000, "gradient"), (7680, 4320, "random"), (3000, 4000, "random")])
-def test_baseline_sizes_bit_exact(engines, oracle, w, h, gen):
+@pytest.mark.parametrize("w,h,gen,fuse", [(4000, 3000, "random", 1), (4000, 3000, "gradient", 2), (7680, 4320, "random", 1),
+                                          (3000, 4000, "random", 2)])
+def test_baseline_sizes_bit_exact(engines, oracle, w, h, gen, fuse):
     a = rgba_random(w, h, 1000) if gen == "random" else rgba_gradient(w, h)
-    e = engines(ip.PRECISION_EXACT, lane_device_bytes=2 << 30)
+    e = engines(ip.PRECISION_EXACT, lane_device_bytes=2 << 30, fuse_targets=fuse)
     f0 = e.stats()["exact_fallbacks"]
     out, (nw, nh), gl, col = full_pipeline(e, a)
     assert e.stats()["exact_fallbacks"] == f0, "the streaming kernel must take these geometries"

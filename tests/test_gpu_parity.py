@@ -66,14 +66,15 @@ def test_watermark_bit_exact(engines, oracle, w, h):
     assert not np.array_equal(out[0], a)      # the blend did something
 
 
-def test_full_pipeline_one_pass(engines, oracle):
+@pytest.mark.parametrize("fuse", [1, 2])
+def test_full_pipeline_one_pass(engines, oracle, fuse):
     w, h = 1600, 1200
     a = rgba_gradient(w, h)
     gl = synthetic_glyphs(w, h, 1, n=10)
     col = (255, 255, 255, 127)
     ops, (nw, nh) = _ops_resize_thumb(w, h)
     ops.append(ip.OpSpec.watermark(w, h, col, [ip.GlyphMask(*g) for g in gl]))
-    e = engines(ip.PRECISION_EXACT)
+    e = engines(ip.PRECISION_EXACT, fuse_targets=fuse)      # one pass per target (default) / both targets fused
     k0 = e.stats()["kernels_launched"]
     out = e.run(ip.Image.from_rgba(a), ops)
     assert e.stats()["kernels_launched"] > k0

@@ -209,9 +209,11 @@ def test_process_batch_is_the_batching_worker_loop(engines, oracle):
     imgs = [rgba_random(640 + 16 * k, 480 + 8 * k, 200 + k) for k in range(6)]
     tasks = [task(CANONICAL_OPS[:2], image_id=f"im{k}") for k in range(6)]
     tasks[3] = task([{"Type": "resize", "Parameters": {}}], image_id="im3")        # one bad message among good ones
+    proc.process_batch(tasks, [ip.Image.from_rgba(a) for a in imgs], ["jpeg"] * 6)   # warms the pinned output buffers
+    repo.objects.clear()
     b0 = e.stats()["batches"]
     out = proc.process_batch(tasks, [ip.Image.from_rgba(a) for a in imgs], ["jpeg"] * 6)
-    assert e.stats()["batches"] - b0 < 5          # tickets were coalesced, not one launch sequence per image
+    assert e.stats()["batches"] - b0 <= 3         # tickets were coalesced, not one launch sequence per image
     for k, ((res, err), a) in enumerate(zip(out, imgs)):
         if k == 3:
             assert err and res["Status"] == "failed" and res["ProcessedPaths"] == {}
