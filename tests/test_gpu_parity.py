@@ -178,3 +178,30 @@ def test_error_paths(engines):
     # zero-sized output (e.g. keep-aspect of an extreme strip) is an empty image, not an error
     out = e.run(ip.Image.from_rgba(a), [ip.OpSpec.resize(0, 5)])
     assert out[0].size == 0
+
+
+def test_mixed_size_stream(engines, oracle):
+    """BASELINE configs[4] in miniature: a seeded stream of odd sizes and aspect ratios (portrait, square,
+    panoramic, tiny), every image through all three operations, tickets in flight together."""
+    e = engines(ip.PRECISION_EXACT)
+    rng = np.random.default_rng(77)
+    shapes = [(int(rng.integers(40, 1900)), int(rng.integers(40, 1300))) for _ in range(14)]
+    shapes += [(1, 1), (3, 2), (2048, 17), (19, 1500), (1024, 768), (200, 200)]
+    work = []
+    for k, (w, h) in enumerate(shapes):
+        a = rgba_random(w, h, 3000 + k, ["opaque", "premul", "raw"][k % 3])
+        nw, nh = ip.keep_aspect_dims(w, h, 1024, 768)
+        cx, cy, cs = ip.crop_square(w, h)
+        gl = synthetic_glyphs(w, h, k, n=4)
+        col = (255, 255, 255, 127)
+        ops = [ip.OpSpec.resize(nw, nh), ip.OpSpec.thumb_crop((cx, cy, cs, cs), 200),
+               ip.OpSpec.watermark(w, h, col, [ip.GlyphMask(*g) for g in gl])]
+        work.append((a, (nw, nh), gl, col, e.submit(ip.Image.from_rgba(a), ops)))
+    for a, (nw, nh), gl, col, t in work:
+        out = e.wait(t)
+        R = oracle.Raster.rgba(a)
+        h, w = a.shape[:2]
+        if nw > 0 and nh > 0:
+            assert np.array_equal(out[0], oracle.resize_image(R, nw, nh)), f"resize {w}x{h} -> {nw}x{nh}"
+        assert np.array_equal(out[1], oracle.crop_and_resize(R, 200)), f"thumb {w}x{h}"
+        assert np.array_equal(out[2], oracle.watermark(R, col, [oracle.Glyph(*g) for g in gl])), f"watermark {w}x{h}"

@@ -102,3 +102,37 @@ def test_single_target_and_identity(emu, oracle):
     ref = oracle.resize_image(oracle.Raster.rgba(a), 500, 333)
     amb = flags[0] == 1
     assert np.array_equal(dsts[0][~amb], ref[~amb])
+
+
+def test_stream_plan_random_geometries(emu, oracle):
+    """Seeded sweep over odd sizes, aspect ratios and scales (the mixed-size stream of BASELINE configs[4],
+    shrunk so the oracle stays fast): whatever the planner accepts must be a partition of the outputs and
+    certified; whatever it rejects must be a vertical upscale or a support wider than a slab."""
+    rng = np.random.default_rng(4242)
+    accepted = 0
+    for case in range(40):
+        w, h = int(rng.integers(33, 1400)), int(rng.integers(33, 1100))
+        rw, rh = int(rng.integers(16, 1100)), int(rng.integers(16, 800))
+        size = int(rng.integers(8, 220))
+        bands = int(rng.integers(1, 9))
+        a = rgba_random(w, h, 9000 + case, "raw" if case % 3 == 0 else "opaque")
+        nw, nh = oracle.keep_aspect_dims(w, h, rw, rh)
+        if nw <= 0 or nh <= 0:
+            continue
+        cx, cy, cs = oracle.crop_square(w, h)
+        R = oracle.Raster.rgba(a)
+        for spec, two_stage, ref in (((0, 0, w, h, nw, nh), 0, lambda: oracle.resize_image(R, nw, nh)),
+                                     ((cx, cy, cs, cs, size, size), 1, lambda: oracle.crop_and_resize(R, size))):
+            rc, dsts, flags, info = run_emu(emu, a, [spec], [two_stage], bands)
+            if rc == -1:
+                assert spec[5] > spec[3] or spec[2] / spec[4] > 200, f"planner rejected a streamable geometry {spec}"
+                continue
+            assert rc == 0, f"emulator error {rc} for {spec} in {w}x{h}"
+            accepted += 1
+            want = ref()
+            f = flags[0]
+            assert np.all((f == 16) | (f == 1)), f"outputs not written exactly once for {spec}"
+            amb = f == 1
+            diff = np.abs(dsts[0].astype(int) - want.astype(int)).max(axis=2)
+            assert diff[~amb].max(initial=0) == 0 and diff.max(initial=0) <= 1, f"certification broken for {spec} in {w}x{h}"
+    assert accepted >= 40
