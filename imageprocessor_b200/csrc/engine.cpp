@@ -226,12 +226,16 @@ struct Batch {
     int n_kernels = 0;
     uint64_t h2d = 0, d2h = 0;
     uint64_t exact_fallbacks = 0;
+    uint64_t fast_jobs = 0;
     bool has_fix = false;
 };
 
 struct Lane {
     cudaStream_t st = nullptr;
+    cudaStream_t st2 = nullptr;     // side stream: the general k_stream launch that does not depend on the lean one
+    cudaEvent_t fork = nullptr, join = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evf = nullptr;      // after the lean k_stream launch
     cudaEvent_t begin = nullptr;    // before the batch's first H2D (upload stream)
     cudaEvent_t uploaded = nullptr; // after its last H2D (upload stream)
     cudaEvent_t done = nullptr;     // after its last D2H (download stream)
@@ -280,10 +284,12 @@ struct Ctx {
     // even though the source is read twice -- measured 32.0 vs 39.0 us per 12 MP image.  ipg_config.fuse_targets = 2
     // (or IPG_FUSE_TARGETS=2) restores the single pass.
     int fuse_targets = 1;
+    bool overlap_streams = true; // IPG_NO_OVERLAP=1: lean and general k_stream launches back to back (per-kernel timing)
     // stats
     std::atomic<uint64_t> s_done{0}, s_batches{0}, s_kernels{0}, s_h2d{0}, s_d2h{0}, s_fix{0}, s_fallback{0}, s_staged{0};
     std::mutex smu;
-    double s_stream_ms = 0, s_fix_ms = 0, s_other_ms = 0;
+    double s_stream_ms = 0, s_fix_ms = 0, s_other_ms = 0, s_fast_ms = 0;
+    std::atomic<uint64_t> s_fast_jobs{0};
 };
 
 } // namespace ipg
@@ -389,7 +395,13 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     Blob blob{L.param_host, blob_dev, L.param_cap};
 
     std::vector<StreamJob> sjobs;
-    std::vector<StreamItem> sitems;
+    std::vector<StreamItem> sitems;   // general k_stream instantiations, independent of the lean launch
+    std::vector<StreamItem> ritems;   // general k_stream instantiation: on-demand redo of lean jobs
+    std::vector<StreamItem> fitems;   // lean instantiation
+    bool any_wm_fast = false;
+    size_t max_jobs = 0;
+    for (auto &tp : B.tickets) max_jobs += tp->ops.size() + 1;
+    int32_t *redo_flags = (int32_t *)arena.take(4 * max_jobs + 256); // one per stream job, raised on the device
     std::vector<ExactJob> fixjobs;    // one per stream target (EXACT mode)
     std::vector<ExactJob> xjobs;      // whole-output fp64 jobs
     std::vector<ExactItem> xitems;
@@ -608,13 +620,26 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                     if (o.two_stage && !t.src.opaque_hint) j.check_premul = 1;
                 }
                 if (wm) j.wm = make_wm(*wm);
-                max_nt = std::max(max_nt, nt);
-                any_wm |= wm != nullptr;
                 const int ji = (int)sjobs.size();
+                // the lean instantiation takes the common case; it needs TMA-storable watermark rows
+                const bool wm_tma_ok = !wm || ((sv.w % 4) == 0 && ((((uintptr_t)wm->dev_out) | (uintptr_t)wm->dev_pitch) & 15) == 0);
+                j.fast_path = geom->lean_ok && wm_tma_ok && redo_flags && (size_t)ji < max_jobs;
+                j.redo_flag = (j.fast_path && !t.src.opaque_hint) ? redo_flags + ji : nullptr;
                 sjobs.push_back(j);
+                if (!j.fast_path) {
+                    max_nt = std::max(max_nt, nt);
+                    any_wm |= wm != nullptr;
+                } else {
+                    any_wm_fast |= wm != nullptr;
+                    B.fast_jobs++;
+                }
                 for (auto it : geom->items) {
                     it.job = ji;
-                    sitems.push_back(it);
+                    if (!j.fast_path) sitems.push_back(it);
+                    else {
+                        fitems.push_back(it);
+                        if (j.redo_flag) ritems.push_back(it);
+                    }
                 }
             }
         } else {
@@ -650,6 +675,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     // ---- parameter blob upload
     const StreamJob *d_sjobs = blob.dptr<const StreamJob>(blob.put(sjobs.data(), sjobs.size() * sizeof(StreamJob), 16));
     const StreamItem *d_sitems = blob.dptr<const StreamItem>(blob.put(sitems.data(), sitems.size() * sizeof(StreamItem), 16));
+    const StreamItem *d_fitems = blob.dptr<const StreamItem>(blob.put(fitems.data(), fitems.size() * sizeof(StreamItem), 16));
+    const StreamItem *d_ritems = blob.dptr<const StreamItem>(blob.put(ritems.data(), ritems.size() * sizeof(StreamItem), 16));
     const ExactJob *d_fixjobs = blob.dptr<const ExactJob>(blob.put(fixjobs.data(), fixjobs.size() * sizeof(ExactJob), 16));
     const ExactJob *d_xjobs = blob.dptr<const ExactJob>(blob.put(xjobs.data(), xjobs.size() * sizeof(ExactJob), 16));
     const ExactItem *d_xitems = blob.dptr<const ExactItem>(blob.put(xitems.data(), xitems.size() * sizeof(ExactItem), 16));
@@ -667,11 +694,32 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     // already fills the GPU; overlapping them only makes them evict each other), while the
     // copies of the other lanes overlap with them.
     if (d.last_compute) IPG_CU(cudaStreamWaitEvent(st, d.last_compute, 0));
+    if (!fitems.empty() && redo_flags) IPG_CU(cudaMemsetAsync(redo_flags, 0, 4 * max_jobs, st));
     IPG_CU(cudaEventRecord(L.ev[0], st));
-    if (!sitems.empty()) {
+    // The general launch over jobs the lean kernel does not take runs beside the lean launch on a side
+    // stream (each fills the other's ramp and tail); the on-demand redo of lean jobs follows the lean launch.
+    const bool side = !fitems.empty() && !sitems.empty() && c.overlap_streams;
+    if (side) {
+        IPG_CU(cudaEventRecord(L.fork, st));
+        IPG_CU(cudaStreamWaitEvent(L.st2, L.fork, 0));
+        IPG_CU(launch_stream(d_sjobs, d_sitems, (int)sitems.size(), max_nt, any_wm, fix, L.st2));
+        IPG_CU(cudaEventRecord(L.join, L.st2));
+        B.n_kernels++;
+    }
+    if (!fitems.empty()) {
+        IPG_CU(launch_stream_fast(d_sjobs, d_fitems, (int)fitems.size(), any_wm_fast, fix, st));
+        B.n_kernels++;
+    }
+    IPG_CU(cudaEventRecord(L.evf, st));
+    if (!side && !sitems.empty()) {
         IPG_CU(launch_stream(d_sjobs, d_sitems, (int)sitems.size(), max_nt, any_wm, fix, st));
         B.n_kernels++;
     }
+    if (!ritems.empty()) {
+        IPG_CU(launch_stream(d_sjobs, d_ritems, (int)ritems.size(), 1, any_wm_fast, fix, st));
+        B.n_kernels++;
+    }
+    if (side) IPG_CU(cudaStreamWaitEvent(st, L.join, 0));
     IPG_CU(cudaEventRecord(L.ev[1], st));
     if (!fixjobs.empty()) {
         IPG_CU(launch_exact_fix(d_fixjobs, (int)fixjobs.size(), fix, st));
@@ -804,7 +852,8 @@ static void completer_main(Ctx *c, Device *d)
                 status = IPG_ERR_CUDA;
                 err = cuda_msg("batch execution", e);
             } else {
-                float a = 0, b = 0, o = 0;
+                float a = 0, b = 0, o = 0, f = 0;
+                cudaEventElapsedTime(&f, L.ev[0], L.evf);
                 cudaEventElapsedTime(&a, L.ev[0], L.ev[1]);
                 cudaEventElapsedTime(&b, L.ev[1], L.ev[2]);
                 cudaEventElapsedTime(&o, L.ev[2], L.ev[3]);
@@ -818,6 +867,7 @@ static void completer_main(Ctx *c, Device *d)
                             d->index, B->lane, B->tickets.size(), t0, t1, t2, t3, B->h2d / 1e6, B->d2h / 1e6);
                 std::lock_guard<std::mutex> lk(c->smu);
                 c->s_stream_ms += a;
+                c->s_fast_ms += f;
                 c->s_fix_ms += b;
                 c->s_other_ms += o;
                 if (B->n_kernels > 0) {
@@ -833,6 +883,7 @@ static void completer_main(Ctx *c, Device *d)
             c->s_h2d += B->h2d;
             c->s_d2h += B->d2h;
             c->s_fallback += B->exact_fallbacks;
+            c->s_fast_jobs += B->fast_jobs;
         }
         for (auto &t : B->tickets) finish_ticket(*c, *d, t, status, err);
         {
@@ -1055,6 +1106,7 @@ static void destroy_impl(Ctx *c)
         for (auto &L : d.lanes) {
             if (L.st) cudaStreamSynchronize(L.st);
             for (auto &e : L.ev) if (e) cudaEventDestroy(e);
+            if (L.evf) cudaEventDestroy(L.evf);
             if (L.begin) cudaEventDestroy(L.begin);
             if (L.uploaded) cudaEventDestroy(L.uploaded);
             if (L.done) cudaEventDestroy(L.done);
@@ -1062,6 +1114,9 @@ static void destroy_impl(Ctx *c)
             if (L.param_host) cudaFreeHost(L.param_host);
             if (L.fix_count_host) cudaFreeHost(L.fix_count_host);
             if (L.st) cudaStreamDestroy(L.st);
+            if (L.st2) cudaStreamDestroy(L.st2);
+            if (L.fork) cudaEventDestroy(L.fork);
+            if (L.join) cudaEventDestroy(L.join);
         }
         if (d.up) { cudaStreamSynchronize(d.up); cudaStreamDestroy(d.up); }
         if (d.down) { cudaStreamSynchronize(d.down); cudaStreamDestroy(d.down); }
@@ -1110,6 +1165,7 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
         c->cfg = k;
         c->trace = getenv("IPG_TRACE") && atoi(getenv("IPG_TRACE")) != 0;
         c->fuse_targets = k.fuse_targets == 2 ? 2 : 1;
+        c->overlap_streams = !(getenv("IPG_NO_OVERLAP") && atoi(getenv("IPG_NO_OVERLAP")) != 0);
         if (getenv("IPG_FUSE_TARGETS")) c->fuse_targets = std::min(2, std::max(1, atoi(getenv("IPG_FUSE_TARGETS"))));
         std::vector<int> ids;
         if (device_ids && n > 0) ids.assign(device_ids, device_ids + n);
@@ -1130,7 +1186,11 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
             if (k.lane_device_bytes < param_cap + (128u << 20)) throw std::runtime_error("lane_device_bytes too small (< 160 MiB)");
             for (auto &L : d->lanes) {
                 IPG_CU(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+                IPG_CU(cudaStreamCreateWithFlags(&L.st2, cudaStreamNonBlocking));
+                IPG_CU(cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming));
+                IPG_CU(cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming));
                 for (auto &ev : L.ev) IPG_CU(cudaEventCreate(&ev));
+                IPG_CU(cudaEventCreate(&L.evf));
                 IPG_CU(cudaEventCreate(&L.begin));
                 IPG_CU(cudaEventCreateWithFlags(&L.uploaded, cudaEventDisableTiming));
                 IPG_CU(cudaEventCreate(&L.done));
@@ -1282,6 +1342,8 @@ int ipg_get_stats(ipg_ctx *ctx, ipg_stats *out)
     out->stream_kernel_ms = ctx->s_stream_ms;
     out->fix_kernel_ms = ctx->s_fix_ms;
     out->other_kernel_ms = ctx->s_other_ms;
+    out->stream_fast_kernel_ms = ctx->s_fast_ms;
+    out->fast_jobs = ctx->s_fast_jobs.load();
     out->kernel_ms = ctx->s_stream_ms + ctx->s_fix_ms + ctx->s_other_ms;
     for (auto &d : ctx->devs) {
         if (d->k_last >= 0) out->kernel_span_ms = std::max(out->kernel_span_ms, d->k_last - d->k_first);
@@ -1298,7 +1360,8 @@ int ipg_reset_stats(ipg_ctx *ctx)
     ctx->s_done = 0; ctx->s_batches = 0; ctx->s_kernels = 0; ctx->s_h2d = 0; ctx->s_d2h = 0;
     ctx->s_fix = 0; ctx->s_fallback = 0; ctx->s_staged = 0;
     std::lock_guard<std::mutex> lk(ctx->smu);
-    ctx->s_stream_ms = ctx->s_fix_ms = ctx->s_other_ms = 0;
+    ctx->s_stream_ms = ctx->s_fix_ms = ctx->s_other_ms = ctx->s_fast_ms = 0;
+    ctx->s_fast_jobs = 0;
     for (auto &d : ctx->devs) {
         cudaSetDevice(d->cuda_id);
         cudaEventRecord(d->epoch, d->lanes[0].st);

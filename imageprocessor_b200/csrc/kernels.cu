@@ -468,9 +468,9 @@ template <int NT, int STAGES> struct __align__(128) StreamSmem {
     uint64_t empty[STAGES];                      // the 4 V warps are done with a stage
     XInfo xi[2];                                 // per target; parts = tile_parts of this CTA's tile
 };
-template <int NT> struct StreamCfg {
-    static constexpr int STAGES = NT == 2 ? STREAM_STAGES_2T : STREAM_STAGES_1T;
-    static constexpr int CTAS_PER_SM = NT == 2 ? STREAM_CTAS_2T : STREAM_CTAS_1T;
+template <int NT, bool FAST = false> struct StreamCfg {
+    static constexpr int STAGES = FAST ? STREAM_STAGES_FAST : NT == 2 ? STREAM_STAGES_2T : STREAM_STAGES_1T;
+    static constexpr int CTAS_PER_SM = FAST ? STREAM_CTAS_FAST : NT == 2 ? STREAM_CTAS_2T : STREAM_CTAS_1T;
     using Smem = StreamSmem<NT, STAGES>;
 };
 
@@ -600,6 +600,12 @@ __device__ __forceinline__ void unpack_alpha(const uint4 &c, float2 *va)
 // Park one completed, vertically-filtered row (accumulator set SET) at elements
 // 4*slot .. 4*slot+3 of `buf` (XOR-swizzled) and clear the set.  `sa` is the opaque alpha
 // chain value (ALPHA=false).
+__device__ __forceinline__ void sts128(float4 *p, float x, float y, float z, float w)
+{
+    // volatile: keeps the two accumulator-set variants of an emit in separate (uniform) branches; left
+    // to itself the compiler if-converts them into ~40 FSELs per emit
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 template <int SET, bool ALPHA>
 __device__ __forceinline__ void park_row(VAcc<ALPHA> &S, float sa, float4 *buf, int slot)
 {
@@ -607,10 +613,10 @@ __device__ __forceinline__ void park_row(VAcc<ALPHA> &S, float sa, float4 *buf, 
     const float2 *g = S.rgb[SET];
     float a0 = sa, a1 = sa, a2 = sa, a3 = sa;
     if constexpr (ALPHA) { a0 = S.al[SET][0].x; a1 = S.al[SET][0].y; a2 = S.al[SET][1].x; a3 = S.al[SET][1].y; }
-    buf[base | ((lo + 0) ^ key)] = make_float4(g[0].x, g[0].y, g[1].x, a0);
-    buf[base | ((lo + 1) ^ key)] = make_float4(g[1].y, g[2].x, g[2].y, a1);
-    buf[base | ((lo + 2) ^ key)] = make_float4(g[3].x, g[3].y, g[4].x, a2);
-    buf[base | ((lo + 3) ^ key)] = make_float4(g[4].y, g[5].x, g[5].y, a3);
+    sts128(&buf[base | ((lo + 0) ^ key)], g[0].x, g[0].y, g[1].x, a0);
+    sts128(&buf[base | ((lo + 1) ^ key)], g[1].y, g[2].x, g[2].y, a1);
+    sts128(&buf[base | ((lo + 2) ^ key)], g[3].x, g[3].y, g[4].x, a2);
+    sts128(&buf[base | ((lo + 3) ^ key)], g[4].y, g[5].x, g[5].y, a3);
 #pragma unroll
     for (int i = 0; i < 6; i++) S.rgb[SET][i] = make_float2(0.f, 0.f);
     if constexpr (ALPHA) S.al[SET][0] = S.al[SET][1] = make_float2(0.f, 0.f);
@@ -634,6 +640,46 @@ struct VCtx {
     uint8_t *wm_dst;
     int wm_stride, c, W, ys1;
 };
+
+// The common case, stripped of every test it does not need: one target, active in this tile,
+// in the lane-per-output form, all four rows inside the band, opaque so far, watermark (if any)
+// copied by the producer.  Everything else takes v_rows below.
+template <typename SM>
+__device__ __forceinline__ void v_rows_fast(VAcc<false> &S, const StreamStage &stg, SM &sm, const VCtx &C, const FixList &fix)
+{
+    uint4 cur = stg.rows[0][C.slot];
+#pragma unroll
+    for (int k = 0; k < STREAM_GROUP; k++) {
+        const uint4 nxt = stg.rows[(k + 1) & (STREAM_GROUP - 1)][C.slot];
+        float2 vp[6];
+        unpack_rgb(cur, vp);
+        const float4 r = *reinterpret_cast<const float4 *>(&stg.rec[0].row[k]); // LDS.128 broadcast
+        const float2 w00 = make_float2(r.x, r.x), w11 = make_float2(r.y, r.y);
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            S.rgb[0][i] = __ffma2_rn(vp[i], w00, S.rgb[0][i]);
+            S.rgb[1][i] = __ffma2_rn(vp[i], w11, S.rgb[1][i]);
+        }
+        const int e = stg.rec[0].emit[k];
+        if (e >= 0) { // CTA-uniform: this source row completes output row e>>1, held in set e&1
+            if (e & 1) park_row<1, false>(S, r.w, sm.xbuf[0], C.pslot[0]);
+            else       park_row<0, false>(S, r.z, sm.xbuf[0], C.pslot[0]);
+            __syncwarp();
+            const float4 *buf = sm.xbuf[0];
+            float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < STREAM_XTAPS; q++) { // weight 0 past the end adds exactly nothing
+                const float4 v = buf[swz(C.x0_e0 + q)];
+                const float2 ww = make_float2(C.x0_w[q], C.x0_w[q]);
+                rg = __ffma2_rn(make_float2(v.x, v.y), ww, rg);
+                ba = __ffma2_rn(make_float2(v.z, v.w), ww, ba);
+            }
+            if (C.x0_ox >= 0) xfinish(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
+            __syncwarp(); // the strip is reused by the next emit
+        }
+        cur = nxt;
+    }
+}
 
 // The source rows of one ring stage into every active target; rows are taken one at a
 // time (the next one is requested before this one's math) so the code stays small.
@@ -726,17 +772,26 @@ __device__ __forceinline__ void v_rows(VAcc<ALPHA> *S, const StreamJob &J, const
     }
 }
 
-template <int NT, bool WM>
-__global__ void __launch_bounds__(STREAM_CTA, StreamCfg<NT>::CTAS_PER_SM)
+// FAST (NT == 1 only): the lean instantiation for the common case -- one local target in the
+// lane-per-output form, watermark copied by the producer, every pixel opaque.  It carries none of the
+// general paths, so it fits 4 CTAs per SM in ~96 registers and runs the fused resize + watermark
+// copy near the HBM roofline.  Opacity is checked, not assumed: a warp that meets a non-opaque
+// pixel raises the job's redo flag and the general instantiation, launched right after over the same
+// items, redoes exactly the flagged jobs (it exits at once for the others).
+template <int NT, bool WM, bool FAST>
+__global__ void __launch_bounds__(STREAM_CTA, (StreamCfg<NT, FAST>::CTAS_PER_SM))
 k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ items, FixList fix)
 {
-    constexpr int STAGES = StreamCfg<NT>::STAGES;
-    using Smem = typename StreamCfg<NT>::Smem;
+    static_assert(!FAST || NT == 1, "the lean instantiation has exactly one target");
+    constexpr int STAGES = StreamCfg<NT, FAST>::STAGES;
+    using Smem = typename StreamCfg<NT, FAST>::Smem;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
     const StreamItem it = items[blockIdx.x];
     const StreamJob &J = jobs[it.job];
+    // a job the lean kernel already ran is redone here only if it met a non-opaque pixel
+    if (!FAST && J.fast_path && (J.redo_flag == nullptr || *(volatile const int32_t *)J.redo_flag == 0)) return;
     const int tile = it.tile, band = it.band;
     const int W = J.src.w;
     const int cx0 = tile * J.tile_w;
@@ -779,6 +834,12 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
                 const int P = __ldg(t.tile_parts + tile);
                 if (tid == 0) sm.xi[T] = XInfo{t.dst, t.dst_stride, t.exact_job, (uint32_t)t.fix_d, t.local, P, 0};
                 for (int e = tid; e < STREAM_XBUF; e += STREAM_THREADS) sm.xbuf[T][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (FAST && P == 0) { // a tile without outputs: lanes gather zeros and store nothing
+                    sm.xt.ox[T][tid] = -1;
+                    sm.xt.e0[T][tid] = 0;
+#pragma unroll
+                    for (int k = 0; k < STREAM_XTAPS; k++) sm.xt.w[T][k][tid] = 0.f;
+                }
                 if (P == 0) continue;
                 int ox = -1, e0 = 0, k0 = 0, n = 0, part = 0;
                 if (t.local) { // one output per lane of the owning warp; strip w sits at elements [128 w, 128 w + 128)
@@ -867,7 +928,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
 #pragma unroll
     for (int k = 0; k < STREAM_XTAPS; k++) C.x0_w[k] = 0.f;
     if constexpr (NT > 0) {
-        if (C.act[0] && sm.xi[0].local && sm.xi[0].parts == 1) {
+        if (FAST || (C.act[0] && sm.xi[0].local && sm.xi[0].parts == 1)) {
             C.x0_inline = true;
             C.x0_ox = sm.xt.ox[0][tid];
             C.x0_e0 = sm.xt.e0[0][tid];
@@ -902,18 +963,27 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
         mbar_wait(&sm.full[rs], rph);
         const StreamStage &stg = sm.stage[rs];
         const int nr = yend - ys0 - g * STREAM_GROUP;
-        if (NT > 0) {
+        if (NT > 0 && (!FAST || J.redo_flag != nullptr)) {
             uint32_t m = 0xffffffffu;
 #pragma unroll
             for (int k = 0; k < STREAM_GROUP; k++) {
                 const uint4 q = stg.rows[k][slot];
                 if (k < nr) m = min(m, min(min(q.x, q.y), min(q.z, q.w)));
             }
-            if (__any_sync(0xffffffffu, m < 0xff000000u)) { switch_alpha = true; break; }
+            if (__any_sync(0xffffffffu, m < 0xff000000u)) {
+                if constexpr (FAST) { // not this kernel's case: have the general one redo the job
+                    if ((tid & 31) == 0) atomicExch(J.redo_flag, 1);
+                } else {
+                    switch_alpha = true;
+                    break;
+                }
+            }
         }
-        v_rows<NT, WM, false>(S, J, stg, sm, C, ys0 + g * STREAM_GROUP, nr, fix);
+        if constexpr (FAST) v_rows_fast(S[0], stg, sm, C, fix);
+        else                v_rows<NT, WM, false>(S, J, stg, sm, C, ys0 + g * STREAM_GROUP, nr, fix);
         advance();
     }
+    if constexpr (FAST) return;
     if constexpr (NT > 0) {
         if (!switch_alpha) return;
         // phase 2: first non-opaque pixel this warp meets: materialise the per-pixel alpha lanes from the
@@ -939,18 +1009,18 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
 
 int stream_smem_bytes() { return (int)sizeof(StreamCfg<2>::Smem); }
 
-template <int NT, bool WM>
+template <int NT, bool WM, bool FAST>
 static cudaError_t launch_stream_t(const StreamJob *jobs, const StreamItem *items, int n, FixList fix, cudaStream_t st)
 {
-    using Smem = typename StreamCfg<NT>::Smem;
+    using Smem = typename StreamCfg<NT, FAST>::Smem;
     static bool configured = false; // per instantiation; benign race (idempotent attribute)
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_stream<NT, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_stream<NT, WM, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_stream<NT, WM><<<n, STREAM_CTA, sizeof(Smem), st>>>(jobs, items, fix);
+    k_stream<NT, WM, FAST><<<n, STREAM_CTA, sizeof(Smem), st>>>(jobs, items, fix);
     return cudaGetLastError();
 }
 
@@ -961,12 +1031,21 @@ cudaError_t launch_stream(const StreamJob *jobs, const StreamItem *items, int n_
 {
     if (n_items <= 0) return cudaSuccess;
     switch (max_targets) {
-    case 0: return any_wm ? launch_stream_t<0, true>(jobs, items, n_items, fix, st) : cudaSuccess;
-    case 1: return any_wm ? launch_stream_t<1, true>(jobs, items, n_items, fix, st)
-                          : launch_stream_t<1, false>(jobs, items, n_items, fix, st);
-    default: return any_wm ? launch_stream_t<2, true>(jobs, items, n_items, fix, st)
-                           : launch_stream_t<2, false>(jobs, items, n_items, fix, st);
+    case 0: return any_wm ? launch_stream_t<0, true, false>(jobs, items, n_items, fix, st) : cudaSuccess;
+    case 1: return any_wm ? launch_stream_t<1, true, false>(jobs, items, n_items, fix, st)
+                          : launch_stream_t<1, false, false>(jobs, items, n_items, fix, st);
+    default: return any_wm ? launch_stream_t<2, true, false>(jobs, items, n_items, fix, st)
+                           : launch_stream_t<2, false, false>(jobs, items, n_items, fix, st);
     }
+}
+
+// The lean instantiation over items of jobs with StreamJob::fast_path set.
+cudaError_t launch_stream_fast(const StreamJob *jobs, const StreamItem *items, int n_items, bool any_wm, FixList fix,
+                               cudaStream_t st)
+{
+    if (n_items <= 0) return cudaSuccess;
+    return any_wm ? launch_stream_t<1, true, true>(jobs, items, n_items, fix, st)
+                  : launch_stream_t<1, false, true>(jobs, items, n_items, fix, st);
 }
 
 cudaError_t launch_exact_tiles(const ExactJob *jobs, const ExactItem *items, int n_items, cudaStream_t st)

@@ -10,6 +10,10 @@ namespace ipg {
 cudaError_t launch_stream(const StreamJob *jobs, const StreamItem *items, int n_items,
                           int max_targets, bool any_wm, FixList fix, cudaStream_t st);
 
+// The lean single-target instantiation (k_stream<1, WM, true>) over jobs with fast_path set.
+cudaError_t launch_stream_fast(const StreamJob *jobs, const StreamItem *items, int n_items, bool any_wm,
+                               FixList fix, cudaStream_t st);
+
 // fp64 reference-order resample of whole outputs: one CTA per 32x8 output tile.
 cudaError_t launch_exact_tiles(const ExactJob *jobs, const ExactItem *items, int n_items,
                                cudaStream_t st);

@@ -169,6 +169,9 @@ typedef struct {
      * last kernel end, and first batch H2D start -> last batch D2H end */
     double kernel_span_ms;
     double batch_span_ms;
+    /* of stream_kernel_ms: the lean single-target k_stream instantiation; and the stream jobs it ran */
+    double stream_fast_kernel_ms;
+    uint64_t fast_jobs;
 } ipg_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */
