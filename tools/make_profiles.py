@@ -36,7 +36,7 @@ rep = os.path.join(ROOT, "gpurun_out", f"prof_{ftag}.ncu-rep")
 txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hot.py"), rep, "1.0"], capture_output=True, text=True).stdout
 with open(os.path.join(out, f"{rnd}_k_stream_full.txt"), "w") as f:
     f.write(f"ncu --set full --clock-control none --import-source on -k regex:k_stream -s 1 -c 1\n")
-    f.write(f"command: python tools/profile_step.py --images {n_img} --steps 1 --ops rtw  (one launch = {n_img} 12 MP images)\n")
+    f.write(f"command: python tools/profile_step.py --images {n_img} --steps 1 --ops rtw  (one launch = {n_img} 12 MP images; kernel filter: the lean instantiation k_stream<1,true,true>)\n")
     f.write("summary by tools/ncu_hot.py (headline metrics, stall totals, SASS lines with >= 1% of the samples)\n\n")
     f.write(txt)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -52,5 +52,12 @@ json.dump({"kernel": v[h.index("Kernel Name")], "images_per_launch": n_img,
            "dram_bytes_per_launch": rd + wr, "dram_bytes_per_image": (rd + wr) / n_img,
            "note": f"ncu --set full, profiles/{rnd}_k_stream_full.txt; dram__bytes_read.sum + dram__bytes_write.sum"},
           open(os.path.join(out, "traffic.json"), "w"), indent=1)
+# optional: further captures "name=tag" -> profiles/<rnd>_<name>_full.txt
+for extra in sys.argv[5:]:
+    name, tag = extra.split("=")
+    t = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hot.py"), os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep"), "1.0"],
+                       capture_output=True, text=True).stdout
+    with open(os.path.join(out, f"{rnd}_{name}_full.txt"), "w") as f:
+        f.write("ncu --set full --clock-control none --import-source on (same command as the k_stream capture)\n\n" + t)
 print(open(os.path.join(out, f"{rnd}_launch_summary.txt")).read())
 print(open(os.path.join(out, "traffic.json")).read())
