@@ -168,25 +168,37 @@ def run_reference(args, rank, world):
 
 
 def bind_near_gpu(index):
-    """Best effort: run this rank (and first-touch its pinned buffers) on the cores of the GPU's NUMA node,
-    so 8 ranks do not all stream their host buffers through one socket's memory controllers."""
+    """Best effort, N > 1 only: keep this rank's pinned host buffers on the NUMA node of its GPU (memory policy
+    first -- it works even when the allowed cores are all on the other socket -- then the node's cores), so 8
+    ranks do not push their H2D/D2H traffic across the socket interconnect."""
+    info = {}
     try:
         bus = subprocess.check_output(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
                                       text=True, timeout=20).strip().lower()
         dom, rest = bus.split(":", 1)
-        path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/local_cpulist"
+        dev = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}"
+        node = int(open(dev + "/numa_node").read().strip())
+        info["gpu_numa_node"] = node
+        if node >= 0:
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            MPOL_PREFERRED = 1
+            rc = libc.syscall(238, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))  # set_mempolicy
+            info["mempolicy"] = "preferred" if rc == 0 else f"errno {ctypes.get_errno()}"
         cpus = set()
-        for part in open(path).read().strip().split(","):
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
         allowed = os.sched_getaffinity(0)
         use = cpus & allowed
+        info["allowed_cpus"], info["local_allowed_cpus"] = len(allowed), len(use)
         if use and use != allowed:
             os.sched_setaffinity(0, use)
-            return f"{len(use)} cores local to GPU {index}"
-        return "no narrower local core set available"
+            info["affinity"] = "narrowed"
     except Exception as e:  # noqa: BLE001
-        return f"unavailable ({type(e).__name__})"
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
 
 
 def workload_config(n_gpus, images_per_gpu):
@@ -359,7 +371,7 @@ def main():
     thumb_GBps = BYTES_THUMB_PASS * n_iso / (max(both_ms - lean_ms, 1e-9) * 1e-3) / 1e9
     pipeline_GBps = BYTES_PER_IMAGE / (stream_ms_per_image * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "k_stream<1,true,lean>: resize + watermark copy, one pass over the source",
+        "bound": "hbm", "kernel": "k_stream<1,true,1> (lean, local target): resize + watermark copy, one pass over the source",
         "achieved": lean_GBps, "peak": peak, "unit": "GB/s", "frac": lean_GBps / peak, "peak_source": peak_src,
         "frac_of_nominal_8TBs": lean_GBps / 8000.0,
         "algorithmic_bytes_per_image": BYTES_LEAN_PASS, "images_per_launch": n_iso / lean_launches,
@@ -370,7 +382,7 @@ def main():
         "traffic_note": (traffic.get("note") + f"; {traffic['dram_bytes_per_image'] / 1e6:.1f} MB per image x images_per_launch")
                         if traffic else "no ncu --set full capture committed yet",
         "kernel_share_of_step": lean_ms / max(both_ms + iso["fix_kernel_ms"] + iso["other_kernel_ms"], 1e-9),
-        "thumbnail_kernel": {"kernel": "k_stream<1,false,general>: crop + 15:1 thumbnail", "achieved": thumb_GBps,
+        "thumbnail_kernel": {"kernel": "k_stream<1,false,2> (lean, wide target): crop + 15:1 thumbnail", "achieved": thumb_GBps,
                              "frac": thumb_GBps / peak, "algorithmic_bytes_per_image": BYTES_THUMB_PASS,
                              "ms_per_image": (both_ms - lean_ms) / n_iso},
         "pipeline": {"what": "all k_stream work of the timed run against the source-read-once figure of SURVEY.md 8(d)",

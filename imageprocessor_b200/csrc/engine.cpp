@@ -397,8 +397,9 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     std::vector<StreamJob> sjobs;
     std::vector<StreamItem> sitems;   // general k_stream instantiations, independent of the lean launch
     std::vector<StreamItem> ritems;   // general k_stream instantiation: on-demand redo of lean jobs
-    std::vector<StreamItem> fitems;   // lean instantiation
-    bool any_wm_fast = false;
+    std::vector<StreamItem> fitems;   // lean instantiation, local target
+    std::vector<StreamItem> f2items;  // lean instantiation, wide target
+    bool any_wm_fast = false, any_wm_fast2 = false;
     size_t max_jobs = 0;
     for (auto &tp : B.tickets) max_jobs += tp->ops.size() + 1;
     int32_t *redo_flags = (int32_t *)arena.take(4 * max_jobs + 256); // one per stream job, raised on the device
@@ -623,21 +624,21 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 const int ji = (int)sjobs.size();
                 // the lean instantiation takes the common case; it needs TMA-storable watermark rows
                 const bool wm_tma_ok = !wm || ((sv.w % 4) == 0 && ((((uintptr_t)wm->dev_out) | (uintptr_t)wm->dev_pitch) & 15) == 0);
-                j.fast_path = geom->lean_ok && wm_tma_ok && redo_flags && (size_t)ji < max_jobs;
+                j.fast_path = (geom->lean_ok && wm_tma_ok && redo_flags && (size_t)ji < max_jobs) ? (geom->t[0].local ? 1 : 2) : 0;
                 j.redo_flag = (j.fast_path && !t.src.opaque_hint) ? redo_flags + ji : nullptr;
                 sjobs.push_back(j);
                 if (!j.fast_path) {
                     max_nt = std::max(max_nt, nt);
                     any_wm |= wm != nullptr;
                 } else {
-                    any_wm_fast |= wm != nullptr;
+                    (j.fast_path == 1 ? any_wm_fast : any_wm_fast2) |= wm != nullptr;
                     B.fast_jobs++;
                 }
                 for (auto it : geom->items) {
                     it.job = ji;
                     if (!j.fast_path) sitems.push_back(it);
                     else {
-                        fitems.push_back(it);
+                        (j.fast_path == 1 ? fitems : f2items).push_back(it);
                         if (j.redo_flag) ritems.push_back(it);
                     }
                 }
@@ -676,6 +677,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     const StreamJob *d_sjobs = blob.dptr<const StreamJob>(blob.put(sjobs.data(), sjobs.size() * sizeof(StreamJob), 16));
     const StreamItem *d_sitems = blob.dptr<const StreamItem>(blob.put(sitems.data(), sitems.size() * sizeof(StreamItem), 16));
     const StreamItem *d_fitems = blob.dptr<const StreamItem>(blob.put(fitems.data(), fitems.size() * sizeof(StreamItem), 16));
+    const StreamItem *d_f2items = blob.dptr<const StreamItem>(blob.put(f2items.data(), f2items.size() * sizeof(StreamItem), 16));
     const StreamItem *d_ritems = blob.dptr<const StreamItem>(blob.put(ritems.data(), ritems.size() * sizeof(StreamItem), 16));
     const ExactJob *d_fixjobs = blob.dptr<const ExactJob>(blob.put(fixjobs.data(), fixjobs.size() * sizeof(ExactJob), 16));
     const ExactJob *d_xjobs = blob.dptr<const ExactJob>(blob.put(xjobs.data(), xjobs.size() * sizeof(ExactJob), 16));
@@ -694,32 +696,44 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     // already fills the GPU; overlapping them only makes them evict each other), while the
     // copies of the other lanes overlap with them.
     if (d.last_compute) IPG_CU(cudaStreamWaitEvent(st, d.last_compute, 0));
-    if (!fitems.empty() && redo_flags) IPG_CU(cudaMemsetAsync(redo_flags, 0, 4 * max_jobs, st));
+    if ((!fitems.empty() || !f2items.empty()) && redo_flags) IPG_CU(cudaMemsetAsync(redo_flags, 0, 4 * max_jobs, st));
     IPG_CU(cudaEventRecord(L.ev[0], st));
-    // The general launch over jobs the lean kernel does not take runs beside the lean launch on a side
-    // stream (each fills the other's ramp and tail); the on-demand redo of lean jobs follows the lean launch.
-    const bool side = !fitems.empty() && !sitems.empty() && c.overlap_streams;
+    // Two streams: the lean local-target launch (resize + watermark copy) on the lane's stream; beside it, on a
+    // side stream, the lean wide-target launch (thumbnail) and the general launch over whatever neither lean kernel
+    // takes -- each fills the other's ramp and tail.  The on-demand redo of lean jobs follows both.
+    const bool side_work = !f2items.empty() || !sitems.empty();
+    const bool side = side_work && !fitems.empty() && c.overlap_streams;
+    cudaStream_t s2 = side ? L.st2 : st;
     if (side) {
         IPG_CU(cudaEventRecord(L.fork, st));
         IPG_CU(cudaStreamWaitEvent(L.st2, L.fork, 0));
-        IPG_CU(launch_stream(d_sjobs, d_sitems, (int)sitems.size(), max_nt, any_wm, fix, L.st2));
+    }
+    if (!side && !fitems.empty()) { // no overlap: lean local first, timed alone
+        IPG_CU(launch_stream_fast(d_sjobs, d_fitems, (int)fitems.size(), 1, any_wm_fast, fix, st));
+        B.n_kernels++;
+        IPG_CU(cudaEventRecord(L.evf, st));
+    }
+    if (!f2items.empty()) {
+        IPG_CU(launch_stream_fast(d_sjobs, d_f2items, (int)f2items.size(), 2, any_wm_fast2, fix, s2));
+        B.n_kernels++;
+    }
+    if (!sitems.empty()) {
+        IPG_CU(launch_stream(d_sjobs, d_sitems, (int)sitems.size(), max_nt, any_wm, fix, s2));
+        B.n_kernels++;
+    }
+    if (side) {
         IPG_CU(cudaEventRecord(L.join, L.st2));
+        IPG_CU(launch_stream_fast(d_sjobs, d_fitems, (int)fitems.size(), 1, any_wm_fast, fix, st));
         B.n_kernels++;
-    }
-    if (!fitems.empty()) {
-        IPG_CU(launch_stream_fast(d_sjobs, d_fitems, (int)fitems.size(), any_wm_fast, fix, st));
-        B.n_kernels++;
-    }
-    IPG_CU(cudaEventRecord(L.evf, st));
-    if (!side && !sitems.empty()) {
-        IPG_CU(launch_stream(d_sjobs, d_sitems, (int)sitems.size(), max_nt, any_wm, fix, st));
-        B.n_kernels++;
+        IPG_CU(cudaEventRecord(L.evf, st));
+        IPG_CU(cudaStreamWaitEvent(st, L.join, 0));
+    } else if (fitems.empty()) {
+        IPG_CU(cudaEventRecord(L.evf, st));
     }
     if (!ritems.empty()) {
-        IPG_CU(launch_stream(d_sjobs, d_ritems, (int)ritems.size(), 1, any_wm_fast, fix, st));
+        IPG_CU(launch_stream(d_sjobs, d_ritems, (int)ritems.size(), 1, any_wm_fast || any_wm_fast2, fix, st));
         B.n_kernels++;
     }
-    if (side) IPG_CU(cudaStreamWaitEvent(st, L.join, 0));
     IPG_CU(cudaEventRecord(L.ev[1], st));
     if (!fixjobs.empty()) {
         IPG_CU(launch_exact_fix(d_fixjobs, (int)fixjobs.size(), fix, st));

@@ -157,7 +157,7 @@ struct StreamJob {
     int32_t slab_cols;         // 3 * warp_stride + 128: columns a CTA loads per row
     int32_t n_tiles, n_bands;
     int32_t check_premul;      // RGBA8 source, alpha unknown, a two_stage target exists
-    int32_t fast_path;         // the lean instantiation runs this job; the general one only redoes it on demand
+    int32_t fast_path;         // 1 / 2: a lean instantiation (local / wide target) runs this job; the general one only redoes it on demand
     int32_t *redo_flag;        // fast_path: raised by the lean kernel on a non-opaque pixel (nullptr: caller vouches for opacity)
     const int32_t *band_y;     // [n_bands+1] owned source rows of each band
     const int32_t *band_yend;  // [n_bands]   one past the last row the band must read

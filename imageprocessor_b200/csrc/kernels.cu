@@ -468,7 +468,8 @@ template <int NT, int STAGES> struct __align__(128) StreamSmem {
     uint64_t empty[STAGES];                      // the 4 V warps are done with a stage
     XInfo xi[2];                                 // per target; parts = tile_parts of this CTA's tile
 };
-template <int NT, bool FAST = false> struct StreamCfg {
+template <int NT, int LEAN = 0> struct StreamCfg {
+    static constexpr bool FAST = LEAN != 0;
     static constexpr int STAGES = FAST ? STREAM_STAGES_FAST : NT == 2 ? STREAM_STAGES_2T : STREAM_STAGES_1T;
     static constexpr int CTAS_PER_SM = FAST ? STREAM_CTAS_FAST : NT == 2 ? STREAM_CTAS_2T : STREAM_CTAS_1T;
     using Smem = StreamSmem<NT, STAGES>;
@@ -644,8 +645,9 @@ struct VCtx {
 // The common case, stripped of every test it does not need: one target, active in this tile,
 // in the lane-per-output form, all four rows inside the band, opaque so far, watermark (if any)
 // copied by the producer.  Everything else takes v_rows below.
-template <typename SM>
-__device__ __forceinline__ void v_rows_fast(VAcc<false> &S, const StreamStage &stg, SM &sm, const VCtx &C, const FixList &fix)
+template <int LEAN, typename SM>
+__device__ __forceinline__ void v_rows_fast(VAcc<false> &S, const StreamJob &J, const StreamStage &stg, SM &sm, const VCtx &C,
+                                            const FixList &fix)
 {
     uint4 cur = stg.rows[0][C.slot];
 #pragma unroll
@@ -664,18 +666,22 @@ __device__ __forceinline__ void v_rows_fast(VAcc<false> &S, const StreamStage &s
         if (e >= 0) { // CTA-uniform: this source row completes output row e>>1, held in set e&1
             if (e & 1) park_row<1, false>(S, r.w, sm.xbuf[0], C.pslot[0]);
             else       park_row<0, false>(S, r.z, sm.xbuf[0], C.pslot[0]);
-            __syncwarp();
-            const float4 *buf = sm.xbuf[0];
-            float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
+            if constexpr (LEAN == 1) { // local target: this warp filters its own strip, one output per lane
+                __syncwarp();
+                const float4 *buf = sm.xbuf[0];
+                float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int q = 0; q < STREAM_XTAPS; q++) { // weight 0 past the end adds exactly nothing
-                const float4 v = buf[swz(C.x0_e0 + q)];
-                const float2 ww = make_float2(C.x0_w[q], C.x0_w[q]);
-                rg = __ffma2_rn(make_float2(v.x, v.y), ww, rg);
-                ba = __ffma2_rn(make_float2(v.z, v.w), ww, ba);
+                for (int q = 0; q < STREAM_XTAPS; q++) { // weight 0 past the end adds exactly nothing
+                    const float4 v = buf[swz(C.x0_e0 + q)];
+                    const float2 ww = make_float2(C.x0_w[q], C.x0_w[q]);
+                    rg = __ffma2_rn(make_float2(v.x, v.y), ww, rg);
+                    ba = __ffma2_rn(make_float2(v.z, v.w), ww, ba);
+                }
+                if (C.x0_ox >= 0) xfinish(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
+                __syncwarp(); // the strip is reused by the next emit
+            } else {           // wide support (the thumbnail): CTA-wide split pass, once per ~15 rows
+                xpass<1>(J, sm, 0, e >> 1, C.tile, C.cx0, C.vtid, fix);
             }
-            if (C.x0_ox >= 0) xfinish(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
-            __syncwarp(); // the strip is reused by the next emit
         }
         cur = nxt;
     }
@@ -772,26 +778,28 @@ __device__ __forceinline__ void v_rows(VAcc<ALPHA> *S, const StreamJob &J, const
     }
 }
 
-// FAST (NT == 1 only): the lean instantiation for the common case -- one local target in the
-// lane-per-output form, watermark copied by the producer, every pixel opaque.  It carries none of the
+// FAST (NT == 1 only): the lean instantiation for the common case -- one target whose horizontal
+// pass is in a cached form (local: one output per lane; wide: split over adjacent threads), watermark
+// copied by the producer, every pixel opaque.  It carries none of the
 // general paths, so it fits 4 CTAs per SM in ~96 registers and runs the fused resize + watermark
 // copy near the HBM roofline.  Opacity is checked, not assumed: a warp that meets a non-opaque
 // pixel raises the job's redo flag and the general instantiation, launched right after over the same
 // items, redoes exactly the flagged jobs (it exits at once for the others).
-template <int NT, bool WM, bool FAST>
-__global__ void __launch_bounds__(STREAM_CTA, (StreamCfg<NT, FAST>::CTAS_PER_SM))
+template <int NT, bool WM, int LEAN>
+__global__ void __launch_bounds__(STREAM_CTA, (StreamCfg<NT, LEAN>::CTAS_PER_SM))
 k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ items, FixList fix)
 {
-    static_assert(!FAST || NT == 1, "the lean instantiation has exactly one target");
-    constexpr int STAGES = StreamCfg<NT, FAST>::STAGES;
-    using Smem = typename StreamCfg<NT, FAST>::Smem;
+    constexpr bool FAST = LEAN != 0; // LEAN 1: local target (lane-per-output pass inline); 2: wide target (split pass)
+    static_assert(!FAST || NT == 1, "the lean instantiations have exactly one target");
+    constexpr int STAGES = StreamCfg<NT, LEAN>::STAGES;
+    using Smem = typename StreamCfg<NT, LEAN>::Smem;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
     const StreamItem it = items[blockIdx.x];
     const StreamJob &J = jobs[it.job];
     // a job the lean kernel already ran is redone here only if it met a non-opaque pixel
-    if (!FAST && J.fast_path && (J.redo_flag == nullptr || *(volatile const int32_t *)J.redo_flag == 0)) return;
+    if (!FAST && J.fast_path != 0 && (J.redo_flag == nullptr || *(volatile const int32_t *)J.redo_flag == 0)) return;
     const int tile = it.tile, band = it.band;
     const int W = J.src.w;
     const int cx0 = tile * J.tile_w;
@@ -835,6 +843,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
                 if (tid == 0) sm.xi[T] = XInfo{t.dst, t.dst_stride, t.exact_job, (uint32_t)t.fix_d, t.local, P, 0};
                 for (int e = tid; e < STREAM_XBUF; e += STREAM_THREADS) sm.xbuf[T][e] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (FAST && P == 0) { // a tile without outputs: lanes gather zeros and store nothing
+                    if (tid == 0) sm.xi[T].parts = 1;
                     sm.xt.ox[T][tid] = -1;
                     sm.xt.e0[T][tid] = 0;
 #pragma unroll
@@ -928,7 +937,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
 #pragma unroll
     for (int k = 0; k < STREAM_XTAPS; k++) C.x0_w[k] = 0.f;
     if constexpr (NT > 0) {
-        if (FAST || (C.act[0] && sm.xi[0].local && sm.xi[0].parts == 1)) {
+        if (LEAN == 1 || (!FAST && C.act[0] && sm.xi[0].local && sm.xi[0].parts == 1)) {
             C.x0_inline = true;
             C.x0_ox = sm.xt.ox[0][tid];
             C.x0_e0 = sm.xt.e0[0][tid];
@@ -979,7 +988,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
                 }
             }
         }
-        if constexpr (FAST) v_rows_fast(S[0], stg, sm, C, fix);
+        if constexpr (FAST) v_rows_fast<LEAN>(S[0], J, stg, sm, C, fix);
         else                v_rows<NT, WM, false>(S, J, stg, sm, C, ys0 + g * STREAM_GROUP, nr, fix);
         advance();
     }
@@ -1009,18 +1018,18 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
 
 int stream_smem_bytes() { return (int)sizeof(StreamCfg<2>::Smem); }
 
-template <int NT, bool WM, bool FAST>
+template <int NT, bool WM, int LEAN>
 static cudaError_t launch_stream_t(const StreamJob *jobs, const StreamItem *items, int n, FixList fix, cudaStream_t st)
 {
-    using Smem = typename StreamCfg<NT, FAST>::Smem;
+    using Smem = typename StreamCfg<NT, LEAN>::Smem;
     static bool configured = false; // per instantiation; benign race (idempotent attribute)
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_stream<NT, WM, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_stream<NT, WM, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_stream<NT, WM, FAST><<<n, STREAM_CTA, sizeof(Smem), st>>>(jobs, items, fix);
+    k_stream<NT, WM, LEAN><<<n, STREAM_CTA, sizeof(Smem), st>>>(jobs, items, fix);
     return cudaGetLastError();
 }
 
@@ -1031,21 +1040,24 @@ cudaError_t launch_stream(const StreamJob *jobs, const StreamItem *items, int n_
 {
     if (n_items <= 0) return cudaSuccess;
     switch (max_targets) {
-    case 0: return any_wm ? launch_stream_t<0, true, false>(jobs, items, n_items, fix, st) : cudaSuccess;
-    case 1: return any_wm ? launch_stream_t<1, true, false>(jobs, items, n_items, fix, st)
-                          : launch_stream_t<1, false, false>(jobs, items, n_items, fix, st);
-    default: return any_wm ? launch_stream_t<2, true, false>(jobs, items, n_items, fix, st)
-                           : launch_stream_t<2, false, false>(jobs, items, n_items, fix, st);
+    case 0: return any_wm ? launch_stream_t<0, true, 0>(jobs, items, n_items, fix, st) : cudaSuccess;
+    case 1: return any_wm ? launch_stream_t<1, true, 0>(jobs, items, n_items, fix, st)
+                          : launch_stream_t<1, false, 0>(jobs, items, n_items, fix, st);
+    default: return any_wm ? launch_stream_t<2, true, 0>(jobs, items, n_items, fix, st)
+                           : launch_stream_t<2, false, 0>(jobs, items, n_items, fix, st);
     }
 }
 
-// The lean instantiation over items of jobs with StreamJob::fast_path set.
-cudaError_t launch_stream_fast(const StreamJob *jobs, const StreamItem *items, int n_items, bool any_wm, FixList fix,
-                               cudaStream_t st)
+// A lean instantiation over items of jobs with StreamJob::fast_path == kind (1: local target, 2: wide target).
+cudaError_t launch_stream_fast(const StreamJob *jobs, const StreamItem *items, int n_items, int kind, bool any_wm,
+                               FixList fix, cudaStream_t st)
 {
     if (n_items <= 0) return cudaSuccess;
-    return any_wm ? launch_stream_t<1, true, true>(jobs, items, n_items, fix, st)
-                  : launch_stream_t<1, false, true>(jobs, items, n_items, fix, st);
+    if (kind == 1)
+        return any_wm ? launch_stream_t<1, true, 1>(jobs, items, n_items, fix, st)
+                      : launch_stream_t<1, false, 1>(jobs, items, n_items, fix, st);
+    return any_wm ? launch_stream_t<1, true, 2>(jobs, items, n_items, fix, st)
+                  : launch_stream_t<1, false, 2>(jobs, items, n_items, fix, st);
 }
 
 cudaError_t launch_exact_tiles(const ExactJob *jobs, const ExactItem *items, int n_items, cudaStream_t st)

@@ -10,8 +10,8 @@ namespace ipg {
 cudaError_t launch_stream(const StreamJob *jobs, const StreamItem *items, int n_items,
                           int max_targets, bool any_wm, FixList fix, cudaStream_t st);
 
-// The lean single-target instantiation (k_stream<1, WM, true>) over jobs with fast_path set.
-cudaError_t launch_stream_fast(const StreamJob *jobs, const StreamItem *items, int n_items, bool any_wm,
+// A lean single-target instantiation (k_stream<1, WM, kind>) over jobs with fast_path == kind.
+cudaError_t launch_stream_fast(const StreamJob *jobs, const StreamItem *items, int n_items, int kind, bool any_wm,
                                FixList fix, cudaStream_t st);
 
 // fp64 reference-order resample of whole outputs: one CTA per 32x8 output tile.

@@ -295,9 +295,9 @@ static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const Stream
             }
         }
     }
-    g->lean_ok = n_targets == 1 && g->t[0].local;
+    g->lean_ok = n_targets == 1;
     for (int tile = 0; tile < g->n_tiles && g->lean_ok; tile++)
-        if (g->t[0].tile_ox[tile + 1] > g->t[0].tile_ox[tile] && g->t[0].tile_parts[tile] != 1) g->lean_ok = false;
+        if (g->t[0].tile_ox[tile + 1] > g->t[0].tile_ox[tile] && g->t[0].tile_parts[tile] < 1) g->lean_ok = false;
     for (int b = 0; b < n_bands; b++) {
         for (int tile = 0; tile < g->n_tiles; tile++) {
             bool work = has_wm;
