@@ -84,9 +84,9 @@ struct StreamTarget {
     const int32_t *tile_ox;      // [n_tiles+1] output columns owned by each column tile
     int32_t local;               // 1: narrow support, each V warp runs its own horizontal pass
     const int32_t *warp_ox;      // local: [n_tiles*4+1] output columns owned by each (tile, warp)
-    const int32_t *tile_parts;   // [n_tiles] horizontal-pass form of the tile: 0 = generic loops; P >= 1 =
+    const int32_t *tile_parts;   // [n_tiles] horizontal-pass form of the tile, P | taps_per_thread << 8: P == 0 = generic loops; P >= 1 =
                                  // "cached": every output is split over P adjacent V threads, each holding
-                                 // at most STREAM_XTAPS interleaved taps (local targets: P == 1)
+                                 // at most STREAM_XTAPS (local) / STREAM_XTAPS_TAB (wide) interleaved taps
     const RowRec *rows;          // per-band records, concatenated
     const int32_t *band_rec_off; // [n_bands] first record of each band
     const int32_t *band_tend;    // [n_bands] one past the last source row that contributes
@@ -141,7 +141,8 @@ enum {
     STREAM_GROUP = 4,           // source rows per ring stage / TMA barrier phase (<= 8 KB)
     STREAM_PTHREADS = 32,       // producer warp
     STREAM_CTA = STREAM_THREADS + STREAM_PTHREADS,
-    STREAM_XTAPS = 8,           // local targets: taps per output kept in registers
+    STREAM_XTAPS = 8,           // local targets: taps per thread kept in registers
+    STREAM_XTAPS_TAB = 12,      // wide targets: taps per thread in the shared-memory table
     STREAM_LOCAL_MAX_HALO = 16, // a target is local when its widest support - 1 fits this overlap
     STREAM_STAGES_2T = IPG_STAGES_2T, STREAM_CTAS_2T = IPG_CTAS_2T,   // ring depth / CTAs per SM, two-target instantiation
     STREAM_STAGES_1T = IPG_STAGES_1T, STREAM_CTAS_1T = IPG_CTAS_1T,   // ... otherwise

@@ -440,7 +440,7 @@ struct __align__(16) StreamStage {
 template <int NT> struct XTab {
     int32_t ox[NT][STREAM_THREADS];              // output column, or -1 when the thread has none
     int32_t e0[NT][STREAM_THREADS];              // element of xbuf[T] holding its first tap
-    float w[NT][STREAM_XTAPS][STREAM_THREADS];   // its weights, 0 past the end
+    float w[NT][STREAM_XTAPS_TAB][STREAM_THREADS]; // its weights, 0 past the end
 };
 template <> struct XTab<0> {};
 
@@ -455,7 +455,7 @@ struct XInfo {
     uint8_t *dst;
     int32_t dst_stride, exact_job;
     uint32_t D;
-    int32_t local, parts, pad;
+    int32_t local, parts, ntap;  // parts = threads per output (0: generic form), ntap = taps per thread
 };
 
 template <int NT, int STAGES> struct __align__(128) StreamSmem {
@@ -527,8 +527,9 @@ __device__ __noinline__ void xpass(const StreamJob &J, SM &sm, int T, int oy, in
         const int e0 = sm.xt.e0[T][vtid];
         float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
         if (ox >= 0) {
-#pragma unroll
-            for (int k = 0; k < STREAM_XTAPS; k++) { // weight 0 past the end adds exactly nothing (the buffer is padded and finite)
+            const int ntap = xi.ntap;
+#pragma unroll 4
+            for (int k = 0; k < ntap; k++) { // weight 0 past the end adds exactly nothing (the buffer is padded and finite)
                 const float w = sm.xt.w[T][k][vtid];
                 const float4 q = buf[swz(e0 + k * P)];
                 const float2 ww = make_float2(w, w);
@@ -632,6 +633,7 @@ struct VCtx {
     // target 0 in its common form (local, one output per lane, <= STREAM_XTAPS taps): the horizontal
     // pass runs inline with the taps in registers; every other case goes through xpass()
     bool x0_inline;
+    int x0_parts;            // lanes sharing one output (1, 2 or 4)
     int x0_ox;               // output column of this lane, or -1
     const float4 *x0_tap;    // address of its first tap in xbuf[0] when no swizzle step is crossed ... see x0_off
     int x0_e0;
@@ -672,12 +674,18 @@ __device__ __forceinline__ void v_rows_fast(VAcc<false> &S, const StreamJob &J, 
                 float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int q = 0; q < STREAM_XTAPS; q++) { // weight 0 past the end adds exactly nothing
-                    const float4 v = buf[swz(C.x0_e0 + q)];
+                    const float4 v = buf[swz(C.x0_e0 + q * C.x0_parts)];
                     const float2 ww = make_float2(C.x0_w[q], C.x0_w[q]);
                     rg = __ffma2_rn(make_float2(v.x, v.y), ww, rg);
                     ba = __ffma2_rn(make_float2(v.z, v.w), ww, ba);
                 }
-                if (C.x0_ox >= 0) xfinish(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
+                for (int off = 1; off < C.x0_parts; off <<= 1) { // lanes sharing an output (supports of 9..32 taps)
+                    rg.x += __shfl_xor_sync(0xffffffffu, rg.x, off);
+                    rg.y += __shfl_xor_sync(0xffffffffu, rg.y, off);
+                    ba.x += __shfl_xor_sync(0xffffffffu, ba.x, off);
+                    ba.y += __shfl_xor_sync(0xffffffffu, ba.y, off);
+                }
+                if (C.x0_ox >= 0 && (threadIdx.x & (C.x0_parts - 1)) == 0) xfinish(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
                 __syncwarp(); // the strip is reused by the next emit
             } else {           // wide support (the thumbnail): CTA-wide split pass, once per ~15 rows
                 xpass<1>(J, sm, 0, e >> 1, C.tile, C.cx0, C.vtid, fix);
@@ -751,17 +759,28 @@ __device__ __forceinline__ void v_rows(VAcc<ALPHA> *S, const StreamJob &J, const
                     else       park_row<0, ALPHA>(S[T], r.z, sm.xbuf[T], C.pslot[T]);
                     if (T == 0 && C.x0_inline) {
                         __syncwarp();
+                        float2 x0_rg = make_float2(0.f, 0.f), x0_ba = make_float2(0.f, 0.f);
                         if (C.x0_ox >= 0) {
                             const float4 *buf = sm.xbuf[0];
-                            float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
+                            float2 &rg = x0_rg, &ba = x0_ba;
 #pragma unroll
                             for (int q = 0; q < STREAM_XTAPS; q++) { // weight 0 past the end adds exactly nothing
-                                const float4 v = buf[swz(C.x0_e0 + q)];
+                                const float4 v = buf[swz(C.x0_e0 + q * C.x0_parts)];
                                 const float2 ww = make_float2(C.x0_w[q], C.x0_w[q]);
                                 rg = __ffma2_rn(make_float2(v.x, v.y), ww, rg);
                                 ba = __ffma2_rn(make_float2(v.z, v.w), ww, ba);
                             }
-                            xfinish(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
+                        }
+                        {
+                            float2 &rg = x0_rg, &ba = x0_ba;
+                            for (int off = 1; off < C.x0_parts; off <<= 1) {
+                                rg.x += __shfl_xor_sync(0xffffffffu, rg.x, off);
+                                rg.y += __shfl_xor_sync(0xffffffffu, rg.y, off);
+                                ba.x += __shfl_xor_sync(0xffffffffu, ba.x, off);
+                                ba.y += __shfl_xor_sync(0xffffffffu, ba.y, off);
+                            }
+                            if (C.x0_ox >= 0 && (threadIdx.x & (C.x0_parts - 1)) == 0)
+                                xfinish(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
                         }
                         __syncwarp(); // the strip is reused by the next emit
                     } else {
@@ -839,22 +858,23 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
             for (int T = 0; T < NT; T++) {
                 if (T >= J.n_targets) continue;
                 const StreamTarget &t = J.t[T];
-                const int P = __ldg(t.tile_parts + tile);
-                if (tid == 0) sm.xi[T] = XInfo{t.dst, t.dst_stride, t.exact_job, (uint32_t)t.fix_d, t.local, P, 0};
+                const int pv = __ldg(t.tile_parts + tile), P = pv & 255;
+                if (tid == 0) sm.xi[T] = XInfo{t.dst, t.dst_stride, t.exact_job, (uint32_t)t.fix_d, t.local, P, pv >> 8};
                 for (int e = tid; e < STREAM_XBUF; e += STREAM_THREADS) sm.xbuf[T][e] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (FAST && P == 0) { // a tile without outputs: lanes gather zeros and store nothing
                     if (tid == 0) sm.xi[T].parts = 1;
                     sm.xt.ox[T][tid] = -1;
                     sm.xt.e0[T][tid] = 0;
 #pragma unroll
-                    for (int k = 0; k < STREAM_XTAPS; k++) sm.xt.w[T][k][tid] = 0.f;
+                    for (int k = 0; k < STREAM_XTAPS_TAB; k++) sm.xt.w[T][k][tid] = 0.f;
                 }
                 if (P == 0) continue;
                 int ox = -1, e0 = 0, k0 = 0, n = 0, part = 0;
-                if (t.local) { // one output per lane of the owning warp; strip w sits at elements [128 w, 128 w + 128)
+                if (t.local) { // P adjacent lanes per output of the owning warp; strip w sits at elements [128 w, 128 w + 128)
                     const int ox0 = __ldg(t.warp_ox + tile * 4 + warp);
-                    if ((tid & 31) < __ldg(t.warp_ox + tile * 4 + warp + 1) - ox0) ox = ox0 + (tid & 31);
-                    if (ox >= 0) e0 = __ldg(t.xfirst + ox) + t.rect_x - cx0 + warp * (STREAM_WARP_COLS - ws);
+                    part = tid & (P - 1);
+                    if ((tid & 31) / P < __ldg(t.warp_ox + tile * 4 + warp + 1) - ox0) ox = ox0 + (tid & 31) / P;
+                    if (ox >= 0) e0 = __ldg(t.xfirst + ox) + t.rect_x - cx0 + warp * (STREAM_WARP_COLS - ws) + part;
                 } else {       // P adjacent threads per output of the tile
                     const int ox0 = __ldg(t.tile_ox + tile);
                     part = tid & (P - 1);
@@ -868,7 +888,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
                 sm.xt.ox[T][tid] = ox;
                 sm.xt.e0[T][tid] = e0;
 #pragma unroll
-                for (int k = 0; k < STREAM_XTAPS; k++)
+                for (int k = 0; k < STREAM_XTAPS_TAB; k++)
                     sm.xt.w[T][k][tid] = (ox >= 0 && part + k * P < n) ? __ldg(t.xw + k0 + part + k * P) : 0.f;
             }
         }
@@ -931,14 +951,16 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
         C.pslot[T] = (T < NT && T < J.n_targets && J.t[T].local) ? tid : slot;
     }
     C.x0_inline = false;
+    C.x0_parts = 1;
     C.x0_ox = -1;
     C.x0_e0 = 0;
     C.x0_tap = nullptr;
 #pragma unroll
     for (int k = 0; k < STREAM_XTAPS; k++) C.x0_w[k] = 0.f;
     if constexpr (NT > 0) {
-        if (LEAN == 1 || (!FAST && C.act[0] && sm.xi[0].local && sm.xi[0].parts == 1)) {
+        if (LEAN == 1 || (!FAST && C.act[0] && sm.xi[0].local && sm.xi[0].parts >= 1)) {
             C.x0_inline = true;
+            C.x0_parts = sm.xi[0].parts;
             C.x0_ox = sm.xt.ox[0][tid];
             C.x0_e0 = sm.xt.e0[0][tid];
 #pragma unroll

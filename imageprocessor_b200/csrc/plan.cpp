@@ -149,15 +149,18 @@ static bool build_target(StreamGeom &g, int ti, const StreamTargetSpec &s, doubl
         int32_t maxn = 0;
         for (int32_t ox = o0; ox < o1; ox++) maxn = std::max(maxn, ax.off[ox + 1] - ax.off[ox]);
         if (o1 == o0) continue;
-        if (t.local) {
-            bool ok = maxn <= STREAM_XTAPS;
-            for (int32_t w = 0; w < 4 && ok; w++)
-                ok = t.warp_ox[(size_t)tile * 4 + w + 1] - t.warp_ox[(size_t)tile * 4 + w] <= 32;
-            t.tile_parts[tile] = ok ? 1 : 0;
-        } else {
+        if (t.local) { // P adjacent lanes of the owning warp per output
+            int32_t maxw = 0;
+            for (int32_t w = 0; w < 4; w++)
+                maxw = std::max(maxw, t.warp_ox[(size_t)tile * 4 + w + 1] - t.warp_ox[(size_t)tile * 4 + w]);
+            for (int32_t P = 1; P <= 4; P <<= 1) {
+                if (maxw * P > 32) break;
+                if ((maxn + P - 1) / P <= STREAM_XTAPS) { t.tile_parts[tile] = P | (((maxn + P - 1) / P) << 8); break; }
+            }
+        } else {       // P adjacent threads of the CTA per output
             for (int32_t P = 1; P <= 32; P <<= 1) {
                 if ((o1 - o0) * P > STREAM_THREADS) break;
-                if ((maxn + P - 1) / P <= STREAM_XTAPS) { t.tile_parts[tile] = P; break; }
+                if ((maxn + P - 1) / P <= STREAM_XTAPS_TAB) { t.tile_parts[tile] = P | (((maxn + P - 1) / P) << 8); break; }
             }
         }
     }
@@ -297,7 +300,7 @@ static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const Stream
     }
     g->lean_ok = n_targets == 1;
     for (int tile = 0; tile < g->n_tiles && g->lean_ok; tile++)
-        if (g->t[0].tile_ox[tile + 1] > g->t[0].tile_ox[tile] && g->t[0].tile_parts[tile] < 1) g->lean_ok = false;
+        if (g->t[0].tile_ox[tile + 1] > g->t[0].tile_ox[tile] && (g->t[0].tile_parts[tile] & 255) < 1) g->lean_ok = false;
     for (int b = 0; b < n_bands; b++) {
         for (int tile = 0; tile < g->n_tiles; tile++) {
             bool work = has_wm;

@@ -99,7 +99,7 @@ extern "C" int planemu_run(const uint8_t *src, int stride, int W, int H, int n_t
                             if (e0 < 0 || e0 + n > g->slab_cols) return -2;
                             // horizontal sum in the kernel's order: P threads per output, each over
                             // its interleaved taps in order, then an xor-butterfly of the partial sums
-                            const int P = std::max(tg.tile_parts[tile], 1);
+                            const int P = std::max(tg.tile_parts[tile] & 255, 1);
                             if (tg.local) { // must lie inside the owning warp's 128 loaded columns
                                 int w = 0;
                                 while (w < 3 && ox >= tg.warp_ox[(size_t)tile * 4 + w + 1]) w++;
