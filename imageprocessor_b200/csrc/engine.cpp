@@ -283,6 +283,9 @@ struct Ctx {
     // passes (3 CTAs/SM each) beat one two-target pass (its 48 accumulators per thread leave 2 CTAs/SM)
     // even though the source is read twice -- measured 32.0 vs 39.0 us per 12 MP image.  ipg_config.fuse_targets = 2
     // (or IPG_FUSE_TARGETS=2) restores the single pass.
+    // 1: one target per pass (default: measured fastest on B200 -- 28.4 us per 12 MP image for the full pipeline);
+    // 2: two targets in the general instantiation (39 us); 3: a local and a wide target in the lean fused
+    // instantiation when eligible (38 us: 48 accumulators per thread cost more occupancy than the second read saves)
     int fuse_targets = 1;
     bool overlap_streams = true; // IPG_NO_OVERLAP=1: lean and general k_stream launches back to back (per-kernel timing)
     // stats
@@ -399,7 +402,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     std::vector<StreamItem> ritems;   // general k_stream instantiation: on-demand redo of lean jobs
     std::vector<StreamItem> fitems;   // lean instantiation, local target
     std::vector<StreamItem> f2items;  // lean instantiation, wide target
-    bool any_wm_fast = false, any_wm_fast2 = false;
+    std::vector<StreamItem> f3items;  // lean instantiation, local + wide targets fused
+    bool any_wm_fast = false, any_wm_fast2 = false, any_wm_fast3 = false;
     size_t max_jobs = 0;
     for (auto &tp : B.tickets) max_jobs += tp->ops.size() + 1;
     int32_t *redo_flags = (int32_t *)arena.take(4 * max_jobs + 256); // one per stream job, raised on the device
@@ -557,17 +561,39 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 OpRec *tg[2] = {nullptr, nullptr};
                 int nt = 0;
                 StreamTargetSpec spec[2];
-                while (ri < res.size() && nt < c.fuse_targets) {
-                    OpRec *op = res[ri];
+                auto spec_of = [&](OpRec *op) {
                     StreamTargetSpec s{0, 0, sv.w, sv.h, op->dw, op->dh};
                     if (op->kind == IPG_OP_THUMB_CROP) s = StreamTargetSpec{op->rx, op->ry, op->rw, op->rh, op->dw, op->dh};
-                    spec[nt] = s;
+                    return s;
+                };
+                OpRec *wm = wi < wms.size() ? wms[wi] : nullptr;
+                std::shared_ptr<const StreamGeom> geom;
+                bool lean2 = false;
+                if (c.fuse_targets == 3 && ri + 1 < res.size()) {
+                    // fuse the next two targets when the lean local + wide instantiation can take them
+                    // (either order: the local one goes first), otherwise one target per pass
+                    for (int order = 0; order < 2 && !lean2; order++) {
+                        OpRec *a = res[ri + order], *b = res[ri + 1 - order];
+                        StreamTargetSpec sp2[2] = {spec_of(a), spec_of(b)};
+                        auto g2 = get_stream_geom(sv.w, sv.h, sp2, 2, wm != nullptr, bands_hint, 257.0);
+                        if (g2 && g2->lean2_ok) {
+                            geom = g2;
+                            tg[0] = a; tg[1] = b;
+                            spec[0] = sp2[0]; spec[1] = sp2[1];
+                            nt = 2;
+                            ri += 2;
+                            lean2 = true;
+                        }
+                    }
+                }
+                const int per_pass = c.fuse_targets == 2 ? 2 : 1;
+                while (!lean2 && ri < res.size() && nt < per_pass) {
+                    OpRec *op = res[ri];
+                    spec[nt] = spec_of(op);
                     tg[nt++] = op;
                     ri++;
                 }
-                OpRec *wm = wi < wms.size() ? wms[wi] : nullptr;
-                std::shared_ptr<const StreamGeom> geom;
-                if (nt > 0 || wm) geom = get_stream_geom(sv.w, sv.h, spec, nt, wm != nullptr, bands_hint, 257.0);
+                if (!geom && (nt > 0 || wm)) geom = get_stream_geom(sv.w, sv.h, spec, nt, wm != nullptr, bands_hint, 257.0);
                 if (!geom && nt == 2) { // retry the targets one at a time
                     ri -= 1;
                     nt = 1;
@@ -624,21 +650,25 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 const int ji = (int)sjobs.size();
                 // the lean instantiation takes the common case; it needs TMA-storable watermark rows
                 const bool wm_tma_ok = !wm || ((sv.w % 4) == 0 && ((((uintptr_t)wm->dev_out) | (uintptr_t)wm->dev_pitch) & 15) == 0);
-                j.fast_path = (geom->lean_ok && wm_tma_ok && redo_flags && (size_t)ji < max_jobs) ? (geom->t[0].local ? 1 : 2) : 0;
+                j.fast_path = 0;
+                if (wm_tma_ok && redo_flags && (size_t)ji < max_jobs) {
+                    if (geom->lean_ok) j.fast_path = geom->t[0].local ? 1 : 2;
+                    else if (lean2 && geom->lean2_ok) j.fast_path = 3;
+                }
                 j.redo_flag = (j.fast_path && !t.src.opaque_hint) ? redo_flags + ji : nullptr;
                 sjobs.push_back(j);
                 if (!j.fast_path) {
                     max_nt = std::max(max_nt, nt);
                     any_wm |= wm != nullptr;
                 } else {
-                    (j.fast_path == 1 ? any_wm_fast : any_wm_fast2) |= wm != nullptr;
+                    (j.fast_path == 1 ? any_wm_fast : j.fast_path == 2 ? any_wm_fast2 : any_wm_fast3) |= wm != nullptr;
                     B.fast_jobs++;
                 }
                 for (auto it : geom->items) {
                     it.job = ji;
                     if (!j.fast_path) sitems.push_back(it);
                     else {
-                        (j.fast_path == 1 ? fitems : f2items).push_back(it);
+                        (j.fast_path == 1 ? fitems : j.fast_path == 2 ? f2items : f3items).push_back(it);
                         if (j.redo_flag) ritems.push_back(it);
                     }
                 }
@@ -678,6 +708,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     const StreamItem *d_sitems = blob.dptr<const StreamItem>(blob.put(sitems.data(), sitems.size() * sizeof(StreamItem), 16));
     const StreamItem *d_fitems = blob.dptr<const StreamItem>(blob.put(fitems.data(), fitems.size() * sizeof(StreamItem), 16));
     const StreamItem *d_f2items = blob.dptr<const StreamItem>(blob.put(f2items.data(), f2items.size() * sizeof(StreamItem), 16));
+    const StreamItem *d_f3items = blob.dptr<const StreamItem>(blob.put(f3items.data(), f3items.size() * sizeof(StreamItem), 16));
     const StreamItem *d_ritems = blob.dptr<const StreamItem>(blob.put(ritems.data(), ritems.size() * sizeof(StreamItem), 16));
     const ExactJob *d_fixjobs = blob.dptr<const ExactJob>(blob.put(fixjobs.data(), fixjobs.size() * sizeof(ExactJob), 16));
     const ExactJob *d_xjobs = blob.dptr<const ExactJob>(blob.put(xjobs.data(), xjobs.size() * sizeof(ExactJob), 16));
@@ -696,23 +727,31 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     // already fills the GPU; overlapping them only makes them evict each other), while the
     // copies of the other lanes overlap with them.
     if (d.last_compute) IPG_CU(cudaStreamWaitEvent(st, d.last_compute, 0));
-    if ((!fitems.empty() || !f2items.empty()) && redo_flags) IPG_CU(cudaMemsetAsync(redo_flags, 0, 4 * max_jobs, st));
+    if ((!fitems.empty() || !f2items.empty() || !f3items.empty()) && redo_flags) IPG_CU(cudaMemsetAsync(redo_flags, 0, 4 * max_jobs, st));
     IPG_CU(cudaEventRecord(L.ev[0], st));
     // Two streams: the lean local-target launch (resize + watermark copy) on the lane's stream; beside it, on a
     // side stream, the lean wide-target launch (thumbnail) and the general launch over whatever neither lean kernel
     // takes -- each fills the other's ramp and tail.  The on-demand redo of lean jobs follows both.
     const bool side_work = !f2items.empty() || !sitems.empty();
-    const bool side = side_work && !fitems.empty() && c.overlap_streams;
+    const bool main_work = !fitems.empty() || !f3items.empty();
+    const bool side = side_work && main_work && c.overlap_streams;
     cudaStream_t s2 = side ? L.st2 : st;
     if (side) {
         IPG_CU(cudaEventRecord(L.fork, st));
         IPG_CU(cudaStreamWaitEvent(L.st2, L.fork, 0));
     }
-    if (!side && !fitems.empty()) { // no overlap: lean local first, timed alone
-        IPG_CU(launch_stream_fast(d_sjobs, d_fitems, (int)fitems.size(), 1, any_wm_fast, fix, st));
-        B.n_kernels++;
+    auto launch_main = [&]() { // the lean launches that carry most of the bytes
+        if (!f3items.empty()) {
+            IPG_CU(launch_stream_fast(d_sjobs, d_f3items, (int)f3items.size(), 3, any_wm_fast3, fix, st));
+            B.n_kernels++;
+        }
+        if (!fitems.empty()) {
+            IPG_CU(launch_stream_fast(d_sjobs, d_fitems, (int)fitems.size(), 1, any_wm_fast, fix, st));
+            B.n_kernels++;
+        }
         IPG_CU(cudaEventRecord(L.evf, st));
-    }
+    };
+    if (!side && main_work) launch_main(); // no overlap: timed alone
     if (!f2items.empty()) {
         IPG_CU(launch_stream_fast(d_sjobs, d_f2items, (int)f2items.size(), 2, any_wm_fast2, fix, s2));
         B.n_kernels++;
@@ -723,15 +762,14 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     }
     if (side) {
         IPG_CU(cudaEventRecord(L.join, L.st2));
-        IPG_CU(launch_stream_fast(d_sjobs, d_fitems, (int)fitems.size(), 1, any_wm_fast, fix, st));
-        B.n_kernels++;
-        IPG_CU(cudaEventRecord(L.evf, st));
+        launch_main();
         IPG_CU(cudaStreamWaitEvent(st, L.join, 0));
-    } else if (fitems.empty()) {
+    } else if (!main_work) {
         IPG_CU(cudaEventRecord(L.evf, st));
     }
     if (!ritems.empty()) {
-        IPG_CU(launch_stream(d_sjobs, d_ritems, (int)ritems.size(), 1, any_wm_fast || any_wm_fast2, fix, st));
+        IPG_CU(launch_stream(d_sjobs, d_ritems, (int)ritems.size(), f3items.empty() ? 1 : 2,
+                             any_wm_fast || any_wm_fast2 || any_wm_fast3, fix, st));
         B.n_kernels++;
     }
     IPG_CU(cudaEventRecord(L.ev[1], st));
@@ -1178,9 +1216,9 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
         if (k.lane_pinned_bytes == 0) k.lane_pinned_bytes = 256ull << 20;
         c->cfg = k;
         c->trace = getenv("IPG_TRACE") && atoi(getenv("IPG_TRACE")) != 0;
-        c->fuse_targets = k.fuse_targets == 2 ? 2 : 1;
+        c->fuse_targets = (k.fuse_targets >= 1 && k.fuse_targets <= 3) ? k.fuse_targets : 1;
         c->overlap_streams = !(getenv("IPG_NO_OVERLAP") && atoi(getenv("IPG_NO_OVERLAP")) != 0);
-        if (getenv("IPG_FUSE_TARGETS")) c->fuse_targets = std::min(2, std::max(1, atoi(getenv("IPG_FUSE_TARGETS"))));
+        if (getenv("IPG_FUSE_TARGETS")) c->fuse_targets = std::min(3, std::max(1, atoi(getenv("IPG_FUSE_TARGETS"))));
         std::vector<int> ids;
         if (device_ids && n > 0) ids.assign(device_ids, device_ids + n);
         else for (int i = 0; i < count; i++) ids.push_back(i);

@@ -127,6 +127,12 @@ struct WatermarkD {
 #ifndef IPG_STAGES_FAST
 #define IPG_STAGES_FAST 4
 #endif
+#ifndef IPG_CTAS_FAST2
+#define IPG_CTAS_FAST2 3
+#endif
+#ifndef IPG_STAGES_FAST2
+#define IPG_STAGES_FAST2 4
+#endif
 
 // k_stream CTA: 4 V warps + one producer warp (one elected lane drives the TMA ring: bulk
 // loads of source rows + group records, bulk stores of the watermark copy straight out of
@@ -146,7 +152,8 @@ enum {
     STREAM_LOCAL_MAX_HALO = 16, // a target is local when its widest support - 1 fits this overlap
     STREAM_STAGES_2T = IPG_STAGES_2T, STREAM_CTAS_2T = IPG_CTAS_2T,   // ring depth / CTAs per SM, two-target instantiation
     STREAM_STAGES_1T = IPG_STAGES_1T, STREAM_CTAS_1T = IPG_CTAS_1T,   // ... otherwise
-    STREAM_STAGES_FAST = IPG_STAGES_FAST, STREAM_CTAS_FAST = IPG_CTAS_FAST, // the lean single-target instantiation
+    STREAM_STAGES_FAST = IPG_STAGES_FAST, STREAM_CTAS_FAST = IPG_CTAS_FAST, // the lean single-target instantiations
+    STREAM_STAGES_FAST2 = IPG_STAGES_FAST2, STREAM_CTAS_FAST2 = IPG_CTAS_FAST2, // the lean local + wide instantiation
 };
 
 struct StreamJob {
@@ -158,7 +165,8 @@ struct StreamJob {
     int32_t slab_cols;         // 3 * warp_stride + 128: columns a CTA loads per row
     int32_t n_tiles, n_bands;
     int32_t check_premul;      // RGBA8 source, alpha unknown, a two_stage target exists
-    int32_t fast_path;         // 1 / 2: a lean instantiation (local / wide target) runs this job; the general one only redoes it on demand
+    int32_t fast_path;         // 1 / 2 / 3: a lean instantiation (local / wide / local + wide targets) runs this job;
+                               // the general one only redoes it on demand
     int32_t *redo_flag;        // fast_path: raised by the lean kernel on a non-opaque pixel (nullptr: caller vouches for opacity)
     const int32_t *band_y;     // [n_bands+1] owned source rows of each band
     const int32_t *band_yend;  // [n_bands]   one past the last row the band must read

@@ -470,8 +470,8 @@ template <int NT, int STAGES> struct __align__(128) StreamSmem {
 };
 template <int NT, int LEAN = 0> struct StreamCfg {
     static constexpr bool FAST = LEAN != 0;
-    static constexpr int STAGES = FAST ? STREAM_STAGES_FAST : NT == 2 ? STREAM_STAGES_2T : STREAM_STAGES_1T;
-    static constexpr int CTAS_PER_SM = FAST ? STREAM_CTAS_FAST : NT == 2 ? STREAM_CTAS_2T : STREAM_CTAS_1T;
+    static constexpr int STAGES = LEAN == 3 ? STREAM_STAGES_FAST2 : FAST ? STREAM_STAGES_FAST : NT == 2 ? STREAM_STAGES_2T : STREAM_STAGES_1T;
+    static constexpr int CTAS_PER_SM = LEAN == 3 ? STREAM_CTAS_FAST2 : FAST ? STREAM_CTAS_FAST : NT == 2 ? STREAM_CTAS_2T : STREAM_CTAS_1T;
     using Smem = StreamSmem<NT, STAGES>;
 };
 
@@ -695,6 +695,69 @@ __device__ __forceinline__ void v_rows_fast(VAcc<false> &S, const StreamJob &J, 
     }
 }
 
+// The lean two-target case: target 0 local (inline lane-per-output pass), target 1 wide (split pass
+// through xpass, once per ~15 rows) -- resize + thumbnail (+ watermark copy) with the source read once.
+template <typename SM>
+__device__ __forceinline__ void v_rows_fast2(VAcc<false> *S, const StreamJob &J, const StreamStage &stg, SM &sm, const VCtx &C,
+                                             const FixList &fix)
+{
+    uint4 cur = stg.rows[0][C.slot];
+#pragma unroll
+    for (int k = 0; k < STREAM_GROUP; k++) {
+        const uint4 nxt = stg.rows[(k + 1) & (STREAM_GROUP - 1)][C.slot];
+        float2 vp[6];
+        unpack_rgb(cur, vp);
+        {
+            const float4 r = *reinterpret_cast<const float4 *>(&stg.rec[0].row[k]); // LDS.128 broadcast
+            const float2 w00 = make_float2(r.x, r.x), w11 = make_float2(r.y, r.y);
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                S[0].rgb[0][i] = __ffma2_rn(vp[i], w00, S[0].rgb[0][i]);
+                S[0].rgb[1][i] = __ffma2_rn(vp[i], w11, S[0].rgb[1][i]);
+            }
+            const int e = stg.rec[0].emit[k];
+            if (e >= 0) { // CTA-uniform
+                if (e & 1) park_row<1, false>(S[0], r.w, sm.xbuf[0], C.pslot[0]);
+                else       park_row<0, false>(S[0], r.z, sm.xbuf[0], C.pslot[0]);
+                __syncwarp();
+                const float4 *buf = sm.xbuf[0];
+                float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < STREAM_XTAPS; q++) { // weight 0 past the end adds exactly nothing
+                    const float4 v = buf[swz(C.x0_e0 + q * C.x0_parts)];
+                    const float2 ww = make_float2(C.x0_w[q], C.x0_w[q]);
+                    rg = __ffma2_rn(make_float2(v.x, v.y), ww, rg);
+                    ba = __ffma2_rn(make_float2(v.z, v.w), ww, ba);
+                }
+                for (int off = 1; off < C.x0_parts; off <<= 1) {
+                    rg.x += __shfl_xor_sync(0xffffffffu, rg.x, off);
+                    rg.y += __shfl_xor_sync(0xffffffffu, rg.y, off);
+                    ba.x += __shfl_xor_sync(0xffffffffu, ba.x, off);
+                    ba.y += __shfl_xor_sync(0xffffffffu, ba.y, off);
+                }
+                if (C.x0_ox >= 0 && (threadIdx.x & (C.x0_parts - 1)) == 0) xfinish(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
+                __syncwarp(); // the strip is reused by the next emit
+            }
+        }
+        if (C.act[1]) { // CTA-uniform: this tile overlaps the crop square
+            const float4 r = *reinterpret_cast<const float4 *>(&stg.rec[1].row[k]);
+            const float2 w00 = make_float2(r.x, r.x), w11 = make_float2(r.y, r.y);
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                S[1].rgb[0][i] = __ffma2_rn(vp[i], w00, S[1].rgb[0][i]);
+                S[1].rgb[1][i] = __ffma2_rn(vp[i], w11, S[1].rgb[1][i]);
+            }
+            const int e = stg.rec[1].emit[k];
+            if (e >= 0) {
+                if (e & 1) park_row<1, false>(S[1], r.w, sm.xbuf[1], C.pslot[1]);
+                else       park_row<0, false>(S[1], r.z, sm.xbuf[1], C.pslot[1]);
+                xpass<2>(J, sm, 1, e >> 1, C.tile, C.cx0, C.vtid, fix);
+            }
+        }
+        cur = nxt;
+    }
+}
+
 // The source rows of one ring stage into every active target; rows are taken one at a
 // time (the next one is requested before this one's math) so the code stays small.
 template <int NT, bool WM, bool ALPHA, typename SM>
@@ -808,8 +871,10 @@ template <int NT, bool WM, int LEAN>
 __global__ void __launch_bounds__(STREAM_CTA, (StreamCfg<NT, LEAN>::CTAS_PER_SM))
 k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ items, FixList fix)
 {
-    constexpr bool FAST = LEAN != 0; // LEAN 1: local target (lane-per-output pass inline); 2: wide target (split pass)
-    static_assert(!FAST || NT == 1, "the lean instantiations have exactly one target");
+    // LEAN 1: one local target (lane-per-output pass inline); 2: one wide target (split pass);
+    // 3: a local and a wide target fused (the source is read once for resize + thumbnail)
+    constexpr bool FAST = LEAN != 0;
+    static_assert(!FAST || (LEAN == 3 ? NT == 2 : NT == 1), "lean instantiations: one target, or local + wide");
     constexpr int STAGES = StreamCfg<NT, LEAN>::STAGES;
     using Smem = typename StreamCfg<NT, LEAN>::Smem;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -958,7 +1023,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
 #pragma unroll
     for (int k = 0; k < STREAM_XTAPS; k++) C.x0_w[k] = 0.f;
     if constexpr (NT > 0) {
-        if (LEAN == 1 || (!FAST && C.act[0] && sm.xi[0].local && sm.xi[0].parts >= 1)) {
+        if (LEAN == 1 || LEAN == 3 || (!FAST && C.act[0] && sm.xi[0].local && sm.xi[0].parts >= 1)) {
             C.x0_inline = true;
             C.x0_parts = sm.xi[0].parts;
             C.x0_ox = sm.xt.ox[0][tid];
@@ -1010,7 +1075,8 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
                 }
             }
         }
-        if constexpr (FAST) v_rows_fast<LEAN>(S[0], J, stg, sm, C, fix);
+        if constexpr (LEAN == 3) v_rows_fast2(S, J, stg, sm, C, fix);
+        else if constexpr (FAST) v_rows_fast<LEAN>(S[0], J, stg, sm, C, fix);
         else                v_rows<NT, WM, false>(S, J, stg, sm, C, ys0 + g * STREAM_GROUP, nr, fix);
         advance();
     }
@@ -1078,6 +1144,9 @@ cudaError_t launch_stream_fast(const StreamJob *jobs, const StreamItem *items, i
     if (kind == 1)
         return any_wm ? launch_stream_t<1, true, 1>(jobs, items, n_items, fix, st)
                       : launch_stream_t<1, false, 1>(jobs, items, n_items, fix, st);
+    if (kind == 3)
+        return any_wm ? launch_stream_t<2, true, 3>(jobs, items, n_items, fix, st)
+                      : launch_stream_t<2, false, 3>(jobs, items, n_items, fix, st);
     return any_wm ? launch_stream_t<1, true, 2>(jobs, items, n_items, fix, st)
                   : launch_stream_t<1, false, 2>(jobs, items, n_items, fix, st);
 }

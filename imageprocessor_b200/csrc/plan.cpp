@@ -298,6 +298,10 @@ static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const Stream
             }
         }
     }
+    g->lean2_ok = n_targets == 2 && g->t[0].local && !g->t[1].local;
+    for (int i = 0; i < 2 && g->lean2_ok; i++)
+        for (int tile = 0; tile < g->n_tiles && g->lean2_ok; tile++)
+            if (g->t[i].tile_ox[tile + 1] > g->t[i].tile_ox[tile] && (g->t[i].tile_parts[tile] & 255) < 1) g->lean2_ok = false;
     g->lean_ok = n_targets == 1;
     for (int tile = 0; tile < g->n_tiles && g->lean_ok; tile++)
         if (g->t[0].tile_ox[tile + 1] > g->t[0].tile_ox[tile] && (g->t[0].tile_parts[tile] & 255) < 1) g->lean_ok = false;

@@ -96,8 +96,9 @@ typedef struct {
     int32_t lanes_per_device;    /* streams + staging sets per device, default 3 */
     int32_t max_batch;           /* tickets coalesced into one launch sequence, default 16 */
     int32_t batch_window_us;     /* how long the batcher waits to fill a batch; <0: default 200, 0: none */
-    int32_t fuse_targets;        /* resample targets per pass over the source: 0/1 = one pass per target (default,
-                                    faster on B200: higher occupancy beats the second read), 2 = fuse two */
+    int32_t fuse_targets;        /* resample targets per pass over the source: 0/1 = one per pass (default, measured fastest on
+                                    B200), 2 = fuse two (general instantiation), 3 = fuse a narrow- and a wide-support target
+                                    in the lean fused instantiation when eligible */
     uint64_t lane_device_bytes;  /* device arena per lane, default 1 GiB      */
     uint64_t lane_pinned_bytes;  /* pinned staging per lane (for non-pinned callers), default 256 MiB */
 } ipg_config;

@@ -21,8 +21,8 @@ def full_pipeline(e, a, text="© ImageProcessor"):
     return out, (nw, nh), gl, col
 
 
-@pytest.mark.parametrize("w,h,gen,fuse", [(4000, 3000, "random", 1), (4000, 3000, "gradient", 2), (7680, 4320, "random", 1),
-                                          (3000, 4000, "random", 2)])
+@pytest.mark.parametrize("w,h,gen,fuse", [(4000, 3000, "random", 1), (4000, 3000, "random", 3), (4000, 3000, "gradient", 2),
+                                          (7680, 4320, "random", 1), (3000, 4000, "random", 3)])
 def test_baseline_sizes_bit_exact(engines, oracle, w, h, gen, fuse):
     a = rgba_random(w, h, 1000) if gen == "random" else rgba_gradient(w, h)
     e = engines(ip.PRECISION_EXACT, lane_device_bytes=2 << 30, fuse_targets=fuse)

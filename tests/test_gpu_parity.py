@@ -66,7 +66,7 @@ def test_watermark_bit_exact(engines, oracle, w, h):
     assert not np.array_equal(out[0], a)      # the blend did something
 
 
-@pytest.mark.parametrize("fuse", [1, 2])
+@pytest.mark.parametrize("fuse", [1, 2, 3])
 def test_full_pipeline_one_pass(engines, oracle, fuse):
     w, h = 1600, 1200
     a = rgba_gradient(w, h)

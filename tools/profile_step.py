@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--w", type=int, default=4000)
     ap.add_argument("--h", type=int, default=3000)
     ap.add_argument("--opaque-hint", type=int, default=0)
+    ap.add_argument("--fuse", type=int, default=0)
     a = ap.parse_args()
     import torch
     dev = torch.device("cuda", 0)
@@ -45,7 +46,7 @@ def main():
     gl = G.layout_watermark(W, H, "© ImageProcessor")
     col, _ = G.parse_color("255,255,255", 0.5)
     eng = ip.Engine(devices=[0], precision=a.precision, lanes_per_device=a.lanes, max_batch=a.max_batch,
-                    batch_window_us=2000)
+                    batch_window_us=2000, fuse_targets=a.fuse)
     for step in range(a.steps + 1):
         if step == 1:
             eng.reset_stats()
