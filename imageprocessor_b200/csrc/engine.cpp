@@ -287,6 +287,10 @@ struct Ctx {
     // 2: two targets in the general instantiation (39 us); 3: a local and a wide target in the lean fused
     // instantiation when eligible (38 us: 48 accumulators per thread cost more occupancy than the second read saves)
     int fuse_targets = 1;
+    // local- and wide-target lean jobs in ONE launch (k_stream<1,WM,4>): CTAs of the HBM-bound resize + watermark
+    // pass and of the issue-bound thumbnail pass share the SMs (26.2 vs 28.4 us per 12 MP image).  IPG_MERGE_LEAN=0
+    // launches them separately (k_stream<1,WM,1> and <1,WM,2> on two streams), which is how bench.py times each pass alone.
+    bool merge_lean = true;
     bool overlap_streams = true; // IPG_NO_OVERLAP=1: lean and general k_stream launches back to back (per-kernel timing)
     // stats
     std::atomic<uint64_t> s_done{0}, s_batches{0}, s_kernels{0}, s_h2d{0}, s_d2h{0}, s_fix{0}, s_fallback{0}, s_staged{0};
@@ -652,7 +656,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 const bool wm_tma_ok = !wm || ((sv.w % 4) == 0 && ((((uintptr_t)wm->dev_out) | (uintptr_t)wm->dev_pitch) & 15) == 0);
                 j.fast_path = 0;
                 if (wm_tma_ok && redo_flags && (size_t)ji < max_jobs) {
-                    if (geom->lean_ok) j.fast_path = geom->t[0].local ? 1 : 2;
+                    if (geom->lean_ok) j.fast_path = (geom->t[0].local || c.merge_lean) ? 1 : 2;
                     else if (lean2 && geom->lean2_ok) j.fast_path = 3;
                 }
                 j.redo_flag = (j.fast_path && !t.src.opaque_hint) ? redo_flags + ji : nullptr;
@@ -746,7 +750,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
             B.n_kernels++;
         }
         if (!fitems.empty()) {
-            IPG_CU(launch_stream_fast(d_sjobs, d_fitems, (int)fitems.size(), 1, any_wm_fast, fix, st));
+            IPG_CU(launch_stream_fast(d_sjobs, d_fitems, (int)fitems.size(), c.merge_lean ? 4 : 1, any_wm_fast, fix, st));
             B.n_kernels++;
         }
         IPG_CU(cudaEventRecord(L.evf, st));
@@ -1217,6 +1221,7 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
         c->cfg = k;
         c->trace = getenv("IPG_TRACE") && atoi(getenv("IPG_TRACE")) != 0;
         c->fuse_targets = (k.fuse_targets >= 1 && k.fuse_targets <= 3) ? k.fuse_targets : 1;
+        if (getenv("IPG_MERGE_LEAN")) c->merge_lean = atoi(getenv("IPG_MERGE_LEAN")) != 0;
         c->overlap_streams = !(getenv("IPG_NO_OVERLAP") && atoi(getenv("IPG_NO_OVERLAP")) != 0);
         if (getenv("IPG_FUSE_TARGETS")) c->fuse_targets = std::min(3, std::max(1, atoi(getenv("IPG_FUSE_TARGETS"))));
         std::vector<int> ids;

@@ -668,7 +668,7 @@ __device__ __forceinline__ void v_rows_fast(VAcc<false> &S, const StreamJob &J, 
         if (e >= 0) { // CTA-uniform: this source row completes output row e>>1, held in set e&1
             if (e & 1) park_row<1, false>(S, r.w, sm.xbuf[0], C.pslot[0]);
             else       park_row<0, false>(S, r.z, sm.xbuf[0], C.pslot[0]);
-            if constexpr (LEAN == 1) { // local target: this warp filters its own strip, one output per lane
+            if (LEAN == 1 || (LEAN == 4 && C.x0_inline)) { // local target: this warp filters its own strip, one output per lane
                 __syncwarp();
                 const float4 *buf = sm.xbuf[0];
                 float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
@@ -687,6 +687,31 @@ __device__ __forceinline__ void v_rows_fast(VAcc<false> &S, const StreamJob &J, 
                 }
                 if (C.x0_ox >= 0 && (threadIdx.x & (C.x0_parts - 1)) == 0) xfinish(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
                 __syncwarp(); // the strip is reused by the next emit
+            } else if constexpr (LEAN == 4) { // wide target, inline (no call: the accumulators stay in registers)
+                vwarps_bar(); // all four warps have parked
+                const int tid = (int)threadIdx.x;
+                const int ox = sm.xt.ox[0][tid], e0 = sm.xt.e0[0][tid];
+                const int P = sm.xi[0].parts, ntap = sm.xi[0].ntap;
+                const float4 *buf = sm.xbuf[0];
+                float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
+                if (ox >= 0) {
+#pragma unroll 4
+                    for (int q = 0; q < ntap; q++) {
+                        const float w = sm.xt.w[0][q][tid];
+                        const float4 v = buf[swz(e0 + q * P)];
+                        const float2 ww = make_float2(w, w);
+                        rg = __ffma2_rn(make_float2(v.x, v.y), ww, rg);
+                        ba = __ffma2_rn(make_float2(v.z, v.w), ww, ba);
+                    }
+                }
+                for (int off = 1; off < P; off <<= 1) {
+                    rg.x += __shfl_xor_sync(0xffffffffu, rg.x, off);
+                    rg.y += __shfl_xor_sync(0xffffffffu, rg.y, off);
+                    ba.x += __shfl_xor_sync(0xffffffffu, ba.x, off);
+                    ba.y += __shfl_xor_sync(0xffffffffu, ba.y, off);
+                }
+                if (ox >= 0 && (tid & (P - 1)) == 0) xfinish(sm.xi[0], sm.xi[0].D, ox, e >> 1, rg, ba, fix);
+                vwarps_bar(); // the row buffer is reused by the next emit
             } else {           // wide support (the thumbnail): CTA-wide split pass, once per ~15 rows
                 xpass<1>(J, sm, 0, e >> 1, C.tile, C.cx0, C.vtid, fix);
             }
@@ -872,7 +897,8 @@ __global__ void __launch_bounds__(STREAM_CTA, (StreamCfg<NT, LEAN>::CTAS_PER_SM)
 k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ items, FixList fix)
 {
     // LEAN 1: one local target (lane-per-output pass inline); 2: one wide target (split pass);
-    // 3: a local and a wide target fused (the source is read once for resize + thumbnail)
+    // 3: a local and a wide target fused (the source is read once for resize + thumbnail);
+    // 4: one target, local or wide decided per CTA (both passes inline): CTAs of both kinds share the SMs
     constexpr bool FAST = LEAN != 0;
     static_assert(!FAST || (LEAN == 3 ? NT == 2 : NT == 1), "lean instantiations: one target, or local + wide");
     constexpr int STAGES = StreamCfg<NT, LEAN>::STAGES;
@@ -1023,7 +1049,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
 #pragma unroll
     for (int k = 0; k < STREAM_XTAPS; k++) C.x0_w[k] = 0.f;
     if constexpr (NT > 0) {
-        if (LEAN == 1 || LEAN == 3 || (!FAST && C.act[0] && sm.xi[0].local && sm.xi[0].parts >= 1)) {
+        if (LEAN == 1 || LEAN == 3 || (LEAN == 4 && sm.xi[0].local) || (!FAST && C.act[0] && sm.xi[0].local && sm.xi[0].parts >= 1)) {
             C.x0_inline = true;
             C.x0_parts = sm.xi[0].parts;
             C.x0_ox = sm.xt.ox[0][tid];
@@ -1144,6 +1170,9 @@ cudaError_t launch_stream_fast(const StreamJob *jobs, const StreamItem *items, i
     if (kind == 1)
         return any_wm ? launch_stream_t<1, true, 1>(jobs, items, n_items, fix, st)
                       : launch_stream_t<1, false, 1>(jobs, items, n_items, fix, st);
+    if (kind == 4)
+        return any_wm ? launch_stream_t<1, true, 4>(jobs, items, n_items, fix, st)
+                      : launch_stream_t<1, false, 4>(jobs, items, n_items, fix, st);
     if (kind == 3)
         return any_wm ? launch_stream_t<2, true, 3>(jobs, items, n_items, fix, st)
                       : launch_stream_t<2, false, 3>(jobs, items, n_items, fix, st);

@@ -10,5 +10,5 @@ python bench.py --steps 1 --warmup 3 --images 64 --no-e2e --no-cpu-baseline --no
 ncu --metrics gpu__time_duration.sum --clock-control none -c 260 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 1 --warmup 3 --images 64 --no-e2e --no-cpu-baseline --no-verify > gpurun_out/ncu_launches_$TAG.log 2>&1
 echo launches rc=$?
-# full capture of the dominant kernel (the lean k_stream instantiation with the watermark copy)
-KREGEX='k_stream<1, true, true>' KSKIP=1 bash tools/jobs/ncu_one.sh rtw lean_$TAG | tail -4
+# full captures (ncu --set full) of the dominant kernel and of its main pass alone
+bash tools/jobs/ncu_two.sh $TAG
