@@ -36,7 +36,7 @@ rep = os.path.join(ROOT, "gpurun_out", f"prof_{ftag}.ncu-rep")
 txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hot.py"), rep, "1.0"], capture_output=True, text=True).stdout
 with open(os.path.join(out, f"{rnd}_k_stream_full.txt"), "w") as f:
     f.write(f"ncu --set full --clock-control none --import-source on -k regex:k_stream -s 1 -c 1\n")
-    f.write(f"command: python tools/profile_step.py --images {n_img} --steps 1 --ops rtw  (one launch = {n_img} 12 MP images; kernel filter: the lean instantiation k_stream<1,true,true>)\n")
+    f.write(f"command: python tools/profile_step.py --images {n_img} --steps 1 --ops rtw  (one launch = {n_img} 12 MP images; kernel filter: the merged lean instantiation k_stream<1,true,4>)\n")
     f.write("summary by tools/ncu_hot.py (headline metrics, stall totals, SASS lines with >= 1% of the samples)\n\n")
     f.write(txt)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
