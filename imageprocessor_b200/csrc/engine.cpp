@@ -407,6 +407,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     std::vector<StreamItem> fitems;   // lean instantiation, local target
     std::vector<StreamItem> f2items;  // lean instantiation, wide target
     std::vector<StreamItem> f3items;  // lean instantiation, local + wide targets fused
+    std::vector<StreamItem> pitems;   // k_stream_planar (YCbCr sources)
     bool any_wm_fast = false, any_wm_fast2 = false, any_wm_fast3 = false;
     size_t max_jobs = 0;
     for (auto &tp : B.tickets) max_jobs += tp->ops.size() + 1;
@@ -678,9 +679,66 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 }
             }
         } else {
+            // planar YCbCr: the lean planar kernel takes every resample whose geometry streams in a cached form
+            const bool planar_ok = precision != IPG_PRECISION_REFERENCE && sv.layout >= L_YCBCR444 && sv.layout <= L_YCBCR440 &&
+                                   ((((uintptr_t)sv.p0) | ((uintptr_t)sv.p1) | ((uintptr_t)sv.p2) | (uintptr_t)sv.s0 |
+                                     (uintptr_t)sv.s1 | (uintptr_t)sv.s2) & 15) == 0;
             for (auto *op : res) {
-                add_exact_whole(*op);
-                if (precision != IPG_PRECISION_REFERENCE) B.exact_fallbacks++;
+                std::shared_ptr<const StreamGeom> geom;
+                StreamTargetSpec sp1{0, 0, sv.w, sv.h, op->dw, op->dh};
+                if (op->kind == IPG_OP_THUMB_CROP) sp1 = StreamTargetSpec{op->rx, op->ry, op->rw, op->rh, op->dw, op->dh};
+                if (planar_ok) geom = get_stream_geom(sv.w, sv.h, &sp1, 1, false, bands_hint, 1.0);
+                if (!geom || !geom->lean_ok) {
+                    add_exact_whole(*op);
+                    if (precision != IPG_PRECISION_REFERENCE) B.exact_fallbacks++;
+                    continue;
+                }
+                StreamJob j{};
+                j.src = sv;
+                j.n_targets = 1;
+                j.tile_w = geom->tile_w;
+                j.warp_stride = geom->warp_stride;
+                j.slab_cols = geom->slab_cols;
+                j.n_tiles = geom->n_tiles;
+                j.n_bands = geom->n_bands;
+                j.band_y = blob.put_vec(geom->band_y);
+                j.band_yend = blob.put_vec(geom->band_yend);
+                j.grec = blob.put_vec(geom->grec);
+                j.band_grec_off = blob.put_vec(geom->band_grec_off);
+                const StreamTargetGeom &tgm = geom->t[0];
+                StreamTarget &o = j.t[0];
+                o.dst = op->dev_out;
+                o.dst_stride = (int)op->dev_pitch;
+                o.dw = op->dw; o.dh = op->dh;
+                o.rect_x = sp1.rect_x; o.rect_y = sp1.rect_y;
+                o.two_stage = op->kind == IPG_OP_THUMB_CROP;
+                o.fix_d = tgm.fix_d;
+                o.xoff = blob.put_vec(tgm.ax->off);
+                o.xfirst = blob.put_vec(tgm.ax->first);
+                o.xw = blob.put_vec(tgm.xw);
+                o.tile_ox = blob.put_vec(tgm.tile_ox);
+                o.local = tgm.local ? 1 : 0;
+                o.warp_ox = tgm.local ? blob.put_vec(tgm.warp_ox) : nullptr;
+                o.tile_parts = blob.put_vec(tgm.tile_parts);
+                o.rows = blob.put_vec(tgm.rows);
+                o.band_rec_off = blob.put_vec(tgm.band_rec_off);
+                o.band_tend = blob.put_vec(tgm.band_tend);
+                o.band_oy = blob.put_vec(tgm.band_oy);
+                o.exact_job = -1;
+                if (precision == IPG_PRECISION_EXACT) {
+                    o.exact_job = add_exact(*op, fixjobs);
+                    fix_px += (uint64_t)o.dw * (uint64_t)o.dh;
+                }
+                j.fast_path = 5;
+                const int ji = (int)sjobs.size();
+                sjobs.push_back(j);
+                B.fast_jobs++;
+                for (auto it : geom->items) {
+                    // tiles outside the crop square have no outputs: skip them
+                    if (tgm.tile_ox[it.tile + 1] == tgm.tile_ox[it.tile]) continue;
+                    it.job = ji;
+                    pitems.push_back(it);
+                }
             }
         }
         for (; wi < wms.size(); wi++) {
@@ -713,6 +771,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     const StreamItem *d_fitems = blob.dptr<const StreamItem>(blob.put(fitems.data(), fitems.size() * sizeof(StreamItem), 16));
     const StreamItem *d_f2items = blob.dptr<const StreamItem>(blob.put(f2items.data(), f2items.size() * sizeof(StreamItem), 16));
     const StreamItem *d_f3items = blob.dptr<const StreamItem>(blob.put(f3items.data(), f3items.size() * sizeof(StreamItem), 16));
+    const StreamItem *d_pitems = blob.dptr<const StreamItem>(blob.put(pitems.data(), pitems.size() * sizeof(StreamItem), 16));
     const StreamItem *d_ritems = blob.dptr<const StreamItem>(blob.put(ritems.data(), ritems.size() * sizeof(StreamItem), 16));
     const ExactJob *d_fixjobs = blob.dptr<const ExactJob>(blob.put(fixjobs.data(), fixjobs.size() * sizeof(ExactJob), 16));
     const ExactJob *d_xjobs = blob.dptr<const ExactJob>(blob.put(xjobs.data(), xjobs.size() * sizeof(ExactJob), 16));
@@ -737,7 +796,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     // side stream, the lean wide-target launch (thumbnail) and the general launch over whatever neither lean kernel
     // takes -- each fills the other's ramp and tail.  The on-demand redo of lean jobs follows both.
     const bool side_work = !f2items.empty() || !sitems.empty();
-    const bool main_work = !fitems.empty() || !f3items.empty();
+    const bool main_work = !fitems.empty() || !f3items.empty() || !pitems.empty();
     const bool side = side_work && main_work && c.overlap_streams;
     cudaStream_t s2 = side ? L.st2 : st;
     if (side) {
@@ -745,6 +804,10 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
         IPG_CU(cudaStreamWaitEvent(L.st2, L.fork, 0));
     }
     auto launch_main = [&]() { // the lean launches that carry most of the bytes
+        if (!pitems.empty()) {
+            IPG_CU(launch_stream_planar(d_sjobs, d_pitems, (int)pitems.size(), fix, st));
+            B.n_kernels++;
+        }
         if (!f3items.empty()) {
             IPG_CU(launch_stream_fast(d_sjobs, d_f3items, (int)f3items.size(), 3, any_wm_fast3, fix, st));
             B.n_kernels++;

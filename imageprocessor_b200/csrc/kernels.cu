@@ -1130,6 +1130,238 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     }
 }
 
+// ---------------------------------------------------------------------------------
+// k_stream_planar: the lean streaming resample for planar YCbCr sources (*image.YCbCr,
+// 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0), one target per pass, local or wide per CTA.
+//
+// Same structure as k_stream<1,false,4>; what differs is the source: the producer lands the
+// Y row and the chroma rows that belong to each of the group's 4 luma rows (nearest chroma
+// sample, no interpolation), and the V lanes convert their 4 pixels to the 16-bit RGB that
+// x/image's scaleX_YCbCr<ratio> feeds its filter -- the inlined color.YCbCr.RGBA() integer
+// formula, per tap, before any filtering -- so the result is the reference's, not that of an
+// 8-bit RGBA intermediate.  cropAndResize's 1:1 first pass stores uint8(c16 >> 8), which the
+// second pass re-expands (two_stage).  Alpha is the constant 0xffff.  H2D is 1.5 bytes per
+// pixel instead of 4 for a 4:2:0 JPEG.
+// ---------------------------------------------------------------------------------
+struct __align__(16) PlanarStage {
+    uint8_t y[STREAM_GROUP][STREAM_COLS];
+    uint8_t cb[STREAM_GROUP][STREAM_COLS];
+    uint8_t cr[STREAM_GROUP][STREAM_COLS];
+    GroupRec rec[1];
+};
+template <int STAGES> struct __align__(128) PlanarSmem {
+    PlanarStage stage[STAGES];
+    float4 xbuf[1][STREAM_XBUF];
+    XTab<1> xt;
+    uint64_t full[STAGES], empty[STAGES];
+    XInfo xi[2];
+};
+enum { PLANAR_STAGES = 4, PLANAR_CTAS = 4 };
+
+__device__ __forceinline__ uint32_t clamp16(int v) { return (uint32_t)min(max(v, 0), 0xffff); }
+// two 16-bit samples -> fp32 pair via the 2^23 mantissa trick (exact for values < 2^23)
+__device__ __forceinline__ float2 u16x2_f32(uint32_t a, uint32_t b)
+{
+    return __fadd2_rn(make_float2(__uint_as_float(0x4B000000u | a), __uint_as_float(0x4B000000u | b)),
+                      make_float2(-8388608.0f, -8388608.0f));
+}
+
+__global__ void __launch_bounds__(STREAM_CTA, PLANAR_CTAS)
+k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ items, FixList fix)
+{
+    using Smem = PlanarSmem<PLANAR_STAGES>;
+    constexpr int STAGES = PLANAR_STAGES;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+
+    const StreamItem it = items[blockIdx.x];
+    const StreamJob &J = jobs[it.job];
+    const int tile = it.tile, band = it.band;
+    const int W = J.src.w;
+    const int cx0 = tile * J.tile_w;
+    const int ys0 = __ldg(J.band_y + band);
+    const int yend = __ldg(J.band_yend + band);
+    const int warp = threadIdx.x >> 5;
+    const int ngroups = (yend - ys0 + STREAM_GROUP - 1) / STREAM_GROUP;
+    const int tid = (int)threadIdx.x;
+    const int ws = J.warp_stride;
+    const int slot = (warp & 3) * (ws >> 2) + (tid & 31);
+    const int layout = J.src.layout;
+    const bool sub_x = layout == L_YCBCR422 || layout == L_YCBCR420; // chroma at half horizontal resolution
+    const bool sub_y = layout == L_YCBCR420 || layout == L_YCBCR440; // ... vertical
+    const int ncols = min(J.slab_cols, W - cx0);
+    const uint32_t y_bytes = (uint32_t)((ncols + 15) & ~15);
+    const uint32_t c_bytes = (uint32_t)(((sub_x ? (ncols + 1) >> 1 : ncols) + 15) & ~15);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], STREAM_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // horizontal-pass table (cached form; the engine only sends jobs whose tiles have one)
+    if (tid < STREAM_THREADS) {
+        const StreamTarget &t = J.t[0];
+        const int pv = __ldg(t.tile_parts + tile), P0 = pv & 255, P = max(P0, 1);
+        if (tid == 0) sm.xi[0] = XInfo{t.dst, t.dst_stride, t.exact_job, (uint32_t)t.fix_d, t.local, P, P0 ? pv >> 8 : 0};
+        for (int e = tid; e < STREAM_XBUF; e += STREAM_THREADS) sm.xbuf[0][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int ox = -1, e0 = 0, k0 = 0, n = 0, part = tid & (P - 1);
+        if (P0 > 0) {
+            if (t.local) {
+                const int ox0 = __ldg(t.warp_ox + tile * 4 + warp);
+                if ((tid & 31) / P < __ldg(t.warp_ox + tile * 4 + warp + 1) - ox0) ox = ox0 + (tid & 31) / P;
+                if (ox >= 0) e0 = __ldg(t.xfirst + ox) + t.rect_x - cx0 + warp * (STREAM_WARP_COLS - ws) + part;
+            } else {
+                const int ox0 = __ldg(t.tile_ox + tile);
+                if (tid / P < __ldg(t.tile_ox + tile + 1) - ox0) ox = ox0 + tid / P;
+                if (ox >= 0) e0 = __ldg(t.xfirst + ox) + t.rect_x - cx0 + part;
+            }
+        }
+        if (ox >= 0) {
+            k0 = __ldg(t.xoff + ox);
+            n = __ldg(t.xoff + ox + 1) - k0;
+        }
+        sm.xt.ox[0][tid] = ox;
+        sm.xt.e0[0][tid] = e0;
+#pragma unroll
+        for (int k = 0; k < STREAM_XTAPS_TAB; k++)
+            sm.xt.w[0][k][tid] = (ox >= 0 && part + k * P < n) ? __ldg(t.xw + k0 + part + k * P) : 0.f;
+    }
+    __syncthreads();
+
+    if (warp == STREAM_THREADS / 32) {
+        // ===== producer =====
+        if ((tid & 31) != 0) return;
+        const uint8_t *grec = (const uint8_t *)(J.grec + (size_t)__ldg(J.band_grec_off + band));
+        const int ccx0 = sub_x ? cx0 >> 1 : cx0;
+        auto refill = [&](int group, int stage) {
+            const int y0 = ys0 + group * STREAM_GROUP;
+            const int nr = min(STREAM_GROUP, yend - y0);
+            PlanarStage &st = sm.stage[stage];
+            mbar_arrive_expect_tx(&sm.full[stage], (y_bytes + 2 * c_bytes) * (uint32_t)nr + (uint32_t)sizeof(GroupRec));
+            for (int k = 0; k < nr; k++) {
+                const int y = y0 + k, cy = sub_y ? y >> 1 : y;
+                tma_load_1d(&st.y[k][0], J.src.p0 + (size_t)y * J.src.s0 + cx0, y_bytes, &sm.full[stage]);
+                tma_load_1d(&st.cb[k][0], J.src.p1 + (size_t)cy * J.src.s1 + ccx0, c_bytes, &sm.full[stage]);
+                tma_load_1d(&st.cr[k][0], J.src.p2 + (size_t)cy * J.src.s2 + ccx0, c_bytes, &sm.full[stage]);
+            }
+            tma_load_1d(&st.rec[0], grec + (size_t)group * sizeof(GroupRec), (uint32_t)sizeof(GroupRec), &sm.full[stage]);
+        };
+        for (int g = 0; g < min(STAGES, ngroups); g++) refill(g, g);
+        int sp = 0;
+        uint32_t php = 0;
+        for (int g = 1; g < ngroups; g++) {
+            if (g - 1 + STAGES < ngroups) {
+                mbar_wait(&sm.empty[sp], php);
+                refill(g - 1 + STAGES, sp);
+            }
+            if (++sp == STAGES) { sp = 0; php ^= 1; }
+        }
+        return;
+    }
+
+    // ===== V warps =====
+    VAcc<false> S;
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int i = 0; i < 6; i++) S.rgb[k][i] = make_float2(0.f, 0.f);
+    const bool local = sm.xi[0].local != 0;
+    const bool two_stage = J.t[0].two_stage != 0;
+    const int pslot = local ? tid : slot;
+    const int P = sm.xi[0].parts, ntap = sm.xi[0].ntap;
+    const int x_ox = sm.xt.ox[0][tid], x_e0 = sm.xt.e0[0][tid];
+    int rs = 0;
+    uint32_t rph = 0;
+    for (int g = 0; g < ngroups; g++) {
+        mbar_wait(&sm.full[rs], rph);
+        const PlanarStage &stg = sm.stage[rs];
+#pragma unroll 2
+        for (int k = 0; k < STREAM_GROUP; k++) {
+            // ---- 4 pixels -> 16-bit RGB exactly as color.YCbCr.RGBA() (x/image scaleX_YCbCr*)
+            const uint32_t y4 = *reinterpret_cast<const uint32_t *>(&stg.y[k][slot * 4]);
+            uint32_t cb4, cr4; // chroma byte of each of the 4 pixels
+            if (sub_x) {
+                const uint32_t b2 = *reinterpret_cast<const uint16_t *>(&stg.cb[k][slot * 2]);
+                const uint32_t r2 = *reinterpret_cast<const uint16_t *>(&stg.cr[k][slot * 2]);
+                cb4 = __byte_perm(b2, 0, 0x1100);
+                cr4 = __byte_perm(r2, 0, 0x1100);
+            } else {
+                cb4 = *reinterpret_cast<const uint32_t *>(&stg.cb[k][slot * 4]);
+                cr4 = *reinterpret_cast<const uint32_t *>(&stg.cr[k][slot * 4]);
+            }
+            uint32_t c16[12];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int yy1 = (int)((y4 >> (8 * j)) & 0xff) * 0x10101;
+                const int cb1 = (int)((cb4 >> (8 * j)) & 0xff) - 128;
+                const int cr1 = (int)((cr4 >> (8 * j)) & 0xff) - 128;
+                uint32_t r = clamp16((yy1 + 91881 * cr1) >> 8);
+                uint32_t gg = clamp16((yy1 - 22554 * cb1 - 46802 * cr1) >> 8);
+                uint32_t b = clamp16((yy1 + 116130 * cb1) >> 8);
+                if (two_stage) { // the 1:1 crop pass stored uint8(c16 >> 8); scaleX_RGBA re-expands it
+                    r = (r >> 8) * 0x101u; gg = (gg >> 8) * 0x101u; b = (b >> 8) * 0x101u;
+                }
+                c16[3 * j] = r; c16[3 * j + 1] = gg; c16[3 * j + 2] = b;
+            }
+            float2 vp[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) vp[i] = u16x2_f32(c16[2 * i], c16[2 * i + 1]);
+            const float4 r = *reinterpret_cast<const float4 *>(&stg.rec[0].row[k]);
+            const float2 w00 = make_float2(r.x, r.x), w11 = make_float2(r.y, r.y);
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                S.rgb[0][i] = __ffma2_rn(vp[i], w00, S.rgb[0][i]);
+                S.rgb[1][i] = __ffma2_rn(vp[i], w11, S.rgb[1][i]);
+            }
+            const int e = stg.rec[0].emit[k];
+            if (e >= 0) { // CTA-uniform
+                if (e & 1) park_row<1, false>(S, r.w, sm.xbuf[0], pslot);
+                else       park_row<0, false>(S, r.z, sm.xbuf[0], pslot);
+                if (local) __syncwarp(); else vwarps_bar();
+                const float4 *buf = sm.xbuf[0];
+                float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
+                if (x_ox >= 0) {
+#pragma unroll 4
+                    for (int q = 0; q < ntap; q++) {
+                        const float w = sm.xt.w[0][q][tid];
+                        const float4 v = buf[swz(x_e0 + q * P)];
+                        const float2 ww = make_float2(w, w);
+                        rg = __ffma2_rn(make_float2(v.x, v.y), ww, rg);
+                        ba = __ffma2_rn(make_float2(v.z, v.w), ww, ba);
+                    }
+                }
+                for (int off = 1; off < P; off <<= 1) {
+                    rg.x += __shfl_xor_sync(0xffffffffu, rg.x, off);
+                    rg.y += __shfl_xor_sync(0xffffffffu, rg.y, off);
+                    ba.x += __shfl_xor_sync(0xffffffffu, ba.x, off);
+                    ba.y += __shfl_xor_sync(0xffffffffu, ba.y, off);
+                }
+                if (x_ox >= 0 && (tid & (P - 1)) == 0) xfinish(sm.xi[0], sm.xi[0].D, x_ox, e >> 1, rg, ba, fix);
+                if (local) __syncwarp(); else vwarps_bar();
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&sm.empty[rs]);
+        if (++rs == STAGES) { rs = 0; rph ^= 1; }
+    }
+}
+
+cudaError_t launch_stream_planar(const StreamJob *jobs, const StreamItem *items, int n_items, FixList fix, cudaStream_t st)
+{
+    if (n_items <= 0) return cudaSuccess;
+    using Smem = PlanarSmem<PLANAR_STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_stream_planar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_stream_planar<<<n_items, STREAM_CTA, sizeof(Smem), st>>>(jobs, items, fix);
+    return cudaGetLastError();
+}
+
 int stream_smem_bytes() { return (int)sizeof(StreamCfg<2>::Smem); }
 
 template <int NT, bool WM, int LEAN>

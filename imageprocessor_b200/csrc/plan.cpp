@@ -234,10 +234,13 @@ static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const Stream
     // consecutive V warps overlap by the local halo, rounded up to the 4-pixel thread granule
     g->warp_stride = STREAM_WARP_COLS - (local_halo + STREAM_PX - 1) / STREAM_PX * STREAM_PX;
     g->slab_cols = 3 * g->warp_stride + STREAM_WARP_COLS;
-    const int tile_w_max = ((g->slab_cols - (max_taps_x - 1)) / STREAM_PX) * STREAM_PX;
+    // planar (16-bit sample) sources: tile origins must keep the Y and the half-resolution chroma rows
+    // 16-byte aligned for the bulk copies
+    const int col_align = sample_scale == 1.0 ? 32 : STREAM_PX;
+    const int tile_w_max = ((g->slab_cols - (max_taps_x - 1)) / col_align) * col_align;
     if (tile_w_max < 64) return nullptr;
     g->n_tiles = (W + tile_w_max - 1) / tile_w_max;
-    g->tile_w = (((W + g->n_tiles - 1) / g->n_tiles) + STREAM_PX - 1) / STREAM_PX * STREAM_PX;
+    g->tile_w = (((W + g->n_tiles - 1) / g->n_tiles) + col_align - 1) / col_align * col_align;
     if (g->tile_w > tile_w_max) g->tile_w = tile_w_max;
     g->n_tiles = (W + g->tile_w - 1) / g->tile_w;
 
@@ -273,6 +276,7 @@ static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const Stream
             const StreamTargetGeom &t = g->t[i];
             int par = 0;
             float sa[2] = {0.f, 0.f};
+            const float asamp = (float)(65535.0 / sample_scale); // opaque alpha in source-sample units (255 for 8-bit RGBA)
             for (int32_t gi = 0; gi < ng; gi++) {
                 GroupRec &G = g->grec[(base + (size_t)gi) * (size_t)n_targets + (size_t)i];
                 G.seed0 = sa[0];
@@ -285,8 +289,8 @@ static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const Stream
                     float w[2];
                     w[par] = r.wa;
                     w[par ^ 1] = r.wb;
-                    sa[0] = std::fmaf(255.0f, w[0], sa[0]);
-                    sa[1] = std::fmaf(255.0f, w[1], sa[1]);
+                    sa[0] = std::fmaf(asamp, w[0], sa[0]);
+                    sa[1] = std::fmaf(asamp, w[1], sa[1]);
                     G.row[k] = GroupRow{w[0], w[1], sa[0], sa[1]};
                     G.emit[k] = -1;
                     if (r.emit >= 0) {

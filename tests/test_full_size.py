@@ -73,3 +73,23 @@ def test_properties_at_full_size(engines):
     r1 = e.run(ip.Image.from_rgba(c), [ip.OpSpec.resize(512, 384)])[0].astype(np.int16)
     r2 = e.run(ip.Image.from_rgba(inv), [ip.OpSpec.resize(512, 384)])[0].astype(np.int16)
     assert np.abs((255 - r1[..., :3]) - r2[..., :3]).max() <= 1
+
+
+@pytest.mark.parametrize("layout", ["420", "444", "422", "440"])
+def test_ycbcr_12mp_streams_and_is_bit_exact(engines, oracle, layout):
+    """A 12 MP planar source (what image.Decode hands over for a JPEG): resize + crop thumbnail run on the
+    planar streaming kernel (no whole-image fp64 fallback) and equal the oracle's per-tap 16-bit conversion."""
+    lay = {"420": ip.YCBCR420, "444": ip.YCBCR444, "422": ip.YCBCR422, "440": ip.YCBCR440}[layout]
+    olay = {"420": oracle.YCBCR420, "444": oracle.YCBCR444, "422": oracle.YCBCR422, "440": oracle.YCBCR440}[layout]
+    w, h = 4000, 3000
+    rng = np.random.default_rng(99)
+    ch, cw = oracle.chroma_shape(olay, w, h)
+    y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    cb, cr = rng.integers(0, 256, (ch, cw), dtype=np.uint8), rng.integers(0, 256, (ch, cw), dtype=np.uint8)
+    e = engines(ip.PRECISION_EXACT, lane_device_bytes=2 << 30)
+    f0 = e.stats()["exact_fallbacks"]
+    out = e.run(ip.Image.from_ycbcr(y, cb, cr, lay), [ip.OpSpec.resize(1024, 768), ip.OpSpec.thumb_crop((500, 0, 3000, 3000), 200)])
+    assert e.stats()["exact_fallbacks"] == f0
+    R = oracle.Raster.ycbcr(y, cb, cr, olay)
+    assert np.array_equal(out[0], oracle.resize_image(R, 1024, 768))
+    assert np.array_equal(out[1], oracle.crop_and_resize(R, 200))

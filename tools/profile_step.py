@@ -26,14 +26,22 @@ def main():
     ap.add_argument("--h", type=int, default=3000)
     ap.add_argument("--opaque-hint", type=int, default=0)
     ap.add_argument("--fuse", type=int, default=0)
+    ap.add_argument("--layout", default="rgba", choices=["rgba", "ycbcr420", "ycbcr444"])
     a = ap.parse_args()
     import torch
     dev = torch.device("cuda", 0)
     W, H = a.w, a.h
     srcs = []
     g = torch.Generator(device=dev)
+    planar = a.layout != "rgba"
+    cw, ch = ((W + 1) // 2, (H + 1) // 2) if a.layout == "ycbcr420" else (W, H)
     for i in range(a.images):
         g.manual_seed(1000 + i)
+        if planar:
+            srcs.append((torch.randint(0, 256, (H, W), dtype=torch.uint8, device=dev, generator=g),
+                         torch.randint(0, 256, (ch, cw), dtype=torch.uint8, device=dev, generator=g),
+                         torch.randint(0, 256, (ch, cw), dtype=torch.uint8, device=dev, generator=g)))
+            continue
         t = torch.randint(0, 256, (H, W, 4), dtype=torch.uint8, device=dev, generator=g)
         t[..., 3] = 255
         srcs.append(t)
@@ -59,13 +67,18 @@ def main():
                 ops.append(ip.OpSpec.thumb_crop((cx, cy, cs, cs), 200, dst_device=(o_t[i].data_ptr(), 800)))
             if "w" in a.ops:
                 ops.append(ip.OpSpec.watermark(W, H, col, gl, dst_device=(o_w[i].data_ptr(), W * 4)))
-            img = ip.Image.on_device(ip.RGBA8, W, H, [srcs[i].data_ptr()], [W * 4], opaque_hint=bool(a.opaque_hint))
+            if planar:
+                lay = ip.YCBCR420 if a.layout == "ycbcr420" else ip.YCBCR444
+                img = ip.Image.on_device(lay, W, H, [p.data_ptr() for p in srcs[i]], [W, cw, cw], opaque_hint=True)
+            else:
+                img = ip.Image.on_device(ip.RGBA8, W, H, [srcs[i].data_ptr()], [W * 4], opaque_hint=bool(a.opaque_hint))
             tk.append(eng.submit(img, ops, device=0))
         for t in tk:
             eng.wait(t)
     st = eng.stats()
     n = a.images * a.steps
-    bytes_img = W * H * 4 * (2 if "w" in a.ops else 1) + (nw * nh * 4 if "r" in a.ops else 0) + (160000 if "t" in a.ops else 0)
+    src_bytes = (W * H + 2 * cw * ch) if planar else W * H * 4
+    bytes_img = src_bytes + (W * H * 4 if "w" in a.ops else 0) + (nw * nh * 4 if "r" in a.ops else 0) + (160000 if "t" in a.ops else 0)
     out = {"images": n, "ops": a.ops, "batches": st["batches"], "launches": st["kernels_launched"],
            "stream_us_per_image": 1e3 * st["stream_kernel_ms"] / n, "fix_us_per_image": 1e3 * st["fix_kernel_ms"] / n,
            "other_us_per_image": 1e3 * st["other_kernel_ms"] / n, "fixups_per_image": st["exact_fixups"] / n,
