@@ -680,7 +680,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
             }
         } else {
             // planar YCbCr: the lean planar kernel takes every resample whose geometry streams in a cached form
-            const bool planar_ok = precision != IPG_PRECISION_REFERENCE && sv.layout >= L_YCBCR444 && sv.layout <= L_YCBCR440 &&
+            const bool planar_ok = precision != IPG_PRECISION_REFERENCE &&
+                                   ((sv.layout >= L_YCBCR444 && sv.layout <= L_YCBCR440) || sv.layout == L_GRAY8) &&
                                    ((((uintptr_t)sv.p0) | ((uintptr_t)sv.p1) | ((uintptr_t)sv.p2) | (uintptr_t)sv.s0 |
                                      (uintptr_t)sv.s1 | (uintptr_t)sv.s2) & 15) == 0;
             for (auto *op : res) {

@@ -1132,7 +1132,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
 
 // ---------------------------------------------------------------------------------
 // k_stream_planar: the lean streaming resample for planar YCbCr sources (*image.YCbCr,
-// 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0), one target per pass, local or wide per CTA.
+// 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0) and *image.Gray, one target per pass, local or wide per CTA.
 //
 // Same structure as k_stream<1,false,4>; what differs is the source: the producer lands the
 // Y row and the chroma rows that belong to each of the group's 4 luma rows (nearest chroma
@@ -1189,6 +1189,7 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
     const int layout = J.src.layout;
     const bool sub_x = layout == L_YCBCR422 || layout == L_YCBCR420; // chroma at half horizontal resolution
     const bool sub_y = layout == L_YCBCR420 || layout == L_YCBCR440; // ... vertical
+    const bool gray = layout == L_GRAY8;                              // *image.Gray: one plane, r = g = b = Y * 0x101
     const int ncols = min(J.slab_cols, W - cx0);
     const uint32_t y_bytes = (uint32_t)((ncols + 15) & ~15);
     const uint32_t c_bytes = (uint32_t)(((sub_x ? (ncols + 1) >> 1 : ncols) + 15) & ~15);
@@ -1239,10 +1240,11 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
             const int y0 = ys0 + group * STREAM_GROUP;
             const int nr = min(STREAM_GROUP, yend - y0);
             PlanarStage &st = sm.stage[stage];
-            mbar_arrive_expect_tx(&sm.full[stage], (y_bytes + 2 * c_bytes) * (uint32_t)nr + (uint32_t)sizeof(GroupRec));
+            mbar_arrive_expect_tx(&sm.full[stage], (y_bytes + (gray ? 0u : 2 * c_bytes)) * (uint32_t)nr + (uint32_t)sizeof(GroupRec));
             for (int k = 0; k < nr; k++) {
                 const int y = y0 + k, cy = sub_y ? y >> 1 : y;
                 tma_load_1d(&st.y[k][0], J.src.p0 + (size_t)y * J.src.s0 + cx0, y_bytes, &sm.full[stage]);
+                if (gray) continue;
                 tma_load_1d(&st.cb[k][0], J.src.p1 + (size_t)cy * J.src.s1 + ccx0, c_bytes, &sm.full[stage]);
                 tma_load_1d(&st.cr[k][0], J.src.p2 + (size_t)cy * J.src.s2 + ccx0, c_bytes, &sm.full[stage]);
             }
@@ -1281,8 +1283,9 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
         for (int k = 0; k < STREAM_GROUP; k++) {
             // ---- 4 pixels -> 16-bit RGB exactly as color.YCbCr.RGBA() (x/image scaleX_YCbCr*)
             const uint32_t y4 = *reinterpret_cast<const uint32_t *>(&stg.y[k][slot * 4]);
-            uint32_t cb4, cr4; // chroma byte of each of the 4 pixels
-            if (sub_x) {
+            uint32_t cb4 = 0x80808080u, cr4 = 0x80808080u; // chroma byte of each of the 4 pixels
+            if (gray) {
+            } else if (sub_x) {
                 const uint32_t b2 = *reinterpret_cast<const uint16_t *>(&stg.cb[k][slot * 2]);
                 const uint32_t r2 = *reinterpret_cast<const uint16_t *>(&stg.cr[k][slot * 2]);
                 cb4 = __byte_perm(b2, 0, 0x1100);
@@ -1300,6 +1303,7 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
                 uint32_t r = clamp16((yy1 + 91881 * cr1) >> 8);
                 uint32_t gg = clamp16((yy1 - 22554 * cb1 - 46802 * cr1) >> 8);
                 uint32_t b = clamp16((yy1 + 116130 * cb1) >> 8);
+                if (gray) r = gg = b = ((y4 >> (8 * j)) & 0xff) * 0x101u; // scaleX_Gray: y16 = Y * 0x101
                 if (two_stage) { // the 1:1 crop pass stored uint8(c16 >> 8); scaleX_RGBA re-expands it
                     r = (r >> 8) * 0x101u; gg = (gg >> 8) * 0x101u; b = (b >> 8) * 0x101u;
                 }

@@ -93,3 +93,17 @@ def test_ycbcr_12mp_streams_and_is_bit_exact(engines, oracle, layout):
     R = oracle.Raster.ycbcr(y, cb, cr, olay)
     assert np.array_equal(out[0], oracle.resize_image(R, 1024, 768))
     assert np.array_equal(out[1], oracle.crop_and_resize(R, 200))
+
+
+def test_gray_streams_and_is_bit_exact(engines, oracle):
+    w, h = 4001, 3003      # (the planar kernel takes scales whose outputs fit one lane each; milder ones fall back)
+    g = np.random.default_rng(5).integers(0, 256, (h, w), dtype=np.uint8)
+    e = engines(ip.PRECISION_EXACT, lane_device_bytes=2 << 30)
+    f0 = e.stats()["exact_fallbacks"]
+    nw, nh = ip.keep_aspect_dims(w, h, 1024, 768)
+    cx, cy, cs = ip.crop_square(w, h)
+    out = e.run(ip.Image.from_gray(g), [ip.OpSpec.resize(nw, nh), ip.OpSpec.thumb_crop((cx, cy, cs, cs), 200)])
+    assert e.stats()["exact_fallbacks"] == f0
+    R = oracle.Raster.gray(g)
+    assert np.array_equal(out[0], oracle.resize_image(R, nw, nh))
+    assert np.array_equal(out[1], oracle.crop_and_resize(R, 200))

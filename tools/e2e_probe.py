@@ -10,6 +10,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--ops", default="rtw"); ap.add_argument("--images", type=int, default=128)
 ap.add_argument("--slots", type=int, default=48); ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--lanes", type=int, default=4); ap.add_argument("--steps", type=int, default=3); ap.add_argument("--precision", type=int, default=0)
+ap.add_argument("--layout", default="rgba", choices=["rgba", "ycbcr420"])
 a = ap.parse_args()
 W, H = 4000, 3000
 eng = ip.Engine(devices=[0], precision=a.precision, lanes_per_device=a.lanes, max_batch=a.batch, batch_window_us=100)
@@ -25,9 +26,16 @@ rng = np.random.default_rng(0)
 base = rng.integers(0, 256, (H, W, 4), dtype=np.uint8); base[..., 3] = 255
 descs, opss, pins = [], [], []
 for s in range(a.slots):
-    pi = eng.alloc_pinned(W * H * 4); pi.array[:] = base.reshape(-1); pins.append(pi)
-    d = L.ImageDesc(); d.layout, d.memspace, d.width, d.height = L.RGBA8, L.MEM_HOST, W, H
-    d.plane[0] = pi.ptr; d.stride[0] = W * 4; descs.append(d)
+    d = L.ImageDesc(); d.memspace, d.width, d.height = L.MEM_HOST, W, H
+    if a.layout == "rgba":
+        pi = eng.alloc_pinned(W * H * 4); pi.array[:] = base.reshape(-1); pins.append(pi)
+        d.layout = L.RGBA8; d.plane[0] = pi.ptr; d.stride[0] = W * 4
+    else:  # what image.Decode returns for a 4:2:0 JPEG: three planes, 1.5 bytes per pixel over PCIe
+        d.layout = L.YCBCR420; d.opaque_hint = 1
+        for k, (pw, ph) in enumerate(((W, H), (W // 2, H // 2), (W // 2, H // 2))):
+            pi = eng.alloc_pinned(pw * ph); pi.array[:] = base.reshape(-1)[:pw * ph]; pins.append(pi)
+            d.plane[k] = pi.ptr; d.stride[k] = pw
+    descs.append(d)
     ops = (L.Op * 3)(); n = 0
     if "r" in a.ops:
         p = eng.alloc_pinned(nw * nh * 4); pins.append(p)
@@ -53,6 +61,6 @@ def step():
 step(); eng.reset_stats(); t0 = time.perf_counter()
 for _ in range(a.steps): step()
 eng.flush(); dt = time.perf_counter() - t0; st = eng.stats()
-print(json.dumps({"ops": a.ops, "batch": a.batch, "lanes": a.lanes, "slots": a.slots, "img_per_s": a.images * a.steps / dt,
+print(json.dumps({"layout": a.layout, "ops": a.ops, "batch": a.batch, "lanes": a.lanes, "slots": a.slots, "img_per_s": a.images * a.steps / dt,
                   "h2d_GBps": st["bytes_h2d"] / dt / 1e9, "d2h_GBps": st["bytes_d2h"] / dt / 1e9, "batches": st["batches"]}))
 eng.close()
