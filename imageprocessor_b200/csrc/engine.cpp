@@ -657,7 +657,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 const bool wm_tma_ok = !wm || ((sv.w % 4) == 0 && ((((uintptr_t)wm->dev_out) | (uintptr_t)wm->dev_pitch) & 15) == 0);
                 j.fast_path = 0;
                 if (wm_tma_ok && redo_flags && (size_t)ji < max_jobs) {
-                    if (geom->lean_ok) j.fast_path = (geom->t[0].local || c.merge_lean) ? 1 : 2;
+                    if (geom->lean_ok) j.fast_path = (c.merge_lean || geom->lean_regs_ok) ? 1 : 2;
                     else if (lean2 && geom->lean2_ok) j.fast_path = 3;
                 }
                 j.redo_flag = (j.fast_path && !t.src.opaque_hint) ? redo_flags + ji : nullptr;

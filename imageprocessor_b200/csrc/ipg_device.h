@@ -84,9 +84,10 @@ struct StreamTarget {
     const int32_t *tile_ox;      // [n_tiles+1] output columns owned by each column tile
     int32_t local;               // 1: narrow support, each V warp runs its own horizontal pass
     const int32_t *warp_ox;      // local: [n_tiles*4+1] output columns owned by each (tile, warp)
-    const int32_t *tile_parts;   // [n_tiles] horizontal-pass form of the tile, P | taps_per_thread << 8: P == 0 = generic loops; P >= 1 =
-                                 // "cached": every output is split over P adjacent V threads, each holding
-                                 // at most STREAM_XTAPS (local) / STREAM_XTAPS_TAB (wide) interleaved taps
+    const int32_t *tile_parts;   // [n_tiles] horizontal-pass form of the tile, P | taps_per_thread << 8 | rounds << 16:
+                                 // P == 0 = generic loops; P >= 1 = "cached": every output is split over P adjacent
+                                 // V threads holding taps_per_thread interleaved taps each, and a thread takes
+                                 // `rounds` outputs (taps_per_thread * rounds <= STREAM_XTAPS_TAB)
     const RowRec *rows;          // per-band records, concatenated
     const int32_t *band_rec_off; // [n_bands] first record of each band
     const int32_t *band_tend;    // [n_bands] one past the last source row that contributes
@@ -131,7 +132,7 @@ struct WatermarkD {
 #define IPG_CTAS_FAST2 3
 #endif
 #ifndef IPG_STAGES_FAST2
-#define IPG_STAGES_FAST2 4
+#define IPG_STAGES_FAST2 3
 #endif
 
 // k_stream CTA: 4 V warps + one producer warp (one elected lane drives the TMA ring: bulk
@@ -148,7 +149,8 @@ enum {
     STREAM_PTHREADS = 32,       // producer warp
     STREAM_CTA = STREAM_THREADS + STREAM_PTHREADS,
     STREAM_XTAPS = 8,           // local targets: taps per thread kept in registers
-    STREAM_XTAPS_TAB = 12,      // wide targets: taps per thread in the shared-memory table
+    STREAM_XTAPS_TAB = 16,      // shared-memory table: taps per thread, all rounds together
+    STREAM_XROUNDS = 4,         // ... and outputs per thread (rounds) in the table forms (mild downscales)
     STREAM_LOCAL_MAX_HALO = 16, // a target is local when its widest support - 1 fits this overlap
     STREAM_STAGES_2T = IPG_STAGES_2T, STREAM_CTAS_2T = IPG_CTAS_2T,   // ring depth / CTAs per SM, two-target instantiation
     STREAM_STAGES_1T = IPG_STAGES_1T, STREAM_CTAS_1T = IPG_CTAS_1T,   // ... otherwise

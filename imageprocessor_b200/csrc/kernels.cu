@@ -438,9 +438,9 @@ struct __align__(16) StreamStage {
 // e0, e0 + P, e0 + 2P, ...  Lives in shared memory, not registers: the emit code exists
 // once for all targets and the accumulators keep the register file.
 template <int NT> struct XTab {
-    int32_t ox[NT][STREAM_THREADS];              // output column, or -1 when the thread has none
-    int32_t e0[NT][STREAM_THREADS];              // element of xbuf[T] holding its first tap
-    float w[NT][STREAM_XTAPS_TAB][STREAM_THREADS]; // its weights, 0 past the end
+    int32_t ox[NT][STREAM_XROUNDS][STREAM_THREADS]; // output column of each round, or -1 when the thread has none
+    int32_t e0[NT][STREAM_XROUNDS][STREAM_THREADS]; // element of xbuf[T] holding its first tap
+    float w[NT][STREAM_XTAPS_TAB][STREAM_THREADS];  // its weights (round r: entries r * ntap ...), 0 past the end
 };
 template <> struct XTab<0> {};
 
@@ -455,7 +455,7 @@ struct XInfo {
     uint8_t *dst;
     int32_t dst_stride, exact_job;
     uint32_t D;
-    int32_t local, parts, ntap;  // parts = threads per output (0: generic form), ntap = taps per thread
+    int32_t local, parts, ntap, rounds; // parts = threads per output (0: generic form), ntap = taps per thread and round
 };
 
 template <int NT, int STAGES> struct __align__(128) StreamSmem {
@@ -509,6 +509,76 @@ __device__ __forceinline__ void xgather(const float *__restrict__ wp, int e0, in
     }
 }
 
+// This thread's entries of target T's cached-form table for the CTA's tile (all rounds).  pv is the tile's
+// tile_parts word; a tile without outputs (P == 0) gets an empty one-round table.
+template <typename XT>
+__device__ __forceinline__ void xtab_fill(XT &xt, XInfo &xi, int T, const StreamTarget &t, int tile, int cx0, int ws, int tid,
+                                          int pv)
+{
+    const int warp = tid >> 5, lane = tid & 31;
+    const int P0 = pv & 255, P = max(P0, 1), ntap = P0 ? (pv >> 8) & 255 : 0, R = P0 ? pv >> 16 : 1;
+    if (tid == 0) xi = XInfo{t.dst, t.dst_stride, t.exact_job, (uint32_t)t.fix_d, t.local, P, ntap, R};
+    const int part = tid & (P - 1);
+#pragma unroll
+    for (int r = 0; r < STREAM_XROUNDS; r++) {
+        int ox = -1, e0 = 0, k0 = 0, n = 0;
+        if (P0 > 0 && r < R) {
+            if (t.local) { // P adjacent lanes per output of the owning warp; strip w sits at elements [128 w, 128 w + 128)
+                const int ox0 = __ldg(t.warp_ox + tile * 4 + warp);
+                const int j = lane / P + r * (32 / P);
+                if (j < __ldg(t.warp_ox + tile * 4 + warp + 1) - ox0) ox = ox0 + j;
+                if (ox >= 0) e0 = __ldg(t.xfirst + ox) + t.rect_x - cx0 + warp * (STREAM_WARP_COLS - ws) + part;
+            } else {       // P adjacent threads per output of the tile
+                const int ox0 = __ldg(t.tile_ox + tile);
+                const int j = tid / P + r * (STREAM_THREADS / P);
+                if (j < __ldg(t.tile_ox + tile + 1) - ox0) ox = ox0 + j;
+                if (ox >= 0) e0 = __ldg(t.xfirst + ox) + t.rect_x - cx0 + part;
+            }
+        }
+        if (ox >= 0) {
+            k0 = __ldg(t.xoff + ox);
+            n = __ldg(t.xoff + ox + 1) - k0;
+        }
+        xt.ox[T][r][tid] = ox;
+        xt.e0[T][r][tid] = e0;
+        if (r < R) // rounds past R have no table entries (R * ntap <= STREAM_XTAPS_TAB is what the planner guarantees)
+            for (int k = 0; k < ntap; k++)
+                xt.w[T][r * ntap + k][tid] = (ox >= 0 && part + k * P < n) ? __ldg(t.xw + k0 + part + k * P) : 0.f;
+    }
+}
+
+// The cached horizontal pass over the row parked in xbuf[T]: every round of this thread.  All V threads
+// of the unit (warp if local, CTA if not) call it together: the butterfly shuffles are warp-wide.
+template <typename SM>
+__device__ __forceinline__ void xcached(SM &sm, int T, int oy, int tid, const FixList &fix)
+{
+    const XInfo xi = sm.xi[T];
+    const int P = xi.parts, ntap = xi.ntap;
+    const float4 *buf = sm.xbuf[T];
+    for (int r = 0; r < xi.rounds; r++) {
+        const int ox = sm.xt.ox[T][r][tid];
+        const int e0 = sm.xt.e0[T][r][tid];
+        float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
+        if (ox >= 0) {
+#pragma unroll 4
+            for (int k = 0; k < ntap; k++) { // weight 0 past the end adds exactly nothing (the buffer is padded and finite)
+                const float w = sm.xt.w[T][r * ntap + k][tid];
+                const float4 q = buf[swz(e0 + k * P)];
+                const float2 ww = make_float2(w, w);
+                rg = __ffma2_rn(make_float2(q.x, q.y), ww, rg);
+                ba = __ffma2_rn(make_float2(q.z, q.w), ww, ba);
+            }
+        }
+        for (int off = 1; off < P; off <<= 1) { // butterfly over the P threads of an output (P divides 32)
+            rg.x += __shfl_xor_sync(0xffffffffu, rg.x, off);
+            rg.y += __shfl_xor_sync(0xffffffffu, rg.y, off);
+            ba.x += __shfl_xor_sync(0xffffffffu, ba.x, off);
+            ba.y += __shfl_xor_sync(0xffffffffu, ba.y, off);
+        }
+        if (ox >= 0 && (tid & (P - 1)) == 0) xfinish(xi, xi.D, ox, oy, rg, ba, fix);
+    }
+}
+
 // Horizontal pass of the row the V warps just parked for target T (runtime value: this
 // code exists once).  Local target: warp-private, one __syncwarp on each side.  Shared
 // target: all 128 V threads, one named barrier on each side.
@@ -522,28 +592,7 @@ __device__ __noinline__ void xpass(const StreamJob &J, SM &sm, int T, int oy, in
     const float4 *buf = sm.xbuf[T];
     if (local) __syncwarp(); else vwarps_bar(); // the row is parked
     if (P > 0) {
-        // cached form: this thread's taps and weights come from the shared-memory table
-        const int ox = sm.xt.ox[T][vtid];
-        const int e0 = sm.xt.e0[T][vtid];
-        float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
-        if (ox >= 0) {
-            const int ntap = xi.ntap;
-#pragma unroll 4
-            for (int k = 0; k < ntap; k++) { // weight 0 past the end adds exactly nothing (the buffer is padded and finite)
-                const float w = sm.xt.w[T][k][vtid];
-                const float4 q = buf[swz(e0 + k * P)];
-                const float2 ww = make_float2(w, w);
-                rg = __ffma2_rn(make_float2(q.x, q.y), ww, rg);
-                ba = __ffma2_rn(make_float2(q.z, q.w), ww, ba);
-            }
-        }
-        for (int off = 1; off < P; off <<= 1) { // butterfly over the P threads of an output (P divides 32)
-            rg.x += __shfl_xor_sync(0xffffffffu, rg.x, off);
-            rg.y += __shfl_xor_sync(0xffffffffu, rg.y, off);
-            ba.x += __shfl_xor_sync(0xffffffffu, ba.x, off);
-            ba.y += __shfl_xor_sync(0xffffffffu, ba.y, off);
-        }
-        if (ox >= 0 && (vtid & (P - 1)) == 0) xfinish(xi, xi.D, ox, oy, rg, ba, fix);
+        xcached(sm, T, oy, vtid, fix); // cached form: taps and weights from the shared-memory table
     } else {
         const StreamTarget &t = J.t[T];
         int ox0, n_own, ebase = t.rect_x - cx0, j0 = vtid, step = STREAM_THREADS;
@@ -687,31 +736,11 @@ __device__ __forceinline__ void v_rows_fast(VAcc<false> &S, const StreamJob &J, 
                 }
                 if (C.x0_ox >= 0 && (threadIdx.x & (C.x0_parts - 1)) == 0) xfinish(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
                 __syncwarp(); // the strip is reused by the next emit
-            } else if constexpr (LEAN == 4) { // wide target, inline (no call: the accumulators stay in registers)
-                vwarps_bar(); // all four warps have parked
-                const int tid = (int)threadIdx.x;
-                const int ox = sm.xt.ox[0][tid], e0 = sm.xt.e0[0][tid];
-                const int P = sm.xi[0].parts, ntap = sm.xi[0].ntap;
-                const float4 *buf = sm.xbuf[0];
-                float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
-                if (ox >= 0) {
-#pragma unroll 4
-                    for (int q = 0; q < ntap; q++) {
-                        const float w = sm.xt.w[0][q][tid];
-                        const float4 v = buf[swz(e0 + q * P)];
-                        const float2 ww = make_float2(w, w);
-                        rg = __ffma2_rn(make_float2(v.x, v.y), ww, rg);
-                        ba = __ffma2_rn(make_float2(v.z, v.w), ww, ba);
-                    }
-                }
-                for (int off = 1; off < P; off <<= 1) {
-                    rg.x += __shfl_xor_sync(0xffffffffu, rg.x, off);
-                    rg.y += __shfl_xor_sync(0xffffffffu, rg.y, off);
-                    ba.x += __shfl_xor_sync(0xffffffffu, ba.x, off);
-                    ba.y += __shfl_xor_sync(0xffffffffu, ba.y, off);
-                }
-                if (ox >= 0 && (tid & (P - 1)) == 0) xfinish(sm.xi[0], sm.xi[0].D, ox, e >> 1, rg, ba, fix);
-                vwarps_bar(); // the row buffer is reused by the next emit
+            } else if constexpr (LEAN == 4) { // table forms, inline (no call: the accumulators stay in registers):
+                const bool loc = sm.xi[0].local != 0; // a wide target, or a local one with several outputs per lane
+                if (loc) __syncwarp(); else vwarps_bar();
+                xcached(sm, 0, e >> 1, (int)threadIdx.x, fix);
+                if (loc) __syncwarp(); else vwarps_bar(); // the row buffer is reused by the next emit
             } else {           // wide support (the thumbnail): CTA-wide split pass, once per ~15 rows
                 xpass<1>(J, sm, 0, e >> 1, C.tile, C.cx0, C.vtid, fix);
             }
@@ -949,38 +978,12 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
             for (int T = 0; T < NT; T++) {
                 if (T >= J.n_targets) continue;
                 const StreamTarget &t = J.t[T];
-                const int pv = __ldg(t.tile_parts + tile), P = pv & 255;
-                if (tid == 0) sm.xi[T] = XInfo{t.dst, t.dst_stride, t.exact_job, (uint32_t)t.fix_d, t.local, P, pv >> 8};
                 for (int e = tid; e < STREAM_XBUF; e += STREAM_THREADS) sm.xbuf[T][e] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (FAST && P == 0) { // a tile without outputs: lanes gather zeros and store nothing
-                    if (tid == 0) sm.xi[T].parts = 1;
-                    sm.xt.ox[T][tid] = -1;
-                    sm.xt.e0[T][tid] = 0;
-#pragma unroll
-                    for (int k = 0; k < STREAM_XTAPS_TAB; k++) sm.xt.w[T][k][tid] = 0.f;
-                }
-                if (P == 0) continue;
-                int ox = -1, e0 = 0, k0 = 0, n = 0, part = 0;
-                if (t.local) { // P adjacent lanes per output of the owning warp; strip w sits at elements [128 w, 128 w + 128)
-                    const int ox0 = __ldg(t.warp_ox + tile * 4 + warp);
-                    part = tid & (P - 1);
-                    if ((tid & 31) / P < __ldg(t.warp_ox + tile * 4 + warp + 1) - ox0) ox = ox0 + (tid & 31) / P;
-                    if (ox >= 0) e0 = __ldg(t.xfirst + ox) + t.rect_x - cx0 + warp * (STREAM_WARP_COLS - ws) + part;
-                } else {       // P adjacent threads per output of the tile
-                    const int ox0 = __ldg(t.tile_ox + tile);
-                    part = tid & (P - 1);
-                    if (tid / P < __ldg(t.tile_ox + tile + 1) - ox0) ox = ox0 + tid / P;
-                    if (ox >= 0) e0 = __ldg(t.xfirst + ox) + t.rect_x - cx0 + part;
-                }
-                if (ox >= 0) {
-                    k0 = __ldg(t.xoff + ox);
-                    n = __ldg(t.xoff + ox + 1) - k0;
-                }
-                sm.xt.ox[T][tid] = ox;
-                sm.xt.e0[T][tid] = e0;
-#pragma unroll
-                for (int k = 0; k < STREAM_XTAPS_TAB; k++)
-                    sm.xt.w[T][k][tid] = (ox >= 0 && part + k * P < n) ? __ldg(t.xw + k0 + part + k * P) : 0.f;
+                const int pv = __ldg(t.tile_parts + tile);
+                // the lean kernels always run the table form (a tile without outputs gets an empty table);
+                // the general one keeps its generic loops when the tile has no cached form
+                if (FAST || (pv & 255)) xtab_fill(sm.xt, sm.xi[T], T, t, tile, cx0, ws, tid, pv);
+                else if (tid == 0) sm.xi[T] = XInfo{t.dst, t.dst_stride, t.exact_job, (uint32_t)t.fix_d, t.local, 0, 0, 1};
             }
         }
     }
@@ -1049,13 +1052,14 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
 #pragma unroll
     for (int k = 0; k < STREAM_XTAPS; k++) C.x0_w[k] = 0.f;
     if constexpr (NT > 0) {
-        if (LEAN == 1 || LEAN == 3 || (LEAN == 4 && sm.xi[0].local) || (!FAST && C.act[0] && sm.xi[0].local && sm.xi[0].parts >= 1)) {
+        if (LEAN == 1 || LEAN == 3 || (LEAN == 4 && sm.xi[0].local && sm.xi[0].rounds == 1) ||
+            (!FAST && C.act[0] && sm.xi[0].local && sm.xi[0].parts >= 1 && sm.xi[0].rounds == 1)) {
             C.x0_inline = true;
             C.x0_parts = sm.xi[0].parts;
-            C.x0_ox = sm.xt.ox[0][tid];
-            C.x0_e0 = sm.xt.e0[0][tid];
+            C.x0_ox = sm.xt.ox[0][0][tid];
+            C.x0_e0 = sm.xt.e0[0][0][tid];
 #pragma unroll
-            for (int k = 0; k < STREAM_XTAPS; k++) C.x0_w[k] = sm.xt.w[0][k][tid];
+            for (int k = 0; k < STREAM_XTAPS; k++) C.x0_w[k] = k < sm.xi[0].ntap ? sm.xt.w[0][k][tid] : 0.f; // the table holds ntap entries
         }
     }
     // fallback watermark copy by the V warps when the rows are not 16-byte granular
@@ -1203,31 +1207,8 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
     }
     // horizontal-pass table (cached form; the engine only sends jobs whose tiles have one)
     if (tid < STREAM_THREADS) {
-        const StreamTarget &t = J.t[0];
-        const int pv = __ldg(t.tile_parts + tile), P0 = pv & 255, P = max(P0, 1);
-        if (tid == 0) sm.xi[0] = XInfo{t.dst, t.dst_stride, t.exact_job, (uint32_t)t.fix_d, t.local, P, P0 ? pv >> 8 : 0};
         for (int e = tid; e < STREAM_XBUF; e += STREAM_THREADS) sm.xbuf[0][e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int ox = -1, e0 = 0, k0 = 0, n = 0, part = tid & (P - 1);
-        if (P0 > 0) {
-            if (t.local) {
-                const int ox0 = __ldg(t.warp_ox + tile * 4 + warp);
-                if ((tid & 31) / P < __ldg(t.warp_ox + tile * 4 + warp + 1) - ox0) ox = ox0 + (tid & 31) / P;
-                if (ox >= 0) e0 = __ldg(t.xfirst + ox) + t.rect_x - cx0 + warp * (STREAM_WARP_COLS - ws) + part;
-            } else {
-                const int ox0 = __ldg(t.tile_ox + tile);
-                if (tid / P < __ldg(t.tile_ox + tile + 1) - ox0) ox = ox0 + tid / P;
-                if (ox >= 0) e0 = __ldg(t.xfirst + ox) + t.rect_x - cx0 + part;
-            }
-        }
-        if (ox >= 0) {
-            k0 = __ldg(t.xoff + ox);
-            n = __ldg(t.xoff + ox + 1) - k0;
-        }
-        sm.xt.ox[0][tid] = ox;
-        sm.xt.e0[0][tid] = e0;
-#pragma unroll
-        for (int k = 0; k < STREAM_XTAPS_TAB; k++)
-            sm.xt.w[0][k][tid] = (ox >= 0 && part + k * P < n) ? __ldg(t.xw + k0 + part + k * P) : 0.f;
+        xtab_fill(sm.xt, sm.xi[0], 0, J.t[0], tile, cx0, ws, tid, __ldg(J.t[0].tile_parts + tile));
     }
     __syncthreads();
 
@@ -1272,8 +1253,6 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
     const bool local = sm.xi[0].local != 0;
     const bool two_stage = J.t[0].two_stage != 0;
     const int pslot = local ? tid : slot;
-    const int P = sm.xi[0].parts, ntap = sm.xi[0].ntap;
-    const int x_ox = sm.xt.ox[0][tid], x_e0 = sm.xt.e0[0][tid];
     int rs = 0;
     uint32_t rph = 0;
     for (int g = 0; g < ngroups; g++) {
@@ -1324,25 +1303,7 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
                 if (e & 1) park_row<1, false>(S, r.w, sm.xbuf[0], pslot);
                 else       park_row<0, false>(S, r.z, sm.xbuf[0], pslot);
                 if (local) __syncwarp(); else vwarps_bar();
-                const float4 *buf = sm.xbuf[0];
-                float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
-                if (x_ox >= 0) {
-#pragma unroll 4
-                    for (int q = 0; q < ntap; q++) {
-                        const float w = sm.xt.w[0][q][tid];
-                        const float4 v = buf[swz(x_e0 + q * P)];
-                        const float2 ww = make_float2(w, w);
-                        rg = __ffma2_rn(make_float2(v.x, v.y), ww, rg);
-                        ba = __ffma2_rn(make_float2(v.z, v.w), ww, ba);
-                    }
-                }
-                for (int off = 1; off < P; off <<= 1) {
-                    rg.x += __shfl_xor_sync(0xffffffffu, rg.x, off);
-                    rg.y += __shfl_xor_sync(0xffffffffu, rg.y, off);
-                    ba.x += __shfl_xor_sync(0xffffffffu, ba.x, off);
-                    ba.y += __shfl_xor_sync(0xffffffffu, ba.y, off);
-                }
-                if (x_ox >= 0 && (tid & (P - 1)) == 0) xfinish(sm.xi[0], sm.xi[0].D, x_ox, e >> 1, rg, ba, fix);
+                xcached(sm, 0, e >> 1, tid, fix);
                 if (local) __syncwarp(); else vwarps_bar();
             }
         }
@@ -1367,6 +1328,12 @@ cudaError_t launch_stream_planar(const StreamJob *jobs, const StreamItem *items,
 }
 
 int stream_smem_bytes() { return (int)sizeof(StreamCfg<2>::Smem); }
+// shared memory must not be what limits the residency the launch bounds ask for (227 KB per SM, 1 KB per CTA reserved)
+static_assert(sizeof(StreamCfg<1, 4>::Smem) + 1024 <= 227 * 1024 / STREAM_CTAS_FAST, "lean k_stream: shared memory limits occupancy");
+static_assert(sizeof(StreamCfg<1, 0>::Smem) + 1024 <= 227 * 1024 / STREAM_CTAS_1T, "k_stream<1>: shared memory limits occupancy");
+static_assert(sizeof(StreamCfg<2, 0>::Smem) + 1024 <= 227 * 1024 / STREAM_CTAS_2T, "k_stream<2>: shared memory limits occupancy");
+static_assert(sizeof(StreamCfg<2, 3>::Smem) + 1024 <= 227 * 1024 / STREAM_CTAS_FAST2, "lean fused k_stream: shared memory limits occupancy");
+static_assert(sizeof(PlanarSmem<PLANAR_STAGES>) + 1024 <= 227 * 1024 / PLANAR_CTAS, "k_stream_planar: shared memory limits occupancy");
 
 template <int NT, bool WM, int LEAN>
 static cudaError_t launch_stream_t(const StreamJob *jobs, const StreamItem *items, int n, FixList fix, cudaStream_t st)

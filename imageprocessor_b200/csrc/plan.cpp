@@ -149,18 +149,21 @@ static bool build_target(StreamGeom &g, int ti, const StreamTargetSpec &s, doubl
         int32_t maxn = 0;
         for (int32_t ox = o0; ox < o1; ox++) maxn = std::max(maxn, ax.off[ox + 1] - ax.off[ox]);
         if (o1 == o0) continue;
-        if (t.local) { // P adjacent lanes of the owning warp per output
-            int32_t maxw = 0;
+        // cheapest (rounds, P) whose table fits: P threads per output, `rounds` outputs per thread
+        const int32_t units = t.local ? 32 : STREAM_THREADS;
+        int32_t maxo = o1 - o0;
+        if (t.local) {
+            maxo = 0;
             for (int32_t w = 0; w < 4; w++)
-                maxw = std::max(maxw, t.warp_ox[(size_t)tile * 4 + w + 1] - t.warp_ox[(size_t)tile * 4 + w]);
-            for (int32_t P = 1; P <= 4; P <<= 1) {
-                if (maxw * P > 32) break;
-                if ((maxn + P - 1) / P <= STREAM_XTAPS) { t.tile_parts[tile] = P | (((maxn + P - 1) / P) << 8); break; }
-            }
-        } else {       // P adjacent threads of the CTA per output
-            for (int32_t P = 1; P <= 32; P <<= 1) {
-                if ((o1 - o0) * P > STREAM_THREADS) break;
-                if ((maxn + P - 1) / P <= STREAM_XTAPS_TAB) { t.tile_parts[tile] = P | (((maxn + P - 1) / P) << 8); break; }
+                maxo = std::max(maxo, t.warp_ox[(size_t)tile * 4 + w + 1] - t.warp_ox[(size_t)tile * 4 + w]);
+        }
+        for (int32_t R = 1; R <= STREAM_XROUNDS && !t.tile_parts[tile]; R++) {
+            for (int32_t P = 1; P <= (t.local ? 4 : 32); P <<= 1) {
+                if (maxo * P > units * R) break;
+                const int32_t ntap = (maxn + P - 1) / P;
+                if (ntap * R > STREAM_XTAPS_TAB || (t.local && R == 1 && ntap > STREAM_XTAPS)) continue;
+                t.tile_parts[tile] = P | (ntap << 8) | (R << 16);
+                break;
             }
         }
     }
@@ -305,7 +308,12 @@ static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const Stream
     g->lean2_ok = n_targets == 2 && g->t[0].local && !g->t[1].local;
     for (int i = 0; i < 2 && g->lean2_ok; i++)
         for (int tile = 0; tile < g->n_tiles && g->lean2_ok; tile++)
-            if (g->t[i].tile_ox[tile + 1] > g->t[i].tile_ox[tile] && (g->t[i].tile_parts[tile] & 255) < 1) g->lean2_ok = false;
+            if (g->t[i].tile_ox[tile + 1] > g->t[i].tile_ox[tile] &&
+                ((g->t[i].tile_parts[tile] & 255) < 1 || (i == 0 && (g->t[i].tile_parts[tile] >> 16) != 1)))
+                g->lean2_ok = false; // the fused kernel keeps target 0's taps in registers: one output per lane group
+    g->lean_regs_ok = n_targets == 1 && g->t[0].local;
+    for (int tile = 0; tile < g->n_tiles && g->lean_regs_ok; tile++)
+        if (g->t[0].tile_ox[tile + 1] > g->t[0].tile_ox[tile] && (g->t[0].tile_parts[tile] >> 16) != 1) g->lean_regs_ok = false;
     g->lean_ok = n_targets == 1;
     for (int tile = 0; tile < g->n_tiles && g->lean_ok; tile++)
         if (g->t[0].tile_ox[tile + 1] > g->t[0].tile_ox[tile] && (g->t[0].tile_parts[tile] & 255) < 1) g->lean_ok = false;

@@ -63,6 +63,7 @@ struct StreamGeom {
     std::vector<int32_t> band_grec_off; // [n_bands] first group of each band
     std::vector<StreamItem> items;  // (tile, band) pairs that have work; job index left 0
     bool lean2_ok = false;          // two targets, [0] local and [1] wide, both in cached forms: the lean fused instantiation
+    bool lean_regs_ok = false;      // ... and local with one output per lane group everywhere (taps in registers)
     bool lean_ok = false;           // one target, every tile with outputs in a cached horizontal-pass form:
                                     // the lean k_stream instantiation can run it (given opaque pixels)
 };

@@ -95,8 +95,8 @@ def test_ycbcr_12mp_streams_and_is_bit_exact(engines, oracle, layout):
     assert np.array_equal(out[1], oracle.crop_and_resize(R, 200))
 
 
-def test_gray_streams_and_is_bit_exact(engines, oracle):
-    w, h = 4001, 3003      # (the planar kernel takes scales whose outputs fit one lane each; milder ones fall back)
+@pytest.mark.parametrize("w,h", [(4001, 3003), (3001, 2003), (1920, 1080)])
+def test_gray_streams_and_is_bit_exact(engines, oracle, w, h):
     g = np.random.default_rng(5).integers(0, 256, (h, w), dtype=np.uint8)
     e = engines(ip.PRECISION_EXACT, lane_device_bytes=2 << 30)
     f0 = e.stats()["exact_fallbacks"]

@@ -205,3 +205,51 @@ def test_mixed_size_stream(engines, oracle):
             assert np.array_equal(out[0], oracle.resize_image(R, nw, nh)), f"resize {w}x{h} -> {nw}x{nh}"
         assert np.array_equal(out[1], oracle.crop_and_resize(R, 200)), f"thumb {w}x{h}"
         assert np.array_equal(out[2], oracle.watermark(R, col, [oracle.Glyph(*g) for g in gl])), f"watermark {w}x{h}"
+
+
+def test_concurrent_submitters_and_timeouts(engines, oracle):
+    """WORKER_CONCURRENCY goroutines call Process at once (worker.go:90-96): 8 threads submit and wait on one
+    context concurrently; every result is right, tickets are single-use, a zero timeout reports IPG_ERR_TIMEOUT
+    and leaves the ticket valid."""
+    import threading
+    e = engines(ip.PRECISION_EXACT)
+    errors, lock = [], threading.Lock()
+
+    def worker(k):
+        try:
+            rng = np.random.default_rng(400 + k)
+            for it in range(6):
+                w, h = int(rng.integers(200, 1500)), int(rng.integers(200, 1100))
+                a = rgba_random(w, h, 1000 * k + it, ["opaque", "premul"][it % 2])
+                ops, (nw, nh) = _ops_resize_thumb(w, h, 512, 384, 64)
+                t = e.submit(ip.Image.from_rgba(a), ops)
+                out = e.wait(t)
+                R = oracle.Raster.rgba(a)
+                ok = np.array_equal(out[0], oracle.resize_image(R, nw, nh)) and np.array_equal(out[1], oracle.crop_and_resize(R, 64))
+                if not ok:
+                    raise AssertionError(f"thread {k} image {it} ({w}x{h}) differs")
+        except Exception as ex:  # noqa: BLE001
+            with lock:
+                errors.append(repr(ex))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    # ticket semantics
+    a = rgba_random(3000, 2000, 9)
+    t = e.submit(ip.Image.from_rgba(a), [ip.OpSpec.resize(750, 500)])
+    try:
+        e.wait(t, timeout_ms=0)          # may or may not have finished yet
+        finished_early = True
+    except ip.IpgError as ex:
+        assert ex.code == ip._lib.ERR_TIMEOUT
+        finished_early = False
+    if not finished_early:
+        out = e.wait(t)                  # still valid after the timeout
+        assert np.array_equal(out[0], oracle.resize_image(oracle.Raster.rgba(a), 750, 500))
+    with pytest.raises(ip.IpgError) as ei:
+        e.wait(t)                        # consumed
+    assert ei.value.code == ip._lib.ERR_INVALID
