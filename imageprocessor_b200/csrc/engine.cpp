@@ -243,7 +243,7 @@ struct Lane {
     size_t arena_bytes = 0;
     uint8_t *param_host = nullptr; // pinned
     size_t param_cap = 0;
-    uint32_t *fix_count_host = nullptr; // pinned, 1 word
+    uint32_t *fix_count_host = nullptr; // pinned copy of FixList::count (4 words)
     bool busy = false;
 };
 
@@ -762,7 +762,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
         fix.count = (uint32_t *)cnt;
         fix.entries = (FixEntry *)ent;
         fix.capacity = (uint32_t)cap;
-        IPG_CU(cudaMemsetAsync(cnt, 0, 4, st));
+        IPG_CU(cudaMemsetAsync(cnt, 0, 16, st)); // FixList::count: append counter, re-queue counter, two work cursors
         B.has_fix = true;
     }
 
@@ -843,7 +843,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     IPG_CU(cudaEventRecord(L.ev[1], st));
     if (!fixjobs.empty()) {
         IPG_CU(launch_exact_fix(d_fixjobs, (int)fixjobs.size(), fix, st));
-        B.n_kernels++;
+        B.n_kernels += 2; // k_exact_fix + k_exact_fix_wide
     }
     IPG_CU(cudaEventRecord(L.ev[2], st));
     if (!xitems.empty()) {
@@ -863,7 +863,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
 
     // ---- read back
     IPG_CU(cudaStreamWaitEvent(down, L.ev[3], 0));
-    if (B.has_fix) IPG_CU(cudaMemcpyAsync(L.fix_count_host, fix.count, 4, cudaMemcpyDeviceToHost, down));
+    if (B.has_fix) IPG_CU(cudaMemcpyAsync(L.fix_count_host, fix.count, 16, cudaMemcpyDeviceToHost, down));
     for (auto &r : readbacks) {
         if (r.pitch == r.hstride)
             IPG_CU(cudaMemcpyAsync(r.host, r.dev, r.pitch * (size_t)(r.rows - 1) + r.row_bytes, cudaMemcpyDeviceToHost, down));
@@ -997,7 +997,7 @@ static void completer_main(Ctx *c, Device *d)
                 d->b_first = std::min(d->b_first, (double)t0);
                 d->b_last = std::max(d->b_last, (double)t3);
             }
-            if (B->has_fix && status == IPG_OK) c->s_fix += *L.fix_count_host;
+            if (B->has_fix && status == IPG_OK) c->s_fix += L.fix_count_host[0];
             c->s_batches++;
             c->s_kernels += (uint64_t)B->n_kernels;
             c->s_h2d += B->h2d;

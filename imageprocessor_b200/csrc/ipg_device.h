@@ -41,11 +41,15 @@ struct ExactJob {
 
 struct ExactItem { int32_t job; int32_t tile_x, tile_y; int32_t pad; };
 
-// Output pixel flagged by a stream kernel for fp64 re-evaluation.
+// Output pixel flagged by a stream kernel for fp64 re-evaluation.  k_exact_fix gives a narrow-support
+// pixel to one lane and re-queues the wide-support ones at the unused back end of the list for
+// k_exact_fix_wide (a whole warp each).
 struct FixEntry { int32_t job; int32_t x, y; };
 struct FixList {
     FixEntry *entries;
-    uint32_t *count;     // device counter (entries appended, may exceed capacity)
+    uint32_t *count;     // device counters, 4 words, zeroed per batch: [0] entries appended by the stream kernels
+                         // (may exceed capacity: then every target is redone whole); [2] wide entries re-queued
+                         // from the back; [1], [3] the fix kernels' work cursors
     uint32_t capacity;
 };
 

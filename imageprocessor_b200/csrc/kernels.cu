@@ -145,54 +145,253 @@ k_exact_tiles(const ExactJob *__restrict__ jobs, const ExactItem *__restrict__ i
     *(uchar4 *)(J.dst + (size_t)oy * J.dst_stride + (size_t)ox * 4) = o;
 }
 
-// Warp-cooperative variant for the fix-up list: lanes take the contributing source
-// rows round-robin and run their horizontal sums (each sum still sequential, unfused,
-// in tap order); lanes 0..3 then run the vertical sum of one channel each in row
-// order.  Same operations in the same order per value as exact_pixel, ~30x less
-// latency for the 29x29-tap thumbnail pixels.
-enum { FIX_THREADS = 128, FIX_MAX_ROWS = 96 };
+// The fix-up list.  A flagged pixel costs ny x nx source samples (8 x 8 for the 4:1 resize, 29 x 29 for
+// the 15:1 thumbnail) behind a chain of dependent global loads (entry -> job -> tap offsets -> weights
+// and samples): walked naively it is pure latency.  So a warp takes 32 entries at a time:
+//   header   everything the pixel needs from the entry, the job and the two axis tables;
+//   narrow   supports up to 17 x 17: 32 entries per warp, one per lane -- their dependent header loads
+//            overlap -- each finished by its own lane (exact_pixel_thread, k_exact_fix);
+//   wide     queued by k_exact_fix, one pixel per warp in k_exact_fix_wide: the header is broadcast; ALL lanes stage the
+//            two weight runs and the ny x nx block of 16-bit samples in shared memory (the loads of a
+//            pixel are in flight together; rows in chunks if the block is large); then lanes take the
+//            staged rows and run their horizontal sums (each sum sequential, unfused, in tap order)
+//            and lanes 0..3 run the vertical sum of one channel each in row order.
+// Same operations in the same order per value as exact_pixel.
+enum { FIX_THREADS = 128, FIX_MAX_ROWS = 64, FIX_MAX_TAPS = 64, FIX_STAGE_PX = 1024, FIX_MLP = 16 };
 
-__device__ void exact_pixel_warp(const ExactJob &J, int ox, int oy, double (*tmp)[4])
+struct FixWarpSmem {
+    uint2 px[FIX_STAGE_PX];      // staged samples: (r16 | g16 << 16, b16 | a16 << 16)
+    double tmp[FIX_MAX_ROWS][4]; // horizontally filtered rows
+    double wx[FIX_MAX_TAPS];
+    double wy[FIX_MAX_ROWS];
+};
+
+struct FixHdr {
+    SrcView src;
+    const double *wx, *wy;  // first weight of the pixel's taps on each axis
+    uint8_t *dst;           // the pixel's 4 bytes
+    double ifx, iy;
+    int32_t x0, y0, nx, ny; // first tap (absolute source coordinates) and tap counts
+    int32_t two_stage, job, ox, oy;
+};
+
+template <typename T> __device__ __forceinline__ T warp_bcast(const T &v, int src_lane)
+{
+    static_assert(sizeof(T) % 4 == 0, "word-sized POD");
+    T r;
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(&v);
+    uint32_t *out = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 4); i++) out[i] = __shfl_sync(0xffffffffu, in[i], src_lane);
+    return r;
+}
+
+__device__ __forceinline__ FixHdr fix_header(const ExactJob *__restrict__ jobs, const FixEntry e)
+{
+    const ExactJob &J = jobs[e.job];
+    FixHdr h;
+    h.src = J.src;
+    const int kx0 = __ldg(J.ax.off + e.x), ky0 = __ldg(J.ay.off + e.y);
+    h.nx = __ldg(J.ax.off + e.x + 1) - kx0;
+    h.ny = __ldg(J.ay.off + e.y + 1) - ky0;
+    h.x0 = __ldg(J.ax.first + e.x) + J.rect_x;
+    h.y0 = __ldg(J.ay.first + e.y) + J.rect_y;
+    h.ifx = __ldg(J.ax.inv_ffff + e.x);
+    h.iy = __ldg(J.ay.inv + e.y);
+    h.wx = J.ax.w + kx0;
+    h.wy = J.ay.w + ky0;
+    h.dst = J.dst + (size_t)e.y * J.dst_stride + (size_t)e.x * 4;
+    h.two_stage = J.two_stage;
+    h.job = e.job; h.ox = e.x; h.oy = e.y;
+    return h;
+}
+
+// One flagged pixel by ONE thread, from its header: for small supports (the 4:1 resize has 8 x 8 taps,
+// 88 % of all fix-ups) 32 pixels per warp beat one pixel per warp by an order of magnitude in issued
+// instructions.  Each row's samples are requested together (FIX_TMLP loads in flight per thread), then
+// summed in tap order; the vertical sum runs row by row.  Operation order per value as exact_pixel.
+enum { FIX_TMLP = 8, FIX_TROWS = 4, FIX_THREAD_TAPS = 17 };
+
+// the x-sum of one staged row and its contribution to the vertical sums (reference order)
+__device__ __forceinline__ void fix_row_rgba(const uint32_t *q, const double *w, int nx, bool two_stage, bool const_alpha, double ifx,
+                                             double wy, double &pr, double &pg, double &pb, double &pa)
+{
+    double xr = 0, xg = 0, xb = 0, xa = 0;
+#pragma unroll
+    for (int u = 0; u < FIX_TMLP; u++) {
+        if (u >= nx) break;
+        uint32_t p[4] = {(q[u] & 0xff) * 0x101u, ((q[u] >> 8) & 0xff) * 0x101u, ((q[u] >> 16) & 0xff) * 0x101u, (q[u] >> 24) * 0x101u};
+        if (two_stage) to_cropped_rgba16(p);
+        xr = __dadd_rn(xr, __dmul_rn((double)p[0], w[u]));
+        xg = __dadd_rn(xg, __dmul_rn((double)p[1], w[u]));
+        xb = __dadd_rn(xb, __dmul_rn((double)p[2], w[u]));
+        xa = __dadd_rn(xa, __dmul_rn((double)p[3], w[u]));
+    }
+    const double ta = const_alpha ? 1.0 : __dmul_rn(xa, ifx);
+    pr = __dadd_rn(pr, __dmul_rn(__dmul_rn(xr, ifx), wy));
+    pg = __dadd_rn(pg, __dmul_rn(__dmul_rn(xg, ifx), wy));
+    pb = __dadd_rn(pb, __dmul_rn(__dmul_rn(xb, ifx), wy));
+    pa = __dadd_rn(pa, __dmul_rn(ta, wy));
+}
+
+__device__ __forceinline__ void exact_pixel_thread(const FixHdr &h)
+{
+    const bool const_alpha = h.src.layout >= L_GRAY8 && !h.two_stage;
+    double pr = 0, pg = 0, pb = 0, pa = 0;
+    if (h.src.layout == L_RGBA8 && h.nx <= FIX_TMLP) {
+        // the resize case: FIX_TROWS rows x nx taps requested together (every load of the pixel is 2-4 round
+        // trips to DRAM instead of one per row), weights once
+        double w[FIX_TMLP];
+#pragma unroll
+        for (int u = 0; u < FIX_TMLP; u++) w[u] = u < h.nx ? __ldg(h.wx + u) : 0.0;
+        const uint8_t *base = h.src.p0 + (size_t)h.y0 * h.src.s0 + (size_t)h.x0 * 4;
+        for (int j0 = 0; j0 < h.ny; j0 += FIX_TROWS) {
+            uint32_t q[FIX_TROWS][FIX_TMLP];
+            double wy[FIX_TROWS];
+#pragma unroll
+            for (int r = 0; r < FIX_TROWS; r++) {
+                const bool rin = j0 + r < h.ny;
+                const uint32_t *row = (const uint32_t *)(base + (size_t)(j0 + r) * h.src.s0);
+                wy[r] = rin ? __ldg(h.wy + j0 + r) : 0.0;
+#pragma unroll
+                for (int u = 0; u < FIX_TMLP; u++) q[r][u] = (rin && u < h.nx) ? __ldg(row + u) : 0u;
+            }
+#pragma unroll
+            for (int r = 0; r < FIX_TROWS; r++)
+                if (j0 + r < h.ny) fix_row_rgba(q[r], w, h.nx, h.two_stage != 0, const_alpha, h.ifx, wy[r], pr, pg, pb, pa);
+        }
+    } else
+    for (int j = 0; j < h.ny; j++) {
+        double xr = 0, xg = 0, xb = 0, xa = 0;
+        if (h.src.layout == L_RGBA8) {
+            const uint32_t *row = (const uint32_t *)(h.src.p0 + (size_t)(h.y0 + j) * h.src.s0) + h.x0;
+            for (int k0 = 0; k0 < h.nx; k0 += FIX_TMLP) {
+                uint32_t q[FIX_TMLP];
+                double w[FIX_TMLP];
+#pragma unroll
+                for (int u = 0; u < FIX_TMLP; u++) {
+                    const bool in = k0 + u < h.nx;
+                    q[u] = in ? __ldg(row + k0 + u) : 0u;
+                    w[u] = in ? __ldg(h.wx + k0 + u) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < FIX_TMLP; u++) {
+                    if (k0 + u >= h.nx) break;
+                    uint32_t p[4] = {(q[u] & 0xff) * 0x101u, ((q[u] >> 8) & 0xff) * 0x101u, ((q[u] >> 16) & 0xff) * 0x101u,
+                                     (q[u] >> 24) * 0x101u};
+                    if (h.two_stage) to_cropped_rgba16(p);
+                    xr = __dadd_rn(xr, __dmul_rn((double)p[0], w[u]));
+                    xg = __dadd_rn(xg, __dmul_rn((double)p[1], w[u]));
+                    xb = __dadd_rn(xb, __dmul_rn((double)p[2], w[u]));
+                    xa = __dadd_rn(xa, __dmul_rn((double)p[3], w[u]));
+                }
+            }
+        } else {
+            for (int k = 0; k < h.nx; k++) {
+                uint32_t p[4];
+                sample16(h.src, h.x0 + k, h.y0 + j, p);
+                if (h.two_stage) to_cropped_rgba16(p);
+                const double w = __ldg(h.wx + k);
+                xr = __dadd_rn(xr, __dmul_rn((double)p[0], w));
+                xg = __dadd_rn(xg, __dmul_rn((double)p[1], w));
+                xb = __dadd_rn(xb, __dmul_rn((double)p[2], w));
+                xa = __dadd_rn(xa, __dmul_rn((double)p[3], w));
+            }
+        }
+        const double wy = __ldg(h.wy + j);
+        const double ta = const_alpha ? 1.0 : __dmul_rn(xa, h.ifx);
+        pr = __dadd_rn(pr, __dmul_rn(__dmul_rn(xr, h.ifx), wy));
+        pg = __dadd_rn(pg, __dmul_rn(__dmul_rn(xg, h.ifx), wy));
+        pb = __dadd_rn(pb, __dmul_rn(__dmul_rn(xb, h.ifx), wy));
+        pa = __dadd_rn(pa, __dmul_rn(ta, wy));
+    }
+    if (pr > pa) pr = pa;
+    if (pg > pa) pg = pa;
+    if (pb > pa) pb = pa;
+    uchar4 o;
+    o.x = (unsigned char)(ftou(__dmul_rn(pr, h.iy)) >> 8);
+    o.y = (unsigned char)(ftou(__dmul_rn(pg, h.iy)) >> 8);
+    o.z = (unsigned char)(ftou(__dmul_rn(pb, h.iy)) >> 8);
+    o.w = (unsigned char)(ftou(__dmul_rn(pa, h.iy)) >> 8);
+    *(uchar4 *)h.dst = o;
+}
+
+__device__ void exact_pixel_warp(const ExactJob *__restrict__ jobs, const FixHdr &h, FixWarpSmem &S)
 {
     const int lane = threadIdx.x & 31;
-    const int kx0 = __ldg(J.ax.off + ox), nx = __ldg(J.ax.off + ox + 1) - kx0;
-    const int ky0 = __ldg(J.ay.off + oy), ny = __ldg(J.ay.off + oy + 1) - ky0;
-    if (ny > FIX_MAX_ROWS) { // cannot stage: one lane does it alone
-        if (lane == 0) *(uchar4 *)(J.dst + (size_t)oy * J.dst_stride + (size_t)ox * 4) = exact_pixel(J, ox, oy);
+    const int nx = h.nx, ny = h.ny;
+    if (ny > FIX_MAX_ROWS || nx > FIX_MAX_TAPS || nx < 1) { // cannot stage: one lane does it alone
+        if (lane == 0) *(uchar4 *)h.dst = exact_pixel(jobs[h.job], h.ox, h.oy);
         __syncwarp();
         return;
     }
-    const int x0 = __ldg(J.ax.first + ox) + J.rect_x;
-    const int y0 = __ldg(J.ay.first + oy) + J.rect_y;
-    const double ifx = __ldg(J.ax.inv_ffff + ox);
-    for (int j = lane; j < ny; j += 32) {
-        double xr = 0, xg = 0, xb = 0, xa = 0;
-        bool const_alpha = false;
-        for (int k = 0; k < nx; k++) {
-            uint32_t p[4];
-            const_alpha = sample16(J.src, x0 + k, y0 + j, p);
-            if (J.two_stage) { to_cropped_rgba16(p); const_alpha = false; }
-            const double w = __ldg(J.ax.w + kx0 + k);
-            xr = __dadd_rn(xr, __dmul_rn((double)p[0], w));
-            xg = __dadd_rn(xg, __dmul_rn((double)p[1], w));
-            xb = __dadd_rn(xb, __dmul_rn((double)p[2], w));
-            xa = __dadd_rn(xa, __dmul_rn((double)p[3], w));
+    const bool const_alpha = h.src.layout >= L_GRAY8 && !h.two_stage; // Gray / YCbCr: alpha is the literal 1.0
+    for (int k = lane; k < nx; k += 32) S.wx[k] = __ldg(h.wx + k);
+    for (int j = lane; j < ny; j += 32) S.wy[j] = __ldg(h.wy + j);
+    // staging index: lanes walk (row, tap) with the tap count rounded up to a power of two (no division)
+    const int lg = 32 - __clz(nx - 1), nxp = 1 << lg; // nx = 1 -> lg 0
+    const int rows_per_chunk = FIX_STAGE_PX / nx;     // >= 16
+    const bool rgba = h.src.layout == L_RGBA8;
+    for (int j0 = 0; j0 < ny; j0 += rows_per_chunk) {
+        const int R = min(rows_per_chunk, ny - j0), n = R << lg;
+        if (rgba) { // the common case without the per-sample layout switch: 8-bit premultiplied, 16 bits = byte * 0x101
+            const uint8_t *base = h.src.p0 + (size_t)(h.y0 + j0) * h.src.s0 + (size_t)h.x0 * 4;
+            for (int i0 = lane; i0 < n; i0 += 32 * FIX_MLP) { // FIX_MLP loads per lane in flight, then their unpacking
+                uint32_t q[FIX_MLP];
+#pragma unroll
+                for (int u = 0; u < FIX_MLP; u++) {
+                    const int i = i0 + 32 * u, jj = i >> lg, k = i & (nxp - 1);
+                    q[u] = (i < n && k < nx) ? __ldg((const uint32_t *)(base + (size_t)jj * h.src.s0) + k) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < FIX_MLP; u++) {
+                    const int i = i0 + 32 * u, jj = i >> lg, k = i & (nxp - 1);
+                    if (i >= n || k >= nx) continue;
+                    uint32_t p[4] = {(q[u] & 0xff) * 0x101u, ((q[u] >> 8) & 0xff) * 0x101u, ((q[u] >> 16) & 0xff) * 0x101u,
+                                     (q[u] >> 24) * 0x101u};
+                    if (h.two_stage) to_cropped_rgba16(p);
+                    S.px[jj * nx + k] = make_uint2(p[0] | (p[1] << 16), p[2] | (p[3] << 16));
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int i = lane; i < n; i += 32) {
+                const int jj = i >> lg, k = i & (nxp - 1);
+                if (k >= nx) continue;
+                uint32_t p[4];
+                sample16(h.src, h.x0 + k, h.y0 + j0 + jj, p);
+                if (h.two_stage) to_cropped_rgba16(p);
+                S.px[jj * nx + k] = make_uint2(p[0] | (p[1] << 16), p[2] | (p[3] << 16));
+            }
         }
-        tmp[j][0] = __dmul_rn(xr, ifx);
-        tmp[j][1] = __dmul_rn(xg, ifx);
-        tmp[j][2] = __dmul_rn(xb, ifx);
-        tmp[j][3] = const_alpha ? 1.0 : __dmul_rn(xa, ifx);
+        __syncwarp();
+        for (int jj = lane; jj < R; jj += 32) {
+            const uint2 *row = S.px + jj * nx;
+            double xr = 0, xg = 0, xb = 0, xa = 0;
+            for (int k = 0; k < nx; k++) {
+                const uint2 q = row[k];
+                const double w = S.wx[k];
+                xr = __dadd_rn(xr, __dmul_rn((double)(q.x & 0xffffu), w));
+                xg = __dadd_rn(xg, __dmul_rn((double)(q.x >> 16), w));
+                xb = __dadd_rn(xb, __dmul_rn((double)(q.y & 0xffffu), w));
+                xa = __dadd_rn(xa, __dmul_rn((double)(q.y >> 16), w));
+            }
+            double *t = S.tmp[j0 + jj];
+            t[0] = __dmul_rn(xr, h.ifx);
+            t[1] = __dmul_rn(xg, h.ifx);
+            t[2] = __dmul_rn(xb, h.ifx);
+            t[3] = const_alpha ? 1.0 : __dmul_rn(xa, h.ifx);
+        }
+        __syncwarp();
     }
-    __syncwarp();
     double p = 0;
     if (lane < 4) {
-        for (int j = 0; j < ny; j++) p = __dadd_rn(p, __dmul_rn(tmp[j][lane], __ldg(J.ay.w + ky0 + j)));
+        for (int j = 0; j < ny; j++) p = __dadd_rn(p, __dmul_rn(S.tmp[j][lane], S.wy[j]));
     }
     const double pa = __shfl_sync(0xffffffffu, p, 3);
     if (lane < 4) {
         if (p > pa) p = pa;
-        const uint32_t q = ftou(__dmul_rn(p, __ldg(J.ay.inv + oy))) >> 8;
-        J.dst[(size_t)oy * J.dst_stride + (size_t)ox * 4 + lane] = (unsigned char)q;
+        h.dst[lane] = (unsigned char)(ftou(__dmul_rn(p, h.iy)) >> 8);
     }
     __syncwarp();
 }
@@ -200,13 +399,42 @@ __device__ void exact_pixel_warp(const ExactJob &J, int ox, int oy, double (*tmp
 __global__ void __launch_bounds__(FIX_THREADS)
 k_exact_fix(const ExactJob *__restrict__ jobs, int n_jobs, FixList fix)
 {
-    __shared__ double tmp[FIX_THREADS / 32][FIX_MAX_ROWS][4];
-    const uint32_t cnt = *fix.count;
+    __shared__ FixWarpSmem ws[FIX_THREADS / 32];
+    const uint32_t cnt = fix.count[0];
+    if (cnt == 0) return;
     if (cnt <= fix.capacity) {
-        const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-        for (uint32_t i = wid; i < cnt; i += nw) {
-            const FixEntry e = fix.entries[i];
-            exact_pixel_warp(jobs[e.job], e.x, e.y, tmp[threadIdx.x >> 5]);
+        // Warps claim batches of up to 32 entries (one per lane) from the cursor fix.count[1].  Batch b takes the
+        // entries b, b + nbatch, b + 2 nbatch, ... (list neighbours -- the flagged pixels of one emitted row --
+        // land in different batches).  A lane finishes its own pixel if the support is narrow; wide ones are
+        // queued at the unused back end of the list (fix.count[2]) for k_exact_fix_wide, one warp each.
+        const int lane = threadIdx.x & 31;
+        const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+        const uint32_t width = min(32u, (cnt + nwarps - 1) / nwarps); // entries per batch: one batch per warp while they last
+        const uint32_t nbatch = (cnt + width - 1) / width;
+        for (;;) {
+            uint32_t b = 0;
+            if (lane == 0) b = atomicAdd(fix.count + 1, 1u);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b >= nbatch) break;
+            const uint32_t idx = b + (uint32_t)lane * nbatch;
+            const bool valid = (uint32_t)lane < width && idx < cnt;
+            FixHdr mine = {};
+            if (valid) mine = fix_header(jobs, fix.entries[idx]);
+            const bool small = valid && mine.nx <= FIX_THREAD_TAPS && mine.ny <= FIX_THREAD_TAPS;
+            bool inline_wide = false;
+            if (small) {
+                exact_pixel_thread(mine);
+            } else if (valid) {
+                const uint32_t pos = atomicAdd(fix.count + 2, 1u);
+                if (cnt + pos < fix.capacity) fix.entries[fix.capacity - 1u - pos] = FixEntry{mine.job, mine.ox, mine.oy};
+                else inline_wide = true; // no room left at the back: the warp does it here
+            }
+            uint32_t big = __ballot_sync(0xffffffffu, inline_wide);
+            while (big) {
+                const int k = __ffs(big) - 1;
+                big &= big - 1;
+                exact_pixel_warp(jobs, warp_bcast(mine, k), ws[threadIdx.x >> 5]);
+            }
         }
     } else {
         // the list overflowed: entries were dropped, so redo every stream target whole
@@ -220,6 +448,27 @@ k_exact_fix(const ExactJob *__restrict__ jobs, int n_jobs, FixList fix)
                 *(uchar4 *)(J.dst + (size_t)y * J.dst_stride + (size_t)x * 4) = o;
             }
         }
+    }
+}
+
+// The wide supports queued by k_exact_fix at the back of the list: one pixel per warp and claim (cursor
+// fix.count[3]), so a 29 x 29-tap thumbnail pixel never waits behind another one in the same warp.
+__global__ void __launch_bounds__(FIX_THREADS)
+k_exact_fix_wide(const ExactJob *__restrict__ jobs, FixList fix)
+{
+    __shared__ FixWarpSmem ws[FIX_THREADS / 32];
+    const uint32_t cnt = fix.count[0];
+    if (cnt > fix.capacity) return; // overflow: k_exact_fix redid every target whole
+    const uint32_t n_wide = min(fix.count[2], fix.capacity - cnt);
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(fix.count + 3, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n_wide) break;
+        FixHdr h = {};
+        if (lane == 0) h = fix_header(jobs, fix.entries[fix.capacity - 1u - i]);
+        exact_pixel_warp(jobs, warp_bcast(h, 0), ws[threadIdx.x >> 5]);
     }
 }
 
@@ -653,8 +902,6 @@ __device__ __forceinline__ void unpack_alpha(const uint4 &c, float2 *va)
 // chain value (ALPHA=false).
 __device__ __forceinline__ void sts128(float4 *p, float x, float y, float z, float w)
 {
-    // volatile: keeps the two accumulator-set variants of an emit in separate (uniform) branches; left
-    // to itself the compiler if-converts them into ~40 FSELs per emit
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 template <int SET, bool ALPHA>
@@ -671,6 +918,21 @@ __device__ __forceinline__ void park_row(VAcc<ALPHA> &S, float sa, float4 *buf, 
 #pragma unroll
     for (int i = 0; i < 6; i++) S.rgb[SET][i] = make_float2(0.f, 0.f);
     if constexpr (ALPHA) S.al[SET][0] = S.al[SET][1] = make_float2(0.f, 0.f);
+}
+
+// Park the set that source-row record `r` completes (emit word e: output row << 1 | set).  e is
+// CTA-uniform.  A convergence barrier in each arm keeps the two set variants in real branches:
+// if-converted, both variants' ~30 instructions would issue at every emit.
+template <bool ALPHA>
+__device__ __forceinline__ void park_emit(VAcc<ALPHA> &S, int e, const float4 &r, float4 *buf, int slot)
+{
+    if (e & 1) {
+        park_row<1, ALPHA>(S, r.w, buf, slot);
+        asm volatile("bar.warp.sync 0xffffffff; // set 1" ::: "memory");
+    } else {
+        park_row<0, ALPHA>(S, r.z, buf, slot);
+        asm volatile("bar.warp.sync 0xffffffff; // set 0" ::: "memory");
+    }
 }
 
 // What a V thread carries through the row loop besides its accumulators.
@@ -697,13 +959,15 @@ struct VCtx {
 // in the lane-per-output form, all four rows inside the band, opaque so far, watermark (if any)
 // copied by the producer.  Everything else takes v_rows below.
 template <int LEAN, typename SM>
-__device__ __forceinline__ void v_rows_fast(VAcc<false> &S, const StreamJob &J, const StreamStage &stg, SM &sm, const VCtx &C,
-                                            const FixList &fix)
+__device__ __forceinline__ uint32_t v_rows_fast(VAcc<false> &S, const StreamJob &J, const StreamStage &stg, SM &sm, const VCtx &C,
+                                                const FixList &fix)
 {
     uint4 cur = stg.rows[0][C.slot];
+    uint32_t opq = 0xffffffffu; // AND of every pixel word met: all four alpha bytes are 0xff iff opq >= 0xff000000
 #pragma unroll
     for (int k = 0; k < STREAM_GROUP; k++) {
         const uint4 nxt = stg.rows[(k + 1) & (STREAM_GROUP - 1)][C.slot];
+        opq &= (cur.x & cur.y) & (cur.z & cur.w);
         float2 vp[6];
         unpack_rgb(cur, vp);
         const float4 r = *reinterpret_cast<const float4 *>(&stg.rec[0].row[k]); // LDS.128 broadcast
@@ -715,8 +979,7 @@ __device__ __forceinline__ void v_rows_fast(VAcc<false> &S, const StreamJob &J, 
         }
         const int e = stg.rec[0].emit[k];
         if (e >= 0) { // CTA-uniform: this source row completes output row e>>1, held in set e&1
-            if (e & 1) park_row<1, false>(S, r.w, sm.xbuf[0], C.pslot[0]);
-            else       park_row<0, false>(S, r.z, sm.xbuf[0], C.pslot[0]);
+            park_emit<false>(S, e, r, sm.xbuf[0], C.pslot[0]);
             if (LEAN == 1 || (LEAN == 4 && C.x0_inline)) { // local target: this warp filters its own strip, one output per lane
                 __syncwarp();
                 const float4 *buf = sm.xbuf[0];
@@ -747,6 +1010,7 @@ __device__ __forceinline__ void v_rows_fast(VAcc<false> &S, const StreamJob &J, 
         }
         cur = nxt;
     }
+    return opq;
 }
 
 // The lean two-target case: target 0 local (inline lane-per-output pass), target 1 wide (split pass
@@ -771,8 +1035,7 @@ __device__ __forceinline__ void v_rows_fast2(VAcc<false> *S, const StreamJob &J,
             }
             const int e = stg.rec[0].emit[k];
             if (e >= 0) { // CTA-uniform
-                if (e & 1) park_row<1, false>(S[0], r.w, sm.xbuf[0], C.pslot[0]);
-                else       park_row<0, false>(S[0], r.z, sm.xbuf[0], C.pslot[0]);
+                park_emit<false>(S[0], e, r, sm.xbuf[0], C.pslot[0]);
                 __syncwarp();
                 const float4 *buf = sm.xbuf[0];
                 float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
@@ -803,8 +1066,7 @@ __device__ __forceinline__ void v_rows_fast2(VAcc<false> *S, const StreamJob &J,
             }
             const int e = stg.rec[1].emit[k];
             if (e >= 0) {
-                if (e & 1) park_row<1, false>(S[1], r.w, sm.xbuf[1], C.pslot[1]);
-                else       park_row<0, false>(S[1], r.z, sm.xbuf[1], C.pslot[1]);
+                park_emit<false>(S[1], e, r, sm.xbuf[1], C.pslot[1]);
                 xpass<2>(J, sm, 1, e >> 1, C.tile, C.cx0, C.vtid, fix);
             }
         }
@@ -872,8 +1134,7 @@ __device__ __forceinline__ void v_rows(VAcc<ALPHA> *S, const StreamJob &J, const
                 const int e = stg.rec[T].emit[k];
                 oyv[T] = e >> 1;
                 if (e >= 0) { // CTA-uniform: this source row completes output row e>>1, held in set e&1
-                    if (e & 1) park_row<1, ALPHA>(S[T], r.w, sm.xbuf[T], C.pslot[T]);
-                    else       park_row<0, ALPHA>(S[T], r.z, sm.xbuf[T], C.pslot[T]);
+                    park_emit<ALPHA>(S[T], e, r, sm.xbuf[T], C.pslot[T]);
                     if (T == 0 && C.x0_inline) {
                         __syncwarp();
                         float2 x0_rg = make_float2(0.f, 0.f), x0_ba = make_float2(0.f, 0.f);
@@ -1083,13 +1344,19 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
         if (++rs == STAGES) { rs = 0; rph ^= 1; }
     };
 
-    // phase 1: every pixel this warp has met so far is opaque -- alpha comes from the records
+    // phase 1: every pixel this warp has met so far is opaque -- alpha comes from the records.
+    // The general kernel scans a group before it runs it (it switches to per-pixel alpha from that
+    // group on); the lean single-target kernels only raise the redo flag, so they fold the scan into
+    // the row loop (one AND per row on registers they hold anyway) and vote after the group.
     bool switch_alpha = false;
+    constexpr bool FOLD = FAST && LEAN != 3;
+    const bool check = NT > 0 && (!FAST || J.redo_flag != nullptr); // read once: the asm memory clobbers would reload it per group
     for (; g < ngroups; g++) {
         mbar_wait(&sm.full[rs], rph);
         const StreamStage &stg = sm.stage[rs];
         const int nr = yend - ys0 - g * STREAM_GROUP;
-        if (NT > 0 && (!FAST || J.redo_flag != nullptr)) {
+        const bool folded = FOLD && nr >= STREAM_GROUP; // a partial last group holds stale rows: scan it the guarded way
+        if (check && !folded) {
             uint32_t m = 0xffffffffu;
 #pragma unroll
             for (int k = 0; k < STREAM_GROUP; k++) {
@@ -1106,8 +1373,10 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
             }
         }
         if constexpr (LEAN == 3) v_rows_fast2(S, J, stg, sm, C, fix);
-        else if constexpr (FAST) v_rows_fast<LEAN>(S[0], J, stg, sm, C, fix);
-        else                v_rows<NT, WM, false>(S, J, stg, sm, C, ys0 + g * STREAM_GROUP, nr, fix);
+        else if constexpr (FAST) {
+            const uint32_t opq = v_rows_fast<LEAN>(S[0], J, stg, sm, C, fix);
+            if (check && folded && __any_sync(0xffffffffu, opq < 0xff000000u) && (tid & 31) == 0) atomicExch(J.redo_flag, 1);
+        } else              v_rows<NT, WM, false>(S, J, stg, sm, C, ys0 + g * STREAM_GROUP, nr, fix);
         advance();
     }
     if constexpr (FAST) return;
@@ -1300,8 +1569,7 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
             }
             const int e = stg.rec[0].emit[k];
             if (e >= 0) { // CTA-uniform
-                if (e & 1) park_row<1, false>(S, r.w, sm.xbuf[0], pslot);
-                else       park_row<0, false>(S, r.z, sm.xbuf[0], pslot);
+                park_emit<false>(S, e, r, sm.xbuf[0], pslot);
                 if (local) __syncwarp(); else vwarps_bar();
                 xcached(sm, 0, e >> 1, tid, fix);
                 if (local) __syncwarp(); else vwarps_bar();
@@ -1393,7 +1661,17 @@ cudaError_t launch_exact_tiles(const ExactJob *jobs, const ExactItem *items, int
 cudaError_t launch_exact_fix(const ExactJob *jobs, int n_jobs, FixList fix, cudaStream_t st)
 {
     if (!fix.capacity || n_jobs <= 0) return cudaSuccess;
-    k_exact_fix<<<148 * 16, FIX_THREADS, 0, st>>>(jobs, n_jobs, fix); // 64 resident warps per SM hide the fp64/LDG latency
+    static int grid = 0, grid_wide = 0; // one resident wave each: the warps claim work from cursors (benign race: idempotent)
+    if (grid == 0) {
+        int dev = 0, sms = 148, per_sm = 4, per_sm_wide = 4;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_exact_fix, FIX_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_wide, k_exact_fix_wide, FIX_THREADS, 0) != cudaSuccess || per_sm_wide < 1) per_sm_wide = 4;
+        grid_wide = sms * per_sm_wide;
+        grid = sms * per_sm;
+    }
+    k_exact_fix<<<grid, FIX_THREADS, 0, st>>>(jobs, n_jobs, fix);
+    k_exact_fix_wide<<<grid_wide, FIX_THREADS, 0, st>>>(jobs, fix);
     return cudaGetLastError();
 }
 
