@@ -257,7 +257,7 @@ def main():
     n_img = args.images
     lib = L.load()
     eng = ip.Engine(devices=[local_rank], precision=ip.PRECISION_EXACT, lanes_per_device=3,
-                    max_batch=env_int("IPG_BENCH_MAX_BATCH", 32), batch_window_us=100)
+                    max_batch=env_int("IPG_BENCH_MAX_BATCH", 128), batch_window_us=100)
     ctx = eng._ctx
 
     # ---- synthetic sources, resident in HBM (seeded per image; A=255)
@@ -358,7 +358,7 @@ def main():
     os.environ["IPG_NO_OVERLAP"] = "1"
     os.environ["IPG_MERGE_LEAN"] = "0"
     eng_iso = ip.Engine(devices=[local_rank], precision=ip.PRECISION_EXACT, lanes_per_device=1,
-                        max_batch=env_int("IPG_BENCH_MAX_BATCH", 32), batch_window_us=2000)
+                        max_batch=env_int("IPG_BENCH_MAX_BATCH", 128), batch_window_us=2000)
     del os.environ["IPG_NO_OVERLAP"], os.environ["IPG_MERGE_LEAN"]
     n_iso = min(n_img, 64)
     for rep in range(3):           # 2 warm-up passes, 1 timed

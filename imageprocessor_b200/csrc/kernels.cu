@@ -697,6 +697,10 @@ template <> struct XTab<0> {};
 #define IPG_ROW_UNROLL 4
 #endif
 constexpr int kRowUnroll = IPG_ROW_UNROLL; // rows of a group unrolled in the V loop
+#ifndef IPG_FAST_UNROLL
+#define IPG_FAST_UNROLL 4
+#endif
+constexpr int kFastUnroll = IPG_FAST_UNROLL; // ... in the lean instantiations (each unrolled row carries its own copy of the emit code)
 enum { STREAM_XBUF = STREAM_COLS + 64 }; // padded: zero-weight taps past an output's support read finite data
 
 // What the horizontal pass needs of a target, copied to shared memory once per CTA.
@@ -735,7 +739,7 @@ __device__ __forceinline__ void xfinish(const TI &t, uint32_t D, int ox, int oy,
     const uint32_t o = quant16(r, D, span, amb) | (quant16(g, D, span, amb) << 8) |
                        (quant16(b, D, span, amb) << 16) | (quant16(a, D, span, amb) << 24);
     *(uint32_t *)(t.dst + (size_t)oy * t.dst_stride + (size_t)ox * 4) = o;
-    if (amb && fix.capacity) {
+    if (amb && fix.capacity) { // (keep this shape: the compiler aggregates the atomic per warp; other forms cost the V loop 5-30 %)
         const uint32_t idx = atomicAdd(fix.count, 1u);
         if (idx < fix.capacity) fix.entries[idx] = FixEntry{t.exact_job, ox, oy};
     }
@@ -874,27 +878,37 @@ template <bool ALPHA> struct VAcc;
 template <> struct VAcc<false> { float2 rgb[2][6]; };
 template <> struct VAcc<true> { float2 rgb[2][6]; float2 al[2][2]; };
 
-__device__ __forceinline__ float2 magic2(uint32_t qa, int ka, uint32_t qb, int kb)
+#ifndef IPG_DP4A_MASK
+#define IPG_DP4A_MASK 0
+#endif
+// byte k of q -> the bit pattern of 2^23 + b.  PRMT runs on the ALU pipe, the V loop's busiest; for the
+// byte positions in IPG_DP4A_MASK the same word comes from IDP.4A (0x4B000000 + q . (1 << 8k)) on the
+// FMA-side integer pipe instead.
+template <int K> __device__ __forceinline__ uint32_t magic1(uint32_t q)
+{
+    if constexpr ((IPG_DP4A_MASK >> K) & 1) return __dp4a(q, 1u << (8 * K), 0x4B000000u);
+    else return __byte_perm(q, 0x4B000000u, 0x7540 + K);
+}
+template <int KA, int KB> __device__ __forceinline__ float2 magic2(uint32_t qa, uint32_t qb)
 {
     // two bytes -> (2^23 + b) bit patterns; the caller subtracts 2^23 with one FADD2
-    return make_float2(__uint_as_float(__byte_perm(qa, 0x4B000000u, 0x7540 + ka)),
-                       __uint_as_float(__byte_perm(qb, 0x4B000000u, 0x7540 + kb)));
+    return make_float2(__uint_as_float(magic1<KA>(qa)), __uint_as_float(magic1<KB>(qb)));
 }
 __device__ __forceinline__ void unpack_rgb(const uint4 &c, float2 *vp)
 {
     const float2 m = make_float2(-8388608.0f, -8388608.0f);
-    vp[0] = __fadd2_rn(magic2(c.x, 0, c.x, 1), m);
-    vp[1] = __fadd2_rn(magic2(c.x, 2, c.y, 0), m);
-    vp[2] = __fadd2_rn(magic2(c.y, 1, c.y, 2), m);
-    vp[3] = __fadd2_rn(magic2(c.z, 0, c.z, 1), m);
-    vp[4] = __fadd2_rn(magic2(c.z, 2, c.w, 0), m);
-    vp[5] = __fadd2_rn(magic2(c.w, 1, c.w, 2), m);
+    vp[0] = __fadd2_rn(magic2<0, 1>(c.x, c.x), m);
+    vp[1] = __fadd2_rn(magic2<2, 0>(c.x, c.y), m);
+    vp[2] = __fadd2_rn(magic2<1, 2>(c.y, c.y), m);
+    vp[3] = __fadd2_rn(magic2<0, 1>(c.z, c.z), m);
+    vp[4] = __fadd2_rn(magic2<2, 0>(c.z, c.w), m);
+    vp[5] = __fadd2_rn(magic2<1, 2>(c.w, c.w), m);
 }
 __device__ __forceinline__ void unpack_alpha(const uint4 &c, float2 *va)
 {
     const float2 m = make_float2(-8388608.0f, -8388608.0f);
-    va[0] = __fadd2_rn(magic2(c.x, 3, c.y, 3), m);
-    va[1] = __fadd2_rn(magic2(c.z, 3, c.w, 3), m);
+    va[0] = __fadd2_rn(magic2<3, 3>(c.x, c.y), m);
+    va[1] = __fadd2_rn(magic2<3, 3>(c.z, c.w), m);
 }
 
 // Park one completed, vertically-filtered row (accumulator set SET) at elements
@@ -964,7 +978,7 @@ __device__ __forceinline__ uint32_t v_rows_fast(VAcc<false> &S, const StreamJob 
 {
     uint4 cur = stg.rows[0][C.slot];
     uint32_t opq = 0xffffffffu; // AND of every pixel word met: all four alpha bytes are 0xff iff opq >= 0xff000000
-#pragma unroll
+#pragma unroll kFastUnroll
     for (int k = 0; k < STREAM_GROUP; k++) {
         const uint4 nxt = stg.rows[(k + 1) & (STREAM_GROUP - 1)][C.slot];
         opq &= (cur.x & cur.y) & (cur.z & cur.w);

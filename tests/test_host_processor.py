@@ -203,7 +203,9 @@ def test_process_formats_fit_thumbnail_and_failure_isolation(engines, oracle):
 @pytest.mark.gpu
 def test_process_batch_is_the_batching_worker_loop(engines, oracle):
     import imageprocessor_b200 as ip
-    e = engines(ip.PRECISION_EXACT)
+    # its own engine with a long batching window: the coalescing asserted below must not depend on how fast
+    # this (Python) submitter happens to run on a loaded box
+    e = engines(ip.PRECISION_EXACT, batch_window_us=20000)
     repo = P.MemoryFileRepo()
     proc = P.ImageProcessor(e, repo, encode=P.raw_encode)
     imgs = [rgba_random(640 + 16 * k, 480 + 8 * k, 200 + k) for k in range(6)]
