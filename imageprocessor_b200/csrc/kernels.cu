@@ -687,8 +687,8 @@ struct __align__(16) StreamStage {
 // e0, e0 + P, e0 + 2P, ...  Lives in shared memory, not registers: the emit code exists
 // once for all targets and the accumulators keep the register file.
 template <int NT> struct XTab {
-    int32_t ox[NT][STREAM_XROUNDS][STREAM_THREADS]; // output column of each round, or -1 when the thread has none
-    int32_t e0[NT][STREAM_XROUNDS][STREAM_THREADS]; // element of xbuf[T] holding its first tap
+    int16_t ox[NT][STREAM_XROUNDS][STREAM_THREADS]; // output column of each round (< 32768), or -1 when the thread has none
+    int16_t e0[NT][STREAM_XROUNDS][STREAM_THREADS]; // element of xbuf[T] holding its first tap
     float w[NT][STREAM_XTAPS_TAB][STREAM_THREADS];  // its weights (round r: entries r * ntap ...), 0 past the end
 };
 template <> struct XTab<0> {};
@@ -792,8 +792,8 @@ __device__ __forceinline__ void xtab_fill(XT &xt, XInfo &xi, int T, const Stream
             k0 = __ldg(t.xoff + ox);
             n = __ldg(t.xoff + ox + 1) - k0;
         }
-        xt.ox[T][r][tid] = ox;
-        xt.e0[T][r][tid] = e0;
+        xt.ox[T][r][tid] = (int16_t)ox;
+        xt.e0[T][r][tid] = (int16_t)e0;
         if (r < R) // rounds past R have no table entries (R * ntap <= STREAM_XTAPS_TAB is what the planner guarantees)
             for (int k = 0; k < ntap; k++)
                 xt.w[T][r * ntap + k][tid] = (ox >= 0 && part + k * P < n) ? __ldg(t.xw + k0 + part + k * P) : 0.f;

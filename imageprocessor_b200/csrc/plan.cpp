@@ -227,6 +227,7 @@ static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const Stream
         const StreamTargetSpec &s = targets[i];
         if (s.dw <= 0 || s.dh <= 0 || s.rect_w <= 0 || s.rect_h <= 0) return nullptr;
         if (s.rect_h < s.dh) return nullptr; // vertical upscale: many open rows -> k_exact
+        if (s.dw > 32767) return nullptr;    // the kernel's per-thread tables hold output columns in 16 bits
         auto ax = get_axis_plan(s.dw, s.rect_w);
         max_taps_x = std::max(max_taps_x, ax->max_taps);
         max_scale_y = std::max(max_scale_y, (double)s.rect_h / (double)s.dh);
