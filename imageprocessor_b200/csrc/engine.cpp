@@ -407,7 +407,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     std::vector<StreamItem> fitems;   // lean instantiation, local target
     std::vector<StreamItem> f2items;  // lean instantiation, wide target
     std::vector<StreamItem> f3items;  // lean instantiation, local + wide targets fused
-    std::vector<StreamItem> pitems;   // k_stream_planar (YCbCr sources)
+    std::vector<StreamItem> pitems;   // k_stream_planar<false> (YCbCr and Gray sources)
+    std::vector<StreamItem> nitems;   // k_stream_planar<true> (NRGBA sources)
     bool any_wm_fast = false, any_wm_fast2 = false, any_wm_fast3 = false;
     size_t max_jobs = 0;
     for (auto &tp : B.tickets) max_jobs += tp->ops.size() + 1;
@@ -679,9 +680,11 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 }
             }
         } else {
-            // planar YCbCr: the lean planar kernel takes every resample whose geometry streams in a cached form
+            // planar YCbCr, Gray, NRGBA: the lean 16-bit-sample kernel takes every resample whose geometry streams in a
+            // cached form
             const bool planar_ok = precision != IPG_PRECISION_REFERENCE &&
-                                   ((sv.layout >= L_YCBCR444 && sv.layout <= L_YCBCR440) || sv.layout == L_GRAY8) &&
+                                   ((sv.layout >= L_YCBCR444 && sv.layout <= L_YCBCR440) || sv.layout == L_GRAY8 ||
+                                    sv.layout == L_NRGBA8) &&
                                    ((((uintptr_t)sv.p0) | ((uintptr_t)sv.p1) | ((uintptr_t)sv.p2) | (uintptr_t)sv.s0 |
                                      (uintptr_t)sv.s1 | (uintptr_t)sv.s2) & 15) == 0;
             for (auto *op : res) {
@@ -738,7 +741,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                     // tiles outside the crop square have no outputs: skip them
                     if (tgm.tile_ox[it.tile + 1] == tgm.tile_ox[it.tile]) continue;
                     it.job = ji;
-                    pitems.push_back(it);
+                    (sv.layout == L_NRGBA8 ? nitems : pitems).push_back(it);
                 }
             }
         }
@@ -773,6 +776,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     const StreamItem *d_f2items = blob.dptr<const StreamItem>(blob.put(f2items.data(), f2items.size() * sizeof(StreamItem), 16));
     const StreamItem *d_f3items = blob.dptr<const StreamItem>(blob.put(f3items.data(), f3items.size() * sizeof(StreamItem), 16));
     const StreamItem *d_pitems = blob.dptr<const StreamItem>(blob.put(pitems.data(), pitems.size() * sizeof(StreamItem), 16));
+    const StreamItem *d_nitems = blob.dptr<const StreamItem>(blob.put(nitems.data(), nitems.size() * sizeof(StreamItem), 16));
     const StreamItem *d_ritems = blob.dptr<const StreamItem>(blob.put(ritems.data(), ritems.size() * sizeof(StreamItem), 16));
     const ExactJob *d_fixjobs = blob.dptr<const ExactJob>(blob.put(fixjobs.data(), fixjobs.size() * sizeof(ExactJob), 16));
     const ExactJob *d_xjobs = blob.dptr<const ExactJob>(blob.put(xjobs.data(), xjobs.size() * sizeof(ExactJob), 16));
@@ -797,7 +801,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     // side stream, the lean wide-target launch (thumbnail) and the general launch over whatever neither lean kernel
     // takes -- each fills the other's ramp and tail.  The on-demand redo of lean jobs follows both.
     const bool side_work = !f2items.empty() || !sitems.empty();
-    const bool main_work = !fitems.empty() || !f3items.empty() || !pitems.empty();
+    const bool main_work = !fitems.empty() || !f3items.empty() || !pitems.empty() || !nitems.empty();
     const bool side = side_work && main_work && c.overlap_streams;
     cudaStream_t s2 = side ? L.st2 : st;
     if (side) {
@@ -806,7 +810,11 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     }
     auto launch_main = [&]() { // the lean launches that carry most of the bytes
         if (!pitems.empty()) {
-            IPG_CU(launch_stream_planar(d_sjobs, d_pitems, (int)pitems.size(), fix, st));
+            IPG_CU(launch_stream_planar(d_sjobs, d_pitems, (int)pitems.size(), false, fix, st));
+            B.n_kernels++;
+        }
+        if (!nitems.empty()) {
+            IPG_CU(launch_stream_planar(d_sjobs, d_nitems, (int)nitems.size(), true, fix, st));
             B.n_kernels++;
         }
         if (!f3items.empty()) {

@@ -1430,20 +1430,29 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
 // second pass re-expands (two_stage).  Alpha is the constant 0xffff.  H2D is 1.5 bytes per
 // pixel instead of 4 for a 4:2:0 JPEG.
 // ---------------------------------------------------------------------------------
-struct __align__(16) PlanarStage {
+// NRGBA = true is the same kernel for *image.NRGBA (PNG with straight alpha): rows of 4 bytes per
+// pixel land as in k_stream; every V lane premultiplies its 4 pixels at 16 bits exactly as
+// scaleX_NRGBA does (a16 = A * 0x101; c16 = C * a16 / 0xff in uint32) and carries per-pixel alpha
+// accumulators (the alpha lane is data here, never a constant).
+template <bool NRGBA> struct PlanarStage;
+template <> struct __align__(16) PlanarStage<false> {
     uint8_t y[STREAM_GROUP][STREAM_COLS];
     uint8_t cb[STREAM_GROUP][STREAM_COLS];
     uint8_t cr[STREAM_GROUP][STREAM_COLS];
     GroupRec rec[1];
 };
-template <int STAGES> struct __align__(128) PlanarSmem {
-    PlanarStage stage[STAGES];
+template <> struct __align__(16) PlanarStage<true> {
+    uint4 rows[STREAM_GROUP][STREAM_THREADS];
+    GroupRec rec[1];
+};
+template <bool NRGBA, int STAGES> struct __align__(128) PlanarSmem {
+    PlanarStage<NRGBA> stage[STAGES];
     float4 xbuf[1][STREAM_XBUF];
     XTab<1> xt;
     uint64_t full[STAGES], empty[STAGES];
     XInfo xi[2];
 };
-enum { PLANAR_STAGES = 4, PLANAR_CTAS = 4 };
+enum { PLANAR_STAGES = 4, PLANAR_CTAS = 4, NRGBA_CTAS = 3 };
 
 __device__ __forceinline__ uint32_t clamp16(int v) { return (uint32_t)min(max(v, 0), 0xffff); }
 // two 16-bit samples -> fp32 pair via the 2^23 mantissa trick (exact for values < 2^23)
@@ -1452,11 +1461,13 @@ __device__ __forceinline__ float2 u16x2_f32(uint32_t a, uint32_t b)
     return __fadd2_rn(make_float2(__uint_as_float(0x4B000000u | a), __uint_as_float(0x4B000000u | b)),
                       make_float2(-8388608.0f, -8388608.0f));
 }
+__device__ __forceinline__ uint32_t div255(uint32_t x) { return __umulhi(x, 0x80808081u) >> 7; } // exact for every uint32
 
-__global__ void __launch_bounds__(STREAM_CTA, PLANAR_CTAS)
+template <bool NRGBA>
+__global__ void __launch_bounds__(STREAM_CTA, (NRGBA ? NRGBA_CTAS : PLANAR_CTAS))
 k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ items, FixList fix)
 {
-    using Smem = PlanarSmem<PLANAR_STAGES>;
+    using Smem = PlanarSmem<NRGBA, PLANAR_STAGES>;
     constexpr int STAGES = PLANAR_STAGES;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -1478,7 +1489,7 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
     const bool sub_y = layout == L_YCBCR420 || layout == L_YCBCR440; // ... vertical
     const bool gray = layout == L_GRAY8;                              // *image.Gray: one plane, r = g = b = Y * 0x101
     const int ncols = min(J.slab_cols, W - cx0);
-    const uint32_t y_bytes = (uint32_t)((ncols + 15) & ~15);
+    const uint32_t y_bytes = (uint32_t)(((NRGBA ? ncols * 4 : ncols) + 15) & ~15);
     const uint32_t c_bytes = (uint32_t)(((sub_x ? (ncols + 1) >> 1 : ncols) + 15) & ~15);
 
     if (tid == 0) {
@@ -1487,6 +1498,13 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
             mbar_init(&sm.empty[s], STREAM_THREADS / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if constexpr (NRGBA) {
+        // slab columns past the image edge are never written by TMA: park transparent black there (finite, feeds nothing)
+        if (tid < STREAM_THREADS && cx0 + slot * STREAM_PX >= W) {
+            for (int s = 0; s < STAGES; s++)
+                for (int k = 0; k < STREAM_GROUP; k++) sm.stage[s].rows[k][slot] = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
     // horizontal-pass table (cached form; the engine only sends jobs whose tiles have one)
     if (tid < STREAM_THREADS) {
@@ -1498,19 +1516,26 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
     if (warp == STREAM_THREADS / 32) {
         // ===== producer =====
         if ((tid & 31) != 0) return;
+        if constexpr (NRGBA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const uint8_t *grec = (const uint8_t *)(J.grec + (size_t)__ldg(J.band_grec_off + band));
         const int ccx0 = sub_x ? cx0 >> 1 : cx0;
         auto refill = [&](int group, int stage) {
             const int y0 = ys0 + group * STREAM_GROUP;
             const int nr = min(STREAM_GROUP, yend - y0);
-            PlanarStage &st = sm.stage[stage];
-            mbar_arrive_expect_tx(&sm.full[stage], (y_bytes + (gray ? 0u : 2 * c_bytes)) * (uint32_t)nr + (uint32_t)sizeof(GroupRec));
-            for (int k = 0; k < nr; k++) {
-                const int y = y0 + k, cy = sub_y ? y >> 1 : y;
-                tma_load_1d(&st.y[k][0], J.src.p0 + (size_t)y * J.src.s0 + cx0, y_bytes, &sm.full[stage]);
-                if (gray) continue;
-                tma_load_1d(&st.cb[k][0], J.src.p1 + (size_t)cy * J.src.s1 + ccx0, c_bytes, &sm.full[stage]);
-                tma_load_1d(&st.cr[k][0], J.src.p2 + (size_t)cy * J.src.s2 + ccx0, c_bytes, &sm.full[stage]);
+            auto &st = sm.stage[stage];
+            if constexpr (NRGBA) {
+                mbar_arrive_expect_tx(&sm.full[stage], y_bytes * (uint32_t)nr + (uint32_t)sizeof(GroupRec));
+                for (int k = 0; k < nr; k++)
+                    tma_load_1d(&st.rows[k][0], J.src.p0 + (size_t)(y0 + k) * J.src.s0 + (size_t)cx0 * 4, y_bytes, &sm.full[stage]);
+            } else {
+                mbar_arrive_expect_tx(&sm.full[stage], (y_bytes + (gray ? 0u : 2 * c_bytes)) * (uint32_t)nr + (uint32_t)sizeof(GroupRec));
+                for (int k = 0; k < nr; k++) {
+                    const int y = y0 + k, cy = sub_y ? y >> 1 : y;
+                    tma_load_1d(&st.y[k][0], J.src.p0 + (size_t)y * J.src.s0 + cx0, y_bytes, &sm.full[stage]);
+                    if (gray) continue;
+                    tma_load_1d(&st.cb[k][0], J.src.p1 + (size_t)cy * J.src.s1 + ccx0, c_bytes, &sm.full[stage]);
+                    tma_load_1d(&st.cr[k][0], J.src.p2 + (size_t)cy * J.src.s2 + ccx0, c_bytes, &sm.full[stage]);
+                }
             }
             tma_load_1d(&st.rec[0], grec + (size_t)group * sizeof(GroupRec), (uint32_t)sizeof(GroupRec), &sm.full[stage]);
         };
@@ -1528,11 +1553,13 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
     }
 
     // ===== V warps =====
-    VAcc<false> S;
+    VAcc<NRGBA> S;
 #pragma unroll
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < 2; k++) {
 #pragma unroll
         for (int i = 0; i < 6; i++) S.rgb[k][i] = make_float2(0.f, 0.f);
+        if constexpr (NRGBA) S.al[k][0] = S.al[k][1] = make_float2(0.f, 0.f);
+    }
     const bool local = sm.xi[0].local != 0;
     const bool two_stage = J.t[0].two_stage != 0;
     const int pslot = local ? tid : slot;
@@ -1540,36 +1567,53 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
     uint32_t rph = 0;
     for (int g = 0; g < ngroups; g++) {
         mbar_wait(&sm.full[rs], rph);
-        const PlanarStage &stg = sm.stage[rs];
+        const auto &stg = sm.stage[rs];
 #pragma unroll 2
         for (int k = 0; k < STREAM_GROUP; k++) {
-            // ---- 4 pixels -> 16-bit RGB exactly as color.YCbCr.RGBA() (x/image scaleX_YCbCr*)
-            const uint32_t y4 = *reinterpret_cast<const uint32_t *>(&stg.y[k][slot * 4]);
-            uint32_t cb4 = 0x80808080u, cr4 = 0x80808080u; // chroma byte of each of the 4 pixels
-            if (gray) {
-            } else if (sub_x) {
-                const uint32_t b2 = *reinterpret_cast<const uint16_t *>(&stg.cb[k][slot * 2]);
-                const uint32_t r2 = *reinterpret_cast<const uint16_t *>(&stg.cr[k][slot * 2]);
-                cb4 = __byte_perm(b2, 0, 0x1100);
-                cr4 = __byte_perm(r2, 0, 0x1100);
-            } else {
-                cb4 = *reinterpret_cast<const uint32_t *>(&stg.cb[k][slot * 4]);
-                cr4 = *reinterpret_cast<const uint32_t *>(&stg.cr[k][slot * 4]);
-            }
             uint32_t c16[12];
+            [[maybe_unused]] uint32_t a16[4];
+            if constexpr (NRGBA) {
+                // ---- 4 straight-alpha pixels -> 16-bit premultiplied exactly as x/image scaleX_NRGBA
+                const uint4 q4 = stg.rows[k][slot]; // (rows past the band's end: stale ring contents, weight 0)
+                const uint32_t q[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int yy1 = (int)((y4 >> (8 * j)) & 0xff) * 0x10101;
-                const int cb1 = (int)((cb4 >> (8 * j)) & 0xff) - 128;
-                const int cr1 = (int)((cr4 >> (8 * j)) & 0xff) - 128;
-                uint32_t r = clamp16((yy1 + 91881 * cr1) >> 8);
-                uint32_t gg = clamp16((yy1 - 22554 * cb1 - 46802 * cr1) >> 8);
-                uint32_t b = clamp16((yy1 + 116130 * cb1) >> 8);
-                if (gray) r = gg = b = ((y4 >> (8 * j)) & 0xff) * 0x101u; // scaleX_Gray: y16 = Y * 0x101
-                if (two_stage) { // the 1:1 crop pass stored uint8(c16 >> 8); scaleX_RGBA re-expands it
-                    r = (r >> 8) * 0x101u; gg = (gg >> 8) * 0x101u; b = (b >> 8) * 0x101u;
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t pa = (q[j] >> 24) * 0x101u;
+                    uint32_t r = div255((q[j] & 0xff) * pa), gg = div255(((q[j] >> 8) & 0xff) * pa), b = div255(((q[j] >> 16) & 0xff) * pa);
+                    uint32_t a = pa;
+                    if (two_stage) { // the 1:1 crop pass stored uint8(c16 >> 8) into an *image.RGBA; scaleX_RGBA re-expands it
+                        r = (r >> 8) * 0x101u; gg = (gg >> 8) * 0x101u; b = (b >> 8) * 0x101u; a = (a >> 8) * 0x101u;
+                    }
+                    c16[3 * j] = r; c16[3 * j + 1] = gg; c16[3 * j + 2] = b; a16[j] = a;
                 }
-                c16[3 * j] = r; c16[3 * j + 1] = gg; c16[3 * j + 2] = b;
+            } else {
+                // ---- 4 pixels -> 16-bit RGB exactly as color.YCbCr.RGBA() (x/image scaleX_YCbCr*)
+                const uint32_t y4 = *reinterpret_cast<const uint32_t *>(&stg.y[k][slot * 4]);
+                uint32_t cb4 = 0x80808080u, cr4 = 0x80808080u; // chroma byte of each of the 4 pixels
+                if (gray) {
+                } else if (sub_x) {
+                    const uint32_t b2 = *reinterpret_cast<const uint16_t *>(&stg.cb[k][slot * 2]);
+                    const uint32_t r2 = *reinterpret_cast<const uint16_t *>(&stg.cr[k][slot * 2]);
+                    cb4 = __byte_perm(b2, 0, 0x1100);
+                    cr4 = __byte_perm(r2, 0, 0x1100);
+                } else {
+                    cb4 = *reinterpret_cast<const uint32_t *>(&stg.cb[k][slot * 4]);
+                    cr4 = *reinterpret_cast<const uint32_t *>(&stg.cr[k][slot * 4]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int yy1 = (int)((y4 >> (8 * j)) & 0xff) * 0x10101;
+                    const int cb1 = (int)((cb4 >> (8 * j)) & 0xff) - 128;
+                    const int cr1 = (int)((cr4 >> (8 * j)) & 0xff) - 128;
+                    uint32_t r = clamp16((yy1 + 91881 * cr1) >> 8);
+                    uint32_t gg = clamp16((yy1 - 22554 * cb1 - 46802 * cr1) >> 8);
+                    uint32_t b = clamp16((yy1 + 116130 * cb1) >> 8);
+                    if (gray) r = gg = b = ((y4 >> (8 * j)) & 0xff) * 0x101u; // scaleX_Gray: y16 = Y * 0x101
+                    if (two_stage) { // the 1:1 crop pass stored uint8(c16 >> 8); scaleX_RGBA re-expands it
+                        r = (r >> 8) * 0x101u; gg = (gg >> 8) * 0x101u; b = (b >> 8) * 0x101u;
+                    }
+                    c16[3 * j] = r; c16[3 * j + 1] = gg; c16[3 * j + 2] = b;
+                }
             }
             float2 vp[6];
 #pragma unroll
@@ -1581,9 +1625,17 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
                 S.rgb[0][i] = __ffma2_rn(vp[i], w00, S.rgb[0][i]);
                 S.rgb[1][i] = __ffma2_rn(vp[i], w11, S.rgb[1][i]);
             }
+            if constexpr (NRGBA) {
+                const float2 va[2] = {u16x2_f32(a16[0], a16[1]), u16x2_f32(a16[2], a16[3])};
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    S.al[0][i] = __ffma2_rn(va[i], w00, S.al[0][i]);
+                    S.al[1][i] = __ffma2_rn(va[i], w11, S.al[1][i]);
+                }
+            }
             const int e = stg.rec[0].emit[k];
             if (e >= 0) { // CTA-uniform
-                park_emit<false>(S, e, r, sm.xbuf[0], pslot);
+                park_emit<NRGBA>(S, e, r, sm.xbuf[0], pslot);
                 if (local) __syncwarp(); else vwarps_bar();
                 xcached(sm, 0, e >> 1, tid, fix);
                 if (local) __syncwarp(); else vwarps_bar();
@@ -1595,18 +1647,24 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
     }
 }
 
-cudaError_t launch_stream_planar(const StreamJob *jobs, const StreamItem *items, int n_items, FixList fix, cudaStream_t st)
+template <bool NRGBA>
+static cudaError_t launch_stream_planar_t(const StreamJob *jobs, const StreamItem *items, int n_items, FixList fix, cudaStream_t st)
 {
-    if (n_items <= 0) return cudaSuccess;
-    using Smem = PlanarSmem<PLANAR_STAGES>;
+    using Smem = PlanarSmem<NRGBA, PLANAR_STAGES>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_stream_planar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        cudaError_t e = cudaFuncSetAttribute(k_stream_planar<NRGBA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_stream_planar<<<n_items, STREAM_CTA, sizeof(Smem), st>>>(jobs, items, fix);
+    k_stream_planar<NRGBA><<<n_items, STREAM_CTA, sizeof(Smem), st>>>(jobs, items, fix);
     return cudaGetLastError();
+}
+
+cudaError_t launch_stream_planar(const StreamJob *jobs, const StreamItem *items, int n_items, bool nrgba, FixList fix, cudaStream_t st)
+{
+    if (n_items <= 0) return cudaSuccess;
+    return nrgba ? launch_stream_planar_t<true>(jobs, items, n_items, fix, st) : launch_stream_planar_t<false>(jobs, items, n_items, fix, st);
 }
 
 int stream_smem_bytes() { return (int)sizeof(StreamCfg<2>::Smem); }
@@ -1615,7 +1673,8 @@ static_assert(sizeof(StreamCfg<1, 4>::Smem) + 1024 <= 227 * 1024 / STREAM_CTAS_F
 static_assert(sizeof(StreamCfg<1, 0>::Smem) + 1024 <= 227 * 1024 / STREAM_CTAS_1T, "k_stream<1>: shared memory limits occupancy");
 static_assert(sizeof(StreamCfg<2, 0>::Smem) + 1024 <= 227 * 1024 / STREAM_CTAS_2T, "k_stream<2>: shared memory limits occupancy");
 static_assert(sizeof(StreamCfg<2, 3>::Smem) + 1024 <= 227 * 1024 / STREAM_CTAS_FAST2, "lean fused k_stream: shared memory limits occupancy");
-static_assert(sizeof(PlanarSmem<PLANAR_STAGES>) + 1024 <= 227 * 1024 / PLANAR_CTAS, "k_stream_planar: shared memory limits occupancy");
+static_assert(sizeof(PlanarSmem<false, PLANAR_STAGES>) + 1024 <= 227 * 1024 / PLANAR_CTAS, "k_stream_planar: shared memory limits occupancy");
+static_assert(sizeof(PlanarSmem<true, PLANAR_STAGES>) + 1024 <= 227 * 1024 / NRGBA_CTAS, "k_stream_planar<NRGBA>: shared memory limits occupancy");
 
 template <int NT, bool WM, int LEAN>
 static cudaError_t launch_stream_t(const StreamJob *jobs, const StreamItem *items, int n, FixList fix, cudaStream_t st)

@@ -107,3 +107,27 @@ def test_gray_streams_and_is_bit_exact(engines, oracle, w, h):
     R = oracle.Raster.gray(g)
     assert np.array_equal(out[0], oracle.resize_image(R, nw, nh))
     assert np.array_equal(out[1], oracle.crop_and_resize(R, 200))
+
+
+@pytest.mark.parametrize("w,h,alpha", [(4000, 3000, "raw"), (3001, 2003, "raw"), (1920, 1080, "edges"), (640, 480, "raw")])
+def test_nrgba_streams_and_is_bit_exact(engines, oracle, w, h, alpha):
+    """*image.NRGBA (a PNG with an alpha channel): resize + crop thumbnail run on the 16-bit-sample streaming
+    kernel (no whole-image fp64 fallback) and equal the oracle's per-tap integer premultiply
+    (x/image scaleX_NRGBA: a16 = A * 0x101, c16 = C * a16 / 0xff)."""
+    a = rgba_random(w, h, 31, "raw")
+    if alpha == "edges":  # mostly opaque or transparent, as real cut-outs are
+        m = np.random.default_rng(7).integers(0, 8, (h, w))
+        a[..., 3] = np.where(m < 3, 0, np.where(m < 7, 255, a[..., 3]))
+    e = engines(ip.PRECISION_EXACT, lane_device_bytes=2 << 30)
+    f0 = e.stats()["exact_fallbacks"]
+    nw, nh = ip.keep_aspect_dims(w, h, 1024, 768)
+    cx, cy, cs = ip.crop_square(w, h)
+    ops = [ip.OpSpec.thumb_crop((cx, cy, cs, cs), 200)]
+    if nh <= h:  # (a vertical upscale does not stream: whole-image fp64, tested in test_gpu_parity)
+        ops.insert(0, ip.OpSpec.resize(nw, nh))
+    out = e.run(ip.Image.from_rgba(a, ip.NRGBA8), ops)
+    assert e.stats()["exact_fallbacks"] == f0
+    R = oracle.Raster.rgba(a, oracle.NRGBA8)
+    if nh <= h:
+        assert np.array_equal(out[0], oracle.resize_image(R, nw, nh))
+    assert np.array_equal(out[-1], oracle.crop_and_resize(R, 200))

@@ -26,14 +26,14 @@ def main():
     ap.add_argument("--h", type=int, default=3000)
     ap.add_argument("--opaque-hint", type=int, default=0)
     ap.add_argument("--fuse", type=int, default=0)
-    ap.add_argument("--layout", default="rgba", choices=["rgba", "ycbcr420", "ycbcr444"])
+    ap.add_argument("--layout", default="rgba", choices=["rgba", "nrgba", "ycbcr420", "ycbcr444"])
     a = ap.parse_args()
     import torch
     dev = torch.device("cuda", 0)
     W, H = a.w, a.h
     srcs = []
     g = torch.Generator(device=dev)
-    planar = a.layout != "rgba"
+    planar = a.layout not in ("rgba", "nrgba")
     cw, ch = ((W + 1) // 2, (H + 1) // 2) if a.layout == "ycbcr420" else (W, H)
     for i in range(a.images):
         g.manual_seed(1000 + i)
@@ -43,7 +43,8 @@ def main():
                          torch.randint(0, 256, (ch, cw), dtype=torch.uint8, device=dev, generator=g)))
             continue
         t = torch.randint(0, 256, (H, W, 4), dtype=torch.uint8, device=dev, generator=g)
-        t[..., 3] = 255
+        if a.layout == "rgba":
+            t[..., 3] = 255
         srcs.append(t)
     nw, nh = ip.keep_aspect_dims(W, H, 1024, 768)
     cx, cy, cs = ip.crop_square(W, H)
@@ -71,7 +72,8 @@ def main():
                 lay = ip.YCBCR420 if a.layout == "ycbcr420" else ip.YCBCR444
                 img = ip.Image.on_device(lay, W, H, [p.data_ptr() for p in srcs[i]], [W, cw, cw], opaque_hint=True)
             else:
-                img = ip.Image.on_device(ip.RGBA8, W, H, [srcs[i].data_ptr()], [W * 4], opaque_hint=bool(a.opaque_hint))
+                img = ip.Image.on_device(ip.NRGBA8 if a.layout == "nrgba" else ip.RGBA8, W, H, [srcs[i].data_ptr()], [W * 4],
+                                         opaque_hint=bool(a.opaque_hint))
             tk.append(eng.submit(img, ops, device=0))
         for t in tk:
             eng.wait(t)
