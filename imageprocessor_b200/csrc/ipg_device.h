@@ -135,6 +135,12 @@ struct WatermarkD {
 #ifndef IPG_CTAS_FAST2
 #define IPG_CTAS_FAST2 3
 #endif
+#ifndef IPG_CTAS_INL
+#define IPG_CTAS_INL 5
+#endif
+#ifndef IPG_STAGES_INL
+#define IPG_STAGES_INL 3
+#endif
 #ifndef IPG_STAGES_FAST2
 #define IPG_STAGES_FAST2 3
 #endif
@@ -160,6 +166,7 @@ enum {
     STREAM_STAGES_1T = IPG_STAGES_1T, STREAM_CTAS_1T = IPG_CTAS_1T,   // ... otherwise
     STREAM_STAGES_FAST = IPG_STAGES_FAST, STREAM_CTAS_FAST = IPG_CTAS_FAST, // the lean single-target instantiations
     STREAM_STAGES_FAST2 = IPG_STAGES_FAST2, STREAM_CTAS_FAST2 = IPG_CTAS_FAST2, // the lean local + wide instantiation
+    STREAM_STAGES_INL = IPG_STAGES_INL, STREAM_CTAS_INL = IPG_CTAS_INL,         // the lean single-target instantiations without a producer warp
 };
 
 struct StreamJob {

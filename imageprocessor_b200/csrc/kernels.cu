@@ -720,11 +720,28 @@ template <int NT, int STAGES> struct __align__(128) StreamSmem {
     uint64_t full[STAGES];                       // TMA completion of a stage
     uint64_t empty[STAGES];                      // the 4 V warps are done with a stage
     XInfo xi[2];                                 // per target; parts = tile_parts of this CTA's tile
+    // what a refill / watermark store needs, once per CTA (the lanes that drive the ring read it from here)
+    const uint8_t *ring_src, *ring_rec;          // first source row of the band at the tile's first column; the band's records
+    uint8_t *ring_wm;                            // watermark destination of that row and column
+    int32_t ring_wm_stride;
+    uint32_t ring_rec_bytes;
+    uint32_t done[STAGES];                       // no-producer-warp form: V warps done with the stage (the 4th one refills it)
 };
+#ifndef IPG_INLINE_PRODUCER
+#define IPG_INLINE_PRODUCER 0
+#endif
 template <int NT, int LEAN = 0> struct StreamCfg {
     static constexpr bool FAST = LEAN != 0;
-    static constexpr int STAGES = LEAN == 3 ? STREAM_STAGES_FAST2 : FAST ? STREAM_STAGES_FAST : NT == 2 ? STREAM_STAGES_2T : STREAM_STAGES_1T;
-    static constexpr int CTAS_PER_SM = LEAN == 3 ? STREAM_CTAS_FAST2 : FAST ? STREAM_CTAS_FAST : NT == 2 ? STREAM_CTAS_2T : STREAM_CTAS_1T;
+    // IPG_INLINE_PRODUCER=1 builds the lean single-target instantiations without a producer warp: lane 0 of V warp
+    // (g mod 4) stores group g when it lands and the last V warp to finish a group refills its stage, so a CTA is 4
+    // warps and 5 CTAs fit an SM at the same 96 registers (20 V warps per SM instead of 16, 3 ring stages).
+    // Parity-green, but measured SLOWER (17.8 / 32.2 us per 12 MP image for resize / all three ops against
+    // 15.1 / 24.6 with the producer warp): the refill then waits for the slowest warp's lane to get to it and
+    // stalls that warp, and the ring is one stage shallower.  Kept as a tested option, off by default.
+    static constexpr bool INLINE_PROD = IPG_INLINE_PRODUCER != 0 && (LEAN == 1 || LEAN == 2 || LEAN == 4);
+    static constexpr int THREADS = INLINE_PROD ? (int)STREAM_THREADS : (int)STREAM_CTA;
+    static constexpr int STAGES = INLINE_PROD ? STREAM_STAGES_INL : LEAN == 3 ? STREAM_STAGES_FAST2 : FAST ? STREAM_STAGES_FAST : NT == 2 ? STREAM_STAGES_2T : STREAM_STAGES_1T;
+    static constexpr int CTAS_PER_SM = INLINE_PROD ? STREAM_CTAS_INL : LEAN == 3 ? STREAM_CTAS_FAST2 : FAST ? STREAM_CTAS_FAST : NT == 2 ? STREAM_CTAS_2T : STREAM_CTAS_1T;
     using Smem = StreamSmem<NT, STAGES>;
 };
 
@@ -1197,7 +1214,7 @@ __device__ __forceinline__ void v_rows(VAcc<ALPHA> *S, const StreamJob &J, const
 // pixel raises the job's redo flag and the general instantiation, launched right after over the same
 // items, redoes exactly the flagged jobs (it exits at once for the others).
 template <int NT, bool WM, int LEAN>
-__global__ void __launch_bounds__(STREAM_CTA, (StreamCfg<NT, LEAN>::CTAS_PER_SM))
+__global__ void __launch_bounds__((StreamCfg<NT, LEAN>::THREADS), (StreamCfg<NT, LEAN>::CTAS_PER_SM))
 k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ items, FixList fix)
 {
     // LEAN 1: one local target (lane-per-output pass inline); 2: one wide target (split pass);
@@ -1206,6 +1223,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     constexpr bool FAST = LEAN != 0;
     static_assert(!FAST || (LEAN == 3 ? NT == 2 : NT == 1), "lean instantiations: one target, or local + wide");
     constexpr int STAGES = StreamCfg<NT, LEAN>::STAGES;
+    constexpr bool INLINE = StreamCfg<NT, LEAN>::INLINE_PROD;
     using Smem = typename StreamCfg<NT, LEAN>::Smem;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -1236,8 +1254,14 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&sm.full[s], 1);
             mbar_init(&sm.empty[s], STREAM_THREADS / 32);
+            sm.done[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sm.ring_src = J.src.p0 + (size_t)ys0 * stride + (size_t)cx0 * 4;
+        sm.ring_rec = (const uint8_t *)(J.grec + (size_t)__ldg(J.band_grec_off + band) * (size_t)J.n_targets);
+        sm.ring_rec_bytes = (uint32_t)(NT > 0 ? J.n_targets * (int)sizeof(GroupRec) : 0);
+        sm.ring_wm = has_wm ? J.wm.dst + (size_t)ys0 * J.wm.dst_stride + (size_t)cx0 * 4 : nullptr;
+        sm.ring_wm_stride = has_wm ? J.wm.dst_stride : 0;
     }
     // slab columns past the image edge are never written by TMA: park opaque black there
     // so they neither look transparent nor feed anything (no output taps them)
@@ -1264,48 +1288,58 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     }
     __syncthreads();
 
-    if (warp == STREAM_THREADS / 32) {
-        // ===== producer: one lane drives the ring =====
-        if ((tid & 31) != 0) return;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const uint8_t *gsrc = J.src.p0 + (size_t)ys0 * stride + (size_t)cx0 * 4;
-        const uint8_t *grec = (const uint8_t *)(J.grec + (size_t)__ldg(J.band_grec_off + band) * (size_t)J.n_targets);
-        const uint32_t rec_bytes = (uint32_t)(NT > 0 ? J.n_targets * (int)sizeof(GroupRec) : 0);
-        uint8_t *wdst = has_wm ? J.wm.dst + (size_t)ys0 * J.wm.dst_stride + (size_t)cx0 * 4 : nullptr;
-        const int wm_stride = has_wm ? J.wm.dst_stride : 0;
-        auto refill = [&](int group, int stage) {
-            const int nr = min(STREAM_GROUP, yend - ys0 - group * STREAM_GROUP);
-            StreamStage &st = sm.stage[stage];
-            mbar_arrive_expect_tx(&sm.full[stage], row_bytes * (uint32_t)nr + rec_bytes);
-            const uint8_t *g = gsrc + (size_t)group * STREAM_GROUP * stride;
-            for (int k = 0; k < nr; k++, g += stride) tma_load_1d(&st.rows[k][0], g, row_bytes, &sm.full[stage]);
-            if (rec_bytes) tma_load_1d(&st.rec[0], grec + (size_t)group * rec_bytes, rec_bytes, &sm.full[stage]);
-        };
-        for (int g = 0; g < min(STAGES, ngroups); g++) refill(g, g); // prologue: fill the ring
-        int s = 0, sp = 0;        // stage of group g / of group g-1
-        uint32_t ph = 0, php = 0; // their phases
-        for (int g = 0; g < ngroups; g++) {
-            if (wm_tma) {
-                const int nw = min(STREAM_GROUP, ys1 - ys0 - g * STREAM_GROUP); // rows of this group the band owns
-                if (nw > 0) {
-                    mbar_wait(&sm.full[s], ph);
-                    uint8_t *d = wdst + (size_t)g * STREAM_GROUP * wm_stride;
-                    for (int k = 0; k < nw; k++, d += wm_stride) tma_store_1d(d, &sm.stage[s].rows[k][0], wm_bytes);
-                }
-                tma_store_commit(); // one (possibly empty) bulk group per ring group keeps the wait count uniform
-            }
-            if (g >= 1) {
-                if (g - 1 + STAGES < ngroups) {
-                    mbar_wait(&sm.empty[sp], php);            // V warps are done with group g-1
-                    if (wm_tma) tma_store_wait_read<1>();     // ... and so is its store (all but group g's)
-                    refill(g - 1 + STAGES, sp);
-                }
-                if (++sp == STAGES) { sp = 0; php ^= 1; }
-            }
-            if (++s == STAGES) { s = 0; ph ^= 1; }
+    // one ring stage <- one group of source rows + its records, under one mbarrier phase
+    auto refill = [&](int group, int stage) {
+        const uint32_t rec_bytes = sm.ring_rec_bytes;
+        const int nr = min(STREAM_GROUP, yend - ys0 - group * STREAM_GROUP);
+        StreamStage &st = sm.stage[stage];
+        mbar_arrive_expect_tx(&sm.full[stage], row_bytes * (uint32_t)nr + rec_bytes);
+        const uint8_t *g = sm.ring_src + (size_t)group * STREAM_GROUP * stride;
+        for (int k = 0; k < nr; k++, g += stride) tma_load_1d(&st.rows[k][0], g, row_bytes, &sm.full[stage]);
+        if (rec_bytes) tma_load_1d(&st.rec[0], sm.ring_rec + (size_t)group * rec_bytes, rec_bytes, &sm.full[stage]);
+    };
+    // the watermark copy of a landed group: the owned columns of the rows the band owns, ring -> destination
+    auto store_group = [&](int group, int stage) {
+        const int nw = min(STREAM_GROUP, ys1 - ys0 - group * STREAM_GROUP);
+        if (nw > 0) {
+            const int wm_stride = sm.ring_wm_stride;
+            uint8_t *d = sm.ring_wm + (size_t)group * STREAM_GROUP * wm_stride;
+            for (int k = 0; k < nw; k++, d += wm_stride) tma_store_1d(d, &sm.stage[stage].rows[k][0], wm_bytes);
         }
-        if (wm_tma) tma_store_wait_all(); // shared memory must outlive the reads
-        return;
+        tma_store_commit(); // one (possibly empty) bulk group per ring group keeps the wait counts uniform
+    };
+    if constexpr (!INLINE) {
+        if (warp == STREAM_THREADS / 32) {
+            // ===== producer: one lane drives the ring =====
+            if ((tid & 31) != 0) return;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int g = 0; g < min(STAGES, ngroups); g++) refill(g, g); // prologue: fill the ring
+            int s = 0, sp = 0;        // stage of group g / of group g-1
+            uint32_t ph = 0, php = 0; // their phases
+            for (int g = 0; g < ngroups; g++) {
+                if (wm_tma) {
+                    if (ys1 - ys0 - g * STREAM_GROUP > 0) mbar_wait(&sm.full[s], ph);
+                    store_group(g, s);
+                }
+                if (g >= 1) {
+                    if (g - 1 + STAGES < ngroups) {
+                        mbar_wait(&sm.empty[sp], php);            // V warps are done with group g-1
+                        if (wm_tma) tma_store_wait_read<1>();     // ... and so is its store (all but group g's)
+                        refill(g - 1 + STAGES, sp);
+                    }
+                    if (++sp == STAGES) { sp = 0; php ^= 1; }
+                }
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            if (wm_tma) tma_store_wait_all(); // shared memory must outlive the reads
+            return;
+        }
+    } else {
+        // no producer warp: lane 0 of V warp (g mod 4) stores group g when it lands; the last V warp to finish a
+        // group refills its stage (nobody ever waits for a slower warp); here the ring is filled for the first time
+        if ((tid & 31) == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (tid == 0)
+            for (int g = 0; g < min(STAGES, ngroups); g++) refill(g, g);
     }
 
     // ===== V warps: vertical pass, and the horizontal pass of every row they complete =====
@@ -1354,7 +1388,23 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     uint32_t rph = 0;
     auto advance = [&]() {
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&sm.empty[rs]);
+        if ((tid & 31) == 0) {
+            if constexpr (INLINE) {
+                // the lane that stored this group lets the copy finish reading the stage before it counts as done (the
+                // copy was issued a whole group ago)
+                if (wm_tma && (g & 3) == warp) tma_store_wait_read<0>();
+            }
+            mbar_arrive(&sm.empty[rs]);
+            if constexpr (INLINE) {
+                if (atomicAdd(&sm.done[rs], 1u) == STREAM_THREADS / 32 - 1) { // the last of the four: refill the stage
+                    sm.done[rs] = 0;
+                    if (g + STAGES < ngroups) {
+                        mbar_wait(&sm.empty[rs], rph); // complete by now: taken for its acquire, as the producer warp does
+                        refill(g + STAGES, rs);
+                    }
+                }
+            }
+        }
         if (++rs == STAGES) { rs = 0; rph ^= 1; }
     };
 
@@ -1367,6 +1417,9 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     const bool check = NT > 0 && (!FAST || J.redo_flag != nullptr); // read once: the asm memory clobbers would reload it per group
     for (; g < ngroups; g++) {
         mbar_wait(&sm.full[rs], rph);
+        if constexpr (INLINE) {
+            if (wm_tma && (g & 3) == warp && (tid & 31) == 0) store_group(g, rs);
+        }
         const StreamStage &stg = sm.stage[rs];
         const int nr = yend - ys0 - g * STREAM_GROUP;
         const bool folded = FOLD && nr >= STREAM_GROUP; // a partial last group holds stale rows: scan it the guarded way
@@ -1392,6 +1445,9 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
             if (check && folded && __any_sync(0xffffffffu, opq < 0xff000000u) && (tid & 31) == 0) atomicExch(J.redo_flag, 1);
         } else              v_rows<NT, WM, false>(S, J, stg, sm, C, ys0 + g * STREAM_GROUP, nr, fix);
         advance();
+    }
+    if constexpr (INLINE) {
+        if (wm_tma && (tid & 31) == 0) tma_store_wait_all(); // shared memory must outlive this lane's stores
     }
     if constexpr (FAST) return;
     if constexpr (NT > 0) {
@@ -1669,7 +1725,7 @@ cudaError_t launch_stream_planar(const StreamJob *jobs, const StreamItem *items,
 
 int stream_smem_bytes() { return (int)sizeof(StreamCfg<2>::Smem); }
 // shared memory must not be what limits the residency the launch bounds ask for (227 KB per SM, 1 KB per CTA reserved)
-static_assert(sizeof(StreamCfg<1, 4>::Smem) + 1024 <= 227 * 1024 / STREAM_CTAS_FAST, "lean k_stream: shared memory limits occupancy");
+static_assert(sizeof(StreamCfg<1, 4>::Smem) + 1024 <= 227 * 1024 / StreamCfg<1, 4>::CTAS_PER_SM, "lean k_stream: shared memory limits occupancy");
 static_assert(sizeof(StreamCfg<1, 0>::Smem) + 1024 <= 227 * 1024 / STREAM_CTAS_1T, "k_stream<1>: shared memory limits occupancy");
 static_assert(sizeof(StreamCfg<2, 0>::Smem) + 1024 <= 227 * 1024 / STREAM_CTAS_2T, "k_stream<2>: shared memory limits occupancy");
 static_assert(sizeof(StreamCfg<2, 3>::Smem) + 1024 <= 227 * 1024 / STREAM_CTAS_FAST2, "lean fused k_stream: shared memory limits occupancy");
@@ -1687,7 +1743,7 @@ static cudaError_t launch_stream_t(const StreamJob *jobs, const StreamItem *item
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_stream<NT, WM, LEAN><<<n, STREAM_CTA, sizeof(Smem), st>>>(jobs, items, fix);
+    k_stream<NT, WM, LEAN><<<n, StreamCfg<NT, LEAN>::THREADS, sizeof(Smem), st>>>(jobs, items, fix);
     return cudaGetLastError();
 }
 
