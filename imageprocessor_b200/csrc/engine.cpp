@@ -291,6 +291,7 @@ struct Ctx {
     // pass and of the issue-bound thumbnail pass share the SMs (26.2 vs 28.4 us per 12 MP image).  IPG_MERGE_LEAN=0
     // launches them separately (k_stream<1,WM,1> and <1,WM,2> on two streams), which is how bench.py times each pass alone.
     bool merge_lean = true;
+    uint32_t fix_capacity = 0;     // IPG_FIX_CAPACITY: fix-list entries per batch (0: sized from the batch); tests force the overflow paths with it
     bool overlap_streams = true; // IPG_NO_OVERLAP=1: lean and general k_stream launches back to back (per-kernel timing)
     // stats
     std::atomic<uint64_t> s_done{0}, s_batches{0}, s_kernels{0}, s_h2d{0}, s_d2h{0}, s_fix{0}, s_fallback{0}, s_staged{0};
@@ -759,6 +760,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     FixList fix{nullptr, nullptr, 0};
     if (!fixjobs.empty()) {
         uint64_t cap = std::min<uint64_t>(fix_px / 8 + 4096, 8u << 20);
+        if (c.fix_capacity) cap = c.fix_capacity;
         uint8_t *cnt = arena.take(256);
         uint8_t *ent = arena.take((size_t)cap * sizeof(FixEntry));
         if (!cnt || !ent) throw std::runtime_error("device arena exhausted (fix list)");
@@ -1294,6 +1296,7 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
         c->trace = getenv("IPG_TRACE") && atoi(getenv("IPG_TRACE")) != 0;
         c->fuse_targets = (k.fuse_targets >= 1 && k.fuse_targets <= 3) ? k.fuse_targets : 1;
         if (getenv("IPG_MERGE_LEAN")) c->merge_lean = atoi(getenv("IPG_MERGE_LEAN")) != 0;
+        if (getenv("IPG_FIX_CAPACITY")) c->fix_capacity = (uint32_t)std::max(1, atoi(getenv("IPG_FIX_CAPACITY")));
         c->overlap_streams = !(getenv("IPG_NO_OVERLAP") && atoi(getenv("IPG_NO_OVERLAP")) != 0);
         if (getenv("IPG_FUSE_TARGETS")) c->fuse_targets = std::min(3, std::max(1, atoi(getenv("IPG_FUSE_TARGETS"))));
         std::vector<int> ids;
