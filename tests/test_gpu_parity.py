@@ -271,3 +271,31 @@ def test_fix_list_overflow_paths(oracle, capacity, monkeypatch):
     assert n_fix == 1166       # (what the capacities above are chosen around)
     assert np.array_equal(out[0], oracle.resize_image(R, nw, nh))
     assert np.array_equal(out[1], oracle.crop_and_resize(R, 200))
+
+
+@pytest.mark.parametrize("kind", ["nrgba", "gray", "420", "422", "444", "440"])
+def test_sixteen_bit_sample_layouts_odd_sizes(engines, oracle, kind):
+    """k_stream_planar (planar YCbCr, Gray, NRGBA) over awkward geometries: widths that are not multiples of the
+    4-pixel thread granule or of the 16-byte bulk-copy granule, single rows and columns, extreme aspect ratios,
+    mild and strong downscales, the centre crop at odd offsets.  Whatever the planner cannot stream falls back to the fp64
+    kernel; the bytes must be the oracle's either way."""
+    rng = np.random.default_rng({"nrgba": 1, "gray": 2, "420": 3, "422": 4, "444": 5, "440": 6}[kind])
+    sizes = [(1, 1), (2, 3), (5, 4), (17, 2048), (2048, 17), (333, 222), (1001, 999), (1280, 960), (1919, 1081), (2500, 64)]
+    e = engines(ip.PRECISION_EXACT)
+    for w, h in sizes:
+        if kind == "nrgba":
+            a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+            img, R = ip.Image.from_rgba(a, ip.NRGBA8), oracle.Raster.rgba(a, oracle.NRGBA8)
+        elif kind == "gray":
+            g = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            img, R = ip.Image.from_gray(g), oracle.Raster.gray(g)
+        else:
+            lay = {"420": ip.YCBCR420, "422": ip.YCBCR422, "444": ip.YCBCR444, "440": ip.YCBCR440}[kind]
+            y, cb, cr = _ycbcr(oracle, w, h, lay, int(rng.integers(1 << 30)))
+            img, R = ip.Image.from_ycbcr(y, cb, cr, lay), oracle.Raster.ycbcr(y, cb, cr, lay)
+        dw, dh = max(1, int(w / rng.uniform(1.0, 6.0))), max(1, int(h / rng.uniform(1.0, 6.0)))
+        cx, cy, cs = ip.crop_square(w, h)       # the reference's centre square (thumbnail.go:115-127)
+        size = int(rng.integers(1, 96))
+        out = e.run(img, [ip.OpSpec.resize(dw, dh), ip.OpSpec.thumb_crop((cx, cy, cs, cs), size)])
+        assert np.array_equal(out[0], oracle.resize_image(R, dw, dh)), f"{kind} resize {w}x{h} -> {dw}x{dh}"
+        assert np.array_equal(out[1], oracle.crop_and_resize(R, size)), f"{kind} thumb {w}x{h} crop {cx},{cy},{cs} -> {size}"
