@@ -291,6 +291,7 @@ struct Ctx {
     // pass and of the issue-bound thumbnail pass share the SMs (26.2 vs 28.4 us per 12 MP image).  IPG_MERGE_LEAN=0
     // launches them separately (k_stream<1,WM,1> and <1,WM,2> on two streams), which is how bench.py times each pass alone.
     bool merge_lean = true;
+    uint32_t band_cta_target = 1400;
     uint32_t fix_capacity = 0;     // IPG_FIX_CAPACITY: fix-list entries per batch (0: sized from the batch); tests force the overflow paths with it
     bool overlap_streams = true; // IPG_NO_OVERLAP=1: lean and general k_stream launches back to back (per-kernel timing)
     // stats
@@ -431,7 +432,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     // band count: aim for >= ~2 waves of CTAs over the whole batch
     size_t est_ctas = 0;
     for (auto &tp : B.tickets) est_ctas += (size_t)(tp->src.width + 479) / 480;
-    int bands_hint = (int)std::min<size_t>(32, std::max<size_t>(1, (1400 + est_ctas - 1) / std::max<size_t>(est_ctas, 1)));
+    const size_t cta_target = c.band_cta_target; // CTAs a batch should at least give (IPG_BAND_CTAS; default 1400 = ~2.4 waves of 4 x 148)
+    int bands_hint = (int)std::min<size_t>(32, std::max<size_t>(1, (cta_target + est_ctas - 1) / std::max<size_t>(est_ctas, 1)));
 
     for (auto &tp : B.tickets) {
         Ticket &t = *tp;
@@ -1296,6 +1298,7 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
         c->trace = getenv("IPG_TRACE") && atoi(getenv("IPG_TRACE")) != 0;
         c->fuse_targets = (k.fuse_targets >= 1 && k.fuse_targets <= 3) ? k.fuse_targets : 1;
         if (getenv("IPG_MERGE_LEAN")) c->merge_lean = atoi(getenv("IPG_MERGE_LEAN")) != 0;
+        if (getenv("IPG_BAND_CTAS")) c->band_cta_target = (uint32_t)std::max(1, atoi(getenv("IPG_BAND_CTAS")));
         if (getenv("IPG_FIX_CAPACITY")) c->fix_capacity = (uint32_t)std::max(1, atoi(getenv("IPG_FIX_CAPACITY")));
         c->overlap_streams = !(getenv("IPG_NO_OVERLAP") && atoi(getenv("IPG_NO_OVERLAP")) != 0);
         if (getenv("IPG_FUSE_TARGETS")) c->fuse_targets = std::min(3, std::max(1, atoi(getenv("IPG_FUSE_TARGETS"))));
