@@ -260,6 +260,47 @@ __device__ __forceinline__ void exact_pixel_thread(const FixHdr &h)
             for (int r = 0; r < FIX_TROWS; r++)
                 if (j0 + r < h.ny) fix_row_rgba(q[r], w, h.nx, h.two_stage != 0, const_alpha, h.ifx, wy[r], pr, pg, pb, pa);
         }
+    } else if (h.nx <= FIX_TMLP) {
+        // the same for the other layouts (planar YCbCr, Gray, NRGBA): two rows of converted 16-bit samples at a time
+        double w[FIX_TMLP];
+#pragma unroll
+        for (int u = 0; u < FIX_TMLP; u++) w[u] = u < h.nx ? __ldg(h.wx + u) : 0.0;
+        for (int j0 = 0; j0 < h.ny; j0 += 2) {
+            uint2 q[2][FIX_TMLP];
+            double wy[2];
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const bool rin = j0 + r < h.ny;
+                wy[r] = rin ? __ldg(h.wy + j0 + r) : 0.0;
+#pragma unroll
+                for (int u = 0; u < FIX_TMLP; u++) {
+                    uint32_t p[4] = {0u, 0u, 0u, 0u};
+                    if (rin && u < h.nx) {
+                        sample16(h.src, h.x0 + u, h.y0 + j0 + r, p);
+                        if (h.two_stage) to_cropped_rgba16(p);
+                    }
+                    q[r][u] = make_uint2(p[0] | (p[1] << 16), p[2] | (p[3] << 16));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                if (j0 + r >= h.ny) break;
+                double xr = 0, xg = 0, xb = 0, xa = 0;
+#pragma unroll
+                for (int u = 0; u < FIX_TMLP; u++) {
+                    if (u >= h.nx) break;
+                    xr = __dadd_rn(xr, __dmul_rn((double)(q[r][u].x & 0xffffu), w[u]));
+                    xg = __dadd_rn(xg, __dmul_rn((double)(q[r][u].x >> 16), w[u]));
+                    xb = __dadd_rn(xb, __dmul_rn((double)(q[r][u].y & 0xffffu), w[u]));
+                    xa = __dadd_rn(xa, __dmul_rn((double)(q[r][u].y >> 16), w[u]));
+                }
+                const double ta = const_alpha ? 1.0 : __dmul_rn(xa, h.ifx);
+                pr = __dadd_rn(pr, __dmul_rn(__dmul_rn(xr, h.ifx), wy[r]));
+                pg = __dadd_rn(pg, __dmul_rn(__dmul_rn(xg, h.ifx), wy[r]));
+                pb = __dadd_rn(pb, __dmul_rn(__dmul_rn(xb, h.ifx), wy[r]));
+                pa = __dadd_rn(pa, __dmul_rn(ta, wy[r]));
+            }
+        }
     } else
     for (int j = 0; j < h.ny; j++) {
         double xr = 0, xg = 0, xb = 0, xa = 0;
@@ -1510,7 +1551,6 @@ template <bool NRGBA, int STAGES> struct __align__(128) PlanarSmem {
 };
 enum { PLANAR_STAGES = 4, PLANAR_CTAS = 4, NRGBA_CTAS = 3 };
 
-__device__ __forceinline__ uint32_t clamp16(int v) { return (uint32_t)min(max(v, 0), 0xffff); }
 // two 16-bit samples -> fp32 pair via the 2^23 mantissa trick (exact for values < 2^23)
 __device__ __forceinline__ float2 u16x2_f32(uint32_t a, uint32_t b)
 {
@@ -1518,6 +1558,119 @@ __device__ __forceinline__ float2 u16x2_f32(uint32_t a, uint32_t b)
                       make_float2(-8388608.0f, -8388608.0f));
 }
 __device__ __forceinline__ uint32_t div255(uint32_t x) { return __umulhi(x, 0x80808081u) >> 7; } // exact for every uint32
+
+// 16-bit sample >> SH clamped to [0, 0xffff >> (SH - 8)]: color.YCbCr.RGBA()'s "(x >> 8) clamped to 16 bits" for SH = 8;
+// for the crop stage, which keeps uint8(c16 >> 8), SH = 16 gives that byte directly (the two clamps commute with the shift).
+template <int SH> __device__ __forceinline__ uint32_t ycc_chan(int v)
+{
+    return (uint32_t)min(max(v >> SH, 0), SH == 8 ? 0xffff : 0xff);
+}
+
+// The V warps' row loop of k_stream_planar.  KIND 0: one chroma sample per pixel in the row (4:4:4, 4:4:0) -- or,
+// with NRGBA, no chroma at all; 1: one per pixel pair (4:2:2, 4:2:0); 2: *image.Gray.  TWO: cropAndResize's 1:1 first
+// pass stored uint8(c16 >> 8) into an *image.RGBA and scaleX_RGBA re-expands it (byte * 0x101).
+template <bool NRGBA, int KIND, bool TWO, typename SM>
+__device__ __forceinline__ void planar_vloop(SM &sm, int ngroups, int slot, int tid, const FixList &fix)
+{
+    constexpr int STAGES = PLANAR_STAGES;
+    VAcc<NRGBA> S;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) S.rgb[k][i] = make_float2(0.f, 0.f);
+        if constexpr (NRGBA) S.al[k][0] = S.al[k][1] = make_float2(0.f, 0.f);
+    }
+    const bool local = sm.xi[0].local != 0;
+    const int pslot = local ? tid : slot;
+    int rs = 0;
+    uint32_t rph = 0;
+    for (int g = 0; g < ngroups; g++) {
+        mbar_wait(&sm.full[rs], rph);
+        const auto &stg = sm.stage[rs];
+#pragma unroll 2
+        for (int k = 0; k < STREAM_GROUP; k++) {
+            uint32_t c16[12];
+            [[maybe_unused]] uint32_t a16[4];
+            if constexpr (NRGBA) {
+                // ---- 4 straight-alpha pixels -> 16-bit premultiplied exactly as x/image scaleX_NRGBA
+                const uint4 q4 = stg.rows[k][slot]; // (rows past the band's end: stale ring contents, weight 0)
+                const uint32_t q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t pa = (q[j] >> 24) * 0x101u;
+                    uint32_t r = div255((q[j] & 0xff) * pa), gg = div255(((q[j] >> 8) & 0xff) * pa), b = div255(((q[j] >> 16) & 0xff) * pa);
+                    if constexpr (TWO) { r = (r >> 8) * 0x101u; gg = (gg >> 8) * 0x101u; b = (b >> 8) * 0x101u; }
+                    c16[3 * j] = r; c16[3 * j + 1] = gg; c16[3 * j + 2] = b;
+                    a16[j] = pa; // (pa >> 8) * 0x101 == pa: the crop stage keeps alpha as it is
+                }
+            } else if constexpr (KIND == 2) {
+                // ---- *image.Gray: scaleX_Gray feeds y16 = Y * 0x101 on all three channels; the crop stage changes nothing
+                // ((Y * 0x101 >> 8) * 0x101 == Y * 0x101)
+                const uint32_t y4 = *reinterpret_cast<const uint32_t *>(&stg.y[k][slot * 4]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) c16[3 * j] = c16[3 * j + 1] = c16[3 * j + 2] = ((y4 >> (8 * j)) & 0xff) * 0x101u;
+            } else {
+                // ---- 4 pixels -> 16-bit RGB exactly as color.YCbCr.RGBA() (x/image scaleX_YCbCr*): the chroma terms
+                // once per chroma sample, then per pixel yy1 + term, >> 8, clamp
+                constexpr int NC = KIND == 1 ? 2 : 4; // chroma samples under this thread's 4 pixels
+                constexpr int SH = TWO ? 16 : 8;
+                const uint32_t y4 = *reinterpret_cast<const uint32_t *>(&stg.y[k][slot * 4]);
+                uint32_t cb4, cr4;
+                if constexpr (KIND == 1) {
+                    cb4 = *reinterpret_cast<const uint16_t *>(&stg.cb[k][slot * 2]);
+                    cr4 = *reinterpret_cast<const uint16_t *>(&stg.cr[k][slot * 2]);
+                } else {
+                    cb4 = *reinterpret_cast<const uint32_t *>(&stg.cb[k][slot * 4]);
+                    cr4 = *reinterpret_cast<const uint32_t *>(&stg.cr[k][slot * 4]);
+                }
+                int tr[NC], tg[NC], tb[NC];
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    const int cb1 = (int)((cb4 >> (8 * c)) & 0xff) - 128, cr1 = (int)((cr4 >> (8 * c)) & 0xff) - 128;
+                    tr[c] = 91881 * cr1;
+                    tg[c] = -22554 * cb1 - 46802 * cr1;
+                    tb[c] = 116130 * cb1;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int yy1 = (int)((y4 >> (8 * j)) & 0xff) * 0x10101;
+                    const int c = KIND == 1 ? j >> 1 : j;
+                    uint32_t r = ycc_chan<SH>(yy1 + tr[c]), gg = ycc_chan<SH>(yy1 + tg[c]), b = ycc_chan<SH>(yy1 + tb[c]);
+                    if constexpr (TWO) { r *= 0x101u; gg *= 0x101u; b *= 0x101u; }
+                    c16[3 * j] = r; c16[3 * j + 1] = gg; c16[3 * j + 2] = b;
+                }
+            }
+            float2 vp[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) vp[i] = u16x2_f32(c16[2 * i], c16[2 * i + 1]);
+            const float4 r = *reinterpret_cast<const float4 *>(&stg.rec[0].row[k]);
+            const float2 w00 = make_float2(r.x, r.x), w11 = make_float2(r.y, r.y);
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                S.rgb[0][i] = __ffma2_rn(vp[i], w00, S.rgb[0][i]);
+                S.rgb[1][i] = __ffma2_rn(vp[i], w11, S.rgb[1][i]);
+            }
+            if constexpr (NRGBA) {
+                const float2 va[2] = {u16x2_f32(a16[0], a16[1]), u16x2_f32(a16[2], a16[3])};
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    S.al[0][i] = __ffma2_rn(va[i], w00, S.al[0][i]);
+                    S.al[1][i] = __ffma2_rn(va[i], w11, S.al[1][i]);
+                }
+            }
+            const int e = stg.rec[0].emit[k];
+            if (e >= 0) { // CTA-uniform
+                park_emit<NRGBA>(S, e, r, sm.xbuf[0], pslot);
+                if (local) __syncwarp(); else vwarps_bar();
+                xcached(sm, 0, e >> 1, tid, fix);
+                if (local) __syncwarp(); else vwarps_bar();
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&sm.empty[rs]);
+        if (++rs == STAGES) { rs = 0; rph ^= 1; }
+    }
+}
 
 template <bool NRGBA>
 __global__ void __launch_bounds__(STREAM_CTA, (NRGBA ? NRGBA_CTAS : PLANAR_CTAS))
@@ -1608,98 +1761,20 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
         return;
     }
 
-    // ===== V warps =====
-    VAcc<NRGBA> S;
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-#pragma unroll
-        for (int i = 0; i < 6; i++) S.rgb[k][i] = make_float2(0.f, 0.f);
-        if constexpr (NRGBA) S.al[k][0] = S.al[k][1] = make_float2(0.f, 0.f);
-    }
-    const bool local = sm.xi[0].local != 0;
+    // ===== V warps: one specialisation of the row loop per (source kind, crop stage), chosen per CTA =====
     const bool two_stage = J.t[0].two_stage != 0;
-    const int pslot = local ? tid : slot;
-    int rs = 0;
-    uint32_t rph = 0;
-    for (int g = 0; g < ngroups; g++) {
-        mbar_wait(&sm.full[rs], rph);
-        const auto &stg = sm.stage[rs];
-#pragma unroll 2
-        for (int k = 0; k < STREAM_GROUP; k++) {
-            uint32_t c16[12];
-            [[maybe_unused]] uint32_t a16[4];
-            if constexpr (NRGBA) {
-                // ---- 4 straight-alpha pixels -> 16-bit premultiplied exactly as x/image scaleX_NRGBA
-                const uint4 q4 = stg.rows[k][slot]; // (rows past the band's end: stale ring contents, weight 0)
-                const uint32_t q[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t pa = (q[j] >> 24) * 0x101u;
-                    uint32_t r = div255((q[j] & 0xff) * pa), gg = div255(((q[j] >> 8) & 0xff) * pa), b = div255(((q[j] >> 16) & 0xff) * pa);
-                    uint32_t a = pa;
-                    if (two_stage) { // the 1:1 crop pass stored uint8(c16 >> 8) into an *image.RGBA; scaleX_RGBA re-expands it
-                        r = (r >> 8) * 0x101u; gg = (gg >> 8) * 0x101u; b = (b >> 8) * 0x101u; a = (a >> 8) * 0x101u;
-                    }
-                    c16[3 * j] = r; c16[3 * j + 1] = gg; c16[3 * j + 2] = b; a16[j] = a;
-                }
-            } else {
-                // ---- 4 pixels -> 16-bit RGB exactly as color.YCbCr.RGBA() (x/image scaleX_YCbCr*)
-                const uint32_t y4 = *reinterpret_cast<const uint32_t *>(&stg.y[k][slot * 4]);
-                uint32_t cb4 = 0x80808080u, cr4 = 0x80808080u; // chroma byte of each of the 4 pixels
-                if (gray) {
-                } else if (sub_x) {
-                    const uint32_t b2 = *reinterpret_cast<const uint16_t *>(&stg.cb[k][slot * 2]);
-                    const uint32_t r2 = *reinterpret_cast<const uint16_t *>(&stg.cr[k][slot * 2]);
-                    cb4 = __byte_perm(b2, 0, 0x1100);
-                    cr4 = __byte_perm(r2, 0, 0x1100);
-                } else {
-                    cb4 = *reinterpret_cast<const uint32_t *>(&stg.cb[k][slot * 4]);
-                    cr4 = *reinterpret_cast<const uint32_t *>(&stg.cr[k][slot * 4]);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int yy1 = (int)((y4 >> (8 * j)) & 0xff) * 0x10101;
-                    const int cb1 = (int)((cb4 >> (8 * j)) & 0xff) - 128;
-                    const int cr1 = (int)((cr4 >> (8 * j)) & 0xff) - 128;
-                    uint32_t r = clamp16((yy1 + 91881 * cr1) >> 8);
-                    uint32_t gg = clamp16((yy1 - 22554 * cb1 - 46802 * cr1) >> 8);
-                    uint32_t b = clamp16((yy1 + 116130 * cb1) >> 8);
-                    if (gray) r = gg = b = ((y4 >> (8 * j)) & 0xff) * 0x101u; // scaleX_Gray: y16 = Y * 0x101
-                    if (two_stage) { // the 1:1 crop pass stored uint8(c16 >> 8); scaleX_RGBA re-expands it
-                        r = (r >> 8) * 0x101u; gg = (gg >> 8) * 0x101u; b = (b >> 8) * 0x101u;
-                    }
-                    c16[3 * j] = r; c16[3 * j + 1] = gg; c16[3 * j + 2] = b;
-                }
-            }
-            float2 vp[6];
-#pragma unroll
-            for (int i = 0; i < 6; i++) vp[i] = u16x2_f32(c16[2 * i], c16[2 * i + 1]);
-            const float4 r = *reinterpret_cast<const float4 *>(&stg.rec[0].row[k]);
-            const float2 w00 = make_float2(r.x, r.x), w11 = make_float2(r.y, r.y);
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                S.rgb[0][i] = __ffma2_rn(vp[i], w00, S.rgb[0][i]);
-                S.rgb[1][i] = __ffma2_rn(vp[i], w11, S.rgb[1][i]);
-            }
-            if constexpr (NRGBA) {
-                const float2 va[2] = {u16x2_f32(a16[0], a16[1]), u16x2_f32(a16[2], a16[3])};
-#pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    S.al[0][i] = __ffma2_rn(va[i], w00, S.al[0][i]);
-                    S.al[1][i] = __ffma2_rn(va[i], w11, S.al[1][i]);
-                }
-            }
-            const int e = stg.rec[0].emit[k];
-            if (e >= 0) { // CTA-uniform
-                park_emit<NRGBA>(S, e, r, sm.xbuf[0], pslot);
-                if (local) __syncwarp(); else vwarps_bar();
-                xcached(sm, 0, e >> 1, tid, fix);
-                if (local) __syncwarp(); else vwarps_bar();
-            }
-        }
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&sm.empty[rs]);
-        if (++rs == STAGES) { rs = 0; rph ^= 1; }
+    if constexpr (NRGBA) {
+        if (two_stage) planar_vloop<true, 0, true>(sm, ngroups, slot, tid, fix);
+        else           planar_vloop<true, 0, false>(sm, ngroups, slot, tid, fix);
+    } else if (gray) {
+        if (two_stage) planar_vloop<false, 2, true>(sm, ngroups, slot, tid, fix);
+        else           planar_vloop<false, 2, false>(sm, ngroups, slot, tid, fix);
+    } else if (sub_x) {
+        if (two_stage) planar_vloop<false, 1, true>(sm, ngroups, slot, tid, fix);
+        else           planar_vloop<false, 1, false>(sm, ngroups, slot, tid, fix);
+    } else {
+        if (two_stage) planar_vloop<false, 0, true>(sm, ngroups, slot, tid, fix);
+        else           planar_vloop<false, 0, false>(sm, ngroups, slot, tid, fix);
     }
 }
 
