@@ -35,19 +35,25 @@ extern "C" int planemu_axis(int dn, int sn, int32_t *off, int32_t *first, double
 // specs: 6 ints per target {rect_x, rect_y, rect_w, rect_h, dw, dh}.
 // flags[t]: dw*dh bytes, 1 where the kernel would queue an fp64 fix-up.
 // info: {n_tiles, n_bands, tile_w, n_items, rows_read}
-extern "C" int planemu_run(const uint8_t *src, int stride, int W, int H, int n_targets, const int *specs,
-                           const int *two_stage, uint8_t **dsts, uint8_t **flags, int bands_hint, int *info)
+// SAMPLE = uint8_t: an *image.RGBA source (k_stream: samples are bytes, the vertical weights carry the 0x101);
+// SAMPLE = uint16_t: the 16-bit premultiplied samples x/image's pass 1 reads from an NRGBA / YCbCr / Gray source
+// (k_stream_planar: the lanes convert per tap, the vertical weights are unscaled).  Four samples per pixel.
+template <typename SAMPLE>
+static int run_impl(const SAMPLE *src, int stride, int W, int H, int n_targets, const int *specs,
+                    const int *two_stage, uint8_t **dsts, uint8_t **flags, int bands_hint, int *info)
 {
+    constexpr bool WIDE = sizeof(SAMPLE) == 2;
+    constexpr int OPAQUE = WIDE ? 0xffff : 0xff;
     StreamTargetSpec sp[2];
     for (int t = 0; t < n_targets; t++)
         sp[t] = StreamTargetSpec{specs[6 * t], specs[6 * t + 1], specs[6 * t + 2], specs[6 * t + 3], specs[6 * t + 4], specs[6 * t + 5]};
-    auto g = get_stream_geom(W, H, sp, n_targets, false, bands_hint, 257.0);
+    auto g = get_stream_geom(W, H, sp, n_targets, false, bands_hint, WIDE ? 1.0 : 257.0);
     if (!g) return -1;
     long rows_read = 0;
     bool opaque_src = true; // then every column's alpha chain must equal the record's precomputed one
     for (int y = 0; y < H && opaque_src; y++)
         for (int x = 0; x < W; x++)
-            if (src[(size_t)y * stride + (size_t)x * 4 + 3] != 255) { opaque_src = false; break; }
+            if (src[(size_t)y * stride + (size_t)x * 4 + 3] != OPAQUE) { opaque_src = false; break; }
     for (const StreamItem &it : g->items) {
         const int tile = it.tile, band = it.band;
         const int cx0 = tile * g->tile_w;
@@ -74,9 +80,13 @@ extern "C" int planemu_run(const uint8_t *src, int stride, int W, int H, int n_t
                     if (ys >= yend && (r.w0 != 0.f || r.w1 != 0.f || G.emit[k] >= 0)) return -3; // padding rows must be inert
                     for (int e = 0; e < STREAM_COLS; e++) {
                         const int c = cx0 + e;
-                        uint8_t px[4] = {0, 0, 0, 255};
-                        if (c < W && ys < yend) memcpy(px, src + (size_t)ys * stride + (size_t)c * 4, 4);
-                        if (two_stage[t]) for (int q = 0; q < 3; q++) px[q] = std::min(px[q], px[3]);
+                        SAMPLE px[4] = {0, 0, 0, (SAMPLE)OPAQUE};
+                        if (c < W && ys < yend) memcpy(px, src + (size_t)ys * stride + (size_t)c * 4, 4 * sizeof(SAMPLE));
+                        if (two_stage[t]) {
+                            for (int q = 0; q < 3; q++) px[q] = std::min(px[q], px[3]);
+                            // cropAndResize's 1:1 first pass keeps uint8(c16 >> 8); scaleX_RGBA re-expands it
+                            if (WIDE) for (int q = 0; q < 4; q++) px[q] = (SAMPLE)((px[q] >> 8) * 0x101);
+                        }
                         for (int q = 0; q < 4; q++) {
                             float &a = acc[t][0][(size_t)e * 4 + q], &b = acc[t][1][(size_t)e * 4 + q];
                             a = std::fmaf((float)px[q], r.w0, a);
@@ -136,4 +146,17 @@ extern "C" int planemu_run(const uint8_t *src, int stride, int W, int H, int n_t
         info[3] = (int)g->items.size(); info[4] = (int)std::min<long>(rows_read, 2147483647L);
     }
     return 0;
+}
+
+extern "C" int planemu_run(const uint8_t *src, int stride, int W, int H, int n_targets, const int *specs,
+                           const int *two_stage, uint8_t **dsts, uint8_t **flags, int bands_hint, int *info)
+{
+    return run_impl<uint8_t>(src, stride, W, H, n_targets, specs, two_stage, dsts, flags, bands_hint, info);
+}
+
+// the same over 16-bit samples (stride in samples, 4 per pixel)
+extern "C" int planemu_run16(const uint16_t *src, int stride, int W, int H, int n_targets, const int *specs,
+                             const int *two_stage, uint8_t **dsts, uint8_t **flags, int bands_hint, int *info)
+{
+    return run_impl<uint16_t>(src, stride, W, H, n_targets, specs, two_stage, dsts, flags, bands_hint, info);
 }

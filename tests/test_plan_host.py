@@ -136,3 +136,69 @@ def test_stream_plan_random_geometries(emu, oracle):
             diff = np.abs(dsts[0].astype(int) - want.astype(int)).max(axis=2)
             assert diff[~amb].max(initial=0) == 0 and diff.max(initial=0) <= 1, f"certification broken for {spec} in {w}x{h}"
     assert accepted >= 40
+
+
+# ---- the 16-bit-sample kernels (k_stream_planar: planar YCbCr, Gray, NRGBA) ---------------------------------
+def samples16(oracle, kind, w, h, seed):
+    """A random source of the given kind as (oracle Raster, H x W x 4 uint16 samples): the 16-bit premultiplied
+    values x/image's pass 1 reads per tap (draw/impl.go scaleX_NRGBA / scaleX_Gray / scaleX_YCbCr*), in numpy."""
+    rng = np.random.default_rng(seed)
+    s = np.empty((h, w, 4), np.uint16)
+    if kind == "nrgba":
+        a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        a16 = a[..., 3].astype(np.uint32) * 0x101
+        for q in range(3):
+            s[..., q] = a[..., q].astype(np.uint32) * a16 // 0xFF
+        s[..., 3] = a16
+        return oracle.Raster.rgba(a, oracle.NRGBA8), s
+    if kind == "gray":
+        g = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        s[..., :3] = (g.astype(np.uint16) * 0x101)[..., None]
+        s[..., 3] = 0xFFFF
+        return oracle.Raster.gray(g), s
+    lay = {"420": oracle.YCBCR420, "422": oracle.YCBCR422, "444": oracle.YCBCR444, "440": oracle.YCBCR440}[kind]
+    ch, cw = oracle.chroma_shape(lay, w, h)
+    y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    cb, cr = rng.integers(0, 256, (ch, cw), dtype=np.uint8), rng.integers(0, 256, (ch, cw), dtype=np.uint8)
+    yi = np.arange(h)[:, None] >> (1 if kind in ("420", "440") else 0)     # nearest chroma sample, as Go indexes it
+    xi = np.arange(w)[None, :] >> (1 if kind in ("420", "422") else 0)
+    yy1 = y.astype(np.int64) * 0x10101
+    cb1, cr1 = cb[yi, xi].astype(np.int64) - 128, cr[yi, xi].astype(np.int64) - 128
+    s[..., 0] = np.clip((yy1 + 91881 * cr1) >> 8, 0, 0xFFFF)
+    s[..., 1] = np.clip((yy1 - 22554 * cb1 - 46802 * cr1) >> 8, 0, 0xFFFF)
+    s[..., 2] = np.clip((yy1 + 116130 * cb1) >> 8, 0, 0xFFFF)
+    s[..., 3] = 0xFFFF
+    return oracle.Raster.ycbcr(y, cb, cr, lay), s
+
+
+def run_emu16(L, s, spec, two_stage, bands_hint=4):
+    h, w = s.shape[:2]
+    L.planemu_run16.argtypes = L.planemu_run.argtypes
+    sp = np.array(spec, np.int32)
+    ts = np.array([two_stage], np.int32)
+    dst, flag = np.zeros((spec[5], spec[4], 4), np.uint8), np.zeros((spec[5], spec[4]), np.uint8)
+    dp, fp = (C.c_void_p * 1)(dst.ctypes.data), (C.c_void_p * 1)(flag.ctypes.data)
+    info = np.zeros(5, np.int32)
+    rc = L.planemu_run16(s.ctypes.data, w * 4, w, h, 1, sp.ctypes.data, ts.ctypes.data, dp, fp, bands_hint, info.ctypes.data)
+    return rc, dst, flag
+
+
+@pytest.mark.parametrize("kind", ["nrgba", "gray", "420", "422", "444", "440"])
+def test_sixteen_bit_sample_kernels_certified_fp32(emu, oracle, kind):
+    """The same certificate for k_stream_planar: over 16-bit samples with unscaled vertical weights, every byte the
+    fp32 pass does not flag equals the oracle's float64 result for the real source (NRGBA, Gray, four YCbCr
+    subsamplings), flagged ones are within 1 -- resize and the two-stage crop thumbnail, several geometries."""
+    for i, (w, h, rw, rh, size, bands) in enumerate([(400, 300, 102, 76, 20, 1), (1203, 899, 300, 224, 64, 7),
+                                                     (1601, 1201, 640, 480, 100, 5), (997, 1403, 1024, 768, 200, 3)]):
+        R, s = samples16(oracle, kind, w, h, 700 + i)
+        nw, nh = oracle.keep_aspect_dims(w, h, rw, rh)
+        cx, cy, cs = oracle.crop_square(w, h)
+        for spec, two, ref in (((0, 0, w, h, nw, nh), 0, lambda: oracle.resize_image(R, nw, nh)),
+                               ((cx, cy, cs, cs, size, size), 1, lambda: oracle.crop_and_resize(R, size))):
+            rc, d, f = run_emu16(emu, s, spec, two, bands)
+            assert rc == 0, f"emulator error {rc} for {kind} {spec}"
+            assert np.all((f == 16) | (f == 1)), "each output pixel written exactly once"
+            amb = f == 1
+            diff = np.abs(d.astype(int) - ref().astype(int)).max(axis=2)
+            assert diff[~amb].max(initial=0) == 0, f"{kind} {spec}: an unflagged byte differs from the fp64 oracle"
+            assert diff.max(initial=0) <= 1 and amb.mean() < 0.03
