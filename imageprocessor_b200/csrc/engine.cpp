@@ -124,10 +124,15 @@ public:
         base_ = nullptr;
     }
     size_t size() const { return size_; }
-    uint8_t *alloc(size_t n, const std::atomic<bool> &stop)
+    // Waits at most timeout_ms for space (the ABI returns a status, it does not block for ever: staging of a
+    // pageable destination is only released by ipg_wait, so a caller that submits more than the pool holds before it
+    // waits would otherwise hang).  *timed_out tells a full pool from a request that can never fit.
+    uint8_t *alloc(size_t n, const std::atomic<bool> &stop, int timeout_ms, bool *timed_out)
     {
+        if (timed_out) *timed_out = false;
         n = align_up(std::max<size_t>(n, 1), 256);
         if (n > size_) return nullptr;
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(std::max(timeout_ms, 0));
         std::unique_lock<std::mutex> lk(mu_);
         for (;;) {
             for (auto it = free_.begin(); it != free_.end(); ++it) {
@@ -140,7 +145,11 @@ public:
                 }
             }
             if (stop.load()) return nullptr;
-            cv_.wait_for(lk, std::chrono::milliseconds(50));
+            if (std::chrono::steady_clock::now() >= deadline) {
+                if (timed_out) *timed_out = true;
+                return nullptr;
+            }
+            cv_.wait_for(lk, std::chrono::milliseconds(20));
         }
     }
     void release(uint8_t *p)
@@ -294,6 +303,7 @@ struct Ctx {
     uint32_t band_cta_target = 1400;
     uint32_t fix_capacity = 0;     // IPG_FIX_CAPACITY: fix-list entries per batch (0: sized from the batch); tests force the overflow paths with it
     bool overlap_streams = true; // IPG_NO_OVERLAP=1: lean and general k_stream launches back to back (per-kernel timing)
+    int staging_timeout_ms = 2000; // IPG_STAGING_TIMEOUT_MS: how long ipg_submit waits for pinned staging before IPG_ERR_NOMEM
     // stats
     std::atomic<uint64_t> s_done{0}, s_batches{0}, s_kernels{0}, s_h2d{0}, s_d2h{0}, s_fix{0}, s_fallback{0}, s_staged{0};
     std::mutex smu;
@@ -326,7 +336,13 @@ struct Blob {
     uint8_t *dev;
     size_t cap, off = 0;
     bool overflow = false;
-    std::unordered_map<const void *, size_t> seen;
+    // Tables already in the blob, keyed by (address, bytes) of the host vector.  The vectors belong to cached plans
+    // (StreamGeom / AxisPlan); the plan caches may evict at any time, on this thread or another device's batcher,
+    // so every plan a batch reads from is pinned in `keep` until the blob is complete -- a freed vector's address
+    // can then never be reused by a different table while `seen` still maps it.
+    std::map<std::pair<const void *, size_t>, size_t> seen;
+    std::vector<std::shared_ptr<const void>> keep;
+    template <typename P> void hold(const std::shared_ptr<P> &p) { if (p) keep.push_back(std::static_pointer_cast<const void>(p)); }
     template <typename T> T *dptr(size_t o) const { return (T *)(dev + o); }
     size_t put(const void *data, size_t bytes, size_t a = 16)
     {
@@ -341,10 +357,11 @@ struct Blob {
     }
     template <typename T> const T *put_vec(const std::vector<T> &v)
     {
-        auto it = seen.find((const void *)v.data());
+        const std::pair<const void *, size_t> key{(const void *)v.data(), v.size() * sizeof(T)};
+        auto it = seen.find(key);
         if (it != seen.end()) return dptr<const T>(it->second);
         size_t o = put(v.data(), v.size() * sizeof(T), 16);
-        seen[(const void *)v.data()] = o;
+        if (!overflow) seen[key] = o;
         return dptr<const T>(o);
     }
     size_t reserve(size_t bytes, size_t a = 16)
@@ -543,8 +560,11 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
             const int sh = op.kind == IPG_OP_THUMB_CROP ? op.rh : sv.h;
             j.dw = op.dw; j.dh = op.dh;
             j.dst = op.dev_out; j.dst_stride = (int)op.dev_pitch;
-            j.ax = pack_axis(blob, *get_axis_plan(op.dw, sw));
-            j.ay = pack_axis(blob, *get_axis_plan(op.dh, sh));
+            auto pax = get_axis_plan(op.dw, sw), pay = get_axis_plan(op.dh, sh);
+            blob.hold(pax);
+            blob.hold(pay);
+            j.ax = pack_axis(blob, *pax);
+            j.ay = pack_axis(blob, *pay);
             vec.push_back(j);
             return (int)vec.size() - 1;
         };
@@ -615,6 +635,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                     continue;
                 }
                 if (wm) wi++;
+                blob.hold(geom);
                 StreamJob j{};
                 j.src = sv;
                 j.n_targets = nt;
@@ -700,6 +721,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                     if (precision != IPG_PRECISION_REFERENCE) B.exact_fallbacks++;
                     continue;
                 }
+                blob.hold(geom);
                 StreamJob j{};
                 j.src = sv;
                 j.n_targets = 1;
@@ -1130,9 +1152,13 @@ static int submit_impl(Ctx *c, int dev_index, const ipg_image_desc *src, const i
             plane_dims(src->layout, p, src->width, src->height, &wb, &ph);
             size_t span = (size_t)src->stride[p] * (size_t)(ph - 1) + (size_t)wb;
             if (c->pinned.contains(src->plane[p], span)) continue;
-            uint8_t *s = d.staging.alloc((size_t)wb * (size_t)ph, c->stop);
+            bool timed_out = false;
+            uint8_t *s = d.staging.alloc((size_t)wb * (size_t)ph, c->stop, c->staging_timeout_ms, &timed_out);
             if (!s) {
                 for (int q = 0; q < p; q++) d.staging.release(t->src_stage[q]);
+                if (timed_out)
+                    return fail(IPG_ERR_NOMEM, "pinned staging pool exhausted by tickets that were not waited for yet (ipg_wait earlier tickets, "
+                                               "raise lane_pinned_bytes, or use ipg_alloc_pinned buffers)");
                 return fail(IPG_ERR_NOMEM, "image larger than the pinned staging pool (raise lane_pinned_bytes or decode into ipg_alloc_pinned memory)");
             }
             for (int y = 0; y < ph; y++)
@@ -1145,10 +1171,15 @@ static int submit_impl(Ctx *c, int dev_index, const ipg_image_desc *src, const i
         if (r.dst_mem != IPG_MEM_HOST || r.dw <= 0 || r.dh <= 0) continue;
         size_t span = (size_t)r.dst_stride * (size_t)(r.dh - 1) + (size_t)r.dw * 4;
         if (c->pinned.contains(r.dst, span)) continue;
-        r.stage = d.staging.alloc((size_t)r.dw * 4 * (size_t)r.dh, c->stop);
+        bool timed_out = false;
+        r.stage = d.staging.alloc((size_t)r.dw * 4 * (size_t)r.dh, c->stop, c->staging_timeout_ms, &timed_out);
         if (!r.stage) {
             for (auto &q : t->ops) { d.staging.release(q.stage); q.stage = nullptr; }
             for (int p = 0; p < 3; p++) d.staging.release(t->src_stage[p]);
+            if (timed_out)
+                return fail(IPG_ERR_NOMEM, "pinned staging pool exhausted by outputs of tickets that were not waited for yet (staging of a pageable "
+                                           "destination is held until ipg_wait: wait for earlier tickets, raise lane_pinned_bytes, or use "
+                                           "ipg_alloc_pinned destinations)");
             return fail(IPG_ERR_NOMEM, "output larger than the pinned staging pool");
         }
     }
@@ -1301,6 +1332,7 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
         if (getenv("IPG_BAND_CTAS")) c->band_cta_target = (uint32_t)std::max(1, atoi(getenv("IPG_BAND_CTAS")));
         if (getenv("IPG_FIX_CAPACITY")) c->fix_capacity = (uint32_t)std::max(1, atoi(getenv("IPG_FIX_CAPACITY")));
         c->overlap_streams = !(getenv("IPG_NO_OVERLAP") && atoi(getenv("IPG_NO_OVERLAP")) != 0);
+        if (getenv("IPG_STAGING_TIMEOUT_MS")) c->staging_timeout_ms = std::max(0, atoi(getenv("IPG_STAGING_TIMEOUT_MS")));
         if (getenv("IPG_FUSE_TARGETS")) c->fuse_targets = std::min(3, std::max(1, atoi(getenv("IPG_FUSE_TARGETS"))));
         std::vector<int> ids;
         if (device_ids && n > 0) ids.assign(device_ids, device_ids + n);

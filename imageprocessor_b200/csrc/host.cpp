@@ -473,6 +473,7 @@ struct iph_processor {
             if (it != pinned_free.end() && it->first <= n + n / 4 + 4096) {
                 uint8_t *p = it->second;
                 sizes[p] = it->first;
+                pooled_bytes -= it->first;
                 pinned_free.erase(it);
                 return p;
             }
@@ -484,13 +485,29 @@ struct iph_processor {
         }
         return p;
     }
+    // The pool is bounded: a buffer that would push the parked bytes past kPoolCapBytes (or that alone exceeds a
+    // quarter of it) goes straight back to the driver, so one odd task cannot pin host memory for the life of the
+    // processor (the Go reference would have freed such a buffer at the next GC).
+    static constexpr size_t kPoolCapBytes = (size_t)1 << 30;
     void give_pinned(uint8_t *p)
     {
         if (!p) return;
-        std::lock_guard<std::mutex> lk(mu);
-        pinned_free.emplace(sizes[p], p);
+        size_t n = 0;
+        bool drop = false;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            n = sizes[p];
+            drop = n > kPoolCapBytes / 4 || pooled_bytes + n > kPoolCapBytes;
+            if (drop) sizes.erase(p);
+            else {
+                pinned_free.emplace(n, p);
+                pooled_bytes += n;
+            }
+        }
+        if (drop && ctx) ipg_free_pinned(ctx, p);
     }
     std::map<uint8_t *, size_t> sizes;
+    size_t pooled_bytes = 0; // bytes parked in pinned_free
 };
 
 namespace {
@@ -524,22 +541,31 @@ static bool layout_text(iph_processor *P, const std::string &text, double font_s
     int32_t pen_x = px * 64, pen_y = py * 64; // freetype.Pt
     uint32_t prev = 0;
     bool has_prev = false;
-    // Context.glyph() caches masks per (glyph, quarter-pixel x, whole-pixel y): a rune met again in the
-    // same bucket reuses the mask rasterised for its first occurrence
-    struct Cached { iph_glyph g; std::shared_ptr<std::vector<uint8_t>> mask; };
-    std::map<std::tuple<uint32_t, int, int>, Cached> cache;
+    // Context.glyph() (golang/freetype freetype.go): a direct-mapped cache of nGlyphs(256) x nXFractions(4) x
+    // nYFractions(1) slots, slot = ((index % 256) * 4 + fx / 16) * 1 + fy / 64; a hit needs the SAME glyph index in
+    // the slot (the sub-pixel offset is implied by the slot: the first occurrence's mask is reused for the whole
+    // quarter-pixel bucket); a miss rasterises at this occurrence's (fx, fy) and OVERWRITES the slot.  The Context is
+    // made per addTextWatermark call (watermark.go:98), so the cache starts empty for every text.  Runes that map to
+    // one glyph index (e.g. all runes the face lacks -> .notdef) share masks, exactly as there.
+    struct Cached { bool valid = false; uint32_t index = 0; iph_glyph g{}; std::shared_ptr<std::vector<uint8_t>> mask; };
+    std::map<int, Cached> cache; // slot -> entry (sparse stand-in for the 1024-entry array)
     for (uint32_t r : runes_of(text)) {
         if (has_prev && P->cb.kern) pen_x += P->cb.kern(P->cb.user, prev, r, font_size);
         const int ix = pen_x >> 6, fx = pen_x & 63, iy = pen_y >> 6, fy = pen_y & 63;
-        auto key = std::make_tuple(r, fx / 16, fy / 64);
-        auto it = cache.find(key);
-        if (it == cache.end()) {
+        // Font.Index(rune); hosts without the callback get the rune itself as a stand-in (distinct runes then never
+        // share a mask and collide only when equal mod 256)
+        const uint32_t index = P->cb.glyph_index ? P->cb.glyph_index(P->cb.user, r) : r;
+        const int slot = ((int)(index % 256u) * 4 + fx / 16) * 1 + fy / 64;
+        Cached &e = cache[slot];
+        if (!e.valid || e.index != index) {
             iph_glyph g{};
             if (!P->cb.glyph_mask || P->cb.glyph_mask(P->cb.user, r, font_size, fx, fy, &g) != 0) {
                 err = "failed to draw watermark text: glyph rasterisation failed";
                 return false;
             }
             Cached c;
+            c.valid = true;
+            c.index = index;
             c.g = g;
             c.mask = std::make_shared<std::vector<uint8_t>>();
             if (g.mask && g.mask_w > 0 && g.mask_h > 0) {
@@ -549,9 +575,9 @@ static bool layout_text(iph_processor *P, const std::string &text, double font_s
             }
             c.g.mask = nullptr;
             c.g.mask_stride = g.mask_w;
-            it = cache.emplace(key, std::move(c)).first;
+            e = std::move(c);
         }
-        const Cached &c = it->second;
+        const Cached &c = e;
         if (c.g.mask_w > 0 && c.g.mask_h > 0) {
             // glyphRect = mask.Bounds().Add(offset + (ix, iy)); dr = clip.Intersect(glyphRect)
             const int gx0 = ix + c.g.off_x, gy0 = iy + c.g.off_y;
@@ -578,6 +604,8 @@ static bool layout_text(iph_processor *P, const std::string &text, double font_s
     }
     return true;
 }
+
+enum { kMaxDstSide = 65536 };
 
 // Resizer.Process / Thumbnailer.Process / Watermarker.Process up to the raster call:
 // parameters, geometry.  Returns false with the operation's error text.
@@ -645,6 +673,13 @@ static bool plan_op(iph_processor *P, const Operation &o, const ipg_image_desc &
         err = "unsupported operation type: " + o.type;
         return false;
     }
+    // The raster engine takes destinations up to 65536 px a side (ipg_submit rejects more): refuse here, before a
+    // Kafka-supplied {"width": 60000, "height": 60000} reaches the pinned allocator.
+    if (po.dw > kMaxDstSide || po.dh > kMaxDstSide) {
+        err = "output dimensions " + std::to_string(po.dw) + "x" + std::to_string(po.dh) + " exceed the raster engine's limit of " +
+              std::to_string(kMaxDstSide) + " px per side";
+        return false;
+    }
     po.path = generate_path("", o.type, po.out_format, o.params); // image id filled by the caller
     return true;
 }
@@ -708,7 +743,7 @@ static void job_begin(iph_processor *P, Job &j, const char *task_json, const ipg
         po.op.dst_w = po.dw;
         po.op.dst_h = po.dh;
         po.op.dst = po.dst;
-        po.op.dst_stride = po.dw * 4;
+        po.op.dst_stride = (int32_t)((size_t)po.dw * 4); // dw <= 65536: fits
         po.op.dst_memspace = IPG_MEM_HOST;
         po.glyph_arr.clear();
         for (auto &g : po.glyphs) po.glyph_arr.push_back(g.g);

@@ -18,6 +18,16 @@
 
 namespace ipg {
 
+// Launch-side state that CUDA keeps per device (function attributes, occupancy-derived grids) is cached per
+// device: one process may drive every GPU of the box (ipg_init(NULL, 0, ...)).
+enum { kMaxDevices = 64 };
+static int current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
+}
+
 // ---------------------------------------------------------------------------------
 // source adaptors (the inner expressions of x/image draw/impl.go scaleX_<type>)
 // ---------------------------------------------------------------------------------
@@ -1782,11 +1792,13 @@ template <bool NRGBA>
 static cudaError_t launch_stream_planar_t(const StreamJob *jobs, const StreamItem *items, int n_items, FixList fix, cudaStream_t st)
 {
     using Smem = PlanarSmem<NRGBA, PLANAR_STAGES>;
-    static bool configured = false;
-    if (!configured) {
+    // the attribute belongs to the function handle of ONE device's primary context: keep the flag per device
+    static bool configured[kMaxDevices] = {}; // per instantiation; benign race (idempotent attribute)
+    const int dev = current_device();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_stream_planar<NRGBA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     k_stream_planar<NRGBA><<<n_items, STREAM_CTA, sizeof(Smem), st>>>(jobs, items, fix);
     return cudaGetLastError();
@@ -1811,12 +1823,13 @@ template <int NT, bool WM, int LEAN>
 static cudaError_t launch_stream_t(const StreamJob *jobs, const StreamItem *items, int n, FixList fix, cudaStream_t st)
 {
     using Smem = typename StreamCfg<NT, LEAN>::Smem;
-    static bool configured = false; // per instantiation; benign race (idempotent attribute)
-    if (!configured) {
+    static bool configured[kMaxDevices] = {}; // per instantiation AND device (the attribute is per primary context); benign race
+    const int dev = current_device();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_stream<NT, WM, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     k_stream<NT, WM, LEAN><<<n, StreamCfg<NT, LEAN>::THREADS, sizeof(Smem), st>>>(jobs, items, fix);
     return cudaGetLastError();
@@ -1865,17 +1878,19 @@ cudaError_t launch_exact_tiles(const ExactJob *jobs, const ExactItem *items, int
 cudaError_t launch_exact_fix(const ExactJob *jobs, int n_jobs, FixList fix, cudaStream_t st)
 {
     if (!fix.capacity || n_jobs <= 0) return cudaSuccess;
-    static int grid = 0, grid_wide = 0; // one resident wave each: the warps claim work from cursors (benign race: idempotent)
-    if (grid == 0) {
-        int dev = 0, sms = 148, per_sm = 4, per_sm_wide = 4;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // one resident wave each: the warps claim work from cursors.  Sized per device (benign race: idempotent)
+    static int grid[kMaxDevices] = {}, grid_wide[kMaxDevices] = {};
+    const int dev = current_device();
+    if (grid[dev] == 0) {
+        int sms = 148, per_sm = 4, per_sm_wide = 4;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_exact_fix, FIX_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_wide, k_exact_fix_wide, FIX_THREADS, 0) != cudaSuccess || per_sm_wide < 1) per_sm_wide = 4;
-        grid_wide = sms * per_sm_wide;
-        grid = sms * per_sm;
+        grid_wide[dev] = sms * per_sm_wide;
+        grid[dev] = sms * per_sm;
     }
-    k_exact_fix<<<grid, FIX_THREADS, 0, st>>>(jobs, n_jobs, fix);
-    k_exact_fix_wide<<<grid_wide, FIX_THREADS, 0, st>>>(jobs, fix);
+    k_exact_fix<<<grid[dev], FIX_THREADS, 0, st>>>(jobs, n_jobs, fix);
+    k_exact_fix_wide<<<grid_wide[dev], FIX_THREADS, 0, st>>>(jobs, fix);
     return cudaGetLastError();
 }
 

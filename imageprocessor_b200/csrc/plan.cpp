@@ -7,8 +7,43 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 
 namespace ipg {
+
+// Plan cache with least-recently-used eviction: when full, the older half (by last use) goes; a long-running worker
+// on a mixed-size stream keeps its working set instead of rebuilding everything after a clear.  Entries are shared_ptrs:
+// whoever still uses an evicted plan keeps it alive (engine.cpp pins the plans of a batch until its blob is built).
+template <typename K, typename V> class AgedCache {
+public:
+    explicit AgedCache(size_t cap) : cap_(cap) {}
+    bool find(const K &k, V &out)
+    {
+        auto it = map_.find(k);
+        if (it == map_.end()) return false;
+        it->second.second = ++tick_;
+        out = it->second.first;
+        return true;
+    }
+    void put(const K &k, const V &v)
+    {
+        if (map_.size() >= cap_) {
+            std::vector<uint64_t> ages;
+            ages.reserve(map_.size());
+            for (auto &kv : map_) ages.push_back(kv.second.second);
+            std::nth_element(ages.begin(), ages.begin() + ages.size() / 2, ages.end());
+            const uint64_t cut = ages[ages.size() / 2];
+            for (auto it = map_.begin(); it != map_.end();) it = it->second.second < cut ? map_.erase(it) : std::next(it);
+        }
+        map_[k] = {v, ++tick_};
+    }
+    size_t size() const { return map_.size(); }
+
+private:
+    size_t cap_;
+    uint64_t tick_ = 0;
+    std::map<K, std::pair<V, uint64_t>> map_;
+};
 
 static std::shared_ptr<const AxisPlan> build_axis(int32_t dn, int32_t sn)
 {
@@ -64,16 +99,15 @@ static std::shared_ptr<const AxisPlan> build_axis(int32_t dn, int32_t sn)
 std::shared_ptr<const AxisPlan> get_axis_plan(int dn, int sn)
 {
     static std::mutex mu;
-    static std::map<std::pair<int, int>, std::shared_ptr<const AxisPlan>> cache;
+    static AgedCache<std::pair<int, int>, std::shared_ptr<const AxisPlan>> cache(4096);
     {
         std::lock_guard<std::mutex> lk(mu);
-        auto it = cache.find({dn, sn});
-        if (it != cache.end()) return it->second;
+        std::shared_ptr<const AxisPlan> hit;
+        if (cache.find({dn, sn}, hit)) return hit;
     }
     auto p = build_axis(dn, sn);
     std::lock_guard<std::mutex> lk(mu);
-    if (cache.size() > 4096) cache.clear();
-    cache[{dn, sn}] = p;
+    cache.put({dn, sn}, p);
     return p;
 }
 
@@ -350,20 +384,19 @@ std::shared_ptr<const StreamGeom> get_stream_geom(int W, int H, const StreamTarg
                                                   bool has_wm, int n_bands_hint, double sample_scale)
 {
     static std::mutex mu;
-    static std::map<GeomKey, std::shared_ptr<const StreamGeom>> cache; // value may be nullptr (infeasible)
+    static AgedCache<GeomKey, std::shared_ptr<const StreamGeom>> cache(1024); // value may be nullptr (infeasible)
     GeomKey key{};
     key.W = W; key.H = H; key.n_targets = n_targets; key.has_wm = has_wm; key.n_bands = n_bands_hint;
     key.scale_bits = (long long)(sample_scale * 65536.0);
     for (int i = 0; i < n_targets && i < 2; i++) key.t[i] = targets[i];
     {
         std::lock_guard<std::mutex> lk(mu);
-        auto it = cache.find(key);
-        if (it != cache.end()) return it->second;
+        std::shared_ptr<const StreamGeom> hit;
+        if (cache.find(key, hit)) return hit;
     }
     auto g = (n_targets <= 2) ? build_stream(W, H, targets, n_targets, has_wm, n_bands_hint, sample_scale) : nullptr;
     std::lock_guard<std::mutex> lk(mu);
-    if (cache.size() > 1024) cache.clear();
-    cache[key] = g;
+    cache.put(key, g);
     return g;
 }
 

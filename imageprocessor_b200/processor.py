@@ -33,11 +33,12 @@ SAVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C
 ADVANCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_double, C.POINTER(C.c_int32))
 MASK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_double, C.c_int, C.c_int, C.POINTER(IphGlyph))
 KERN_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_double)
+INDEX_FN = C.CFUNCTYPE(C.c_uint32, C.c_void_p, C.c_uint32)
 
 
 class Callbacks(C.Structure):
     _fields_ = [("user", C.c_void_p), ("encode", ENCODE_FN), ("release", RELEASE_FN), ("save_processed", SAVE_FN),
-                ("glyph_advance", ADVANCE_FN), ("glyph_mask", MASK_FN), ("kern", KERN_FN)]
+                ("glyph_advance", ADVANCE_FN), ("glyph_mask", MASK_FN), ("kern", KERN_FN), ("glyph_index", INDEX_FN)]
 
 
 def _host_lib():
@@ -154,6 +155,10 @@ class PilFace:
     def advance_26_6(self, rune: int, size: float) -> Optional[int]:
         return int(round(self.font(size).getlength(chr(rune)) * 64))
 
+    def index(self, rune: int) -> int:
+        """Font.Index(rune) stand-in: PIL does not expose the cmap, so the rune is its own index."""
+        return rune
+
     def mask(self, rune: int, size: float, fx: int, fy: int):
         """(advance_26_6, off_x, off_y, mask) with offsets relative to the integer pen, y down."""
         f = self.font(size)
@@ -218,8 +223,11 @@ class ImageProcessor:
             except Exception:
                 return -1
 
+        def _index(user, rune):
+            return self.face.index(rune)
+
         self._cbs = Callbacks(None, ENCODE_FN(_encode), RELEASE_FN(_release), SAVE_FN(_save), ADVANCE_FN(_advance),
-                              MASK_FN(_mask), KERN_FN(0))
+                              MASK_FN(_mask), KERN_FN(0), INDEX_FN(_index) if hasattr(self.face, "index") else INDEX_FN(0))
         self._engine = engine
         self._p = self._lib.iph_processor_new(engine._ctx if engine else None, C.byref(self._cbs))
         if not self._p:

@@ -65,6 +65,9 @@ typedef struct {
     int (*glyph_mask)(void *user, uint32_t rune, double font_size, int fx, int fy, iph_glyph *out);
     /* Font.Kern(scale, prev, index), 26.6; may be NULL (no kerning). */
     int32_t (*kern)(void *user, uint32_t prev_rune, uint32_t rune, double font_size);
+    /* Font.Index(rune): the glyph index freetype.Context.glyph() keys its 256 x 4 direct-mapped mask cache on
+     * (slot = index % 256, quarter-pixel x).  May be NULL: the rune then stands in for the index. */
+    uint32_t (*glyph_index)(void *user, uint32_t rune);
 } iph_callbacks;
 
 /* ctx may be NULL for host-only use (parameter handling, paths, JSON): raster work then

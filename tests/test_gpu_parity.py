@@ -299,3 +299,28 @@ def test_sixteen_bit_sample_layouts_odd_sizes(engines, oracle, kind):
         out = e.run(img, [ip.OpSpec.resize(dw, dh), ip.OpSpec.thumb_crop((cx, cy, cs, cs), size)])
         assert np.array_equal(out[0], oracle.resize_image(R, dw, dh)), f"{kind} resize {w}x{h} -> {dw}x{dh}"
         assert np.array_equal(out[1], oracle.crop_and_resize(R, size)), f"{kind} thumb {w}x{h} crop {cx},{cy},{cs} -> {size}"
+
+
+@pytest.mark.gpu
+def test_submit_returns_nomem_instead_of_blocking_when_staging_is_exhausted(monkeypatch):
+    """ipg_submit must answer with a status when pageable outputs that were never waited for fill the
+    pinned staging pool (staging of a pageable destination is released by ipg_wait) -- not block for ever."""
+    import time
+    import imageprocessor_b200 as ip
+    from imageprocessor_b200 import _lib as L
+    monkeypatch.setenv("IPG_STAGING_TIMEOUT_MS", "300")
+    w, h = 1024, 1024                                   # 4 MiB source + 4 MiB watermark output per ticket, both pageable
+    a = rgba_random(w, h, 1)
+    with ip.Engine(devices=[0], lanes_per_device=1, lane_pinned_bytes=16 << 20) as e:
+        held, t0, err = [], time.time(), None
+        try:
+            for _ in range(16):                          # 16 x 4 MiB of outputs never fit 16 MiB of staging
+                held.append(e.submit(ip.Image.from_rgba(a), [ip.OpSpec.watermark(w, h, (255, 255, 255, 127), [])]))
+        except L.IpgError as ex:
+            err = ex
+        assert err is not None and err.code == L.ERR_NOMEM and "not waited for" in str(err)
+        assert time.time() - t0 < 30
+        for t in held:                                   # the tickets that were accepted still complete, bit-exact
+            assert np.array_equal(e.wait(t)[0], a)
+        # and the pool is whole again
+        assert np.array_equal(e.run(ip.Image.from_rgba(a), [ip.OpSpec.watermark(w, h, (255, 255, 255, 127), [])])[0], a)

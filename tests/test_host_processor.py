@@ -108,6 +108,68 @@ def test_result_json_is_encoding_json_shaped():
     ip_.close()
 
 
+def test_oversized_output_is_refused_before_any_allocation():
+    """{"width": 60000, "height": 70000} from the broker must not reach the pinned allocator."""
+    from imageprocessor_b200 import Image
+    ip_ = P.ImageProcessor(None, P.MemoryFileRepo())
+    img = Image.from_rgba(rgba_random(64, 48, 1))
+    res, err = ip_.process(task([{"Type": "resize", "Parameters": {"width": 60000, "height": 70000}}]), img)
+    assert "exceed the raster engine's limit of 65536" in err and res["Status"] == "failed"
+    res, err = ip_.process(task([{"Type": "thumbnail", "Parameters": {"size": 1e9, "crop_to_fit": True}}]), img)
+    assert "exceed the raster engine's limit" in err
+    # keep_aspect brings 60000x70000 down to the source's aspect: 64x48 * min(937.5, 1458.3) = 60000x45000 -> accepted
+    # by the bound (and then stopped only by the missing engine)
+    res, err = ip_.process(task([{"Type": "resize", "Parameters": {"width": 60000, "height": 70000, "keep_aspect": True}}]), img)
+    assert "no raster engine" in err
+    ip_.close()
+
+
+class CountingFace(P.PilFace):
+    """Counts rasterise calls; maps runes to glyph indices through a table (default: the rune)."""
+
+    def __init__(self, index_of=None):
+        super().__init__()
+        self.calls = []
+        self.index_of = index_of or {}
+
+    def index(self, rune):
+        return self.index_of.get(rune, rune)
+
+    def mask(self, rune, size, fx, fy):
+        self.calls.append((rune, fx, fy))
+        return super().mask(rune, size, fx, fy)
+
+
+def _watermark_calls(text, face):
+    from imageprocessor_b200 import Image
+    ip_ = P.ImageProcessor(None, P.MemoryFileRepo(), face=face)
+    ip_.process(task([{"Type": "watermark", "Parameters": {"text": text}}]), Image.from_rgba(rgba_random(900, 300, 1)))
+    ip_.close()
+    return face.calls
+
+
+def test_glyph_mask_cache_is_freetypes_direct_mapped_table():
+    """freetype.Context.glyph(): slot = (index % 256) * 4 + fx / 16; hit iff the slot holds the same index; a miss
+    rasterises at this occurrence's sub-pixel offset and overwrites the slot."""
+    # integer advances keep fx == 0 for every rune: one bucket per glyph index
+    class IntFace(CountingFace):
+        def advance_26_6(self, rune, size):
+            return 20 * 64
+
+        def mask(self, rune, size, fx, fy):
+            adv, ox, oy, m = super().mask(rune, size, fx, fy)
+            return 20 * 64, ox, oy, m
+    # same rune again in the same bucket: one rasterisation
+    assert [c[0] for c in _watermark_calls("aaaa", IntFace())] == [ord("a")]
+    # two runes with ONE glyph index (e.g. both missing -> .notdef) share the first one's mask
+    assert [c[0] for c in _watermark_calls("abab", IntFace({ord("a"): 7, ord("b"): 7}))] == [ord("a")]
+    # indices equal mod 256 collide in the slot: each occurrence evicts the other and is rasterised again
+    calls = _watermark_calls("abab", IntFace({ord("a"): 7, ord("b"): 7 + 256}))
+    assert [c[0] for c in calls] == [ord("a"), ord("b"), ord("a"), ord("b")]
+    # distinct slots: once each
+    assert [c[0] for c in _watermark_calls("abab", IntFace({ord("a"): 7, ord("b"): 8}))] == [ord("a"), ord("b")]
+
+
 # ---- end to end on the GPU --------------------------------------------------------------
 def go_drawstring_layout(face, text, size, W, H, px, py):
     """freetype.Context.DrawString restated for the oracle side of the test (26.6 pen, the
@@ -117,10 +179,11 @@ def go_drawstring_layout(face, text, size, W, H, px, py):
     for ch in text:
         r = ord(ch)
         ix, fx, iy, fy = pen_x >> 6, pen_x & 63, pen_y >> 6, pen_y & 63
-        key = (r, fx // 16, fy // 64)
-        if key not in cache:
-            cache[key] = face.mask(r, size, fx, fy)
-        adv, ox, oy, m = cache[key]
+        idx = face.index(r)
+        slot = ((idx % 256) * 4 + fx // 16) * 1 + fy // 64
+        if slot not in cache or cache[slot][0] != idx:
+            cache[slot] = (idx, face.mask(r, size, fx, fy))
+        adv, ox, oy, m = cache[slot][1]
         if m.size:
             gx0, gy0 = ix + ox, iy + oy
             x0, y0, x1, y1 = max(gx0, 0), max(gy0, 0), min(gx0 + m.shape[1], W), min(gy0 + m.shape[0], H)
