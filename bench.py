@@ -1,18 +1,20 @@
 #!/usr/bin/env python
-"""bench.py -- images/sec for resize(1024x768 keep-aspect) + thumbnail(200 crop) +
-watermark on a batch of 12 MP RGBA images (BASELINE.json metric / configs[1..2]).
+"""bench.py -- images/sec for resize(1024x768 keep-aspect) + thumbnail(200 crop) + watermark on a batch of 12 MP
+RGBA images (BASELINE.json metric, configs[1..2]), plus one measured, parity-checked sub-record per remaining
+BASELINE config under `configs` (c1: one 12 MP JPEG through the CPU path; c4: 8K full pipeline sharded by image;
+c5: mixed 0.3-48 MP PNG+JPEG stream end to end incl. host decode/encode).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
   python bench.py --impl reference [...]                        # restated reference CPU path
   torchrun ... bench.py --gpus N ...                            # one rank per GPU, images shard by rank
+  python bench.py --single-process --gpus N                     # ONE process, one engine context over N devices
 
 One step = one pass of the hot path over the whole batch (256 images per GPU).
-`value`  : device-resident inputs/outputs, device clock from the first kernel start to
-           the last kernel end of the K timed steps (CUDA events on the launching streams).
-`e2e`    : the same K steps through the C ABI with pinned HOST buffers: H2D of every
-           source and D2H of every result inside the timed region.
-`roofline`: k_stream's algorithmic bytes per launch / its mean launch duration, against
-           the measured HBM copy peak (MEASURED_PEAKS.json).
+`value`   : device-resident inputs/outputs, device clock from the first kernel start to the last kernel end of the
+            K timed steps (CUDA events on the launching streams).
+`e2e`     : the same K steps through the C ABI with pinned HOST buffers: H2D of every source and D2H of every result
+            inside the timed region; `e2e.pcie` puts the measured host<->device ceiling of the box beside it.
+`roofline`: k_stream's algorithmic bytes per launch / its mean launch duration, against the measured HBM copy peak.
 `cpu_baseline`: oracle/ (C restatement of the reference algorithm) on the host cores.
 Nothing here reads /root/reference.
 """
@@ -21,10 +23,12 @@ from __future__ import annotations
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import numpy as np
@@ -36,12 +40,6 @@ W_IMG, H_IMG = 4000, 3000
 RW, RH, THUMB = 1024, 768, 200
 WM_TEXT, WM_OPACITY, WM_COLOR = "© ImageProcessor", 0.5, "255,255,255"
 METRIC = "images/sec resize+thumb+watermark, 12MP batch"
-# algorithmic bytes per 12 MP RGBA image, source read once
-BYTES_PER_IMAGE = W_IMG * H_IMG * 4 + RW * RH * 4 + THUMB * THUMB * 4 + W_IMG * H_IMG * 4
-# ... and of the two passes the engine runs per image: the lean k_stream instantiation fuses
-# resize + watermark copy (source read once), the general one does the thumbnail over the crop square
-BYTES_LEAN_PASS = W_IMG * H_IMG * 4 + RW * RH * 4 + W_IMG * H_IMG * 4
-BYTES_THUMB_PASS = H_IMG * H_IMG * 4 + THUMB * THUMB * 4
 
 
 def env_int(name, default):
@@ -68,6 +66,22 @@ def ncu_traffic():
         return None
 
 
+def pcie_ceiling(n_devices):
+    """Measured host<->device ceiling for n_devices copying concurrently in both directions (GB/s per direction,
+    aggregate over the devices): tools/micro/pcie_scale.cu, committed run in profiles/pcie_scaling.json."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "pcie_scaling.json")) as f:
+            d = json.load(f)
+        best = None
+        for r in d["results"]:
+            if r.get("ok") and r["dir"] == "both" and r["n_devices"] == n_devices and r["alloc"] == "cudaHostAlloc" and r["chunk_mb"] > 40:
+                v = min(r["h2d_GBps_aggregate"], r["d2h_GBps_aggregate"])
+                best = v if best is None else max(best, v)
+        return best, d.get("box", "profiles/pcie_scaling.json")
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -84,8 +98,9 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            time.sleep(0.3)   # nvidia-smi needs a moment before its first sample
         except Exception:
             self.proc = None
 
@@ -123,17 +138,16 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------
-def make_host_image(seed):
+def make_host_image(seed, w=W_IMG, h=H_IMG):
     rng = np.random.default_rng(seed)
-    a = rng.integers(0, 256, (H_IMG, W_IMG, 4), dtype=np.uint8)
+    a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
     a[..., 3] = 255
     return a
 
 
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path: Go cannot be built here, so
-    this is oracle/ (C restatement, float64 scalar, fresh temp buffers, one image per
-    thread) on all host cores, on a bounded sample per step."""
+    """The reference's own CPU implementation of the path: Go cannot be built here, so this is oracle/ (C restatement,
+    float64 scalar, fresh temp buffers, one image per thread) on all host cores, on a bounded sample per step."""
     if rank != 0:
         return
     from oracle import oracle as O
@@ -141,7 +155,7 @@ def run_reference(args, rank, world):
     O.build()
     cores = os.cpu_count() or 1
     n = env_int("IPG_BENCH_REF_IMAGES", 4 * cores)
-    imgs = [make_host_image(1000 + i) for i in range(min(n, 4))]
+    imgs = [make_host_image(1000 + i) for i in range(min(n, 16))]
     rasters = [O.Raster.rgba(imgs[i % len(imgs)]) for i in range(n)]
     gl = [O.Glyph(g.x0, g.y0, g.x1, g.y1, g.mask, g.mp_x, g.mp_y)
           for g in G.layout_watermark(W_IMG, H_IMG, WM_TEXT)]
@@ -153,13 +167,17 @@ def run_reference(args, rank, world):
         s, _ = O.bench_batch(rasters, cores, 7, RW, RH, True, THUMB, col, gl)
         secs += s
     value = n * args.steps / secs
-    sample = f"{n} images per step (one per host thread), {args.steps} steps"
+    sample = f"{n} images per step (one per host thread, {len(imgs)} distinct), {args.steps} steps"
+    cfg = workload_config(args.gpus, args.images)   # the workload both arms are quoted on ...
+    cfg["images_per_step"] = n                      # ... and what THIS arm actually ran per step: a bounded sample of it
+    cfg["note"] = ("same workload (image shape, ops, parameters) as the CUDA arm; this arm's step is a bounded sample of "
+                   f"{n} images, not images_per_gpu_per_step -- the rates compare, the step times do not")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus, args.images),   # the CUDA arm's config; the bounded sample is in cpu_baseline.sample
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "restated reference CPU path (C), not the Go build"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -180,12 +198,11 @@ def bind_near_gpu(index):
         node = int(open(dev + "/numa_node").read().strip())
         info["gpu_numa_node"] = node
         if node >= 0:
-            import ctypes
-            libc = ctypes.CDLL(None, use_errno=True)
-            mask = ctypes.c_ulong(1 << node)
+            libc = C.CDLL(None, use_errno=True)
+            mask = C.c_ulong(1 << node)
             MPOL_PREFERRED = 1
-            rc = libc.syscall(238, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))  # set_mempolicy
-            info["mempolicy"] = "preferred" if rc == 0 else f"errno {ctypes.get_errno()}"
+            rc = libc.syscall(238, MPOL_PREFERRED, C.byref(mask), C.c_ulong(64))  # set_mempolicy
+            info["mempolicy"] = "preferred" if rc == 0 else f"errno {C.get_errno()}"
         cpus = set()
         for part in open(dev + "/local_cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
@@ -212,6 +229,433 @@ def workload_config(n_gpus, images_per_gpu):
     }
 
 
+# ---------------------------------------------------------------------------------
+class Geometry:
+    """Everything of one (W, H) RGBA workload that does not depend on buffers: reference geometry, glyphs, bytes."""
+
+    def __init__(self, ip, G, L, w, h):
+        self.L, self.w, self.h = L, w, h
+        self.nw, self.nh = ip.keep_aspect_dims(w, h, RW, RH)
+        self.cx, self.cy, self.cs = ip.crop_square(w, h)
+        self.glyph_list = G.layout_watermark(w, h, WM_TEXT, "bottom-right", 36.0)
+        self.color, _ = G.parse_color(WM_COLOR, WM_OPACITY)
+        self.garr = (L.Glyph * len(self.glyph_list))()
+        self._keep = []
+        for j, g in enumerate(self.glyph_list):
+            m = np.ascontiguousarray(g.mask, np.uint8)
+            self._keep.append(m)
+            a = self.garr[j]
+            a.x0, a.y0, a.x1, a.y1, a.mp_x, a.mp_y = g.x0, g.y0, g.x1, g.y1, g.mp_x, g.mp_y
+            a.mask_w, a.mask_h, a.mask_stride, a.mask = m.shape[1], m.shape[0], m.strides[0], m.ctypes.data
+        self.src_bytes = w * h * 4
+        self.r_bytes, self.t_bytes = self.nw * self.nh * 4, THUMB * THUMB * 4
+        # SURVEY.md 8(d): algorithmic bytes per image, source read once ("pipeline-min")
+        self.bytes_per_image = self.src_bytes + self.r_bytes + self.t_bytes + self.src_bytes
+        # ... and of the two passes the engine runs per image (DESIGN.md 4.1)
+        self.bytes_lean_pass = self.src_bytes + self.r_bytes + self.src_bytes
+        self.bytes_thumb_pass = self.cs * self.cs * 4 + self.t_bytes
+
+    def ops(self, dst_r, dst_t, dst_w, memspace):
+        L = self.L
+        ops = (L.Op * 3)()
+        ops[0].kind, ops[0].dst_w, ops[0].dst_h = L.OP_RESIZE, self.nw, self.nh
+        ops[0].dst, ops[0].dst_stride, ops[0].dst_memspace = dst_r, self.nw * 4, memspace
+        ops[1].kind, ops[1].dst_w, ops[1].dst_h = L.OP_THUMB_CROP, THUMB, THUMB
+        ops[1].rect_x, ops[1].rect_y, ops[1].rect_w, ops[1].rect_h = self.cx, self.cy, self.cs, self.cs
+        ops[1].dst, ops[1].dst_stride, ops[1].dst_memspace = dst_t, THUMB * 4, memspace
+        ops[2].kind, ops[2].dst_w, ops[2].dst_h = L.OP_WATERMARK, self.w, self.h
+        for k in range(4):
+            ops[2].color[k] = self.color[k]
+        ops[2].n_glyphs, ops[2].glyphs = len(self.glyph_list), self.garr
+        ops[2].dst, ops[2].dst_stride, ops[2].dst_memspace = dst_w, self.w * 4, memspace
+        return ops
+
+    def desc(self, ptr, memspace):
+        d = self.L.ImageDesc()
+        d.layout, d.memspace, d.width, d.height = self.L.RGBA8, memspace, self.w, self.h
+        d.plane[0] = ptr
+        d.stride[0] = self.w * 4
+        d.opaque_hint = 0   # *image.RGBA: alpha unknown to the caller, as in the reference
+        return d
+
+    def oracle_outputs(self, O, a):
+        R = O.Raster.rgba(a)
+        ogl = [O.Glyph(g.x0, g.y0, g.x1, g.y1, g.mask, g.mp_x, g.mp_y) for g in self.glyph_list]
+        return O.resize_image(R, self.nw, self.nh), O.crop_and_resize(R, THUMB), O.watermark(R, self.color, ogl)
+
+
+class DeviceBatch:
+    """n images of one geometry resident in HBM on the engine's device `dev_index` (torch owns the memory)."""
+
+    def __init__(self, torch, geo, n, cuda_index, seed0):
+        dev = torch.device("cuda", cuda_index)
+        gen = torch.Generator(device=dev)
+        self.geo, self.n = geo, n
+        self.srcs = []
+        for i in range(n):
+            gen.manual_seed(seed0 + i)
+            t = torch.randint(0, 256, (geo.h, geo.w, 4), dtype=torch.uint8, device=dev, generator=gen)
+            t[..., 3] = 255
+            self.srcs.append(t)
+        self.out_r = torch.empty((n, geo.nh, geo.nw, 4), dtype=torch.uint8, device=dev)
+        self.out_t = torch.empty((n, THUMB, THUMB, 4), dtype=torch.uint8, device=dev)
+        self.out_w = torch.empty((n, geo.h, geo.w, 4), dtype=torch.uint8, device=dev)
+        L = geo.L
+        self.descs = [geo.desc(self.srcs[i].data_ptr(), L.MEM_DEVICE) for i in range(n)]
+        self.ops = [geo.ops(self.out_r[i].data_ptr(), self.out_t[i].data_ptr(), self.out_w[i].data_ptr(), L.MEM_DEVICE)
+                    for i in range(n)]
+
+    def verify(self, O, i=0):
+        er, et, ew = self.geo.oracle_outputs(O, self.srcs[i].cpu().numpy())
+        return {"resize_bit_exact": bool(np.array_equal(self.out_r[i].cpu().numpy(), er)),
+                "thumb_bit_exact": bool(np.array_equal(self.out_t[i].cpu().numpy(), et)),
+                "watermark_bit_exact": bool(np.array_equal(self.out_w[i].cpu().numpy(), ew))}
+
+
+class Submitter:
+    """K steps over device-resident batches (one per engine device): step k+1 is submitted before step k is waited
+    for (a worker keeps submitting; the batcher never starves between steps)."""
+
+    def __init__(self, lib, L, ctx, batches):
+        self.lib, self.L, self.ctx, self.batches = lib, L, ctx, batches   # batches[d] lives on engine device d
+        n = sum(b.n for b in batches)
+        self.tids = [(C.c_uint64 * n)() for _ in range(2)]
+        self.refs = [[C.cast(C.byref(t, 8 * i), C.POINTER(C.c_uint64)) for i in range(n)] for t in self.tids]
+        self.n = n
+
+    def submit_step(self, k):
+        refs, j = self.refs[k & 1], 0
+        submit_on, ctx = self.lib.ipg_submit_on, self.ctx
+        # interleave the devices so every batcher fills at the same rate
+        per = max(b.n for b in self.batches)
+        for i in range(per):
+            for d, b in enumerate(self.batches):
+                if i < b.n:
+                    rc = submit_on(ctx, d, C.byref(b.descs[i]), b.ops[i], 3, refs[j])
+                    if rc:
+                        self.L.check(rc)
+                    j += 1
+
+    def wait_step(self, k):
+        t, wait, ctx = self.tids[k & 1], self.lib.ipg_wait, self.ctx
+        for i in range(self.n):
+            rc = wait(ctx, t[i], -1)
+            if rc:
+                self.L.check(rc)
+
+    def run_steps(self, n):
+        for k in range(n):
+            self.submit_step(k)
+            if k:
+                self.wait_step(k - 1)
+        if n:
+            self.wait_step(n - 1)
+
+
+class HostRing:
+    """n_slots pinned host slots per engine device, each a source + its three destinations; a slot is re-submitted as
+    soon as its previous ticket is done, so the K steps run as one stream of submissions (a worker does not drain its
+    pipeline between batches).  Every submission, copy and completion lies inside the caller's timed region."""
+
+    def __init__(self, lib, L, eng, geo, host_images, n_slots, n_dev):
+        self.lib, self.L, self.ctx, self.geo, self.n_dev = lib, L, eng._ctx, geo, n_dev
+        self.pins, self.descs, self.ops = [], [], []
+        for s in range(n_slots * n_dev):
+            p_in = eng.alloc_pinned(geo.src_bytes)
+            p_in.array[:] = host_images[s % len(host_images)].reshape(-1)
+            p_r, p_t, p_w = eng.alloc_pinned(geo.r_bytes), eng.alloc_pinned(geo.t_bytes), eng.alloc_pinned(geo.src_bytes)
+            self.pins += [p_in, p_r, p_t, p_w]
+            self.descs.append(geo.desc(p_in.ptr, L.MEM_HOST))
+            self.ops.append(geo.ops(p_r.ptr, p_t.ptr, p_w.ptr, L.MEM_HOST))
+        self.n_slots = n_slots * n_dev
+        self.tid = (C.c_uint64 * self.n_slots)()
+        self.ref = [C.cast(C.byref(self.tid, 8 * s), C.POINTER(C.c_uint64)) for s in range(self.n_slots)]
+
+    def run(self, total):
+        wait, ctx, n_slots, n_dev = self.lib.ipg_wait, self.ctx, self.n_slots, self.n_dev
+        submit_on = self.lib.ipg_submit_on
+        for j in range(total):
+            s = j % n_slots
+            if j >= n_slots:          # bounded in flight: slot s is free once its previous ticket is done
+                rc = wait(ctx, self.tid[s], -1)
+                if rc:
+                    self.L.check(rc)
+            rc = submit_on(ctx, s % n_dev, C.byref(self.descs[s]), self.ops[s], 3, self.ref[s])
+            if rc:
+                self.L.check(rc)
+        for s in range(min(n_slots, total)):
+            rc = wait(ctx, self.tid[s], -1)
+            if rc:
+                self.L.check(rc)
+
+    def verify_slot0(self, O):
+        g = self.geo
+        a = self.pins[0].array.reshape(g.h, g.w, 4)
+        er, et, ew = g.oracle_outputs(O, a)
+        return bool(np.array_equal(self.pins[1].array.reshape(g.nh, g.nw, 4), er) and
+                    np.array_equal(self.pins[2].array.reshape(THUMB, THUMB, 4), et) and
+                    np.array_equal(self.pins[3].array.reshape(g.h, g.w, 4), ew))
+
+    def free(self):
+        for p in self.pins:
+            p.free()
+        self.pins = []
+
+
+# ---------------------------------------------------------------------------------
+# BASELINE config sub-records
+# ---------------------------------------------------------------------------------
+def config_c1(ip, eng):
+    """configs[0]: single 4000x3000 RGB JPEG through resize(1024x768)+thumbnail(200x200) on the CPU path, in-process;
+    decode/encode timed separately.  The same decoded planes then go through the GPU path and must match byte for byte."""
+    from oracle import oracle as O
+    from imageprocessor_b200 import codecs
+    data = codecs.synth_file(W_IMG, H_IMG, 1, "jpeg")
+    t0 = time.perf_counter()
+    img, fmt = codecs.decode(data)
+    decode_ms = 1e3 * (time.perf_counter() - t0)
+    lay_names = {ip.YCBCR444: "4:4:4", ip.YCBCR422: "4:2:2", ip.YCBCR420: "4:2:0", ip.YCBCR440: "4:4:0"}
+    nw, nh = ip.keep_aspect_dims(img.width, img.height, RW, RH)
+    cx, cy, cs = ip.crop_square(img.width, img.height)
+    R = O.Raster.ycbcr(*img.planes, img.layout)
+    t0 = time.perf_counter()
+    er = O.resize_image(R, nw, nh)
+    t1 = time.perf_counter()
+    et = O.crop_and_resize(R, THUMB)
+    t2 = time.perf_counter()
+    t3 = time.perf_counter()
+    enc = [codecs.encode(er, "jpeg", 85), codecs.encode(et, "jpeg", 85)]
+    encode_ms = 1e3 * (time.perf_counter() - t3)
+    ops = [ip.OpSpec.resize(nw, nh), ip.OpSpec.thumb_crop((cx, cy, cs, cs), THUMB)]
+    eng.run(img, ops)                      # warm the plan cache
+    lat = []
+    for _ in range(5):
+        t0g = time.perf_counter()
+        out = eng.run(img, ops)
+        lat.append(1e3 * (time.perf_counter() - t0g))
+    return {
+        "workload": "BASELINE configs[0]: one 4000x3000 RGB JPEG (PIL-synthesised, 4:2:0, q90) -> *image.YCbCr planes -> "
+                    "resize 1024x768 keep-aspect + thumbnail 200 crop",
+        "source_file_bytes": len(data), "decoded_as": f"planar YCbCr {lay_names.get(img.layout, img.layout)} "
+                                                       f"({sum(p.nbytes for p in img.planes)} B)",
+        "decode_ms": decode_ms, "encode_ms": encode_ms, "codec": "PIL/libjpeg-turbo stand-in for Go image/jpeg (host, timed apart)",
+        "cpu_path": {"impl": "oracle/ip_oracle.c (C restatement of the reference, float64, 1 thread = one goroutine per image)",
+                     "resize_ms": 1e3 * (t1 - t0), "thumbnail_ms": 1e3 * (t2 - t1), "images_per_s": 1.0 / (t2 - t0)},
+        "gpu_path": {"latency_ms_median": float(np.median(lat)), "what": "ipg_submit + ipg_wait of one image, pageable host planes "
+                                                                          "(staged copy + 18 MB H2D + 2 kernels + D2H), batch of 1",
+                     "images_per_s_single_stream": 1e3 / float(np.median(lat))},
+        "verified": {"resize_bit_exact": bool(np.array_equal(out[0], er)), "thumb_bit_exact": bool(np.array_equal(out[1], et))},
+        "encoded_bytes": [len(e) for e in enc],
+    }
+
+
+def config_c4(ip, L, lib, torch, G, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks, steps):
+    """configs[3]: 8K (7680x4320) RGBA, full pipeline, sharded by image over the run's N GPUs: device-resident and e2e."""
+    W8, H8 = 7680, 4320
+    geo = Geometry(ip, G, L, W8, H8)
+    n_img = env_int("IPG_BENCH_8K_IMAGES", 24)
+    eng = ip.Engine(devices=[local_rank], precision=ip.PRECISION_EXACT, lanes_per_device=3, max_batch=32, batch_window_us=100,
+                    lane_device_bytes=2 << 30)
+    batch = DeviceBatch(torch, geo, n_img, local_rank, 5000 + rank * n_img)
+    sub = Submitter(lib, L, eng._ctx, [batch])
+    sub.run_steps(3)
+    barrier()
+    eng.reset_stats()
+    sub.run_steps(steps)
+    eng.flush()
+    barrier()
+    st = eng.stats()
+    span = max_over_ranks(st["kernel_span_ms"] / 1e3)
+    total = sum_over_ranks(float(n_img * steps))
+    peak, _ = measured_peak()
+    verified = None
+    if rank == 0:
+        from oracle import oracle as O
+        verified = batch.verify(O, 0)
+    host_imgs = [batch.srcs[i].cpu().numpy() for i in range(2)]
+    stream_ms = st["stream_kernel_ms"]
+    del batch, sub
+    torch.cuda.empty_cache()
+    eng.close()
+    # e2e: pinned host buffers
+    eng = ip.Engine(devices=[local_rank], precision=ip.PRECISION_EXACT, lanes_per_device=4, max_batch=4, batch_window_us=100,
+                    lane_device_bytes=2 << 30)
+    ring = HostRing(lib, L, eng, geo, host_imgs, env_int("IPG_BENCH_8K_SLOTS", 12), 1)
+    ring.run(n_img)
+    barrier()
+    eng.reset_stats()
+    t0 = time.perf_counter()
+    ring.run(n_img * steps)
+    eng.flush()
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - t0)
+    st2 = eng.stats()
+    ok_e2e = None
+    if rank == 0:
+        from oracle import oracle as O
+        ok_e2e = ring.verify_slot0(O)
+    ring.free()
+    eng.close()
+    return {
+        "workload": "BASELINE configs[3]: 8K (7680x4320) synthetic RGBA, resize 1024x576 + thumbnail 200 crop (4320^2 at x=1680) "
+                    "+ watermark, sharded by image, no collective",
+        "n_gpus": world, "images_per_gpu_per_step": n_img, "steps": steps,
+        "value": total / span, "unit": "images/s", "ms_per_image_device": 1e3 * span / (n_img * steps),
+        "algorithmic_bytes_per_image": geo.bytes_per_image,
+        "stream_kernel_GBps": geo.bytes_per_image * n_img * steps / (stream_ms * 1e-3) / 1e9,
+        "stream_kernel_frac_of_hbm_peak": geo.bytes_per_image * n_img * steps / (stream_ms * 1e-3) / 1e9 / peak,
+        "e2e": {"value": total / wall, "unit": "images/s", "h2d_GBps_per_gpu": st2["bytes_h2d"] / wall / 1e9,
+                "d2h_GBps_per_gpu": st2["bytes_d2h"] / wall / 1e9,
+                "h2d_bytes_per_image": geo.src_bytes, "d2h_bytes_per_image": geo.src_bytes + geo.r_bytes + geo.t_bytes},
+        "verified": verified, "verified_e2e_slot0_all_outputs": ok_e2e,
+    }
+
+
+def c5_stream_spec(seed, n):
+    """sizes log-uniform 0.3-48 MP, aspect in {4:3, 3:2, 16:9, 1:1, 3:4}, half JPEG -> YCbCr
+    4:2:0, half PNG -> RGBA / NRGBA.  The first two entries pin the range ends (640x480 and 8000x6000)."""
+    rng = np.random.default_rng(seed)
+    aspects = [(4, 3), (3, 2), (16, 9), (1, 1), (3, 4)]
+    out = []
+    for i in range(n):
+        if i == 0:
+            w, h = 8000, 6000
+        elif i == 1:
+            w, h = 640, 480
+        else:
+            mp = math.exp(rng.uniform(math.log(0.3e6), math.log(48e6)))
+            ax, ay = aspects[int(rng.integers(0, len(aspects)))]
+            h = int(round(math.sqrt(mp * ay / ax)))
+            w = int(round(h * ax / ay))
+            w, h = min(max(w, 320), 8000), min(max(h, 240), 8000)
+        kind = ("jpeg", "png", "jpeg", "png-alpha")[i % 4]
+        out.append((w, h, kind, seed * 1000 + i))
+    return out
+
+
+def config_c5(ip, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks):
+    """configs[4]: mixed-size stream, PNG+JPEG decoded on the host, end to end incl. H2D/D2H and host decode/encode, through
+    the streaming worker (worker.go:112-149 shape: W threads, each decode -> Process -> encode -> save)."""
+    from imageprocessor_b200 import codecs, processor as P
+    from imageprocessor_b200.worker import StreamingWorker
+    n = env_int("IPG_BENCH_STREAM_IMAGES", 32)
+    spec = c5_stream_spec(42 + rank, n)
+    t0 = time.perf_counter()
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max(2, min(16, (os.cpu_count() or 8) // max(world, 1)))) as pool:   # PIL releases the GIL
+        files = list(pool.map(lambda s: codecs.synth_file(s[0], s[1], s[3], s[2]), spec))
+    setup_s = time.perf_counter() - t0
+    ops = [{"Type": "thumbnail", "Parameters": {"size": 200, "crop_to_fit": True}},
+           {"Type": "resize", "Parameters": {"width": 1024, "height": 768, "keep_aspect": True}},
+           {"Type": "watermark", "Parameters": {"text": WM_TEXT, "opacity": 0.5, "position": "bottom-right"}}]
+
+    def task(i):
+        return {"ID": f"t{rank}-{i}", "ImageID": f"img{rank}-{i}", "OriginalPath": f"original/{i}", "Bucket": "images",
+                "Operations": ops, "Format": ""}
+
+    threads = env_int("IPG_BENCH_WORKER_THREADS", max(4, min(32, (os.cpu_count() or 8) // max(world, 1))))
+    eng = ip.Engine(devices=[local_rank], precision=ip.PRECISION_EXACT, lanes_per_device=4, max_batch=8, batch_window_us=200,
+                    lane_device_bytes=2 << 30, lane_pinned_bytes=1 << 30)
+    msgs = [(task(i), files[i]) for i in range(n)]
+
+    # pass A: the whole worker loop, real codecs (PIL stand-ins), objects saved to the in-memory repository
+    repo = P.MemoryFileRepo()
+    proc = P.ImageProcessor(eng, repo, encode=lambda a, f, q: codecs.encode(a, f, q))
+    wk = StreamingWorker(proc, threads)
+    wk.run(msgs[2:2 + min(6, n - 2)])              # warm-up: plan cache, pinned pools, PIL
+    barrier()
+    eng.reset_stats()
+    sA = wk.run(msgs)
+    eng.flush()
+    barrier()
+    stA = eng.stats()
+    wallA = max_over_ranks(sA.wall_s)
+    n_objects = len(repo.objects)
+    proc.close()
+
+    # pass B: raster only -- the same stream, already decoded (decode outside the timed region), outputs not encoded:
+    # what H2D + kernels + D2H cost end to end for this mix
+    decoded = [codecs.decode(f) for f in files]
+    repoB = P.MemoryFileRepo()
+    procB = P.ImageProcessor(eng, repoB, encode=lambda a, f, q: b"")
+    wkB = StreamingWorker(procB, threads, decode=lambda item: item)
+    msgsB = [(task(i), decoded[i]) for i in range(n)]
+    wkB.run(msgsB[2:8])
+    barrier()
+    eng.reset_stats()
+    sB = wkB.run(msgsB)
+    eng.flush()
+    barrier()
+    stB = eng.stats()
+    wallB = max_over_ranks(sB.wall_s)
+    procB.close()
+
+    # parity on a sampled subset (rank 0): same engine, lossless container instead of the lossy encoders
+    verified = None
+    if rank == 0:
+        from oracle import oracle as O
+        sample = [0, 1, 2, 3, 5, 6]              # 48 MP jpeg, 0.3 MP png, and one of each kind from the random part
+        repoV = P.MemoryFileRepo()
+        procV = P.ImageProcessor(eng, repoV, encode=P.raw_encode)
+        verified = {"images": [], "all_bit_exact": True}
+        for i in [k for k in sample if k < n]:
+            img, fmt = decoded[i]
+            res, err = procV.process(task(i), img, fmt)
+            ok = err is None
+            if ok:
+                if img.layout in (ip.RGBA8, ip.NRGBA8):
+                    R = O.Raster.rgba(img.planes[0].reshape(img.height, img.width, 4), img.layout)
+                elif img.layout == ip.GRAY8:
+                    R = O.Raster.gray(img.planes[0])
+                else:
+                    R = O.Raster.ycbcr(*img.planes, img.layout)
+                nw, nh = ip.keep_aspect_dims(img.width, img.height, RW, RH)
+                want = {"resize": O.resize_image(R, nw, nh), "thumbnail": O.crop_and_resize(R, THUMB)}
+                for op, path in res["ProcessedPaths"].items():
+                    got = P.raw_decode(repoV.objects[path][0])[1]
+                    if op == "watermark":
+                        wpx = (sum(procV.face.advance_26_6(ord(ch), 36.0) for ch in WM_TEXT) + 63) >> 6
+                        px, py = P.watermark_anchor("bottom-right", img.width, img.height, wpx, P.watermark_height_px(36.0))
+                        gl = O.drawstring_layout(procV.face, WM_TEXT, 36.0, img.width, img.height, px, py)
+                        want_w = O.watermark(R, (255, 255, 255, 127), [O.Glyph(*g) for g in gl])
+                        ok = ok and bool(np.array_equal(got, want_w))
+                    else:
+                        ok = ok and bool(np.array_equal(got, want[op]))
+                ok = ok and len(res["ProcessedPaths"]) == 3
+            verified["images"].append({"index": i, "size": f"{img.width}x{img.height}", "kind": spec[i][2], "bit_exact": bool(ok)})
+            verified["all_bit_exact"] = verified["all_bit_exact"] and bool(ok)
+        procV.close()
+    eng.close()
+
+    mp = sum(w * h for (w, h, _, _) in spec) / 1e6
+    tot_imgs = sum_over_ranks(float(n))
+    tot_mp = sum_over_ranks(mp)
+
+    def leg(s, st, wall):
+        d = s.summary()
+        return {"images_per_s": tot_imgs / wall, "megapixels_per_s": tot_mp / wall, "wall_s": wall,
+                "rank0_thread_seconds": d["thread_seconds"], "rank0_mean_ms_per_image": d["mean_ms_per_image"],
+                "rank0_failed": d["failed"],
+                "rank0_engine": {"h2d_MB": st["bytes_h2d"] / 1e6, "d2h_MB": st["bytes_d2h"] / 1e6, "kernel_ms": st["kernel_ms"],
+                                 "batches": st["batches"], "kernels_launched": st["kernels_launched"],
+                                 "exact_fallbacks": st["exact_fallbacks"], "staged_host_copies": st["staged_copies"],
+                                 "device_busy_frac_of_wall": st["kernel_ms"] / 1e3 / max(s.wall_s, 1e-9)}}
+
+    return {
+        "workload": "BASELINE configs[4]: mixed-size stream, sizes log-uniform 0.3-48 MP (incl. 640x480 and 8000x6000), aspects "
+                    "4:3/3:2/16:9/1:1/3:4, seed 42+rank; 1/2 JPEG -> planar YCbCr 4:2:0, 1/4 PNG -> RGBA, 1/4 PNG+alpha -> NRGBA; "
+                    "ops thumbnail(200, crop) + resize(1024x768 keep-aspect) + watermark per image",
+        "n_gpus": world, "images_per_gpu": n, "megapixels_per_gpu": mp, "worker_threads_per_gpu": threads,
+        "host_cores": os.cpu_count(),
+        "codecs": "PIL stand-ins on the host (libjpeg-turbo q85; libpng compress_level=1 -- Go's png.Encode default is zlib 6), timed apart "
+                  "from the raster work; outputs follow the reference's format rule (jpeg source -> jpeg, png -> png)",
+        "end_to_end_with_codecs": leg(sA, stA, wallA),
+        "raster_only_decoded_inputs_no_encode": leg(sB, stB, wallB),
+        "objects_saved_rank0": n_objects, "setup_s_untimed": setup_s, "verified": verified,
+    }
+
+
+# ---------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -219,9 +663,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=env_int("IPG_BENCH_IMAGES", 256), help="images per GPU per step")
+    ap.add_argument("--single-process", action="store_true",
+                    help="one process, one engine context over --gpus devices (north_star's layout) instead of one rank per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the c1 / c4 / c5 sub-records")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -240,9 +687,12 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    single = args.single_process and world == 1
+    n_dev = max(1, min(args.gpus, torch.cuda.device_count())) if single else 1
+    dev_ids = list(range(n_dev)) if single else [local_rank]
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa = bind_near_gpu(local_rank) if world > 1 else "single rank: not bound"
+    numa = bind_near_gpu(local_rank) if world > 1 else "single process: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -250,113 +700,42 @@ def main():
 
     def barrier():
         S.barrier()
-        torch.cuda.synchronize()
+        for d in dev_ids:
+            torch.cuda.synchronize(d)
 
     max_over_ranks, sum_over_ranks = S.reduce_max, S.reduce_sum
+    n_gpus_total = world * n_dev
 
     n_img = args.images
     lib = L.load()
-    eng = ip.Engine(devices=[local_rank], precision=ip.PRECISION_EXACT, lanes_per_device=3,
+    geo = Geometry(ip, G, L, W_IMG, H_IMG)
+    eng = ip.Engine(devices=dev_ids, precision=ip.PRECISION_EXACT, lanes_per_device=3,
                     max_batch=env_int("IPG_BENCH_MAX_BATCH", 128), batch_window_us=100)
-    ctx = eng._ctx
 
-    # ---- synthetic sources, resident in HBM (seeded per image; A=255)
-    gen = torch.Generator(device=dev)
-    srcs = []
-    for i in range(n_img):
-        gen.manual_seed(1000 + rank * n_img + i)
-        t = torch.randint(0, 256, (H_IMG, W_IMG, 4), dtype=torch.uint8, device=dev, generator=gen)
-        t[..., 3] = 255
-        srcs.append(t)
-    nw, nh = ip.keep_aspect_dims(W_IMG, H_IMG, RW, RH)
-    cx, cy, cs = ip.crop_square(W_IMG, H_IMG)
-    out_r = torch.empty((n_img, nh, nw, 4), dtype=torch.uint8, device=dev)
-    out_t = torch.empty((n_img, THUMB, THUMB, 4), dtype=torch.uint8, device=dev)
-    out_w = torch.empty((n_img, H_IMG, W_IMG, 4), dtype=torch.uint8, device=dev)
-    torch.cuda.synchronize()
-
-    glyph_list = G.layout_watermark(W_IMG, H_IMG, WM_TEXT, "bottom-right", 36.0)
-    color, _ = G.parse_color(WM_COLOR, WM_OPACITY)
-    garr = (L.Glyph * len(glyph_list))()
-    gkeep = []
-    for j, g in enumerate(glyph_list):
-        m = np.ascontiguousarray(g.mask, np.uint8)
-        gkeep.append(m)
-        garr[j].x0, garr[j].y0, garr[j].x1, garr[j].y1 = g.x0, g.y0, g.x1, g.y1
-        garr[j].mp_x, garr[j].mp_y = g.mp_x, g.mp_y
-        garr[j].mask_w, garr[j].mask_h, garr[j].mask_stride = m.shape[1], m.shape[0], m.strides[0]
-        garr[j].mask = m.ctypes.data
-
-    def make_ops(dst_r, dst_t, dst_w, memspace):
-        ops = (L.Op * 3)()
-        ops[0].kind, ops[0].dst_w, ops[0].dst_h = L.OP_RESIZE, nw, nh
-        ops[0].dst, ops[0].dst_stride, ops[0].dst_memspace = dst_r, nw * 4, memspace
-        ops[1].kind, ops[1].dst_w, ops[1].dst_h = L.OP_THUMB_CROP, THUMB, THUMB
-        ops[1].rect_x, ops[1].rect_y, ops[1].rect_w, ops[1].rect_h = cx, cy, cs, cs
-        ops[1].dst, ops[1].dst_stride, ops[1].dst_memspace = dst_t, THUMB * 4, memspace
-        ops[2].kind, ops[2].dst_w, ops[2].dst_h = L.OP_WATERMARK, W_IMG, H_IMG
-        for k in range(4):
-            ops[2].color[k] = color[k]
-        ops[2].n_glyphs, ops[2].glyphs = len(glyph_list), garr
-        ops[2].dst, ops[2].dst_stride, ops[2].dst_memspace = dst_w, W_IMG * 4, memspace
-        return ops
-
-    def make_desc(ptr, memspace):
-        d = L.ImageDesc()
-        d.layout, d.memspace, d.width, d.height = L.RGBA8, memspace, W_IMG, H_IMG
-        d.plane[0] = ptr
-        d.stride[0] = W_IMG * 4
-        d.opaque_hint = 0   # *image.RGBA: alpha unknown to the caller, as in the reference
-        return d
-
-    dev_descs = [make_desc(srcs[i].data_ptr(), L.MEM_DEVICE) for i in range(n_img)]
-    dev_ops = [make_ops(out_r[i].data_ptr(), out_t[i].data_ptr(), out_w[i].data_ptr(), L.MEM_DEVICE) for i in range(n_img)]
-    # two ticket sets: a worker keeps submitting, so step k+1 is submitted before step k is waited for (the
-    # batcher never starves between steps); every step's submissions and completions lie inside the timed region
-    tids = [(C.c_uint64 * n_img)() for _ in range(2)]
-    tid_ref = [[C.cast(C.byref(t, 8 * i), C.POINTER(C.c_uint64)) for i in range(n_img)] for t in tids]
-    submit_on, wait = lib.ipg_submit_on, lib.ipg_wait
-
-    def submit_step(k):
-        refs = tid_ref[k & 1]
-        for i in range(n_img):
-            rc = submit_on(ctx, 0, C.byref(dev_descs[i]), dev_ops[i], 3, refs[i])
-            if rc:
-                L.check(rc)
-
-    def wait_step(k):
-        t = tids[k & 1]
-        for i in range(n_img):
-            rc = wait(ctx, t[i], -1)
-            if rc:
-                L.check(rc)
-
-    def run_steps(n):
-        for k in range(n):
-            submit_step(k)
-            if k:
-                wait_step(k - 1)
-        if n:
-            wait_step(n - 1)
+    # ---- synthetic sources, resident in HBM (seeded per image; A=255): one batch per engine device
+    batches = [DeviceBatch(torch, geo, n_img, d, 1000 + (rank * n_dev + k) * n_img) for k, d in enumerate(dev_ids)]
+    for d in dev_ids:
+        torch.cuda.synchronize(d)
+    sub = Submitter(lib, L, eng._ctx, batches)
 
     # ---- device-resident throughput
-    run_steps(args.warmup)
+    sub.run_steps(args.warmup)
     barrier()
     eng.reset_stats()
     sampler = ClockSampler(local_rank)
     sampler.start()
     t0 = time.perf_counter()
-    run_steps(args.steps)
+    sub.run_steps(args.steps)
     eng.flush()
     barrier()
     wall_dev = time.perf_counter() - t0
-    clocks = sampler.stop()
     st = eng.stats()
     span_s = max_over_ranks(st["kernel_span_ms"] / 1e3)
-    total_images = sum_over_ranks(float(n_img * args.steps))
+    total_images = sum_over_ranks(float(n_img * n_dev * args.steps))
     value = total_images / span_s
     launches = int(sum_over_ranks(float(st["kernels_launched"])))
-    stream_ms_per_image = st["stream_kernel_ms"] / (n_img * args.steps)
+    imgs_run = n_img * n_dev * args.steps
+    stream_ms_per_image = st["stream_kernel_ms"] / imgs_run
     peak, peak_src = measured_peak()
     traffic = ncu_traffic()
 
@@ -365,134 +744,107 @@ def main():
     # Each pass alone is timed in a short extra run with the merge and the stream overlap switched off.
     lean_ms_run = st["stream_fast_kernel_ms"]
     launches_run = max(st["batches"], 1)
-    imgs_per_launch = n_img * args.steps / launches_run
-    merged_GBps = BYTES_PER_IMAGE * n_img * args.steps / (lean_ms_run * 1e-3) / 1e9
+    imgs_per_launch = imgs_run / launches_run
+    merged_GBps = geo.bytes_per_image * imgs_run / (lean_ms_run * 1e-3) / 1e9
     os.environ["IPG_NO_OVERLAP"] = "1"
     os.environ["IPG_MERGE_LEAN"] = "0"
-    eng_iso = ip.Engine(devices=[local_rank], precision=ip.PRECISION_EXACT, lanes_per_device=1,
+    eng_iso = ip.Engine(devices=[dev_ids[0]], precision=ip.PRECISION_EXACT, lanes_per_device=1,
                         max_batch=env_int("IPG_BENCH_MAX_BATCH", 128), batch_window_us=2000)
     del os.environ["IPG_NO_OVERLAP"], os.environ["IPG_MERGE_LEAN"]
     n_iso = min(n_img, 64)
+    b0 = batches[0]
     for rep in range(3):           # 2 warm-up passes, 1 timed
         if rep == 2:
             eng_iso.reset_stats()
         for i in range(n_iso):
-            L.check(submit_on(eng_iso._ctx, 0, C.byref(dev_descs[i]), dev_ops[i], 3, tid_ref[0][i]))
+            L.check(lib.ipg_submit_on(eng_iso._ctx, 0, C.byref(b0.descs[i]), b0.ops[i], 3, sub.refs[0][i]))
         for i in range(n_iso):
-            L.check(wait(eng_iso._ctx, tids[0][i], -1))
+            L.check(lib.ipg_wait(eng_iso._ctx, sub.tids[0][i], -1))
     iso = eng_iso.stats()
     eng_iso.close()
     pass_a_ms, both_ms = iso["stream_fast_kernel_ms"], iso["stream_kernel_ms"]
-    pass_a_GBps = BYTES_LEAN_PASS * n_iso / (pass_a_ms * 1e-3) / 1e9
-    pass_b_GBps = BYTES_THUMB_PASS * n_iso / (max(both_ms - pass_a_ms, 1e-9) * 1e-3) / 1e9
+    pass_a_GBps = geo.bytes_lean_pass * n_iso / (pass_a_ms * 1e-3) / 1e9
+    pass_b_GBps = geo.bytes_thumb_pass * n_iso / (max(both_ms - pass_a_ms, 1e-9) * 1e-3) / 1e9
     roofline = {
         "bound": "hbm",
         "kernel": "k_stream<1,true,4> (lean): per image a resize + watermark-copy pass and a thumbnail pass, all in one launch",
         "achieved": merged_GBps, "peak": peak, "unit": "GB/s", "frac": merged_GBps / peak, "peak_source": peak_src,
         "frac_of_nominal_8TBs": merged_GBps / 8000.0,
-        "algorithmic_bytes_per_image": BYTES_PER_IMAGE,
+        "algorithmic_bytes_per_image": geo.bytes_per_image,
         "algorithmic_note": "SURVEY.md 8(d) pipeline-min figure: the source counted ONCE although the thumbnail pass reads its "
                             "crop square a second time (DESIGN.md 4.1.3: two lean passes beat every fused form measured)",
         "images_per_launch": imgs_per_launch, "ms_per_launch": lean_ms_run / launches_run,
-        "how": "CUDA events on the launching stream around the kernel, summed over the K timed steps",
+        "how": "CUDA events on the launching stream around the kernel, summed over the K timed steps"
+               + (f" (single process: kernel time summed over {n_dev} devices, achieved = per-device average)" if n_dev > 1 else ""),
         "traffic": traffic["dram_bytes_per_image"] * imgs_per_launch if traffic else None,
         "traffic_note": (traffic.get("note") + f"; {traffic['dram_bytes_per_image'] / 1e6:.1f} MB per image x images_per_launch")
                         if traffic else "no ncu --set full capture committed yet",
         "kernel_share_of_step": lean_ms_run / max(st["kernel_ms"], 1e-9),
         "passes_timed_alone": {
             "how": f"second engine, IPG_MERGE_LEAN=0 IPG_NO_OVERLAP=1, {n_iso} device-resident images: each pass is its own launch",
-            "resize+watermark_copy": {"kernel": "k_stream<1,true,1>", "algorithmic_bytes_per_image": BYTES_LEAN_PASS,
+            "resize+watermark_copy": {"kernel": "k_stream<1,true,1>", "algorithmic_bytes_per_image": geo.bytes_lean_pass,
                                       "achieved": pass_a_GBps, "frac": pass_a_GBps / peak, "us_per_image": 1e3 * pass_a_ms / n_iso},
-            "thumbnail": {"kernel": "k_stream<1,false,2>", "algorithmic_bytes_per_image": BYTES_THUMB_PASS,
+            "thumbnail": {"kernel": "k_stream<1,false,2>", "algorithmic_bytes_per_image": geo.bytes_thumb_pass,
                           "achieved": pass_b_GBps, "frac": pass_b_GBps / peak, "us_per_image": 1e3 * (both_ms - pass_a_ms) / n_iso}},
         "stream_us_per_image": 1e3 * stream_ms_per_image,
         "fix_kernel_ms_per_step": st["fix_kernel_ms"] / args.steps,
-        "exact_fixups_per_image": st["exact_fixups"] / max(n_img * args.steps, 1),
+        "exact_fixups_per_image": st["exact_fixups"] / max(imgs_run, 1),
     }
 
-    # ---- verification of the timed outputs against the oracle (rank 0, one image)
+    # ---- verification of the timed outputs against the oracle (rank 0, one image per device)
     verified = None
     if rank == 0 and not args.no_verify:
         from oracle import oracle as O
-        a = srcs[0].cpu().numpy()
-        R = O.Raster.rgba(a)
-        ok_r = np.array_equal(out_r[0].cpu().numpy(), O.resize_image(R, nw, nh))
-        ok_t = np.array_equal(out_t[0].cpu().numpy(), O.crop_and_resize(R, THUMB))
-        ogl = [O.Glyph(g.x0, g.y0, g.x1, g.y1, g.mask, g.mp_x, g.mp_y) for g in glyph_list]
-        ok_w = np.array_equal(out_w[0].cpu().numpy(), O.watermark(R, color, ogl))
-        verified = {"resize_bit_exact": bool(ok_r), "thumb_bit_exact": bool(ok_t), "watermark_bit_exact": bool(ok_w)}
+        verified = batches[0].verify(O, 0)
+        for k in range(1, n_dev):
+            v = batches[k].verify(O, 0)
+            verified = {key: verified[key] and v[key] for key in verified}
 
     # ---- end to end through the C ABI with pinned host buffers
     e2e = None
+    host_imgs = [batches[0].srcs[s].cpu().numpy() for s in range(min(8, n_img))]
     if not args.no_e2e:
         # a separate context tuned for the PCIe-bound path: smaller batches, more lanes, so
         # the H2D of one batch overlaps the D2H of another
         eng.close()
-        eng = ip.Engine(devices=[local_rank], precision=ip.PRECISION_EXACT, lanes_per_device=4,
-                        max_batch=env_int("IPG_BENCH_E2E_BATCH", 8), batch_window_us=100)
-        ctx = eng._ctx
-        n_slots = min(env_int("IPG_BENCH_HOST_SLOTS", 64), n_img)
-        src_bytes = W_IMG * H_IMG * 4
-        pins = []
-        h_descs, h_ops = [], []
-        for s in range(n_slots):
-            p_in = eng.alloc_pinned(src_bytes)
-            p_in.array[:] = srcs[s].cpu().numpy().reshape(-1)
-            p_r, p_t, p_w = eng.alloc_pinned(nw * nh * 4), eng.alloc_pinned(THUMB * THUMB * 4), eng.alloc_pinned(src_bytes)
-            pins += [p_in, p_r, p_t, p_w]
-            h_descs.append(make_desc(p_in.ptr, L.MEM_HOST))
-            h_ops.append(make_ops(p_r.ptr, p_t.ptr, p_w.ptr, L.MEM_HOST))
-        submit = lib.ipg_submit_on
-
-        # a ring of n_slots pinned slots: slot s is re-submitted as soon as its previous ticket is done.  The K steps
-        # run as one stream of K * n_img submissions (a worker does not drain its pipeline between batches); every
-        # submission, copy and completion lies inside the timed region.
-        slot_tid = (C.c_uint64 * n_slots)()
-        slot_ref = [C.cast(C.byref(slot_tid, 8 * s), C.POINTER(C.c_uint64)) for s in range(n_slots)]
-
-        def run_host(n_steps):
-            total = n_steps * n_img
-            for j in range(total):
-                s = j % n_slots
-                if j >= n_slots:          # bounded in flight: slot s is free once its previous ticket is done
-                    rc = wait(ctx, slot_tid[s], -1)
-                    if rc:
-                        L.check(rc)
-                rc = submit(ctx, 0, C.byref(h_descs[s]), h_ops[s], 3, slot_ref[s])
-                if rc:
-                    L.check(rc)
-            for s in range(min(n_slots, total)):
-                rc = wait(ctx, slot_tid[s], -1)
-                if rc:
-                    L.check(rc)
-
-        del out_w
+        for b in batches:
+            del b.out_w
         torch.cuda.empty_cache()
-        run_host(max(1, min(args.warmup, 3)))
+        eng = ip.Engine(devices=dev_ids, precision=ip.PRECISION_EXACT, lanes_per_device=4,
+                        max_batch=env_int("IPG_BENCH_E2E_BATCH", 8), batch_window_us=100)
+        n_slots = min(env_int("IPG_BENCH_HOST_SLOTS", 64), n_img)
+        ring = HostRing(lib, L, eng, geo, host_imgs, n_slots, n_dev)
+        ring.run(max(1, min(args.warmup, 3)) * n_img * n_dev)
         barrier()
         eng.reset_stats()
         t0 = time.perf_counter()
-        run_host(args.steps)
+        ring.run(args.steps * n_img * n_dev)
         eng.flush()
         barrier()
         wall = max_over_ranks(time.perf_counter() - t0)
         st2 = eng.stats()
+        up, down = sum_over_ranks(st2["bytes_h2d"]) / wall / 1e9, sum_over_ranks(st2["bytes_d2h"]) / wall / 1e9
+        ceil_GBps, ceil_src = pcie_ceiling(n_gpus_total)
         e2e = {
             "value": total_images / wall, "unit": "images/s",
             "h2d_bytes_per_step": int(st2["bytes_h2d"] / args.steps), "d2h_bytes_per_step": int(st2["bytes_d2h"] / args.steps),
             "timing": "host wall clock around K steps submitted as one stream (barrier + flush both sides), max over ranks",
             "device_span_s": st2["batch_span_ms"] / 1e3,
-            "h2d_GBps": st2["bytes_h2d"] / wall / 1e9, "d2h_GBps": st2["bytes_d2h"] / wall / 1e9,
-            "host_buffers": f"{n_slots} pinned slots per rank (ipg_alloc_pinned), zero staging copies: {st2['staged_copies'] == 0}",
+            "h2d_GBps": up / n_gpus_total, "d2h_GBps": down / n_gpus_total,
+            "h2d_GBps_aggregate": up, "d2h_GBps_aggregate": down,
+            "pcie": {"bound": "pcie", "unit": "GB/s per direction, aggregate over the run's GPUs, both directions busy",
+                     "achieved": min(up, down), "peak": ceil_GBps,
+                     "frac_of_pcie": (min(up, down) / ceil_GBps) if ceil_GBps else None,
+                     "peak_source": f"tools/micro/pcie_scale.cu, {ceil_src}: {n_gpus_total} device(s) copying H2D + D2H concurrently, "
+                                    "cudaHostAlloc memory, 48 MB per cudaMemcpyAsync" if ceil_GBps else "no committed pcie_scale run for this N"},
+            "host_buffers": f"{n_slots} pinned slots per GPU (ipg_alloc_pinned), zero staging copies: {st2['staged_copies'] == 0}",
             "verified_slot0": None,
         }
         if rank == 0 and not args.no_verify:
             from oracle import oracle as O
-            a = pins[0].array.reshape(H_IMG, W_IMG, 4)
-            e2e["verified_slot0"] = bool(np.array_equal(pins[1].array.reshape(nh, nw, 4),
-                                                        O.resize_image(O.Raster.rgba(a), nw, nh)))
-        for p in pins:
-            p.free()
+            e2e["verified_slot0"] = ring.verify_slot0(O)
+        ring.free()
+    clocks = sampler.stop()   # sampled across the device-resident AND the end-to-end leg
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
@@ -500,30 +852,53 @@ def main():
         from oracle import oracle as O
         cores = os.cpu_count() or 1
         n_s = env_int("IPG_BENCH_CPU_IMAGES", 8 * cores)
-        host_imgs = [srcs[i % n_img].cpu().numpy() for i in range(min(n_s, 4))]
         rasters = [O.Raster.rgba(host_imgs[i % len(host_imgs)]) for i in range(n_s)]
-        ogl = [O.Glyph(g.x0, g.y0, g.x1, g.y1, g.mask, g.mp_x, g.mp_y) for g in glyph_list]
-        secs, _ = O.bench_batch(rasters, cores, 7, RW, RH, True, THUMB, color, ogl)
+        ogl = [O.Glyph(g.x0, g.y0, g.x1, g.y1, g.mask, g.mp_x, g.mp_y) for g in geo.glyph_list]
+        secs, _ = O.bench_batch(rasters, cores, 7, RW, RH, True, THUMB, geo.color, ogl)
         cpu = {"value": n_s / secs, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"{n_s} images of the same workload, one per host thread, one pass ({secs:.1f} s)",
+               "sample": f"{n_s} images of the same workload ({len(host_imgs)} distinct), one per host thread, one pass ({secs:.1f} s)",
                "note": "restated reference CPU path (C, float64 scalar), not the Go build"}
+
+    # ---- the other BASELINE configs, each measured and parity-checked
+    configs = None
+    if not args.no_configs and not single:
+        eng.close()
+        eng = None
+        del batches, sub
+        torch.cuda.empty_cache()
+        configs = {}
+        try:
+            if rank == 0:
+                e1 = ip.Engine(devices=[local_rank], precision=ip.PRECISION_EXACT, lanes_per_device=2, max_batch=4, batch_window_us=0)
+                configs["c1"] = config_c1(ip, e1)
+                e1.close()
+            barrier()
+            configs["c4"] = config_c4(ip, L, lib, torch, G, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks,
+                                      max(2, min(args.steps, 4)))
+            configs["c5"] = config_c5(ip, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks)
+        except Exception as e:  # noqa: BLE001 -- a sub-record must not take the headline line down; it says what failed
+            import traceback
+            configs["error"] = f"{type(e).__name__}: {e}"
+            configs["traceback"] = traceback.format_exc()[-1500:]
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n_gpus_total, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * span_s / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world, n_img),
+            "config": workload_config(n_gpus_total, n_img),
+            "process_model": f"one process, one engine context over {n_dev} device(s)" if single else "one rank per GPU",
             "timing": "CUDA events on the launching streams: first kernel start -> last kernel end over the K steps, max over ranks; "
                       "step k+1 is submitted before step k is waited for (a worker keeps submitting), all inside the timed region",
             "wall_ms_per_step": 1e3 * wall_dev / args.steps,
-            "hbm_GBps": value * BYTES_PER_IMAGE / 1e9 / world,
+            "hbm_GBps": value * geo.bytes_per_image / 1e9 / n_gpus_total,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "e2e": e2e, "verified": verified,
+            "cpu_baseline": cpu, "e2e": e2e, "verified": verified, "configs": configs,
             "host": {"nproc": os.cpu_count(), "numa_binding_rank0": numa},
         }
         print(json.dumps(line), flush=True)
-    eng.close()
+    if eng is not None:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
 

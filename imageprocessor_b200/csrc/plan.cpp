@@ -113,6 +113,24 @@ std::shared_ptr<const AxisPlan> get_axis_plan(int dn, int sn)
 
 // ---------------------------------------------------------------------------------
 
+// The fp32 certificate (DESIGN.md 2.1 derives it term by term).  Units: 1/256 of a 16-bit step, i.e. the LSB of
+// T = floor(v * 256 + 128), the 16.8 fixed-point value whose bits 16.. are the output byte.  For one output channel
+//   |T_fp32 - T_exact| <= 2                     the two fp32-rounded weights on every term (relative 2^-24 each, value < 2^16)
+//                        + 0.5 * taps_y          one round-to-nearest per vertical fmaf, partial sums < 2^16 (half ulp = 2^-9)
+//                        + 0.5 * taps_x          one per horizontal fmaf
+//                        + log2(P)               the xor-butterfly over the P threads sharing an output (<= 1 per level)
+//                        + 0.5                   the rounding of fmaf(v, 256, 128) itself (values in [2^23, 2^24): ulp 1)
+//                        + 1                     floor() against the exact, unfloored value
+//                        (+ < 0.001              the float64 reference's own rounding)
+// so D = ceil((taps_x + taps_y) / 2) + log2(P) + 4 covers it, and one more unit of margin is added on top.
+// A byte can differ from the float64 result only when a multiple of 65536 lies within D of T: those are flagged.
+int certified_fix_d(int taps_x, int taps_y, int parts)
+{
+    int lg = 0;
+    while ((1 << lg) < parts) lg++;
+    return (taps_x + taps_y + 1) / 2 + lg + 5;
+}
+
 static bool build_target(StreamGeom &g, int ti, const StreamTargetSpec &s, double sample_scale)
 {
     StreamTargetGeom &t = g.t[ti];
@@ -240,9 +258,11 @@ static bool build_target(StreamGeom &g, int ti, const StreamTargetSpec &s, doubl
     }
     if (oy != s.dh) return false;
 
-    // |fp32 - exact| <= (taps_x + taps_y + 3) units of 1/256 of a 16-bit step
-    // (DESIGN.md "certified fp32"); +3 units of margin on top.
-    t.fix_d = ax.max_taps + ay.max_taps + 6;
+    t.fix_d = certified_fix_d(ax.max_taps, ay.max_taps, [&] {
+        int p = 1;
+        for (int32_t v : t.tile_parts) p = std::max(p, (int)(v & 255));
+        return p;
+    }());
     return true;
 }
 

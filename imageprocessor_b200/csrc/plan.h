@@ -25,6 +25,10 @@ struct AxisPlan {
 
 std::shared_ptr<const AxisPlan> get_axis_plan(int dn, int sn); // cached, thread-safe
 
+// Half-width of the ambiguity window of the fp32 streaming kernels, in 1/256 of a 16-bit step, for a target whose
+// widest supports are taps_x / taps_y and whose horizontal pass splits an output over `parts` threads (plan.cpp).
+int certified_fix_d(int taps_x, int taps_y, int parts);
+
 struct StreamTargetSpec {
     int32_t rect_x, rect_y, rect_w, rect_h;
     int32_t dw, dh;

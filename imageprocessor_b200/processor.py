@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes as C
 import io
 import json
+import threading
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -179,7 +180,7 @@ class ImageProcessor:
         self.encode = encode
         self.face = face or PilFace()
         self._live = {}
-        self._mask_keep = None
+        self._tls = threading.local()   # Process is re-entrant (WORKER_CONCURRENCY threads): the mask handed to C lives per thread
 
         def _encode(user, rgba, w, h, stride, fmt, quality, out, out_len):
             try:
@@ -213,12 +214,12 @@ class ImageProcessor:
         def _mask(user, rune, size, fx, fy, out):
             try:
                 adv, ox, oy, m = self.face.mask(rune, size, fx, fy)
-                self._mask_keep = np.ascontiguousarray(m)
+                keep = self._tls.mask_keep = np.ascontiguousarray(m)
                 g = out[0]
                 g.advance_26_6, g.off_x, g.off_y = adv, ox, oy
                 g.mask_h, g.mask_w = (m.shape if m.size else (0, 0))
                 g.mask_stride = m.shape[1] if m.size else 0
-                g.mask = self._mask_keep.ctypes.data if m.size else None
+                g.mask = keep.ctypes.data if m.size else None
                 return 0
             except Exception:
                 return -1

@@ -14,6 +14,12 @@
 
 using namespace ipg;
 
+// optional capture (tests of the error bound): per target, dw * dh * 4 floats receiving fmaf(v, 256, 128) -- the
+// 16.8 fixed-point value before floor() -- of every channel
+static float *g_capture[2] = {nullptr, nullptr};
+extern "C" void planemu_capture(float *t0, float *t1) { g_capture[0] = t0; g_capture[1] = t1; }
+extern "C" int planemu_fix_d(int taps_x, int taps_y, int parts) { return certified_fix_d(taps_x, taps_y, parts); }
+
 static inline int quant16(float v, int D, bool &amb)
 {
     const uint32_t T = (uint32_t)std::min((int)std::floor(std::fmaf(v, 256.0f, 128.0f)), 0xffffff);
@@ -134,6 +140,8 @@ static int run_impl(const SAMPLE *src, int stride, int W, int H, int n_targets, 
                             bool amb = false;
                             uint8_t *d = dsts[t] + ((size_t)oy * sp[t].dw + ox) * 4;
                             for (int ch = 0; ch < 4; ch++) d[ch] = (uint8_t)quant16(s[ch], tg.fix_d, amb);
+                            if (g_capture[t])
+                                for (int ch = 0; ch < 4; ch++) g_capture[t][((size_t)oy * sp[t].dw + ox) * 4 + ch] = std::fmaf(s[ch], 256.0f, 128.0f);
                             if (flags && flags[t]) flags[t][(size_t)oy * sp[t].dw + ox] += amb ? 1 : 16; // 16: written once
                         }
                     }
@@ -144,6 +152,7 @@ static int run_impl(const SAMPLE *src, int stride, int W, int H, int n_targets, 
     if (info) {
         info[0] = g->n_tiles; info[1] = g->n_bands; info[2] = g->tile_w;
         info[3] = (int)g->items.size(); info[4] = (int)std::min<long>(rows_read, 2147483647L);
+        info[5] = g->t[0].fix_d; info[6] = n_targets > 1 ? g->t[1].fix_d : 0;
     }
     return 0;
 }

@@ -171,26 +171,7 @@ def test_glyph_mask_cache_is_freetypes_direct_mapped_table():
 
 
 # ---- end to end on the GPU --------------------------------------------------------------
-def go_drawstring_layout(face, text, size, W, H, px, py):
-    """freetype.Context.DrawString restated for the oracle side of the test (26.6 pen, the
-    (rune, quarter-pixel) mask cache, per-rune clipped rectangle with mask point (0, dy))."""
-    pen_x, pen_y = px * 64, py * 64
-    cache, out = {}, []
-    for ch in text:
-        r = ord(ch)
-        ix, fx, iy, fy = pen_x >> 6, pen_x & 63, pen_y >> 6, pen_y & 63
-        idx = face.index(r)
-        slot = ((idx % 256) * 4 + fx // 16) * 1 + fy // 64
-        if slot not in cache or cache[slot][0] != idx:
-            cache[slot] = (idx, face.mask(r, size, fx, fy))
-        adv, ox, oy, m = cache[slot][1]
-        if m.size:
-            gx0, gy0 = ix + ox, iy + oy
-            x0, y0, x1, y1 = max(gx0, 0), max(gy0, 0), min(gx0 + m.shape[1], W), min(gy0 + m.shape[0], H)
-            if x0 < x1 and y0 < y1:
-                out.append((x0, y0, min(x1, x0 + m.shape[1]), y1, m, 0, y0 - gy0))
-        pen_x += adv
-    return out
+from oracle.oracle import drawstring_layout as go_drawstring_layout  # noqa: E402
 
 
 @pytest.mark.gpu

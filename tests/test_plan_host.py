@@ -39,7 +39,7 @@ def run_emu(L, a, specs, two_stage, bands_hint=4):
     flags = [np.zeros((s[5], s[4]), np.uint8) for s in specs]
     dp = (C.c_void_p * n)(*[d.ctypes.data for d in dsts])
     fp = (C.c_void_p * n)(*[f.ctypes.data for f in flags])
-    info = np.zeros(5, np.int32)
+    info = np.zeros(8, np.int32)
     rc = L.planemu_run(a.ctypes.data, a.strides[0], w, h, n, sp.ctypes.data, ts.ctypes.data, dp, fp,
                        bands_hint, info.ctypes.data)
     return rc, dsts, flags, info
@@ -178,7 +178,7 @@ def run_emu16(L, s, spec, two_stage, bands_hint=4):
     ts = np.array([two_stage], np.int32)
     dst, flag = np.zeros((spec[5], spec[4], 4), np.uint8), np.zeros((spec[5], spec[4]), np.uint8)
     dp, fp = (C.c_void_p * 1)(dst.ctypes.data), (C.c_void_p * 1)(flag.ctypes.data)
-    info = np.zeros(5, np.int32)
+    info = np.zeros(8, np.int32)
     rc = L.planemu_run16(s.ctypes.data, w * 4, w, h, 1, sp.ctypes.data, ts.ctypes.data, dp, fp, bands_hint, info.ctypes.data)
     return rc, dst, flag
 
@@ -202,3 +202,189 @@ def test_sixteen_bit_sample_kernels_certified_fp32(emu, oracle, kind):
             diff = np.abs(d.astype(int) - ref().astype(int)).max(axis=2)
             assert diff[~amb].max(initial=0) == 0, f"{kind} {spec}: an unflagged byte differs from the fp64 oracle"
             assert diff.max(initial=0) <= 1 and amb.mean() < 0.03
+
+
+# ---- the fp32 certificate, attacked (DESIGN.md 2.1 has the derivation) ---------------------------
+def exact_T(oracle, a8, spec):
+    """256 * v + 128 for every output channel in float64 from dense weight matrices (error ~1e-9 units): the real
+    value the fp32 kernel approximates, in the units of the certificate (1/256 of a 16-bit step)."""
+    rx, ry, rw, rh, dw, dh = spec
+
+    def dense(dn, sn):
+        st, co, w, inv = oracle.distrib(dn, sn)
+        M = np.zeros((dn, sn), np.float64)
+        for o in range(dn):
+            M[o, co[st[o]:st[o + 1]]] = w[st[o]:st[o + 1]] * inv[o]
+        return M, int(np.diff(st).max())
+
+    Mx, tx = dense(dw, rw)
+    My, ty = dense(dh, rh)
+    crop = a8[ry:ry + rh, rx:rx + rw].astype(np.float64) * 257.0
+    T = np.empty((dh, dw, 4))
+    for ch in range(4):
+        T[..., ch] = (My @ crop[..., ch] @ Mx.T) * 256.0 + 128.0
+    return T, tx, ty
+
+
+def run_emu_capture(L, a, spec, two_stage, bands=3):
+    cap = np.zeros((spec[5], spec[4], 4), np.float32)
+    L.planemu_capture.argtypes = [C.c_void_p, C.c_void_p]
+    L.planemu_capture(cap.ctypes.data, None)
+    try:
+        rc, dsts, flags, info = run_emu(L, a, [spec], [two_stage], bands)
+    finally:
+        L.planemu_capture(None, None)
+    return rc, dsts[0], flags[0], info, cap
+
+
+def adversarial_images(w, h):
+    yield "random", rgba_random(w, h, 5)
+    a = np.full((h, w, 4), 255, np.uint8)
+    yield "all-255 (largest partial sums: every rounding at its half-ulp maximum)", a
+    for period, phase in [(2, 0), (2, 1), (3, 1), (5, 2), (7, 3)]:
+        a = np.zeros((h, w, 4), np.uint8)
+        a[..., 3] = 255
+        a[(np.arange(h) % period) == phase, :, :3] = 255
+        yield f"row stripes {period}/{phase}", a
+        a = np.zeros((h, w, 4), np.uint8)
+        a[..., 3] = 255
+        a[:, (np.arange(w) % period) == phase, :3] = 255
+        yield f"column stripes {period}/{phase}", a
+    yy, xx = np.mgrid[0:h, 0:w]
+    a = np.zeros((h, w, 4), np.uint8)
+    a[..., 3] = 255
+    a[..., :3] = (((yy + xx) & 1) * 255)[..., None]
+    yield "checkerboard", a
+
+
+@pytest.mark.parametrize("w,h,spec", [
+    (400, 300, (0, 0, 400, 300, 102, 76)),        # the 4:1 resize shape (8 x 8 taps)
+    (1000, 750, (125, 0, 750, 750, 50, 50)),      # the 15:1 thumbnail shape (29-31 taps, split over 4 threads)
+    (640, 480, (0, 0, 640, 480, 512, 384)),       # mild 1.25:1 downscale (several outputs per lane)
+    (900, 880, (10, 0, 880, 880, 20, 20)),        # 44:1 -- the 8K thumbnail's support (87-89 taps is past it; 44 here)
+])
+def test_fp32_error_stays_inside_the_proven_bound(emu, oracle, w, h, spec):
+    """max |T_fp32 - T_exact| over adversarial images must stay below the derived bound, with the flag rule
+    (window D = bound + floor + margin) catching every byte that differs from the float64 oracle."""
+    worst = 0.0
+    for name, a in adversarial_images(w, h):
+        rc, d, f, info, cap = run_emu_capture(emu, a, spec, 0)
+        assert rc == 0, name
+        T, tx, ty = exact_T(oracle, a, spec)
+        D = int(info[5])
+        err = np.abs(cap.astype(np.float64) - T)
+        # the clamp to alpha acts on r, g, b only when they exceed alpha: opaque inputs here, so it never binds
+        worst = max(worst, float(err.max()))
+        assert err.max() <= D - 2, f"{name}: |T_fp32 - T_exact| = {err.max():.2f} exceeds the proven bound {D - 2} (D = {D})"
+        rx, ry, rw, rh, dw, dh = spec
+        ref = oracle.scale_bilinear(oracle.Raster.rgba(a), (rx, ry, rw, rh), dw, dh)
+        amb = f == 1
+        assert np.array_equal(d[~amb], ref[~amb]), f"{name}: an unflagged byte differs from the float64 oracle"
+        assert np.abs(d.astype(int) - ref.astype(int)).max() <= 1
+    print(f"{spec}: taps {tx}x{ty}, D = {D}, worst observed |dT| = {worst:.2f}")
+    assert D == emu.planemu_fix_d(tx, ty, 1) or D > emu.planemu_fix_d(tx, ty, 1)   # parts only ever widen the window
+
+
+def test_constants_sit_mid_cell_and_are_never_flagged(emu, oracle):
+    """byte * 0x101 puts an exact constant at T = c * 65792 + 128: 128 units from either quantiser step, so a constant
+    region is never ambiguous while D < 128 -- every value 0..255, inside bands 3 supports tall."""
+    w, band = 256, 40
+    a = np.zeros((256 * band, w, 4), np.uint8)
+    a[..., 3] = 255
+    for c in range(256):
+        a[c * band:(c + 1) * band, :, :3] = c
+    spec = (0, 0, w, 256 * band, 64, 256 * band // 4)
+    rc, d, f, info, cap = run_emu_capture(emu, a, spec, 0, 8)
+    assert rc == 0 and info[5] < 128
+    for c in range(256):
+        rows = slice(c * band // 4 + 3, (c + 1) * band // 4 - 3)       # output rows whose support lies inside band c
+        assert (d[rows, :, :3] == c).all() and (d[rows, :, 3] == 255).all()
+        assert (f[rows] == 16).all(), f"constant {c} was flagged"
+        assert np.all(np.abs(cap[rows, :, 0] - (c * 65792 + 128)) <= info[5] - 2)
+
+
+def test_values_engineered_onto_a_quantiser_step_are_flagged(emu, oracle):
+    """For a handful of output pixels the source bytes under their support are searched until the EXACT value sits
+    within a few hundredths of a unit of a quantiser step (256 v + 128 = 65536 m): the worst case for the certificate.
+    Every one of them must be flagged, and no unflagged byte anywhere may differ from the float64 oracle."""
+    w, h, spec = 400, 300, (0, 0, 400, 300, 102, 76)
+    a = rgba_random(w, h, 77)
+    stx, cox, wx, invx = oracle.distrib(102, 400)
+    sty, coy, wy, invy = oracle.distrib(76, 300)
+    rng = np.random.default_rng(1)
+    targets = [(ox, oy) for oy in range(5, 70, 9) for ox in range(6, 96, 11)]
+    hit = []
+    for (ox, oy) in targets:
+        xs, ys = cox[stx[ox]:stx[ox + 1]], coy[sty[oy]:sty[oy + 1]]
+        c = 257.0 * 256.0 * np.outer(wy[sty[oy]:sty[oy + 1]] * invy[oy], wx[stx[ox]:stx[ox + 1]] * invx[ox])  # units per byte step
+        ch = int(rng.integers(0, 3))
+        blk = a[ys[0]:ys[-1] + 1, xs[0]:xs[-1] + 1, ch].astype(np.int64)
+        T = float((c * blk).sum()) + 128.0
+        goal = round(T / 65536.0) * 65536.0
+        goal = min(max(goal, 65536.0), 255 * 65536.0)
+        r = goal - T
+        # best single or pairwise +-1 move per round (differences of two weights reach far below the smallest weight)
+        cf, bf = c.reshape(-1), blk.reshape(-1)
+        n = cf.size
+        for it in range(600):
+            if abs(r) < 0.02:
+                break
+            if abs(r) > 2.0 * cf.max():                          # coarse phase: the largest whole step any one tap allows
+                step = np.clip(np.round(r / cf), -bf, 255 - bf).astype(np.int64)
+                q = int(np.argmin(np.abs(r - cf * step)))
+                if step[q] != 0:
+                    bf[q] += step[q]
+                    r -= cf[q] * step[q]
+                    continue
+            up, dn = bf < 255, bf > 0
+            cand = []                                            # (delta of T, i, di, j, dj)
+            one = np.concatenate([np.where(up, cf, np.inf), np.where(dn, -cf, np.inf)])
+            k = int(np.argmin(np.abs(r - one)))
+            cand.append((one[k], k % n, 1 if k < n else -1, -1, 0))
+            for di, mi in ((1, up), (-1, dn)):
+                for dj, mj in ((1, up), (-1, dn)):
+                    M = di * cf[:, None] + dj * cf[None, :]
+                    M = np.where(mi[:, None] & mj[None, :], M, np.inf)
+                    np.fill_diagonal(M, np.inf)
+                    k = int(np.argmin(np.abs(r - M)))
+                    cand.append((M.reshape(-1)[k], k // n, di, k % n, dj))
+            dT, i, di, j, dj = min(cand, key=lambda t: abs(r - t[0]))
+            if not np.isfinite(dT) or abs(r - dT) >= abs(r):
+                q = int(rng.integers(0, n))                                  # stuck: nudge one tap and go on
+                bf[q] = min(max(bf[q] + int(rng.integers(-2, 3)), 0), 255)
+                r = goal - (float((cf * bf).sum()) + 128.0)
+                continue
+            bf[i] += di
+            if j >= 0:
+                bf[j] += dj
+            r -= dT
+        blk = bf.reshape(blk.shape)
+        a[ys[0]:ys[-1] + 1, xs[0]:xs[-1] + 1, ch] = blk.astype(np.uint8)
+        hit.append((ox, oy, ch, abs(r)))
+    assert sum(1 for t in hit if t[3] < 0.5) >= len(hit) * 0.6, "the search failed to reach the step"
+    rc, d, f, info, cap = run_emu_capture(emu, a, spec, 0)
+    assert rc == 0
+    T, _, _ = exact_T(oracle, a, spec)
+    ref = oracle.resize_image(oracle.Raster.rgba(a), 102, 76)
+    amb = f == 1
+    assert np.array_equal(d[~amb], ref[~amb]), "an unflagged byte differs from the float64 oracle"
+    for (ox, oy, ch, r) in hit:
+        if r < 0.5:
+            dist = abs(((T[oy, ox, ch] + 32768.0) % 65536.0) - 32768.0)
+            assert dist < 1.0 and amb[oy, ox], f"pixel ({ox},{oy}) sits {dist:.3f} units from a step and was not flagged"
+
+
+def test_8k_thumbnail_support_certified(emu, oracle):
+    """The 8K crop thumbnail: 4320 -> 200, 44 taps per axis, one output split over 4 threads -- the widest support of
+    the BASELINE configs (the 48 MP one, 61 taps, runs on the GPU in tests/test_full_size.py)."""
+    w, h = 2592, 2160       # half-scale 8K with the same 21.6:1 ratio and tap counts: crop 2160^2 -> 100
+    a = rgba_random(w, h, 8)
+    spec = (216, 0, 2160, 2160, 100, 100)
+    rc, d, f, info, cap = run_emu_capture(emu, a, spec, 1, 4)
+    assert rc == 0
+    T, tx, ty = exact_T(oracle, a, spec)
+    assert tx >= 44 and ty >= 44
+    assert np.abs(cap.astype(np.float64) - T).max() <= info[5] - 2
+    ref = oracle.crop_and_resize(oracle.Raster.rgba(a), 100)
+    amb = f == 1
+    assert np.array_equal(d[~amb], ref[~amb]) and np.abs(d.astype(int) - ref.astype(int)).max() <= 1
