@@ -62,7 +62,8 @@ class Stats(C.Structure):
                 ("kernel_ms", C.c_double), ("stream_kernel_ms", C.c_double),
                 ("fix_kernel_ms", C.c_double), ("other_kernel_ms", C.c_double),
                 ("kernel_span_ms", C.c_double), ("batch_span_ms", C.c_double),
-                ("stream_fast_kernel_ms", C.c_double), ("fast_jobs", C.c_uint64)]
+                ("stream_fast_kernel_ms", C.c_double), ("fast_jobs", C.c_uint64),
+                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

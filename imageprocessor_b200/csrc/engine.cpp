@@ -247,6 +247,7 @@ struct Lane {
     cudaEvent_t evf = nullptr;      // after the lean k_stream launch
     cudaEvent_t begin = nullptr;    // before the batch's first H2D (upload stream)
     cudaEvent_t uploaded = nullptr; // after its last H2D (upload stream)
+    cudaEvent_t dl_begin = nullptr; // before its first D2H (download stream, after the wait for the kernels)
     cudaEvent_t done = nullptr;     // after its last D2H (download stream)
     uint8_t *arena = nullptr;
     size_t arena_bytes = 0;
@@ -275,7 +276,16 @@ struct Device {
     // H2D queues behind another lane's D2H; two dedicated streams always run both directions.
     cudaStream_t up = nullptr, down = nullptr;
     cudaEvent_t epoch = nullptr;
-    cudaEvent_t last_compute = nullptr; // end-of-kernels event of the most recent batch (owned by its lane)
+    // Compute sections of consecutive batches (different lanes) are ordered by events owned by the earlier batch's lane:
+    // the next batch's stream kernels wait for `last_stream` (end of the previous batch's k_stream section) and its
+    // fix / blend section waits for `last_compute` (end of the previous batch's last kernel).  So the small latency-bound
+    // tail of batch k (k_exact_fix, k_exact_fix_wide, k_blend: ~8 % of a step) runs beside the bandwidth-bound k_stream
+    // of batch k+1 instead of in front of it, while two k_stream sections still never evict each other.
+    cudaEvent_t last_stream = nullptr;
+    cudaEvent_t last_compute = nullptr;
+    cudaEvent_t prev_compute = nullptr; // ... and of the batch before that: a stream section never starts before the tail
+                                        // two batches back has finished (callers that resubmit the same destination
+                                        // buffers back to back keep the old "later batch wins" behaviour)
     double k_first = 1e300, k_last = -1, b_first = 1e300, b_last = -1;
 };
 
@@ -303,11 +313,12 @@ struct Ctx {
     uint32_t band_cta_target = 1400;
     uint32_t fix_capacity = 0;     // IPG_FIX_CAPACITY: fix-list entries per batch (0: sized from the batch); tests force the overflow paths with it
     bool overlap_streams = true; // IPG_NO_OVERLAP=1: lean and general k_stream launches back to back (per-kernel timing)
+    bool overlap_tail = true;    // IPG_OVERLAP_TAIL=0: a batch's kernels start only after the previous batch's last kernel
     int staging_timeout_ms = 2000; // IPG_STAGING_TIMEOUT_MS: how long ipg_submit waits for pinned staging before IPG_ERR_NOMEM
     // stats
     std::atomic<uint64_t> s_done{0}, s_batches{0}, s_kernels{0}, s_h2d{0}, s_d2h{0}, s_fix{0}, s_fallback{0}, s_staged{0};
     std::mutex smu;
-    double s_stream_ms = 0, s_fix_ms = 0, s_other_ms = 0, s_fast_ms = 0;
+    double s_stream_ms = 0, s_fix_ms = 0, s_other_ms = 0, s_fast_ms = 0, s_h2d_ms = 0, s_d2h_ms = 0;
     std::atomic<uint64_t> s_fast_jobs{0};
 };
 
@@ -820,7 +831,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     // ---- kernels.  Compute sections of different lanes run one after another (each kernel
     // already fills the GPU; overlapping them only makes them evict each other), while the
     // copies of the other lanes overlap with them.
-    if (d.last_compute) IPG_CU(cudaStreamWaitEvent(st, d.last_compute, 0));
+    if (cudaEvent_t prev = c.overlap_tail ? d.last_stream : d.last_compute) IPG_CU(cudaStreamWaitEvent(st, prev, 0));
+    if (c.overlap_tail && d.prev_compute) IPG_CU(cudaStreamWaitEvent(st, d.prev_compute, 0));
     if ((!fitems.empty() || !f2items.empty() || !f3items.empty()) && redo_flags) IPG_CU(cudaMemsetAsync(redo_flags, 0, 4 * max_jobs, st));
     IPG_CU(cudaEventRecord(L.ev[0], st));
     // Two streams: the lean local-target launch (resize + watermark copy) on the lane's stream; beside it, on a
@@ -875,6 +887,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
         B.n_kernels++;
     }
     IPG_CU(cudaEventRecord(L.ev[1], st));
+    d.last_stream = L.ev[1];
+    if (c.overlap_tail && d.last_compute) IPG_CU(cudaStreamWaitEvent(st, d.last_compute, 0)); // tails stay in batch order
     if (!fixjobs.empty()) {
         IPG_CU(launch_exact_fix(d_fixjobs, (int)fixjobs.size(), fix, st));
         B.n_kernels += 2; // k_exact_fix + k_exact_fix_wide
@@ -893,10 +907,12 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
         B.n_kernels++;
     }
     IPG_CU(cudaEventRecord(L.ev[3], st));
+    d.prev_compute = d.last_compute;
     d.last_compute = L.ev[3];
 
     // ---- read back
     IPG_CU(cudaStreamWaitEvent(down, L.ev[3], 0));
+    IPG_CU(cudaEventRecord(L.dl_begin, down));
     if (B.has_fix) IPG_CU(cudaMemcpyAsync(L.fix_count_host, fix.count, 16, cudaMemcpyDeviceToHost, down));
     for (auto &r : readbacks) {
         if (r.pitch == r.hstride)
@@ -1011,6 +1027,9 @@ static void completer_main(Ctx *c, Device *d)
                 cudaEventElapsedTime(&a, L.ev[0], L.ev[1]);
                 cudaEventElapsedTime(&b, L.ev[1], L.ev[2]);
                 cudaEventElapsedTime(&o, L.ev[2], L.ev[3]);
+                float up_ms = 0, down_ms = 0;
+                cudaEventElapsedTime(&up_ms, L.begin, L.uploaded);
+                cudaEventElapsedTime(&down_ms, L.dl_begin, L.done);
                 float t0 = 0, t1 = 0, t2 = 0, t3 = 0;
                 cudaEventElapsedTime(&t0, d->epoch, L.begin);
                 cudaEventElapsedTime(&t1, d->epoch, L.ev[0]);
@@ -1024,6 +1043,8 @@ static void completer_main(Ctx *c, Device *d)
                 c->s_fast_ms += f;
                 c->s_fix_ms += b;
                 c->s_other_ms += o;
+                c->s_h2d_ms += up_ms;
+                c->s_d2h_ms += down_ms;
                 if (B->n_kernels > 0) {
                     d->k_first = std::min(d->k_first, (double)t1);
                     d->k_last = std::max(d->k_last, (double)t2);
@@ -1273,6 +1294,7 @@ static void destroy_impl(Ctx *c)
             if (L.begin) cudaEventDestroy(L.begin);
             if (L.uploaded) cudaEventDestroy(L.uploaded);
             if (L.done) cudaEventDestroy(L.done);
+            if (L.dl_begin) cudaEventDestroy(L.dl_begin);
             if (L.arena) cudaFree(L.arena);
             if (L.param_host) cudaFreeHost(L.param_host);
             if (L.fix_count_host) cudaFreeHost(L.fix_count_host);
@@ -1332,6 +1354,7 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
         if (getenv("IPG_BAND_CTAS")) c->band_cta_target = (uint32_t)std::max(1, atoi(getenv("IPG_BAND_CTAS")));
         if (getenv("IPG_FIX_CAPACITY")) c->fix_capacity = (uint32_t)std::max(1, atoi(getenv("IPG_FIX_CAPACITY")));
         c->overlap_streams = !(getenv("IPG_NO_OVERLAP") && atoi(getenv("IPG_NO_OVERLAP")) != 0);
+        if (getenv("IPG_OVERLAP_TAIL")) c->overlap_tail = atoi(getenv("IPG_OVERLAP_TAIL")) != 0;
         if (getenv("IPG_STAGING_TIMEOUT_MS")) c->staging_timeout_ms = std::max(0, atoi(getenv("IPG_STAGING_TIMEOUT_MS")));
         if (getenv("IPG_FUSE_TARGETS")) c->fuse_targets = std::min(3, std::max(1, atoi(getenv("IPG_FUSE_TARGETS"))));
         std::vector<int> ids;
@@ -1359,8 +1382,9 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
                 for (auto &ev : L.ev) IPG_CU(cudaEventCreate(&ev));
                 IPG_CU(cudaEventCreate(&L.evf));
                 IPG_CU(cudaEventCreate(&L.begin));
-                IPG_CU(cudaEventCreateWithFlags(&L.uploaded, cudaEventDisableTiming));
+                IPG_CU(cudaEventCreate(&L.uploaded));
                 IPG_CU(cudaEventCreate(&L.done));
+                IPG_CU(cudaEventCreate(&L.dl_begin));
                 L.arena_bytes = (size_t)k.lane_device_bytes;
                 IPG_CU(cudaMalloc((void **)&L.arena, L.arena_bytes));
                 L.param_cap = param_cap;
@@ -1511,6 +1535,8 @@ int ipg_get_stats(ipg_ctx *ctx, ipg_stats *out)
     out->other_kernel_ms = ctx->s_other_ms;
     out->stream_fast_kernel_ms = ctx->s_fast_ms;
     out->fast_jobs = ctx->s_fast_jobs.load();
+    out->h2d_ms = ctx->s_h2d_ms;
+    out->d2h_ms = ctx->s_d2h_ms;
     out->kernel_ms = ctx->s_stream_ms + ctx->s_fix_ms + ctx->s_other_ms;
     for (auto &d : ctx->devs) {
         if (d->k_last >= 0) out->kernel_span_ms = std::max(out->kernel_span_ms, d->k_last - d->k_first);
@@ -1527,7 +1553,7 @@ int ipg_reset_stats(ipg_ctx *ctx)
     ctx->s_done = 0; ctx->s_batches = 0; ctx->s_kernels = 0; ctx->s_h2d = 0; ctx->s_d2h = 0;
     ctx->s_fix = 0; ctx->s_fallback = 0; ctx->s_staged = 0;
     std::lock_guard<std::mutex> lk(ctx->smu);
-    ctx->s_stream_ms = ctx->s_fix_ms = ctx->s_other_ms = ctx->s_fast_ms = 0;
+    ctx->s_stream_ms = ctx->s_fix_ms = ctx->s_other_ms = ctx->s_fast_ms = ctx->s_h2d_ms = ctx->s_d2h_ms = 0;
     ctx->s_fast_jobs = 0;
     for (auto &d : ctx->devs) {
         cudaSetDevice(d->cuda_id);

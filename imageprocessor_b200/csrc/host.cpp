@@ -460,54 +460,106 @@ struct PlannedOp {
 
 } // namespace
 
+// Pinned output buffers come from a few large slabs (ipg_alloc_pinned once per slab) that are sub-allocated first-fit:
+// a mixed-size stream asks for a differently sized watermark output per image, and one cudaHostAlloc / cudaFreeHost per
+// image (each a device-synchronising driver call of ~0.3 ms per MB) would put the allocator, not the copy engines, on
+// the critical path.  The pool is bounded: slabs that are entirely free are returned to the driver once the pool holds
+// more than kPoolCapBytes, so one odd task cannot pin host memory for the life of the processor (the Go reference would
+// have freed such a buffer at the next GC).
+class PinnedSlabs {
+public:
+    static constexpr size_t kSlabBytes = (size_t)256 << 20;
+    static constexpr size_t kPoolCapBytes = (size_t)2 << 30;
+    uint8_t *take(ipg_ctx *ctx, size_t n)
+    {
+        n = (std::max<size_t>(n, 1) + 4095) & ~(size_t)4095;
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto &s : slabs_)
+            if (uint8_t *p = carve(s, n)) return p;
+        if (!ctx) return nullptr;
+        Slab s;
+        s.bytes = std::max(n, kSlabBytes);
+        s.base = (uint8_t *)ipg_alloc_pinned(ctx, s.bytes);
+        if (!s.base && s.bytes > n) { // a whole slab did not fit: try the bare request
+            s.bytes = n;
+            s.base = (uint8_t *)ipg_alloc_pinned(ctx, s.bytes);
+        }
+        if (!s.base) return nullptr;
+        s.free_[0] = s.bytes;
+        total_ += s.bytes;
+        slabs_.push_back(std::move(s));
+        return carve(slabs_.back(), n);
+    }
+    void give(ipg_ctx *ctx, uint8_t *p)
+    {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu_);
+        for (size_t i = 0; i < slabs_.size(); i++) {
+            Slab &s = slabs_[i];
+            if (p < s.base || p >= s.base + s.bytes) continue;
+            const size_t off = (size_t)(p - s.base);
+            auto u = s.used.find(off);
+            if (u == s.used.end()) return;
+            size_t n = u->second;
+            s.used.erase(u);
+            auto nx = s.free_.lower_bound(off);
+            if (nx != s.free_.end() && off + n == nx->first) { n += nx->second; nx = s.free_.erase(nx); }
+            if (nx != s.free_.begin()) {
+                auto pv = std::prev(nx);
+                if (pv->first + pv->second == off) { pv->second += n; n = 0; }
+            }
+            if (n) s.free_[off] = n;
+            if (s.used.empty() && total_ > kPoolCapBytes) { // shrink: this slab is idle and the pool is over its cap
+                total_ -= s.bytes;
+                if (ctx) ipg_free_pinned(ctx, s.base);
+                slabs_.erase(slabs_.begin() + (long)i);
+            }
+            return;
+        }
+    }
+    void release_all(ipg_ctx *ctx)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto &s : slabs_)
+            if (ctx) ipg_free_pinned(ctx, s.base);
+        slabs_.clear();
+        total_ = 0;
+    }
+    size_t total_bytes()
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        return total_;
+    }
+
+private:
+    struct Slab {
+        uint8_t *base = nullptr;
+        size_t bytes = 0;
+        std::map<size_t, size_t> free_, used; // offset -> bytes
+    };
+    static uint8_t *carve(Slab &s, size_t n)
+    {
+        for (auto it = s.free_.begin(); it != s.free_.end(); ++it) {
+            if (it->second < n) continue;
+            const size_t off = it->first, rem = it->second - n;
+            s.free_.erase(it);
+            if (rem) s.free_[off + n] = rem;
+            s.used[off] = n;
+            return s.base + off;
+        }
+        return nullptr;
+    }
+    std::mutex mu_;
+    std::vector<Slab> slabs_;
+    size_t total_ = 0;
+};
+
 struct iph_processor {
     ipg_ctx *ctx = nullptr;
     iph_callbacks cb{};
-    std::mutex mu;
-    std::multimap<size_t, uint8_t *> pinned_free; // output buffers, reused across calls
-    uint8_t *take_pinned(size_t n)
-    {
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            auto it = pinned_free.lower_bound(n);
-            if (it != pinned_free.end() && it->first <= n + n / 4 + 4096) {
-                uint8_t *p = it->second;
-                sizes[p] = it->first;
-                pooled_bytes -= it->first;
-                pinned_free.erase(it);
-                return p;
-            }
-        }
-        uint8_t *p = ctx ? (uint8_t *)ipg_alloc_pinned(ctx, n) : nullptr;
-        if (p) {
-            std::lock_guard<std::mutex> lk(mu);
-            sizes[p] = n;
-        }
-        return p;
-    }
-    // The pool is bounded: a buffer that would push the parked bytes past kPoolCapBytes (or that alone exceeds a
-    // quarter of it) goes straight back to the driver, so one odd task cannot pin host memory for the life of the
-    // processor (the Go reference would have freed such a buffer at the next GC).
-    static constexpr size_t kPoolCapBytes = (size_t)1 << 30;
-    void give_pinned(uint8_t *p)
-    {
-        if (!p) return;
-        size_t n = 0;
-        bool drop = false;
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            n = sizes[p];
-            drop = n > kPoolCapBytes / 4 || pooled_bytes + n > kPoolCapBytes;
-            if (drop) sizes.erase(p);
-            else {
-                pinned_free.emplace(n, p);
-                pooled_bytes += n;
-            }
-        }
-        if (drop && ctx) ipg_free_pinned(ctx, p);
-    }
-    std::map<uint8_t *, size_t> sizes;
-    size_t pooled_bytes = 0; // bytes parked in pinned_free
+    PinnedSlabs pinned; // output buffers, reused across calls
+    uint8_t *take_pinned(size_t n) { return pinned.take(ctx, n); }
+    void give_pinned(uint8_t *p) { pinned.give(ctx, p); }
 };
 
 namespace {
@@ -822,8 +874,7 @@ iph_processor *iph_processor_new(ipg_ctx *ctx, const iph_callbacks *cb)
 void iph_processor_free(iph_processor *p)
 {
     if (!p) return;
-    if (p->ctx)
-        for (auto &kv : p->pinned_free) ipg_free_pinned(p->ctx, kv.second);
+    p->pinned.release_all(p->ctx);
     delete p;
 }
 

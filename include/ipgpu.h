@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define IPG_ABI_VERSION 1
+#define IPG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define IPG_API __attribute__((visibility("default")))
@@ -173,6 +173,9 @@ typedef struct {
     /* of stream_kernel_ms: the lean single-target k_stream instantiation; and the stream jobs it ran */
     double stream_fast_kernel_ms;
     uint64_t fast_jobs;
+    /* device time of the copies, summed over batches: first H2D start -> last H2D end on the upload stream, and first
+     * D2H start -> last D2H end on the download stream (copies of different batches overlap each other and the kernels) */
+    double h2d_ms, d2h_ms;
 } ipg_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */
