@@ -82,6 +82,42 @@ def pcie_ceiling(n_devices):
         return None, None
 
 
+def measure_pcie_live(torch, cuda_ids, barrier, max_over_ranks, sum_over_ranks, mb_per_direction=1536, chunk_mb=48):
+    """The box's host<->device ceiling for THIS run's devices, measured with nothing of the engine in the way: every
+    device of every rank copies H2D and D2H concurrently (one cudaMemcpyAsync per 48 MB chunk on a dedicated stream per
+    direction, pinned cudaHostAlloc memory), all released by one barrier.  Same procedure as tools/micro/pcie_scale.cu
+    (whose committed runs are profiles/pcie_scaling*.json); torch is only the plumbing.  Returns aggregate GB/s per
+    direction over all ranks' devices."""
+    chunk = chunk_mb << 20
+    reps = max(1, mb_per_direction // chunk_mb)
+    bufs = []
+    for d in cuda_ids:
+        dev = torch.device("cuda", d)
+        bufs.append((torch.empty(chunk, dtype=torch.uint8).pin_memory(), torch.empty(chunk, dtype=torch.uint8).pin_memory(),
+                     torch.empty(chunk, dtype=torch.uint8, device=dev), torch.empty(chunk, dtype=torch.uint8, device=dev),
+                     torch.cuda.Stream(dev), torch.cuda.Stream(dev)))
+
+    def run(n):
+        for _ in range(n):
+            for (h_up, h_dn, d_up, d_dn, s_up, s_dn) in bufs:
+                with torch.cuda.stream(s_up):
+                    d_up.copy_(h_up, non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    h_dn.copy_(d_dn, non_blocking=True)
+        for b in bufs:
+            b[4].synchronize()
+            b[5].synchronize()
+
+    run(2)
+    barrier()
+    t0 = time.perf_counter()
+    run(reps)
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    total = sum_over_ranks(float(reps * chunk * len(cuda_ids)))
+    return total / dt / 1e9
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -324,17 +360,30 @@ class Submitter:
         self.n = n
 
     def submit_step(self, k):
-        refs, j = self.refs[k & 1], 0
+        refs = self.refs[k & 1]
         submit_on, ctx = self.lib.ipg_submit_on, self.ctx
-        # interleave the devices so every batcher fills at the same rate
-        per = max(b.n for b in self.batches)
-        for i in range(per):
-            for d, b in enumerate(self.batches):
-                if i < b.n:
-                    rc = submit_on(ctx, d, C.byref(b.descs[i]), b.ops[i], 3, refs[j])
-                    if rc:
-                        self.L.check(rc)
-                    j += 1
+
+        def one_device(d, base):
+            b = self.batches[d]
+            for i in range(b.n):
+                rc = submit_on(ctx, d, C.byref(b.descs[i]), b.ops[i], 3, refs[base + i])
+                if rc:
+                    self.L.check(rc)
+
+        bases, acc = [], 0
+        for b in self.batches:
+            bases.append(acc)
+            acc += b.n
+        if len(self.batches) == 1:
+            one_device(0, 0)
+            return
+        # one submitting thread per device (the north_star layout: a worker thread per device inside one process);
+        # ctypes releases the GIL around ipg_submit_on
+        ths = [threading.Thread(target=one_device, args=(d, bases[d])) for d in range(len(self.batches))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
 
     def wait_step(self, k):
         t, wait, ctx = self.tids[k & 1], self.lib.ipg_wait, self.ctx
@@ -823,8 +872,15 @@ def main():
         barrier()
         wall = max_over_ranks(time.perf_counter() - t0)
         st2 = eng.stats()
+        verified_slot0 = None
+        if rank == 0 and not args.no_verify:
+            from oracle import oracle as O
+            verified_slot0 = ring.verify_slot0(O)
         up, down = sum_over_ranks(st2["bytes_h2d"]) / wall / 1e9, sum_over_ranks(st2["bytes_d2h"]) / wall / 1e9
-        ceil_GBps, ceil_src = pcie_ceiling(n_gpus_total)
+        ring.free()
+        ring = None
+        ceil_file, ceil_src = pcie_ceiling(n_gpus_total)
+        ceil_GBps = measure_pcie_live(torch, dev_ids, barrier, max_over_ranks, sum_over_ranks)
         e2e = {
             "value": total_images / wall, "unit": "images/s",
             "h2d_bytes_per_step": int(st2["bytes_h2d"] / args.steps), "d2h_bytes_per_step": int(st2["bytes_d2h"] / args.steps),
@@ -835,15 +891,17 @@ def main():
             "pcie": {"bound": "pcie", "unit": "GB/s per direction, aggregate over the run's GPUs, both directions busy",
                      "achieved": min(up, down), "peak": ceil_GBps,
                      "frac_of_pcie": (min(up, down) / ceil_GBps) if ceil_GBps else None,
-                     "peak_source": f"tools/micro/pcie_scale.cu, {ceil_src}: {n_gpus_total} device(s) copying H2D + D2H concurrently, "
-                                    "cudaHostAlloc memory, 48 MB per cudaMemcpyAsync" if ceil_GBps else "no committed pcie_scale run for this N"},
+                     "peak_source": f"measured live in this run right after the timed region: all {n_gpus_total} device(s) copy H2D + D2H "
+                                    "concurrently, pinned cudaHostAlloc memory, one cudaMemcpyAsync per 48 MB, no engine "
+                                    "(the procedure of tools/micro/pcie_scale.cu)",
+                     "peak_committed_run": ceil_file, "peak_committed_run_source": ceil_src,
+                     "note": "the ceiling is a property of the box, not of N GPUs' links: profiles/pcie_scaling.json (8-GPU box: 44 / 51.5 / 51 / "
+                             "64 GB/s per direction at N = 1/2/4/8 whatever the allocator or process model) vs profiles/pcie_scaling_2gpu_box.json "
+                             "(48 / 80 GB/s at N = 1/2)"},
             "host_buffers": f"{n_slots} pinned slots per GPU (ipg_alloc_pinned), zero staging copies: {st2['staged_copies'] == 0}",
             "verified_slot0": None,
         }
-        if rank == 0 and not args.no_verify:
-            from oracle import oracle as O
-            e2e["verified_slot0"] = ring.verify_slot0(O)
-        ring.free()
+        e2e["verified_slot0"] = verified_slot0
     clocks = sampler.stop()   # sampled across the device-resident AND the end-to-end leg
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload

@@ -313,7 +313,10 @@ struct Ctx {
     uint32_t band_cta_target = 1400;
     uint32_t fix_capacity = 0;     // IPG_FIX_CAPACITY: fix-list entries per batch (0: sized from the batch); tests force the overflow paths with it
     bool overlap_streams = true; // IPG_NO_OVERLAP=1: lean and general k_stream launches back to back (per-kernel timing)
-    bool overlap_tail = true;    // IPG_OVERLAP_TAIL=0: a batch's kernels start only after the previous batch's last kernel
+    // IPG_OVERLAP_TAIL=1: a batch's stream kernels start as soon as the previous batch's STREAM section ends, beside its
+    // fix / blend tail.  Measured (r2): +1.4 % images/s device-resident, but the tail kernels then share SMs with
+    // k_stream and its own duration (what the roofline is quoted on) grows 3 %; off by default.
+    bool overlap_tail = false;
     int staging_timeout_ms = 2000; // IPG_STAGING_TIMEOUT_MS: how long ipg_submit waits for pinned staging before IPG_ERR_NOMEM
     // stats
     std::atomic<uint64_t> s_done{0}, s_batches{0}, s_kernels{0}, s_h2d{0}, s_d2h{0}, s_fix{0}, s_fallback{0}, s_staged{0};

@@ -65,14 +65,25 @@ struct RowRec { float wa, wb; int32_t emit; int32_t pad; };
 // the alpha sums an all-opaque image would have accumulated (so the opaque fast path does
 // no alpha arithmetic at all).  One block of n_targets GroupRecs per (band, group) rides
 // into shared memory with the group's source rows in the same TMA transaction.
+// Source rows per ring stage / TMA barrier phase.  The per-group fixed cost of a V warp (mbarrier wait, opacity vote,
+// stage release, ring bookkeeping: ~50-60 issued instructions, ncu r2: 15-23 % of the kernel at 4 rows) is paid once per
+// group.  IPG_GROUP=8 halves it with half as many, twice as large stages (same shared memory): measured on the B200
+// (r2, tools/jobs/r2_variants.sh) each pass ALONE gains (resize + watermark 0.914 -> 0.939 of the HBM roofline, thumbnail
+// 0.447 -> 0.503) but the merged launch the engine actually runs loses (25.2 -> 25.8 us per 12 MP image, bench frac
+// 0.667 -> 0.641): two 8-row stages leave one stage of slack where four 4-row stages leave three.  Default stays 4.
+#ifndef IPG_GROUP
+#define IPG_GROUP 4
+#endif
 struct GroupRow { float w0, w1;    // weight of this source row for accumulator set 0 / 1
                   float sa0, sa1; };// fmaf(255, w, .) chains of set 0 / 1 after this row (before an emit clears it)
 struct GroupRec {
-    GroupRow row[4];               // STREAM_GROUP rows
-    int32_t emit[4];               // -1, or (output row << 1 | set): the row completes that set
+    GroupRow row[IPG_GROUP];       // STREAM_GROUP rows
+    int32_t emit[IPG_GROUP];       // -1, or (output row << 1 | set): the row completes that set
     float seed0, seed1;            // the two alpha chains entering the group
     int32_t pad[2];
 };
+static_assert(sizeof(GroupRec) % 16 == 0, "group records ride in TMA bulk copies (16-byte granular)");
+static_assert(IPG_GROUP == 4 || IPG_GROUP == 8, "the row loop indexes the next row with a power-of-two mask");
 
 struct StreamTarget {
     uint8_t *dst;
@@ -118,19 +129,19 @@ struct WatermarkD {
 #define IPG_CTAS_2T 2
 #endif
 #ifndef IPG_STAGES_2T
-#define IPG_STAGES_2T 8
+#define IPG_STAGES_2T (32 / IPG_GROUP)
 #endif
 #ifndef IPG_CTAS_1T
 #define IPG_CTAS_1T 3
 #endif
 #ifndef IPG_STAGES_1T
-#define IPG_STAGES_1T 5
+#define IPG_STAGES_1T (IPG_GROUP == 4 ? 5 : 3)
 #endif
 #ifndef IPG_CTAS_FAST
 #define IPG_CTAS_FAST 4
 #endif
 #ifndef IPG_STAGES_FAST
-#define IPG_STAGES_FAST 4
+#define IPG_STAGES_FAST (16 / IPG_GROUP)
 #endif
 #ifndef IPG_CTAS_FAST2
 #define IPG_CTAS_FAST2 3
@@ -139,10 +150,10 @@ struct WatermarkD {
 #define IPG_CTAS_INL 5
 #endif
 #ifndef IPG_STAGES_INL
-#define IPG_STAGES_INL 3
+#define IPG_STAGES_INL (IPG_GROUP == 4 ? 3 : 2)
 #endif
 #ifndef IPG_STAGES_FAST2
-#define IPG_STAGES_FAST2 3
+#define IPG_STAGES_FAST2 (IPG_GROUP == 4 ? 3 : 2)
 #endif
 
 // k_stream CTA: 4 V warps + one producer warp (one elected lane drives the TMA ring: bulk
@@ -155,7 +166,7 @@ struct WatermarkD {
 enum {
     STREAM_THREADS = 128, STREAM_PX = 4, STREAM_WARP_COLS = 32 * STREAM_PX,
     STREAM_COLS = STREAM_THREADS * STREAM_PX, // widest slab (warp_stride == 128)
-    STREAM_GROUP = 4,           // source rows per ring stage / TMA barrier phase (<= 8 KB)
+    STREAM_GROUP = IPG_GROUP,   // source rows per ring stage / TMA barrier phase (<= 16 KB)
     STREAM_PTHREADS = 32,       // producer warp
     STREAM_CTA = STREAM_THREADS + STREAM_PTHREADS,
     STREAM_XTAPS = 8,           // local targets: taps per thread kept in registers

@@ -1559,7 +1559,7 @@ template <bool NRGBA, int STAGES> struct __align__(128) PlanarSmem {
     uint64_t full[STAGES], empty[STAGES];
     XInfo xi[2];
 };
-enum { PLANAR_STAGES = 4, PLANAR_CTAS = 4, NRGBA_CTAS = 3 };
+enum { PLANAR_STAGES = 16 / STREAM_GROUP, PLANAR_CTAS = 4, NRGBA_CTAS = 3 };
 
 // two 16-bit samples -> fp32 pair via the 2^23 mantissa trick (exact for values < 2^23)
 __device__ __forceinline__ float2 u16x2_f32(uint32_t a, uint32_t b)
