@@ -8,7 +8,7 @@ this package is the Python-side harness over it.  No CPU fallback exists.
 from . import _lib
 from ._lib import (IpgError, RGBA8, NRGBA8, GRAY8, YCBCR444, YCBCR422, YCBCR420, YCBCR440,
                    PRECISION_EXACT, PRECISION_FAST, PRECISION_REFERENCE,
-                   OP_RESIZE, OP_THUMB_CROP, OP_WATERMARK, MEM_HOST, MEM_DEVICE)
+                   OP_RESIZE, OP_THUMB_CROP, OP_WATERMARK, OPF_WATERMARK_PATCH_ONLY, MEM_HOST, MEM_DEVICE)
 from .engine import (Engine, Image, OpSpec, GlyphMask, Ticket, PinnedBuffer,
                      keep_aspect_dims, thumb_fit_dims, crop_square)
 

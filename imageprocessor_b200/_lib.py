@@ -22,6 +22,8 @@ MEM_HOST, MEM_DEVICE = 0, 1
 PRECISION_EXACT, PRECISION_FAST, PRECISION_REFERENCE = 0, 1, 2
 # ipg_op_kind
 OP_RESIZE, OP_THUMB_CROP, OP_WATERMARK = 1, 2, 3
+# ipg_op_flags
+OPF_WATERMARK_PATCH_ONLY = 1
 
 
 class IpgError(RuntimeError):
@@ -52,7 +54,7 @@ class Op(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dst_w", C.c_int32), ("dst_h", C.c_int32),
                 ("rect_x", C.c_int32), ("rect_y", C.c_int32), ("rect_w", C.c_int32), ("rect_h", C.c_int32),
                 ("color", C.c_uint8 * 4), ("n_glyphs", C.c_int32), ("glyphs", C.POINTER(Glyph)),
-                ("dst", C.c_void_p), ("dst_stride", C.c_int32), ("dst_memspace", C.c_int32)]
+                ("dst", C.c_void_p), ("dst_stride", C.c_int32), ("dst_memspace", C.c_int32), ("flags", C.c_int32)]
 
 
 class Stats(C.Structure):

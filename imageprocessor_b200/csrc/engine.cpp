@@ -203,6 +203,9 @@ struct OpRec {
     void *dst = nullptr;
     int dst_stride = 0;
     int dst_mem = 0;
+    int flags = 0;
+    bool patch_only = false;  // IPG_OPF_WATERMARK_PATCH_ONLY on an RGBA8 source: only the glyph union box is produced
+    int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0; // ... that box (empty: nothing to do)
     uint8_t *stage = nullptr; // staging for a non-pinned host dst (tight rows)
     uint8_t *dev_out = nullptr;
     size_t dev_pitch = 0;
@@ -414,7 +417,8 @@ static size_t ticket_device_bytes(const Ticket &t)
         }
     }
     for (auto &op : t.ops) {
-        if (op.dst_mem == IPG_MEM_HOST) n += (align_up((size_t)std::max(op.dw, 0) * 4, 256) + 256) * (size_t)std::max(op.dh, 0) + 256;
+        if (op.patch_only) n += (align_up((size_t)std::max(op.bx1 - op.bx0, 0) * 4, 256) + 256) * (size_t)std::max(op.by1 - op.by0, 0) + 256;
+        else if (op.dst_mem == IPG_MEM_HOST) n += (align_up((size_t)std::max(op.dw, 0) * 4, 256) + 256) * (size_t)std::max(op.dh, 0) + 256;
         for (auto &g : op.glyphs) n += align_up(g.mask.size(), 256) + 256;
         n += 4096;
     }
@@ -453,6 +457,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     std::vector<WmItem> witems;
     std::vector<WatermarkD> blends;   // every watermark of the batch that has glyphs
     std::vector<BlendItem> bitems;
+    std::vector<PatchJob> pjobs;      // patch-only watermarks (RGBA8 sources): glyph box alone
+    std::vector<BlendItem> pbitems;
     struct Readback { uint8_t *dev; size_t pitch; void *host; size_t hstride; size_t row_bytes; int rows; };
     std::vector<Readback> readbacks;
     int max_nt = 0;
@@ -515,6 +521,23 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
         for (auto &op : t.ops) {
             op.dev_out = nullptr;
             if (op.dw <= 0 || op.dh <= 0) continue;
+            if (op.patch_only) { // the box alone: a patch buffer read back as a rectangle, or the caller's device frame
+                const int bw = op.bx1 - op.bx0, bh = op.by1 - op.by0;
+                if (bw <= 0 || bh <= 0) continue;
+                if (op.dst_mem == IPG_MEM_DEVICE) {
+                    op.dev_out = (uint8_t *)op.dst;
+                    op.dev_pitch = (size_t)op.dst_stride;
+                } else {
+                    const size_t pitch = align_up((size_t)bw * 4, 256);
+                    op.dev_out = arena.take(pitch * (size_t)bh);
+                    if (!op.dev_out) throw std::runtime_error("device arena exhausted (watermark patch)");
+                    op.dev_pitch = pitch;
+                    if (op.stage) readbacks.push_back({op.dev_out, pitch, op.stage, (size_t)bw * 4, (size_t)bw * 4, bh});
+                    else readbacks.push_back({op.dev_out, pitch, (uint8_t *)op.dst + (size_t)op.by0 * (size_t)op.dst_stride + (size_t)op.bx0 * 4,
+                                              (size_t)op.dst_stride, (size_t)bw * 4, bh});
+                }
+                continue;
+            }
             if (op.dst_mem == IPG_MEM_DEVICE) {
                 op.dev_out = (uint8_t *)op.dst;
                 op.dev_pitch = (size_t)op.dst_stride;
@@ -592,6 +615,24 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
         std::vector<OpRec *> res, wms;
         for (auto &op : t.ops) {
             if (op.dw <= 0 || op.dh <= 0) continue;
+            if (op.patch_only) {
+                if (!op.dev_out) continue; // no glyph touches the image
+                PatchJob pj{};
+                pj.src = sv;
+                pj.wm = make_wm(op);   // (its entry in `blends` is replaced by the patch job's own items below)
+                if (pj.wm.n_glyphs > 0) { // make_wm queued in-place blend tiles for this watermark: take them back
+                    const int bi = (int)blends.size() - 1;
+                    while (!bitems.empty() && bitems.back().wm == bi) bitems.pop_back();
+                    blends.pop_back();
+                }
+                pj.ox = op.dst_mem == IPG_MEM_DEVICE ? 0 : op.bx0;
+                pj.oy = op.dst_mem == IPG_MEM_DEVICE ? 0 : op.by0;
+                const int ji = (int)pjobs.size();
+                pjobs.push_back(pj);
+                for (int ty = 0; ty < (op.by1 - op.by0 + 7) / 8; ty++)
+                    for (int tx = 0; tx < (op.bx1 - op.bx0 + 31) / 32; tx++) pbitems.push_back(BlendItem{ji, tx, ty});
+                continue;
+            }
             (op.kind == IPG_OP_WATERMARK ? wms : res).push_back(&op);
         }
         const bool streamable = precision != IPG_PRECISION_REFERENCE && sv.layout == L_RGBA8 &&
@@ -825,6 +866,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     const WmItem *d_witems = blob.dptr<const WmItem>(blob.put(witems.data(), witems.size() * sizeof(WmItem), 16));
     const WatermarkD *d_blends = blob.dptr<const WatermarkD>(blob.put(blends.data(), blends.size() * sizeof(WatermarkD), 16));
     const BlendItem *d_bitems = blob.dptr<const BlendItem>(blob.put(bitems.data(), bitems.size() * sizeof(BlendItem), 16));
+    const PatchJob *d_pjobs = blob.dptr<const PatchJob>(blob.put(pjobs.data(), pjobs.size() * sizeof(PatchJob), 16));
+    const BlendItem *d_pbitems = blob.dptr<const BlendItem>(blob.put(pbitems.data(), pbitems.size() * sizeof(BlendItem), 16));
     if (blob.overflow) throw std::runtime_error("parameter blob overflow (batch too heterogeneous); lower max_batch");
     IPG_CU(cudaMemcpyAsync(blob_dev, L.param_host, blob.off, cudaMemcpyHostToDevice, up));
     B.h2d += blob.off;
@@ -907,6 +950,10 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     }
     if (!bitems.empty()) {
         IPG_CU(launch_blend(d_blends, d_bitems, (int)bitems.size(), st));
+        B.n_kernels++;
+    }
+    if (!pbitems.empty()) {
+        IPG_CU(launch_blend_patch(d_pjobs, d_pbitems, (int)pbitems.size(), st));
         B.n_kernels++;
     }
     IPG_CU(cudaEventRecord(L.ev[3], st));
@@ -1154,6 +1201,18 @@ static int submit_impl(Ctx *c, int dev_index, const ipg_image_desc *src, const i
         r.rx = o.rect_x; r.ry = o.rect_y; r.rw = o.rect_w; r.rh = o.rect_h;
         memcpy(r.color, o.color, 4);
         r.dst = o.dst; r.dst_stride = o.dst_stride; r.dst_mem = o.dst_memspace;
+        r.flags = o.flags;
+        if (o.kind == IPG_OP_WATERMARK && (o.flags & IPG_OPF_WATERMARK_PATCH_ONLY) && src->layout == IPG_LAYOUT_RGBA8 && o.dst_w > 0 && o.dst_h > 0) {
+            r.patch_only = true; // the union of the non-empty glyph rectangles (what freetype's DrawMask calls can touch)
+            int bx0 = INT32_MAX, by0 = INT32_MAX, bx1 = INT32_MIN, by1 = INT32_MIN;
+            for (int g = 0; g < o.n_glyphs; g++) {
+                const ipg_glyph &G = o.glyphs[g];
+                if (G.x0 >= G.x1 || G.y0 >= G.y1) continue;
+                bx0 = std::min(bx0, G.x0); by0 = std::min(by0, G.y0);
+                bx1 = std::max(bx1, G.x1); by1 = std::max(by1, G.y1);
+            }
+            if (bx0 < bx1 && by0 < by1) { r.bx0 = bx0; r.by0 = by0; r.bx1 = bx1; r.by1 = by1; }
+        }
         if (o.kind == IPG_OP_WATERMARK) {
             for (int g = 0; g < o.n_glyphs; g++) {
                 const ipg_glyph &G = o.glyphs[g];
@@ -1195,8 +1254,10 @@ static int submit_impl(Ctx *c, int dev_index, const ipg_image_desc *src, const i
         if (r.dst_mem != IPG_MEM_HOST || r.dw <= 0 || r.dh <= 0) continue;
         size_t span = (size_t)r.dst_stride * (size_t)(r.dh - 1) + (size_t)r.dw * 4;
         if (c->pinned.contains(r.dst, span)) continue;
+        if (r.patch_only && (r.bx1 <= r.bx0 || r.by1 <= r.by0)) continue; // nothing will be written
         bool timed_out = false;
-        r.stage = d.staging.alloc((size_t)r.dw * 4 * (size_t)r.dh, c->stop, c->staging_timeout_ms, &timed_out);
+        const size_t stage_bytes = r.patch_only ? (size_t)(r.bx1 - r.bx0) * 4 * (size_t)(r.by1 - r.by0) : (size_t)r.dw * 4 * (size_t)r.dh;
+        r.stage = d.staging.alloc(stage_bytes, c->stop, c->staging_timeout_ms, &timed_out);
         if (!r.stage) {
             for (auto &q : t->ops) { d.staging.release(q.stage); q.stage = nullptr; }
             for (int p = 0; p < 3; p++) d.staging.release(t->src_stage[p]);
@@ -1255,8 +1316,14 @@ static int wait_impl(Ctx *c, ipg_ticket id, int timeout_ms)
     for (auto &r : t->ops) {
         if (!r.stage) continue;
         if (t->status == IPG_OK) {
-            for (int y = 0; y < r.dh; y++)
-                memcpy((uint8_t *)r.dst + (size_t)y * r.dst_stride, r.stage + (size_t)y * r.dw * 4, (size_t)r.dw * 4);
+            if (r.patch_only) {
+                const size_t bw4 = (size_t)(r.bx1 - r.bx0) * 4;
+                for (int y = r.by0; y < r.by1; y++)
+                    memcpy((uint8_t *)r.dst + (size_t)y * r.dst_stride + (size_t)r.bx0 * 4, r.stage + (size_t)(y - r.by0) * bw4, bw4);
+            } else {
+                for (int y = 0; y < r.dh; y++)
+                    memcpy((uint8_t *)r.dst + (size_t)y * r.dst_stride, r.stage + (size_t)y * r.dw * 4, (size_t)r.dw * 4);
+            }
             c->s_staged++;
         }
         d.staging.release(r.stage);

@@ -208,6 +208,15 @@ struct WmJob {
     WatermarkD wm;
 };
 struct WmItem { int32_t job; int32_t row0; };  // WM_ROWS rows per item
+// Patch-only watermark of an RGBA8 source (IPG_OPF_WATERMARK_PATCH_ONLY): the glyph union box alone is produced, read
+// from the source, blended, written at (x - ox, y - oy) of wm.dst (a box-sized patch buffer, or the caller's device
+// frame with ox = oy = 0).
+struct PatchJob {
+    SrcView src;
+    WatermarkD wm;
+    int32_t ox, oy;
+    int32_t pad[2];
+};
 struct BlendItem { int32_t wm; int32_t tile_x, tile_y; }; // 32x8 px of a watermark's glyph box
 enum { WM_ROWS = 8 };
 

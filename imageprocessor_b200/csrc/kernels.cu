@@ -624,6 +624,23 @@ k_blend(const WatermarkD *__restrict__ wms, const BlendItem *__restrict__ items)
     if (o != d) *p = o;
 }
 
+// The same blend for the patch-only watermark of an *image.RGBA source: the box pixels come from the SOURCE (draw.Draw
+// Src of an RGBA is a copy), are blended in string order and land in the patch buffer / the caller's frame.  Every box
+// pixel is written (blended or not): the patch is copied over the caller's buffer as a rectangle.
+__global__ void __launch_bounds__(256)
+k_blend_patch(const PatchJob *__restrict__ jobs, const BlendItem *__restrict__ items)
+{
+    const BlendItem it = items[blockIdx.x];
+    const PatchJob &J = jobs[it.wm];
+    const WatermarkD &wm = J.wm;
+    const int x = wm.bx0 + it.tile_x * 32 + (threadIdx.x & 31);
+    const int y = wm.by0 + it.tile_y * 8 + (threadIdx.x >> 5);
+    if (x >= wm.bx1 || y >= wm.by1) return;
+    const uint32_t d = __ldg((const uint32_t *)(J.src.p0 + (size_t)y * J.src.s0) + x);
+    uint32_t *p = (uint32_t *)(wm.dst + (size_t)(y - J.oy) * wm.dst_stride) + (x - J.ox);
+    *p = glyph_over_px(d, x, y, wm);
+}
+
 // ---------------------------------------------------------------------------------
 // k_stream: vertical-first fp32 streaming resample
 //
@@ -1898,6 +1915,13 @@ cudaError_t launch_blend(const WatermarkD *wms, const BlendItem *items, int n_it
 {
     if (n_items <= 0) return cudaSuccess;
     k_blend<<<n_items, 256, 0, st>>>(wms, items);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_blend_patch(const PatchJob *jobs, const BlendItem *items, int n_items, cudaStream_t st)
+{
+    if (n_items <= 0) return cudaSuccess;
+    k_blend_patch<<<n_items, 256, 0, st>>>(jobs, items);
     return cudaGetLastError();
 }
 

@@ -27,6 +27,9 @@ cudaError_t launch_exact_fix(const ExactJob *jobs, int n_jobs, FixList fix, cuda
 // Ordered glyph blend in place over each watermark's glyph box (after the copy/convert).
 cudaError_t launch_blend(const WatermarkD *wms, const BlendItem *items, int n_items, cudaStream_t st);
 
+// Patch-only watermark of RGBA8 sources: source box -> blend -> patch buffer / caller frame.
+cudaError_t launch_blend_patch(const PatchJob *jobs, const BlendItem *items, int n_items, cudaStream_t st);
+
 // draw.Draw(Src) convert/copy for any layout (glyphs follow in launch_blend).
 cudaError_t launch_watermark(const WmJob *jobs, const WmItem *items, int n_items, cudaStream_t st);
 

@@ -90,6 +90,7 @@ class OpSpec:
     glyphs: Sequence[GlyphMask] = ()
     dst: Optional[np.ndarray] = None      # host destination (h, w, 4) uint8; allocated if None
     dst_device: Optional[Tuple[int, int]] = None  # (device pointer, stride) instead of dst
+    flags: int = 0                        # ipg_op_flags (OPF_WATERMARK_PATCH_ONLY: dst must already hold the source pixels)
 
     @staticmethod
     def resize(dw: int, dh: int, **kw) -> "OpSpec":
@@ -207,7 +208,7 @@ class Engine:
         outs: List[Optional[np.ndarray]] = []
         for k, o in enumerate(ops):
             c = arr[k]
-            c.kind, c.dst_w, c.dst_h = o.kind, o.dst_w, o.dst_h
+            c.kind, c.dst_w, c.dst_h, c.flags = o.kind, o.dst_w, o.dst_h, o.flags
             c.rect_x, c.rect_y, c.rect_w, c.rect_h = o.rect
             for j in range(4):
                 c.color[j] = o.color[j]

@@ -151,7 +151,19 @@ typedef struct {
     void *dst;
     int32_t dst_stride;
     int32_t dst_memspace;     /* ipg_memspace                                 */
+    int32_t flags;            /* ipg_op_flags (new in ABI 2: sizeof(ipg_op) 64 -> 72) */
 } ipg_op;
+
+typedef enum {
+    /* IPG_OP_WATERMARK on an IPG_LAYOUT_RGBA8 source only.  draw.Draw(result, b, img, Point{}, Src) of an *image.RGBA is
+     * a copy (watermark.go:91-92), so the watermarked image differs from its source only inside the union of the glyph
+     * rectangles (~300 x 45 px for the default text).  With this flag the engine writes ONLY that box into dst and
+     * leaves every other byte of dst untouched: the caller guarantees they already hold the source pixels -- e.g. dst IS
+     * the source buffer (ops of one ticket all read the uploaded original, so aliasing is safe in any op order), or a
+     * host copy of it.  Saves the full-frame device copy and (w*h*4 - box) bytes of D2H per image.  Ignored for other
+     * source layouts (their draw.Draw is a conversion: the full frame is produced as usual). */
+    IPG_OPF_WATERMARK_PATCH_ONLY = 1,
+} ipg_op_flags;
 
 typedef struct {
     uint64_t tickets_done;

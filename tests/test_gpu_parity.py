@@ -331,3 +331,66 @@ def test_submit_returns_nomem_instead_of_blocking_when_staging_is_exhausted(monk
             assert np.array_equal(e.wait(t)[0], a)
         # and the pool is whole again
         assert np.array_equal(e.run(ip.Image.from_rgba(a), [ip.OpSpec.watermark(w, h, (255, 255, 255, 127), [])])[0], a)
+
+
+@pytest.mark.parametrize("w,h,where", [(1600, 1200, "pinned-alias"), (4000, 3000, "pageable-copy"), (1001, 777, "device")])
+def test_watermark_patch_only_equals_the_full_frame_result(engines, oracle, w, h, where):
+    """IPG_OPF_WATERMARK_PATCH_ONLY: for an *image.RGBA source draw.Draw(Src) is a copy, so only the glyph union box is
+    produced and written; with dst holding the source pixels (the source buffer itself, or a copy) the result must be the
+    oracle's full watermarked frame, and nothing outside the box may be touched.  Other ops of the same ticket still see
+    the ORIGINAL pixels although the watermark lands in the very buffer they were uploaded from."""
+    from imageprocessor_b200 import _lib as L
+    e = engines(ip.PRECISION_EXACT)
+    a = rgba_random(w, h, 55, "premul")
+    gl = synthetic_glyphs(w, h, 9, n=7)
+    col = (255, 255, 255, 127)
+    R = oracle.Raster.rgba(a)
+    want = oracle.watermark(R, col, [oracle.Glyph(*g) for g in gl])
+    glyphs = [ip.GlyphMask(*g) for g in gl]
+    nw, nh = ip.keep_aspect_dims(w, h, 1024, 768)
+    d0 = e.stats()["bytes_d2h"]
+    if where == "pinned-alias":
+        buf = e.alloc_pinned(a.nbytes)
+        src = buf.array.reshape(h, w, 4)
+        src[...] = a
+        out = e.run(ip.Image.from_rgba(src), [ip.OpSpec.watermark(w, h, col, glyphs, dst=src, flags=L.OPF_WATERMARK_PATCH_ONLY),
+                                              ip.OpSpec.resize(nw, nh)])
+        got = src.copy()
+        assert np.array_equal(out[1], oracle.resize_image(R, nw, nh)), "the resize must see the original, not the patched buffer"
+        buf.free()
+    elif where == "pageable-copy":
+        dst = a.copy()
+        dst[0, 0] = (1, 2, 3, 4)                       # a sentinel outside the box: the engine must not touch it
+        e.run(ip.Image.from_rgba(a), [ip.OpSpec.watermark(w, h, col, glyphs, dst=dst, flags=L.OPF_WATERMARK_PATCH_ONLY)])
+        assert tuple(dst[0, 0]) == (1, 2, 3, 4)
+        dst[0, 0] = a[0, 0]
+        got = dst
+    else:
+        p_src, p_dst = e.alloc_device(0, a.nbytes), e.alloc_device(0, a.nbytes)
+        e.to_device(0, p_src, a)
+        e.to_device(0, p_dst, a)
+        e.run(ip.Image.on_device(L.RGBA8, w, h, [p_src], [w * 4]),
+              [ip.OpSpec.watermark(w, h, col, glyphs, dst_device=(p_dst, w * 4), flags=L.OPF_WATERMARK_PATCH_ONLY)], device=0)
+        got = np.empty_like(a)
+        e.from_device(0, got, p_dst)
+        e.free_device(0, p_src)
+        e.free_device(0, p_dst)
+    assert np.array_equal(got, want)
+    if where != "device":
+        x0, y0 = min(g.x0 for g in gl), min(g.y0 for g in gl)
+        x1, y1 = max(g.x1 for g in gl), max(g.y1 for g in gl)
+        moved = e.stats()["bytes_d2h"] - d0
+        assert moved < (x1 - x0) * (y1 - y0) * 4 + nw * nh * 4 + 4096, "only the box (and the resize) may cross PCIe"
+
+
+def test_watermark_patch_only_is_ignored_for_converting_layouts(engines, oracle):
+    """For NRGBA / YCbCr / Gray sources draw.Draw(Src) is a conversion: the flag is ignored and the full frame is produced."""
+    from imageprocessor_b200 import _lib as L
+    e = engines(ip.PRECISION_EXACT)
+    w, h = 640, 480
+    a = rgba_random(w, h, 3, "raw")
+    gl = synthetic_glyphs(w, h, 2)
+    col = (10, 200, 30, 200)
+    out = e.run(ip.Image.from_rgba(a, ip.NRGBA8), [ip.OpSpec.watermark(w, h, col, [ip.GlyphMask(*g) for g in gl],
+                                                                      flags=L.OPF_WATERMARK_PATCH_ONLY)])
+    assert np.array_equal(out[0], oracle.watermark(oracle.Raster.rgba(a, oracle.NRGBA8), col, [oracle.Glyph(*g) for g in gl]))
