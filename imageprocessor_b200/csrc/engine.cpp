@@ -315,6 +315,7 @@ struct Ctx {
     bool merge_lean = true;
     uint32_t band_cta_target = 1400;
     uint32_t fix_capacity = 0;     // IPG_FIX_CAPACITY: fix-list entries per batch (0: sized from the batch); tests force the overflow paths with it
+    int use_direct = 1;          // IPG_DIRECT=0: vertical upscales take the whole-image fp64 kernel as in round 1; 2: mild downscales too go to k_direct
     bool overlap_streams = true; // IPG_NO_OVERLAP=1: lean and general k_stream launches back to back (per-kernel timing)
     // IPG_OVERLAP_TAIL=1: a batch's stream kernels start as soon as the previous batch's STREAM section ends, beside its
     // fix / blend tail.  Measured (r2): +1.4 % images/s device-resident, but the tail kernels then share SMs with
@@ -457,6 +458,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     std::vector<WmItem> witems;
     std::vector<WatermarkD> blends;   // every watermark of the batch that has glyphs
     std::vector<BlendItem> bitems;
+    std::vector<DirectJob> djobs;     // small-support targets (vertical upscales, mild downscales): k_direct
+    std::vector<DirectItem> ditems;
     std::vector<PatchJob> pjobs;      // patch-only watermarks (RGBA8 sources): glyph box alone
     std::vector<BlendItem> pbitems;
     struct Readback { uint8_t *dev; size_t pitch; void *host; size_t hstride; size_t row_bytes; int rows; };
@@ -637,6 +640,39 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
         }
         const bool streamable = precision != IPG_PRECISION_REFERENCE && sv.layout == L_RGBA8 &&
                                 (sv.s0 % 4) == 0 && ((size_t)sv.p0 % 4) == 0;
+        // vertical upscales have no streaming form (many output rows open at once) and the reference upscales small
+        // images too (resize.go:63-72): one thread per output pixel (k_direct, fp32 + the same certificate) takes them,
+        // where round 1 ran the whole image in fp64
+        if (precision != IPG_PRECISION_REFERENCE && (sv.layout != L_RGBA8 || streamable)) {
+            std::vector<OpRec *> keep;
+            for (auto *op : res) {
+                StreamTargetSpec sp{0, 0, sv.w, sv.h, op->dw, op->dh};
+                if (op->kind == IPG_OP_THUMB_CROP) sp = StreamTargetSpec{op->rx, op->ry, op->rw, op->rh, op->dw, op->dh};
+                auto dg = c.use_direct ? get_direct_geom(sp, sv.layout == L_RGBA8 ? 257.0 : 1.0, c.use_direct == 2) : nullptr;
+                if (!dg) { keep.push_back(op); continue; }
+                blob.hold(dg);
+                DirectJob j{};
+                j.src = sv;
+                j.rect_x = sp.rect_x; j.rect_y = sp.rect_y;
+                j.two_stage = op->kind == IPG_OP_THUMB_CROP;
+                j.dw = op->dw; j.dh = op->dh;
+                j.dst = op->dev_out; j.dst_stride = (int)op->dev_pitch;
+                j.xoff = blob.put_vec(dg->ax->off); j.xfirst = blob.put_vec(dg->ax->first); j.xw = blob.put_vec(dg->xw);
+                j.yoff = blob.put_vec(dg->ay->off); j.yfirst = blob.put_vec(dg->ay->first); j.yw = blob.put_vec(dg->yw);
+                j.fix_d = dg->fix_d;
+                j.exact_job = -1;
+                if (precision == IPG_PRECISION_EXACT) {
+                    j.exact_job = add_exact(*op, fixjobs);
+                    fix_px += (uint64_t)op->dw * (uint64_t)op->dh;
+                }
+                const int ji = (int)djobs.size();
+                djobs.push_back(j);
+                for (int ty = 0; ty < (op->dh + 7) / 8; ty++)
+                    for (int tx = 0; tx < (op->dw + 31) / 32; tx++) ditems.push_back(DirectItem{ji, tx, ty, 0});
+                B.fast_jobs++;
+            }
+            res.swap(keep);
+        }
         size_t wi = 0;
         if (streamable) {
             size_t ri = 0;
@@ -770,12 +806,22 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 std::shared_ptr<const StreamGeom> geom;
                 StreamTargetSpec sp1{0, 0, sv.w, sv.h, op->dw, op->dh};
                 if (op->kind == IPG_OP_THUMB_CROP) sp1 = StreamTargetSpec{op->rx, op->ry, op->rw, op->rh, op->dw, op->dh};
-                if (planar_ok) geom = get_stream_geom(sv.w, sv.h, &sp1, 1, false, bands_hint, 1.0);
+                // the watermark's full-frame conversion rides on a single-stage (resize) pass when one exists: the V lanes
+                // hold the 16-bit samples whose high bytes draw.Draw(Src) would store, so the planar source is read once
+                // for both (it needs 16-byte aligned destination rows: the arena's always are)
+                OpRec *wm = nullptr;
+                if (planar_ok && op->kind == IPG_OP_RESIZE && wi < wms.size() &&
+                    ((((uintptr_t)wms[wi]->dev_out) | (uintptr_t)wms[wi]->dev_pitch) & 15) == 0) {
+                    auto gw = get_stream_geom(sv.w, sv.h, &sp1, 1, true, bands_hint, 1.0);
+                    if (gw && gw->lean_ok) { geom = gw; wm = wms[wi]; }
+                }
+                if (!geom && planar_ok) geom = get_stream_geom(sv.w, sv.h, &sp1, 1, false, bands_hint, 1.0);
                 if (!geom || !geom->lean_ok) {
                     add_exact_whole(*op);
                     if (precision != IPG_PRECISION_REFERENCE) B.exact_fallbacks++;
                     continue;
                 }
+                if (wm) wi++;
                 blob.hold(geom);
                 StreamJob j{};
                 j.src = sv;
@@ -814,12 +860,16 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                     fix_px += (uint64_t)o.dw * (uint64_t)o.dh;
                 }
                 j.fast_path = 5;
+                if (wm) {
+                    j.has_wm = 1;
+                    j.wm = make_wm(*wm);
+                }
                 const int ji = (int)sjobs.size();
                 sjobs.push_back(j);
                 B.fast_jobs++;
                 for (auto it : geom->items) {
-                    // tiles outside the crop square have no outputs: skip them
-                    if (tgm.tile_ox[it.tile + 1] == tgm.tile_ox[it.tile]) continue;
+                    // tiles outside the crop square have no outputs: skip them (unless they carry watermark rows)
+                    if (!wm && tgm.tile_ox[it.tile + 1] == tgm.tile_ox[it.tile]) continue;
                     it.job = ji;
                     (sv.layout == L_NRGBA8 ? nitems : pitems).push_back(it);
                 }
@@ -866,6 +916,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     const WmItem *d_witems = blob.dptr<const WmItem>(blob.put(witems.data(), witems.size() * sizeof(WmItem), 16));
     const WatermarkD *d_blends = blob.dptr<const WatermarkD>(blob.put(blends.data(), blends.size() * sizeof(WatermarkD), 16));
     const BlendItem *d_bitems = blob.dptr<const BlendItem>(blob.put(bitems.data(), bitems.size() * sizeof(BlendItem), 16));
+    const DirectJob *d_djobs = blob.dptr<const DirectJob>(blob.put(djobs.data(), djobs.size() * sizeof(DirectJob), 16));
+    const DirectItem *d_ditems = blob.dptr<const DirectItem>(blob.put(ditems.data(), ditems.size() * sizeof(DirectItem), 16));
     const PatchJob *d_pjobs = blob.dptr<const PatchJob>(blob.put(pjobs.data(), pjobs.size() * sizeof(PatchJob), 16));
     const BlendItem *d_pbitems = blob.dptr<const BlendItem>(blob.put(pbitems.data(), pbitems.size() * sizeof(BlendItem), 16));
     if (blob.overflow) throw std::runtime_error("parameter blob overflow (batch too heterogeneous); lower max_batch");
@@ -881,6 +933,10 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     if (c.overlap_tail && d.prev_compute) IPG_CU(cudaStreamWaitEvent(st, d.prev_compute, 0));
     if ((!fitems.empty() || !f2items.empty() || !f3items.empty()) && redo_flags) IPG_CU(cudaMemsetAsync(redo_flags, 0, 4 * max_jobs, st));
     IPG_CU(cudaEventRecord(L.ev[0], st));
+    if (!ditems.empty()) {
+        IPG_CU(launch_direct(d_djobs, d_ditems, (int)ditems.size(), fix, st));
+        B.n_kernels++;
+    }
     // Two streams: the lean local-target launch (resize + watermark copy) on the lane's stream; beside it, on a
     // side stream, the lean wide-target launch (thumbnail) and the general launch over whatever neither lean kernel
     // takes -- each fills the other's ramp and tail.  The on-demand redo of lean jobs follows both.
@@ -1424,6 +1480,7 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
         if (getenv("IPG_BAND_CTAS")) c->band_cta_target = (uint32_t)std::max(1, atoi(getenv("IPG_BAND_CTAS")));
         if (getenv("IPG_FIX_CAPACITY")) c->fix_capacity = (uint32_t)std::max(1, atoi(getenv("IPG_FIX_CAPACITY")));
         c->overlap_streams = !(getenv("IPG_NO_OVERLAP") && atoi(getenv("IPG_NO_OVERLAP")) != 0);
+        if (getenv("IPG_DIRECT")) c->use_direct = std::min(2, std::max(0, atoi(getenv("IPG_DIRECT"))));
         if (getenv("IPG_OVERLAP_TAIL")) c->overlap_tail = atoi(getenv("IPG_OVERLAP_TAIL")) != 0;
         if (getenv("IPG_STAGING_TIMEOUT_MS")) c->staging_timeout_ms = std::max(0, atoi(getenv("IPG_STAGING_TIMEOUT_MS")));
         if (getenv("IPG_FUSE_TARGETS")) c->fuse_targets = std::min(3, std::max(1, atoi(getenv("IPG_FUSE_TARGETS"))));

@@ -202,6 +202,23 @@ struct StreamJob {
 
 struct StreamItem { int32_t job; int16_t tile, band; };
 
+// Small-support fp32 resample, one thread per output pixel (k_direct): vertical upscales, which cannot stream (many output
+// rows open at once).  Same certificate and fix list as the streaming kernels.
+enum { DIRECT_MAX_TAPS = 4 };
+struct DirectJob {
+    SrcView src;
+    int32_t rect_x, rect_y;      // source rect origin (crop)
+    int32_t two_stage;           // samples pass cropAndResize's 8-bit crop stage first
+    int32_t dw, dh, dst_stride;
+    uint8_t *dst;
+    const int32_t *xoff, *xfirst; // [dw+1], [dw]
+    const float *xw;              // normalised fp32 horizontal weights (sum 1)
+    const int32_t *yoff, *yfirst; // [dh+1], [dh]
+    const float *yw;              // normalised fp32 vertical weights times the sample scale (257 for 8-bit samples, 1 for 16-bit)
+    int32_t exact_job, fix_d;
+};
+struct DirectItem { int32_t job; int32_t tile_x, tile_y; int32_t pad; }; // 32 x 8 output pixels
+
 // Standalone convert/copy + watermark blend (any layout) -------------------------
 struct WmJob {
     SrcView src;

@@ -32,6 +32,7 @@ static int current_device()
 // source adaptors (the inner expressions of x/image draw/impl.go scaleX_<type>)
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+__device__ __forceinline__ uint32_t div255(uint32_t x) { return __umulhi(x, 0x80808081u) >> 7; } // exact for every uint32
 
 __device__ __forceinline__ size_t chroma_index(int layout, int s1, int x, int y)
 {
@@ -583,26 +584,84 @@ __device__ __forceinline__ uint32_t draw_src_px(const SrcView &s, int x, int y)
     }
 }
 
+// 8-bit color.YCbCrToRGB of one pixel from the chroma terms of its chroma sample (imageutil.DrawYCbCr's inner expression)
+__device__ __forceinline__ uint32_t ycc_px8(uint32_t y, int tr, int tg, int tb)
+{
+    const int yy1 = (int)y * 0x10101;
+    const uint32_t r = (uint32_t)min(max((yy1 + tr) >> 16, 0), 0xff);
+    const uint32_t g = (uint32_t)min(max((yy1 + tg) >> 16, 0), 0xff);
+    const uint32_t b = (uint32_t)min(max((yy1 + tb) >> 16, 0), 0xff);
+    return r | (g << 8) | (b << 16) | 0xff000000u;
+}
+
+// Full-frame draw.Draw(Src) conversion.  A thread converts 8 consecutive pixels of a row per step from vector loads
+// (8 luma bytes + 4 or 8 bytes of each chroma plane, or two uint4 of NRGBA / one uint2 of Gray) into two 16-byte
+// stores; rows whose planes are not aligned for that, and the ragged right edge, take the per-pixel expression.
 __global__ void __launch_bounds__(256)
 k_watermark(const WmJob *__restrict__ jobs, const WmItem *__restrict__ items)
 {
     const WmItem it = items[blockIdx.x];
     const WmJob &J = jobs[it.job];
-    const int W = J.src.w;
-    const int y1 = min(it.row0 + WM_ROWS, J.src.h);
+    const SrcView s = J.src;
+    const int W = s.w;
+    const int y1 = min(it.row0 + WM_ROWS, s.h);
+    const int layout = s.layout;
+    const bool ycc = layout >= L_YCBCR444;
+    const bool sub_x = layout == L_YCBCR422 || layout == L_YCBCR420;
+    const bool dst_vec = ((J.wm.dst_stride | (int)(size_t)J.wm.dst) & 15) == 0;
+    bool vec = dst_vec;
+    if (layout == L_RGBA8 || layout == L_NRGBA8) vec = vec && (((size_t)s.p0 | (size_t)s.s0) & 15) == 0;
+    else vec = vec && (((size_t)s.p0 | (size_t)s.s0) & 7) == 0;
+    if (ycc) vec = vec && (((size_t)s.p1 | (size_t)s.p2 | (size_t)s.s1 | (size_t)s.s2) & (sub_x ? 3 : 7)) == 0;
+    const int Wv = vec ? (W & ~7) : 0; // columns converted 8 at a time
     for (int y = it.row0; y < y1; y++) {
         uint8_t *drow = J.wm.dst + (size_t)y * J.wm.dst_stride;
-        for (int x = threadIdx.x * 4; x < W; x += 256 * 4) {
-            uint32_t o[4];
+        for (int x = threadIdx.x * 8; x < Wv; x += 256 * 8) {
+            uint32_t o[8];
+            if (layout == L_RGBA8) {
+                const uint4 *q = (const uint4 *)(s.p0 + (size_t)y * s.s0 + (size_t)x * 4);
+                const uint4 a = __ldg(q), b = __ldg(q + 1);
+                o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+            } else if (layout == L_NRGBA8) { // drawNRGBASrc: sa = A * 0x101; c = uint8((C * sa / 0xff) >> 8); a = uint8(sa >> 8)
+                const uint4 *q = (const uint4 *)(s.p0 + (size_t)y * s.s0 + (size_t)x * 4);
+                const uint4 a = __ldg(q), b = __ldg(q + 1);
+                const uint32_t in[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                o[j] = (x + j < W) ? draw_src_px(J.src, x + j, y) : 0u;
-            if (x + 4 <= W && ((J.wm.dst_stride | (int)(size_t)J.wm.dst) & 15) == 0) {
-                *(uint4 *)(drow + (size_t)x * 4) = make_uint4(o[0], o[1], o[2], o[3]);
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t sa = (in[j] >> 24) * 0x101u;
+                    const uint32_t r = div255((in[j] & 0xff) * sa) >> 8, g = div255(((in[j] >> 8) & 0xff) * sa) >> 8,
+                                   bb = div255(((in[j] >> 16) & 0xff) * sa) >> 8;
+                    o[j] = r | (g << 8) | (bb << 16) | (in[j] & 0xff000000u);
+                }
+            } else if (layout == L_GRAY8) {
+                const uint2 g = __ldg((const uint2 *)(s.p0 + (size_t)y * s.s0 + x));
+#pragma unroll
+                for (int j = 0; j < 8; j++) o[j] = (((j < 4 ? g.x : g.y) >> (8 * (j & 3))) & 0xff) * 0x010101u | 0xff000000u;
             } else {
-                for (int j = 0; j < 4 && x + j < W; j++) *(uint32_t *)(drow + (size_t)(x + j) * 4) = o[j];
+                const uint2 yy = __ldg((const uint2 *)(s.p0 + (size_t)y * s.s0 + x));
+                const int cy = (layout == L_YCBCR420 || layout == L_YCBCR440) ? y >> 1 : y;
+                uint2 cb, cr; // chroma samples under these 8 pixels: 4 (in .x) when subsampled horizontally, else 8
+                if (sub_x) {
+                    cb = make_uint2(__ldg((const uint32_t *)(s.p1 + (size_t)cy * s.s1 + (x >> 1))), 0u);
+                    cr = make_uint2(__ldg((const uint32_t *)(s.p2 + (size_t)cy * s.s2 + (x >> 1))), 0u);
+                } else {
+                    cb = __ldg((const uint2 *)(s.p1 + (size_t)cy * s.s1 + x));
+                    cr = __ldg((const uint2 *)(s.p2 + (size_t)cy * s.s2 + x));
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int c = sub_x ? j >> 1 : j;
+                    const int cb1 = (int)(((c < 4 ? cb.x : cb.y) >> (8 * (c & 3))) & 0xff) - 128;
+                    const int cr1 = (int)(((c < 4 ? cr.x : cr.y) >> (8 * (c & 3))) & 0xff) - 128;
+                    o[j] = ycc_px8(((j < 4 ? yy.x : yy.y) >> (8 * (j & 3))) & 0xff, 91881 * cr1, -22554 * cb1 - 46802 * cr1, 116130 * cb1);
+                }
             }
+            uint4 *d = (uint4 *)(drow + (size_t)x * 4);
+            d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            d[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
+        for (int x = Wv + threadIdx.x; x < W; x += 256) // unaligned planes and the ragged right edge
+            *(uint32_t *)(drow + (size_t)x * 4) = draw_src_px(s, x, y);
     }
 }
 
@@ -1575,6 +1634,10 @@ template <bool NRGBA, int STAGES> struct __align__(128) PlanarSmem {
     XTab<1> xt;
     uint64_t full[STAGES], empty[STAGES];
     XInfo xi[2];
+    // fused watermark conversion (draw.Draw(Src) of the planar / NRGBA source into the RGBA8 frame): destination of the
+    // band's first own row at the tile's first column, and how many rows the band owns (0: no watermark on this job)
+    uint8_t *wm_row0;
+    int32_t wm_stride, wm_rows;
 };
 enum { PLANAR_STAGES = 16 / STREAM_GROUP, PLANAR_CTAS = 4, NRGBA_CTAS = 3 };
 
@@ -1584,7 +1647,6 @@ __device__ __forceinline__ float2 u16x2_f32(uint32_t a, uint32_t b)
     return __fadd2_rn(make_float2(__uint_as_float(0x4B000000u | a), __uint_as_float(0x4B000000u | b)),
                       make_float2(-8388608.0f, -8388608.0f));
 }
-__device__ __forceinline__ uint32_t div255(uint32_t x) { return __umulhi(x, 0x80808081u) >> 7; } // exact for every uint32
 
 // 16-bit sample >> SH clamped to [0, 0xffff >> (SH - 8)]: color.YCbCr.RGBA()'s "(x >> 8) clamped to 16 bits" for SH = 8;
 // for the crop stage, which keeps uint8(c16 >> 8), SH = 16 gives that byte directly (the two clamps commute with the shift).
@@ -1596,8 +1658,12 @@ template <int SH> __device__ __forceinline__ uint32_t ycc_chan(int v)
 // The V warps' row loop of k_stream_planar.  KIND 0: one chroma sample per pixel in the row (4:4:4, 4:4:0) -- or,
 // with NRGBA, no chroma at all; 1: one per pixel pair (4:2:2, 4:2:0); 2: *image.Gray.  TWO: cropAndResize's 1:1 first
 // pass stored uint8(c16 >> 8) into an *image.RGBA and scaleX_RGBA re-expands it (byte * 0x101).
-template <bool NRGBA, int KIND, bool TWO, typename SM>
-__device__ __forceinline__ void planar_vloop(SM &sm, int ngroups, int slot, int tid, const FixList &fix)
+// WM: this job also carries the watermark's full-frame conversion: a lane that owns its 4 columns stores, for every row
+// the band owns, the 8-bit pixels draw.Draw(Src) would produce -- the high bytes of the 16-bit samples it has just
+// computed (clamp and shift commute: uint8(YCbCrToRGB) == RGBA() >> 8; drawNRGBASrc's uint8((C * sa / 0xff) >> 8) is the
+// premultiplied sample >> 8), so the source is read once for the resize and the watermark frame.
+template <bool NRGBA, int KIND, bool TWO, bool WM, typename SM>
+__device__ __forceinline__ void planar_vloop(SM &sm, int ngroups, int slot, int tid, const FixList &fix, int wm_cols)
 {
     constexpr int STAGES = PLANAR_STAGES;
     VAcc<NRGBA> S;
@@ -1667,6 +1733,22 @@ __device__ __forceinline__ void planar_vloop(SM &sm, int ngroups, int slot, int 
                     c16[3 * j] = r; c16[3 * j + 1] = gg; c16[3 * j + 2] = b;
                 }
             }
+            if constexpr (WM) {
+                const int row = g * STREAM_GROUP + k;
+                if (wm_cols > 0 && row < sm.wm_rows) { // wm_cols: how many of this lane's 4 columns it owns and the image has
+                    uint32_t o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint32_t al = 0xffu;
+                        if constexpr (NRGBA) al = a16[j] >> 8;
+                        o[j] = (c16[3 * j] >> 8) | ((c16[3 * j + 1] >> 8) << 8) | ((c16[3 * j + 2] >> 8) << 16) | (al << 24);
+                    }
+                    uint8_t *d = sm.wm_row0 + (size_t)row * sm.wm_stride + (size_t)slot * 16;
+                    if (wm_cols == 4) *reinterpret_cast<uint4 *>(d) = make_uint4(o[0], o[1], o[2], o[3]);
+                    else
+                        for (int j = 0; j < wm_cols; j++) reinterpret_cast<uint32_t *>(d)[j] = o[j];
+                }
+            }
             float2 vp[6];
 #pragma unroll
             for (int i = 0; i < 6; i++) vp[i] = u16x2_f32(c16[2 * i], c16[2 * i + 1]);
@@ -1728,12 +1810,17 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
     const uint32_t y_bytes = (uint32_t)(((NRGBA ? ncols * 4 : ncols) + 15) & ~15);
     const uint32_t c_bytes = (uint32_t)(((sub_x ? (ncols + 1) >> 1 : ncols) + 15) & ~15);
 
+    const int ys1 = __ldg(J.band_y + band + 1);
+    const bool has_wm = J.has_wm != 0;
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&sm.full[s], 1);
             mbar_init(&sm.empty[s], STREAM_THREADS / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sm.wm_row0 = has_wm ? J.wm.dst + (size_t)ys0 * J.wm.dst_stride + (size_t)cx0 * 4 : nullptr;
+        sm.wm_stride = has_wm ? J.wm.dst_stride : 0;
+        sm.wm_rows = has_wm ? ys1 - ys0 : 0;
     }
     if constexpr (NRGBA) {
         // slab columns past the image edge are never written by TMA: park transparent black there (finite, feeds nothing)
@@ -1790,19 +1877,86 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
 
     // ===== V warps: one specialisation of the row loop per (source kind, crop stage), chosen per CTA =====
     const bool two_stage = J.t[0].two_stage != 0;
-    if constexpr (NRGBA) {
-        if (two_stage) planar_vloop<true, 0, true>(sm, ngroups, slot, tid, fix);
-        else           planar_vloop<true, 0, false>(sm, ngroups, slot, tid, fix);
-    } else if (gray) {
-        if (two_stage) planar_vloop<false, 2, true>(sm, ngroups, slot, tid, fix);
-        else           planar_vloop<false, 2, false>(sm, ngroups, slot, tid, fix);
-    } else if (sub_x) {
-        if (two_stage) planar_vloop<false, 1, true>(sm, ngroups, slot, tid, fix);
-        else           planar_vloop<false, 1, false>(sm, ngroups, slot, tid, fix);
-    } else {
-        if (two_stage) planar_vloop<false, 0, true>(sm, ngroups, slot, tid, fix);
-        else           planar_vloop<false, 0, false>(sm, ngroups, slot, tid, fix);
+    // the watermark frame: columns this lane owns (the overlap of consecutive warps belongs to the right-hand one, as in
+    // k_stream) and the image has; the engine attaches a watermark to single-stage (resize) jobs only
+    int wm_cols = 0;
+    if (has_wm) {
+        const int c = cx0 + slot * STREAM_PX;
+        const bool own = c < min(W, cx0 + J.tile_w) && (warp == 3 || (tid & 31) * STREAM_PX < ws);
+        if (own) wm_cols = min(STREAM_PX, min(W, cx0 + J.tile_w) - c);
     }
+    if constexpr (NRGBA) {
+        if (two_stage)   planar_vloop<true, 0, true, false>(sm, ngroups, slot, tid, fix, 0);
+        else if (has_wm) planar_vloop<true, 0, false, true>(sm, ngroups, slot, tid, fix, wm_cols);
+        else             planar_vloop<true, 0, false, false>(sm, ngroups, slot, tid, fix, 0);
+    } else if (gray) {
+        if (two_stage)   planar_vloop<false, 2, true, false>(sm, ngroups, slot, tid, fix, 0);
+        else if (has_wm) planar_vloop<false, 2, false, true>(sm, ngroups, slot, tid, fix, wm_cols);
+        else             planar_vloop<false, 2, false, false>(sm, ngroups, slot, tid, fix, 0);
+    } else if (sub_x) {
+        if (two_stage)   planar_vloop<false, 1, true, false>(sm, ngroups, slot, tid, fix, 0);
+        else if (has_wm) planar_vloop<false, 1, false, true>(sm, ngroups, slot, tid, fix, wm_cols);
+        else             planar_vloop<false, 1, false, false>(sm, ngroups, slot, tid, fix, 0);
+    } else {
+        if (two_stage)   planar_vloop<false, 0, true, false>(sm, ngroups, slot, tid, fix, 0);
+        else if (has_wm) planar_vloop<false, 0, false, true>(sm, ngroups, slot, tid, fix, wm_cols);
+        else             planar_vloop<false, 0, false, false>(sm, ngroups, slot, tid, fix, 0);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// k_direct: small-support fp32 resample, one thread per output pixel.
+//
+// For every contributing source row the horizontal sum (fmaf, taps in order), then its fmaf into the vertical sum:
+// ny * nx taps read through L1 (neighbouring threads share most of them).  RGBA8 bytes go to fp32 with the 2^23 trick
+// and the vertical weights carry the 0x101; every other layout goes through sample16() (16-bit samples, unscaled
+// weights).  |T_fp32 - T_exact| obeys the same bound as the streaming kernels (plan.cpp certified_fix_d with one thread
+// per output: every rounding is a round-to-nearest of a partial sum below 2^16 in final units), so the same ambiguity
+// window flags the bytes k_exact_fix re-evaluates in float64.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_direct(const DirectJob *__restrict__ jobs, const DirectItem *__restrict__ items, FixList fix)
+{
+    const DirectItem it = items[blockIdx.x];
+    const DirectJob &J = jobs[it.job];
+    const int ox = it.tile_x * 32 + (threadIdx.x & 31);
+    const int oy = it.tile_y * 8 + (threadIdx.x >> 5);
+    if (ox >= J.dw || oy >= J.dh) return;
+    const int kx0 = __ldg(J.xoff + ox), nx = __ldg(J.xoff + ox + 1) - kx0;
+    const int ky0 = __ldg(J.yoff + oy), ny = __ldg(J.yoff + oy + 1) - ky0;
+    const int x0 = __ldg(J.xfirst + ox) + J.rect_x, y0 = __ldg(J.yfirst + oy) + J.rect_y;
+    const bool rgba8 = J.src.layout == L_RGBA8;
+    const bool two = J.two_stage != 0;
+    float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
+    for (int j = 0; j < ny; j++) {
+        float2 srg = make_float2(0.f, 0.f), sba = make_float2(0.f, 0.f);
+        if (rgba8) {
+            const uint32_t *row = (const uint32_t *)(J.src.p0 + (size_t)(y0 + j) * J.src.s0) + x0;
+            for (int k = 0; k < nx; k++) {
+                uint32_t q = __ldg(row + k);
+                if (two) q = clamp_to_alpha(q); // the crop stage stores min(c, a) >> 8 of byte * 0x101: the clamped byte
+                const float w = __ldg(J.xw + kx0 + k);
+                const float2 m = make_float2(-8388608.0f, -8388608.0f), ww = make_float2(w, w);
+                srg = __ffma2_rn(__fadd2_rn(magic2<0, 1>(q, q), m), ww, srg);
+                sba = __ffma2_rn(__fadd2_rn(magic2<2, 3>(q, q), m), ww, sba);
+            }
+        } else {
+            for (int k = 0; k < nx; k++) {
+                uint32_t p[4];
+                sample16(J.src, x0 + k, y0 + j, p);
+                if (two) to_cropped_rgba16(p);
+                const float w = __ldg(J.xw + kx0 + k);
+                const float2 ww = make_float2(w, w);
+                srg = __ffma2_rn(u16x2_f32(p[0], p[1]), ww, srg);
+                sba = __ffma2_rn(u16x2_f32(p[2], p[3]), ww, sba);
+            }
+        }
+        const float wy = __ldg(J.yw + ky0 + j);
+        const float2 wwy = make_float2(wy, wy);
+        rg = __ffma2_rn(srg, wwy, rg);
+        ba = __ffma2_rn(sba, wwy, ba);
+    }
+    xfinish(J, (uint32_t)J.fix_d, ox, oy, rg, ba, fix);
 }
 
 template <bool NRGBA>
@@ -1883,6 +2037,13 @@ cudaError_t launch_stream_fast(const StreamJob *jobs, const StreamItem *items, i
                       : launch_stream_t<2, false, 3>(jobs, items, n_items, fix, st);
     return any_wm ? launch_stream_t<1, true, 2>(jobs, items, n_items, fix, st)
                   : launch_stream_t<1, false, 2>(jobs, items, n_items, fix, st);
+}
+
+cudaError_t launch_direct(const DirectJob *jobs, const DirectItem *items, int n_items, FixList fix, cudaStream_t st)
+{
+    if (n_items <= 0) return cudaSuccess;
+    k_direct<<<n_items, 256, 0, st>>>(jobs, items, fix);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_exact_tiles(const ExactJob *jobs, const ExactItem *items, int n_items, cudaStream_t st)

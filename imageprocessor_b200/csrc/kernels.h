@@ -17,6 +17,9 @@ cudaError_t launch_stream_fast(const StreamJob *jobs, const StreamItem *items, i
 // The lean streaming resample for planar YCbCr sources (one target per job, cached pass forms only).
 cudaError_t launch_stream_planar(const StreamJob *jobs, const StreamItem *items, int n_items, bool nrgba, FixList fix, cudaStream_t st);
 
+// Small-support fp32 resample (vertical upscales, mild downscales), one CTA per 32x8 output tile; flags into `fix`.
+cudaError_t launch_direct(const DirectJob *jobs, const DirectItem *items, int n_items, FixList fix, cudaStream_t st);
+
 // fp64 reference-order resample of whole outputs: one CTA per 32x8 output tile.
 cudaError_t launch_exact_tiles(const ExactJob *jobs, const ExactItem *items, int n_items,
                                cudaStream_t st);

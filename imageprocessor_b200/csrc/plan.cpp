@@ -383,6 +383,40 @@ static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const Stream
     return g;
 }
 
+std::shared_ptr<const DirectGeom> get_direct_geom(const StreamTargetSpec &s, double sample_scale, bool mild_downscales)
+{
+    if (s.dw <= 0 || s.dh <= 0 || s.rect_w <= 0 || s.rect_h <= 0) return nullptr;
+    if (s.rect_h >= s.dh && !mild_downscales) return nullptr; // streams: measured faster there (see plan.h)
+    using Key = std::tuple<int, int, int, int, long long>;
+    static std::mutex mu;
+    static AgedCache<Key, std::shared_ptr<const DirectGeom>> cache(2048);
+    const Key key{s.dw, s.rect_w, s.dh, s.rect_h, (long long)(sample_scale * 65536.0)};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        std::shared_ptr<const DirectGeom> hit;
+        if (cache.find(key, hit)) return hit;
+    }
+    std::shared_ptr<DirectGeom> g;
+    auto ax = get_axis_plan(s.dw, s.rect_w), ay = get_axis_plan(s.dh, s.rect_h);
+    const bool v_upscale = s.rect_h < s.dh;
+    if (ax->contiguous && ay->contiguous && ay->max_taps <= DIRECT_MAX_TAPS && (ax->max_taps <= DIRECT_MAX_TAPS || (v_upscale && ax->max_taps <= 256))) {
+        g = std::make_shared<DirectGeom>();
+        g->ax = ax;
+        g->ay = ay;
+        g->xw.resize(ax->w.size());
+        for (int32_t o = 0; o < s.dw; o++)
+            for (int32_t k = ax->off[o]; k < ax->off[o + 1]; k++) g->xw[k] = (float)(ax->w[k] * ax->inv[o]);
+        g->yw.resize(ay->w.size());
+        for (int32_t o = 0; o < s.dh; o++)
+            for (int32_t k = ay->off[o]; k < ay->off[o + 1]; k++) g->yw[k] = (float)(ay->w[k] * ay->inv[o] * sample_scale);
+        g->fix_d = certified_fix_d(ax->max_taps, ay->max_taps, 1);
+        if (g->fix_d >= 120) g.reset(); // an opaque alpha sits 128 units from a quantiser step: keep the window inside it
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    cache.put(key, g);
+    return g;
+}
+
 namespace {
 struct GeomKey {
     int W, H, n_targets, has_wm, n_bands;

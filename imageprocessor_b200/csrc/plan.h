@@ -72,6 +72,20 @@ struct StreamGeom {
                                     // the lean k_stream instantiation can run it (given opaque pixels)
 };
 
+// fp32 tables of the small-support direct kernel (k_direct) for one target: per axis the newDistrib taps with weights
+// normalised to sum 1 (the vertical ones times the sample scale).  Cached like the stream geometry.
+struct DirectGeom {
+    std::shared_ptr<const AxisPlan> ax, ay;
+    std::vector<float> xw, yw;
+    int32_t fix_d = 0;
+};
+// nullptr unless the target is a vertical upscale (no streaming form exists: many output rows are open at once) with
+// at most DIRECT_MAX_TAPS taps per output row... vertically, any horizontal support up to 200 taps.  With
+// mild_downscales (IPG_DIRECT=2, experiments) downscales of <= DIRECT_MAX_TAPS taps per axis are taken too; measured
+// on the B200 (r2, tools/size_sweep.py) the streaming kernel is faster there -- 12.9 vs 16.3 us at 1152x864, 15.8 vs
+// 25.9 at 1632x1224, 17.6 vs 28.1 at 2048x1536 (resize + thumbnail per image) -- so the engine does not ask for them.
+std::shared_ptr<const DirectGeom> get_direct_geom(const StreamTargetSpec &t, double sample_scale, bool mild_downscales = false);
+
 // Returns nullptr when the geometry cannot stream (upscale in y, more than two
 // output rows open at once, support wider than a slab, ...): caller uses k_exact.
 // `sample_scale` maps source samples to the 16-bit scale (257 for 8-bit RGBA).

@@ -169,3 +169,56 @@ extern "C" int planemu_run16(const uint16_t *src, int stride, int W, int H, int 
 {
     return run_impl<uint16_t>(src, stride, W, H, n_targets, specs, two_stage, dsts, flags, bands_hint, info);
 }
+
+// ---- k_direct (small-support fp32 kernel, one thread per output pixel), mirrored: for every contributing row the
+// horizontal fmaf chain, then its fmaf into the vertical sum; same quantiser, same window.  spec as above; SAMPLE as above.
+template <typename SAMPLE>
+static int direct_impl(const SAMPLE *src, int stride, int W, int H, const int *spec, int two_stage, uint8_t *dst, uint8_t *flags,
+                       float *capture, int *info)
+{
+    constexpr bool WIDE = sizeof(SAMPLE) == 2;
+    const StreamTargetSpec sp{spec[0], spec[1], spec[2], spec[3], spec[4], spec[5]};
+    if (sp.rect_x < 0 || sp.rect_y < 0 || sp.rect_x + sp.rect_w > W || sp.rect_y + sp.rect_h > H) return -2;
+    auto g = get_direct_geom(sp, WIDE ? 1.0 : 257.0, true); // (the kernel's arithmetic is certified for mild downscales as well)
+    if (!g) return -1;
+    const AxisPlan &ax = *g->ax, &ay = *g->ay;
+    for (int oy = 0; oy < sp.dh; oy++)
+        for (int ox = 0; ox < sp.dw; ox++) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const int kx0 = ax.off[ox], nx = ax.off[ox + 1] - kx0, ky0 = ay.off[oy], ny = ay.off[oy + 1] - ky0;
+            const int x0 = ax.first[ox] + sp.rect_x, y0 = ay.first[oy] + sp.rect_y;
+            for (int j = 0; j < ny; j++) {
+                float s[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int k = 0; k < nx; k++) {
+                    SAMPLE px[4];
+                    memcpy(px, src + (size_t)(y0 + j) * stride + (size_t)(x0 + k) * 4, 4 * sizeof(SAMPLE));
+                    if (two_stage) {
+                        for (int q = 0; q < 3; q++) px[q] = std::min(px[q], px[3]);
+                        if (WIDE) for (int q = 0; q < 4; q++) px[q] = (SAMPLE)((px[q] >> 8) * 0x101);
+                    }
+                    for (int q = 0; q < 4; q++) s[q] = std::fmaf((float)px[q], g->xw[kx0 + k], s[q]);
+                }
+                for (int q = 0; q < 4; q++) acc[q] = std::fmaf(s[q], g->yw[ky0 + j], acc[q]);
+            }
+            for (int q = 0; q < 3; q++) acc[q] = std::fmin(acc[q], acc[3]);
+            bool amb = false;
+            uint8_t *d = dst + ((size_t)oy * sp.dw + ox) * 4;
+            for (int q = 0; q < 4; q++) d[q] = (uint8_t)quant16(acc[q], g->fix_d, amb);
+            if (flags) flags[(size_t)oy * sp.dw + ox] = amb ? 1 : 16;
+            if (capture)
+                for (int q = 0; q < 4; q++) capture[((size_t)oy * sp.dw + ox) * 4 + q] = std::fmaf(acc[q], 256.0f, 128.0f);
+        }
+    if (info) { info[0] = g->fix_d; info[1] = ax.max_taps; info[2] = ay.max_taps; }
+    return 0;
+}
+
+extern "C" int planemu_direct(const uint8_t *src, int stride, int W, int H, const int *spec, int two_stage, uint8_t *dst,
+                              uint8_t *flags, float *capture, int *info)
+{
+    return direct_impl<uint8_t>(src, stride, W, H, spec, two_stage, dst, flags, capture, info);
+}
+extern "C" int planemu_direct16(const uint16_t *src, int stride, int W, int H, const int *spec, int two_stage, uint8_t *dst,
+                                uint8_t *flags, float *capture, int *info)
+{
+    return direct_impl<uint16_t>(src, stride, W, H, spec, two_stage, dst, flags, capture, info);
+}

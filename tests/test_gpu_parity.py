@@ -394,3 +394,37 @@ def test_watermark_patch_only_is_ignored_for_converting_layouts(engines, oracle)
     out = e.run(ip.Image.from_rgba(a, ip.NRGBA8), [ip.OpSpec.watermark(w, h, col, [ip.GlyphMask(*g) for g in gl],
                                                                       flags=L.OPF_WATERMARK_PATCH_ONLY)])
     assert np.array_equal(out[0], oracle.watermark(oracle.Raster.rgba(a, oracle.NRGBA8), col, [oracle.Glyph(*g) for g in gl]))
+
+
+@pytest.mark.parametrize("kind", ["nrgba", "gray", "420", "422", "444", "440"])
+def test_watermark_frame_of_converting_layouts_fused_and_standalone(engines, oracle, kind):
+    """draw.Draw(Src) of a non-RGBA source is a conversion.  With a streaming resize in the ticket it rides on that pass
+    (k_stream_planar stores the high bytes of the 16-bit samples it computes); without one -- or when the resize cannot
+    stream (upscale) -- the vectorised k_watermark does it.  Odd widths, unaligned tails, bands and tiles; every byte
+    of the frame, the glyph blend on top, and the resize / thumbnail of the same ticket against the oracle."""
+    rng = np.random.default_rng({"nrgba": 11, "gray": 12, "420": 13, "422": 14, "444": 15, "440": 16}[kind])
+    e = engines(ip.PRECISION_EXACT)
+    col = (255, 255, 255, 127)
+    for (w, h, with_resize) in [(1603, 1201, True), (2049, 777, True), (4000, 3000, True), (333, 222, True), (1001, 999, False),
+                                (40, 30, True), (5000, 129, True)]:
+        if kind == "nrgba":
+            a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+            img, R = ip.Image.from_rgba(a, ip.NRGBA8), oracle.Raster.rgba(a, oracle.NRGBA8)
+        elif kind == "gray":
+            g = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            img, R = ip.Image.from_gray(g), oracle.Raster.gray(g)
+        else:
+            lay = {"420": ip.YCBCR420, "422": ip.YCBCR422, "444": ip.YCBCR444, "440": ip.YCBCR440}[kind]
+            y, cb, cr = _ycbcr(oracle, w, h, lay, int(rng.integers(1 << 30)))
+            img, R = ip.Image.from_ycbcr(y, cb, cr, lay), oracle.Raster.ycbcr(y, cb, cr, lay)
+        gl = synthetic_glyphs(w, h, 21, n=5)
+        ops = [ip.OpSpec.watermark(w, h, col, [ip.GlyphMask(*g) for g in gl])]
+        nw, nh = ip.keep_aspect_dims(w, h, 1024, 768)
+        cx, cy, cs = ip.crop_square(w, h)
+        if with_resize:
+            ops += [ip.OpSpec.resize(nw, nh), ip.OpSpec.thumb_crop((cx, cy, cs, cs), 64)]
+        out = e.run(img, ops)
+        assert np.array_equal(out[0], oracle.watermark(R, col, [oracle.Glyph(*g) for g in gl])), f"{kind} watermark {w}x{h}"
+        if with_resize:
+            assert np.array_equal(out[1], oracle.resize_image(R, nw, nh)), f"{kind} resize {w}x{h}"
+            assert np.array_equal(out[2], oracle.crop_and_resize(R, 64)), f"{kind} thumb {w}x{h}"

@@ -388,3 +388,57 @@ def test_8k_thumbnail_support_certified(emu, oracle):
     ref = oracle.crop_and_resize(oracle.Raster.rgba(a), 100)
     amb = f == 1
     assert np.array_equal(d[~amb], ref[~amb]) and np.abs(d.astype(int) - ref.astype(int)).max() <= 1
+
+
+# ---- k_direct: the small-support kernel (vertical upscales, mild downscales) ------------------------------------------
+def run_direct(L, a, spec, two_stage, sixteen=False):
+    h, w = a.shape[:2]
+    dst = np.zeros((spec[5], spec[4], 4), np.uint8)
+    flag = np.zeros((spec[5], spec[4]), np.uint8)
+    cap = np.zeros((spec[5], spec[4], 4), np.float32)
+    info = np.zeros(4, np.int32)
+    sp = np.array(spec, np.int32)
+    fn = L.planemu_direct16 if sixteen else L.planemu_direct
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = fn(a.ctypes.data, a.strides[0] // a.itemsize, w, h, sp.ctypes.data, two_stage, dst.ctypes.data, flag.ctypes.data,
+            cap.ctypes.data, info.ctypes.data)
+    return rc, dst, flag, cap, info
+
+
+@pytest.mark.parametrize("w,h,dw,dh", [(640, 480, 1024, 768), (147, 147, 767, 767), (1152, 864, 1024, 768), (1300, 975, 1024, 768),
+                                       (1002, 751, 1023, 767), (400, 30, 102, 76), (64, 48, 64, 48), (3, 2, 9, 7)])
+@pytest.mark.parametrize("alpha", ["opaque", "raw"])
+def test_direct_kernel_certified_fp32(emu, oracle, w, h, dw, dh, alpha):
+    """Upscales (what the reference does to small images), 1:1 and mild downscales: unflagged bytes equal the float64
+    oracle, flagged ones are within 1, the measured error stays inside the proven bound."""
+    a = rgba_random(w, h, w * 7 + h, alpha)
+    rc, d, f, cap, info = run_direct(emu, a, (0, 0, w, h, dw, dh), 0)
+    assert rc == 0
+    ref = oracle.resize_image(oracle.Raster.rgba(a), dw, dh)
+    amb = f == 1
+    diff = np.abs(d.astype(int) - ref.astype(int)).max(axis=2)
+    assert diff[~amb].max(initial=0) == 0, "an unflagged byte differs from the fp64 oracle"
+    assert diff.max(initial=0) <= 1 and amb.mean() < 0.03
+    if alpha == "opaque":       # (with alpha < 255 the premultiplied clamp may bind: the bound is about the unclamped sums)
+        T, tx, ty = exact_T(oracle, a, (0, 0, w, h, dw, dh))
+        assert np.abs(cap.astype(np.float64) - T).max() <= info[0] - 2
+        assert info[0] == emu.planemu_fix_d(int(info[1]), int(info[2]), 1)
+
+
+def test_direct_kernel_two_stage_sixteen_bit_and_rejections(emu, oracle):
+    # the crop thumbnail of a small image (cropAndResize's 8-bit crop stage, then an upscale)
+    a = rgba_random(180, 120, 3, "raw")
+    cx, cy, cs = oracle.crop_square(180, 120)
+    rc, d, f, cap, info = run_direct(emu, a, (cx, cy, cs, cs, 200, 200), 1)
+    assert rc == 0
+    ref = oracle.crop_and_resize(oracle.Raster.rgba(a), 200)
+    assert np.array_equal(d[f != 1], ref[f != 1]) and np.abs(d.astype(int) - ref.astype(int)).max() <= 1
+    # 16-bit samples (what an NRGBA / YCbCr / Gray source feeds): upscale of a 4:2:0 source
+    R, s = samples16(oracle, "420", 333, 222, 5)
+    rc, d, f, cap, info = run_direct(emu, s, (0, 0, 333, 222, 1024, 682), 0, sixteen=True)
+    assert rc == 0
+    ref = oracle.resize_image(R, 1024, 682)
+    assert np.array_equal(d[f != 1], ref[f != 1]) and np.abs(d.astype(int) - ref.astype(int)).max() <= 1
+    # supports wider than DIRECT_MAX_TAPS on a streamable geometry are not this kernel's: the planner says so
+    rc, *_ = run_direct(emu, rgba_random(400, 300, 1), (0, 0, 400, 300, 102, 76), 0)
+    assert rc == -1
