@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("IPG_LIB_PATH") or os.path.join(_HERE, "libipgpu.so") 
 # ipg_status
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_TIMEOUT, ERR_NO_DEVICE, ERR_SHUTDOWN, ERR_INTERNAL = 0, -1, -2, -3, -4, -5, -6, -7
 # ipg_layout
-RGBA8, NRGBA8, GRAY8, YCBCR444, YCBCR422, YCBCR420, YCBCR440 = range(7)
+RGBA8, NRGBA8, GRAY8, YCBCR444, YCBCR422, YCBCR420, YCBCR440, RGBA64, NRGBA64, GRAY16 = range(10)
 # ipg_memspace
 MEM_HOST, MEM_DEVICE = 0, 1
 # ipg_precision

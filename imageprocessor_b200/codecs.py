@@ -11,6 +11,7 @@ stdlib draw.Draw switch on it (Spec R/W):
     PNG   8-bit truecolour                    -> *image.RGBA  (opaque)
     PNG   8-bit truecolour + alpha            -> *image.NRGBA (straight alpha)
     PNG   8-bit gray                          -> *image.Gray
+    PNG   16-bit gray / colour / + alpha      -> *image.Gray16 / *image.RGBA64 / *image.NRGBA64 (generic RGBA64At path)
     PNG / GIF paletted                        -> *image.Paletted: Scale and draw.Draw reach it through At(x,y).RGBA(),
                                                  which for color.RGBA / color.NRGBA palette entries is byte * 0x101 resp.
                                                  the 16-bit premultiply of scaleX_NRGBA -- bit-identical to expanding the
@@ -36,6 +37,8 @@ from .engine import Image
 def decode(data: bytes) -> Tuple[Image, str]:
     """image.Decode stand-in: (raster of the concrete type Go would produce, format name)."""
     from PIL import Image as PI
+    if data[:8] == b"\x89PNG\r\n\x1a\n" and len(data) > 26 and data[24] == 16:
+        return _decode_png16(data, data[25]), "png"
     im = PI.open(io.BytesIO(data))
     fmt = (im.format or "").lower()
     if fmt == "jpeg":
@@ -71,6 +74,29 @@ def decode(data: bytes) -> Tuple[Image, str]:
     a[..., :3] = rgb
     a[..., 3] = 255
     return Image.from_rgba(a, L.RGBA8, opaque_hint=True), fmt or "png"
+
+
+def _decode_png16(data: bytes, color_type: int) -> Image:
+    """A 16-bit PNG as Go's image/png decodes it: gray -> *image.Gray16, truecolour -> *image.RGBA64 (opaque),
+    gray+alpha / truecolour+alpha -> *image.NRGBA64.  (PIL narrows 16-bit colour to 8 bits; OpenCV keeps it.)"""
+    import cv2
+    a = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_UNCHANGED)
+    if a is None or a.dtype != np.uint16:
+        raise ValueError("png: cannot decode 16-bit image")
+    if a.ndim == 2:                       # gray
+        return Image.from_deep(np.ascontiguousarray(a), L.GRAY16)
+    h, w, c = a.shape
+    out = np.empty((h, w, 4), np.uint16)
+    if c == 2:                            # gray + alpha
+        out[..., 0] = out[..., 1] = out[..., 2] = a[..., 0]
+        out[..., 3] = a[..., 1]
+        return Image.from_deep(out, L.NRGBA64)
+    out[..., 0], out[..., 1], out[..., 2] = a[..., 2], a[..., 1], a[..., 0]     # OpenCV hands back BGR(A)
+    if c == 4:
+        out[..., 3] = a[..., 3]
+        return Image.from_deep(out, L.NRGBA64)
+    out[..., 3] = 0xFFFF
+    return Image.from_deep(out, L.RGBA64)
 
 
 def expand_paletted(indices: np.ndarray, palette_rgba: np.ndarray) -> Image:

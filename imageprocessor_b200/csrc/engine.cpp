@@ -56,11 +56,13 @@ static std::string cuda_msg(const char *what, cudaError_t e)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static int plane_count(int layout) { return layout >= IPG_LAYOUT_YCBCR444 ? 3 : 1; }
+static int plane_count(int layout) { return (layout >= IPG_LAYOUT_YCBCR444 && layout <= IPG_LAYOUT_YCBCR440) ? 3 : 1; }
 static void plane_dims(int layout, int plane, int w, int h, int *pw_bytes, int *ph)
 {
     if (plane == 0) {
-        *pw_bytes = (layout == IPG_LAYOUT_RGBA8 || layout == IPG_LAYOUT_NRGBA8) ? w * 4 : w;
+        *pw_bytes = (layout == IPG_LAYOUT_RGBA8 || layout == IPG_LAYOUT_NRGBA8) ? w * 4
+                    : (layout == IPG_LAYOUT_RGBA64 || layout == IPG_LAYOUT_NRGBA64) ? w * 8
+                    : layout == IPG_LAYOUT_GRAY16 ? w * 2 : w;
         *ph = h;
         return;
     }
@@ -204,6 +206,9 @@ struct OpRec {
     int dst_stride = 0;
     int dst_mem = 0;
     int flags = 0;
+    bool ycc_out = false;     // dst_layout == IPG_LAYOUT_YCBCR420: dst / dst_cb / dst_cr are the planes, dev_out an arena RGBA temp
+    void *dst_cb = nullptr, *dst_cr = nullptr;
+    int dst_cstride = 0;
     bool patch_only = false;  // IPG_OPF_WATERMARK_PATCH_ONLY on an RGBA8 source: only the glyph union box is produced
     int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0; // ... that box (empty: nothing to do)
     uint8_t *stage = nullptr; // staging for a non-pinned host dst (tight rows)
@@ -419,6 +424,9 @@ static size_t ticket_device_bytes(const Ticket &t)
     }
     for (auto &op : t.ops) {
         if (op.patch_only) n += (align_up((size_t)std::max(op.bx1 - op.bx0, 0) * 4, 256) + 256) * (size_t)std::max(op.by1 - op.by0, 0) + 256;
+        else if (op.ycc_out) // the RGBA result in the arena, plus the three planes when they are read back to the host
+            n += (align_up((size_t)std::max(op.dw, 0) * 4, 256) + 256) * (size_t)std::max(op.dh, 0) +
+                 2 * (align_up((size_t)std::max(op.dw, 0), 256) + 256) * (size_t)std::max(op.dh, 0) + 1024;
         else if (op.dst_mem == IPG_MEM_HOST) n += (align_up((size_t)std::max(op.dw, 0) * 4, 256) + 256) * (size_t)std::max(op.dh, 0) + 256;
         for (auto &g : op.glyphs) n += align_up(g.mask.size(), 256) + 256;
         n += 4096;
@@ -458,6 +466,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     std::vector<WmItem> witems;
     std::vector<WatermarkD> blends;   // every watermark of the batch that has glyphs
     std::vector<BlendItem> bitems;
+    std::vector<YccJob> yjobs;        // results handed back as planar YCbCr 4:2:0 (dst_layout)
+    std::vector<YccItem> yitems;
     std::vector<DirectJob> djobs;     // small-support targets (vertical upscales, mild downscales): k_direct
     std::vector<DirectItem> ditems;
     std::vector<PatchJob> pjobs;      // patch-only watermarks (RGBA8 sources): glyph box alone
@@ -541,7 +551,33 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 }
                 continue;
             }
-            if (op.dst_mem == IPG_MEM_DEVICE) {
+            if (op.ycc_out) { // RGBA result in the arena; converted after the last kernel that writes it; planes go back
+                const size_t pitch = align_up((size_t)op.dw * 4, 256);
+                op.dev_out = arena.take(pitch * (size_t)op.dh);
+                if (!op.dev_out) throw std::runtime_error("device arena exhausted (destination)");
+                op.dev_pitch = pitch;
+                const int cw = (op.dw + 1) / 2, ch = (op.dh + 1) / 2;
+                YccJob yj{};
+                yj.rgba = op.dev_out; yj.rgba_pitch = (int)pitch; yj.w = op.dw; yj.h = op.dh;
+                if (op.dst_mem == IPG_MEM_DEVICE) {
+                    yj.y = (uint8_t *)op.dst; yj.cb = (uint8_t *)op.dst_cb; yj.cr = (uint8_t *)op.dst_cr;
+                    yj.y_pitch = op.dst_stride; yj.c_pitch = op.dst_cstride;
+                } else {
+                    const size_t yp = align_up((size_t)op.dw, 256), cp = align_up((size_t)cw, 256);
+                    yj.y = arena.take(yp * (size_t)op.dh);
+                    yj.cb = arena.take(cp * (size_t)ch);
+                    yj.cr = arena.take(cp * (size_t)ch);
+                    if (!yj.y || !yj.cb || !yj.cr) throw std::runtime_error("device arena exhausted (YCbCr destination)");
+                    yj.y_pitch = (int)yp; yj.c_pitch = (int)cp;
+                    readbacks.push_back({yj.y, yp, op.dst, (size_t)op.dst_stride, (size_t)op.dw, op.dh});
+                    readbacks.push_back({yj.cb, cp, op.dst_cb, (size_t)op.dst_cstride, (size_t)cw, ch});
+                    readbacks.push_back({yj.cr, cp, op.dst_cr, (size_t)op.dst_cstride, (size_t)cw, ch});
+                }
+                const int ji = (int)yjobs.size();
+                yjobs.push_back(yj);
+                for (int ty = 0; ty < (op.dh + 15) / 16; ty++)
+                    for (int tx = 0; tx < (op.dw + 255) / 256; tx++) yitems.push_back(YccItem{ji, tx, ty, 0});
+            } else if (op.dst_mem == IPG_MEM_DEVICE) {
                 op.dev_out = (uint8_t *)op.dst;
                 op.dev_pitch = (size_t)op.dst_stride;
             } else {
@@ -916,6 +952,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     const WmItem *d_witems = blob.dptr<const WmItem>(blob.put(witems.data(), witems.size() * sizeof(WmItem), 16));
     const WatermarkD *d_blends = blob.dptr<const WatermarkD>(blob.put(blends.data(), blends.size() * sizeof(WatermarkD), 16));
     const BlendItem *d_bitems = blob.dptr<const BlendItem>(blob.put(bitems.data(), bitems.size() * sizeof(BlendItem), 16));
+    const YccJob *d_yjobs = blob.dptr<const YccJob>(blob.put(yjobs.data(), yjobs.size() * sizeof(YccJob), 16));
+    const YccItem *d_yitems = blob.dptr<const YccItem>(blob.put(yitems.data(), yitems.size() * sizeof(YccItem), 16));
     const DirectJob *d_djobs = blob.dptr<const DirectJob>(blob.put(djobs.data(), djobs.size() * sizeof(DirectJob), 16));
     const DirectItem *d_ditems = blob.dptr<const DirectItem>(blob.put(ditems.data(), ditems.size() * sizeof(DirectItem), 16));
     const PatchJob *d_pjobs = blob.dptr<const PatchJob>(blob.put(pjobs.data(), pjobs.size() * sizeof(PatchJob), 16));
@@ -1010,6 +1048,10 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     }
     if (!pbitems.empty()) {
         IPG_CU(launch_blend_patch(d_pjobs, d_pbitems, (int)pbitems.size(), st));
+        B.n_kernels++;
+    }
+    if (!yitems.empty()) { // after every kernel that writes an RGBA result (stream, fix-ups, blends)
+        IPG_CU(launch_rgba_to_ycbcr420(d_yjobs, d_yitems, (int)yitems.size(), st));
         B.n_kernels++;
     }
     IPG_CU(cudaEventRecord(L.ev[3], st));
@@ -1180,7 +1222,8 @@ static void completer_main(Ctx *c, Device *d)
 static int validate(const ipg_image_desc *src, const ipg_op *ops, int n_ops)
 {
     if (!src || !ops || n_ops <= 0) return fail(IPG_ERR_INVALID, "null source/ops or n_ops <= 0");
-    if (src->layout < IPG_LAYOUT_RGBA8 || src->layout > IPG_LAYOUT_YCBCR440) return fail(IPG_ERR_INVALID, "unknown source layout");
+    if (src->layout < IPG_LAYOUT_RGBA8 || src->layout > IPG_LAYOUT_GRAY16) return fail(IPG_ERR_INVALID, "unknown source layout");
+    if (src->layout >= IPG_LAYOUT_RGBA64 && src->width > (1 << 27)) return fail(IPG_ERR_INVALID, "source image too large");
     if (src->width <= 0 || src->height <= 0) return fail(IPG_ERR_INVALID, "source image is empty");
     if ((int64_t)src->width * src->height > (int64_t)1 << 30) return fail(IPG_ERR_INVALID, "source image too large");
     for (int p = 0; p < plane_count(src->layout); p++) {
@@ -1199,7 +1242,13 @@ static int validate(const ipg_image_desc *src, const ipg_op *ops, int n_ops)
         if (o.dst_w > 65536 || o.dst_h > 65536) return fail(IPG_ERR_INVALID, "destination too large");
         if (o.kind == IPG_OP_WATERMARK && (o.dst_w != src->width || o.dst_h != src->height))
             return fail(IPG_ERR_INVALID, "watermark destination must have the source size");
-        if (o.dst_w > 0 && o.dst_h > 0) {
+        if (o.dst_layout != IPG_LAYOUT_RGBA8 && o.dst_layout != IPG_LAYOUT_YCBCR420)
+            return fail(IPG_ERR_INVALID, "destination layout must be RGBA8 or YCBCR420");
+        if (o.dst_layout == IPG_LAYOUT_YCBCR420 && o.dst_w > 0 && o.dst_h > 0) {
+            if (!o.dst || !o.dst_cb || !o.dst_cr) return fail(IPG_ERR_INVALID, "destination plane pointer is null");
+            if (o.dst_stride < o.dst_w || o.dst_cstride < (o.dst_w + 1) / 2) return fail(IPG_ERR_INVALID, "destination plane stride smaller than a row");
+            if (o.flags & IPG_OPF_WATERMARK_PATCH_ONLY) return fail(IPG_ERR_INVALID, "a patch-only watermark has no YCbCr form");
+        } else if (o.dst_w > 0 && o.dst_h > 0) {
             if (!o.dst) return fail(IPG_ERR_INVALID, "destination pointer is null");
             if (o.dst_stride < o.dst_w * 4) return fail(IPG_ERR_INVALID, "destination stride smaller than a row");
             if (o.dst_memspace == IPG_MEM_DEVICE && ((o.dst_stride & 3) || ((uintptr_t)o.dst & 3)))
@@ -1258,6 +1307,15 @@ static int submit_impl(Ctx *c, int dev_index, const ipg_image_desc *src, const i
         memcpy(r.color, o.color, 4);
         r.dst = o.dst; r.dst_stride = o.dst_stride; r.dst_mem = o.dst_memspace;
         r.flags = o.flags;
+        r.ycc_out = o.dst_layout == IPG_LAYOUT_YCBCR420;
+        r.dst_cb = o.dst_cb; r.dst_cr = o.dst_cr; r.dst_cstride = o.dst_cstride;
+        if (r.ycc_out && o.dst_memspace == IPG_MEM_HOST && o.dst_w > 0 && o.dst_h > 0) {
+            const int cw = (o.dst_w + 1) / 2, ch = (o.dst_h + 1) / 2;
+            if (!c->pinned.contains(o.dst, (size_t)o.dst_stride * (size_t)(o.dst_h - 1) + (size_t)o.dst_w) ||
+                !c->pinned.contains(o.dst_cb, (size_t)o.dst_cstride * (size_t)(ch - 1) + (size_t)cw) ||
+                !c->pinned.contains(o.dst_cr, (size_t)o.dst_cstride * (size_t)(ch - 1) + (size_t)cw))
+                return fail(IPG_ERR_INVALID, "YCbCr destination planes must lie in ipg_alloc_pinned (or device) memory");
+        }
         if (o.kind == IPG_OP_WATERMARK && (o.flags & IPG_OPF_WATERMARK_PATCH_ONLY) && src->layout == IPG_LAYOUT_RGBA8 && o.dst_w > 0 && o.dst_h > 0) {
             r.patch_only = true; // the union of the non-empty glyph rectangles (what freetype's DrawMask calls can touch)
             int bx0 = INT32_MAX, by0 = INT32_MAX, bx1 = INT32_MIN, by1 = INT32_MIN;
@@ -1307,7 +1365,7 @@ static int submit_impl(Ctx *c, int dev_index, const ipg_image_desc *src, const i
         }
     }
     for (auto &r : t->ops) {
-        if (r.dst_mem != IPG_MEM_HOST || r.dw <= 0 || r.dh <= 0) continue;
+        if (r.dst_mem != IPG_MEM_HOST || r.dw <= 0 || r.dh <= 0 || r.ycc_out) continue;
         size_t span = (size_t)r.dst_stride * (size_t)(r.dh - 1) + (size_t)r.dw * 4;
         if (c->pinned.contains(r.dst, span)) continue;
         if (r.patch_only && (r.bx1 <= r.bx0 || r.by1 <= r.by0)) continue; // nothing will be written

@@ -9,6 +9,7 @@ namespace ipg {
 enum Layout : int32_t {
     L_RGBA8 = 0, L_NRGBA8 = 1, L_GRAY8 = 2,
     L_YCBCR444 = 3, L_YCBCR422 = 4, L_YCBCR420 = 5, L_YCBCR440 = 6,
+    L_RGBA64 = 7, L_NRGBA64 = 8, L_GRAY16 = 9,
 };
 
 struct SrcView {
@@ -235,6 +236,16 @@ struct PatchJob {
     int32_t pad[2];
 };
 struct BlendItem { int32_t wm; int32_t tile_x, tile_y; }; // 32x8 px of a watermark's glyph box
+// RGBA8 result -> planar YCbCr 4:2:0 exactly as Go's image/jpeg writer derives it (k_rgba_to_ycbcr420)
+struct YccJob {
+    const uint8_t *rgba;
+    int32_t rgba_pitch;
+    int32_t w, h;
+    uint8_t *y, *cb, *cr;
+    int32_t y_pitch, c_pitch;
+    int32_t pad[2];
+};
+struct YccItem { int32_t job; int32_t tile_x, tile_y; int32_t pad; }; // 256 x 16 pixels
 enum { WM_ROWS = 8 };
 
 } // namespace ipg

@@ -44,6 +44,10 @@ __device__ __forceinline__ size_t chroma_index(int layout, int s1, int x, int y)
     }
 }
 
+__device__ __forceinline__ uint32_t be16(const uint8_t *p) { return ((uint32_t)__ldg(p) << 8) | (uint32_t)__ldg(p + 1); }
+// Gray and YCbCr sources carry the literal constant 1.0 in the alpha lane of x/image's pass 1 (scaleX_Gray, scaleX_YCbCr*)
+__device__ __forceinline__ bool layout_const_alpha(int layout) { return layout >= L_GRAY8 && layout <= L_YCBCR440; }
+
 // 16-bit premultiplied sample as the reference's pass 1 sees source pixel (x,y).
 // Returns true when the alpha lane is the literal constant 1.0 (Gray, YCbCr).
 __device__ __forceinline__ bool sample16(const SrcView &s, int x, int y, uint32_t p[4])
@@ -66,6 +70,24 @@ __device__ __forceinline__ bool sample16(const SrcView &s, int x, int y, uint32_
         uint32_t v = (uint32_t)__ldg(s.p0 + (size_t)y * s.s0 + x) * 0x101u;
         p[0] = p[1] = p[2] = v; p[3] = 0xffffu;
         return true;
+    }
+    // 16-bit types (x/image's generic / RGBA64Image path: RGBA64At per tap, alpha accumulated like a colour channel);
+    // Pix is big-endian
+    case L_RGBA64: {
+        const uint8_t *q = s.p0 + (size_t)y * s.s0 + (size_t)x * 8;
+        p[0] = be16(q); p[1] = be16(q + 2); p[2] = be16(q + 4); p[3] = be16(q + 6);
+        return false;
+    }
+    case L_NRGBA64: { // color.NRGBA64.RGBA(): c = C * A / 0xffff in uint32
+        const uint8_t *q = s.p0 + (size_t)y * s.s0 + (size_t)x * 8;
+        const uint32_t a = be16(q + 6);
+        p[0] = be16(q) * a / 0xffffu; p[1] = be16(q + 2) * a / 0xffffu; p[2] = be16(q + 4) * a / 0xffffu; p[3] = a;
+        return false;
+    }
+    case L_GRAY16: {
+        const uint32_t v = be16(s.p0 + (size_t)y * s.s0 + (size_t)x * 2);
+        p[0] = p[1] = p[2] = v; p[3] = 0xffffu;
+        return false;
     }
     default: {
         size_t ci = chroma_index(s.layout, s.s1, x, y);
@@ -247,7 +269,7 @@ __device__ __forceinline__ void fix_row_rgba(const uint32_t *q, const double *w,
 
 __device__ __forceinline__ void exact_pixel_thread(const FixHdr &h)
 {
-    const bool const_alpha = h.src.layout >= L_GRAY8 && !h.two_stage;
+    const bool const_alpha = layout_const_alpha(h.src.layout) && !h.two_stage;
     double pr = 0, pg = 0, pb = 0, pa = 0;
     if (h.src.layout == L_RGBA8 && h.nx <= FIX_TMLP) {
         // the resize case: FIX_TROWS rows x nx taps requested together (every load of the pixel is 2-4 round
@@ -377,7 +399,7 @@ __device__ void exact_pixel_warp(const ExactJob *__restrict__ jobs, const FixHdr
         __syncwarp();
         return;
     }
-    const bool const_alpha = h.src.layout >= L_GRAY8 && !h.two_stage; // Gray / YCbCr: alpha is the literal 1.0
+    const bool const_alpha = layout_const_alpha(h.src.layout) && !h.two_stage; // Gray / YCbCr: alpha is the literal 1.0
     for (int k = lane; k < nx; k += 32) S.wx[k] = __ldg(h.wx + k);
     for (int j = lane; j < ny; j += 32) S.wy[j] = __ldg(h.wy + j);
     // staging index: lanes walk (row, tap) with the tap count rounded up to a power of two (no division)
@@ -571,6 +593,11 @@ __device__ __forceinline__ uint32_t draw_src_px(const SrcView &s, int x, int y)
         uint32_t v = __ldg(s.p0 + (size_t)y * s.s0 + x);
         return v * 0x010101u | 0xff000000u;
     }
+    case L_RGBA64: case L_NRGBA64: case L_GRAY16: { // no fast path in image/draw: drawRGBA's generic loop, uint8(At().RGBA() >> 8)
+        uint32_t p[4];
+        sample16(s, x, y, p);
+        return (p[0] >> 8) | ((p[1] >> 8) << 8) | ((p[2] >> 8) << 16) | ((p[3] >> 8) << 24);
+    }
     default: {
         size_t ci = chroma_index(s.layout, s.s1, x, y);
         int yy1 = (int)__ldg(s.p0 + (size_t)y * s.s0 + x) * 0x10101;
@@ -606,10 +633,10 @@ k_watermark(const WmJob *__restrict__ jobs, const WmItem *__restrict__ items)
     const int W = s.w;
     const int y1 = min(it.row0 + WM_ROWS, s.h);
     const int layout = s.layout;
-    const bool ycc = layout >= L_YCBCR444;
+    const bool ycc = layout >= L_YCBCR444 && layout <= L_YCBCR440;
     const bool sub_x = layout == L_YCBCR422 || layout == L_YCBCR420;
     const bool dst_vec = ((J.wm.dst_stride | (int)(size_t)J.wm.dst) & 15) == 0;
-    bool vec = dst_vec;
+    bool vec = dst_vec && layout <= L_YCBCR440; // the 16-bit types take the per-pixel expression
     if (layout == L_RGBA8 || layout == L_NRGBA8) vec = vec && (((size_t)s.p0 | (size_t)s.s0) & 15) == 0;
     else vec = vec && (((size_t)s.p0 | (size_t)s.s0) & 7) == 0;
     if (ycc) vec = vec && (((size_t)s.p1 | (size_t)s.p2 | (size_t)s.s1 | (size_t)s.s2) & (sub_x ? 3 : 7)) == 0;
@@ -681,6 +708,72 @@ k_blend(const WatermarkD *__restrict__ wms, const BlendItem *__restrict__ items)
     const uint32_t d = *p;
     const uint32_t o = glyph_over_px(d, x, y, wm);
     if (o != d) *p = o;
+}
+
+// ---------------------------------------------------------------------------------
+// k_rgba_to_ycbcr420: the colour conversion and chroma down-sampling Go's image/jpeg writer applies to an *image.RGBA
+// before its DCT (Go 1.24 image/jpeg/writer.go rgbaToYCbCr + scale; image/color/ycbcr.go RGBToYCbCr), so that the host
+// can hand jpeg.Encode a 4:2:0 *image.YCbCr and get the bytes it would have produced from the RGBA result.
+//   per pixel  yy = (19595 R + 38470 G + 7471 B + 1<<15) >> 16
+//              cb = -11056 R - 21712 G + 32768 B + 257<<15;  cb = cb fits 24 bits ? cb >> 16 : (cb < 0 ? 0 : 255)   (same for cr)
+//   per 2 x 2  c = (c00 + c01 + c10 + c11 + 2) >> 2, coordinates past the last column / row clamped (the writer replicates
+//              the edge pixel inside its 16 x 16 blocks; with clamped reads a 4:2:0 image reproduces exactly that)
+// A thread converts 2 rows x 8 pixels: 16 luma bytes and 4 + 4 chroma bytes.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void rgb_to_ycbcr(uint32_t q, int &yy, int &cb, int &cr)
+{
+    const int r = (int)(q & 0xff), g = (int)((q >> 8) & 0xff), b = (int)((q >> 16) & 0xff);
+    yy = (19595 * r + 38470 * g + 7471 * b + (1 << 15)) >> 16;
+    int c = -11056 * r - 21712 * g + 32768 * b + (257 << 15);
+    cb = (((uint32_t)c & 0xff000000u) == 0 ? c >> 16 : ~(c >> 31)) & 0xff;
+    c = 32768 * r - 27440 * g - 5328 * b + (257 << 15);
+    cr = (((uint32_t)c & 0xff000000u) == 0 ? c >> 16 : ~(c >> 31)) & 0xff;
+}
+
+__global__ void __launch_bounds__(256)
+k_rgba_to_ycbcr420(const YccJob *__restrict__ jobs, const YccItem *__restrict__ items)
+{
+    const YccItem it = items[blockIdx.x];
+    const YccJob &J = jobs[it.job];
+    const int bx = it.tile_x * 32 + (threadIdx.x & 31), by = it.tile_y * 8 + (threadIdx.x >> 5); // 8-pixel, 2-row block
+    const int x0 = bx * 8, y0 = by * 2;
+    if (x0 >= J.w || y0 >= J.h) return;
+    uint32_t yv[2][2] = {{0u, 0u}, {0u, 0u}}; // 8 luma bytes per row, packed
+    int sb[4] = {0, 0, 0, 0}, sr[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t *row = (const uint32_t *)(J.rgba + (size_t)min(y0 + j, J.h - 1) * J.rgba_pitch);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            int yy, cb, cr;
+            rgb_to_ycbcr(__ldg(row + min(x0 + i, J.w - 1)), yy, cb, cr);
+            yv[j][i >> 2] |= (uint32_t)yy << (8 * (i & 3));
+            sb[i >> 1] += cb;
+            sr[i >> 1] += cr;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        if (y0 + j >= J.h) break;
+        uint8_t *d = J.y + (size_t)(y0 + j) * J.y_pitch + x0;
+        if (x0 + 8 <= J.w && (((size_t)d) & 7) == 0) *(uint2 *)d = make_uint2(yv[j][0], yv[j][1]);
+        else
+            for (int i = 0; i < 8 && x0 + i < J.w; i++) d[i] = (uint8_t)(yv[j][i >> 2] >> (8 * (i & 3)));
+    }
+    const int cw = (J.w + 1) >> 1, cx0 = bx * 4;
+    uint32_t pb = 0, pr = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        pb |= (uint32_t)((sb[c] + 2) >> 2) << (8 * c);
+        pr |= (uint32_t)((sr[c] + 2) >> 2) << (8 * c);
+    }
+    uint8_t *db = J.cb + (size_t)by * J.c_pitch + cx0, *dr = J.cr + (size_t)by * J.c_pitch + cx0;
+    if (cx0 + 4 <= cw && ((((size_t)db) | ((size_t)dr)) & 3) == 0) {
+        *(uint32_t *)db = pb;
+        *(uint32_t *)dr = pr;
+    } else {
+        for (int c = 0; c < 4 && cx0 + c < cw; c++) { db[c] = (uint8_t)(pb >> (8 * c)); dr[c] = (uint8_t)(pr >> (8 * c)); }
+    }
 }
 
 // The same blend for the patch-only watermark of an *image.RGBA source: the box pixels come from the SOURCE (draw.Draw
@@ -2076,6 +2169,13 @@ cudaError_t launch_blend(const WatermarkD *wms, const BlendItem *items, int n_it
 {
     if (n_items <= 0) return cudaSuccess;
     k_blend<<<n_items, 256, 0, st>>>(wms, items);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rgba_to_ycbcr420(const YccJob *jobs, const YccItem *items, int n_items, cudaStream_t st)
+{
+    if (n_items <= 0) return cudaSuccess;
+    k_rgba_to_ycbcr420<<<n_items, 256, 0, st>>>(jobs, items);
     return cudaGetLastError();
 }
 

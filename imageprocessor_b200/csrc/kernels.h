@@ -30,6 +30,9 @@ cudaError_t launch_exact_fix(const ExactJob *jobs, int n_jobs, FixList fix, cuda
 // Ordered glyph blend in place over each watermark's glyph box (after the copy/convert).
 cudaError_t launch_blend(const WatermarkD *wms, const BlendItem *items, int n_items, cudaStream_t st);
 
+// RGBA8 results -> planar YCbCr 4:2:0 as Go's image/jpeg writer derives it (one CTA per 256 x 16 pixels).
+cudaError_t launch_rgba_to_ycbcr420(const YccJob *jobs, const YccItem *items, int n_items, cudaStream_t st);
+
 // Patch-only watermark of RGBA8 sources: source box -> blend -> patch buffer / caller frame.
 cudaError_t launch_blend_patch(const PatchJob *jobs, const BlendItem *items, int n_items, cudaStream_t st);
 

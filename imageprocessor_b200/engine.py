@@ -43,6 +43,14 @@ class Image:
         return Image(L.GRAY8, a.shape[1], a.shape[0], (a,), True)
 
     @staticmethod
+    def from_deep(a: np.ndarray, layout: int) -> "Image":
+        """*image.RGBA64 / *image.NRGBA64 from (h, w, 4) uint16 values or *image.Gray16 from (h, w): stored big-endian,
+        8 (2) bytes per pixel, as Go's Pix holds them."""
+        assert a.dtype == np.uint16 and ((a.ndim == 3 and a.shape[2] == 4) or a.ndim == 2)
+        be = np.ascontiguousarray(a.astype(">u2"))
+        return Image(layout, a.shape[1], a.shape[0], (be.view(np.uint8).reshape(a.shape[0], -1),), layout == L.GRAY16)
+
+    @staticmethod
     def from_ycbcr(y: np.ndarray, cb: np.ndarray, cr: np.ndarray, layout: int) -> "Image":
         planes = tuple(p if p.strides[1] == 1 else np.ascontiguousarray(p) for p in (y, cb, cr))
         return Image(layout, y.shape[1], y.shape[0], planes, True)

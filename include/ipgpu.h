@@ -70,6 +70,12 @@ typedef enum {
     IPG_LAYOUT_YCBCR422 = 4,
     IPG_LAYOUT_YCBCR420 = 5,
     IPG_LAYOUT_YCBCR440 = 6,
+    /* 16-bit types (a 16-bit PNG): Pix as Go stores it, big-endian uint16 per channel.  x/image reaches them
+     * through its generic / RGBA64Image path (RGBA64At per tap).  Low volume: vertical upscales run in the fp32 k_direct,
+     * everything else whole-image in float64 (k_exact_tiles); the watermark frame is uint8(At().RGBA() >> 8). */
+    IPG_LAYOUT_RGBA64 = 7,   /* *image.RGBA64 (alpha-premultiplied), 8 bytes per pixel */
+    IPG_LAYOUT_NRGBA64 = 8,  /* *image.NRGBA64 (straight alpha), 8 bytes per pixel     */
+    IPG_LAYOUT_GRAY16 = 9,   /* *image.Gray16, 2 bytes per pixel                        */
 } ipg_layout;
 
 typedef enum {
@@ -151,7 +157,20 @@ typedef struct {
     void *dst;
     int32_t dst_stride;
     int32_t dst_memspace;     /* ipg_memspace                                 */
-    int32_t flags;            /* ipg_op_flags (new in ABI 2: sizeof(ipg_op) 64 -> 72) */
+    int32_t flags;            /* ipg_op_flags (new in ABI 2)                  */
+    /* Destination layout (new in ABI 2).  0 / IPG_LAYOUT_RGBA8: the *image.RGBA the reference's raster functions return.
+     * IPG_LAYOUT_YCBCR420 (opt-in, SURVEY 8f-3 first step, for results that will be JPEG-encoded): the result is handed
+     * back as the planar 4:2:0 image Go's image/jpeg writer derives from that *image.RGBA before its DCT -- per pixel the
+     * integer color.RGBToYCbCr of the (premultiplied) R, G, B bytes, chroma averaged 2 x 2 as writer.go's scale() does,
+     * (sum + 2) >> 2, with the edge pixel replicated for odd sizes -- so jpeg.Encode of
+     *   &image.YCbCr{Y, Cb, Cr, YStride, CStride, SubsampleRatio420, Rect(0, 0, w, h)}
+     * emits the same bytes as jpeg.Encode of the RGBA result, and 1.5 instead of 4 bytes per pixel cross PCIe.
+     * dst / dst_stride are then the Y plane (dst_w bytes per row), dst_cb / dst_cr / dst_cstride the (dst_w+1)/2 x
+     * (dst_h+1)/2 chroma planes.  Host planes must lie in ipg_alloc_pinned memory (no staging path for this layout). */
+    int32_t dst_layout;
+    void *dst_cb, *dst_cr;
+    int32_t dst_cstride;
+    int32_t reserved1;
 } ipg_op;
 
 typedef enum {

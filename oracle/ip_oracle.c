@@ -257,8 +257,29 @@ static inline uint32_t ftou(double f)
 
 /* image.{RGBA,NRGBA}.Opaque(): full scan of the image's own bounds; YCbCr and
  * Gray are always opaque.  x/image draw/scale.go: op Over -> Src if opaque. */
+static inline uint32_t be16(const uint8_t *p) { return ((uint32_t)p[0] << 8) | (uint32_t)p[1]; }
+
 static int image_opaque(const ipo_image *m)
 {
+    if (m->layout == IPO_RGBA64 || m->layout == IPO_NRGBA64) { /* image.RGBA64.Opaque(): every alpha == 0xffff */
+        for (int y = 0; y < m->height; y++) {
+            const uint8_t *row = m->plane[0] + (size_t)y * (size_t)m->stride[0];
+            for (int x = 0; x < m->width; x++)
+                if (be16(row + 8 * x + 6) != 0xffff) return 0;
+        }
+        return 1;
+    }
+    if (m->layout == IPO_PALETTED_RGBA || m->layout == IPO_PALETTED_NRGBA) {
+        /* image.Paletted.Opaque(): the palette entries actually used by the pixels must all have alpha 0xffff */
+        int present[256] = {0};
+        for (int y = 0; y < m->height; y++) {
+            const uint8_t *row = m->plane[0] + (size_t)y * (size_t)m->stride[0];
+            for (int x = 0; x < m->width; x++) present[row[x]] = 1;
+        }
+        for (int i = 0; i < 256; i++)
+            if (present[i] && m->plane[1][4 * i + 3] != 0xff) return 0;
+        return 1;
+    }
     if (m->layout == IPO_RGBA8 || m->layout == IPO_NRGBA8) {
         for (int y = 0; y < m->height; y++) {
             const uint8_t *row = m->plane[0] + (size_t)y * (size_t)m->stride[0];
@@ -334,6 +355,36 @@ static inline int sample16(const ipo_image *s, int x, int y, uint32_t p[4])
         p[0] = p[1] = p[2] = v; p[3] = 0xffff;
         return 1;
     }
+    /* ---- generic path: src.At(x, y).RGBA() / RGBA64At (x/image draw/impl.go scaleX_Image, scaleX_RGBA64Image);
+     * alpha is data here, accumulated like the colour channels ---- */
+    case IPO_RGBA64: { /* color.RGBA64.RGBA(): the stored values */
+        const uint8_t *q = s->plane[0] + (size_t)y * (size_t)s->stride[0] + (size_t)x * 8;
+        p[0] = be16(q); p[1] = be16(q + 2); p[2] = be16(q + 4); p[3] = be16(q + 6);
+        return 0;
+    }
+    case IPO_NRGBA64: { /* color.NRGBA64.RGBA(): c = C * A / 0xffff (uint32) */
+        const uint8_t *q = s->plane[0] + (size_t)y * (size_t)s->stride[0] + (size_t)x * 8;
+        uint32_t a = be16(q + 6);
+        p[0] = be16(q) * a / 0xffff; p[1] = be16(q + 2) * a / 0xffff; p[2] = be16(q + 4) * a / 0xffff; p[3] = a;
+        return 0;
+    }
+    case IPO_GRAY16: { /* color.Gray16.RGBA(): (y, y, y, 0xffff) */
+        uint32_t v = be16(s->plane[0] + (size_t)y * (size_t)s->stride[0] + (size_t)x * 2);
+        p[0] = p[1] = p[2] = v; p[3] = 0xffff;
+        return 0;
+    }
+    case IPO_PALETTED_RGBA: { /* Palette[i].(color.RGBA).RGBA(): c |= c << 8 */
+        const uint8_t *e = s->plane[1] + 4 * (size_t)s->plane[0][(size_t)y * (size_t)s->stride[0] + (size_t)x];
+        p[0] = (uint32_t)e[0] * 0x101; p[1] = (uint32_t)e[1] * 0x101; p[2] = (uint32_t)e[2] * 0x101; p[3] = (uint32_t)e[3] * 0x101;
+        return 0;
+    }
+    case IPO_PALETTED_NRGBA: { /* Palette[i].(color.NRGBA).RGBA(): c |= c << 8; c *= A; c /= 0xff; a |= a << 8 */
+        const uint8_t *e = s->plane[1] + 4 * (size_t)s->plane[0][(size_t)y * (size_t)s->stride[0] + (size_t)x];
+        uint32_t a = e[3];
+        p[0] = (uint32_t)e[0] * 0x101 * a / 0xff; p[1] = (uint32_t)e[1] * 0x101 * a / 0xff; p[2] = (uint32_t)e[2] * 0x101 * a / 0xff;
+        p[3] = a * 0x101;
+        return 0;
+    }
     default: {
         size_t ci = chroma_index(s, x, y);
         int yy = s->plane[0][(size_t)y * (size_t)s->stride[0] + (size_t)x];
@@ -346,9 +397,10 @@ static inline int sample16(const ipo_image *s, int x, int y, uint32_t p[4])
 
 static int layout_ok(const ipo_image *s)
 {
-    return s && s->layout >= IPO_RGBA8 && s->layout <= IPO_YCBCR440 && s->width > 0 &&
-           s->height > 0 && s->plane[0] &&
-           (s->layout < IPO_YCBCR444 || (s->plane[1] && s->plane[2]));
+    if (!s || s->layout < IPO_RGBA8 || s->layout > IPO_PALETTED_NRGBA || s->width <= 0 || s->height <= 0 || !s->plane[0]) return 0;
+    if (s->layout >= IPO_YCBCR444 && s->layout <= IPO_YCBCR440) return s->plane[1] && s->plane[2];
+    if (s->layout >= IPO_PALETTED_RGBA) return s->plane[1] != NULL;
+    return 1;
 }
 
 int ipo_scale_bilinear(const ipo_image *src, int sx0, int sy0, int sw, int sh,
@@ -383,7 +435,7 @@ int ipo_scale_bilinear(const ipo_image *src, int sx0, int sy0, int sw, int sh,
                 pb += (double)p[2] * w;
                 if (!const_alpha) pa += (double)p[3] * w;
             }
-            if (src->layout >= IPO_GRAY8) const_alpha = 1;
+            if (src->layout >= IPO_GRAY8 && src->layout <= IPO_YCBCR440) const_alpha = 1;
             tmp[t][0] = pr * s.inv_total_ffff;
             tmp[t][1] = pg * s.inv_total_ffff;
             tmp[t][2] = pb * s.inv_total_ffff;
@@ -495,6 +547,15 @@ int ipo_draw_src(const ipo_image *src, uint8_t *dst, int dst_stride)
             for (int x = 0; x < src->width; x++, d += 4) {
                 d[0] = d[1] = d[2] = q[x];
                 d[3] = 0xff;
+            }
+            break;
+        }
+        case IPO_RGBA64: case IPO_NRGBA64: case IPO_GRAY16: case IPO_PALETTED_RGBA: case IPO_PALETTED_NRGBA: {
+            /* no fast path in image/draw: drawRGBA's generic loop, d = uint8(At(x, y).RGBA() >> 8) per channel */
+            for (int x = 0; x < src->width; x++, d += 4) {
+                uint32_t p[4];
+                sample16(src, x, y, p);
+                d[0] = (uint8_t)(p[0] >> 8); d[1] = (uint8_t)(p[1] >> 8); d[2] = (uint8_t)(p[2] >> 8); d[3] = (uint8_t)(p[3] >> 8);
             }
             break;
         }

@@ -44,12 +44,21 @@ enum {
     IPO_YCBCR422 = 4,
     IPO_YCBCR420 = 5,
     IPO_YCBCR440 = 6,
+    /* 16-bit types (a 16-bit PNG): Pix holds big-endian uint16 per channel, as Go stores them.  x/image reaches them
+     * through the generic / RGBA64Image path: src.RGBA64At(x, y) (== At(x, y).RGBA()) per tap, alpha accumulated. */
+    IPO_RGBA64   = 7, /* *image.RGBA64: alpha-premultiplied, 8 B/px         */
+    IPO_NRGBA64  = 8, /* *image.NRGBA64: straight alpha, 8 B/px             */
+    IPO_GRAY16   = 9, /* *image.Gray16, 2 B/px                              */
+    /* *image.Paletted (GIF, paletted PNG): plane[0] = 1 index byte per pixel, plane[1] = 256 x 4 palette bytes.
+     * Oracle-only: the product takes the palette expanded on the host (RGBA8 / NRGBA8), which tests prove identical. */
+    IPO_PALETTED_RGBA  = 10, /* palette entries are color.RGBA (GIF; PNG without tRNS) */
+    IPO_PALETTED_NRGBA = 11, /* palette entries are color.NRGBA (PNG with a tRNS chunk) */
 };
 
 typedef struct {
     int32_t layout;
     int32_t width, height;
-    const uint8_t *plane[3]; /* RGBA/NRGBA/Gray: plane[0]; YCbCr: Y, Cb, Cr   */
+    const uint8_t *plane[3]; /* RGBA/NRGBA/Gray(16): plane[0]; YCbCr: Y, Cb, Cr; Paletted: indices, palette */
     int32_t stride[3];       /* bytes per row of each plane                   */
 } ipo_image;
 

@@ -20,7 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libip_oracle.so")
 
-RGBA8, NRGBA8, GRAY8, YCBCR444, YCBCR422, YCBCR420, YCBCR440 = range(7)
+RGBA8, NRGBA8, GRAY8, YCBCR444, YCBCR422, YCBCR420, YCBCR440, RGBA64, NRGBA64, GRAY16, PALETTED_RGBA, PALETTED_NRGBA = range(12)
 OP_OVER, OP_SRC = 0, 1
 
 
@@ -93,6 +93,21 @@ class Raster:
     def gray(a: np.ndarray) -> "Raster":
         a = np.ascontiguousarray(a, dtype=np.uint8)
         return Raster(GRAY8, a.shape[1], a.shape[0], (a,))
+
+    @staticmethod
+    def deep(a: np.ndarray, layout: int) -> "Raster":
+        """*image.RGBA64 / *image.NRGBA64 (h, w, 4) or *image.Gray16 (h, w) from uint16 values: stored big-endian as Go does."""
+        be = np.ascontiguousarray(a.astype(">u2"))
+        h, w = a.shape[:2]
+        return Raster(layout, w, h, (be.view(np.uint8).reshape(h, -1),))
+
+    @staticmethod
+    def paletted(indices: np.ndarray, palette_rgba: np.ndarray, nrgba_entries: bool) -> "Raster":
+        """*image.Paletted: index bytes + up to 256 palette entries (color.RGBA, or color.NRGBA when nrgba_entries)."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint8)
+        pal = np.zeros((256, 4), np.uint8)
+        pal[:len(palette_rgba)] = palette_rgba
+        return Raster(PALETTED_NRGBA if nrgba_entries else PALETTED_RGBA, idx.shape[1], idx.shape[0], (idx, pal.reshape(1, -1)))
 
     @staticmethod
     def ycbcr(y: np.ndarray, cb: np.ndarray, cr: np.ndarray, layout: int) -> "Raster":
