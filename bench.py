@@ -407,7 +407,7 @@ class HostRing:
     soon as its previous ticket is done, so the K steps run as one stream of submissions (a worker does not drain its
     pipeline between batches).  Every submission, copy and completion lies inside the caller's timed region."""
 
-    def __init__(self, lib, L, eng, geo, host_images, n_slots, n_dev, inplace=False):
+    def __init__(self, lib, L, eng, geo, host_images, n_slots, n_dev, inplace=False, ycbcr=False):
         """inplace: the watermark is requested with IPG_OPF_WATERMARK_PATCH_ONLY into the SOURCE buffer itself (an
         *image.RGBA's watermark differs from its source only inside the glyph box): no separate result frame exists."""
         self.lib, self.L, self.ctx, self.geo, self.n_dev, self.inplace = lib, L, eng._ctx, geo, n_dev, inplace
@@ -415,10 +415,21 @@ class HostRing:
         for s in range(n_slots * n_dev):
             p_in = eng.alloc_pinned(geo.src_bytes)
             p_in.array[:] = host_images[s % len(host_images)].reshape(-1)
+            self.descs.append(geo.desc(p_in.ptr, L.MEM_HOST))
+            if ycbcr:   # every result as the planar 4:2:0 image Go's jpeg writer derives (ipg_op.dst_layout): 1.5 B per pixel back
+                dims = [(geo.nw, geo.nh), (THUMB, THUMB), (geo.w, geo.h)]
+                planes = [[eng.alloc_pinned(dw * dh), eng.alloc_pinned(((dw + 1) // 2) * ((dh + 1) // 2)),
+                           eng.alloc_pinned(((dw + 1) // 2) * ((dh + 1) // 2))] for (dw, dh) in dims]
+                self.pins += [p_in] + [b for pl in planes for b in pl]
+                ops = geo.ops(planes[0][0].ptr, planes[1][0].ptr, planes[2][0].ptr, L.MEM_HOST)
+                for k, (dw, dh) in enumerate(dims):
+                    ops[k].dst_layout, ops[k].dst_stride = L.YCBCR420, dw
+                    ops[k].dst_cb, ops[k].dst_cr, ops[k].dst_cstride = planes[k][1].ptr, planes[k][2].ptr, (dw + 1) // 2
+                self.ops.append(ops)
+                continue
             p_r, p_t = eng.alloc_pinned(geo.r_bytes), eng.alloc_pinned(geo.t_bytes)
             p_w = p_in if inplace else eng.alloc_pinned(geo.src_bytes)
             self.pins += [p_in, p_r, p_t] + ([] if inplace else [p_w])
-            self.descs.append(geo.desc(p_in.ptr, L.MEM_HOST))
             self.ops.append(geo.ops(p_r.ptr, p_t.ptr, p_w.ptr, L.MEM_HOST, L.OPF_WATERMARK_PATCH_ONLY if inplace else 0))
         self.n_slots = n_slots * n_dev
         self.tid = (C.c_uint64 * self.n_slots)()
@@ -450,6 +461,18 @@ class HostRing:
         return bool(np.array_equal(self.pins[1].array.reshape(g.nh, g.nw, 4), er) and
                     np.array_equal(self.pins[2].array.reshape(THUMB, THUMB, 4), et) and
                     np.array_equal(self.pins[0].array.reshape(g.h, g.w, 4), ew))
+
+    def verify_ycbcr_slot0(self, O):
+        """Slot 0's nine planes against the oracle's restatement of Go's jpeg writer applied to the oracle's RGBA results."""
+        g = self.geo
+        a = self.pins[0].array.reshape(g.h, g.w, 4)
+        ok, k = True, 1
+        for rgba in g.oracle_outputs(O, a):
+            h, w = rgba.shape[:2]
+            for want in O.rgba_to_ycbcr420(rgba):
+                ok = ok and bool(np.array_equal(self.pins[k].array.reshape(want.shape), want))
+                k += 1
+        return ok
 
     def verify_slot0(self, O):
         g = self.geo
@@ -941,6 +964,32 @@ def main():
             "h2d_GBps_aggregate": sum_over_ranks(st3["bytes_h2d"]) / wall3 / 1e9,
             "d2h_GBps_aggregate": sum_over_ranks(st3["bytes_d2h"]) / wall3 / 1e9,
             "verified_first_submission_all_outputs": ok_inplace,
+        }
+        # ---- and with every result handed back as the planar YCbCr 4:2:0 image Go's jpeg writer derives from it (opt-in
+        # ipg_op.dst_layout for JPEG targets): H2D unchanged, D2H 1.5 instead of 4 bytes per result pixel
+        ring = HostRing(lib, L, eng, geo, host_imgs, min(n_slots, 32), n_dev, ycbcr=True)
+        ring.run(n_img * n_dev)
+        barrier()
+        eng.reset_stats()
+        t0 = time.perf_counter()
+        ring.run(args.steps * n_img * n_dev)
+        eng.flush()
+        barrier()
+        wall4 = max_over_ranks(time.perf_counter() - t0)
+        st4 = eng.stats()
+        ok_ycc = None
+        if rank == 0 and not args.no_verify:
+            from oracle import oracle as O
+            ok_ycc = ring.verify_ycbcr_slot0(O)
+        ring.free()
+        e2e["results_as_ycbcr420"] = {
+            "value": total_images / wall4, "unit": "images/s",
+            "what": "ipg_op.dst_layout = YCBCR420 on all three ops: results come back as the 4:2:0 planes Go's image/jpeg writer "
+                    "computes from the RGBA result before its DCT (jpeg.Encode of that *image.YCbCr emits the same bytes)",
+            "h2d_bytes_per_step": int(st4["bytes_h2d"] / args.steps), "d2h_bytes_per_step": int(st4["bytes_d2h"] / args.steps),
+            "h2d_GBps_aggregate": sum_over_ranks(st4["bytes_h2d"]) / wall4 / 1e9,
+            "d2h_GBps_aggregate": sum_over_ranks(st4["bytes_d2h"]) / wall4 / 1e9,
+            "verified_slot0_all_planes": ok_ycc,
         }
     clocks = sampler.stop()   # sampled across the device-resident AND the end-to-end leg
 

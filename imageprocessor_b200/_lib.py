@@ -54,7 +54,9 @@ class Op(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dst_w", C.c_int32), ("dst_h", C.c_int32),
                 ("rect_x", C.c_int32), ("rect_y", C.c_int32), ("rect_w", C.c_int32), ("rect_h", C.c_int32),
                 ("color", C.c_uint8 * 4), ("n_glyphs", C.c_int32), ("glyphs", C.POINTER(Glyph)),
-                ("dst", C.c_void_p), ("dst_stride", C.c_int32), ("dst_memspace", C.c_int32), ("flags", C.c_int32)]
+                ("dst", C.c_void_p), ("dst_stride", C.c_int32), ("dst_memspace", C.c_int32), ("flags", C.c_int32),
+                ("dst_layout", C.c_int32), ("dst_cb", C.c_void_p), ("dst_cr", C.c_void_p), ("dst_cstride", C.c_int32),
+                ("reserved1", C.c_int32)]
 
 
 class Stats(C.Structure):

@@ -99,6 +99,9 @@ class OpSpec:
     dst: Optional[np.ndarray] = None      # host destination (h, w, 4) uint8; allocated if None
     dst_device: Optional[Tuple[int, int]] = None  # (device pointer, stride) instead of dst
     flags: int = 0                        # ipg_op_flags (OPF_WATERMARK_PATCH_ONLY: dst must already hold the source pixels)
+    # planar YCbCr 4:2:0 result (ipg_op.dst_layout, for results that will be JPEG-encoded): three PinnedBuffer-backed
+    # uint8 planes (Y h x w, Cb and Cr (h+1)//2 x (w+1)//2); the RGBA destination fields are then unused
+    dst_ycbcr420: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None
 
     @staticmethod
     def resize(dw: int, dh: int, **kw) -> "OpSpec":
@@ -232,7 +235,16 @@ class Engine:
                 keep.append(ga)
                 c.n_glyphs = len(o.glyphs)
                 c.glyphs = ga
-            if o.dst_device is not None:
+            if o.dst_ycbcr420 is not None:
+                yp, cbp, crp = o.dst_ycbcr420
+                assert yp.shape == (o.dst_h, o.dst_w) and cbp.shape == crp.shape == ((o.dst_h + 1) // 2, (o.dst_w + 1) // 2)
+                c.dst_layout = L.YCBCR420
+                c.dst, c.dst_stride = yp.ctypes.data, yp.strides[0]
+                c.dst_cb, c.dst_cr, c.dst_cstride = cbp.ctypes.data, crp.ctypes.data, cbp.strides[0]
+                assert crp.strides[0] == cbp.strides[0]
+                c.dst_memspace = L.MEM_HOST
+                outs.append(o.dst_ycbcr420)
+            elif o.dst_device is not None:
                 c.dst, c.dst_stride = o.dst_device
                 c.dst_memspace = L.MEM_DEVICE
                 outs.append(None)

@@ -612,6 +612,54 @@ int ipo_watermark(const ipo_image *src, uint8_t *dst, int dst_stride, const uint
 }
 
 /* ------------------------------------------------------------------------ */
+/* What Go's image/jpeg writer derives from an *image.RGBA before its DCT     */
+/* (Go 1.24 image/jpeg/writer.go rgbaToYCbCr + scale, image/color/ycbcr.go    */
+/* RGBToYCbCr), written as the 4:2:0 image that yields the same blocks.       */
+/* ------------------------------------------------------------------------ */
+static void go_rgb_to_ycbcr(uint8_t r, uint8_t g, uint8_t b, uint8_t *yy, uint8_t *cb, uint8_t *cr)
+{
+    int32_t r1 = r, g1 = g, b1 = b;
+    int32_t y = (19595 * r1 + 38470 * g1 + 7471 * b1 + (1 << 15)) >> 16;
+    int32_t c = -11056 * r1 - 21712 * g1 + 32768 * b1 + (257 << 15);
+    if (((uint32_t)c & 0xff000000u) == 0) c >>= 16; else c = ~(c >> 31);
+    int32_t d = 32768 * r1 - 27440 * g1 - 5328 * b1 + (257 << 15);
+    if (((uint32_t)d & 0xff000000u) == 0) d >>= 16; else d = ~(d >> 31);
+    *yy = (uint8_t)y; *cb = (uint8_t)c; *cr = (uint8_t)d;
+}
+
+/* y: w x h; cb, cr: ((w+1)/2) x ((h+1)/2), tight strides.  Chroma of a 2x2 group = (sum + 2) >> 2 with coordinates
+ * clamped to the image (the writer replicates the last column / row inside its 16x16 blocks). */
+int ipo_rgba_to_ycbcr420(const uint8_t *rgba, int stride, int w, int h, uint8_t *y, uint8_t *cb, uint8_t *cr)
+{
+    if (!rgba || !y || !cb || !cr || w <= 0 || h <= 0) return -1;
+    const int cw = (w + 1) / 2, ch = (h + 1) / 2;
+    for (int j = 0; j < h; j++)
+        for (int i = 0; i < w; i++) {
+            const uint8_t *p = rgba + (size_t)j * (size_t)stride + (size_t)i * 4;
+            uint8_t a, b, c;
+            go_rgb_to_ycbcr(p[0], p[1], p[2], &a, &b, &c);
+            y[(size_t)j * (size_t)w + (size_t)i] = a;
+        }
+    for (int cj = 0; cj < ch; cj++)
+        for (int ci = 0; ci < cw; ci++) {
+            int sb = 0, sr = 0;
+            for (int dj = 0; dj < 2; dj++)
+                for (int di = 0; di < 2; di++) {
+                    int yy = 2 * cj + dj, xx = 2 * ci + di;
+                    if (yy > h - 1) yy = h - 1;
+                    if (xx > w - 1) xx = w - 1;
+                    const uint8_t *p = rgba + (size_t)yy * (size_t)stride + (size_t)xx * 4;
+                    uint8_t a, b, c;
+                    go_rgb_to_ycbcr(p[0], p[1], p[2], &a, &b, &c);
+                    sb += b; sr += c;
+                }
+            cb[(size_t)cj * (size_t)cw + (size_t)ci] = (uint8_t)((sb + 2) >> 2);
+            cr[(size_t)cj * (size_t)cw + (size_t)ci] = (uint8_t)((sr + 2) >> 2);
+        }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
 /* CPU baseline driver (bench.py only)                                       */
 /* ------------------------------------------------------------------------ */
 

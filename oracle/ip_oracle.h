@@ -120,6 +120,10 @@ void ipo_glyph_over(uint8_t *dst, int dst_stride, const uint8_t rgba[4],
 int ipo_watermark(const ipo_image *src, uint8_t *dst, int dst_stride,
                   const uint8_t rgba[4], const ipo_glyph *glyphs, int n_glyphs);
 
+/* ---- what image/jpeg's writer makes of an *image.RGBA (Go 1.24 writer.go rgbaToYCbCr + scale; color.RGBToYCbCr) ---- */
+/* Planar 4:2:0 whose jpeg.Encode output equals that of the RGBA image: y is w x h, cb / cr ((w+1)/2) x ((h+1)/2). */
+int ipo_rgba_to_ycbcr420(const uint8_t *rgba, int stride, int w, int h, uint8_t *y, uint8_t *cb, uint8_t *cr);
+
 /* ---- CPU baseline driver (bench.py only) -------------------------------- */
 /* Runs resize(+thumb crop)(+watermark) over n images of identical geometry on
  * n_threads pthreads, one image per thread at a time, fresh temp buffers per

@@ -67,6 +67,7 @@ def lib():
         L.ipo_glyph_over.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.POINTER(_Glyph)]
         L.ipo_watermark.argtypes = [C.POINTER(_Image), C.c_void_p, C.c_int, C.POINTER(C.c_uint8),
                                     C.POINTER(_Glyph), C.c_int]
+        L.ipo_rgba_to_ycbcr420.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ipo_bench_batch.argtypes = [C.POINTER(_Image), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(_Glyph),
                                       C.c_int, C.POINTER(C.c_uint64)]
@@ -215,6 +216,17 @@ def draw_src(src: Raster) -> np.ndarray:
     if lib().ipo_draw_src(C.byref(im), dst.ctypes.data, dst.strides[0]):
         raise ValueError("ipo_draw_src failed")
     return dst
+
+
+def rgba_to_ycbcr420(rgba: np.ndarray):
+    """(Y, Cb, Cr) planes Go's image/jpeg writer derives from an *image.RGBA (writer.go rgbaToYCbCr + scale)."""
+    a = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = a.shape[:2]
+    y = np.empty((h, w), np.uint8)
+    cb, cr = np.empty(((h + 1) // 2, (w + 1) // 2), np.uint8), np.empty(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    if lib().ipo_rgba_to_ycbcr420(a.ctypes.data, a.strides[0], w, h, y.ctypes.data, cb.ctypes.data, cr.ctypes.data):
+        raise ValueError("ipo_rgba_to_ycbcr420 failed")
+    return y, cb, cr
 
 
 @dataclass

@@ -44,7 +44,7 @@ def test_no_cpu_fallback_without_a_device():
 def test_struct_layouts_match_the_header():
     # sizes the C side was compiled with (x86-64 SysV): guards the ctypes mirrors in _lib.py
     assert C.sizeof(L.Config) == 40 and C.sizeof(L.ImageDesc) == 56 and C.sizeof(L.Glyph) == 48
-    assert C.sizeof(L.Op) == 72 and C.sizeof(L.Stats) == 144
+    assert C.sizeof(L.Op) == 96 and C.sizeof(L.Stats) == 144
 
 
 def test_geometry_helpers_follow_the_reference():

@@ -428,3 +428,58 @@ def test_watermark_frame_of_converting_layouts_fused_and_standalone(engines, ora
         if with_resize:
             assert np.array_equal(out[1], oracle.resize_image(R, nw, nh)), f"{kind} resize {w}x{h}"
             assert np.array_equal(out[2], oracle.crop_and_resize(R, 64)), f"{kind} thumb {w}x{h}"
+
+
+def _pinned_planes(e, w, h):
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    bufs = [e.alloc_pinned(w * h), e.alloc_pinned(cw * ch), e.alloc_pinned(cw * ch)]
+    planes = (bufs[0].array.reshape(h, w), bufs[1].array.reshape(ch, cw), bufs[2].array.reshape(ch, cw))
+    for p in planes:
+        p[...] = 0x5A
+    return bufs, planes
+
+
+@pytest.mark.parametrize("w,h", [(1600, 1200), (1001, 777), (33, 17), (4000, 3000)])
+def test_ycbcr420_destination_is_what_gos_jpeg_writer_derives(engines, oracle, w, h):
+    """ipg_op.dst_layout = YCBCR420 (first step): each result comes back as the planar 4:2:0 image Go's
+    image/jpeg writer computes from the *image.RGBA result before its DCT (integer RGBToYCbCr, 2x2 chroma mean with
+    (sum + 2) >> 2, edge replication) -- compared here with the oracle's restatement applied to the oracle's RGBA result,
+    for all three ops, odd sizes included, RGBA and planar sources."""
+    e = engines(ip.PRECISION_EXACT, lane_device_bytes=2 << 30)
+    col = (255, 255, 255, 127)
+    for src_kind in ("rgba", "420"):
+        if src_kind == "rgba":
+            a = rgba_random(w, h, 91, "premul")
+            img, R = ip.Image.from_rgba(a), oracle.Raster.rgba(a)
+        else:
+            y, cb, cr = _ycbcr(oracle, w, h, ip.YCBCR420, 92)
+            img, R = ip.Image.from_ycbcr(y, cb, cr, ip.YCBCR420), oracle.Raster.ycbcr(y, cb, cr, oracle.YCBCR420)
+        nw, nh = ip.keep_aspect_dims(w, h, 1024, 768)
+        cx, cy, cs = ip.crop_square(w, h)
+        gl = synthetic_glyphs(w, h, 5)
+        keep = []
+        specs = []
+        for (dw, dh) in ((nw, nh), (64, 64), (w, h)):
+            bufs, planes = _pinned_planes(e, dw, dh)
+            keep += bufs
+            specs.append(planes)
+        out = e.run(img, [ip.OpSpec.resize(nw, nh, dst_ycbcr420=specs[0]),
+                          ip.OpSpec.thumb_crop((cx, cy, cs, cs), 64, dst_ycbcr420=specs[1]),
+                          ip.OpSpec.watermark(w, h, col, [ip.GlyphMask(*g) for g in gl], dst_ycbcr420=specs[2])])
+        want = [oracle.resize_image(R, nw, nh), oracle.crop_and_resize(R, 64), oracle.watermark(R, col, [oracle.Glyph(*g) for g in gl])]
+        for k, (planes, rgba) in enumerate(zip(out, want)):
+            ey, ecb, ecr = oracle.rgba_to_ycbcr420(rgba)
+            assert np.array_equal(planes[0], ey), f"{src_kind} op {k}: Y"
+            assert np.array_equal(planes[1], ecb) and np.array_equal(planes[2], ecr), f"{src_kind} op {k}: chroma"
+        for b in keep:
+            b.free()
+
+
+def test_ycbcr420_destination_argument_errors(engines):
+    from imageprocessor_b200 import _lib as L
+    e = engines(ip.PRECISION_EXACT)
+    a = rgba_random(64, 48, 1)
+    y, cb, cr = np.empty((48, 64), np.uint8), np.empty((24, 32), np.uint8), np.empty((24, 32), np.uint8)
+    with pytest.raises(ip.IpgError) as ei:      # pageable planes: there is no staging path for this layout
+        e.run(ip.Image.from_rgba(a), [ip.OpSpec.resize(64, 48, dst_ycbcr420=(y, cb, cr))])
+    assert ei.value.code == L.ERR_INVALID and "pinned" in str(ei.value)
