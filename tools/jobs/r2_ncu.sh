@@ -18,9 +18,14 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 KREGEX='k_stream<\(int\)1, \(bool\)1, \(int\)4>' KSKIP=1 bash tools/jobs/ncu_one.sh rtw lean_$TAG | tail -2
 IPG_MERGE_LEAN=0 KREGEX='k_stream<\(int\)1, \(bool\)0, \(int\)2>' KSKIP=1 bash tools/jobs/ncu_one.sh rt thumb_$TAG | tail -2
 python tools/profile_step.py --images 64 --steps 1 --ops rt --w 1920 --h 1080 --max-batch 64 > gpurun_out/plain_mid_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:k_stream" -s 1 -c 1 -o gpurun_out/prof_mid_$TAG -f \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:k_stream<\(int\)1, \(bool\)0, \(int\)4>' -s 1 -c 1 -o gpurun_out/prof_mid_$TAG -f \
     python tools/profile_step.py --images 64 --steps 1 --ops rt --w 1920 --h 1080 --max-batch 64 > gpurun_out/ncu_mid_$TAG.log 2>&1; echo mid rc=$?; cat gpurun_out/plain_mid_$TAG.log
-python tools/profile_step.py --images 16 --steps 1 --ops rtw --layout ycbcr420 > gpurun_out/plain_planar_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:k_stream_planar" -s 2 -c 1 -o gpurun_out/prof_planar_$TAG -f \
-    python tools/profile_step.py --images 16 --steps 1 --ops rtw --layout ycbcr420 > gpurun_out/ncu_planar_$TAG.log 2>&1; echo planar rc=$?; cat gpurun_out/plain_planar_$TAG.log
+for lay in ycbcr420 nrgba; do
+python tools/profile_step.py --images 16 --steps 1 --ops rtw --layout $lay > gpurun_out/plain_${lay}_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:k_stream_planar" -s 1 -c 1 -o gpurun_out/prof_${lay}_$TAG -f \
+    python tools/profile_step.py --images 16 --steps 1 --ops rtw --layout $lay > gpurun_out/ncu_${lay}_$TAG.log 2>&1; echo $lay rc=$?; cat gpurun_out/plain_${lay}_$TAG.log
+done
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:k_exact_fix" -s 2 -c 2 -o gpurun_out/prof_fix_$TAG -f \
+    python tools/profile_step.py --images 16 --steps 1 --ops rtw > gpurun_out/ncu_fix_$TAG.log 2>&1; echo fix rc=$?
+python tools/size_sweep.py --out gpurun_out/size_sweep_$TAG.json > gpurun_out/size_sweep_$TAG.log 2>&1; echo sweep rc=$?
 ls -la gpurun_out/*_$TAG.ncu-rep

@@ -27,7 +27,7 @@ for r in ours:
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(out, f"{rnd}_launch_summary.txt"), "w") as f:
     f.write(f"ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised launches: compare SHARES)\n")
-    f.write(f"command: python bench.py --steps 1 --warmup 3 --images 64 --no-e2e --no-cpu-baseline --no-verify\n\n")
+    f.write(f"command: python bench.py --steps 1 --warmup 3 --images 64 --no-e2e --no-cpu-baseline --no-verify --no-configs (tools/jobs/r2_ncu.sh)\n\n")
     for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
         f.write(f"{k:32s} launches {n:4d}  total {t/1e3:10.1f} us  share {100*t/tot:5.1f}%\n")
 
