@@ -124,6 +124,16 @@ int ipo_watermark(const ipo_image *src, uint8_t *dst, int dst_stride,
 /* Planar 4:2:0 whose jpeg.Encode output equals that of the RGBA image: y is w x h, cb / cr ((w+1)/2) x ((h+1)/2). */
 int ipo_rgba_to_ycbcr420(const uint8_t *rgba, int stride, int w, int h, uint8_t *y, uint8_t *cb, uint8_t *cr);
 
+/* ---- Go 1.24 image/jpeg ENCODER (ip_jpeg_oracle.c): jpeg.Encode(w, m, &jpeg.Options{Quality: quality}) ------------- */
+/* The checker of the device-side JPEG writer (ipg_op.dst_layout = IPG_LAYOUT_JPEG).  Each returns the number of bytes
+ * of the complete file written to out, 0 for a bad argument, (size_t)-1 when cap is too small.
+ * m = *image.RGBA (what resizeImage / cropAndResize / addTextWatermark return; resize.go:78-91, watermark.go:66-79). */
+size_t ipo_jpeg_encode_rgba(const uint8_t *rgba, int stride, int w, int h, int quality, uint8_t *out, size_t cap);
+/* m = *image.YCbCr (layout IPO_YCBCR444..440): the writer's yCbCrToYCbCr path. */
+size_t ipo_jpeg_encode_ycbcr(const ipo_image *img, int quality, uint8_t *out, size_t cap);
+/* m = *image.Gray: one component, 8 x 8 MCUs. */
+size_t ipo_jpeg_encode_gray(const uint8_t *pix, int stride, int w, int h, int quality, uint8_t *out, size_t cap);
+
 /* ---- CPU baseline driver (bench.py only) -------------------------------- */
 /* Runs resize(+thumb crop)(+watermark) over n images of identical geometry on
  * n_threads pthreads, one image per thread at a time, fresh temp buffers per

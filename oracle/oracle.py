@@ -26,9 +26,9 @@ OP_OVER, OP_SRC = 0, 1
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
-    src = os.path.join(_HERE, "ip_oracle.c")
+    srcs = [os.path.join(_HERE, n) for n in ("ip_oracle.c", "ip_jpeg_oracle.c", "ip_oracle.h")]
     if (force or not os.path.exists(_LIB_PATH)
-            or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)):
+            or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs)):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libip_oracle.so"])
     return _LIB_PATH
 
@@ -68,6 +68,12 @@ def lib():
         L.ipo_watermark.argtypes = [C.POINTER(_Image), C.c_void_p, C.c_int, C.POINTER(C.c_uint8),
                                     C.POINTER(_Glyph), C.c_int]
         L.ipo_rgba_to_ycbcr420.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ipo_jpeg_encode_rgba.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+        L.ipo_jpeg_encode_rgba.restype = C.c_size_t
+        L.ipo_jpeg_encode_ycbcr.argtypes = [C.POINTER(_Image), C.c_int, C.c_void_p, C.c_size_t]
+        L.ipo_jpeg_encode_ycbcr.restype = C.c_size_t
+        L.ipo_jpeg_encode_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+        L.ipo_jpeg_encode_gray.restype = C.c_size_t
         L.ipo_bench_batch.argtypes = [C.POINTER(_Image), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(_Glyph),
                                       C.c_int, C.POINTER(C.c_uint64)]
@@ -227,6 +233,35 @@ def rgba_to_ycbcr420(rgba: np.ndarray):
     if lib().ipo_rgba_to_ycbcr420(a.ctypes.data, a.strides[0], w, h, y.ctypes.data, cb.ctypes.data, cr.ctypes.data):
         raise ValueError("ipo_rgba_to_ycbcr420 failed")
     return y, cb, cr
+
+
+def _jpeg_result(n: int, out: np.ndarray) -> bytes:
+    if n == 0 or n == C.c_size_t(-1).value:
+        raise ValueError("jpeg oracle: bad argument or output buffer too small")
+    return out[:n].tobytes()
+
+
+def jpeg_encode_rgba(rgba: np.ndarray, quality: int = 85) -> bytes:
+    """jpeg.Encode(w, m *image.RGBA, &jpeg.Options{Quality: quality}) -- the whole file (Go 1.24 writer.go)."""
+    a = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = a.shape[:2]
+    out = np.empty(w * h * 8 + 4096, np.uint8)
+    return _jpeg_result(lib().ipo_jpeg_encode_rgba(a.ctypes.data, a.strides[0], w, h, quality, out.ctypes.data, out.size), out)
+
+
+def jpeg_encode_ycbcr(src: "Raster", quality: int = 85) -> bytes:
+    """jpeg.Encode of an *image.YCbCr (any subsample ratio): the writer's yCbCrToYCbCr path."""
+    im = src.c()
+    out = np.empty(src.width * src.height * 8 + 4096, np.uint8)
+    return _jpeg_result(lib().ipo_jpeg_encode_ycbcr(C.byref(im), quality, out.ctypes.data, out.size), out)
+
+
+def jpeg_encode_gray(gray: np.ndarray, quality: int = 85) -> bytes:
+    """jpeg.Encode of an *image.Gray."""
+    a = np.ascontiguousarray(gray, dtype=np.uint8)
+    h, w = a.shape
+    out = np.empty(w * h * 8 + 4096, np.uint8)
+    return _jpeg_result(lib().ipo_jpeg_encode_gray(a.ctypes.data, a.strides[0], w, h, quality, out.ctypes.data, out.size), out)
 
 
 @dataclass
