@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("IPG_LIB_PATH") or os.path.join(_HERE, "libipgpu.so") 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_TIMEOUT, ERR_NO_DEVICE, ERR_SHUTDOWN, ERR_INTERNAL = 0, -1, -2, -3, -4, -5, -6, -7
 # ipg_layout
 RGBA8, NRGBA8, GRAY8, YCBCR444, YCBCR422, YCBCR420, YCBCR440, RGBA64, NRGBA64, GRAY16 = range(10)
+JPEG = 16  # destination only: the result as the JPEG file Go's jpeg.Encode would write, encoded on the device
 # ipg_memspace
 MEM_HOST, MEM_DEVICE = 0, 1
 # ipg_precision
@@ -56,7 +57,7 @@ class Op(C.Structure):
                 ("color", C.c_uint8 * 4), ("n_glyphs", C.c_int32), ("glyphs", C.POINTER(Glyph)),
                 ("dst", C.c_void_p), ("dst_stride", C.c_int32), ("dst_memspace", C.c_int32), ("flags", C.c_int32),
                 ("dst_layout", C.c_int32), ("dst_cb", C.c_void_p), ("dst_cr", C.c_void_p), ("dst_cstride", C.c_int32),
-                ("reserved1", C.c_int32)]
+                ("jpeg_quality", C.c_int32), ("dst_capacity", C.c_uint64), ("dst_len", C.POINTER(C.c_uint64))]
 
 
 class Stats(C.Structure):

@@ -34,6 +34,8 @@
 #include "../../include/ipgpu.h"
 #include "ipg_device.h"
 #include "kernels.h"
+#define IPG_WITH_CUDA_RUNTIME 1
+#include "jpeg.h"
 #include "plan.h"
 
 namespace ipg {
@@ -209,6 +211,10 @@ struct OpRec {
     bool ycc_out = false;     // dst_layout == IPG_LAYOUT_YCBCR420: dst / dst_cb / dst_cr are the planes, dev_out an arena RGBA temp
     void *dst_cb = nullptr, *dst_cr = nullptr;
     int dst_cstride = 0;
+    bool jpeg_out = false;    // dst_layout == IPG_LAYOUT_JPEG: dst is a byte buffer for the file, dev_out an arena RGBA temp
+    int jpeg_quality = 85;
+    size_t dst_capacity = 0;
+    uint64_t *dst_len = nullptr;
     bool patch_only = false;  // IPG_OPF_WATERMARK_PATCH_ONLY on an RGBA8 source: only the glyph union box is produced
     int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0; // ... that box (empty: nothing to do)
     uint8_t *stage = nullptr; // staging for a non-pinned host dst (tight rows)
@@ -245,6 +251,10 @@ struct Batch {
     uint64_t exact_fallbacks = 0;
     uint64_t fast_jobs = 0;
     bool has_fix = false;
+    // results encoded on the device (IPG_LAYOUT_JPEG): the file length is known only after the kernels ran, so the
+    // completer reads it (result words, copied with the batch's read-backs) and issues the exact-size copy itself
+    struct JpegOut { const uint8_t *dev; void *host; size_t cap; uint64_t *len_out; int ticket; int result; bool to_host; };
+    std::vector<JpegOut> jpegs;
 };
 
 struct Lane {
@@ -262,6 +272,8 @@ struct Lane {
     uint8_t *param_host = nullptr; // pinned
     size_t param_cap = 0;
     uint32_t *fix_count_host = nullptr; // pinned copy of FixList::count (4 words)
+    uint32_t *jpeg_result_host = nullptr; // pinned copy of the batch's JpegJob::result words (4 per job)
+    cudaEvent_t done2 = nullptr;    // after the completer's exact-size JPEG copies (download stream 2)
     bool busy = false;
 };
 
@@ -283,6 +295,7 @@ struct Device {
     // with a copy stream per lane the driver maps several lanes onto one copy engine and an
     // H2D queues behind another lane's D2H; two dedicated streams always run both directions.
     cudaStream_t up = nullptr, down = nullptr;
+    cudaStream_t down2 = nullptr;   // the completer's exact-size copies of device-encoded JPEG files
     cudaEvent_t epoch = nullptr;
     // Compute sections of consecutive batches (different lanes) are ordered by events owned by the earlier batch's lane:
     // the next batch's stream kernels wait for `last_stream` (end of the previous batch's k_stream section) and its
@@ -410,6 +423,23 @@ static AxisExact pack_axis(Blob &b, const AxisPlan &p)
     return a;
 }
 
+// Device-encoded JPEG result (IPG_LAYOUT_JPEG): buffer sizes of one job.  The scan can never exceed 1248 bytes per MCU
+// (6 blocks x [20 DC bits + 63 x (16-bit code + 10 value bits)]); the caller's capacity bounds it further.
+enum { kJpegMaxJobs = 4096 };
+struct JpegSizes { int mcu_w, n_mcu; size_t scan_cap, out_cap, total; };
+static JpegSizes jpeg_sizes(int w, int h, size_t dst_capacity, bool out_in_arena)
+{
+    JpegSizes z{};
+    z.mcu_w = (w + 15) / 16;
+    z.n_mcu = z.mcu_w * ((h + 15) / 16);
+    const size_t cap = std::min<size_t>(dst_capacity, 0xffff0000u);
+    z.scan_cap = align_up(std::max<size_t>(std::min((size_t)z.n_mcu * 1248 + 64, cap), 512), JPEG_CHUNK);
+    z.out_cap = std::min(cap, (size_t)JPEG_HDR_MAX + 2 * z.scan_cap + 2);
+    z.total = (size_t)z.n_mcu * (6 * 64 * 2 + 6 * 4 + 4) + z.scan_cap + (z.scan_cap / JPEG_CHUNK + 1) * 4 +
+              (out_in_arena ? z.out_cap : 0) + 8 * 256;
+    return z;
+}
+
 static size_t ticket_device_bytes(const Ticket &t)
 {
     size_t n = 0;
@@ -427,6 +457,9 @@ static size_t ticket_device_bytes(const Ticket &t)
         else if (op.ycc_out) // the RGBA result in the arena, plus the three planes when they are read back to the host
             n += (align_up((size_t)std::max(op.dw, 0) * 4, 256) + 256) * (size_t)std::max(op.dh, 0) +
                  2 * (align_up((size_t)std::max(op.dw, 0), 256) + 256) * (size_t)std::max(op.dh, 0) + 1024;
+        else if (op.jpeg_out) // the RGBA result in the arena, coefficients, the scan in both forms
+            n += (align_up((size_t)std::max(op.dw, 0) * 4, 256) + 256) * (size_t)std::max(op.dh, 0) +
+                 jpeg_sizes(std::max(op.dw, 1), std::max(op.dh, 1), op.dst_capacity, op.dst_mem == IPG_MEM_HOST).total + sizeof(JpegTables) + JPEG_HDR_MAX + 1024;
         else if (op.dst_mem == IPG_MEM_HOST) n += (align_up((size_t)std::max(op.dw, 0) * 4, 256) + 256) * (size_t)std::max(op.dh, 0) + 256;
         for (auto &g : op.glyphs) n += align_up(g.mask.size(), 256) + 256;
         n += 4096;
@@ -468,6 +501,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     std::vector<BlendItem> bitems;
     std::vector<YccJob> yjobs;        // results handed back as planar YCbCr 4:2:0 (dst_layout)
     std::vector<YccItem> yitems;
+    std::vector<std::pair<OpRec *, int>> jpeg_ops; // results encoded on the device (dst_layout JPEG), with their ticket index
     std::vector<DirectJob> djobs;     // small-support targets (vertical upscales, mild downscales): k_direct
     std::vector<DirectItem> ditems;
     std::vector<PatchJob> pjobs;      // patch-only watermarks (RGBA8 sources): glyph box alone
@@ -485,8 +519,10 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     const size_t cta_target = c.band_cta_target; // CTAs a batch should at least give (IPG_BAND_CTAS; default 1400 = ~2.4 waves of 4 x 148)
     int bands_hint = (int)std::min<size_t>(32, std::max<size_t>(1, (cta_target + est_ctas - 1) / std::max<size_t>(est_ctas, 1)));
 
+    int ticket_index = -1;
     for (auto &tp : B.tickets) {
         Ticket &t = *tp;
+        ticket_index++;
         // ---- source view on the device
         SrcView sv{};
         sv.w = t.src.width;
@@ -577,6 +613,12 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 yjobs.push_back(yj);
                 for (int ty = 0; ty < (op.dh + 15) / 16; ty++)
                     for (int tx = 0; tx < (op.dw + 255) / 256; tx++) yitems.push_back(YccItem{ji, tx, ty, 0});
+            } else if (op.jpeg_out) { // RGBA result in the arena; the writer's buffers are carved once every ticket is placed
+                const size_t pitch = align_up((size_t)op.dw * 4, 256);
+                op.dev_out = arena.take(pitch * (size_t)op.dh);
+                if (!op.dev_out) throw std::runtime_error("device arena exhausted (destination)");
+                op.dev_pitch = pitch;
+                jpeg_ops.push_back({&op, ticket_index});
             } else if (op.dst_mem == IPG_MEM_DEVICE) {
                 op.dev_out = (uint8_t *)op.dst;
                 op.dev_pitch = (size_t)op.dst_stride;
@@ -921,6 +963,54 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
         }
     }
 
+    // ---- device-side JPEG writer (dst_layout JPEG): one job per result
+    std::vector<JpegJob> jjobs;
+    std::vector<JpegDctItem> jdct;
+    std::vector<JpegEmitItem> jemit;
+    std::vector<JpegStuffItem> jstuff;
+    uint32_t *d_jresults = nullptr;
+    if (!jpeg_ops.empty()) {
+        if (jpeg_ops.size() > kJpegMaxJobs) throw std::runtime_error("too many JPEG results in one batch; lower max_batch");
+        d_jresults = (uint32_t *)arena.take(16 * jpeg_ops.size(), 256);
+        if (!d_jresults) throw std::runtime_error("device arena exhausted (JPEG results)");
+        std::map<int, const JpegTables *> tabs; // per quality
+        for (auto &jo : jpeg_ops) {
+            OpRec &op = *jo.first;
+            const bool to_host = op.dst_mem == IPG_MEM_HOST;
+            const JpegSizes z = jpeg_sizes(op.dw, op.dh, op.dst_capacity, to_host);
+            JpegJob j{};
+            j.rgba = op.dev_out; j.rgba_pitch = (int)op.dev_pitch; j.w = op.dw; j.h = op.dh;
+            j.mcu_w = z.mcu_w; j.n_mcu = z.n_mcu;
+            auto tb = tabs.find(op.jpeg_quality);
+            if (tb == tabs.end()) {
+                JpegTables T;
+                jpeg_build_tables(op.jpeg_quality, &T);
+                tb = tabs.emplace(op.jpeg_quality, blob.dptr<const JpegTables>(blob.put(&T, sizeof T, 16))).first;
+            }
+            j.tab = tb->second;
+            uint8_t hdr[JPEG_HDR_MAX];
+            j.hdr_len = (uint32_t)jpeg_build_header(op.jpeg_quality, op.dw, op.dh, hdr);
+            j.hdr = blob.dptr<const uint8_t>(blob.put(hdr, j.hdr_len, 16));
+            j.coef = (int16_t *)arena.take((size_t)z.n_mcu * 6 * 64 * 2);
+            j.side = (uint32_t *)arena.take((size_t)z.n_mcu * 6 * 4);
+            j.mcu_off = (uint32_t *)arena.take((size_t)z.n_mcu * 4);
+            j.words = (uint32_t *)arena.take(z.scan_cap);
+            j.cap_bytes = (uint32_t)z.scan_cap;
+            j.chunk_off = (uint32_t *)arena.take((z.scan_cap / JPEG_CHUNK + 1) * 4);
+            j.out = to_host ? arena.take(z.out_cap) : (uint8_t *)op.dst;
+            j.out_cap = (uint32_t)z.out_cap;
+            if (!j.coef || !j.side || !j.mcu_off || !j.words || !j.chunk_off || !j.out) throw std::runtime_error("device arena exhausted (JPEG writer)");
+            const int ji = (int)jjobs.size();
+            j.result = d_jresults + 4 * ji;
+            jjobs.push_back(j);
+            for (int m = 0; m < z.n_mcu; m += JPEG_DCT_MCUS) jdct.push_back(JpegDctItem{ji, m});
+            for (int m = 0; m < z.n_mcu; m += JPEG_EMIT_THREADS) jemit.push_back(JpegEmitItem{ji, m});
+            const int parts = (int)std::min<size_t>(JPEG_STUFF_PARTS, (z.scan_cap / JPEG_CHUNK + 7) / 8); // ... of the strided loops; the stride is fixed
+            for (int q = 0; q < std::max(parts, 1); q++) jstuff.push_back(JpegStuffItem{ji, q});
+            B.jpegs.push_back(Batch::JpegOut{j.out, op.dst, (size_t)op.dst_capacity, op.dst_len, jo.second, ji, to_host});
+        }
+    }
+
     // ---- fix list (EXACT mode)
     FixList fix{nullptr, nullptr, 0};
     if (!fixjobs.empty()) {
@@ -958,6 +1048,10 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     const DirectItem *d_ditems = blob.dptr<const DirectItem>(blob.put(ditems.data(), ditems.size() * sizeof(DirectItem), 16));
     const PatchJob *d_pjobs = blob.dptr<const PatchJob>(blob.put(pjobs.data(), pjobs.size() * sizeof(PatchJob), 16));
     const BlendItem *d_pbitems = blob.dptr<const BlendItem>(blob.put(pbitems.data(), pbitems.size() * sizeof(BlendItem), 16));
+    const JpegJob *d_jjobs = blob.dptr<const JpegJob>(blob.put(jjobs.data(), jjobs.size() * sizeof(JpegJob), 16));
+    const JpegDctItem *d_jdct = blob.dptr<const JpegDctItem>(blob.put(jdct.data(), jdct.size() * sizeof(JpegDctItem), 16));
+    const JpegEmitItem *d_jemit = blob.dptr<const JpegEmitItem>(blob.put(jemit.data(), jemit.size() * sizeof(JpegEmitItem), 16));
+    const JpegStuffItem *d_jstuff = blob.dptr<const JpegStuffItem>(blob.put(jstuff.data(), jstuff.size() * sizeof(JpegStuffItem), 16));
     if (blob.overflow) throw std::runtime_error("parameter blob overflow (batch too heterogeneous); lower max_batch");
     IPG_CU(cudaMemcpyAsync(blob_dev, L.param_host, blob.off, cudaMemcpyHostToDevice, up));
     B.h2d += blob.off;
@@ -1054,6 +1148,11 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
         IPG_CU(launch_rgba_to_ycbcr420(d_yjobs, d_yitems, (int)yitems.size(), st));
         B.n_kernels++;
     }
+    if (!jjobs.empty()) { // ... and the JPEG writer over the results that leave as files
+        IPG_CU(cudaMemsetAsync(d_jresults, 0, 16 * jjobs.size(), st));
+        IPG_CU(launch_jpeg(d_jjobs, (int)jjobs.size(), d_jdct, (int)jdct.size(), d_jemit, (int)jemit.size(), d_jstuff, (int)jstuff.size(), st));
+        B.n_kernels += JPEG_LAUNCHES;
+    }
     IPG_CU(cudaEventRecord(L.ev[3], st));
     d.prev_compute = d.last_compute;
     d.last_compute = L.ev[3];
@@ -1062,6 +1161,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     IPG_CU(cudaStreamWaitEvent(down, L.ev[3], 0));
     IPG_CU(cudaEventRecord(L.dl_begin, down));
     if (B.has_fix) IPG_CU(cudaMemcpyAsync(L.fix_count_host, fix.count, 16, cudaMemcpyDeviceToHost, down));
+    if (!jjobs.empty()) IPG_CU(cudaMemcpyAsync(L.jpeg_result_host, d_jresults, 16 * jjobs.size(), cudaMemcpyDeviceToHost, down));
     for (auto &r : readbacks) {
         if (r.pitch == r.hstride)
             IPG_CU(cudaMemcpyAsync(r.host, r.dev, r.pitch * (size_t)(r.rows - 1) + r.row_bytes, cudaMemcpyDeviceToHost, down));
@@ -1159,6 +1259,7 @@ static void completer_main(Ctx *c, Device *d)
         Lane &L = d->lanes[B->lane];
         int status = IPG_OK;
         std::string err;
+        std::vector<int> tstatus; // per ticket, when only some of a batch's tickets fail (a JPEG file that does not fit)
         if (B->failed) {
             cudaDeviceSynchronize();
             status = IPG_ERR_CUDA;
@@ -1200,6 +1301,39 @@ static void completer_main(Ctx *c, Device *d)
                 d->b_first = std::min(d->b_first, (double)t0);
                 d->b_last = std::max(d->b_last, (double)t3);
             }
+            // Files encoded on the device: their lengths arrived with the read-backs; fetch exactly those bytes now.
+            // Only this thread uses the second download stream, so waiting on it waits for nothing else.
+            if (status == IPG_OK && !B->jpegs.empty()) {
+                tstatus.assign(B->tickets.size(), IPG_OK);
+                bool any_copy = false;
+                for (auto &j : B->jpegs) {
+                    const uint32_t *r = L.jpeg_result_host + 4 * j.result;
+                    if (r[1] != 0 || r[0] == 0 || r[0] > j.cap) {
+                        tstatus[(size_t)j.ticket] = IPG_ERR_NOMEM;
+                        if (j.len_out) *j.len_out = 0;
+                        continue;
+                    }
+                    if (j.len_out) *j.len_out = r[0];
+                    if (!j.to_host) continue;
+                    cudaError_t ce = cudaMemcpyAsync(j.host, j.dev, r[0], cudaMemcpyDeviceToHost, d->down2);
+                    if (ce != cudaSuccess) { status = IPG_ERR_CUDA; err = cuda_msg("JPEG read-back", ce); break; }
+                    B->d2h += r[0];
+                    any_copy = true;
+                }
+                if (status == IPG_OK && any_copy) {
+                    cudaEventRecord(L.done2, d->down2);
+                    cudaError_t ce = cudaEventSynchronize(L.done2);
+                    if (ce != cudaSuccess) { status = IPG_ERR_CUDA; err = cuda_msg("JPEG read-back", ce); }
+                    else {
+                        float t4 = 0, dl = 0;
+                        cudaEventElapsedTime(&t4, d->epoch, L.done2);
+                        cudaEventElapsedTime(&dl, L.done, L.done2);
+                        std::lock_guard<std::mutex> lk(c->smu);
+                        d->b_last = std::max(d->b_last, (double)t4);
+                        c->s_d2h_ms += dl;
+                    }
+                }
+            }
             if (B->has_fix && status == IPG_OK) c->s_fix += L.fix_count_host[0];
             c->s_batches++;
             c->s_kernels += (uint64_t)B->n_kernels;
@@ -1208,7 +1342,11 @@ static void completer_main(Ctx *c, Device *d)
             c->s_fallback += B->exact_fallbacks;
             c->s_fast_jobs += B->fast_jobs;
         }
-        for (auto &t : B->tickets) finish_ticket(*c, *d, t, status, err);
+        for (size_t i = 0; i < B->tickets.size(); i++) {
+            if (status == IPG_OK && i < tstatus.size() && tstatus[i] != IPG_OK)
+                finish_ticket(*c, *d, B->tickets[i], tstatus[i], "the JPEG file does not fit dst_capacity (or the scan its device buffer)");
+            else finish_ticket(*c, *d, B->tickets[i], status, err);
+        }
         {
             std::lock_guard<std::mutex> lk(d->mu);
             L.busy = false;
@@ -1242,9 +1380,15 @@ static int validate(const ipg_image_desc *src, const ipg_op *ops, int n_ops)
         if (o.dst_w > 65536 || o.dst_h > 65536) return fail(IPG_ERR_INVALID, "destination too large");
         if (o.kind == IPG_OP_WATERMARK && (o.dst_w != src->width || o.dst_h != src->height))
             return fail(IPG_ERR_INVALID, "watermark destination must have the source size");
-        if (o.dst_layout != IPG_LAYOUT_RGBA8 && o.dst_layout != IPG_LAYOUT_YCBCR420)
-            return fail(IPG_ERR_INVALID, "destination layout must be RGBA8 or YCBCR420");
-        if (o.dst_layout == IPG_LAYOUT_YCBCR420 && o.dst_w > 0 && o.dst_h > 0) {
+        if (o.dst_layout != IPG_LAYOUT_RGBA8 && o.dst_layout != IPG_LAYOUT_YCBCR420 && o.dst_layout != IPG_LAYOUT_JPEG)
+            return fail(IPG_ERR_INVALID, "destination layout must be RGBA8, YCBCR420 or JPEG");
+        if (o.dst_layout == IPG_LAYOUT_JPEG) {
+            if (o.dst_w <= 0 || o.dst_h <= 0) return fail(IPG_ERR_INVALID, "a JPEG result needs a non-empty image");
+            if (o.dst_w >= 65536 || o.dst_h >= 65536) return fail(IPG_ERR_INVALID, "jpeg: image is too large to encode");
+            if (!o.dst || !o.dst_len) return fail(IPG_ERR_INVALID, "JPEG destination needs dst and dst_len");
+            if (o.dst_capacity < 1024) return fail(IPG_ERR_INVALID, "JPEG destination capacity below 1024 bytes");
+            if (o.flags & IPG_OPF_WATERMARK_PATCH_ONLY) return fail(IPG_ERR_INVALID, "a patch-only watermark has no JPEG form");
+        } else if (o.dst_layout == IPG_LAYOUT_YCBCR420 && o.dst_w > 0 && o.dst_h > 0) {
             if (!o.dst || !o.dst_cb || !o.dst_cr) return fail(IPG_ERR_INVALID, "destination plane pointer is null");
             if (o.dst_stride < o.dst_w || o.dst_cstride < (o.dst_w + 1) / 2) return fail(IPG_ERR_INVALID, "destination plane stride smaller than a row");
             if (o.flags & IPG_OPF_WATERMARK_PATCH_ONLY) return fail(IPG_ERR_INVALID, "a patch-only watermark has no YCbCr form");
@@ -1309,6 +1453,12 @@ static int submit_impl(Ctx *c, int dev_index, const ipg_image_desc *src, const i
         r.flags = o.flags;
         r.ycc_out = o.dst_layout == IPG_LAYOUT_YCBCR420;
         r.dst_cb = o.dst_cb; r.dst_cr = o.dst_cr; r.dst_cstride = o.dst_cstride;
+        r.jpeg_out = o.dst_layout == IPG_LAYOUT_JPEG;
+        if (r.jpeg_out) {
+            r.jpeg_quality = o.jpeg_quality == 0 ? 85 : std::min(100, std::max(1, (int)o.jpeg_quality));
+            r.dst_capacity = (size_t)o.dst_capacity;
+            r.dst_len = o.dst_len;
+        }
         if (r.ycc_out && o.dst_memspace == IPG_MEM_HOST && o.dst_w > 0 && o.dst_h > 0) {
             const int cw = (o.dst_w + 1) / 2, ch = (o.dst_h + 1) / 2;
             if (!c->pinned.contains(o.dst, (size_t)o.dst_stride * (size_t)(o.dst_h - 1) + (size_t)o.dst_w) ||
@@ -1365,7 +1515,7 @@ static int submit_impl(Ctx *c, int dev_index, const ipg_image_desc *src, const i
         }
     }
     for (auto &r : t->ops) {
-        if (r.dst_mem != IPG_MEM_HOST || r.dw <= 0 || r.dh <= 0 || r.ycc_out) continue;
+        if (r.dst_mem != IPG_MEM_HOST || r.dw <= 0 || r.dh <= 0 || r.ycc_out || r.jpeg_out) continue;
         size_t span = (size_t)r.dst_stride * (size_t)(r.dh - 1) + (size_t)r.dw * 4;
         if (c->pinned.contains(r.dst, span)) continue;
         if (r.patch_only && (r.bx1 <= r.bx0 || r.by1 <= r.by0)) continue; // nothing will be written
@@ -1482,6 +1632,8 @@ static void destroy_impl(Ctx *c)
             if (L.arena) cudaFree(L.arena);
             if (L.param_host) cudaFreeHost(L.param_host);
             if (L.fix_count_host) cudaFreeHost(L.fix_count_host);
+            if (L.jpeg_result_host) cudaFreeHost(L.jpeg_result_host);
+            if (L.done2) cudaEventDestroy(L.done2);
             if (L.st) cudaStreamDestroy(L.st);
             if (L.st2) cudaStreamDestroy(L.st2);
             if (L.fork) cudaEventDestroy(L.fork);
@@ -1489,6 +1641,7 @@ static void destroy_impl(Ctx *c)
         }
         if (d.up) { cudaStreamSynchronize(d.up); cudaStreamDestroy(d.up); }
         if (d.down) { cudaStreamSynchronize(d.down); cudaStreamDestroy(d.down); }
+        if (d.down2) { cudaStreamSynchronize(d.down2); cudaStreamDestroy(d.down2); }
         if (d.epoch) cudaEventDestroy(d.epoch);
         d.staging.destroy();
     }
@@ -1575,11 +1728,14 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
                 L.param_cap = param_cap;
                 IPG_CU(cudaHostAlloc((void **)&L.param_host, L.param_cap, cudaHostAllocPortable));
                 IPG_CU(cudaHostAlloc((void **)&L.fix_count_host, 64, cudaHostAllocPortable));
+                IPG_CU(cudaHostAlloc((void **)&L.jpeg_result_host, 16 * kJpegMaxJobs, cudaHostAllocPortable));
+                IPG_CU(cudaEventCreate(&L.done2));
             }
             if (!d->staging.init((size_t)k.lane_pinned_bytes * (size_t)k.lanes_per_device))
                 throw std::runtime_error("pinned staging allocation failed");
             IPG_CU(cudaStreamCreateWithFlags(&d->up, cudaStreamNonBlocking));
             IPG_CU(cudaStreamCreateWithFlags(&d->down, cudaStreamNonBlocking));
+            IPG_CU(cudaStreamCreateWithFlags(&d->down2, cudaStreamNonBlocking));
             IPG_CU(cudaEventCreate(&d->epoch));
             IPG_CU(cudaEventRecord(d->epoch, d->lanes[0].st));
             IPG_CU(cudaEventSynchronize(d->epoch));

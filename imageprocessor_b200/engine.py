@@ -102,6 +102,12 @@ class OpSpec:
     # planar YCbCr 4:2:0 result (ipg_op.dst_layout, for results that will be JPEG-encoded): three PinnedBuffer-backed
     # uint8 planes (Y h x w, Cb and Cr (h+1)//2 x (w+1)//2); the RGBA destination fields are then unused
     dst_ycbcr420: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None
+    # the result as a JPEG file encoded on the device (ipg_op.dst_layout = IPG_LAYOUT_JPEG): quality as jpeg.Options.Quality
+    # (the reference uses 85).  The output is then a `JpegResult`; `jpeg_buffer` is an optional uint8 array to receive the
+    # file (PinnedBuffer-backed for speed), allocated when None; `jpeg_capacity` sizes the allocation (default w * h + 64 KiB)
+    jpeg_quality: Optional[int] = None
+    jpeg_buffer: Optional[np.ndarray] = None
+    jpeg_capacity: Optional[int] = None
 
     @staticmethod
     def resize(dw: int, dh: int, **kw) -> "OpSpec":
@@ -114,6 +120,22 @@ class OpSpec:
     @staticmethod
     def watermark(w: int, h: int, color, glyphs: Sequence[GlyphMask], **kw) -> "OpSpec":
         return OpSpec(L.OP_WATERMARK, w, h, color=tuple(color), glyphs=glyphs, **kw)
+
+
+class JpegResult:
+    """A result encoded on the device: `data` is the file once the ticket was waited for."""
+
+    def __init__(self, buffer: np.ndarray):
+        self.buffer = buffer
+        self._len = C.c_uint64(0)
+
+    @property
+    def nbytes(self) -> int:
+        return int(self._len.value)
+
+    @property
+    def data(self) -> bytes:
+        return self.buffer[:self.nbytes].tobytes()
 
 
 @dataclass
@@ -235,7 +257,19 @@ class Engine:
                 keep.append(ga)
                 c.n_glyphs = len(o.glyphs)
                 c.glyphs = ga
-            if o.dst_ycbcr420 is not None:
+            if o.jpeg_quality is not None:
+                buf = o.jpeg_buffer
+                if buf is None:
+                    buf = np.empty(o.jpeg_capacity or (o.dst_w * o.dst_h + (64 << 10)), np.uint8)
+                assert buf.dtype == np.uint8 and buf.ndim == 1 and buf.flags["C_CONTIGUOUS"]
+                res = JpegResult(buf)
+                c.dst_layout = L.JPEG
+                c.dst, c.dst_capacity, c.jpeg_quality = buf.ctypes.data, buf.size, o.jpeg_quality
+                c.dst_len = C.pointer(res._len)
+                c.dst_memspace = L.MEM_HOST
+                keep.append(res)
+                outs.append(res)
+            elif o.dst_ycbcr420 is not None:
                 yp, cbp, crp = o.dst_ycbcr420
                 assert yp.shape == (o.dst_h, o.dst_w) and cbp.shape == crp.shape == ((o.dst_h + 1) // 2, (o.dst_w + 1) // 2)
                 c.dst_layout = L.YCBCR420

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define IPG_ABI_VERSION 2
+#define IPG_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define IPG_API __attribute__((visibility("default")))
@@ -76,6 +76,10 @@ typedef enum {
     IPG_LAYOUT_RGBA64 = 7,   /* *image.RGBA64 (alpha-premultiplied), 8 bytes per pixel */
     IPG_LAYOUT_NRGBA64 = 8,  /* *image.NRGBA64 (straight alpha), 8 bytes per pixel     */
     IPG_LAYOUT_GRAY16 = 9,   /* *image.Gray16, 2 bytes per pixel                        */
+    /* Destination only (ipg_op.dst_layout, new in ABI 3): the result as the JPEG FILE the reference makes of it,
+     * jpeg.Encode(buf, img, &jpeg.Options{Quality: q}) (operations/resize.go:78-91, watermark.go:66-79), encoded on the
+     * device.  See ipg_op.dst_layout. */
+    IPG_LAYOUT_JPEG = 16,
 } ipg_layout;
 
 typedef enum {
@@ -164,13 +168,31 @@ typedef struct {
      * integer color.RGBToYCbCr of the (premultiplied) R, G, B bytes, chroma averaged 2 x 2 as writer.go's scale() does,
      * (sum + 2) >> 2, with the edge pixel replicated for odd sizes -- so jpeg.Encode of
      *   &image.YCbCr{Y, Cb, Cr, YStride, CStride, SubsampleRatio420, Rect(0, 0, w, h)}
-     * emits the same bytes as jpeg.Encode of the RGBA result, and 1.5 instead of 4 bytes per pixel cross PCIe.
+     * emits the same bytes as jpeg.Encode of the RGBA result when dst_w and dst_h are multiples of 16 (otherwise the
+     * writer pads its last MCUs from the edge chroma SAMPLE of a YCbCr image but from the edge PIXEL of an RGBA one, and
+     * the files differ in those blocks: use IPG_LAYOUT_JPEG for byte identity at any size), and 1.5 instead of 4 bytes
+     * per pixel cross PCIe.
      * dst / dst_stride are then the Y plane (dst_w bytes per row), dst_cb / dst_cr / dst_cstride the (dst_w+1)/2 x
-     * (dst_h+1)/2 chroma planes.  Host planes must lie in ipg_alloc_pinned memory (no staging path for this layout). */
+     * (dst_h+1)/2 chroma planes.  Host planes must lie in ipg_alloc_pinned memory (no staging path for this layout).
+     *
+     * IPG_LAYOUT_JPEG (opt-in, new in ABI 3; SURVEY 8f-3, encode half): the result never leaves the device as pixels.
+     * The engine runs the baseline JPEG writer of Go 1.24's image/jpeg on it -- rgbaToYCbCr (integer color.RGBToYCbCr,
+     * edge pixels replicated), 4:2:0 chroma means, the jfdctint forward DCT of fdct.go, division by 8 * quant rounded
+     * half away from zero, the Annex K Huffman tables, byte stuffing, and the writer's own header layout (SOI, one DQT,
+     * SOF0, one DHT, SOS; no JFIF segment) -- all integer arithmetic, so the file is byte for byte what
+     *   jpeg.Encode(buf, result, &jpeg.Options{Quality: jpeg_quality})
+     * writes, and the host's encode step becomes SaveProcessed(bytes).  dst is then a byte buffer of dst_capacity
+     * bytes (any host memory, pinned preferred, or device memory), dst_stride is ignored, and *dst_len (host memory
+     * that stays valid until ipg_wait returns) receives the file length.  A file that does not fit dst_capacity fails
+     * that ticket with IPG_ERR_NOMEM (w * h bytes is ample for photographs at quality 85; w * h * 3 + 4096 always fits
+     * at the qualities the reference uses).  Images of 65536 pixels or more per side are refused as Go's writer refuses them. */
     int32_t dst_layout;
     void *dst_cb, *dst_cr;
     int32_t dst_cstride;
-    int32_t reserved1;
+    int32_t jpeg_quality;     /* IPG_LAYOUT_JPEG: 1..100 as jpeg.Options.Quality (clamped like Go); 0 = 85, the reference's
+                                 constant (domain/task.go:57) */
+    uint64_t dst_capacity;    /* IPG_LAYOUT_JPEG: bytes available at dst */
+    uint64_t *dst_len;        /* IPG_LAYOUT_JPEG: receives the file length */
 } ipg_op;
 
 typedef enum {

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, f"libipgpu.so lacks {missing}"
     assert sorted(names) == sorted(L.EXPORTS + L.HOST_EXPORTS), "python binding list out of sync with the headers"
-    assert lib.ipg_abi_version() == 2
+    assert lib.ipg_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_a_device():
@@ -44,7 +44,7 @@ def test_no_cpu_fallback_without_a_device():
 def test_struct_layouts_match_the_header():
     # sizes the C side was compiled with (x86-64 SysV): guards the ctypes mirrors in _lib.py
     assert C.sizeof(L.Config) == 40 and C.sizeof(L.ImageDesc) == 56 and C.sizeof(L.Glyph) == 48
-    assert C.sizeof(L.Op) == 96 and C.sizeof(L.Stats) == 144
+    assert C.sizeof(L.Op) == 112 and C.sizeof(L.Stats) == 144
 
 
 def test_geometry_helpers_follow_the_reference():
