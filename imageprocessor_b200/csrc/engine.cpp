@@ -435,7 +435,7 @@ static JpegSizes jpeg_sizes(int w, int h, size_t dst_capacity, bool out_in_arena
     const size_t cap = std::min<size_t>(dst_capacity, 0xffff0000u);
     z.scan_cap = align_up(std::max<size_t>(std::min((size_t)z.n_mcu * 1248 + 64, cap), 512), JPEG_CHUNK);
     z.out_cap = std::min(cap, (size_t)JPEG_HDR_MAX + 2 * z.scan_cap + 2);
-    z.total = (size_t)z.n_mcu * (6 * 64 * 2 + 6 * 4 + 4) + z.scan_cap + (z.scan_cap / JPEG_CHUNK + 1) * 4 +
+    z.total = (size_t)(z.n_mcu + 31) / 32 * 6 * JPEG_SLOT_WORDS * JPEG_SLOT_STRIDE * 4 + (size_t)z.n_mcu * (6 * 4 + 4) + z.scan_cap + (z.scan_cap / JPEG_CHUNK + 1) * 4 +
               (out_in_arena ? z.out_cap : 0) + 8 * 256;
     return z;
 }
@@ -966,7 +966,6 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     // ---- device-side JPEG writer (dst_layout JPEG): one job per result
     std::vector<JpegJob> jjobs;
     std::vector<JpegDctItem> jdct;
-    std::vector<JpegEmitItem> jemit;
     std::vector<JpegStuffItem> jstuff;
     uint32_t *d_jresults = nullptr;
     if (!jpeg_ops.empty()) {
@@ -991,7 +990,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
             uint8_t hdr[JPEG_HDR_MAX];
             j.hdr_len = (uint32_t)jpeg_build_header(op.jpeg_quality, op.dw, op.dh, hdr);
             j.hdr = blob.dptr<const uint8_t>(blob.put(hdr, j.hdr_len, 16));
-            j.coef = (int16_t *)arena.take((size_t)z.n_mcu * 6 * 64 * 2);
+            j.acs = (uint32_t *)arena.take((size_t)(z.n_mcu + 31) / 32 * 6 * JPEG_SLOT_WORDS * JPEG_SLOT_STRIDE * 4);
             j.side = (uint32_t *)arena.take((size_t)z.n_mcu * 6 * 4);
             j.mcu_off = (uint32_t *)arena.take((size_t)z.n_mcu * 4);
             j.words = (uint32_t *)arena.take(z.scan_cap);
@@ -999,12 +998,11 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
             j.chunk_off = (uint32_t *)arena.take((z.scan_cap / JPEG_CHUNK + 1) * 4);
             j.out = to_host ? arena.take(z.out_cap) : (uint8_t *)op.dst;
             j.out_cap = (uint32_t)z.out_cap;
-            if (!j.coef || !j.side || !j.mcu_off || !j.words || !j.chunk_off || !j.out) throw std::runtime_error("device arena exhausted (JPEG writer)");
+            if (!j.acs || !j.side || !j.mcu_off || !j.words || !j.chunk_off || !j.out) throw std::runtime_error("device arena exhausted (JPEG writer)");
             const int ji = (int)jjobs.size();
             j.result = d_jresults + 4 * ji;
             jjobs.push_back(j);
             for (int m = 0; m < z.n_mcu; m += JPEG_DCT_MCUS) jdct.push_back(JpegDctItem{ji, m});
-            for (int m = 0; m < z.n_mcu; m += JPEG_EMIT_THREADS) jemit.push_back(JpegEmitItem{ji, m});
             const int parts = (int)std::min<size_t>(JPEG_STUFF_PARTS, (z.scan_cap / JPEG_CHUNK + 7) / 8); // ... of the strided loops; the stride is fixed
             for (int q = 0; q < std::max(parts, 1); q++) jstuff.push_back(JpegStuffItem{ji, q});
             B.jpegs.push_back(Batch::JpegOut{j.out, op.dst, (size_t)op.dst_capacity, op.dst_len, jo.second, ji, to_host});
@@ -1050,7 +1048,6 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     const BlendItem *d_pbitems = blob.dptr<const BlendItem>(blob.put(pbitems.data(), pbitems.size() * sizeof(BlendItem), 16));
     const JpegJob *d_jjobs = blob.dptr<const JpegJob>(blob.put(jjobs.data(), jjobs.size() * sizeof(JpegJob), 16));
     const JpegDctItem *d_jdct = blob.dptr<const JpegDctItem>(blob.put(jdct.data(), jdct.size() * sizeof(JpegDctItem), 16));
-    const JpegEmitItem *d_jemit = blob.dptr<const JpegEmitItem>(blob.put(jemit.data(), jemit.size() * sizeof(JpegEmitItem), 16));
     const JpegStuffItem *d_jstuff = blob.dptr<const JpegStuffItem>(blob.put(jstuff.data(), jstuff.size() * sizeof(JpegStuffItem), 16));
     if (blob.overflow) throw std::runtime_error("parameter blob overflow (batch too heterogeneous); lower max_batch");
     IPG_CU(cudaMemcpyAsync(blob_dev, L.param_host, blob.off, cudaMemcpyHostToDevice, up));
@@ -1150,7 +1147,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     }
     if (!jjobs.empty()) { // ... and the JPEG writer over the results that leave as files
         IPG_CU(cudaMemsetAsync(d_jresults, 0, 16 * jjobs.size(), st));
-        IPG_CU(launch_jpeg(d_jjobs, (int)jjobs.size(), d_jdct, (int)jdct.size(), d_jemit, (int)jemit.size(), d_jstuff, (int)jstuff.size(), st));
+        IPG_CU(launch_jpeg(d_jjobs, (int)jjobs.size(), d_jdct, (int)jdct.size(), d_jstuff, (int)jstuff.size(), st));
         B.n_kernels += JPEG_LAUNCHES;
     }
     IPG_CU(cudaEventRecord(L.ev[3], st));

@@ -6,10 +6,11 @@
 // crosses PCIe: ~0.2-1 instead of 4 bytes per result pixel, and no host encode.
 //
 // Huffman coding is sequential in the bit position, so the writer is seven data-parallel passes:
-//   k_jpeg_dct      one thread per 8 x 8 block: colour transform, FDCT, quantisation -> zig-zag int16 + (dc, AC bits)
+//   k_jpeg_dct      one thread per 8 x 8 block: colour transform, FDCT, quantisation; the block's AC coefficients are
+//                   entropy-coded on the spot into a private slot (only the DC code depends on another block)
 //   k_jpeg_offsets  one CTA per job: bits per MCU (DC deltas need the neighbour's dc) -> exclusive scan = bit offsets
 //   k_jpeg_zero     clears exactly the words the scan will occupy (its size is known on the device only)
-//   k_jpeg_emit     one thread per MCU: codes OR-ed into the MSB-first scan at its bit offset
+//   k_jpeg_emit     one thread per block: its DC code, then its slot shift-copied into the MSB-first scan at its bit offset
 //   k_jpeg_ffcount  one warp per 512 scan bytes: how many 0xff bytes (each gets a 0x00 stuffed after it)
 //   k_jpeg_chunks   one CTA per job: exclusive scan of those counts, file length
 //   k_jpeg_write    one warp per 512 scan bytes: header | stuffed scan | EOI
@@ -56,25 +57,44 @@ __device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t *smem32
 }
 
 // ---- k_jpeg_dct ---------------------------------------------------------------------------------------------------
-// A CTA takes JPEG_DCT_MCUS consecutive MCUs (scan order) of one job; they may wrap to the next MCU row, every MCU is
-// staged on its own.  The 16 x 16 pixels of each MCU are staged in shared memory with the writer's edge
-// clamp applied; MCU m's rows sit 17 words apart from MCU m+1's so that the 32 lanes of a warp (one MCU each) hit 32
-// different banks.  Warp b then builds block b (Y0..Y3, Cb, Cr) of the 32 MCUs.
+// A CTA takes JPEG_DCT_MCUS = 32 consecutive MCUs (scan order) of one job; they may wrap to the next MCU row, every MCU
+// is staged on its own.  The 16 x 16 pixels of each MCU are staged in shared memory with the writer's edge clamp
+// applied; MCU m's rows sit 17 words apart from MCU m+1's so that the 32 lanes of a warp (one MCU each) hit 32
+// different banks.  Warps 0-3 convert the luma quadrants of the 32 MCUs (and leave the 2 x 2 chroma means of their pixels
+// in shared memory, which is how writer.go's rgbaToYCbCr + scale split the work too); then warp b runs FDCT,
+// quantisation and AC coding of block b (Y0..Y3, Cb, Cr).
 enum { DCT_ROW_WORDS = JPEG_DCT_MCUS * 17 };
+struct DctSmem {
+    uint32_t px[16 * DCT_ROW_WORDS];
+    uint32_t cmean[2][JPEG_DCT_MCUS * 17]; // Cb / Cr: the 16 words (8 x 8 means) of each MCU, MCUs 17 words apart
+    int32_t half[2][64];
+    uint32_t recip[2][64];
+    uint32_t lut_ac[2][256];
+};
 __global__ void __launch_bounds__(192) k_jpeg_dct(const JpegJob *__restrict__ jobs, const JpegDctItem *__restrict__ items)
 {
-    __shared__ uint32_t px[16 * DCT_ROW_WORDS];
+    __shared__ DctSmem sm;
     const JpegDctItem it = items[blockIdx.x];
     const JpegJob &J = jobs[it.job];
+    const JpegTables &T = *J.tab;
     const int xmax = J.w - 1, ymax = J.h - 1;
     const int n_here = min((int)JPEG_DCT_MCUS, J.n_mcu - it.mcu0);
-    // stage: 4 pixels per step (one 16-byte load when they are all inside the image)
-    for (int q = threadIdx.x; q < n_here * 16 * 4; q += blockDim.x) {
-        const int m = q >> 6, row = (q >> 2) & 15, quad = q & 3;
-        const int mcu = it.mcu0 + m;
-        const int x0 = (mcu % J.mcu_w) * 16 + quad * 4, y = min((mcu / J.mcu_w) * 16 + row, ymax);
+    for (int k = threadIdx.x; k < 128; k += blockDim.x) {
+        sm.half[k >> 6][k & 63] = T.half[k >> 6][k & 63];
+        sm.recip[k >> 6][k & 63] = T.recip[k >> 6][k & 63];
+    }
+    for (int k = threadIdx.x; k < 512; k += blockDim.x) sm.lut_ac[k >> 8][k & 255] = T.lut[(k >> 8) * 2 + 1][k & 255];
+    // stage: 4 pixels per step (one 16-byte load when they are all inside the image); consecutive threads take
+    // consecutive 16-byte pieces of one image row, MCU after MCU
+    const int mx0 = it.mcu0 % J.mcu_w, my0 = it.mcu0 / J.mcu_w;
+    for (int q = threadIdx.x; q < 16 * JPEG_DCT_MCUS * 4; q += blockDim.x) {
+        const int row = q >> 7, m = (q >> 2) & 31, quad = q & 3;
+        if (m >= n_here) continue;
+        int mx = mx0 + m, my = my0;
+        while (mx >= J.mcu_w) { mx -= J.mcu_w; my++; }
+        const int x0 = mx * 16 + quad * 4, y = min(my * 16 + row, ymax);
         const uint8_t *rowp = J.rgba + (size_t)y * (size_t)J.rgba_pitch;
-        uint32_t *d = px + row * DCT_ROW_WORDS + m * 17 + quad * 4;
+        uint32_t *d = sm.px + row * DCT_ROW_WORDS + m * 17 + quad * 4;
         if (x0 + 3 <= xmax) {
             const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rowp + (size_t)x0 * 4));
             d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
@@ -85,11 +105,26 @@ __global__ void __launch_bounds__(192) k_jpeg_dct(const JpegJob *__restrict__ jo
     }
     __syncthreads();
     const int blk = threadIdx.x >> 5, m = threadIdx.x & 31;
-    if (m >= n_here) return;
-    const int mcu = it.mcu0 + m;
-    const uint32_t *base = px + m * 17;
-    jpeg_block(*J.tab, blk, J.coef + ((size_t)mcu * 6 + blk) * 64, J.side + (size_t)mcu * 6 + blk,
-               [base](int lx, int ly) { return base[ly * DCT_ROW_WORDS + lx]; });
+    const bool active = m < n_here;
+    const int mcu = it.mcu0 + m, q = blk < 4 ? 0 : 1;
+    int32_t b[64];
+    if (blk < 4 && active) { // the four luma warps convert their quadrants and leave the chroma means for warps 4 and 5
+        const uint32_t *base = sm.px + m * 17;
+        uint32_t cbw[4], crw[4];
+        jpeg_quadrant(blk, b, cbw, crw, [base](int lx, int ly) { return base[ly * DCT_ROW_WORDS + lx]; });
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            sm.cmean[0][m * 17 + jpeg_chroma_word(blk, r)] = cbw[r];
+            sm.cmean[1][m * 17 + jpeg_chroma_word(blk, r)] = crw[r];
+        }
+    }
+    __syncthreads();
+    if (!active) return;
+    if (blk >= 4) {
+        const uint32_t *cw = sm.cmean[blk - 4] + m * 17;
+        jpeg_chroma_block(b, [cw](int k) { return cw[k]; });
+    }
+    jpeg_block_code(b, sm.half[q], sm.recip[q], sm.lut_ac[q], J.acs + jpeg_slot_index(mcu, blk), JPEG_SLOT_STRIDE, J.side + (size_t)mcu * 6 + blk);
 }
 
 // ---- k_jpeg_offsets -------------------------------------------------------------------------------------------------
@@ -137,14 +172,31 @@ __global__ void __launch_bounds__(JPEG_STUFF_THREADS) k_jpeg_zero(const JpegJob 
 }
 
 // ---- k_jpeg_emit ----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(JPEG_EMIT_THREADS) k_jpeg_emit(const JpegJob *__restrict__ jobs, const JpegEmitItem *__restrict__ items)
+// Same CTA shape as k_jpeg_dct: 32 MCUs, warp b = block b.  A block's place in the scan is its MCU's offset plus the
+// bits of the blocks before it in the MCU (their DC codes depend on their predictors: the side words of the 32 MCUs
+// and of the one before them are staged in shared memory).
+__global__ void __launch_bounds__(192) k_jpeg_emit(const JpegJob *__restrict__ jobs, const JpegDctItem *__restrict__ items)
 {
-    const JpegEmitItem it = items[blockIdx.x];
+    __shared__ uint32_t side_s[(JPEG_DCT_MCUS + 1) * 6];
+    __shared__ uint32_t lut_dc[2][16];
+    const JpegDctItem it = items[blockIdx.x];
     const JpegJob &J = jobs[it.job];
     if (J.result[1]) return;
-    const int m = it.mcu0 + threadIdx.x;
-    if (m >= J.n_mcu) return;
-    jpeg_mcu_emit(J, *J.tab, m, m == J.n_mcu - 1);
+    const int n_here = min((int)JPEG_DCT_MCUS, J.n_mcu - it.mcu0);
+    for (int k = threadIdx.x; k < (n_here + 1) * 6; k += blockDim.x) {
+        const int g = (it.mcu0 - 1) * 6 + k;
+        side_s[k] = g >= 0 ? J.side[g] : 0u;
+    }
+    if (threadIdx.x < 32) lut_dc[threadIdx.x >> 4][threadIdx.x & 15] = J.tab->lut[(threadIdx.x >> 4) * 2][threadIdx.x & 15];
+    __syncthreads();
+    const int blk = threadIdx.x >> 5, m = threadIdx.x & 31;
+    if (m >= n_here) return;
+    const int mcu = it.mcu0 + m, mi = m + 1;
+    const bool first = mcu == 0;
+    uint32_t off = J.mcu_off[mcu];
+    for (int b = 0; b < blk; b++) off += jpeg_block_bits(lut_dc[0], lut_dc[1], side_s, mi, b, first);
+    jpeg_block_emit(J.words, lut_dc[blk < 4 ? 0 : 1], side_s[mi * 6 + blk], jpeg_prev_dc(side_s, mi, blk, first), off,
+                    J.acs + jpeg_slot_index(mcu, blk), JPEG_SLOT_STRIDE, mcu == J.n_mcu - 1 && blk == 5);
 }
 
 // ---- byte stuffing --------------------------------------------------------------------------------------------------
@@ -227,14 +279,14 @@ __global__ void __launch_bounds__(JPEG_STUFF_THREADS) k_jpeg_write(const JpegJob
 
 } // namespace
 
-cudaError_t launch_jpeg(const JpegJob *jobs, int n_jobs, const JpegDctItem *dct_items, int n_dct, const JpegEmitItem *emit_items,
-                        int n_emit, const JpegStuffItem *stuff_items, int n_stuff, cudaStream_t st)
+cudaError_t launch_jpeg(const JpegJob *jobs, int n_jobs, const JpegDctItem *dct_items, int n_dct, const JpegStuffItem *stuff_items,
+                        int n_stuff, cudaStream_t st)
 {
     if (n_jobs <= 0) return cudaSuccess;
     k_jpeg_dct<<<n_dct, 192, 0, st>>>(jobs, dct_items);
     k_jpeg_offsets<<<n_jobs, JPEG_SCAN_THREADS, 0, st>>>(jobs);
     k_jpeg_zero<<<n_stuff, JPEG_STUFF_THREADS, 0, st>>>(jobs, stuff_items);
-    k_jpeg_emit<<<n_emit, JPEG_EMIT_THREADS, 0, st>>>(jobs, emit_items);
+    k_jpeg_emit<<<n_dct, 192, 0, st>>>(jobs, dct_items);
     k_jpeg_ffcount<<<n_stuff, JPEG_STUFF_THREADS, 0, st>>>(jobs, stuff_items);
     k_jpeg_chunks<<<n_jobs, JPEG_SCAN_THREADS, 0, st>>>(jobs);
     k_jpeg_write<<<n_stuff, JPEG_STUFF_THREADS, 0, st>>>(jobs, stuff_items);

@@ -13,15 +13,13 @@ namespace ipg {
 enum {
     JPEG_HDR_MAX = 640,      // SOI + DQT + SOF0 + DHT + SOS header = 589 bytes
     JPEG_CHUNK = 512,        // unstuffed scan bytes per stuffing chunk (one warp, 16 bytes per lane)
-    JPEG_DCT_MCUS = 32,      // MCUs per k_jpeg_dct CTA (6 warps: one per block of the MCU)
-    JPEG_EMIT_THREADS = 128, // k_jpeg_emit: one thread per MCU
+    JPEG_DCT_MCUS = 32,      // MCUs per k_jpeg_dct / k_jpeg_emit CTA (6 warps: one per block of the MCU); = JPEG_SLOT_STRIDE
     JPEG_SCAN_THREADS = 1024,
     JPEG_STUFF_THREADS = 256,
     JPEG_STUFF_PARTS = 64,   // k_jpeg_ffcount / k_jpeg_write CTAs per job (each strides over the job's chunks)
 };
 
-struct JpegDctItem { int32_t job; int32_t mcu0; };   // JPEG_DCT_MCUS MCUs starting at mcu0
-struct JpegEmitItem { int32_t job; int32_t mcu0; };  // JPEG_EMIT_THREADS MCUs starting at mcu0
+struct JpegDctItem { int32_t job; int32_t mcu0; };   // JPEG_DCT_MCUS MCUs starting at mcu0 (k_jpeg_dct and k_jpeg_emit)
 struct JpegStuffItem { int32_t job; int32_t part; }; // part of JPEG_STUFF_PARTS
 
 // host helpers (jpeg_host.cpp)
@@ -33,8 +31,8 @@ size_t jpeg_build_header(int quality, int w, int h, uint8_t *out); // <= JPEG_HD
 // k_jpeg_dct -> k_jpeg_offsets -> k_jpeg_zero -> k_jpeg_emit -> k_jpeg_ffcount -> k_jpeg_chunks -> k_jpeg_write.
 // JpegJob::result[0..3] must be zero when it starts.
 enum { JPEG_LAUNCHES = 7 };
-cudaError_t launch_jpeg(const JpegJob *jobs, int n_jobs, const JpegDctItem *dct_items, int n_dct, const JpegEmitItem *emit_items,
-                        int n_emit, const JpegStuffItem *stuff_items, int n_stuff, cudaStream_t st);
+cudaError_t launch_jpeg(const JpegJob *jobs, int n_jobs, const JpegDctItem *dct_items, int n_dct, const JpegStuffItem *stuff_items,
+                        int n_stuff, cudaStream_t st);
 #endif
 
 } // namespace ipg

@@ -39,8 +39,8 @@ struct JpegJob {
     int32_t w, h;
     int32_t mcu_w, n_mcu;     // 16 x 16 MCUs per row, and in all
     const JpegTables *tab;
-    int16_t *coef;            // [n_mcu][6][64] quantised coefficients in zig-zag order (Y0 Y1 Y2 Y3 Cb Cr)
-    uint32_t *side;           // [n_mcu][6] per block: (uint16) dc | AC bits << 16
+    uint32_t *acs;            // per block: its AC bitstring (jpeg_slot_index: JPEG_SLOT_WORDS words, 32 slots interleaved)
+    uint32_t *side;           // [n_mcu][6] per block (Y0 Y1 Y2 Y3 Cb Cr): (uint16) quantised dc | AC bits << 16
     uint32_t *mcu_off;        // [n_mcu] bit offset of each MCU in the unstuffed scan
     uint32_t *words;          // the unstuffed scan, MSB-first bits in 32-bit words (k_jpeg_zero clears what k_jpeg_emit will fill)
     uint32_t cap_bytes;       // capacity of `words` in bytes (multiple of 16) and of the scan part of `out`
@@ -155,37 +155,98 @@ IPG_HD uint32_t jpeg_dc_bits(int diff, const uint32_t *lut_dc)
     return (lut_dc[nb] >> 24) + nb;
 }
 
-// Colour transform + FDCT + quantisation of block `blk` (0..3 luma quadrants, 4 Cb, 5 Cr) of one MCU: 64 zig-zag int16
-// to `coef`, (dc | AC bits << 16) to *side.  px(lx, ly) returns the RGBA8 word of the MCU's pixel (lx, ly), 0 <= lx, ly < 16,
-// with the image coordinate clamped to the last column / row as writer.go's rgbaToYCbCr clamps it.
-template <typename LoadPx>
-IPG_HD void jpeg_block(const JpegTables &T, int blk, int16_t *coef, uint32_t *side, LoadPx px)
-{
-    int32_t b[64];
-    if (blk < 4) {
-        const int bx = (blk & 1) * 8, by = (blk & 2) * 4;
-IPG_UNROLL
-        for (int j = 0; j < 8; j++)
-IPG_UNROLL
-            for (int i = 0; i < 8; i++) b[8 * j + i] = jpeg_luma(px(bx + i, by + j));
-    } else {
-        const int32_t kr = blk == 4 ? -11056 : 32768, kg = blk == 4 ? -21712 : -27440, kb = blk == 4 ? 32768 : -5328;
-IPG_UNROLL
-        for (int j = 0; j < 8; j++)
-IPG_UNROLL
-            for (int i = 0; i < 8; i++) // writer.go scale(): mean of the 2 x 2 group of per-pixel 8-bit chroma values
-                b[8 * j + i] = (jpeg_chroma(px(2 * i, 2 * j), kr, kg, kb) + jpeg_chroma(px(2 * i + 1, 2 * j), kr, kg, kb) +
-                                jpeg_chroma(px(2 * i, 2 * j + 1), kr, kg, kb) + jpeg_chroma(px(2 * i + 1, 2 * j + 1), kr, kg, kb) + 2) >> 2;
+// MSB-first bit writer into a block's private slot: word k of the slot lives at acs[k * stride] (the slots of the 32
+// lanes of a warp are interleaved word by word, so both k_jpeg_dct's stores and k_jpeg_emit's loads coalesce).
+struct JpegSlotWriter {
+    uint32_t *acs;
+    int stride;
+    uint32_t total;  // bits written
+    uint32_t nacc;
+    uint64_t acc;
+    IPG_HD void put(uint32_t bits, uint32_t n) // n <= 32
+    {
+        acc = (acc << n) | bits;
+        nacc += n;
+        total += n;
+        if (nacc >= 32) {
+            nacc -= 32;
+            *acs = (uint32_t)(acc >> nacc);
+            acs += stride;
+            acc &= ((uint64_t)1 << nacc) - 1;
+        }
     }
+    IPG_HD void finish()
+    {
+        if (nacc) *acs = (uint32_t)(acc << (32 - nacc));
+    }
+};
+
+// Slot of block `blk` of MCU m: the blocks are grouped by (32 consecutive MCUs, blk); within a group the 32 slots
+// interleave.  Returns the first word; the slot's word k is JPEG_SLOT_STRIDE words further each.
+enum { JPEG_SLOT_WORDS = 52, JPEG_SLOT_STRIDE = 32 }; // 63 coefficients x (16-bit code + 10 value bits) = 1638 bits <= 52 words
+IPG_HD size_t jpeg_slot_index(int m, int blk) { return ((size_t)(m >> 5) * 6 + blk) * (JPEG_SLOT_WORDS * JPEG_SLOT_STRIDE) + (m & 31); }
+
+// Colour transform of luma quadrant `blk` (0..3) of an MCU, as writer.go's rgbaToYCbCr + scale see it: the quadrant's
+// 64 luma samples to b (natural order), and the 4 x 4 chroma means of its 2 x 2 pixel groups, (sum of the four per-pixel
+// 8-bit values + 2) >> 2, packed four to a word: cbw[r] / crw[r] = chroma row r of the quadrant, byte i = column i.
+// px(lx, ly) returns the RGBA8 word of the MCU's pixel (lx, ly), 0 <= lx, ly < 16, with the image coordinate clamped to
+// the last column / row as rgbaToYCbCr clamps it.
+template <typename LoadPx>
+IPG_HD void jpeg_quadrant(int blk, int32_t *b, uint32_t *cbw, uint32_t *crw, LoadPx px)
+{
+    const int bx = (blk & 1) * 8, by = (blk & 2) * 4;
+IPG_UNROLL
+    for (int r = 0; r < 4; r++) {
+        uint32_t wcb = 0, wcr = 0;
+IPG_UNROLL
+        for (int i = 0; i < 4; i++) {
+            const uint32_t p00 = px(bx + 2 * i, by + 2 * r), p01 = px(bx + 2 * i + 1, by + 2 * r);
+            const uint32_t p10 = px(bx + 2 * i, by + 2 * r + 1), p11 = px(bx + 2 * i + 1, by + 2 * r + 1);
+            b[16 * r + 2 * i] = jpeg_luma(p00);
+            b[16 * r + 2 * i + 1] = jpeg_luma(p01);
+            b[16 * r + 8 + 2 * i] = jpeg_luma(p10);
+            b[16 * r + 8 + 2 * i + 1] = jpeg_luma(p11);
+            const int32_t cb = (jpeg_chroma(p00, -11056, -21712, 32768) + jpeg_chroma(p01, -11056, -21712, 32768) +
+                                jpeg_chroma(p10, -11056, -21712, 32768) + jpeg_chroma(p11, -11056, -21712, 32768) + 2) >> 2;
+            const int32_t cr = (jpeg_chroma(p00, 32768, -27440, -5328) + jpeg_chroma(p01, 32768, -27440, -5328) +
+                                jpeg_chroma(p10, 32768, -27440, -5328) + jpeg_chroma(p11, 32768, -27440, -5328) + 2) >> 2;
+            wcb |= (uint32_t)cb << (8 * i);
+            wcr |= (uint32_t)cr << (8 * i);
+        }
+        cbw[r] = wcb;
+        crw[r] = wcr;
+    }
+}
+// Where quadrant q's chroma row r goes among the 16 words of a chroma block (row-major, two words per row).
+IPG_HD int jpeg_chroma_word(int q, int r) { return ((q >> 1) * 4 + r) * 2 + (q & 1); }
+// The 8 x 8 chroma block from those 16 words; word(k) returns word k.
+template <typename LoadWord>
+IPG_HD void jpeg_chroma_block(int32_t *b, LoadWord word)
+{
+IPG_UNROLL
+    for (int k = 0; k < 16; k++) {
+        const uint32_t w = word(k);
+IPG_UNROLL
+        for (int i = 0; i < 4; i++) b[4 * k + i] = (int32_t)((w >> (8 * i)) & 0xff);
+    }
+}
+
+// FDCT + quantisation + AC entropy coding of one block whose 64 samples are in b: the AC bitstring to the block's slot,
+// (dc | AC bits << 16) to *side.  half / recip: the block's quantiser rows (luminance or chrominance); lut_ac: its AC
+// Huffman table.
+IPG_HD void jpeg_block_code(int32_t *b, const int32_t *half, const uint32_t *recip, const uint32_t *lut_ac, uint32_t *acs, int acs_stride,
+                            uint32_t *side)
+{
     jpeg_fdct(b);
-    const int q = blk < 4 ? 0 : 1;
     int16_t c[64];
-#define IPG_JPEG_Q(zig, nat) c[zig] = (int16_t)jpeg_quant(b[nat], T.half[q][zig], T.recip[q][zig]);
+#define IPG_JPEG_Q(zig, nat) c[zig] = (int16_t)jpeg_quant(b[nat], half[zig], recip[zig]);
     IPG_JPEG_ZIGZAG(IPG_JPEG_Q)
 #undef IPG_JPEG_Q
-    uint32_t bits = 0; // AC bits, counted here while the coefficients are in registers
+    // The AC coefficients are entropy-coded right here, while they sit in registers, into this block's private slot: only
+    // the DC code depends on another block (the predictor), so k_jpeg_emit later writes that code and shift-copies the
+    // slot's bits to the block's place in the scan.
+    JpegSlotWriter sw{acs, acs_stride, 0, 0, 0};
     {
-        const uint32_t *lut = T.lut[2 * q + 1];
         int run = 0;
 IPG_UNROLL
         for (int zig = 1; zig < 64; zig++) {
@@ -193,51 +254,48 @@ IPG_UNROLL
             if (v == 0) {
                 run++;
             } else {
-                bits += (uint32_t)(run >> 4) * (lut[0xf0] >> 24);
+                while (run > 15) { // ZRL
+                    sw.put(lut_ac[0xf0] & 0xffffff, lut_ac[0xf0] >> 24);
+                    run -= 16;
+                }
                 const uint32_t nb = jpeg_nbits((uint32_t)(v < 0 ? -v : v));
-                bits += (lut[(run & 15) << 4 | nb] >> 24) + nb;
+                const uint32_t x = lut_ac[run << 4 | nb];
+                sw.put((x & 0xffffff) << nb | ((uint32_t)(v < 0 ? v - 1 : v) & ((1u << nb) - 1)), (x >> 24) + nb); // <= 16 + 10 bits
                 run = 0;
             }
         }
-        if (run > 0) bits += lut[0x00] >> 24;
+        if (run > 0) sw.put(lut_ac[0x00] & 0xffffff, lut_ac[0x00] >> 24); // EOB
     }
-    *side = (uint32_t)(uint16_t)c[0] | bits << 16;
-IPG_UNROLL
-    for (int k = 0; k < 64; k += 8) { // eight 16-byte stores
-        uint32_t w0 = (uint16_t)c[k] | (uint32_t)(uint16_t)c[k + 1] << 16, w1 = (uint16_t)c[k + 2] | (uint32_t)(uint16_t)c[k + 3] << 16;
-        uint32_t w2 = (uint16_t)c[k + 4] | (uint32_t)(uint16_t)c[k + 5] << 16, w3 = (uint16_t)c[k + 6] | (uint32_t)(uint16_t)c[k + 7] << 16;
-        uint32_t *o = reinterpret_cast<uint32_t *>(coef + k);
-#if defined(__CUDA_ARCH__)
-        *reinterpret_cast<uint4 *>(o) = make_uint4(w0, w1, w2, w3);
-#else
-        o[0] = w0; o[1] = w1; o[2] = w2; o[3] = w3;
-#endif
-    }
+    sw.finish();
+    *side = (uint32_t)(uint16_t)c[0] | sw.total << 16; // total <= 63 * 26 bits
 }
 
-// DC predictor of block `blk` of MCU m: the previous block of the same component in scan order (0 at the start).
-IPG_HD int jpeg_prev_dc(const uint32_t *side, int m, int blk)
+// DC predictor of block `blk` of the MCU whose six side words start at side[mi * 6]: the previous block of the same
+// component in scan order; `first`: the MCU is the scan's first (predictors start at 0).
+IPG_HD int jpeg_prev_dc(const uint32_t *side, int mi, int blk, bool first)
 {
-    if (blk >= 1 && blk <= 3) return (int16_t)(side[m * 6 + blk - 1] & 0xffff);
-    if (m == 0) return 0;
-    return (int16_t)(side[(m - 1) * 6 + (blk == 0 ? 3 : blk)] & 0xffff);
+    if (blk >= 1 && blk <= 3) return (int16_t)(side[mi * 6 + blk - 1] & 0xffff);
+    if (first) return 0;
+    return (int16_t)(side[(mi - 1) * 6 + (blk == 0 ? 3 : blk)] & 0xffff);
 }
-// Bits MCU m occupies in the scan.
+// Bits block `blk` of that MCU occupies in the scan: its DC code and value, and its AC bitstring.
+IPG_HD uint32_t jpeg_block_bits(const uint32_t *lut_dc_lum, const uint32_t *lut_dc_chr, const uint32_t *side, int mi, int blk, bool first)
+{
+    const uint32_t s = side[mi * 6 + blk];
+    return (s >> 16) + jpeg_dc_bits((int16_t)(s & 0xffff) - jpeg_prev_dc(side, mi, blk, first), blk < 4 ? lut_dc_lum : lut_dc_chr);
+}
 IPG_HD uint32_t jpeg_mcu_bits(const JpegTables &T, const uint32_t *side, int m)
 {
     uint32_t bits = 0;
-    for (int blk = 0; blk < 6; blk++) {
-        const uint32_t s = side[m * 6 + blk];
-        bits += (s >> 16) + jpeg_dc_bits((int16_t)(s & 0xffff) - jpeg_prev_dc(side, m, blk), T.lut[blk < 4 ? 0 : 2]);
-    }
+    for (int blk = 0; blk < 6; blk++) bits += jpeg_block_bits(T.lut[0], T.lut[2], side, m, blk, m == 0);
     return bits;
 }
 
-// MSB-first bit writer into 32-bit words shared with the neighbouring MCUs (whole words are OR-ed in).
+// MSB-first bit writer into 32-bit words shared with the neighbouring blocks (whole words are OR-ed in).
 struct JpegBitWriter {
     uint32_t *words;
     uint32_t wi;     // word being filled
-    uint32_t nacc;   // bits of it taken (by the predecessor MCU and by us)
+    uint32_t nacc;   // bits of it taken (by the predecessor and by us)
     uint64_t acc;    // our bits, right-aligned
     IPG_HD void flush_word(uint32_t v)
     {
@@ -248,7 +306,7 @@ struct JpegBitWriter {
 #endif
         wi++;
     }
-    IPG_HD void put(uint32_t bits, uint32_t n) // n <= 16
+    IPG_HD void put(uint32_t bits, uint32_t n) // n <= 32
     {
         acc = (acc << n) | bits;
         nacc += n;
@@ -264,40 +322,21 @@ struct JpegBitWriter {
     }
 };
 
-// Entropy-code MCU m at its bit offset.  `last`: also writes the writer's final emit(0x7f, 7) padding.
-IPG_HD void jpeg_mcu_emit(const JpegJob &J, const JpegTables &T, int m, bool last)
+// Block `blk` of an MCU into the scan at bit offset `off`: emitHuffRLE(dc table, 0, dc - prevDC), then the AC bitstring
+// k_jpeg_dct left in the block's slot.  `last` (the scan's last block): also the writer's final emit(0x7f, 7) padding.
+IPG_HD void jpeg_block_emit(uint32_t *words, const uint32_t *lut_dc, uint32_t side_word, int prev_dc, uint32_t off,
+                            const uint32_t *acs, int acs_stride, bool last)
 {
-    const uint32_t off = J.mcu_off[m];
-    JpegBitWriter bw{J.words, off >> 5, off & 31, 0};
-    for (int blk = 0; blk < 6; blk++) {
-        const int16_t *c = J.coef + ((size_t)m * 6 + blk) * 64;
-        const uint32_t *ldc = T.lut[blk < 4 ? 0 : 2], *lac = T.lut[blk < 4 ? 1 : 3];
-        { // emitHuffRLE(dc table, 0, dc - prevDC)
-            const int diff = (int)c[0] - jpeg_prev_dc(J.side, m, blk);
-            const uint32_t nb = jpeg_nbits((uint32_t)(diff < 0 ? -diff : diff));
-            const uint32_t x = ldc[nb];
-            bw.put(x & 0xffffff, x >> 24);
-            if (nb) bw.put((uint32_t)(diff < 0 ? diff - 1 : diff) & ((1u << nb) - 1), nb);
-        }
-        int run = 0;
-        for (int zig = 1; zig < 64; zig++) {
-            const int v = c[zig];
-            if (v == 0) { run++; continue; }
-            while (run > 15) {
-                const uint32_t z = lac[0xf0];
-                bw.put(z & 0xffffff, z >> 24);
-                run -= 16;
-            }
-            const uint32_t nb = jpeg_nbits((uint32_t)(v < 0 ? -v : v));
-            const uint32_t x = lac[run << 4 | nb];
-            bw.put(x & 0xffffff, x >> 24);
-            bw.put((uint32_t)(v < 0 ? v - 1 : v) & ((1u << nb) - 1), nb);
-            run = 0;
-        }
-        if (run > 0) {
-            const uint32_t z = lac[0x00];
-            bw.put(z & 0xffffff, z >> 24);
-        }
+    JpegBitWriter bw{words, off >> 5, off & 31, 0};
+    const int diff = (int)(int16_t)(side_word & 0xffff) - prev_dc;
+    const uint32_t nb = jpeg_nbits((uint32_t)(diff < 0 ? -diff : diff));
+    const uint32_t x = lut_dc[nb];
+    bw.put((x & 0xffffff) << nb | ((uint32_t)(diff < 0 ? diff - 1 : diff) & ((1u << nb) - 1)), (x >> 24) + nb); // <= 9 + 11 bits
+    const uint32_t acbits = side_word >> 16;
+    for (uint32_t k = 0; k * 32 < acbits; k++) {
+        const uint32_t w = acs[(size_t)k * acs_stride];
+        const uint32_t n = acbits - k * 32 < 32 ? acbits - k * 32 : 32;
+        bw.put(w >> (32 - n), n);
     }
     if (last && bw.nacc % 8) bw.put((1u << (8 - bw.nacc % 8)) - 1, 8 - bw.nacc % 8); // pad the last byte with ones
     bw.finish();

@@ -15,3 +15,9 @@ for r in rows[1:]:
     agg[r[ki].split("(")[0]].append(v)
 for k, v in agg.items(): print(f"{k:40s} n={len(v):3d} mean {sum(v)/len(v):9.1f} us  (4 images x 3 files per launch)")
 PY
+if [ "$1" = "full" ]; then
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:k_jpeg_dct -s 1 -c 1 -o gpurun_out/prof_jpeg_dct -f \
+    python tools/jpeg_probe.py --images 4 --steps 1 --verify 0 > gpurun_out/ncu_jpeg_dct.log 2>&1; echo dct rc=$?
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:k_jpeg_write -s 1 -c 1 -o gpurun_out/prof_jpeg_write -f \
+    python tools/jpeg_probe.py --images 4 --steps 1 --verify 0 > gpurun_out/ncu_jpeg_write.log 2>&1; echo write rc=$?
+fi
