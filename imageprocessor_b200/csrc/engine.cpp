@@ -1003,8 +1003,10 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
             j.result = d_jresults + 4 * ji;
             jjobs.push_back(j);
             for (int m = 0; m < z.n_mcu; m += JPEG_DCT_MCUS) jdct.push_back(JpegDctItem{ji, m});
-            const int parts = (int)std::min<size_t>(JPEG_STUFF_PARTS, (z.scan_cap / JPEG_CHUNK + 7) / 8); // ... of the strided loops; the stride is fixed
-            for (int q = 0; q < std::max(parts, 1); q++) jstuff.push_back(JpegStuffItem{ji, q});
+            // CTAs of the stuffing passes: the scan's real size is known on the device only, so size them for the capacity, 32
+            // chunks (4 per warp) each; CTAs past the real end exit at once
+            const int parts = (int)std::max<size_t>(1, std::min<size_t>(JPEG_STUFF_PARTS, (z.scan_cap / JPEG_CHUNK + 31) / 32));
+            for (int q = 0; q < parts; q++) jstuff.push_back(JpegStuffItem{ji, (int16_t)q, (int16_t)parts});
             B.jpegs.push_back(Batch::JpegOut{j.out, op.dst, (size_t)op.dst_capacity, op.dst_len, jo.second, ji, to_host});
         }
     }

@@ -65,11 +65,19 @@ __device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t *smem32
 // quantisation and AC coding of block b (Y0..Y3, Cb, Cr).
 enum { DCT_ROW_WORDS = JPEG_DCT_MCUS * 17 };
 struct DctSmem {
-    uint32_t px[16 * DCT_ROW_WORDS];
+    union {
+        uint32_t px[16 * DCT_ROW_WORDS];   // the staged pixels: dead once every luma warp has converted its quadrants
+        int16_t coef[64][192];             // then: non-zero quantised AC coefficients, [zig][thread] (lanes side by side)
+    };
     uint32_t cmean[2][JPEG_DCT_MCUS * 17]; // Cb / Cr: the 16 words (8 x 8 means) of each MCU, MCUs 17 words apart
     int32_t half[2][64];
     uint32_t recip[2][64];
     uint32_t lut_ac[2][256];
+};
+struct CoefSmem {
+    int16_t *p; // this thread's column
+    __device__ __forceinline__ void set(int zig, int v) { p[zig * 192] = (int16_t)v; }
+    __device__ __forceinline__ int get(int zig) const { return p[zig * 192]; }
 };
 __global__ void __launch_bounds__(192) k_jpeg_dct(const JpegJob *__restrict__ jobs, const JpegDctItem *__restrict__ items)
 {
@@ -84,24 +92,37 @@ __global__ void __launch_bounds__(192) k_jpeg_dct(const JpegJob *__restrict__ jo
         sm.recip[k >> 6][k & 63] = T.recip[k >> 6][k & 63];
     }
     for (int k = threadIdx.x; k < 512; k += blockDim.x) sm.lut_ac[k >> 8][k & 255] = T.lut[(k >> 8) * 2 + 1][k & 255];
-    // stage: 4 pixels per step (one 16-byte load when they are all inside the image); consecutive threads take
+    // stage: 4 pixels per piece (one 16-byte load when they are all inside the image); consecutive threads take
     // consecutive 16-byte pieces of one image row, MCU after MCU
     const int mx0 = it.mcu0 % J.mcu_w, my0 = it.mcu0 / J.mcu_w;
-    for (int q = threadIdx.x; q < 16 * JPEG_DCT_MCUS * 4; q += blockDim.x) {
+    constexpr int kPieces = 16 * JPEG_DCT_MCUS * 4, kRounds = (kPieces + 191) / 192; // 2048 pieces, 11 per thread
+    uint4 v[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) { // all the loads first: 11 in flight per thread
+        const int q = threadIdx.x + r * 192;
         const int row = q >> 7, m = (q >> 2) & 31, quad = q & 3;
-        if (m >= n_here) continue;
+        v[r] = make_uint4(0u, 0u, 0u, 0u);
+        if (q >= kPieces || m >= n_here) continue;
         int mx = mx0 + m, my = my0;
         while (mx >= J.mcu_w) { mx -= J.mcu_w; my++; }
         const int x0 = mx * 16 + quad * 4, y = min(my * 16 + row, ymax);
         const uint8_t *rowp = J.rgba + (size_t)y * (size_t)J.rgba_pitch;
-        uint32_t *d = sm.px + row * DCT_ROW_WORDS + m * 17 + quad * 4;
         if (x0 + 3 <= xmax) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rowp + (size_t)x0 * 4));
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            v[r] = __ldg(reinterpret_cast<const uint4 *>(rowp + (size_t)x0 * 4));
         } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++) d[k] = __ldg(reinterpret_cast<const uint32_t *>(rowp + (size_t)min(x0 + k, xmax) * 4));
+            v[r].x = __ldg(reinterpret_cast<const uint32_t *>(rowp + (size_t)min(x0, xmax) * 4));
+            v[r].y = __ldg(reinterpret_cast<const uint32_t *>(rowp + (size_t)min(x0 + 1, xmax) * 4));
+            v[r].z = __ldg(reinterpret_cast<const uint32_t *>(rowp + (size_t)min(x0 + 2, xmax) * 4));
+            v[r].w = __ldg(reinterpret_cast<const uint32_t *>(rowp + (size_t)min(x0 + 3, xmax) * 4));
         }
+    }
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) {
+        const int q = threadIdx.x + r * 192;
+        if (q >= kPieces) continue;
+        const int row = q >> 7, m = (q >> 2) & 31, quad = q & 3;
+        uint32_t *d = sm.px + row * DCT_ROW_WORDS + m * 17 + quad * 4;
+        d[0] = v[r].x; d[1] = v[r].y; d[2] = v[r].z; d[3] = v[r].w;
     }
     __syncthreads();
     const int blk = threadIdx.x >> 5, m = threadIdx.x & 31;
@@ -124,7 +145,8 @@ __global__ void __launch_bounds__(192) k_jpeg_dct(const JpegJob *__restrict__ jo
         const uint32_t *cw = sm.cmean[blk - 4] + m * 17;
         jpeg_chroma_block(b, [cw](int k) { return cw[k]; });
     }
-    jpeg_block_code(b, sm.half[q], sm.recip[q], sm.lut_ac[q], J.acs + jpeg_slot_index(mcu, blk), JPEG_SLOT_STRIDE, J.side + (size_t)mcu * 6 + blk);
+    jpeg_block_code(b, sm.half[q], sm.recip[q], sm.lut_ac[q], J.acs + jpeg_slot_index(mcu, blk), JPEG_SLOT_STRIDE, J.side + (size_t)mcu * 6 + blk,
+                    CoefSmem{sm.coef[0] + threadIdx.x});
 }
 
 // ---- k_jpeg_offsets -------------------------------------------------------------------------------------------------
@@ -167,7 +189,7 @@ __global__ void __launch_bounds__(JPEG_STUFF_THREADS) k_jpeg_zero(const JpegJob 
     if (J.result[1]) return;
     const uint32_t n16 = (J.result[2] + JPEG_CHUNK - 1) / JPEG_CHUNK * (JPEG_CHUNK / 16); // whole chunks: the stuffing passes read them
     uint4 *w = reinterpret_cast<uint4 *>(J.words);
-    for (uint32_t k = it.part * JPEG_STUFF_THREADS + threadIdx.x; k < n16; k += JPEG_STUFF_PARTS * JPEG_STUFF_THREADS)
+    for (uint32_t k = it.part * JPEG_STUFF_THREADS + threadIdx.x; k < n16; k += it.nparts * JPEG_STUFF_THREADS)
         w[k] = make_uint4(0u, 0u, 0u, 0u);
 }
 
@@ -215,7 +237,7 @@ __global__ void __launch_bounds__(JPEG_STUFF_THREADS) k_jpeg_ffcount(const JpegJ
     if (J.result[1]) return;
     const uint32_t U = J.result[2], n_chunks = (U + JPEG_CHUNK - 1) / JPEG_CHUNK;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t c = it.part * (JPEG_STUFF_THREADS / 32) + warp; c < n_chunks; c += JPEG_STUFF_PARTS * (JPEG_STUFF_THREADS / 32)) {
+    for (uint32_t c = it.part * (JPEG_STUFF_THREADS / 32) + warp; c < n_chunks; c += it.nparts * (JPEG_STUFF_THREADS / 32)) {
         const uint4 v = *reinterpret_cast<const uint4 *>(J.words + (size_t)c * (JPEG_CHUNK / 4) + lane * 4); // zero past the scan
         const uint32_t n = warp_sum(ff_bytes(v.x) + ff_bytes(v.y) + ff_bytes(v.z) + ff_bytes(v.w));
         if (lane == 0) J.chunk_off[c] = n;
@@ -259,7 +281,7 @@ __global__ void __launch_bounds__(JPEG_STUFF_THREADS) k_jpeg_write(const JpegJob
             J.out[len - 1] = 0xd9;
         }
     }
-    for (uint32_t c = it.part * (JPEG_STUFF_THREADS / 32) + warp; c < n_chunks; c += JPEG_STUFF_PARTS * (JPEG_STUFF_THREADS / 32)) {
+    for (uint32_t c = it.part * (JPEG_STUFF_THREADS / 32) + warp; c < n_chunks; c += it.nparts * (JPEG_STUFF_THREADS / 32)) {
         const uint4 v = *reinterpret_cast<const uint4 *>(J.words + (size_t)c * (JPEG_CHUNK / 4) + lane * 4);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         const uint32_t n = ff_bytes(v.x) + ff_bytes(v.y) + ff_bytes(v.z) + ff_bytes(v.w);

@@ -16,11 +16,11 @@ enum {
     JPEG_DCT_MCUS = 32,      // MCUs per k_jpeg_dct / k_jpeg_emit CTA (6 warps: one per block of the MCU); = JPEG_SLOT_STRIDE
     JPEG_SCAN_THREADS = 1024,
     JPEG_STUFF_THREADS = 256,
-    JPEG_STUFF_PARTS = 64,   // k_jpeg_ffcount / k_jpeg_write CTAs per job (each strides over the job's chunks)
+    JPEG_STUFF_PARTS = 512,  // at most this many k_jpeg_zero / k_jpeg_ffcount / k_jpeg_write CTAs per job (each strides over the job's chunks)
 };
 
 struct JpegDctItem { int32_t job; int32_t mcu0; };   // JPEG_DCT_MCUS MCUs starting at mcu0 (k_jpeg_dct and k_jpeg_emit)
-struct JpegStuffItem { int32_t job; int32_t part; }; // part of JPEG_STUFF_PARTS
+struct JpegStuffItem { int32_t job; int16_t part, nparts; }; // CTA `part` of the job's `nparts`
 
 // host helpers (jpeg_host.cpp)
 void jpeg_build_tables(int quality, JpegTables *t);

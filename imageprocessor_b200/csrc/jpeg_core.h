@@ -131,6 +131,14 @@ IPG_HD uint32_t jpeg_umulhi(uint32_t a, uint32_t b)
     return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
 #endif
 }
+IPG_HD int jpeg_ctz64(uint64_t a) // a != 0
+{
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)a) - 1;
+#else
+    return __builtin_ctzll(a);
+#endif
+}
 IPG_HD uint32_t jpeg_nbits(uint32_t a) // bitCount: bits needed for a (0 for 0)
 {
 #if defined(__CUDA_ARCH__)
@@ -234,40 +242,46 @@ IPG_UNROLL
 // FDCT + quantisation + AC entropy coding of one block whose 64 samples are in b: the AC bitstring to the block's slot,
 // (dc | AC bits << 16) to *side.  half / recip: the block's quantiser rows (luminance or chrominance); lut_ac: its AC
 // Huffman table.
+template <typename CoefStore>
 IPG_HD void jpeg_block_code(int32_t *b, const int32_t *half, const uint32_t *recip, const uint32_t *lut_ac, uint32_t *acs, int acs_stride,
-                            uint32_t *side)
+                            uint32_t *side, CoefStore coef)
 {
     jpeg_fdct(b);
-    int16_t c[64];
-#define IPG_JPEG_Q(zig, nat) c[zig] = (int16_t)jpeg_quant(b[nat], half[zig], recip[zig]);
+    // Quantise in zig-zag order.  The non-zero AC coefficients go to `coef` (the kernel: shared memory, transposed) and
+    // into a 63-bit map, so that the entropy coder below is a loop over the set bits -- as many rounds as the block has
+    // non-zero coefficients, not 63 -- and its code stays small (the fully unrolled form thrashed the instruction cache).
+    uint64_t nz = 0;
+    int dc = 0;
+#define IPG_JPEG_Q(zig, nat)                                                                                                    \
+    {                                                                                                                             \
+        const int v = jpeg_quant(b[nat], half[zig], recip[zig]);                                                                  \
+        if (zig == 0) dc = v;                                                                                                     \
+        else if (v != 0) { coef.set(zig, v); nz |= (uint64_t)1 << zig; }                                                          \
+    }
     IPG_JPEG_ZIGZAG(IPG_JPEG_Q)
 #undef IPG_JPEG_Q
-    // The AC coefficients are entropy-coded right here, while they sit in registers, into this block's private slot: only
-    // the DC code depends on another block (the predictor), so k_jpeg_emit later writes that code and shift-copies the
-    // slot's bits to the block's place in the scan.
+    // The AC coefficients are entropy-coded right here into this block's private slot: only the DC code depends on
+    // another block (the predictor), so k_jpeg_emit later writes that code and shift-copies the slot's bits to the
+    // block's place in the scan.
     JpegSlotWriter sw{acs, acs_stride, 0, 0, 0};
-    {
-        int run = 0;
-IPG_UNROLL
-        for (int zig = 1; zig < 64; zig++) {
-            const int v = c[zig];
-            if (v == 0) {
-                run++;
-            } else {
-                while (run > 15) { // ZRL
-                    sw.put(lut_ac[0xf0] & 0xffffff, lut_ac[0xf0] >> 24);
-                    run -= 16;
-                }
-                const uint32_t nb = jpeg_nbits((uint32_t)(v < 0 ? -v : v));
-                const uint32_t x = lut_ac[run << 4 | nb];
-                sw.put((x & 0xffffff) << nb | ((uint32_t)(v < 0 ? v - 1 : v) & ((1u << nb) - 1)), (x >> 24) + nb); // <= 16 + 10 bits
-                run = 0;
-            }
+    int prev = 0;
+    while (nz) {
+        const int zig = jpeg_ctz64(nz);
+        nz &= nz - 1;
+        int run = zig - prev - 1;
+        prev = zig;
+        const int v = coef.get(zig);
+        while (run > 15) { // ZRL
+            sw.put(lut_ac[0xf0] & 0xffffff, lut_ac[0xf0] >> 24);
+            run -= 16;
         }
-        if (run > 0) sw.put(lut_ac[0x00] & 0xffffff, lut_ac[0x00] >> 24); // EOB
+        const uint32_t nb = jpeg_nbits((uint32_t)(v < 0 ? -v : v));
+        const uint32_t x = lut_ac[run << 4 | nb];
+        sw.put((x & 0xffffff) << nb | ((uint32_t)(v < 0 ? v - 1 : v) & ((1u << nb) - 1)), (x >> 24) + nb); // <= 16 + 10 bits
     }
+    if (prev != 63) sw.put(lut_ac[0x00] & 0xffffff, lut_ac[0x00] >> 24); // EOB
     sw.finish();
-    *side = (uint32_t)(uint16_t)c[0] | sw.total << 16; // total <= 63 * 26 bits
+    *side = (uint32_t)(uint16_t)dc | sw.total << 16; // total <= 63 * 26 bits
 }
 
 // DC predictor of block `blk` of the MCU whose six side words start at side[mi * 6]: the previous block of the same

@@ -50,7 +50,14 @@ extern "C" long jpeg_emu_encode(const uint8_t *rgba, int pitch, int w, int h, in
                 const uint32_t *cw = cmean[blk - 4];
                 jpeg_chroma_block(b, [cw](int k) { return cw[k]; });
             }
-            jpeg_block_code(b, T.half[q], T.recip[q], T.lut[2 * q + 1], J.acs + jpeg_slot_index(m, blk), JPEG_SLOT_STRIDE, J.side + (size_t)m * 6 + blk);
+            struct CoefLocal {
+                int16_t *c;
+                void set(int zig, int v) { c[zig] = (int16_t)v; }
+                int get(int zig) const { return c[zig]; }
+            };
+            int16_t cbuf[64];
+            jpeg_block_code(b, T.half[q], T.recip[q], T.lut[2 * q + 1], J.acs + jpeg_slot_index(m, blk), JPEG_SLOT_STRIDE, J.side + (size_t)m * 6 + blk,
+                            CoefLocal{cbuf});
         }
     }
     // k_jpeg_offsets
