@@ -407,15 +407,27 @@ class HostRing:
     soon as its previous ticket is done, so the K steps run as one stream of submissions (a worker does not drain its
     pipeline between batches).  Every submission, copy and completion lies inside the caller's timed region."""
 
-    def __init__(self, lib, L, eng, geo, host_images, n_slots, n_dev, inplace=False, ycbcr=False):
+    def __init__(self, lib, L, eng, geo, host_images, n_slots, n_dev, inplace=False, ycbcr=False, jpeg=False):
         """inplace: the watermark is requested with IPG_OPF_WATERMARK_PATCH_ONLY into the SOURCE buffer itself (an
         *image.RGBA's watermark differs from its source only inside the glyph box): no separate result frame exists."""
         self.lib, self.L, self.ctx, self.geo, self.n_dev, self.inplace = lib, L, eng._ctx, geo, n_dev, inplace
-        self.pins, self.descs, self.ops = [], [], []
+        self.pins, self.descs, self.ops, self.lens = [], [], [], []
         for s in range(n_slots * n_dev):
             p_in = eng.alloc_pinned(geo.src_bytes)
             p_in.array[:] = host_images[s % len(host_images)].reshape(-1)
             self.descs.append(geo.desc(p_in.ptr, L.MEM_HOST))
+            if jpeg:    # every result as the JPEG file jpeg.Encode(q85) would write, encoded on the device (IPG_LAYOUT_JPEG)
+                dims = [(geo.nw, geo.nh), (THUMB, THUMB), (geo.w, geo.h)]
+                files = [eng.alloc_pinned(dw * dh + 65536) for (dw, dh) in dims]   # 1 byte per pixel: noise needs 0.76
+                lens = (C.c_uint64 * 3)()
+                self.pins += [p_in] + files
+                self.lens.append(lens)
+                ops = geo.ops(files[0].ptr, files[1].ptr, files[2].ptr, L.MEM_HOST)
+                for k in range(3):
+                    ops[k].dst_layout, ops[k].jpeg_quality, ops[k].dst_capacity = L.JPEG, 85, files[k].nbytes
+                    ops[k].dst_len = C.cast(C.byref(lens, 8 * k), C.POINTER(C.c_uint64))
+                self.ops.append(ops)
+                continue
             if ycbcr:   # every result as the planar 4:2:0 image Go's jpeg writer derives (ipg_op.dst_layout): 1.5 B per pixel back
                 dims = [(geo.nw, geo.nh), (THUMB, THUMB), (geo.w, geo.h)]
                 planes = [[eng.alloc_pinned(dw * dh), eng.alloc_pinned(((dw + 1) // 2) * ((dh + 1) // 2)),
@@ -473,6 +485,16 @@ class HostRing:
                 ok = ok and bool(np.array_equal(self.pins[k].array.reshape(want.shape), want))
                 k += 1
         return ok
+
+    def verify_jpeg_slot0(self, O):
+        """Slot 0's three files against the oracle's restatement of Go's jpeg.Encode(q85) applied to the oracle's RGBA results."""
+        g = self.geo
+        a = self.pins[0].array.reshape(g.h, g.w, 4)
+        ok = True
+        for k, rgba in enumerate(g.oracle_outputs(O, a)):
+            n = int(self.lens[0][k])
+            ok = ok and self.pins[1 + k].array[:n].tobytes() == O.jpeg_encode_rgba(rgba, 85)
+        return bool(ok)
 
     def verify_slot0(self, O):
         g = self.geo
@@ -659,6 +681,28 @@ def config_c5(ip, rank, world, local_rank, barrier, max_over_ranks, sum_over_ran
     n_objects = len(repo.objects)
     proc.close()
 
+    # pass C / D: the same worker loop with the JPEG-bound results encoded on the device (iph_set_device_jpeg, opt-in):
+    # C keeps the reference's format rule (jpeg source -> jpeg, png -> png: the PNG half still pays the host encoder),
+    # D sets task.Format = "jpeg" (every output a JPEG, as a client may ask: resize.go:78-91), so no host encoder runs at all
+    def device_jpeg_pass(fmt):
+        repoX = P.MemoryFileRepo()
+        procX = P.ImageProcessor(eng, repoX, encode=lambda a, f, q: codecs.encode(a, f, q), device_jpeg=True)
+        wkX = StreamingWorker(procX, threads)
+        m = [(dict(task(i), Format=fmt), files[i]) for i in range(n)]
+        wkX.run(m[2:2 + min(6, n - 2)])
+        barrier()
+        eng.reset_stats()
+        sX = wkX.run(m)
+        eng.flush()
+        barrier()
+        stX = eng.stats()
+        wallX = max_over_ranks(sX.wall_s)
+        procX.close()
+        return sX, stX, wallX
+
+    sC, stC, wallC = device_jpeg_pass("")
+    sD, stD, wallD = device_jpeg_pass("jpeg")
+
     # pass B: raster only -- the same stream, already decoded (decode outside the timed region), outputs not encoded:
     # what H2D + kernels + D2H cost end to end for this mix
     decoded = [codecs.decode(f) for f in files]
@@ -683,7 +727,9 @@ def config_c5(ip, rank, world, local_rank, barrier, max_over_ranks, sum_over_ran
         sample = [0, 1, 2, 3, 5, 6]              # 48 MP jpeg, 0.3 MP png, and one of each kind from the random part
         repoV = P.MemoryFileRepo()
         procV = P.ImageProcessor(eng, repoV, encode=P.raw_encode)
-        verified = {"images": [], "all_bit_exact": True}
+        repoJ = P.MemoryFileRepo()
+        procJ = P.ImageProcessor(eng, repoJ, encode=P.raw_encode, device_jpeg=True)   # JPEG-bound results as device-encoded files
+        verified = {"images": [], "all_bit_exact": True, "device_jpeg_files_byte_identical": True}
         for i in [k for k in sample if k < n]:
             img, fmt = decoded[i]
             res, err = procV.process(task(i), img, fmt)
@@ -704,13 +750,21 @@ def config_c5(ip, rank, world, local_rank, barrier, max_over_ranks, sum_over_ran
                         px, py = P.watermark_anchor("bottom-right", img.width, img.height, wpx, P.watermark_height_px(36.0))
                         gl = O.drawstring_layout(procV.face, WM_TEXT, 36.0, img.width, img.height, px, py)
                         want_w = O.watermark(R, (255, 255, 255, 127), [O.Glyph(*g) for g in gl])
+                        want["watermark"] = want_w
                         ok = ok and bool(np.array_equal(got, want_w))
                     else:
                         ok = ok and bool(np.array_equal(got, want[op]))
                 ok = ok and len(res["ProcessedPaths"]) == 3
+                if ok and fmt == "jpeg":   # the same task through the device JPEG writer: objects == jpeg.Encode(q85) of the oracle results
+                    resJ, errJ = procJ.process(task(i), img, fmt)
+                    okJ = errJ is None and all(repoJ.objects[path][0] == O.jpeg_encode_rgba(want[op], 85)
+                                                for op, path in resJ["ProcessedPaths"].items())
+                    verified["device_jpeg_files_byte_identical"] = verified["device_jpeg_files_byte_identical"] and bool(okJ)
+                    repoJ.objects.clear()
             verified["images"].append({"index": i, "size": f"{img.width}x{img.height}", "kind": spec[i][2], "bit_exact": bool(ok)})
             verified["all_bit_exact"] = verified["all_bit_exact"] and bool(ok)
         procV.close()
+        procJ.close()
     eng.close()
 
     mp = sum(w * h for (w, h, _, _) in spec) / 1e6
@@ -736,6 +790,10 @@ def config_c5(ip, rank, world, local_rank, barrier, max_over_ranks, sum_over_ran
         "codecs": "PIL stand-ins on the host (libjpeg-turbo q85; libpng compress_level=1 -- Go's png.Encode default is zlib 6), timed apart "
                   "from the raster work; outputs follow the reference's format rule (jpeg source -> jpeg, png -> png)",
         "end_to_end_with_codecs": leg(sA, stA, wallA),
+        "end_to_end_device_jpeg_encode": dict(leg(sC, stC, wallC), what="as above with iph_set_device_jpeg: the JPEG-bound half of the "
+                                             "outputs is encoded on the device (bit for bit Go's jpeg.Encode q85); the PNG half still pays the host encoder"),
+        "end_to_end_device_jpeg_encode_all_targets_jpeg": dict(leg(sD, stD, wallD), what="task.Format = \"jpeg\": every output is a JPEG and "
+                                                              "none is encoded on the host; decode remains"),
         "raster_only_decoded_inputs_no_encode": leg(sB, stB, wallB),
         "objects_saved_rank0": n_objects, "setup_s_untimed": setup_s, "verified": verified,
     }
@@ -990,6 +1048,36 @@ def main():
             "h2d_GBps_aggregate": sum_over_ranks(st4["bytes_h2d"]) / wall4 / 1e9,
             "d2h_GBps_aggregate": sum_over_ranks(st4["bytes_d2h"]) / wall4 / 1e9,
             "verified_slot0_all_planes": ok_ycc,
+        }
+        # ---- and with every result returned as the JPEG FILE the reference would encode from it (opt-in IPG_LAYOUT_JPEG, SURVEY
+        # 8f-3 encode half): the device runs Go's baseline writer (q85) bit for bit; H2D unchanged, D2H = the files, no host encode
+        ring = HostRing(lib, L, eng, geo, host_imgs, min(n_slots, 32), n_dev, jpeg=True)
+        ring.run(n_img * n_dev)
+        barrier()
+        eng.reset_stats()
+        t0 = time.perf_counter()
+        ring.run(args.steps * n_img * n_dev)
+        eng.flush()
+        barrier()
+        wall5 = max_over_ranks(time.perf_counter() - t0)
+        st5 = eng.stats()
+        ok_jpeg = None
+        if rank == 0 and not args.no_verify:
+            from oracle import oracle as O
+            ok_jpeg = ring.verify_jpeg_slot0(O)
+        file_bytes = [int(x) for x in ring.lens[0]]
+        ring.free()
+        e2e["results_as_jpeg_files"] = {
+            "value": total_images / wall5, "unit": "images/s",
+            "what": "ipg_op.dst_layout = JPEG on all three ops: the engine returns jpeg.Encode(result, Quality 85) itself -- Go 1.24's "
+                    "baseline writer reproduced bit for bit on the device (k_jpeg_*), so the reference's host encode step disappears; "
+                    "the synthetic sources are random bytes, the worst case for the file size (a photograph is ~4x smaller)",
+            "h2d_bytes_per_step": int(st5["bytes_h2d"] / args.steps), "d2h_bytes_per_step": int(st5["bytes_d2h"] / args.steps),
+            "h2d_GBps_aggregate": sum_over_ranks(st5["bytes_h2d"]) / wall5 / 1e9,
+            "d2h_GBps_aggregate": sum_over_ranks(st5["bytes_d2h"]) / wall5 / 1e9,
+            "file_bytes_slot0": {"resize": file_bytes[0], "thumbnail": file_bytes[1], "watermark": file_bytes[2]},
+            "kernel_ms_after_stream_and_fix_per_image (blend + the JPEG writer)": st5["other_kernel_ms"] / max(args.steps * n_img * n_dev, 1),
+            "verified_slot0_all_files_byte_identical": ok_jpeg,
         }
     clocks = sampler.stop()   # sampled across the device-resident AND the end-to-end leg
 

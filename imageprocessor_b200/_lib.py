@@ -83,7 +83,7 @@ EXPORTS = [
 ]
 # ... and include/ipgpu_host.h
 HOST_EXPORTS = [
-    "iph_processor_new", "iph_processor_free", "iph_process", "iph_process_batch", "iph_free", "iph_last_error",
+    "iph_processor_new", "iph_processor_free", "iph_set_device_jpeg", "iph_process", "iph_process_batch", "iph_free", "iph_last_error",
     "iph_parse_color", "iph_watermark_height_px", "iph_watermark_anchor", "iph_generate_path", "iph_content_type",
 ]
 

@@ -456,6 +456,8 @@ struct PlannedOp {
     std::vector<ipg_glyph> glyph_arr;
     uint8_t *dst = nullptr; // pinned
     size_t dst_bytes = 0;
+    bool jpeg_dev = false;  // the engine returns this result as the JPEG file (iph_set_device_jpeg): dst holds the file
+    uint64_t jpeg_len = 0;  // ... of this many bytes once the ticket is done
 };
 
 } // namespace
@@ -558,6 +560,8 @@ struct iph_processor {
     ipg_ctx *ctx = nullptr;
     iph_callbacks cb{};
     PinnedSlabs pinned; // output buffers, reused across calls
+    bool device_jpeg = false; // iph_set_device_jpeg
+    int jpeg_first_div = 1;   // first-attempt file buffer = pixels / this + 4096 bytes (IPH_JPEG_FIRST_DIV: tests force the retry with it)
     uint8_t *take_pinned(size_t n) { return pinned.take(ctx, n); }
     void give_pinned(uint8_t *p) { pinned.give(ctx, p); }
 };
@@ -574,6 +578,7 @@ struct Job { // one ProcessingTask in flight
     bool submitted = false;
     ipg_ticket ticket = 0;
     std::string fatal;          // error returned by Process
+    const ipg_image_desc *img = nullptr; // the decoded image (the caller's, valid for the duration of the call)
 };
 
 static void format_switch(const std::string &format, bool watermark, std::string &out_format)
@@ -743,6 +748,57 @@ static void job_fail(Job &j, const std::string &result_error, const std::string 
     j.fatal = err;
 }
 
+// Destination buffers + ipg_submit of a planned task.  With iph_set_device_jpeg, results whose target format is JPEG
+// are requested as files (IPG_LAYOUT_JPEG, quality 85 = domain/task.go:57): 1 byte per pixel of room is ample for
+// photographs (noise needs 0.8-0.95); `roomy` (the retry after a file did not fit) gives 8, more than any scan can take.
+static void submit_job(iph_processor *P, Job &j, bool roomy)
+{
+    std::vector<ipg_op> arr;
+    for (auto &po : j.ops) {
+        po.jpeg_dev = P->device_jpeg && po.out_format == "jpeg" && po.dw > 0 && po.dh > 0 && po.dw < 65536 && po.dh < 65536;
+        const size_t px = (size_t)std::max(po.dw, 0) * (size_t)std::max(po.dh, 0);
+        po.dst_bytes = po.jpeg_dev ? (roomy ? px * 8 : px / (size_t)P->jpeg_first_div) + 4096 : px * 4;
+        if (po.dst_bytes) {
+            po.dst = P->take_pinned(po.dst_bytes);
+            if (!po.dst) {
+                j.plan_err_type = po.type;
+                j.plan_err = "failed to process operation " + po.type + ": " + ipg_last_error();
+                break;
+            }
+        }
+        po.op.dst_w = po.dw;
+        po.op.dst_h = po.dh;
+        po.op.dst = po.dst;
+        po.op.dst_stride = (int32_t)((size_t)po.dw * 4); // dw <= 65536: fits
+        po.op.dst_memspace = IPG_MEM_HOST;
+        if (po.jpeg_dev) {
+            po.op.dst_layout = IPG_LAYOUT_JPEG;
+            po.op.jpeg_quality = 85;
+            po.op.dst_capacity = po.dst_bytes;
+            po.jpeg_len = 0;
+            po.op.dst_len = &po.jpeg_len; // j.ops is not resized while the ticket is in flight
+        }
+        po.glyph_arr.clear();
+        for (auto &g : po.glyphs) po.glyph_arr.push_back(g.g);
+        po.op.n_glyphs = (int)po.glyph_arr.size();
+        po.op.glyphs = po.glyph_arr.data();
+        arr.push_back(po.op);
+    }
+    if (arr.size() != j.ops.size()) { // allocation failed part-way: nothing of this task runs
+        for (auto &po : j.ops) { P->give_pinned(po.dst); po.dst = nullptr; }
+        j.ops.clear();
+        return;
+    }
+    if (ipg_submit(P->ctx, j.img, arr.data(), (int)arr.size(), &j.ticket) != IPG_OK) {
+        j.plan_err_type = j.ops[0].type;
+        j.plan_err = "failed to process operation " + j.ops[0].type + ": " + ipg_last_error();
+        for (auto &po : j.ops) { P->give_pinned(po.dst); po.dst = nullptr; }
+        j.ops.clear();
+        return;
+    }
+    j.submitted = true;
+}
+
 // Process up to and including the submission of the raster work
 static void job_begin(iph_processor *P, Job &j, const char *task_json, const ipg_image_desc *img, const char *decoded_format,
                       const char *decode_error)
@@ -781,41 +837,8 @@ static void job_begin(iph_processor *P, Job &j, const char *task_json, const ipg
         j.ops.clear();
         return;
     }
-    std::vector<ipg_op> arr;
-    for (auto &po : j.ops) {
-        po.dst_bytes = (size_t)std::max(po.dw, 0) * 4 * (size_t)std::max(po.dh, 0);
-        if (po.dst_bytes) {
-            po.dst = P->take_pinned(po.dst_bytes);
-            if (!po.dst) {
-                j.plan_err_type = po.type;
-                j.plan_err = "failed to process operation " + po.type + ": " + ipg_last_error();
-                break;
-            }
-        }
-        po.op.dst_w = po.dw;
-        po.op.dst_h = po.dh;
-        po.op.dst = po.dst;
-        po.op.dst_stride = (int32_t)((size_t)po.dw * 4); // dw <= 65536: fits
-        po.op.dst_memspace = IPG_MEM_HOST;
-        po.glyph_arr.clear();
-        for (auto &g : po.glyphs) po.glyph_arr.push_back(g.g);
-        po.op.n_glyphs = (int)po.glyph_arr.size();
-        po.op.glyphs = po.glyph_arr.data();
-        arr.push_back(po.op);
-    }
-    if (arr.size() != j.ops.size()) { // allocation failed part-way: nothing of this task runs
-        for (auto &po : j.ops) P->give_pinned(po.dst);
-        j.ops.clear();
-        return;
-    }
-    if (ipg_submit(P->ctx, img, arr.data(), (int)arr.size(), &j.ticket) != IPG_OK) {
-        j.plan_err_type = j.ops[0].type;
-        j.plan_err = "failed to process operation " + j.ops[0].type + ": " + ipg_last_error();
-        for (auto &po : j.ops) P->give_pinned(po.dst);
-        j.ops.clear();
-        return;
-    }
-    j.submitted = true;
+    j.img = img;
+    submit_job(P, j, false);
 }
 
 // wait for the raster work, then encode + SaveProcessed per operation in task order
@@ -823,13 +846,33 @@ static void job_finish(iph_processor *P, Job &j)
 {
     if (!j.fatal.empty()) return;
     std::string raster_err;
-    if (j.submitted && ipg_wait(P->ctx, j.ticket, -1) != IPG_OK) raster_err = ipg_last_error();
+    if (j.submitted) {
+        int rc = ipg_wait(P->ctx, j.ticket, -1);
+        bool any_jpeg = false;
+        for (auto &po : j.ops) any_jpeg |= po.jpeg_dev;
+        if (rc == IPG_ERR_NOMEM && any_jpeg) { // a file did not fit its buffer (not a photograph): once more with room for any scan
+            for (auto &po : j.ops) { P->give_pinned(po.dst); po.dst = nullptr; }
+            j.submitted = false;
+            submit_job(P, j, true);
+            rc = j.submitted ? ipg_wait(P->ctx, j.ticket, -1) : IPG_OK;
+        }
+        if (rc != IPG_OK) raster_err = ipg_last_error();
+    }
     for (auto &po : j.ops) {
         if (!j.fatal.empty()) break;
         if (!raster_err.empty()) {
             const std::string e = "failed to process operation " + po.type + ": " + raster_err;
             job_fail(j, "Operation " + po.type + " failed: " + e, "operation " + po.type + " failed: " + e);
             break;
+        }
+        if (po.jpeg_dev) { // jpeg.Encode already happened on the device: dst holds the file
+            const int rc = P->cb.save_processed ? P->cb.save_processed(P->cb.user, po.path.c_str(), po.dst, (size_t)po.jpeg_len, content_type(po.path)) : -1;
+            if (rc != 0) {
+                job_fail(j, "Failed to save processed image: save failed", "failed to save processed image: save failed");
+                break;
+            }
+            j.res.paths[po.type] = po.path;
+            continue;
         }
         uint8_t *enc = nullptr;
         size_t enc_len = 0;
@@ -869,6 +912,14 @@ iph_processor *iph_processor_new(ipg_ctx *ctx, const iph_callbacks *cb)
     p->ctx = ctx;
     if (cb) p->cb = *cb;
     return p;
+}
+
+int iph_set_device_jpeg(iph_processor *p, int enabled)
+{
+    if (!p) return -1;
+    p->device_jpeg = enabled != 0;
+    if (const char *e = getenv("IPH_JPEG_FIRST_DIV")) p->jpeg_first_div = std::max(1, atoi(e));
+    return 0;
 }
 
 void iph_processor_free(iph_processor *p)

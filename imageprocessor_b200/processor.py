@@ -51,6 +51,7 @@ def _host_lib():
     lib.iph_processor_new.restype = vp
     lib.iph_processor_free.argtypes = [vp]
     lib.iph_processor_free.restype = None
+    lib.iph_set_device_jpeg.argtypes = [vp, C.c_int]
     lib.iph_process.argtypes = [vp, C.c_char_p, C.POINTER(L.ImageDesc), C.c_char_p, C.c_char_p, C.POINTER(vp)]
     lib.iph_process_batch.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(L.ImageDesc), C.POINTER(C.c_char_p),
                                       C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(vp)]
@@ -174,7 +175,10 @@ class PilFace:
 class ImageProcessor:
     """processor.ImageProcessor (image_processor.go:21-37): Process(task, decoded image)."""
 
-    def __init__(self, engine: Optional[Engine], file_repo: MemoryFileRepo, encode=pil_encode, face: Optional[PilFace] = None):
+    def __init__(self, engine: Optional[Engine], file_repo: MemoryFileRepo, encode=pil_encode, face: Optional[PilFace] = None,
+                 device_jpeg: bool = False):
+        """device_jpeg: JPEG-bound results are encoded on the device exactly as Go's jpeg.Encode(q85) would (opt-in,
+        iph_set_device_jpeg); `encode` then only sees PNG / GIF targets."""
         self._lib = _host_lib()
         self.file_repo = file_repo
         self.encode = encode
@@ -233,6 +237,8 @@ class ImageProcessor:
         self._p = self._lib.iph_processor_new(engine._ctx if engine else None, C.byref(self._cbs))
         if not self._p:
             raise MemoryError("iph_processor_new failed")
+        if device_jpeg:
+            self._lib.iph_set_device_jpeg(self._p, 1)
 
     def close(self):
         if self._p:

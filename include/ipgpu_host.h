@@ -74,6 +74,11 @@ typedef struct {
  * fails with "no raster engine" -- there is no CPU fallback. */
 IPG_API iph_processor *iph_processor_new(ipg_ctx *ctx, const iph_callbacks *cb);
 IPG_API void iph_processor_free(iph_processor *p);
+/* Opt-in (encode half; off by default): results whose target format is JPEG -- format_switch of
+ * resize.go:78-91 / thumbnail.go:68-81 / watermark.go:66-79 -- are encoded on the device as
+ * jpeg.Encode(buf, img, &jpeg.Options{Quality: 85}) would encode them (ipg_op.dst_layout = IPG_LAYOUT_JPEG) and go
+ * straight to save_processed; the encode callback is then called for PNG and GIF targets only.  Returns 0. */
+IPG_API int iph_set_device_jpeg(iph_processor *p, int enabled);
 
 /* ImageProcessor.Process on an already decoded image.  task_json is the broker message
  * value (ProcessingTask); decoded_format what image.Decode returned ("jpeg", "png", "gif").

@@ -272,3 +272,42 @@ def test_process_batch_is_the_batching_worker_loop(engines, oracle):
         _, got = P.raw_decode(repo.objects[f"processed/thumbnails/im{k}/200.jpeg"][0])
         assert np.array_equal(got, oracle.crop_and_resize(oracle.Raster.rgba(a), 200))
     proc.close()
+
+
+@pytest.mark.gpu
+def test_process_with_device_jpeg_saves_the_files_go_would_encode(engines, oracle, monkeypatch):
+    """iph_set_device_jpeg: JPEG-bound results skip the encode callback and are saved as the device writer produced them --
+    byte for byte jpeg.Encode(q85) of the oracle's raster result; PNG targets still go through the callback."""
+    import imageprocessor_b200 as ip
+    w, h = 1600, 1200
+    a = rgba_random(w, h, 78)
+    repo = P.MemoryFileRepo()
+    seen = []
+
+    def encode(rgba, fmt, quality):
+        seen.append(fmt)
+        return P.raw_encode(rgba, fmt, quality)
+
+    proc = P.ImageProcessor(engines(ip.PRECISION_EXACT), repo, encode=encode, device_jpeg=True)
+    res, err = proc.process(task(CANONICAL_OPS), ip.Image.from_rgba(a), "jpeg")
+    assert err is None and res["Status"] == "completed" and seen == []
+    R = oracle.Raster.rgba(a)
+    nw, nh = oracle.keep_aspect_dims(w, h, 1024, 768)
+    assert repo.objects["processed/resize/img-1/1024x768.jpeg"] == (oracle.jpeg_encode_rgba(oracle.resize_image(R, nw, nh), 85), "image/jpeg")
+    assert repo.objects["processed/thumbnails/img-1/200.jpeg"][0] == oracle.jpeg_encode_rgba(oracle.crop_and_resize(R, 200), 85)
+    face, text = proc.face, "© ImageProcessor"
+    width_px = (sum(face.advance_26_6(ord(c), 36.0) for c in text) + 63) >> 6
+    px, py = oracle.watermark_anchor("bottom-right", w, h, width_px, oracle.watermark_height_px(36.0))
+    gl = go_drawstring_layout(face, text, 36.0, w, h, px, py)
+    want = oracle.watermark(R, (255, 255, 255, 127), [oracle.Glyph(*g) for g in gl])
+    assert repo.objects["processed/watermarked/img-1/watermarked.jpeg"][0] == oracle.jpeg_encode_rgba(want, 85)
+    # a PNG target keeps the host encoder
+    res, err = proc.process(task([{"Type": "resize", "Parameters": {"width": 300, "height": 200}}], fmt="png"), ip.Image.from_rgba(a), "jpeg")
+    assert err is None and seen == ["png"]
+    proc.close()
+    # a file that does not fit the first buffer (forced: 1/16 byte per pixel) is retried with room for any scan
+    monkeypatch.setenv("IPH_JPEG_FIRST_DIV", "16")
+    proc = P.ImageProcessor(engines(ip.PRECISION_EXACT), repo, encode=encode, device_jpeg=True)
+    res, err = proc.process(task([{"Type": "watermark", "Parameters": {}}]), ip.Image.from_rgba(a), "jpeg")
+    assert err is None and repo.objects["processed/watermarked/img-1/watermarked.jpeg"][0] == oracle.jpeg_encode_rgba(want, 85)
+    proc.close()
