@@ -418,14 +418,15 @@ class HostRing:
             self.descs.append(geo.desc(p_in.ptr, L.MEM_HOST))
             if jpeg:    # every result as the JPEG file jpeg.Encode(q85) would write, encoded on the device (IPG_LAYOUT_JPEG)
                 dims = [(geo.nw, geo.nh), (THUMB, THUMB), (geo.w, geo.h)]
-                files = [eng.alloc_pinned(dw * dh + 65536) for (dw, dh) in dims]   # 1 byte per pixel: noise needs 0.76
-                lens = (C.c_uint64 * 3)()
+                caps = [(dw * dh + 65536) & ~7 for (dw, dh) in dims]               # 1 byte per pixel: noise needs 0.76
+                files = [eng.alloc_pinned(cap + 8) for cap in caps]                # ... + 8 bytes for the length (pinned too)
+                lens = [f.array[cap:cap + 8].view(np.uint64) for f, cap in zip(files, caps)]
                 self.pins += [p_in] + files
                 self.lens.append(lens)
                 ops = geo.ops(files[0].ptr, files[1].ptr, files[2].ptr, L.MEM_HOST)
                 for k in range(3):
-                    ops[k].dst_layout, ops[k].jpeg_quality, ops[k].dst_capacity = L.JPEG, 85, files[k].nbytes
-                    ops[k].dst_len = C.cast(C.byref(lens, 8 * k), C.POINTER(C.c_uint64))
+                    ops[k].dst_layout, ops[k].jpeg_quality, ops[k].dst_capacity = L.JPEG, 85, caps[k]
+                    ops[k].dst_len = C.cast(files[k].ptr + caps[k], C.POINTER(C.c_uint64))
                 self.ops.append(ops)
                 continue
             if ycbcr:   # every result as the planar 4:2:0 image Go's jpeg writer derives (ipg_op.dst_layout): 1.5 B per pixel back
@@ -492,7 +493,7 @@ class HostRing:
         a = self.pins[0].array.reshape(g.h, g.w, 4)
         ok = True
         for k, rgba in enumerate(g.oracle_outputs(O, a)):
-            n = int(self.lens[0][k])
+            n = int(self.lens[0][k][0])
             ok = ok and self.pins[1 + k].array[:n].tobytes() == O.jpeg_encode_rgba(rgba, 85)
         return bool(ok)
 
@@ -1065,7 +1066,7 @@ def main():
         if rank == 0 and not args.no_verify:
             from oracle import oracle as O
             ok_jpeg = ring.verify_jpeg_slot0(O)
-        file_bytes = [int(x) for x in ring.lens[0]]
+        file_bytes = [int(x[0]) for x in ring.lens[0]]
         ring.free()
         e2e["results_as_jpeg_files"] = {
             "value": total_images / wall5, "unit": "images/s",

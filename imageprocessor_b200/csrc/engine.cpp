@@ -1457,6 +1457,11 @@ static int submit_impl(Ctx *c, int dev_index, const ipg_image_desc *src, const i
             r.jpeg_quality = o.jpeg_quality == 0 ? 85 : std::min(100, std::max(1, (int)o.jpeg_quality));
             r.dst_capacity = (size_t)o.dst_capacity;
             r.dst_len = o.dst_len;
+            // both are written after ipg_submit returned (by the completer thread): the library keeps no caller pointer
+            // past the call unless it lies in its own pinned memory (cgo pointer rule)
+            if (!c->pinned.contains(o.dst_len, sizeof(uint64_t)) ||
+                (o.dst_memspace == IPG_MEM_HOST && !c->pinned.contains(o.dst, (size_t)o.dst_capacity)))
+                return fail(IPG_ERR_INVALID, "a JPEG destination and its dst_len must lie in ipg_alloc_pinned memory (dst may be device memory)");
         }
         if (r.ycc_out && o.dst_memspace == IPG_MEM_HOST && o.dst_w > 0 && o.dst_h > 0) {
             const int cw = (o.dst_w + 1) / 2, ch = (o.dst_h + 1) / 2;

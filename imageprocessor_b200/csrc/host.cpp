@@ -457,7 +457,7 @@ struct PlannedOp {
     uint8_t *dst = nullptr; // pinned
     size_t dst_bytes = 0;
     bool jpeg_dev = false;  // the engine returns this result as the JPEG file (iph_set_device_jpeg): dst holds the file
-    uint64_t jpeg_len = 0;  // ... of this many bytes once the ticket is done
+    uint64_t *jpeg_len_ptr = nullptr; // ... of *this many bytes once the ticket is done (the tail of dst)
 };
 
 } // namespace
@@ -757,7 +757,10 @@ static void submit_job(iph_processor *P, Job &j, bool roomy)
     for (auto &po : j.ops) {
         po.jpeg_dev = P->device_jpeg && po.out_format == "jpeg" && po.dw > 0 && po.dh > 0 && po.dw < 65536 && po.dh < 65536;
         const size_t px = (size_t)std::max(po.dw, 0) * (size_t)std::max(po.dh, 0);
-        po.dst_bytes = po.jpeg_dev ? (roomy ? px * 8 : px / (size_t)P->jpeg_first_div) + 4096 : px * 4;
+        // a device-encoded file: room for the file, then 8 bytes for its length (the engine writes both after ipg_submit
+        // returned, so both live in pinned memory)
+        const size_t file_cap = ((roomy ? px * 8 : px / (size_t)P->jpeg_first_div) + 4096 + 7) & ~(size_t)7;
+        po.dst_bytes = po.jpeg_dev ? file_cap + 8 : px * 4;
         if (po.dst_bytes) {
             po.dst = P->take_pinned(po.dst_bytes);
             if (!po.dst) {
@@ -774,9 +777,10 @@ static void submit_job(iph_processor *P, Job &j, bool roomy)
         if (po.jpeg_dev) {
             po.op.dst_layout = IPG_LAYOUT_JPEG;
             po.op.jpeg_quality = 85;
-            po.op.dst_capacity = po.dst_bytes;
-            po.jpeg_len = 0;
-            po.op.dst_len = &po.jpeg_len; // j.ops is not resized while the ticket is in flight
+            po.op.dst_capacity = file_cap;
+            po.jpeg_len_ptr = (uint64_t *)(po.dst + file_cap);
+            *po.jpeg_len_ptr = 0;
+            po.op.dst_len = po.jpeg_len_ptr;
         }
         po.glyph_arr.clear();
         for (auto &g : po.glyphs) po.glyph_arr.push_back(g.g);
@@ -866,7 +870,7 @@ static void job_finish(iph_processor *P, Job &j)
             break;
         }
         if (po.jpeg_dev) { // jpeg.Encode already happened on the device: dst holds the file
-            const int rc = P->cb.save_processed ? P->cb.save_processed(P->cb.user, po.path.c_str(), po.dst, (size_t)po.jpeg_len, content_type(po.path)) : -1;
+            const int rc = P->cb.save_processed ? P->cb.save_processed(P->cb.user, po.path.c_str(), po.dst, (size_t)*po.jpeg_len_ptr, content_type(po.path)) : -1;
             if (rc != 0) {
                 job_fail(j, "Failed to save processed image: save failed", "failed to save processed image: save failed");
                 break;

@@ -103,8 +103,9 @@ class OpSpec:
     # uint8 planes (Y h x w, Cb and Cr (h+1)//2 x (w+1)//2); the RGBA destination fields are then unused
     dst_ycbcr420: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None
     # the result as a JPEG file encoded on the device (ipg_op.dst_layout = IPG_LAYOUT_JPEG): quality as jpeg.Options.Quality
-    # (the reference uses 85).  The output is then a `JpegResult`; `jpeg_buffer` is an optional uint8 array to receive the
-    # file (PinnedBuffer-backed for speed), allocated when None; `jpeg_capacity` sizes the allocation (default w * h + 64 KiB)
+    # (the reference uses 85).  The output is then a `JpegResult`; `jpeg_buffer` is an optional PinnedBuffer-backed uint8
+    # array to receive the file (its last 8 bytes: the length), allocated when None; `jpeg_capacity` sizes that allocation
+    # (default w * h + 64 KiB)
     jpeg_quality: Optional[int] = None
     jpeg_buffer: Optional[np.ndarray] = None
     jpeg_capacity: Optional[int] = None
@@ -123,19 +124,30 @@ class OpSpec:
 
 
 class JpegResult:
-    """A result encoded on the device: `data` is the file once the ticket was waited for."""
+    """A result encoded on the device: `data` is the file once the ticket was waited for.  The engine writes the file and
+    its length after ipg_submit returned, so both live in ipg_alloc_pinned memory: `buffer` is a uint8 view of a
+    PinnedBuffer whose last 8 bytes (8-byte aligned) hold the length."""
 
-    def __init__(self, buffer: np.ndarray):
+    def __init__(self, buffer: np.ndarray, owner=None):
+        assert buffer.dtype == np.uint8 and buffer.ndim == 1 and buffer.size >= 1032 and buffer.ctypes.data % 8 == 0
+        self.capacity = (buffer.size - 8) & ~7
         self.buffer = buffer
-        self._len = C.c_uint64(0)
+        self._len = buffer[self.capacity:self.capacity + 8].view(np.uint64)
+        self._len[0] = 0
+        self._owner = owner   # a PinnedBuffer this result allocated itself (freed by free())
 
     @property
     def nbytes(self) -> int:
-        return int(self._len.value)
+        return int(self._len[0])
 
     @property
     def data(self) -> bytes:
         return self.buffer[:self.nbytes].tobytes()
+
+    def free(self):
+        if self._owner is not None:
+            self._owner.free()
+            self._owner = None
 
 
 @dataclass
@@ -258,14 +270,14 @@ class Engine:
                 c.n_glyphs = len(o.glyphs)
                 c.glyphs = ga
             if o.jpeg_quality is not None:
-                buf = o.jpeg_buffer
-                if buf is None:
-                    buf = np.empty(o.jpeg_capacity or (o.dst_w * o.dst_h + (64 << 10)), np.uint8)
-                assert buf.dtype == np.uint8 and buf.ndim == 1 and buf.flags["C_CONTIGUOUS"]
-                res = JpegResult(buf)
+                if o.jpeg_buffer is None:   # convenience for tests: one pinned allocation per result (a worker reuses its buffers)
+                    own = self.alloc_pinned((o.jpeg_capacity or (o.dst_w * o.dst_h + (64 << 10))) + 16)
+                    res = JpegResult(own.array, own)
+                else:
+                    res = JpegResult(o.jpeg_buffer)
                 c.dst_layout = L.JPEG
-                c.dst, c.dst_capacity, c.jpeg_quality = buf.ctypes.data, buf.size, o.jpeg_quality
-                c.dst_len = C.pointer(res._len)
+                c.dst, c.dst_capacity, c.jpeg_quality = res.buffer.ctypes.data, res.capacity, o.jpeg_quality
+                c.dst_len = C.cast(res.buffer.ctypes.data + res.capacity, C.POINTER(C.c_uint64))
                 c.dst_memspace = L.MEM_HOST
                 keep.append(res)
                 outs.append(res)

@@ -182,8 +182,9 @@ typedef struct {
      * SOF0, one DHT, SOS; no JFIF segment) -- all integer arithmetic, so the file is byte for byte what
      *   jpeg.Encode(buf, result, &jpeg.Options{Quality: jpeg_quality})
      * writes, and the host's encode step becomes SaveProcessed(bytes).  dst is then a byte buffer of dst_capacity
-     * bytes (any host memory, pinned preferred, or device memory), dst_stride is ignored, and *dst_len (host memory
-     * that stays valid until ipg_wait returns) receives the file length.  A file that does not fit dst_capacity fails
+     * bytes in ipg_alloc_pinned memory (or device memory), dst_stride is ignored, and *dst_len -- also in
+     * ipg_alloc_pinned memory, e.g. the last 8 bytes of the same allocation: both are written after ipg_submit returned,
+     * and the library keeps no other caller pointer past the call -- receives the file length.  A file that does not fit dst_capacity fails
      * that ticket with IPG_ERR_NOMEM (w * h bytes is ample for photographs at quality 85; w * h * 3 + 4096 always fits
      * at the qualities the reference uses).  Images of 65536 pixels or more per side are refused as Go's writer refuses them. */
     int32_t dst_layout;
@@ -192,7 +193,7 @@ typedef struct {
     int32_t jpeg_quality;     /* IPG_LAYOUT_JPEG: 1..100 as jpeg.Options.Quality (clamped like Go); 0 = 85, the reference's
                                  constant (domain/task.go:57) */
     uint64_t dst_capacity;    /* IPG_LAYOUT_JPEG: bytes available at dst */
-    uint64_t *dst_len;        /* IPG_LAYOUT_JPEG: receives the file length */
+    uint64_t *dst_len;        /* IPG_LAYOUT_JPEG: receives the file length (ipg_alloc_pinned memory, 8-byte aligned) */
 } ipg_op;
 
 typedef enum {

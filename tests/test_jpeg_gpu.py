@@ -132,3 +132,13 @@ def test_twelve_megapixel_watermark_file(engines, oracle):
     want = oracle_files(oracle, a, gl, col)
     for k in range(3):
         assert out[k].data == want[k]
+
+
+def test_pageable_destination_is_refused(engines):
+    """The engine writes the file and its length after ipg_submit returned: it takes them in its own pinned memory only."""
+    w, h = 64, 48
+    a = rgba_random(w, h, 3)
+    buf = np.zeros(1 << 16, np.uint8)   # ordinary heap memory
+    with pytest.raises(ip.IpgError) as ei:
+        engines().submit(ip.Image.from_rgba(a), [ip.OpSpec.watermark(w, h, (0, 0, 0, 255), [], jpeg_quality=85, jpeg_buffer=buf)])
+    assert ei.value.code == ip._lib.ERR_INVALID and "ipg_alloc_pinned" in ei.value.message

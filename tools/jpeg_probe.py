@@ -50,7 +50,7 @@ def main():
     col, _ = G.parse_color("255,255,255", 0.5)
     eng = ip.Engine(devices=[0], lanes_per_device=2, max_batch=a.images, batch_window_us=2000, lane_device_bytes=12 << 30)
     cap = W * H * (3 if a.noise else 1)
-    bufs = [[eng.alloc_pinned(nw * nh * 3), eng.alloc_pinned(200 * 200 * 3 + 4096), eng.alloc_pinned(cap)] for _ in range(a.images)]
+    bufs = [[eng.alloc_pinned(nw * nh * 3 + 16), eng.alloc_pinned(200 * 200 * 3 + 4096 + 16), eng.alloc_pinned(cap + 16)] for _ in range(a.images)]
     rgba = [[eng.alloc_pinned(nw * nh * 4), eng.alloc_pinned(200 * 200 * 4), eng.alloc_pinned(W * H * 4)] for _ in range(a.images)]
     out = {}
     for mode in ("jpeg", "rgba"):
