@@ -134,18 +134,23 @@ class JpegResult:
         self.buffer = buffer
         self._len = buffer[self.capacity:self.capacity + 8].view(np.uint64)
         self._len[0] = 0
-        self._owner = owner   # a PinnedBuffer this result allocated itself (freed by free())
+        self._owner = owner   # a PinnedBuffer this result allocated itself (released by detach())
+        self._bytes = None
 
     @property
     def nbytes(self) -> int:
-        return int(self._len[0])
+        return len(self._bytes) if self._bytes is not None else int(self._len[0])
 
     @property
     def data(self) -> bytes:
-        return self.buffer[:self.nbytes].tobytes()
+        return self._bytes if self._bytes is not None else self.buffer[:self.nbytes].tobytes()
 
-    def free(self):
+    def detach(self):
+        """A result that allocated its own pinned buffer copies the file out and frees the buffer (Engine.wait calls
+        this): the bytes then outlive the engine."""
         if self._owner is not None:
+            self._bytes = self.buffer[:int(self._len[0])].tobytes()
+            self.buffer = self._len = None
             self._owner.free()
             self._owner = None
 
@@ -314,7 +319,12 @@ class Engine:
         return Ticket(tid.value, outs, keep)
 
     def wait(self, ticket: Ticket, timeout_ms: int = -1) -> List[Optional[np.ndarray]]:
-        L.check(self._lib.ipg_wait(self._ctx, ticket.id, timeout_ms))
+        rc = self._lib.ipg_wait(self._ctx, ticket.id, timeout_ms)
+        if rc != L.ERR_TIMEOUT:
+            for o in ticket.outputs:
+                if isinstance(o, JpegResult):
+                    o.detach()
+        L.check(rc)
         ticket._keep.clear()
         return ticket.outputs
 
