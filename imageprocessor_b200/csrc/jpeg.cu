@@ -67,7 +67,7 @@ enum { DCT_ROW_WORDS = JPEG_DCT_MCUS * 17 };
 struct DctSmem {
     union {
         uint32_t px[16 * DCT_ROW_WORDS];   // the staged pixels: dead once every luma warp has converted its quadrants
-        int16_t coef[64][192];             // then: non-zero quantised AC coefficients, [zig][thread] (lanes side by side)
+        int16_t coef[64][192];             // then: non-zero quantised AC coefficients, [zig][thread] (lanes side by side; the coding threads are 0..191)
     };
     uint32_t cmean[2][JPEG_DCT_MCUS * 17]; // Cb / Cr: the 16 words (8 x 8 means) of each MCU, MCUs 17 words apart
     int32_t half[2][64];
@@ -79,7 +79,14 @@ struct CoefSmem {
     __device__ __forceinline__ void set(int zig, int v) { p[zig * 192] = (int16_t)v; }
     __device__ __forceinline__ int get(int zig) const { return p[zig * 192]; }
 };
-__global__ void __launch_bounds__(192) k_jpeg_dct(const JpegJob *__restrict__ jobs, const JpegDctItem *__restrict__ items)
+// 4 CTAs per SM (80 registers, a 24-byte spill) beat 3 (96 registers, none) by 6 %: the kernel is latency-bound at 18 warps.
+// Measured and dropped: 8 warps with the chroma means on warps 4-7 beside the luma warps (95-111 us against 95).
+#ifndef IPG_JPEG_DCT_CTAS
+#define IPG_JPEG_DCT_CTAS 4
+#endif
+#define IPG_JPEG_DCT_WARPS 6
+enum { DCT_THREADS = IPG_JPEG_DCT_WARPS * 32 };
+__global__ void __launch_bounds__(DCT_THREADS, IPG_JPEG_DCT_CTAS) k_jpeg_dct(const JpegJob *__restrict__ jobs, const JpegDctItem *__restrict__ items)
 {
     __shared__ DctSmem sm;
     const JpegDctItem it = items[blockIdx.x];
@@ -95,11 +102,11 @@ __global__ void __launch_bounds__(192) k_jpeg_dct(const JpegJob *__restrict__ jo
     // stage: 4 pixels per piece (one 16-byte load when they are all inside the image); consecutive threads take
     // consecutive 16-byte pieces of one image row, MCU after MCU
     const int mx0 = it.mcu0 % J.mcu_w, my0 = it.mcu0 / J.mcu_w;
-    constexpr int kPieces = 16 * JPEG_DCT_MCUS * 4, kRounds = (kPieces + 191) / 192; // 2048 pieces, 11 per thread
+    constexpr int kPieces = 16 * JPEG_DCT_MCUS * 4, kRounds = (kPieces + DCT_THREADS - 1) / DCT_THREADS; // 2048 pieces, 11 per thread
     uint4 v[kRounds];
 #pragma unroll
     for (int r = 0; r < kRounds; r++) { // all the loads first: 11 in flight per thread
-        const int q = threadIdx.x + r * 192;
+        const int q = threadIdx.x + r * DCT_THREADS;
         const int row = q >> 7, m = (q >> 2) & 31, quad = q & 3;
         v[r] = make_uint4(0u, 0u, 0u, 0u);
         if (q >= kPieces || m >= n_here) continue;
@@ -118,29 +125,33 @@ __global__ void __launch_bounds__(192) k_jpeg_dct(const JpegJob *__restrict__ jo
     }
 #pragma unroll
     for (int r = 0; r < kRounds; r++) {
-        const int q = threadIdx.x + r * 192;
+        const int q = threadIdx.x + r * DCT_THREADS;
         if (q >= kPieces) continue;
         const int row = q >> 7, m = (q >> 2) & 31, quad = q & 3;
         uint32_t *d = sm.px + row * DCT_ROW_WORDS + m * 17 + quad * 4;
         d[0] = v[r].x; d[1] = v[r].y; d[2] = v[r].z; d[3] = v[r].w;
     }
     __syncthreads();
-    const int blk = threadIdx.x >> 5, m = threadIdx.x & 31;
+    const int wrp = threadIdx.x >> 5, m = threadIdx.x & 31;
     const bool active = m < n_here;
-    const int mcu = it.mcu0 + m, q = blk < 4 ? 0 : 1;
     int32_t b[64];
-    if (blk < 4 && active) { // the four luma warps convert their quadrants and leave the chroma means for warps 4 and 5
+    {
         const uint32_t *base = sm.px + m * 17;
-        uint32_t cbw[4], crw[4];
-        jpeg_quadrant(blk, b, cbw, crw, [base](int lx, int ly) { return base[ly * DCT_ROW_WORDS + lx]; });
+        auto px = [base](int lx, int ly) { return base[ly * DCT_ROW_WORDS + lx]; };
+        if (wrp < 4 && active) { // the four luma warps convert their quadrants and leave the chroma means for warps 4 and 5
+            uint32_t cbw[4], crw[4];
+            jpeg_quadrant(wrp, b, cbw, crw, px);
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            sm.cmean[0][m * 17 + jpeg_chroma_word(blk, r)] = cbw[r];
-            sm.cmean[1][m * 17 + jpeg_chroma_word(blk, r)] = crw[r];
+            for (int r = 0; r < 4; r++) {
+                sm.cmean[0][m * 17 + jpeg_chroma_word(wrp, r)] = cbw[r];
+                sm.cmean[1][m * 17 + jpeg_chroma_word(wrp, r)] = crw[r];
+            }
         }
     }
     __syncthreads();
+    const int blk = wrp; // warp b codes block b
     if (!active) return;
+    const int mcu = it.mcu0 + m, q = blk < 4 ? 0 : 1;
     if (blk >= 4) {
         const uint32_t *cw = sm.cmean[blk - 4] + m * 17;
         jpeg_chroma_block(b, [cw](int k) { return cw[k]; });
@@ -305,7 +316,7 @@ cudaError_t launch_jpeg(const JpegJob *jobs, int n_jobs, const JpegDctItem *dct_
                         int n_stuff, cudaStream_t st)
 {
     if (n_jobs <= 0) return cudaSuccess;
-    k_jpeg_dct<<<n_dct, 192, 0, st>>>(jobs, dct_items);
+    k_jpeg_dct<<<n_dct, DCT_THREADS, 0, st>>>(jobs, dct_items);
     k_jpeg_offsets<<<n_jobs, JPEG_SCAN_THREADS, 0, st>>>(jobs);
     k_jpeg_zero<<<n_stuff, JPEG_STUFF_THREADS, 0, st>>>(jobs, stuff_items);
     k_jpeg_emit<<<n_dct, 192, 0, st>>>(jobs, dct_items);
