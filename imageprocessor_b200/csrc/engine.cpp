@@ -467,6 +467,59 @@ static size_t ticket_device_bytes(const Ticket &t)
     return n + 4096;
 }
 
+// The device-side JPEG writer's share of a batch: one JpegJob per result that leaves as a file, its buffers carved from
+// the lane's arena, its tables (one set per quality) and header in the parameter blob, and the CTA lists of its passes.
+struct JpegPlan {
+    std::vector<JpegJob> jobs;
+    std::vector<JpegDctItem> dct;     // k_jpeg_dct / k_jpeg_emit: 32 MCUs each
+    std::vector<JpegStuffItem> stuff; // k_jpeg_zero / k_jpeg_ffcount / k_jpeg_write
+    uint32_t *d_results = nullptr;    // 4 words per job
+};
+static void plan_jpeg_jobs(const std::vector<std::pair<OpRec *, int>> &jpeg_ops, Arena &arena, Blob &blob, Batch &B, JpegPlan &P)
+{
+    if (jpeg_ops.empty()) return;
+    if (jpeg_ops.size() > kJpegMaxJobs) throw std::runtime_error("too many JPEG results in one batch; lower max_batch");
+    P.d_results = (uint32_t *)arena.take(16 * jpeg_ops.size(), 256);
+    if (!P.d_results) throw std::runtime_error("device arena exhausted (JPEG results)");
+    std::map<int, const JpegTables *> tabs; // per quality
+    for (auto &jo : jpeg_ops) {
+        OpRec &op = *jo.first;
+        const bool to_host = op.dst_mem == IPG_MEM_HOST;
+        const JpegSizes z = jpeg_sizes(op.dw, op.dh, op.dst_capacity, to_host);
+        JpegJob j{};
+        j.rgba = op.dev_out; j.rgba_pitch = (int)op.dev_pitch; j.w = op.dw; j.h = op.dh;
+        j.mcu_w = z.mcu_w; j.n_mcu = z.n_mcu;
+        auto tb = tabs.find(op.jpeg_quality);
+        if (tb == tabs.end()) {
+            JpegTables T;
+            jpeg_build_tables(op.jpeg_quality, &T);
+            tb = tabs.emplace(op.jpeg_quality, blob.dptr<const JpegTables>(blob.put(&T, sizeof T, 16))).first;
+        }
+        j.tab = tb->second;
+        uint8_t hdr[JPEG_HDR_MAX];
+        j.hdr_len = (uint32_t)jpeg_build_header(op.jpeg_quality, op.dw, op.dh, hdr);
+        j.hdr = blob.dptr<const uint8_t>(blob.put(hdr, j.hdr_len, 16));
+        j.acs = (uint32_t *)arena.take((size_t)(z.n_mcu + 31) / 32 * 6 * JPEG_SLOT_WORDS * JPEG_SLOT_STRIDE * 4);
+        j.side = (uint32_t *)arena.take((size_t)z.n_mcu * 6 * 4);
+        j.mcu_off = (uint32_t *)arena.take((size_t)z.n_mcu * 4);
+        j.words = (uint32_t *)arena.take(z.scan_cap);
+        j.cap_bytes = (uint32_t)z.scan_cap;
+        j.chunk_off = (uint32_t *)arena.take((z.scan_cap / JPEG_CHUNK + 1) * 4);
+        j.out = to_host ? arena.take(z.out_cap) : (uint8_t *)op.dst;
+        j.out_cap = (uint32_t)z.out_cap;
+        if (!j.acs || !j.side || !j.mcu_off || !j.words || !j.chunk_off || !j.out) throw std::runtime_error("device arena exhausted (JPEG writer)");
+        const int ji = (int)P.jobs.size();
+        j.result = P.d_results + 4 * ji;
+        P.jobs.push_back(j);
+        for (int m = 0; m < z.n_mcu; m += JPEG_DCT_MCUS) P.dct.push_back(JpegDctItem{ji, m});
+        // CTAs of the stuffing passes: the scan's real size is known on the device only, so size them for the capacity, 32
+        // chunks (4 per warp) each; CTAs past the real end exit at once
+        const int parts = (int)std::max<size_t>(1, std::min<size_t>(JPEG_STUFF_PARTS, (z.scan_cap / JPEG_CHUNK + 31) / 32));
+        for (int q = 0; q < parts; q++) P.stuff.push_back(JpegStuffItem{ji, (int16_t)q, (int16_t)parts});
+        B.jpegs.push_back(Batch::JpegOut{j.out, op.dst, (size_t)op.dst_capacity, op.dst_len, jo.second, ji, to_host});
+    }
+}
+
 // Build and enqueue one batch on a lane.  Throws std::runtime_error on failure.
 static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
 {
@@ -964,52 +1017,12 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
     }
 
     // ---- device-side JPEG writer (dst_layout JPEG): one job per result
-    std::vector<JpegJob> jjobs;
-    std::vector<JpegDctItem> jdct;
-    std::vector<JpegStuffItem> jstuff;
-    uint32_t *d_jresults = nullptr;
-    if (!jpeg_ops.empty()) {
-        if (jpeg_ops.size() > kJpegMaxJobs) throw std::runtime_error("too many JPEG results in one batch; lower max_batch");
-        d_jresults = (uint32_t *)arena.take(16 * jpeg_ops.size(), 256);
-        if (!d_jresults) throw std::runtime_error("device arena exhausted (JPEG results)");
-        std::map<int, const JpegTables *> tabs; // per quality
-        for (auto &jo : jpeg_ops) {
-            OpRec &op = *jo.first;
-            const bool to_host = op.dst_mem == IPG_MEM_HOST;
-            const JpegSizes z = jpeg_sizes(op.dw, op.dh, op.dst_capacity, to_host);
-            JpegJob j{};
-            j.rgba = op.dev_out; j.rgba_pitch = (int)op.dev_pitch; j.w = op.dw; j.h = op.dh;
-            j.mcu_w = z.mcu_w; j.n_mcu = z.n_mcu;
-            auto tb = tabs.find(op.jpeg_quality);
-            if (tb == tabs.end()) {
-                JpegTables T;
-                jpeg_build_tables(op.jpeg_quality, &T);
-                tb = tabs.emplace(op.jpeg_quality, blob.dptr<const JpegTables>(blob.put(&T, sizeof T, 16))).first;
-            }
-            j.tab = tb->second;
-            uint8_t hdr[JPEG_HDR_MAX];
-            j.hdr_len = (uint32_t)jpeg_build_header(op.jpeg_quality, op.dw, op.dh, hdr);
-            j.hdr = blob.dptr<const uint8_t>(blob.put(hdr, j.hdr_len, 16));
-            j.acs = (uint32_t *)arena.take((size_t)(z.n_mcu + 31) / 32 * 6 * JPEG_SLOT_WORDS * JPEG_SLOT_STRIDE * 4);
-            j.side = (uint32_t *)arena.take((size_t)z.n_mcu * 6 * 4);
-            j.mcu_off = (uint32_t *)arena.take((size_t)z.n_mcu * 4);
-            j.words = (uint32_t *)arena.take(z.scan_cap);
-            j.cap_bytes = (uint32_t)z.scan_cap;
-            j.chunk_off = (uint32_t *)arena.take((z.scan_cap / JPEG_CHUNK + 1) * 4);
-            j.out = to_host ? arena.take(z.out_cap) : (uint8_t *)op.dst;
-            j.out_cap = (uint32_t)z.out_cap;
-            if (!j.acs || !j.side || !j.mcu_off || !j.words || !j.chunk_off || !j.out) throw std::runtime_error("device arena exhausted (JPEG writer)");
-            const int ji = (int)jjobs.size();
-            j.result = d_jresults + 4 * ji;
-            jjobs.push_back(j);
-            for (int m = 0; m < z.n_mcu; m += JPEG_DCT_MCUS) jdct.push_back(JpegDctItem{ji, m});
-            // CTAs of the stuffing passes: the scan's real size is known on the device only, so size them for the capacity, 32
-            // chunks (4 per warp) each; CTAs past the real end exit at once
-            const int parts = (int)std::max<size_t>(1, std::min<size_t>(JPEG_STUFF_PARTS, (z.scan_cap / JPEG_CHUNK + 31) / 32));
-            for (int q = 0; q < parts; q++) jstuff.push_back(JpegStuffItem{ji, (int16_t)q, (int16_t)parts});
-            B.jpegs.push_back(Batch::JpegOut{j.out, op.dst, (size_t)op.dst_capacity, op.dst_len, jo.second, ji, to_host});
-        }
-    }
+    JpegPlan jp;
+    plan_jpeg_jobs(jpeg_ops, arena, blob, B, jp);
+    std::vector<JpegJob> &jjobs = jp.jobs;
+    std::vector<JpegDctItem> &jdct = jp.dct;
+    std::vector<JpegStuffItem> &jstuff = jp.stuff;
+    uint32_t *d_jresults = jp.d_results;
 
     // ---- fix list (EXACT mode)
     FixList fix{nullptr, nullptr, 0};

@@ -18,10 +18,12 @@ def _ops_and_expected(ip, O, a, layout="rgba"):
     gl = synthetic_glyphs(w, h, 5)
     col = (255, 255, 255, 127)
     ops = [ip.OpSpec.resize(nw, nh), ip.OpSpec.thumb_crop((cx, cy, cs, cs), 200),
-           ip.OpSpec.watermark(w, h, col, [ip.GlyphMask(*g) for g in gl])]
+           ip.OpSpec.watermark(w, h, col, [ip.GlyphMask(*g) for g in gl]),
+           ip.OpSpec.thumb_crop((cx, cy, cs, cs), 200, jpeg_quality=85)]   # ... and one result as a device-encoded JPEG file
     R = O.Raster.rgba(a, O.NRGBA8 if layout == "nrgba" else O.RGBA8)
     ogl = [O.Glyph(*g) for g in gl]
-    return ops, [O.resize_image(R, nw, nh), O.crop_and_resize(R, 200), O.watermark(R, col, ogl)]
+    thumb = O.crop_and_resize(R, 200)
+    return ops, [O.resize_image(R, nw, nh), thumb, O.watermark(R, col, ogl), O.jpeg_encode_rgba(thumb, 85)]
 
 
 @pytest.mark.gpu(min_devices=2)
@@ -45,13 +47,13 @@ def test_one_context_all_devices_auto_routing_and_submit_on(oracle):
         tickets = [e.submit(img, ops) for img, ops, _ in cases]
         for t, (_, _, exp) in zip(tickets, cases):
             for got, want in zip(e.wait(t), exp):
-                assert np.array_equal(got, want)
+                assert got.data == want if isinstance(want, bytes) else np.array_equal(got, want)
         # (2) every device explicitly, every kernel family on each
         for dev in range(n_dev):
             tickets = [e.submit(img, ops, device=dev) for img, ops, _ in cases[:6]]
             for t, (_, _, exp) in zip(tickets, cases[:6]):
                 for got, want in zip(e.wait(t), exp):
-                    assert np.array_equal(got, want), f"device {dev}"
+                    assert (got.data == want if isinstance(want, bytes) else np.array_equal(got, want)), f"device {dev}"
         st = e.stats()
         assert st["tickets_done"] == len(cases) + 6 * n_dev and st["kernels_launched"] > 0
 
