@@ -94,3 +94,29 @@ def test_exact_division_by_reciprocal():
     for d in range(8, 2041, 8):
         recip = (1 << 32) // d + 1
         assert np.array_equal((n * np.uint64(recip)) >> np.uint64(32), n // np.uint64(d)), d
+
+
+def test_random_small_images_property(emu):
+    """Seeded sweep over sizes 1..40 x 1..40 and qualities 1..100: every file equals the oracle's (MCU padding in both
+    axes, single-MCU images, scans shorter than one stuffing chunk)."""
+    rng = np.random.default_rng(2024)
+    for _ in range(150):
+        w, h, q = int(rng.integers(1, 41)), int(rng.integers(1, 41)), int(rng.integers(1, 101))
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        elif kind == 1:
+            img = photo(rng, h, w, 3.0)
+        else:   # flat with one impulse: a long run of zeros then a coefficient (ZRL codes)
+            img = np.full((h, w, 4), int(rng.integers(0, 256)), np.uint8)
+            img[int(rng.integers(0, h)), int(rng.integers(0, w)), :3] = rng.integers(0, 256, 3)
+        assert emu(img, q) == O.jpeg_encode_rgba(img, q), (w, h, q, kind)
+
+
+def test_widest_image_the_writer_accepts(emu):
+    """65535 pixels per side is the most Go's writer takes (it refuses 1 << 16): 4096 MCUs in one row, the last one padded."""
+    rng = np.random.default_rng(6)
+    img = np.repeat(rng.integers(0, 256, (3, 65535 // 15 + 1, 4), dtype=np.uint8), 15, axis=1)[:, :65535]
+    f = emu(img, 85)
+    assert f == O.jpeg_encode_rgba(img, 85)
+    assert f[0x88:0x88 + 9] == bytes([0xff, 0xc0, 0, 17, 8, 0, 3, 0xff, 0xff])   # SOF0 at byte 136: height 3, width 65535

@@ -71,6 +71,20 @@ def test_tiny_and_mcu_edge_sizes(engines, oracle):
         assert res.data == oracle.jpeg_encode_rgba(a, 85), (w, h)
 
 
+def test_widest_image_the_writer_accepts_and_the_first_it_refuses(engines, oracle):
+    """65535 pixels per side is the most Go's writer takes; 65536 is refused with its own message before anything runs."""
+    e = engines()
+    rng = np.random.default_rng(6)
+    a = np.repeat(rng.integers(0, 256, (16, 65535 // 15 + 1, 4), dtype=np.uint8), 15, axis=1)[:, :65535].copy()
+    a[..., 3] = 255
+    res = e.run(ip.Image.from_rgba(a), [ip.OpSpec.watermark(65535, 16, (0, 0, 0, 255), [], jpeg_quality=85, jpeg_capacity=65535 * 16 * 2)])[0]
+    assert res.data == oracle.jpeg_encode_rgba(a, 85)
+    b = np.zeros((8, 65536, 4), np.uint8)
+    with pytest.raises(ip.IpgError) as ei:
+        e.submit(ip.Image.from_rgba(b), [ip.OpSpec.watermark(65536, 8, (0, 0, 0, 255), [], jpeg_quality=85)])
+    assert "too large to encode" in ei.value.message
+
+
 def test_alpha_results_encode_their_premultiplied_bytes(engines, oracle):
     """A PNG with alpha resized and written as JPEG: Go's writer reads the premultiplied R, G, B of the *image.RGBA."""
     w, h = 1203, 907
