@@ -966,15 +966,27 @@ template <int NT, int LEAN = 0> struct StreamCfg {
 };
 
 // ---- horizontal pass ---------------------------------------------------------------
-template <typename TI>
+#ifndef IPG_LEAN_OPAQUE_FINISH
+#define IPG_LEAN_OPAQUE_FINISH 1
+#endif
+// OPAQUE (the lean instantiations: every pixel met so far had alpha 255, or the job is redone): the alpha sum is
+// 65535 * (weights summing to 1) -- T = 0xffff80 + a few units, byte 255, 128 units from a quantiser step, never
+// ambiguous while D < 128 -- so the byte is written as a constant, and the premultiplied clamp min(c, a) can only
+// touch values within rounding of 65535 whose byte is 255 either way (a flag it might add or drop there is harmless:
+// the fp64 re-evaluation returns 255 too).
+template <bool OPAQUE = false, typename TI>
 __device__ __forceinline__ void xfinish(const TI &t, uint32_t D, int ox, int oy, float2 rg, float2 ba, const FixList &fix)
 {
-    const float a = ba.y;
-    const float r = fminf(rg.x, a), g = fminf(rg.y, a), b = fminf(ba.x, a);
     bool amb = false;
     const uint32_t span = 65536u - 2u * D;
-    const uint32_t o = quant16(r, D, span, amb) | (quant16(g, D, span, amb) << 8) |
-                       (quant16(b, D, span, amb) << 16) | (quant16(a, D, span, amb) << 24);
+    uint32_t o;
+    if constexpr (OPAQUE && IPG_LEAN_OPAQUE_FINISH) {
+        o = quant16(rg.x, D, span, amb) | (quant16(rg.y, D, span, amb) << 8) | (quant16(ba.x, D, span, amb) << 16) | 0xff000000u;
+    } else {
+        const float a = ba.y;
+        const float r = fminf(rg.x, a), g = fminf(rg.y, a), b = fminf(ba.x, a);
+        o = quant16(r, D, span, amb) | (quant16(g, D, span, amb) << 8) | (quant16(b, D, span, amb) << 16) | (quant16(a, D, span, amb) << 24);
+    }
     *(uint32_t *)(t.dst + (size_t)oy * t.dst_stride + (size_t)ox * 4) = o;
     if (amb && fix.capacity) { // (keep this shape: the compiler aggregates the atomic per warp; other forms cost the V loop 5-30 %)
         const uint32_t idx = atomicAdd(fix.count, 1u);
@@ -1039,7 +1051,7 @@ __device__ __forceinline__ void xtab_fill(XT &xt, XInfo &xi, int T, const Stream
 
 // The cached horizontal pass over the row parked in xbuf[T]: every round of this thread.  All V threads
 // of the unit (warp if local, CTA if not) call it together: the butterfly shuffles are warp-wide.
-template <typename SM>
+template <bool OPAQUE = false, typename SM>
 __device__ __forceinline__ void xcached(SM &sm, int T, int oy, int tid, const FixList &fix)
 {
     const XInfo xi = sm.xi[T];
@@ -1065,7 +1077,7 @@ __device__ __forceinline__ void xcached(SM &sm, int T, int oy, int tid, const Fi
             ba.x += __shfl_xor_sync(0xffffffffu, ba.x, off);
             ba.y += __shfl_xor_sync(0xffffffffu, ba.y, off);
         }
-        if (ox >= 0 && (tid & (P - 1)) == 0) xfinish(xi, xi.D, ox, oy, rg, ba, fix);
+        if (ox >= 0 && (tid & (P - 1)) == 0) xfinish<OPAQUE>(xi, xi.D, ox, oy, rg, ba, fix);
     }
 }
 
@@ -1248,12 +1260,12 @@ __device__ __forceinline__ uint32_t v_rows_fast(VAcc<false> &S, const StreamJob 
                     ba.x += __shfl_xor_sync(0xffffffffu, ba.x, off);
                     ba.y += __shfl_xor_sync(0xffffffffu, ba.y, off);
                 }
-                if (C.x0_ox >= 0 && (threadIdx.x & (C.x0_parts - 1)) == 0) xfinish(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
+                if (C.x0_ox >= 0 && (threadIdx.x & (C.x0_parts - 1)) == 0) xfinish<true>(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
                 __syncwarp(); // the strip is reused by the next emit
             } else if constexpr (LEAN == 4) { // table forms, inline (no call: the accumulators stay in registers):
                 const bool loc = sm.xi[0].local != 0; // a wide target, or a local one with several outputs per lane
                 if (loc) __syncwarp(); else vwarps_bar();
-                xcached(sm, 0, e >> 1, (int)threadIdx.x, fix);
+                xcached<true>(sm, 0, e >> 1, (int)threadIdx.x, fix);
                 if (loc) __syncwarp(); else vwarps_bar(); // the row buffer is reused by the next emit
             } else {           // wide support (the thumbnail): CTA-wide split pass, once per ~15 rows
                 xpass<1>(J, sm, 0, e >> 1, C.tile, C.cx0, C.vtid, fix);
