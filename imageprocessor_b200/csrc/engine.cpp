@@ -339,6 +339,8 @@ struct Ctx {
     // fix / blend tail.  Measured (r2): +1.4 % images/s device-resident, but the tail kernels then share SMs with
     // k_stream and its own duration (what the roofline is quoted on) grows 3 %; off by default.
     bool overlap_tail = false;
+    // IPG_VINT=0: wide 8-bit targets (the 15:1 thumbnail) keep the fp32 vertical pass instead of the integer-moment form
+    bool use_vint = true;
     int staging_timeout_ms = 2000; // IPG_STAGING_TIMEOUT_MS: how long ipg_submit waits for pinned staging before IPG_ERR_NOMEM
     // stats
     std::atomic<uint64_t> s_done{0}, s_batches{0}, s_kernels{0}, s_h2d{0}, s_d2h{0}, s_fix{0}, s_fallback{0}, s_staged{0};
@@ -870,6 +872,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 j.band_y = blob.put_vec(geom->band_y);
                 j.band_yend = blob.put_vec(geom->band_yend);
                 j.grec = blob.put_vec(geom->grec);
+                j.rec_slots = geom->rec_slots;
                 j.band_grec_off = blob.put_vec(geom->band_grec_off);
                 for (int k = 0; k < nt; k++) {
                     const StreamTargetGeom &tgm = geom->t[k];
@@ -880,6 +883,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                     o.rect_x = spec[k].rect_x; o.rect_y = spec[k].rect_y;
                     o.two_stage = tg[k]->kind == IPG_OP_THUMB_CROP;
                     o.fix_d = tgm.fix_d;
+                    o.fix_d_vint = tgm.fix_d_vint;
                     o.xoff = blob.put_vec(tgm.ax->off);
                     o.xfirst = blob.put_vec(tgm.ax->first);
                     o.xw = blob.put_vec(tgm.xw);
@@ -908,6 +912,8 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                     else if (lean2 && geom->lean2_ok) j.fast_path = 3;
                 }
                 j.redo_flag = (j.fast_path && !t.src.opaque_hint) ? redo_flags + ji : nullptr;
+                // a wide target's vertical pass in the integer-moment form (the lean single-target kernels only)
+                j.vint = (c.use_vint && geom->vint_ok && (j.fast_path == 1 || j.fast_path == 2)) ? 1 : 0;
                 sjobs.push_back(j);
                 if (!j.fast_path) {
                     max_nt = std::max(max_nt, nt);
@@ -965,6 +971,7 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 j.band_y = blob.put_vec(geom->band_y);
                 j.band_yend = blob.put_vec(geom->band_yend);
                 j.grec = blob.put_vec(geom->grec);
+                j.rec_slots = geom->rec_slots;
                 j.band_grec_off = blob.put_vec(geom->band_grec_off);
                 const StreamTargetGeom &tgm = geom->t[0];
                 StreamTarget &o = j.t[0];
@@ -1705,6 +1712,7 @@ int ipg_init(const int *device_ids, int n, const ipg_config *cfg, ipg_ctx **out)
         c->trace = getenv("IPG_TRACE") && atoi(getenv("IPG_TRACE")) != 0;
         c->fuse_targets = (k.fuse_targets >= 1 && k.fuse_targets <= 3) ? k.fuse_targets : 1;
         if (getenv("IPG_MERGE_LEAN")) c->merge_lean = atoi(getenv("IPG_MERGE_LEAN")) != 0;
+        if (getenv("IPG_VINT")) c->use_vint = atoi(getenv("IPG_VINT")) != 0;
         if (getenv("IPG_BAND_CTAS")) c->band_cta_target = (uint32_t)std::max(1, atoi(getenv("IPG_BAND_CTAS")));
         if (getenv("IPG_FIX_CAPACITY")) c->fix_capacity = (uint32_t)std::max(1, atoi(getenv("IPG_FIX_CAPACITY")));
         c->overlap_streams = !(getenv("IPG_NO_OVERLAP") && atoi(getenv("IPG_NO_OVERLAP")) != 0);

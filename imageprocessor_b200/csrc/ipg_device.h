@@ -84,6 +84,25 @@ struct GroupRec {
     int32_t pad[2];
 };
 static_assert(sizeof(GroupRec) % 16 == 0, "group records ride in TMA bulk copies (16-byte granular)");
+
+// Integer-moment form of a wide target's vertical pass (plan.cpp build_vint; the 15:1 thumbnail).  Between the
+// centres of two consecutive output rows ("segment", <= 16 source rows) the tent weights of the two open output rows
+// are LINEAR in the row index r, so the segment's contribution to both is a combination of the two exact integer
+// moments M0 = sum x and M1 = sum r * x of every byte column.  A V thread keeps both in ONE 32-bit word per channel,
+// M0 in bits 0..11 (<= 16 * 255) and M1 from bit 12 (<= 255 * 120), fed by one IDP.2A per channel and row with the
+// 16-bit multiplier m = 1 + (r << 12): no byte -> fp32 unpack, no per-row weights, 12 accumulators instead of 24.  When
+// a segment ends, the moments become fp32 once: the completed output row is carry + aR * M0 + bR * M1, and the next
+// row's carry is aL * M0 + bL * M1 (coefficients per segment end, at most one per group).  Same size as a GroupRec:
+// it rides in the slot after the target's fp32 record (StreamJob::rec_slots), which the on-demand redo still uses.
+struct GroupRecI {
+    uint32_t m[IPG_GROUP];     // per source row: 1 + (r << 12), or 0 when the row feeds no output this band owns
+    int32_t emit[IPG_GROUP];   // -1: nothing; -2: a segment ends after this row (carry only); >= 0: ... and completes this output row
+    float aR, bR, aL, bL;      // of the segment that ends in this group
+    int32_t end_k, end_e;      // that end again, as the kernel takes it: row index within the group (IPG_GROUP - 1 when none: then
+                               // every row is "before the end") and its emit word (-1 when none)
+    uint8_t pad[sizeof(GroupRec) - 8 * IPG_GROUP - 24];
+};
+static_assert(sizeof(GroupRecI) == sizeof(GroupRec), "the integer-form record takes a GroupRec slot");
 static_assert(IPG_GROUP == 4 || IPG_GROUP == 8, "the row loop indexes the next row with a power-of-two mask");
 
 struct StreamTarget {
@@ -94,6 +113,7 @@ struct StreamTarget {
     int32_t two_stage;           // samples clamped to alpha (8-bit crop stage) first
     int32_t exact_job;           // ExactJob index used for fix-ups
     int32_t fix_d;               // ambiguity half-width, 1/256 of a 16-bit step
+    int32_t fix_d_vint;          // ... of the integer-moment vertical form (StreamJob::vint)
     const int32_t *xoff;         // [dw+1]
     const int32_t *xfirst;       // [dw]   relative to rect_x
     const float *xw;             // normalised fp32 weights (sum 1)
@@ -192,10 +212,12 @@ struct StreamJob {
     int32_t check_premul;      // RGBA8 source, alpha unknown, a two_stage target exists
     int32_t fast_path;         // 1 / 2 / 3: a lean instantiation (local / wide / local + wide targets) runs this job;
                                // the general one only redoes it on demand
+    int32_t rec_slots;         // GroupRec slots per group in grec (n_targets, + 1 when target 0's integer-moment record rides along)
+    int32_t vint;              // 1: the lean kernels run target 0's vertical pass in the integer-moment form (GroupRecI in slot n_targets)
     int32_t *redo_flag;        // fast_path: raised by the lean kernel on a non-opaque pixel (nullptr: caller vouches for opacity)
     const int32_t *band_y;     // [n_bands+1] owned source rows of each band
     const int32_t *band_yend;  // [n_bands]   one past the last row the band must read
-    const GroupRec *grec;      // [groups of all bands][n_targets]
+    const GroupRec *grec;      // [groups of all bands][rec_slots]
     const int32_t *band_grec_off; // [n_bands] first group of each band
     StreamTarget t[2];
     WatermarkD wm;

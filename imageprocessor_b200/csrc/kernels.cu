@@ -1015,11 +1015,11 @@ __device__ __forceinline__ void xgather(const float *__restrict__ wp, int e0, in
 // tile_parts word; a tile without outputs (P == 0) gets an empty one-round table.
 template <typename XT>
 __device__ __forceinline__ void xtab_fill(XT &xt, XInfo &xi, int T, const StreamTarget &t, int tile, int cx0, int ws, int tid,
-                                          int pv)
+                                          int pv, int fix_d)
 {
     const int warp = tid >> 5, lane = tid & 31;
     const int P0 = pv & 255, P = max(P0, 1), ntap = P0 ? (pv >> 8) & 255 : 0, R = P0 ? pv >> 16 : 1;
-    if (tid == 0) xi = XInfo{t.dst, t.dst_stride, t.exact_job, (uint32_t)t.fix_d, t.local, P, ntap, R};
+    if (tid == 0) xi = XInfo{t.dst, t.dst_stride, t.exact_job, (uint32_t)fix_d, t.local, P, ntap, R};
     const int part = tid & (P - 1);
 #pragma unroll
     for (int r = 0; r < STREAM_XROUNDS; r++) {
@@ -1453,6 +1453,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     // 3: a local and a wide target fused (the source is read once for resize + thumbnail);
     // 4: one target, local or wide decided per CTA (both passes inline): CTAs of both kinds share the SMs
     constexpr bool FAST = LEAN != 0;
+    constexpr bool VINT = LEAN == 2 || LEAN == 4; // these run a wide target's vertical pass in the integer-moment form when the job has one
     static_assert(!FAST || (LEAN == 3 ? NT == 2 : NT == 1), "lean instantiations: one target, or local + wide");
     constexpr int STAGES = StreamCfg<NT, LEAN>::STAGES;
     constexpr bool INLINE = StreamCfg<NT, LEAN>::INLINE_PROD;
@@ -1490,8 +1491,8 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sm.ring_src = J.src.p0 + (size_t)ys0 * stride + (size_t)cx0 * 4;
-        sm.ring_rec = (const uint8_t *)(J.grec + (size_t)__ldg(J.band_grec_off + band) * (size_t)J.n_targets);
-        sm.ring_rec_bytes = (uint32_t)(NT > 0 ? J.n_targets * (int)sizeof(GroupRec) : 0);
+        sm.ring_rec = (const uint8_t *)(J.grec + (size_t)__ldg(J.band_grec_off + band) * (size_t)J.rec_slots);
+        sm.ring_rec_bytes = (uint32_t)(NT > 0 ? J.rec_slots * (int)sizeof(GroupRec) : 0);
         sm.ring_wm = has_wm ? J.wm.dst + (size_t)ys0 * J.wm.dst_stride + (size_t)cx0 * 4 : nullptr;
         sm.ring_wm_stride = has_wm ? J.wm.dst_stride : 0;
     }
@@ -1513,7 +1514,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
                 const int pv = __ldg(t.tile_parts + tile);
                 // the lean kernels always run the table form (a tile without outputs gets an empty table);
                 // the general one keeps its generic loops when the tile has no cached form
-                if (FAST || (pv & 255)) xtab_fill(sm.xt, sm.xi[T], T, t, tile, cx0, ws, tid, pv);
+                if (FAST || (pv & 255)) xtab_fill(sm.xt, sm.xi[T], T, t, tile, cx0, ws, tid, pv, (VINT && J.vint) ? t.fix_d_vint : t.fix_d);
                 else if (tid == 0) sm.xi[T] = XInfo{t.dst, t.dst_stride, t.exact_job, (uint32_t)t.fix_d, t.local, 0, 0, 1};
             }
         }
@@ -1639,6 +1640,86 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
         }
         if (++rs == STAGES) { rs = 0; rph ^= 1; }
     };
+
+    // Integer-moment vertical pass (GroupRecI, ipg_device.h): a wide target whose rows between two output centres
+    // enter two exact integer moments per byte column -- one IDP.2A per channel and row, no byte -> fp32 unpack, no
+    // per-row weights -- and become fp32 once per segment (~15 rows): completed row = carry + aR M0 + bR M1, next
+    // carry = aL M0 + bL M1.  The parked row then takes the same CTA-wide horizontal pass as the fp32 form.
+    if constexpr (VINT) {
+        if (J.vint) { // CTA-uniform
+            uint32_t A[12];
+            float2 cy[6];
+#pragma unroll
+            for (int i = 0; i < 12; i++) A[i] = 0u;
+#pragma unroll
+            for (int i = 0; i < 6; i++) cy[i] = make_float2(0.f, 0.f);
+            const bool check = J.redo_flag != nullptr;
+            float4 *xb = sm.xbuf[0];
+            const int pbase = (slot * 4) & ~7, pkey = (slot >> 1) & 7, plo = (slot & 1) * 4; // swz(4 * slot + j), as park_row
+            // the 12 byte columns of one source row into their moment words: [m, 0] takes bytes 0 / 2, [0, m] bytes 1 / 3
+            auto row_in = [&](const uint4 &q, uint32_t m) {
+                const uint32_t mh = m << 16;
+                A[0] = __dp2a_lo(m, q.x, A[0]); A[1] = __dp2a_lo(mh, q.x, A[1]); A[2] = __dp2a_hi(m, q.x, A[2]);
+                A[3] = __dp2a_lo(m, q.y, A[3]); A[4] = __dp2a_lo(mh, q.y, A[4]); A[5] = __dp2a_hi(m, q.y, A[5]);
+                A[6] = __dp2a_lo(m, q.z, A[6]); A[7] = __dp2a_lo(mh, q.z, A[7]); A[8] = __dp2a_hi(m, q.z, A[8]);
+                A[9] = __dp2a_lo(m, q.w, A[9]); A[10] = __dp2a_lo(mh, q.w, A[10]); A[11] = __dp2a_hi(m, q.w, A[11]);
+            };
+            for (; g < ngroups; g++) {
+                mbar_wait(&sm.full[rs], rph);
+                if constexpr (INLINE) {
+                    if (wm_tma && (g & 3) == warp && (tid & 31) == 0) store_group(g, rs);
+                }
+                const StreamStage &stg = sm.stage[rs];
+                const GroupRecI &G = *reinterpret_cast<const GroupRecI *>(&stg.rec[1]);
+                const int nr = yend - ys0 - g * STREAM_GROUP;
+                // At most one segment ends in a group (after row end_k; STREAM_GROUP - 1 when none): the rows up to it
+                // go in first, then the end -- the one copy of that code: the row loop stays small enough for the
+                // instruction cache it shares with the resize CTAs -- then the rows after it.
+                const int ke = G.end_k, e = G.end_e;
+                uint32_t opq = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < STREAM_GROUP; k++) {
+                    const uint4 q = stg.rows[k][slot];
+                    if (k < nr) opq &= (q.x & q.y) & (q.z & q.w); // (rows past the band's end are stale ring contents, m = 0)
+                    row_in(q, k <= ke ? G.m[k] : 0u);
+                }
+                if (e != -1) { // CTA-uniform: a segment ends in this group
+                    const float4 cf = *reinterpret_cast<const float4 *>(&G.aR);
+                    const float2 aR = make_float2(cf.x, cf.x), bR = make_float2(cf.y, cf.y);
+                    const float2 aL = make_float2(cf.z, cf.z), bL = make_float2(cf.w, cf.w);
+                    float2 v[6];
+#pragma unroll
+                    for (int i = 0; i < 6; i++) {
+                        const uint32_t a0 = A[2 * i], a1 = A[2 * i + 1];
+                        const float2 f0 = make_float2((float)(a0 & 0xfffu), (float)(a1 & 0xfffu));
+                        const float2 f1 = make_float2((float)(a0 >> 12), (float)(a1 >> 12));
+                        v[i] = __ffma2_rn(f1, bR, __ffma2_rn(f0, aR, cy[i]));
+                        cy[i] = __ffma2_rn(f1, bL, __fmul2_rn(f0, aL));
+                        A[2 * i] = A[2 * i + 1] = 0u;
+                    }
+                    if (e >= 0) { // ... and completes output row e
+                        sts128(&xb[pbase | ((plo + 0) ^ pkey)], v[0].x, v[0].y, v[1].x, 65535.0f);
+                        sts128(&xb[pbase | ((plo + 1) ^ pkey)], v[1].y, v[2].x, v[2].y, 65535.0f);
+                        sts128(&xb[pbase | ((plo + 2) ^ pkey)], v[3].x, v[3].y, v[4].x, 65535.0f);
+                        sts128(&xb[pbase | ((plo + 3) ^ pkey)], v[4].y, v[5].x, v[5].y, 65535.0f);
+                        vwarps_bar();
+                        xcached<true>(sm, 0, e, tid, fix);
+                        vwarps_bar(); // the row buffer is reused by the next emit
+                    }
+                    if (ke < STREAM_GROUP - 1) {
+#pragma unroll
+                        for (int k = 1; k < STREAM_GROUP; k++) row_in(stg.rows[k][slot], k > ke ? G.m[k] : 0u);
+                    }
+                }
+                if (check && __any_sync(0xffffffffu, opq < 0xff000000u) && (tid & 31) == 0) atomicExch(J.redo_flag, 1);
+                advance();
+            }
+            if constexpr (INLINE) {
+                if (wm_tma && (tid & 31) == 0) tma_store_wait_all();
+            }
+            return;
+        }
+    }
 
     // phase 1: every pixel this warp has met so far is opaque -- alpha comes from the records.
     // The general kernel scans a group before it runs it (it switches to per-pixel alpha from that
@@ -1937,7 +2018,7 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
     // horizontal-pass table (cached form; the engine only sends jobs whose tiles have one)
     if (tid < STREAM_THREADS) {
         for (int e = tid; e < STREAM_XBUF; e += STREAM_THREADS) sm.xbuf[0][e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        xtab_fill(sm.xt, sm.xi[0], 0, J.t[0], tile, cx0, ws, tid, __ldg(J.t[0].tile_parts + tile));
+        xtab_fill(sm.xt, sm.xi[0], 0, J.t[0], tile, cx0, ws, tid, __ldg(J.t[0].tile_parts + tile), J.t[0].fix_d);
     }
     __syncthreads();
 

@@ -3,7 +3,9 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -129,6 +131,132 @@ int certified_fix_d(int taps_x, int taps_y, int parts)
     int lg = 0;
     while ((1 << lg) < parts) lg++;
     return (taps_x + taps_y + 1) / 2 + lg + 5;
+}
+
+// The integer-moment vertical form (build_vint) replaces the 0.5 * taps_y of the vertical fmaf chain and the vertical
+// weight's unit by `vert_units`, the bound build_vint derives for "moments -> fp32 row"; the horizontal terms stay:
+//   1 (fp32 horizontal weight) + 0.5 * taps_x + log2(P) + 0.5 (fmaf(v, 256, 128)) + 1 (floor) and one unit of margin.
+int certified_fix_d_vint(int taps_x, int parts, double vert_units)
+{
+    int lg = 0;
+    while ((1 << lg) < parts) lg++;
+    return (int)std::ceil(vert_units + 0.5 * taps_x + 2.5) + lg + 1;
+}
+
+// Integer-moment records of a wide 8-bit target (GroupRecI, ipg_device.h).  Segment a = source rows [B[a], B[a+1]) with
+// B[a] = ceil(centre of output row a): there the tent of row a falls (weight (1 - (o - c_a) / s) - r / s at r rows past
+// the segment's first row o) and the tent of row a + 1 rises ((1 - (c_{a+1} - o) / s) + r / s); rows above B[0] only
+// raise row 0's.  The model is CHECKED against the newDistrib table (every owned output row, every source row of the
+// band) and the form is refused when it deviates by more than 1e-10 of a weight, when a segment has more than 16 rows
+// (M0 would leave its 12 bits) or when two segments could end in one group.  `vert_units` returns the bound of
+// |fp32 row - exact row| in 1/256 of a 16-bit step:
+//   carry = fl(bL * M1 + fl(aL * M0))        3 |aL| M0 + 2 |bL| M1          (coefficients, product, sum), times 2^-24
+//   row   = fl(bR * M1 + fl(aR * M0 + carry)) 2 |aR| M0 + |bR| M1 + |carry| + |row|  likewise
+// with M0 <= 255 n and M1 <= 255 sum(r) over the segment's rows, |row| <= 65535 (1 + 2^-20).
+static bool build_vint(const StreamGeom &g, const StreamTargetSpec &s, double sample_scale, std::vector<GroupRecI> &out,
+                       double &vert_units)
+{
+    const StreamTargetGeom &t = g.t[0];
+    const AxisPlan &ay = *t.ay;
+    const double scale = (double)s.rect_h / (double)s.dh;
+    if (sample_scale != 257.0 || !(scale >= (double)STREAM_GROUP + 1.0) || !(scale <= 16.0)) return false;
+    const double arg = 1 / scale;
+    std::vector<double> cen((size_t)s.dh);
+    std::vector<int32_t> B((size_t)s.dh + 1);
+    for (int32_t a = 0; a < s.dh; a++) {
+        cen[a] = ((double)a + 0.5) * scale - 0.5;
+        B[a] = std::min(std::max((int32_t)std::ceil(cen[a]), 0), s.rect_h);
+    }
+    B[s.dh] = s.rect_h;
+    auto last = [&](int32_t oy) { return ay.first[oy] + (ay.off[oy + 1] - ay.off[oy]) - 1; };
+    double worst = 0.0;
+    out.clear();
+    for (int b = 0; b < g.n_bands; b++) {
+        const int32_t Y0 = g.band_y[b];
+        const int32_t ng = (g.band_yend[b] - Y0 + STREAM_GROUP - 1) / STREAM_GROUP;
+        const int32_t oyA = t.band_oy[b], oyB = t.band_oy[b + 1], tend = t.band_tend[b];
+        const size_t base = out.size();
+        out.resize(base + (size_t)ng);
+        // what the kernel will compute, in double: checked against the table below
+        struct Seg { double aR, bR, aL, bL; };
+        std::vector<Seg> segs((size_t)std::max(oyB - oyA + 1, 0), Seg{0, 0, 0, 0}); // segment sg at index sg - (oyA - 1)
+        std::vector<int32_t> row_sg((size_t)ng * STREAM_GROUP, INT32_MIN), row_r((size_t)ng * STREAM_GROUP, 0);
+        double L_prev = 0.0, cy_prev = 0.0; // error weight and magnitude of the carry entering the current segment
+        int32_t cur_sg = INT32_MIN, cur_n = 0;
+        int64_t cur_sr = 0;
+        for (int32_t gi = 0; gi < ng; gi++) {
+            GroupRecI &G = out[base + (size_t)gi];
+            memset(&G, 0, sizeof G);
+            G.end_k = STREAM_GROUP - 1;
+            G.end_e = -1;
+            int ends = 0;
+            for (int k = 0; k < STREAM_GROUP; k++) {
+                G.emit[k] = -1;
+                const int32_t ys = Y0 + gi * STREAM_GROUP + k, yr = ys - s.rect_y;
+                if (oyB <= oyA || ys >= tend || yr < ay.first[oyA]) continue;
+                // the segment of this row: the largest a with B[a] <= yr, -1 above B[0]
+                const int32_t sg = (int32_t)(std::upper_bound(B.begin(), B.begin() + s.dh, yr) - B.begin()) - 1;
+                if (sg < oyA - 1 || sg > oyB - 1) return false;
+                const int32_t o = sg >= 0 ? B[sg] : 0, r = yr - o;
+                if (r < 0 || r > 15) return false;
+                if (sg != cur_sg) {
+                    if (cur_n != 0) return false; // the previous segment never ended
+                    cur_sg = sg;
+                }
+                G.m[k] = 1u + ((uint32_t)r << 12);
+                row_sg[(size_t)(ys - Y0)] = sg;
+                row_r[(size_t)(ys - Y0)] = r;
+                cur_n++;
+                cur_sr += r;
+                if (cur_n > 16) return false;
+                const bool seg_end = yr == B[sg + 1] - 1;
+                if (ys == tend - 1 && !seg_end) return false; // the band's last row closes its last segment
+                if (!seg_end) continue;
+                if (++ends > 1) return false;
+                Seg e{0, 0, 0, 0};
+                if (sg >= oyA) { // falling half of output row sg
+                    e.aR = (1 - ((double)o - cen[sg]) * arg) * ay.inv[sg] * sample_scale;
+                    e.bR = -arg * ay.inv[sg] * sample_scale;
+                }
+                if (sg + 1 < oyB) { // rising half of output row sg + 1
+                    e.aL = (1 - (cen[sg + 1] - (double)o) * arg) * ay.inv[sg + 1] * sample_scale;
+                    e.bL = arg * ay.inv[sg + 1] * sample_scale;
+                }
+                G.aR = (float)e.aR; G.bR = (float)e.bR; G.aL = (float)e.aL; G.bL = (float)e.bL;
+                G.emit[k] = sg >= oyA ? sg : -2;
+                G.end_k = k;
+                G.end_e = G.emit[k];
+                segs[(size_t)(sg - (oyA - 1))] = e;
+                const double M0 = 255.0 * cur_n, M1 = 255.0 * (double)cur_sr;
+                if (sg >= oyA) {
+                    const double R = 2 * std::fabs(e.aR) * M0 + std::fabs(e.bR) * M1 + cy_prev + 65535.0 * (1 + 1e-6);
+                    worst = std::max(worst, (L_prev + R) * 256.0 / 16777216.0);
+                }
+                L_prev = 3 * std::fabs(e.aL) * M0 + 2 * std::fabs(e.bL) * M1;
+                cy_prev = std::fabs(e.aL) * M0 + std::fabs(e.bL) * M1;
+                cur_n = 0;
+                cur_sr = 0;
+            }
+        }
+        if (cur_n != 0) return false;
+        // the model against the table: every owned output row over every source row the band walks
+        for (int32_t a = oyA; a < oyB; a++) {
+            for (int32_t ys = Y0; ys < Y0 + ng * STREAM_GROUP; ys++) {
+                const int32_t yr = ys - s.rect_y;
+                double table = 0.0, model = 0.0;
+                if (yr >= ay.first[a] && yr <= last(a)) table = ay.w[(size_t)ay.off[a] + (size_t)(yr - ay.first[a])] * ay.inv[a] * sample_scale;
+                const int32_t sg = row_sg[(size_t)(ys - Y0)], r = row_r[(size_t)(ys - Y0)];
+                if (sg != INT32_MIN) {
+                    const Seg &e = segs[(size_t)(sg - (oyA - 1))];
+                    if (sg == a) model = e.aR + e.bR * r;
+                    else if (sg + 1 == a) model = e.aL + e.bL * r;
+                }
+                if (std::fabs(table - model) > 1e-10 * sample_scale) return false;
+            }
+        }
+    }
+    vert_units = worst + 0.01; // + the model tolerance (<= 32 rows * 255 * 1e-10 * 257 of a 16-bit step)
+    return true;
 }
 
 static bool build_target(StreamGeom &g, int ti, const StreamTargetSpec &s, double sample_scale)
@@ -320,23 +448,38 @@ static std::shared_ptr<const StreamGeom> build_stream(int W, int H, const Stream
         if (e > H) return nullptr;
         g->band_yend[b] = e;
     }
+    // one wide 8-bit target: its vertical pass may also have the integer-moment form (one more record slot per group)
+    std::vector<GroupRecI> irec;
+    double vert_units = 0.0;
+    g->vint_ok = n_targets == 1 && !g->t[0].local && build_vint(*g, targets[0], sample_scale, irec, vert_units);
+    if (g->vint_ok) {
+        int parts = 1;
+        for (int32_t v : g->t[0].tile_parts) parts = std::max(parts, (int)(v & 255));
+        g->t[0].fix_d_vint = certified_fix_d_vint(g->t[0].ax->max_taps, parts, vert_units);
+        if (g->t[0].fix_d_vint >= 120) g->vint_ok = false; // (an opaque alpha sits 128 units from a quantiser step)
+    }
+    const int slots = n_targets + (g->vint_ok ? 1 : 0);
+    g->rec_slots = slots;
     // Group records: the RowRecs re-expressed per accumulator set (parity resolved here), with
     // the opaque-alpha chains the kernel's fast path reads instead of computing.
     g->band_grec_off.resize((size_t)n_bands);
     for (int b = 0; b < n_bands; b++) {
         const int32_t Y0 = g->band_y[b];
         const int32_t ng = (g->band_yend[b] - Y0 + STREAM_GROUP - 1) / STREAM_GROUP;
-        const size_t base = g->grec.size() / (size_t)std::max(n_targets, 1);
+        const size_t base = g->grec.size() / (size_t)std::max(slots, 1);
         g->band_grec_off[b] = (int32_t)base;
         if (n_targets == 0) continue;
-        g->grec.resize((base + (size_t)ng) * (size_t)n_targets);
+        g->grec.resize((base + (size_t)ng) * (size_t)slots);
+        if (g->vint_ok) // the integer-form records of this band's groups, in the slot after the fp32 one
+            for (int32_t gi = 0; gi < ng; gi++)
+                memcpy(&g->grec[(base + (size_t)gi) * (size_t)slots + 1], &irec[base + (size_t)gi], sizeof(GroupRec));
         for (int i = 0; i < n_targets; i++) {
             const StreamTargetGeom &t = g->t[i];
             int par = 0;
             float sa[2] = {0.f, 0.f};
             const float asamp = (float)(65535.0 / sample_scale); // opaque alpha in source-sample units (255 for 8-bit RGBA)
             for (int32_t gi = 0; gi < ng; gi++) {
-                GroupRec &G = g->grec[(base + (size_t)gi) * (size_t)n_targets + (size_t)i];
+                GroupRec &G = g->grec[(base + (size_t)gi) * (size_t)slots + (size_t)i];
                 G.seed0 = sa[0];
                 G.seed1 = sa[1];
                 G.pad[0] = G.pad[1] = 0;

@@ -28,6 +28,8 @@ std::shared_ptr<const AxisPlan> get_axis_plan(int dn, int sn); // cached, thread
 // Half-width of the ambiguity window of the fp32 streaming kernels, in 1/256 of a 16-bit step, for a target whose
 // widest supports are taps_x / taps_y and whose horizontal pass splits an output over `parts` threads (plan.cpp).
 int certified_fix_d(int taps_x, int taps_y, int parts);
+// ... when the vertical pass runs in the integer-moment form: `vert_units` bounds its fp32 error (plan.cpp build_vint)
+int certified_fix_d_vint(int taps_x, int parts, double vert_units);
 
 struct StreamTargetSpec {
     int32_t rect_x, rect_y, rect_w, rect_h;
@@ -51,6 +53,7 @@ struct StreamTargetGeom {
     std::vector<int32_t> band_tend;   // [n_bands] one past last source row with a contribution
     std::vector<int32_t> band_oy;     // [n_bands+1] first output row owned by each band
     int32_t fix_d = 0;
+    int32_t fix_d_vint = 0;           // certificate of the integer-moment vertical form (StreamGeom::vint_ok)
 };
 
 // Everything k_stream needs that depends only on geometry (not on pointers).
@@ -63,7 +66,9 @@ struct StreamGeom {
     std::vector<int32_t> band_y;    // [n_bands+1]
     std::vector<int32_t> band_yend; // [n_bands]
     StreamTargetGeom t[2];
-    std::vector<GroupRec> grec;         // [groups of all bands][n_targets]: what k_stream consumes
+    std::vector<GroupRec> grec;         // [groups of all bands][rec_slots]: what k_stream consumes
+    int32_t rec_slots = 0;              // n_targets, + 1 when vint_ok: target 0's GroupRecI follows its fp32 record
+    bool vint_ok = false;               // one wide 8-bit target whose vertical pass has the integer-moment form (GroupRecI)
     std::vector<int32_t> band_grec_off; // [n_bands] first group of each band
     std::vector<StreamItem> items;  // (tile, band) pairs that have work; job index left 0
     bool lean2_ok = false;          // two targets, [0] local and [1] wide, both in cached forms: the lean fused instantiation

@@ -19,6 +19,9 @@ using namespace ipg;
 static float *g_capture[2] = {nullptr, nullptr};
 extern "C" void planemu_capture(float *t0, float *t1) { g_capture[0] = t0; g_capture[1] = t1; }
 extern "C" int planemu_fix_d(int taps_x, int taps_y, int parts) { return certified_fix_d(taps_x, taps_y, parts); }
+// 1: a geometry with the integer-moment vertical form (StreamGeom::vint_ok) is walked in that form, as the lean kernels do
+static int g_vint = 0;
+extern "C" void planemu_set_vint(int on) { g_vint = on; }
 
 static inline int quant16(float v, int D, bool &amb)
 {
@@ -67,12 +70,55 @@ static int run_impl(const SAMPLE *src, int stride, int W, int H, int n_targets, 
         // two accumulator sets per target, exactly as the kernel's VAcc; weights and emits come
         // from the GroupRec tables the kernel consumes (parity already resolved by the planner)
         std::vector<float> acc[2][2];
+        const bool vint = g_vint && g->vint_ok && !WIDE && opaque_src; // (a non-opaque source is redone in the fp32 form)
+        std::vector<uint32_t> iacc((size_t)STREAM_COLS * 4, 0u); // integer-moment form: M0 | M1 << 12 per byte column
+        std::vector<float> carry((size_t)STREAM_COLS * 4, 0.f);
         bool act[2] = {false, false};
         for (int t = 0; t < n_targets; t++) {
             acc[t][0].assign((size_t)STREAM_COLS * 4, 0.f);
             acc[t][1].assign((size_t)STREAM_COLS * 4, 0.f);
             act[t] = g->t[t].tile_ox[tile + 1] > g->t[t].tile_ox[tile] && g->t[t].band_tend[band] > ys0;
         }
+        // the horizontal pass over a completed, vertically filtered row of target t
+        auto emit_row = [&](int t, int oy, const std::vector<float> &row, int fix_d) -> int {
+            const StreamTargetGeom &tg = g->t[t];
+            for (int ox = tg.tile_ox[tile]; ox < tg.tile_ox[tile + 1]; ox++) {
+                const int k0 = tg.ax->off[ox], n = tg.ax->off[ox + 1] - k0;
+                const int e0 = tg.ax->first[ox] + sp[t].rect_x - cx0;
+                if (e0 < 0 || e0 + n > g->slab_cols) return -2;
+                // horizontal sum in the kernel's order: P threads per output, each over
+                // its interleaved taps in order, then an xor-butterfly of the partial sums
+                const int P = std::max(tg.tile_parts[tile] & 255, 1);
+                if (tg.local) { // must lie inside the owning warp's 128 loaded columns
+                    int w = 0;
+                    while (w < 3 && ox >= tg.warp_ox[(size_t)tile * 4 + w + 1]) w++;
+                    if (ox < tg.warp_ox[(size_t)tile * 4 + w] || e0 < w * g->warp_stride ||
+                        e0 + n > w * g->warp_stride + STREAM_WARP_COLS) return -5;
+                }
+                float part[32][4];
+                for (int pp = 0; pp < P; pp++)
+                    for (int ch = 0; ch < 4; ch++) {
+                        float a = 0.f;
+                        for (int kk = pp; kk < n; kk += P) a = std::fmaf(row[(size_t)(e0 + kk) * 4 + ch], tg.xw[k0 + kk], a);
+                        part[pp][ch] = a;
+                    }
+                for (int off = 1; off < P; off <<= 1) {
+                    float nx[32][4];
+                    for (int pp = 0; pp < P; pp++)
+                        for (int ch = 0; ch < 4; ch++) nx[pp][ch] = part[pp][ch] + part[pp ^ off][ch];
+                    memcpy(part, nx, sizeof nx);
+                }
+                float s[4] = {part[0][0], part[0][1], part[0][2], part[0][3]};
+                for (int ch = 0; ch < 3; ch++) s[ch] = std::fmin(s[ch], s[3]);
+                bool amb = false;
+                uint8_t *d = dsts[t] + ((size_t)oy * sp[t].dw + ox) * 4;
+                for (int ch = 0; ch < 4; ch++) d[ch] = (uint8_t)quant16(s[ch], fix_d, amb);
+                if (g_capture[t])
+                    for (int ch = 0; ch < 4; ch++) g_capture[t][((size_t)oy * sp[t].dw + ox) * 4 + ch] = std::fmaf(s[ch], 256.0f, 128.0f);
+                if (flags && flags[t]) flags[t][(size_t)oy * sp[t].dw + ox] += amb ? 1 : 16; // 16: written once
+            }
+            return 0;
+        };
         const int ngroups = (yend - ys0 + STREAM_GROUP - 1) / STREAM_GROUP;
         for (int gi = 0; gi < ngroups; gi++) {
             for (int k = 0; k < STREAM_GROUP; k++) {
@@ -81,7 +127,33 @@ static int run_impl(const SAMPLE *src, int stride, int W, int H, int n_targets, 
                 for (int t = 0; t < n_targets; t++) {
                     if (!act[t]) continue;
                     const StreamTargetGeom &tg = g->t[t];
-                    const GroupRec &G = g->grec[((size_t)g->band_grec_off[band] + (size_t)gi) * (size_t)n_targets + (size_t)t];
+                    const GroupRec &G = g->grec[((size_t)g->band_grec_off[band] + (size_t)gi) * (size_t)g->rec_slots + (size_t)t];
+                    if (vint) { // k_stream's v_rows_int: IDP.2A per channel and row, fp32 only when a segment ends
+                        const GroupRecI &GI = *reinterpret_cast<const GroupRecI *>(&g->grec[((size_t)g->band_grec_off[band] + (size_t)gi) * (size_t)g->rec_slots + 1]);
+                        if (ys >= yend && (GI.m[k] != 0 || GI.emit[k] != -1)) return -3;
+                        for (int e = 0; e < STREAM_COLS; e++) {
+                            const int c = cx0 + e;
+                            uint8_t px[4] = {0, 0, 0, 255};
+                            if (c < W && ys < yend) for (int q = 0; q < 4; q++) px[q] = (uint8_t)src[(size_t)ys * stride + (size_t)c * 4 + q];
+                            for (int q = 0; q < 3; q++) iacc[(size_t)e * 4 + q] += (uint32_t)px[q] * GI.m[k];
+                        }
+                        if (GI.emit[k] == -1) continue;
+                        std::vector<float> row((size_t)STREAM_COLS * 4, 65535.0f);
+                        for (int e = 0; e < STREAM_COLS; e++)
+                            for (int q = 0; q < 3; q++) {
+                                const uint32_t a = iacc[(size_t)e * 4 + q];
+                                const float f0 = (float)(a & 0xfffu), f1 = (float)(a >> 12);
+                                float &cy = carry[(size_t)e * 4 + q];
+                                row[(size_t)e * 4 + q] = std::fmaf(GI.bR, f1, std::fmaf(GI.aR, f0, cy));
+                                cy = std::fmaf(GI.bL, f1, GI.aL * f0);
+                                iacc[(size_t)e * 4 + q] = 0u;
+                            }
+                        if (GI.emit[k] >= 0) {
+                            const int rc = emit_row(t, GI.emit[k], row, tg.fix_d_vint);
+                            if (rc) return rc;
+                        }
+                        continue;
+                    }
                     const GroupRow r = G.row[k];
                     if (ys >= yend && (r.w0 != 0.f || r.w1 != 0.f || G.emit[k] >= 0)) return -3; // padding rows must be inert
                     for (int e = 0; e < STREAM_COLS; e++) {
@@ -106,44 +178,11 @@ static int run_impl(const SAMPLE *src, int stride, int W, int H, int n_targets, 
                         }
                     }
                     if (G.emit[k] >= 0) {
-                        const int set = G.emit[k] & 1, oy = G.emit[k] >> 1;
+                        const int set = G.emit[k] & 1;
                         std::vector<float> row = acc[t][set];
                         std::fill(acc[t][set].begin(), acc[t][set].end(), 0.f);
-                        for (int ox = tg.tile_ox[tile]; ox < tg.tile_ox[tile + 1]; ox++) {
-                            const int k0 = tg.ax->off[ox], n = tg.ax->off[ox + 1] - k0;
-                            const int e0 = tg.ax->first[ox] + sp[t].rect_x - cx0;
-                            if (e0 < 0 || e0 + n > g->slab_cols) return -2;
-                            // horizontal sum in the kernel's order: P threads per output, each over
-                            // its interleaved taps in order, then an xor-butterfly of the partial sums
-                            const int P = std::max(tg.tile_parts[tile] & 255, 1);
-                            if (tg.local) { // must lie inside the owning warp's 128 loaded columns
-                                int w = 0;
-                                while (w < 3 && ox >= tg.warp_ox[(size_t)tile * 4 + w + 1]) w++;
-                                if (ox < tg.warp_ox[(size_t)tile * 4 + w] || e0 < w * g->warp_stride ||
-                                    e0 + n > w * g->warp_stride + STREAM_WARP_COLS) return -5;
-                            }
-                            float part[32][4];
-                            for (int pp = 0; pp < P; pp++)
-                                for (int ch = 0; ch < 4; ch++) {
-                                    float a = 0.f;
-                                    for (int kk = pp; kk < n; kk += P) a = std::fmaf(row[(size_t)(e0 + kk) * 4 + ch], tg.xw[k0 + kk], a);
-                                    part[pp][ch] = a;
-                                }
-                            for (int off = 1; off < P; off <<= 1) {
-                                float nx[32][4];
-                                for (int pp = 0; pp < P; pp++)
-                                    for (int ch = 0; ch < 4; ch++) nx[pp][ch] = part[pp][ch] + part[pp ^ off][ch];
-                                memcpy(part, nx, sizeof nx);
-                            }
-                            float s[4] = {part[0][0], part[0][1], part[0][2], part[0][3]};
-                            for (int ch = 0; ch < 3; ch++) s[ch] = std::fmin(s[ch], s[3]);
-                            bool amb = false;
-                            uint8_t *d = dsts[t] + ((size_t)oy * sp[t].dw + ox) * 4;
-                            for (int ch = 0; ch < 4; ch++) d[ch] = (uint8_t)quant16(s[ch], tg.fix_d, amb);
-                            if (g_capture[t])
-                                for (int ch = 0; ch < 4; ch++) g_capture[t][((size_t)oy * sp[t].dw + ox) * 4 + ch] = std::fmaf(s[ch], 256.0f, 128.0f);
-                            if (flags && flags[t]) flags[t][(size_t)oy * sp[t].dw + ox] += amb ? 1 : 16; // 16: written once
-                        }
+                        const int rc = emit_row(t, G.emit[k] >> 1, row, tg.fix_d);
+                        if (rc) return rc;
                     }
                 }
             }
@@ -152,7 +191,8 @@ static int run_impl(const SAMPLE *src, int stride, int W, int H, int n_targets, 
     if (info) {
         info[0] = g->n_tiles; info[1] = g->n_bands; info[2] = g->tile_w;
         info[3] = (int)g->items.size(); info[4] = (int)std::min<long>(rows_read, 2147483647L);
-        info[5] = g->t[0].fix_d; info[6] = n_targets > 1 ? g->t[1].fix_d : 0;
+        info[5] = (g_vint && g->vint_ok) ? g->t[0].fix_d_vint : g->t[0].fix_d; info[6] = n_targets > 1 ? g->t[1].fix_d : 0;
+        info[7] = g->vint_ok ? 1 : 0;
     }
     return 0;
 }

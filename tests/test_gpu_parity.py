@@ -483,3 +483,36 @@ def test_ycbcr420_destination_argument_errors(engines):
     with pytest.raises(ip.IpgError) as ei:      # pageable planes: there is no staging path for this layout
         e.run(ip.Image.from_rgba(a), [ip.OpSpec.resize(64, 48, dst_ycbcr420=(y, cb, cr))])
     assert ei.value.code == L.ERR_INVALID and "pinned" in str(ei.value)
+
+
+@pytest.mark.parametrize("w,h,size,alpha,merge", [
+    (1000, 750, 50, "opaque", "1"),      # 15:1, integer centres, one band
+    (1356, 2203, 100, "opaque", "1"),    # 13.56:1 portrait: fractional centres, several bands
+    (2600, 1951, 200, "opaque", "1"),    # 9.755:1
+    (3204, 2401, 160, "opaque", "0"),    # 15.006:1 through the separate wide-target launch (k_stream<1,WM,2>)
+    (1500, 1300, 100, "premul", "1"),    # alpha < 255: the lean kernel raises the redo flag, the fp32 form redoes the job
+])
+def test_integer_moment_thumbnail_is_bit_exact(oracle, monkeypatch, w, h, size, alpha, merge):
+    """The integer-moment vertical pass of wide 8-bit targets (GroupRecI, k_stream's IDP.2A loop; 8.5:1 ... 16:1
+    thumbnails): byte-identical to the oracle, like the fp32 form it replaces (IPG_VINT=0), with the watermark copy
+    riding on the thumbnail pass (thumbnail first in the op list) and a resize beside it.  The two forms flag different
+    pixels (their certificates differ), which is how the test knows the integer form ran."""
+    a = rgba_random(w, h, w + h, alpha)
+    nw, nh = ip.keep_aspect_dims(w, h, 640, 480)
+    cx, cy, cs = ip.crop_square(w, h)
+    gl = synthetic_glyphs(w, h, 3)
+    col = (255, 255, 255, 127)
+    R = oracle.Raster.rgba(a)
+    want = [oracle.crop_and_resize(R, size), oracle.watermark(R, col, [oracle.Glyph(*g) for g in gl]), oracle.resize_image(R, nw, nh)]
+    monkeypatch.setenv("IPG_MERGE_LEAN", merge)
+    fixups = {}
+    for vint in ("1", "0"):
+        monkeypatch.setenv("IPG_VINT", vint)
+        with ip.Engine(devices=[0], precision=ip.PRECISION_EXACT) as e:
+            out = e.run(ip.Image.from_rgba(a), [ip.OpSpec.thumb_crop((cx, cy, cs, cs), size), ip.OpSpec.watermark(w, h, col, [ip.GlyphMask(*g) for g in gl]),
+                                                ip.OpSpec.resize(nw, nh)])
+            fixups[vint] = e.stats()["exact_fixups"]
+        for k, name in enumerate(("thumbnail", "watermark", "resize")):
+            assert np.array_equal(out[k], want[k]), f"IPG_VINT={vint}: {name} differs from the oracle"
+    if alpha == "opaque":
+        assert fixups["1"] != fixups["0"], "the integer-moment form did not run"
