@@ -747,6 +747,47 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 for (int tx = 0; tx < (op.dw + 31) / 32; tx++) xitems.push_back(ExactItem{ji, tx, ty, 0});
         };
 
+        // what a stream job / target takes from its cached geometry (tables ride in the blob), for both streaming kernels
+        auto fill_job = [&](StreamJob &j, const StreamGeom &geom, int nt) {
+            j.src = sv;
+            j.n_targets = nt;
+            j.tile_w = geom.tile_w;
+            j.warp_stride = geom.warp_stride;
+            j.slab_cols = geom.slab_cols;
+            j.n_tiles = geom.n_tiles;
+            j.n_bands = geom.n_bands;
+            j.band_y = blob.put_vec(geom.band_y);
+            j.band_yend = blob.put_vec(geom.band_yend);
+            j.grec = blob.put_vec(geom.grec);
+            j.rec_slots = geom.rec_slots;
+            j.band_grec_off = blob.put_vec(geom.band_grec_off);
+        };
+        auto fill_target = [&](StreamTarget &o, const StreamTargetGeom &tgm, OpRec &op, const StreamTargetSpec &spec) {
+            o.dst = op.dev_out;
+            o.dst_stride = (int)op.dev_pitch;
+            o.dw = op.dw; o.dh = op.dh;
+            o.rect_x = spec.rect_x; o.rect_y = spec.rect_y;
+            o.two_stage = op.kind == IPG_OP_THUMB_CROP;
+            o.fix_d = tgm.fix_d;
+            o.fix_d_vint = tgm.fix_d_vint;
+            o.xoff = blob.put_vec(tgm.ax->off);
+            o.xfirst = blob.put_vec(tgm.ax->first);
+            o.xw = blob.put_vec(tgm.xw);
+            o.tile_ox = blob.put_vec(tgm.tile_ox);
+            o.local = tgm.local ? 1 : 0;
+            o.warp_ox = tgm.local ? blob.put_vec(tgm.warp_ox) : nullptr;
+            o.tile_parts = blob.put_vec(tgm.tile_parts);
+            o.rows = blob.put_vec(tgm.rows);
+            o.band_rec_off = blob.put_vec(tgm.band_rec_off);
+            o.band_tend = blob.put_vec(tgm.band_tend);
+            o.band_oy = blob.put_vec(tgm.band_oy);
+            o.exact_job = -1;
+            if (precision == IPG_PRECISION_EXACT) {
+                o.exact_job = add_exact(op, fixjobs);
+                fix_px += (uint64_t)o.dw * (uint64_t)o.dh;
+            }
+        };
+
         // ---- classify ops
         std::vector<OpRec *> res, wms;
         for (auto &op : t.ops) {
@@ -861,45 +902,11 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 if (wm) wi++;
                 blob.hold(geom);
                 StreamJob j{};
-                j.src = sv;
-                j.n_targets = nt;
+                fill_job(j, *geom, nt);
                 j.has_wm = wm != nullptr;
-                j.tile_w = geom->tile_w;
-                j.warp_stride = geom->warp_stride;
-                j.slab_cols = geom->slab_cols;
-                j.n_tiles = geom->n_tiles;
-                j.n_bands = geom->n_bands;
-                j.band_y = blob.put_vec(geom->band_y);
-                j.band_yend = blob.put_vec(geom->band_yend);
-                j.grec = blob.put_vec(geom->grec);
-                j.rec_slots = geom->rec_slots;
-                j.band_grec_off = blob.put_vec(geom->band_grec_off);
                 for (int k = 0; k < nt; k++) {
-                    const StreamTargetGeom &tgm = geom->t[k];
                     StreamTarget &o = j.t[k];
-                    o.dst = tg[k]->dev_out;
-                    o.dst_stride = (int)tg[k]->dev_pitch;
-                    o.dw = tg[k]->dw; o.dh = tg[k]->dh;
-                    o.rect_x = spec[k].rect_x; o.rect_y = spec[k].rect_y;
-                    o.two_stage = tg[k]->kind == IPG_OP_THUMB_CROP;
-                    o.fix_d = tgm.fix_d;
-                    o.fix_d_vint = tgm.fix_d_vint;
-                    o.xoff = blob.put_vec(tgm.ax->off);
-                    o.xfirst = blob.put_vec(tgm.ax->first);
-                    o.xw = blob.put_vec(tgm.xw);
-                    o.tile_ox = blob.put_vec(tgm.tile_ox);
-                    o.local = tgm.local ? 1 : 0;
-                    o.warp_ox = tgm.local ? blob.put_vec(tgm.warp_ox) : nullptr;
-                    o.tile_parts = blob.put_vec(tgm.tile_parts);
-                    o.rows = blob.put_vec(tgm.rows);
-                    o.band_rec_off = blob.put_vec(tgm.band_rec_off);
-                    o.band_tend = blob.put_vec(tgm.band_tend);
-                    o.band_oy = blob.put_vec(tgm.band_oy);
-                    o.exact_job = -1;
-                    if (precision == IPG_PRECISION_EXACT) {
-                        o.exact_job = add_exact(*tg[k], fixjobs);
-                        fix_px += (uint64_t)o.dw * (uint64_t)o.dh;
-                    }
+                    fill_target(o, geom->t[k], *tg[k], spec[k]);
                     if (o.two_stage && !t.src.opaque_hint) j.check_premul = 1;
                 }
                 if (wm) j.wm = make_wm(*wm);
@@ -961,42 +968,9 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 if (wm) wi++;
                 blob.hold(geom);
                 StreamJob j{};
-                j.src = sv;
-                j.n_targets = 1;
-                j.tile_w = geom->tile_w;
-                j.warp_stride = geom->warp_stride;
-                j.slab_cols = geom->slab_cols;
-                j.n_tiles = geom->n_tiles;
-                j.n_bands = geom->n_bands;
-                j.band_y = blob.put_vec(geom->band_y);
-                j.band_yend = blob.put_vec(geom->band_yend);
-                j.grec = blob.put_vec(geom->grec);
-                j.rec_slots = geom->rec_slots;
-                j.band_grec_off = blob.put_vec(geom->band_grec_off);
+                fill_job(j, *geom, 1);
                 const StreamTargetGeom &tgm = geom->t[0];
-                StreamTarget &o = j.t[0];
-                o.dst = op->dev_out;
-                o.dst_stride = (int)op->dev_pitch;
-                o.dw = op->dw; o.dh = op->dh;
-                o.rect_x = sp1.rect_x; o.rect_y = sp1.rect_y;
-                o.two_stage = op->kind == IPG_OP_THUMB_CROP;
-                o.fix_d = tgm.fix_d;
-                o.xoff = blob.put_vec(tgm.ax->off);
-                o.xfirst = blob.put_vec(tgm.ax->first);
-                o.xw = blob.put_vec(tgm.xw);
-                o.tile_ox = blob.put_vec(tgm.tile_ox);
-                o.local = tgm.local ? 1 : 0;
-                o.warp_ox = tgm.local ? blob.put_vec(tgm.warp_ox) : nullptr;
-                o.tile_parts = blob.put_vec(tgm.tile_parts);
-                o.rows = blob.put_vec(tgm.rows);
-                o.band_rec_off = blob.put_vec(tgm.band_rec_off);
-                o.band_tend = blob.put_vec(tgm.band_tend);
-                o.band_oy = blob.put_vec(tgm.band_oy);
-                o.exact_job = -1;
-                if (precision == IPG_PRECISION_EXACT) {
-                    o.exact_job = add_exact(*op, fixjobs);
-                    fix_px += (uint64_t)o.dw * (uint64_t)o.dh;
-                }
+                fill_target(j.t[0], tgm, *op, sp1);
                 j.fast_path = 5;
                 if (wm) {
                     j.has_wm = 1;

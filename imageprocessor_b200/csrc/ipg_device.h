@@ -86,18 +86,21 @@ struct GroupRec {
 static_assert(sizeof(GroupRec) % 16 == 0, "group records ride in TMA bulk copies (16-byte granular)");
 
 // Integer-moment form of a wide target's vertical pass (plan.cpp build_vint; the 15:1 thumbnail).  Between the
-// centres of two consecutive output rows ("segment", <= 16 source rows) the tent weights of the two open output rows
-// are LINEAR in the row index r, so the segment's contribution to both is a combination of the two exact integer
-// moments M0 = sum x and M1 = sum r * x of every byte column.  A V thread keeps both in ONE 32-bit word per channel,
-// M0 in bits 0..11 (<= 16 * 255) and M1 from bit 12 (<= 255 * 120), fed by one IDP.2A per channel and row with the
-// 16-bit multiplier m = 1 + (r << 12): no byte -> fp32 unpack, no per-row weights, 12 accumulators instead of 24.  When
-// a segment ends, the moments become fp32 once: the completed output row is carry + aR * M0 + bR * M1, and the next
-// row's carry is aL * M0 + bL * M1 (coefficients per segment end, at most one per group).  Same size as a GroupRec:
-// it rides in the slot after the target's fp32 record (StreamJob::rec_slots), which the on-demand redo still uses.
+// centres of two consecutive output rows ("segment") the tent weights of the two open output rows are LINEAR in the
+// row index r, so a run of rows contributes to both through the two exact integer moments M0 = sum x and
+// M1 = sum r * x of every byte column.  A V thread keeps both in ONE 32-bit word per channel, M0 in bits 0..11
+// (<= 16 rows * 255) and M1 from bit 12 (<= 255 * 120), fed by one IDP.2A per channel and row with the 16-bit multiplier
+// m = 1 + (r << 12): no byte -> fp32 unpack, no per-row weights, 12 accumulators instead of 24.  A "piece" is a segment,
+// or half of one that is longer than 16 rows (scales up to 32:1).  When a piece ends the moments are flushed to fp32,
+//     row = fl(bR * M1 + fl(aR * M0 + row)),   carry = fl(bL * M1 + fl(aL * M0 + carry)),   moments = 0
+// and when it also ends its segment, `row` is the vertically filtered output row (parked for the horizontal pass), then
+// row = carry, carry = 0.  At most one piece ends per group.  Same size as a GroupRec: it rides in the slot after the
+// target's fp32 record (StreamJob::rec_slots), which the on-demand redo still uses.
 struct GroupRecI {
     uint32_t m[IPG_GROUP];     // per source row: 1 + (r << 12), or 0 when the row feeds no output this band owns
-    int32_t emit[IPG_GROUP];   // -1: nothing; -2: a segment ends after this row (carry only); >= 0: ... and completes this output row
-    float aR, bR, aL, bL;      // of the segment that ends in this group
+    int32_t emit[IPG_GROUP];   // -1: nothing; -3: a piece ends after this row; -2: ... and its segment, whose row this band does not own;
+                               // >= 0: ... and its segment: output row `emit` is complete
+    float aR, bR, aL, bL;      // of the piece that ends in this group
     int32_t end_k, end_e;      // that end again, as the kernel takes it: row index within the group (IPG_GROUP - 1 when none: then
                                // every row is "before the end") and its emit word (-1 when none)
     uint8_t pad[sizeof(GroupRec) - 8 * IPG_GROUP - 24];

@@ -1643,16 +1643,17 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
 
     // Integer-moment vertical pass (GroupRecI, ipg_device.h): a wide target whose rows between two output centres
     // enter two exact integer moments per byte column -- one IDP.2A per channel and row, no byte -> fp32 unpack, no
-    // per-row weights -- and become fp32 once per segment (~15 rows): completed row = carry + aR M0 + bR M1, next
-    // carry = aL M0 + bL M1.  The parked row then takes the same CTA-wide horizontal pass as the fp32 form.
+    // per-row weights -- and become fp32 once per piece (a segment, or half of one longer than 16 rows): the open row
+    // gains aR M0 + bR M1, the carry into the next one aL M0 + bL M1.  The parked row then takes the same CTA-wide
+    // horizontal pass as the fp32 form.
     if constexpr (VINT) {
         if (J.vint) { // CTA-uniform
             uint32_t A[12];
-            float2 cy[6];
+            float2 cy[6], nx[6]; // the open output row so far, and the carry into the next one
 #pragma unroll
             for (int i = 0; i < 12; i++) A[i] = 0u;
 #pragma unroll
-            for (int i = 0; i < 6; i++) cy[i] = make_float2(0.f, 0.f);
+            for (int i = 0; i < 6; i++) cy[i] = nx[i] = make_float2(0.f, 0.f);
             const bool check = J.redo_flag != nullptr;
             float4 *xb = sm.xbuf[0];
             const int pbase = (slot * 4) & ~7, pkey = (slot >> 1) & 7, plo = (slot & 1) * 4; // swz(4 * slot + j), as park_row
@@ -1683,28 +1684,40 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
                     if (k < nr) opq &= (q.x & q.y) & (q.z & q.w); // (rows past the band's end are stale ring contents, m = 0)
                     row_in(q, k <= ke ? G.m[k] : 0u);
                 }
-                if (e != -1) { // CTA-uniform: a segment ends in this group
+                if (e != -1) { // CTA-uniform: a piece ends in this group: its moments become fp32
                     const float4 cf = *reinterpret_cast<const float4 *>(&G.aR);
                     const float2 aR = make_float2(cf.x, cf.x), bR = make_float2(cf.y, cf.y);
                     const float2 aL = make_float2(cf.z, cf.z), bL = make_float2(cf.w, cf.w);
-                    float2 v[6];
+                    float2 f0[6], f1[6];
 #pragma unroll
                     for (int i = 0; i < 6; i++) {
                         const uint32_t a0 = A[2 * i], a1 = A[2 * i + 1];
-                        const float2 f0 = make_float2((float)(a0 & 0xfffu), (float)(a1 & 0xfffu));
-                        const float2 f1 = make_float2((float)(a0 >> 12), (float)(a1 >> 12));
-                        v[i] = __ffma2_rn(f1, bR, __ffma2_rn(f0, aR, cy[i]));
-                        cy[i] = __ffma2_rn(f1, bL, __fmul2_rn(f0, aL));
+                        f0[i] = make_float2((float)(a0 & 0xfffu), (float)(a1 & 0xfffu));
+                        f1[i] = make_float2((float)(a0 >> 12), (float)(a1 >> 12));
+                        cy[i] = __ffma2_rn(f1[i], bR, __ffma2_rn(f0[i], aR, cy[i]));
                         A[2 * i] = A[2 * i + 1] = 0u;
                     }
-                    if (e >= 0) { // ... and completes output row e
-                        sts128(&xb[pbase | ((plo + 0) ^ pkey)], v[0].x, v[0].y, v[1].x, 65535.0f);
-                        sts128(&xb[pbase | ((plo + 1) ^ pkey)], v[1].y, v[2].x, v[2].y, 65535.0f);
-                        sts128(&xb[pbase | ((plo + 2) ^ pkey)], v[3].x, v[3].y, v[4].x, 65535.0f);
-                        sts128(&xb[pbase | ((plo + 3) ^ pkey)], v[4].y, v[5].x, v[5].y, 65535.0f);
-                        vwarps_bar();
-                        xcached<true>(sm, 0, e, tid, fix);
-                        vwarps_bar(); // the row buffer is reused by the next emit
+                    if (e == -3) { // half a segment: the carry goes on accumulating
+#pragma unroll
+                        for (int i = 0; i < 6; i++) nx[i] = __ffma2_rn(f1[i], bL, __ffma2_rn(f0[i], aL, nx[i]));
+                    } else {       // ... and its segment with it
+                        if (e >= 0) { // output row e is complete
+                            sts128(&xb[pbase | ((plo + 0) ^ pkey)], cy[0].x, cy[0].y, cy[1].x, 65535.0f);
+                            sts128(&xb[pbase | ((plo + 1) ^ pkey)], cy[1].y, cy[2].x, cy[2].y, 65535.0f);
+                            sts128(&xb[pbase | ((plo + 2) ^ pkey)], cy[3].x, cy[3].y, cy[4].x, 65535.0f);
+                            sts128(&xb[pbase | ((plo + 3) ^ pkey)], cy[4].y, cy[5].x, cy[5].y, 65535.0f);
+                        }
+                        // the carry, with this piece's share, becomes the open row (written where the old row sat: no moves)
+#pragma unroll
+                        for (int i = 0; i < 6; i++) {
+                            cy[i] = __ffma2_rn(f1[i], bL, __ffma2_rn(f0[i], aL, nx[i]));
+                            nx[i] = make_float2(0.f, 0.f);
+                        }
+                        if (e >= 0) {
+                            vwarps_bar();
+                            xcached<true>(sm, 0, e, tid, fix);
+                            vwarps_bar(); // the row buffer is reused by the next emit
+                        }
                     }
                     if (ke < STREAM_GROUP - 1) {
 #pragma unroll

@@ -145,21 +145,24 @@ int certified_fix_d_vint(int taps_x, int parts, double vert_units)
 
 // Integer-moment records of a wide 8-bit target (GroupRecI, ipg_device.h).  Segment a = source rows [B[a], B[a+1]) with
 // B[a] = ceil(centre of output row a): there the tent of row a falls (weight (1 - (o - c_a) / s) - r / s at r rows past
-// the segment's first row o) and the tent of row a + 1 rises ((1 - (c_{a+1} - o) / s) + r / s); rows above B[0] only
-// raise row 0's.  The model is CHECKED against the newDistrib table (every owned output row, every source row of the
-// band) and the form is refused when it deviates by more than 1e-10 of a weight, when a segment has more than 16 rows
-// (M0 would leave its 12 bits) or when two segments could end in one group.  `vert_units` returns the bound of
-// |fp32 row - exact row| in 1/256 of a 16-bit step:
-//   carry = fl(bL * M1 + fl(aL * M0))        3 |aL| M0 + 2 |bL| M1          (coefficients, product, sum), times 2^-24
-//   row   = fl(bR * M1 + fl(aR * M0 + carry)) 2 |aR| M0 + |bR| M1 + |carry| + |row|  likewise
-// with M0 <= 255 n and M1 <= 255 sum(r) over the segment's rows, |row| <= 65535 (1 + 2^-20).
+// an origin o) and the tent of row a + 1 rises ((1 - (c_{a+1} - o) / s) + r / s); rows above B[0] only raise row 0's.
+// A segment of more than 16 rows (scales 16:1 ... 32:1) is cut in two pieces of <= 16 rows, each with its own origin,
+// so that M0 keeps its 12 bits: every piece is flushed to fp32 on its own.  The model is CHECKED against the
+// newDistrib table (every owned output row, every source row of the band) and the form is refused when it deviates by
+// more than 1e-10 of a weight or when two pieces could end in one group.  `vert_units` returns the bound of
+// |fp32 row - exact row| in 1/256 of a 16-bit step.  Per flush, with M0 <= 255 n and M1 <= 255 sum(r) over the piece's
+// rows, the running values bounded by 65535 (1 + 1e-6) (true partial sums of a convex combination) and every rounding
+// at most 2^-24 of the magnitude it rounds:
+//   row   = fl(bR * M1 + fl(aR * M0 + row))   (|aR| M0 + |bR| M1) coefficients + (|aR| M0 + |row|) + |row'|
+//   carry = fl(bL * M1 + fl(aL * M0 + carry)) (|aL| M0 + |bL| M1) coefficients + (|aL| M0 + |carry|) + |carry'|
+// summed over the flushes of segment a - 1 (carry) and of segment a (row) for output row a.
 static bool build_vint(const StreamGeom &g, const StreamTargetSpec &s, double sample_scale, std::vector<GroupRecI> &out,
                        double &vert_units)
 {
     const StreamTargetGeom &t = g.t[0];
     const AxisPlan &ay = *t.ay;
     const double scale = (double)s.rect_h / (double)s.dh;
-    if (sample_scale != 257.0 || !(scale >= (double)STREAM_GROUP + 1.0) || !(scale <= 16.0)) return false;
+    if (sample_scale != 257.0 || !(scale >= (double)STREAM_GROUP + 1.0) || !(scale <= 32.0)) return false;
     const double arg = 1 / scale;
     std::vector<double> cen((size_t)s.dh);
     std::vector<int32_t> B((size_t)s.dh + 1);
@@ -169,6 +172,7 @@ static bool build_vint(const StreamGeom &g, const StreamTargetSpec &s, double sa
     }
     B[s.dh] = s.rect_h;
     auto last = [&](int32_t oy) { return ay.first[oy] + (ay.off[oy + 1] - ay.off[oy]) - 1; };
+    const double vmax = 65535.0 * (1 + 1e-6);
     double worst = 0.0;
     out.clear();
     for (int b = 0; b < g.n_bands; b++) {
@@ -177,13 +181,16 @@ static bool build_vint(const StreamGeom &g, const StreamTargetSpec &s, double sa
         const int32_t oyA = t.band_oy[b], oyB = t.band_oy[b + 1], tend = t.band_tend[b];
         const size_t base = out.size();
         out.resize(base + (size_t)ng);
-        // what the kernel will compute, in double: checked against the table below
-        struct Seg { double aR, bR, aL, bL; };
-        std::vector<Seg> segs((size_t)std::max(oyB - oyA + 1, 0), Seg{0, 0, 0, 0}); // segment sg at index sg - (oyA - 1)
-        std::vector<int32_t> row_sg((size_t)ng * STREAM_GROUP, INT32_MIN), row_r((size_t)ng * STREAM_GROUP, 0);
-        double L_prev = 0.0, cy_prev = 0.0; // error weight and magnitude of the carry entering the current segment
-        int32_t cur_sg = INT32_MIN, cur_n = 0;
+        // what the kernel will compute, in double, per piece: checked against the table below
+        struct Piece { int32_t sg; double aR, bR, aL, bL; };
+        std::vector<Piece> pieces;
+        std::vector<int32_t> row_piece((size_t)ng * STREAM_GROUP, -1), row_r((size_t)ng * STREAM_GROUP, 0);
+        std::vector<int32_t> cur_rows;       // rows (relative to Y0) of the piece being walked
+        int32_t cur_o = INT32_MIN;           // ... and its origin
         int64_t cur_sr = 0;
+        double L_prev = 0.0;                 // error weight of the carry that entered the current segment
+        double L_cur = 0.0, R_cur = 0.0;     // ... accumulated by this segment's flushes: into the next row's carry / into its own row
+        double cy_mag = 0.0, nx_mag = 0.0;   // bounds of the running row / carry values
         for (int32_t gi = 0; gi < ng; gi++) {
             GroupRecI &G = out[base + (size_t)gi];
             memset(&G, 0, sizeof G);
@@ -197,23 +204,25 @@ static bool build_vint(const StreamGeom &g, const StreamTargetSpec &s, double sa
                 // the segment of this row: the largest a with B[a] <= yr, -1 above B[0]
                 const int32_t sg = (int32_t)(std::upper_bound(B.begin(), B.begin() + s.dh, yr) - B.begin()) - 1;
                 if (sg < oyA - 1 || sg > oyB - 1) return false;
-                const int32_t o = sg >= 0 ? B[sg] : 0, r = yr - o;
+                const int32_t lo = sg >= 0 ? B[sg] : 0, hi = B[sg + 1], n = hi - lo;
+                if (n < 1 || n > 32) return false;
+                const int32_t half = n > 16 ? (n + 1) / 2 : n;       // rows of the first piece
+                const int32_t o = yr < lo + half ? lo : lo + half, r = yr - o;
+                const bool seg_end = yr == hi - 1, piece_end = seg_end || yr == lo + half - 1;
                 if (r < 0 || r > 15) return false;
-                if (sg != cur_sg) {
-                    if (cur_n != 0) return false; // the previous segment never ended
-                    cur_sg = sg;
+                if (o != cur_o) {
+                    if (!cur_rows.empty()) return false; // the previous piece was never flushed
+                    cur_o = o;
                 }
                 G.m[k] = 1u + ((uint32_t)r << 12);
-                row_sg[(size_t)(ys - Y0)] = sg;
                 row_r[(size_t)(ys - Y0)] = r;
-                cur_n++;
+                cur_rows.push_back(ys - Y0);
                 cur_sr += r;
-                if (cur_n > 16) return false;
-                const bool seg_end = yr == B[sg + 1] - 1;
+                if (cur_rows.size() > 16) return false;
                 if (ys == tend - 1 && !seg_end) return false; // the band's last row closes its last segment
-                if (!seg_end) continue;
+                if (!piece_end) continue;
                 if (++ends > 1) return false;
-                Seg e{0, 0, 0, 0};
+                Piece e{sg, 0, 0, 0, 0};
                 if (sg >= oyA) { // falling half of output row sg
                     e.aR = (1 - ((double)o - cen[sg]) * arg) * ay.inv[sg] * sample_scale;
                     e.bR = -arg * ay.inv[sg] * sample_scale;
@@ -223,39 +232,45 @@ static bool build_vint(const StreamGeom &g, const StreamTargetSpec &s, double sa
                     e.bL = arg * ay.inv[sg + 1] * sample_scale;
                 }
                 G.aR = (float)e.aR; G.bR = (float)e.bR; G.aL = (float)e.aL; G.bL = (float)e.bL;
-                G.emit[k] = sg >= oyA ? sg : -2;
+                G.emit[k] = !seg_end ? -3 : sg >= oyA ? sg : -2;
                 G.end_k = k;
                 G.end_e = G.emit[k];
-                segs[(size_t)(sg - (oyA - 1))] = e;
-                const double M0 = 255.0 * cur_n, M1 = 255.0 * (double)cur_sr;
-                if (sg >= oyA) {
-                    const double R = 2 * std::fabs(e.aR) * M0 + std::fabs(e.bR) * M1 + cy_prev + 65535.0 * (1 + 1e-6);
-                    worst = std::max(worst, (L_prev + R) * 256.0 / 16777216.0);
-                }
-                L_prev = 3 * std::fabs(e.aL) * M0 + 2 * std::fabs(e.bL) * M1;
-                cy_prev = std::fabs(e.aL) * M0 + std::fabs(e.bL) * M1;
-                cur_n = 0;
+                for (int32_t rr : cur_rows) row_piece[(size_t)rr] = (int32_t)pieces.size();
+                pieces.push_back(e);
+                const double M0 = 255.0 * (double)cur_rows.size(), M1 = 255.0 * (double)cur_sr;
+                const double mR = std::fabs(e.aR) * M0 + std::fabs(e.bR) * M1, mL = std::fabs(e.aL) * M0 + std::fabs(e.bL) * M1;
+                R_cur += mR + (std::fabs(e.aR) * M0 + std::min(cy_mag, vmax)) + vmax;
+                L_cur += mL + (std::fabs(e.aL) * M0 + std::min(nx_mag, vmax)) + std::min(nx_mag + mL, vmax);
+                cy_mag += mR;
+                nx_mag += mL;
+                cur_rows.clear();
                 cur_sr = 0;
+                if (seg_end) {
+                    if (sg >= oyA) worst = std::max(worst, (L_prev + R_cur) * 256.0 / 16777216.0);
+                    L_prev = L_cur;
+                    cy_mag = nx_mag;
+                    L_cur = R_cur = nx_mag = 0.0;
+                }
             }
         }
-        if (cur_n != 0) return false;
+        if (!cur_rows.empty()) return false;
         // the model against the table: every owned output row over every source row the band walks
         for (int32_t a = oyA; a < oyB; a++) {
             for (int32_t ys = Y0; ys < Y0 + ng * STREAM_GROUP; ys++) {
                 const int32_t yr = ys - s.rect_y;
                 double table = 0.0, model = 0.0;
                 if (yr >= ay.first[a] && yr <= last(a)) table = ay.w[(size_t)ay.off[a] + (size_t)(yr - ay.first[a])] * ay.inv[a] * sample_scale;
-                const int32_t sg = row_sg[(size_t)(ys - Y0)], r = row_r[(size_t)(ys - Y0)];
-                if (sg != INT32_MIN) {
-                    const Seg &e = segs[(size_t)(sg - (oyA - 1))];
-                    if (sg == a) model = e.aR + e.bR * r;
-                    else if (sg + 1 == a) model = e.aL + e.bL * r;
+                const int32_t pi = row_piece[(size_t)(ys - Y0)], r = row_r[(size_t)(ys - Y0)];
+                if (pi >= 0) {
+                    const Piece &e = pieces[(size_t)pi];
+                    if (e.sg == a) model = e.aR + e.bR * r;
+                    else if (e.sg + 1 == a) model = e.aL + e.bL * r;
                 }
                 if (std::fabs(table - model) > 1e-10 * sample_scale) return false;
             }
         }
     }
-    vert_units = worst + 0.01; // + the model tolerance (<= 32 rows * 255 * 1e-10 * 257 of a 16-bit step)
+    vert_units = worst + 0.01; // + the model tolerance (<= 64 rows * 255 * 1e-10 * 257 of a 16-bit step)
     return true;
 }
 

@@ -72,7 +72,7 @@ static int run_impl(const SAMPLE *src, int stride, int W, int H, int n_targets, 
         std::vector<float> acc[2][2];
         const bool vint = g_vint && g->vint_ok && !WIDE && opaque_src; // (a non-opaque source is redone in the fp32 form)
         std::vector<uint32_t> iacc((size_t)STREAM_COLS * 4, 0u); // integer-moment form: M0 | M1 << 12 per byte column
-        std::vector<float> carry((size_t)STREAM_COLS * 4, 0.f);
+        std::vector<float> irow((size_t)STREAM_COLS * 4, 0.f), carry((size_t)STREAM_COLS * 4, 0.f); // the kernel's cy / nx
         bool act[2] = {false, false};
         for (int t = 0; t < n_targets; t++) {
             acc[t][0].assign((size_t)STREAM_COLS * 4, 0.f);
@@ -138,20 +138,24 @@ static int run_impl(const SAMPLE *src, int stride, int W, int H, int n_targets, 
                             for (int q = 0; q < 3; q++) iacc[(size_t)e * 4 + q] += (uint32_t)px[q] * GI.m[k];
                         }
                         if (GI.emit[k] == -1) continue;
-                        std::vector<float> row((size_t)STREAM_COLS * 4, 65535.0f);
                         for (int e = 0; e < STREAM_COLS; e++)
-                            for (int q = 0; q < 3; q++) {
+                            for (int q = 0; q < 3; q++) { // a piece ends: its moments become fp32
                                 const uint32_t a = iacc[(size_t)e * 4 + q];
                                 const float f0 = (float)(a & 0xfffu), f1 = (float)(a >> 12);
-                                float &cy = carry[(size_t)e * 4 + q];
-                                row[(size_t)e * 4 + q] = std::fmaf(GI.bR, f1, std::fmaf(GI.aR, f0, cy));
-                                cy = std::fmaf(GI.bL, f1, GI.aL * f0);
+                                float &cy = irow[(size_t)e * 4 + q], &nx = carry[(size_t)e * 4 + q];
+                                cy = std::fmaf(f1, GI.bR, std::fmaf(f0, GI.aR, cy));
+                                nx = std::fmaf(f1, GI.bL, std::fmaf(f0, GI.aL, nx));
                                 iacc[(size_t)e * 4 + q] = 0u;
                             }
-                        if (GI.emit[k] >= 0) {
+                        if (GI.emit[k] == -3) continue;
+                        if (GI.emit[k] >= 0) { // ... and its segment: the row is complete
+                            std::vector<float> row = irow;
+                            for (int e = 0; e < STREAM_COLS; e++) row[(size_t)e * 4 + 3] = 65535.0f;
                             const int rc = emit_row(t, GI.emit[k], row, tg.fix_d_vint);
                             if (rc) return rc;
                         }
+                        irow = carry;
+                        std::fill(carry.begin(), carry.end(), 0.f);
                         continue;
                     }
                     const GroupRow r = G.row[k];

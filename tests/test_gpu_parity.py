@@ -490,10 +490,12 @@ def test_ycbcr420_destination_argument_errors(engines):
     (1356, 2203, 100, "opaque", "1"),    # 13.56:1 portrait: fractional centres, several bands
     (2600, 1951, 200, "opaque", "1"),    # 9.755:1
     (3204, 2401, 160, "opaque", "0"),    # 15.006:1 through the separate wide-target launch (k_stream<1,WM,2>)
+    (2592, 2160, 100, "opaque", "1"),    # 21.6:1, the 8K thumbnail's ratio: segments of 21-22 rows, flushed in two pieces
+    (3004, 3000, 100, "opaque", "1"),    # 30:1, the 48 MP thumbnail's ratio
     (1500, 1300, 100, "premul", "1"),    # alpha < 255: the lean kernel raises the redo flag, the fp32 form redoes the job
 ])
 def test_integer_moment_thumbnail_is_bit_exact(oracle, monkeypatch, w, h, size, alpha, merge):
-    """The integer-moment vertical pass of wide 8-bit targets (GroupRecI, k_stream's IDP.2A loop; 8.5:1 ... 16:1
+    """The integer-moment vertical pass of wide 8-bit targets (GroupRecI, k_stream's IDP.2A loop; 8.5:1 ... 32:1
     thumbnails): byte-identical to the oracle, like the fp32 form it replaces (IPG_VINT=0), with the watermark copy
     riding on the thumbnail pass (thumbnail first in the op list) and a resize beside it.  The two forms flag different
     pixels (their certificates differ), which is how the test knows the integer form ran."""
