@@ -914,13 +914,16 @@ static void launch_batch(Ctx &c, Device &d, Lane &L, Batch &B)
                 // the lean instantiation takes the common case; it needs TMA-storable watermark rows
                 const bool wm_tma_ok = !wm || ((sv.w % 4) == 0 && ((((uintptr_t)wm->dev_out) | (uintptr_t)wm->dev_pitch) & 15) == 0);
                 j.fast_path = 0;
+                // a wide target's vertical pass in the integer-moment form (the lean single-target kernels only)
+                const bool vint = c.use_vint && geom->vint_ok;
                 if (wm_tma_ok && redo_flags && (size_t)ji < max_jobs) {
-                    if (geom->lean_ok) j.fast_path = (c.merge_lean || geom->lean_regs_ok) ? 1 : 2;
+                    // 1: the main lean launch (merged: local lane-per-output pass, integer-moment wide pass and -- when built
+                    // with them -- the table forms); 2: the wide-target instantiation on the side stream (every table form)
+                    if (geom->lean_ok) j.fast_path = (geom->lean_regs_ok || (c.merge_lean && (IPG_LEAN4_TABLES || vint))) ? 1 : 2;
                     else if (lean2 && geom->lean2_ok) j.fast_path = 3;
                 }
                 j.redo_flag = (j.fast_path && !t.src.opaque_hint) ? redo_flags + ji : nullptr;
-                // a wide target's vertical pass in the integer-moment form (the lean single-target kernels only)
-                j.vint = (c.use_vint && geom->vint_ok && (j.fast_path == 1 || j.fast_path == 2)) ? 1 : 0;
+                j.vint = (vint && (j.fast_path == 1 || j.fast_path == 2)) ? 1 : 0;
                 sjobs.push_back(j);
                 if (!j.fast_path) {
                     max_nt = std::max(max_nt, nt);

@@ -148,6 +148,14 @@ struct WatermarkD {
     uint32_t sr, sg, sb, sa;     // Uniform.RGBA(): c * 0x101
 };
 
+// 1: the merged lean instantiation (k_stream<1,WM,4>) carries the table forms of the horizontal pass inline (wide
+// targets in the fp32 form, local targets with several outputs per lane); 0: it carries only the lane-per-output local
+// pass and the integer-moment wide pass, and the engine routes every other lean job to the wide-target instantiation
+// (k_stream<1,WM,2>, table forms behind a call) on the side stream: a smaller row loop for the instruction cache.
+#ifndef IPG_LEAN4_TABLES
+#define IPG_LEAN4_TABLES 1
+#endif
+
 // occupancy knobs (overridable for experiments: make EXTRA=-DIPG_CTAS_2T=2 ...)
 #ifndef IPG_CTAS_2T
 #define IPG_CTAS_2T 2

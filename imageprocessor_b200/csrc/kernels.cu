@@ -1243,7 +1243,7 @@ __device__ __forceinline__ uint32_t v_rows_fast(VAcc<false> &S, const StreamJob 
         const int e = stg.rec[0].emit[k];
         if (e >= 0) { // CTA-uniform: this source row completes output row e>>1, held in set e&1
             park_emit<false>(S, e, r, sm.xbuf[0], C.pslot[0]);
-            if (LEAN == 1 || (LEAN == 4 && C.x0_inline)) { // local target: this warp filters its own strip, one output per lane
+            if constexpr (LEAN == 1) { // local target: this warp filters its own strip, one output per lane
                 __syncwarp();
                 const float4 *buf = sm.xbuf[0];
                 float2 rg = make_float2(0.f, 0.f), ba = make_float2(0.f, 0.f);
@@ -1262,6 +1262,8 @@ __device__ __forceinline__ uint32_t v_rows_fast(VAcc<false> &S, const StreamJob 
                 }
                 if (C.x0_ox >= 0 && (threadIdx.x & (C.x0_parts - 1)) == 0) xfinish<true>(sm.xi[0], sm.xi[0].D, C.x0_ox, e >> 1, rg, ba, fix);
                 __syncwarp(); // the strip is reused by the next emit
+            } else if constexpr (LEAN == 4 && !IPG_LEAN4_TABLES) {
+                // (not this build's case: the engine gives such jobs to the wide-target instantiation)
             } else if constexpr (LEAN == 4) { // table forms, inline (no call: the accumulators stay in registers):
                 const bool loc = sm.xi[0].local != 0; // a wide target, or a local one with several outputs per lane
                 if (loc) __syncwarp(); else vwarps_bar();
@@ -1767,7 +1769,12 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
         }
         if constexpr (LEAN == 3) v_rows_fast2(S, J, stg, sm, C, fix);
         else if constexpr (FAST) {
-            const uint32_t opq = v_rows_fast<LEAN>(S[0], J, stg, sm, C, fix);
+            // The merged instantiation keeps one row loop per horizontal-pass form and picks per CTA: the lane-per-output
+            // local pass (the 12 MP resize) never shares its loop body with the table forms' code, so what a batch of
+            // one kind executes fits the instruction cache (measured: 24.1 -> 23.5 us per 12 MP image, r+t+w).
+            uint32_t opq;
+            if constexpr (LEAN == 4) opq = C.x0_inline ? v_rows_fast<1>(S[0], J, stg, sm, C, fix) : v_rows_fast<4>(S[0], J, stg, sm, C, fix);
+            else opq = v_rows_fast<LEAN>(S[0], J, stg, sm, C, fix);
             if (check && folded && __any_sync(0xffffffffu, opq < 0xff000000u) && (tid & 31) == 0) atomicExch(J.redo_flag, 1);
         } else              v_rows<NT, WM, false>(S, J, stg, sm, C, ys0 + g * STREAM_GROUP, nr, fix);
         advance();
