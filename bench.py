@@ -261,7 +261,7 @@ def workload_config(n_gpus, images_per_gpu):
         "images_per_gpu_per_step": images_per_gpu, "image": f"{W_IMG}x{H_IMG} RGBA8", "ops": "resize+thumb+watermark",
         "sharding": f"by image, {n_gpus} rank(s), no collective",
         "l2_policy": "inputs larger than L2 (each step streams >= 12 GB of distinct sources per GPU)",
-        "precision": "EXACT (fp32 stream + fp64 fix-up: byte-identical to the fp64 reference algorithm)",
+        "precision": "EXACT (fp32 stream -- the thumbnail's vertical pass in exact integer moments -- + fp64 fix-up: byte-identical to the fp64 reference algorithm)",
     }
 
 
@@ -712,13 +712,19 @@ def config_c5(ip, rank, world, local_rank, barrier, max_over_ranks, sum_over_ran
     wkB = StreamingWorker(procB, threads, decode=lambda item: item)
     msgsB = [(task(i), decoded[i]) for i in range(n)]
     wkB.run(msgsB)                                   # untimed: a steady-state worker has its pinned slabs and plans already
-    barrier()
-    eng.reset_stats()
-    sB = wkB.run(msgsB)
-    eng.flush()
-    barrier()
-    stB = eng.stats()
-    wallB = max_over_ranks(sB.wall_s)
+    # the pass lasts ~70 ms, so one pinned-slab allocation or plan-cache miss inside it (~100 ms; which images share a batch,
+    # hence the band hints and the first-fit slab layout, is a matter of thread timing) shows as a 2.5x slower pass: three
+    # timed passes, the median one is reported and all three walls are kept
+    repsB = []
+    for _ in range(3):
+        barrier()
+        eng.reset_stats()
+        sB = wkB.run(msgsB)
+        eng.flush()
+        barrier()
+        repsB.append((max_over_ranks(sB.wall_s), sB, eng.stats()))
+    wallB, sB, stB = sorted(repsB, key=lambda r: r[0])[1]
+    wallsB = [round(r[0], 4) for r in repsB]
     procB.close()
 
     # parity on a sampled subset (rank 0): same engine, lossless container instead of the lossy encoders
@@ -795,7 +801,8 @@ def config_c5(ip, rank, world, local_rank, barrier, max_over_ranks, sum_over_ran
                                              "outputs is encoded on the device (bit for bit Go's jpeg.Encode q85); the PNG half still pays the host encoder"),
         "end_to_end_device_jpeg_encode_all_targets_jpeg": dict(leg(sD, stD, wallD), what="task.Format = \"jpeg\": every output is a JPEG and "
                                                               "none is encoded on the host; decode remains"),
-        "raster_only_decoded_inputs_no_encode": leg(sB, stB, wallB),
+        "raster_only_decoded_inputs_no_encode": dict(leg(sB, stB, wallB), wall_s_of_the_three_timed_passes=wallsB,
+                                                     what="median of three timed passes over the decoded stream"),
         "objects_saved_rank0": n_objects, "setup_s_untimed": setup_s, "verified": verified,
     }
 
@@ -912,7 +919,7 @@ def main():
     pass_b_GBps = geo.bytes_thumb_pass * n_iso / (max(both_ms - pass_a_ms, 1e-9) * 1e-3) / 1e9
     roofline = {
         "bound": "hbm",
-        "kernel": "k_stream<1,true,4> (lean): per image a resize + watermark-copy pass and a thumbnail pass, all in one launch",
+        "kernel": "k_stream<1,true,4> (lean): per image a resize + watermark-copy pass and a thumbnail pass (integer-moment vertical form), all in one launch",
         "achieved": merged_GBps, "peak": peak, "unit": "GB/s", "frac": merged_GBps / peak, "peak_source": peak_src,
         "frac_of_nominal_8TBs": merged_GBps / 8000.0,
         "algorithmic_bytes_per_image": geo.bytes_per_image,
@@ -929,7 +936,7 @@ def main():
             "how": f"second engine, IPG_MERGE_LEAN=0 IPG_NO_OVERLAP=1, {n_iso} device-resident images: each pass is its own launch",
             "resize+watermark_copy": {"kernel": "k_stream<1,true,1>", "algorithmic_bytes_per_image": geo.bytes_lean_pass,
                                       "achieved": pass_a_GBps, "frac": pass_a_GBps / peak, "us_per_image": 1e3 * pass_a_ms / n_iso},
-            "thumbnail": {"kernel": "k_stream<1,false,2>", "algorithmic_bytes_per_image": geo.bytes_thumb_pass,
+            "thumbnail": {"kernel": "k_stream<1,false,2> (integer-moment vertical form)", "algorithmic_bytes_per_image": geo.bytes_thumb_pass,
                           "achieved": pass_b_GBps, "frac": pass_b_GBps / peak, "us_per_image": 1e3 * (both_ms - pass_a_ms) / n_iso}},
         "stream_us_per_image": 1e3 * stream_ms_per_image,
         "fix_kernel_ms_per_step": st["fix_kernel_ms"] / args.steps,

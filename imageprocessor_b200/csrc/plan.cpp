@@ -185,8 +185,9 @@ static bool build_vint(const StreamGeom &g, const StreamTargetSpec &s, double sa
         struct Piece { int32_t sg; double aR, bR, aL, bL; };
         std::vector<Piece> pieces;
         std::vector<int32_t> row_piece((size_t)ng * STREAM_GROUP, -1), row_r((size_t)ng * STREAM_GROUP, 0);
-        std::vector<int32_t> cur_rows;       // rows (relative to Y0) of the piece being walked
+        int32_t cur_first = -1, cur_n = 0;   // rows (relative to Y0) of the piece being walked: first, count
         int32_t cur_o = INT32_MIN;           // ... and its origin
+        int32_t seg_hint = std::max(oyA - 1, -1); // the segments are met in order: no search per row
         int64_t cur_sr = 0;
         double L_prev = 0.0;                 // error weight of the carry that entered the current segment
         double L_cur = 0.0, R_cur = 0.0;     // ... accumulated by this segment's flushes: into the next row's carry / into its own row
@@ -202,8 +203,9 @@ static bool build_vint(const StreamGeom &g, const StreamTargetSpec &s, double sa
                 const int32_t ys = Y0 + gi * STREAM_GROUP + k, yr = ys - s.rect_y;
                 if (oyB <= oyA || ys >= tend || yr < ay.first[oyA]) continue;
                 // the segment of this row: the largest a with B[a] <= yr, -1 above B[0]
-                const int32_t sg = (int32_t)(std::upper_bound(B.begin(), B.begin() + s.dh, yr) - B.begin()) - 1;
-                if (sg < oyA - 1 || sg > oyB - 1) return false;
+                while (seg_hint + 1 < s.dh && B[seg_hint + 1] <= yr) seg_hint++;
+                const int32_t sg = seg_hint;
+                if (sg < oyA - 1 || sg > oyB - 1 || (sg >= 0 && B[sg] > yr)) return false;
                 const int32_t lo = sg >= 0 ? B[sg] : 0, hi = B[sg + 1], n = hi - lo;
                 if (n < 1 || n > 32) return false;
                 const int32_t half = n > 16 ? (n + 1) / 2 : n;       // rows of the first piece
@@ -211,14 +213,15 @@ static bool build_vint(const StreamGeom &g, const StreamTargetSpec &s, double sa
                 const bool seg_end = yr == hi - 1, piece_end = seg_end || yr == lo + half - 1;
                 if (r < 0 || r > 15) return false;
                 if (o != cur_o) {
-                    if (!cur_rows.empty()) return false; // the previous piece was never flushed
+                    if (cur_n != 0) return false; // the previous piece was never flushed
                     cur_o = o;
                 }
+                if (cur_n == 0) cur_first = ys - Y0;
                 G.m[k] = 1u + ((uint32_t)r << 12);
                 row_r[(size_t)(ys - Y0)] = r;
-                cur_rows.push_back(ys - Y0);
+                cur_n++;
                 cur_sr += r;
-                if (cur_rows.size() > 16) return false;
+                if (cur_n > 16) return false;
                 if (ys == tend - 1 && !seg_end) return false; // the band's last row closes its last segment
                 if (!piece_end) continue;
                 if (++ends > 1) return false;
@@ -235,15 +238,15 @@ static bool build_vint(const StreamGeom &g, const StreamTargetSpec &s, double sa
                 G.emit[k] = !seg_end ? -3 : sg >= oyA ? sg : -2;
                 G.end_k = k;
                 G.end_e = G.emit[k];
-                for (int32_t rr : cur_rows) row_piece[(size_t)rr] = (int32_t)pieces.size();
+                for (int32_t rr = cur_first; rr < cur_first + cur_n; rr++) row_piece[(size_t)rr] = (int32_t)pieces.size();
                 pieces.push_back(e);
-                const double M0 = 255.0 * (double)cur_rows.size(), M1 = 255.0 * (double)cur_sr;
+                const double M0 = 255.0 * (double)cur_n, M1 = 255.0 * (double)cur_sr;
                 const double mR = std::fabs(e.aR) * M0 + std::fabs(e.bR) * M1, mL = std::fabs(e.aL) * M0 + std::fabs(e.bL) * M1;
                 R_cur += mR + (std::fabs(e.aR) * M0 + std::min(cy_mag, vmax)) + vmax;
                 L_cur += mL + (std::fabs(e.aL) * M0 + std::min(nx_mag, vmax)) + std::min(nx_mag + mL, vmax);
                 cy_mag += mR;
                 nx_mag += mL;
-                cur_rows.clear();
+                cur_n = 0;
                 cur_sr = 0;
                 if (seg_end) {
                     if (sg >= oyA) worst = std::max(worst, (L_prev + R_cur) * 256.0 / 16777216.0);
@@ -253,10 +256,12 @@ static bool build_vint(const StreamGeom &g, const StreamTargetSpec &s, double sa
                 }
             }
         }
-        if (!cur_rows.empty()) return false;
+        if (cur_n != 0) return false;
         // the model against the table: every owned output row over every source row the band walks
         for (int32_t a = oyA; a < oyB; a++) {
-            for (int32_t ys = Y0; ys < Y0 + ng * STREAM_GROUP; ys++) {
+            // (rows outside output a's support and outside segments a - 1 and a have neither a tap nor a model weight)
+            const int32_t r0 = std::min(ay.first[a], a > 0 ? B[a - 1] : 0), r1 = std::max(last(a), B[a + 1] - 1);
+            for (int32_t ys = std::max(Y0, r0 + s.rect_y); ys < std::min(Y0 + ng * STREAM_GROUP, r1 + s.rect_y + 1); ys++) {
                 const int32_t yr = ys - s.rect_y;
                 double table = 0.0, model = 0.0;
                 if (yr >= ay.first[a] && yr <= last(a)) table = ay.w[(size_t)ay.off[a] + (size_t)(yr - ay.first[a])] * ay.inv[a] * sample_scale;

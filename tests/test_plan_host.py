@@ -442,3 +442,77 @@ def test_direct_kernel_two_stage_sixteen_bit_and_rejections(emu, oracle):
     # supports wider than DIRECT_MAX_TAPS on a streamable geometry are not this kernel's: the planner says so
     rc, *_ = run_direct(emu, rgba_random(400, 300, 1), (0, 0, 400, 300, 102, 76), 0)
     assert rc == -1
+
+
+# ---- the integer-moment vertical form of wide 8-bit targets (GroupRecI; k_stream's IDP.2A loop) -----------------------------
+@pytest.fixture()
+def vint_emu(emu):
+    emu.planemu_set_vint(1)
+    yield emu
+    emu.planemu_set_vint(0)
+
+
+@pytest.mark.parametrize("w,h,size,bands", [
+    (1000, 750, 50, 3),      # 15:1, integer centres (the 12 MP thumbnail's shape)
+    (1000, 750, 50, 1),      # ... one band
+    (1356, 2203, 100, 7),    # 13.56:1 portrait, fractional centres, many bands
+    (905, 640, 64, 2),       # 10:1
+    (2592, 2160, 100, 4),    # 21.6:1, the 8K thumbnail's ratio: segments of 21-22 rows flushed in two pieces
+    (3004, 3000, 100, 5),    # 30:1, the 48 MP thumbnail's ratio
+    (1283, 1279, 40, 6),     # 31.98:1, the longest segments the form takes
+])
+def test_integer_moment_form_certified(vint_emu, oracle, w, h, size, bands):
+    """Every byte the integer-moment form does not flag equals the float64 oracle, flagged ones are within 1, the
+    measured |T - T_exact| stays inside the window the planner derived for this form (smaller than the fp32 chain's),
+    and fewer pixels are flagged than by the fp32 form."""
+    a = rgba_random(w, h, w * 3 + h)
+    cx, cy, cs = oracle.crop_square(w, h)
+    spec = (cx, cy, cs, cs, size, size)
+    rc, d, f, info, cap = run_emu_capture(vint_emu, a, spec, 1, bands)
+    assert rc == 0 and info[7] == 1, "the planner did not offer the integer-moment form"
+    T, tx, ty = exact_T(oracle, a, spec)
+    err = np.abs(cap.astype(np.float64) - T)[..., :3].max()
+    assert err <= info[5] - 2, f"|T - T_exact| = {err:.2f} exceeds the derived bound (D = {info[5]})"
+    assert info[5] < vint_emu.planemu_fix_d(tx, ty, 4)
+    ref = oracle.crop_and_resize(oracle.Raster.rgba(a), size)
+    assert np.all((f == 16) | (f == 1)), "each output pixel written exactly once"
+    amb = f == 1
+    assert np.array_equal(d[~amb], ref[~amb]) and np.abs(d.astype(int) - ref.astype(int)).max() <= 1
+    vint_emu.planemu_set_vint(0)
+    rc0, d0, f0, info0, _ = run_emu_capture(vint_emu, a, spec, 1, bands)
+    assert rc0 == 0 and (f0 == 1).sum() >= amb.sum()
+
+
+def test_integer_moment_form_attacked(vint_emu, oracle):
+    """The adversarial images of the fp32 certificate through the integer form (15:1 and 21.6:1): all-255 puts every
+    moment at its maximum (M0 = 16 * 255 fills its 12 bits), stripes at every phase move the mass to either end of a
+    segment; a non-opaque source is not this form's (the emulator, like the engine's redo, takes the fp32 one)."""
+    for (w, h, spec) in [(1000, 750, (125, 0, 750, 750, 50, 50)), (1300, 1080, (110, 0, 1080, 1080, 50, 50))]:
+        worst = 0.0
+        for name, a in adversarial_images(w, h):
+            rc, d, f, info, cap = run_emu_capture(vint_emu, a, spec, 0)
+            assert rc == 0 and info[7] == 1, name
+            T, _, _ = exact_T(oracle, a, spec)
+            err = float(np.abs(cap.astype(np.float64) - T)[..., :3].max())
+            worst = max(worst, err)
+            assert err <= info[5] - 2, f"{name}: |T - T_exact| = {err:.2f} exceeds the derived bound (D = {info[5]})"
+            ref = oracle.scale_bilinear(oracle.Raster.rgba(a), spec[:4], spec[4], spec[5])
+            amb = f == 1
+            assert np.array_equal(d[~amb], ref[~amb]), f"{name}: an unflagged byte differs from the float64 oracle"
+        print(f"{spec}: D = {info[5]}, worst observed |dT| = {worst:.2f}")
+    a = rgba_random(1000, 750, 3, "raw")
+    rc, d, f, info, cap = run_emu_capture(vint_emu, a, (125, 0, 750, 750, 50, 50), 1)
+    ref = oracle.crop_and_resize(oracle.Raster.rgba(a), 50)
+    assert rc == 0 and np.array_equal(d[f != 1], ref[f != 1])
+
+
+def test_integer_moment_form_is_refused_where_it_does_not_apply(vint_emu, oracle):
+    """Local (narrow-support) targets, scales above 32:1 and 16-bit sample sources keep the fp32 form."""
+    for (w, h, spec) in [(400, 300, (0, 0, 400, 300, 102, 76)),        # 4:1 resize: local
+                         (700, 660, (20, 0, 660, 660, 20, 20)),        # 33:1
+                         (640, 480, (80, 0, 480, 480, 200, 200))]:     # 2.4:1 thumbnail of a small image
+        rc, dsts, flags, info = run_emu(vint_emu, rgba_random(w, h, 1), [spec], [1])
+        assert rc == 0 and info[7] == 0, spec
+    R, s = samples16(oracle, "420", 1000, 750, 5)
+    rc, d, f = run_emu16(vint_emu, s, (125, 0, 750, 750, 50, 50), 1)
+    assert rc == 0 and np.array_equal(d[f != 1], oracle.crop_and_resize(R, 50)[f != 1])
