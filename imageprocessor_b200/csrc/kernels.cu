@@ -857,6 +857,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
 }
+// ... on a precomputed 32-bit shared address.  smem_u32() of a ring barrier costs an S2R (SR_CgaCtaId: the address carries
+// the CTA's rank in its cluster window) wherever the compiler rematerialises it -- once per group in the V loops -- so
+// the V warps compute the ring's barrier addresses once and keep them.
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity), "r"(1000000u) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
 {
@@ -1461,7 +1480,14 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     constexpr bool INLINE = StreamCfg<NT, LEAN>::INLINE_PROD;
     using Smem = typename StreamCfg<NT, LEAN>::Smem;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    // The shared-window address of the CTA's memory carries its rank in the cluster (SR_CgaCtaId << 24) and the compiler
+    // rematerialises it -- an S2R in front of every group's loads and barrier waits -- rather than keep it in a register.
+    // Computed once and made opaque, it stays; the assumption gives the pointer its address space back (LDS / STS).
+    uint32_t sm32 = smem_u32(smem_raw);
+    asm volatile("" : "+r"(sm32));
+    Smem *smp = reinterpret_cast<Smem *>(__cvta_shared_to_generic(sm32));
+    __builtin_assume(__isShared(smp));
+    Smem &sm = *smp;
 
     const StreamItem it = items[blockIdx.x];
     const StreamJob &J = jobs[it.job];
@@ -1578,6 +1604,9 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     }
 
     // ===== V warps: vertical pass, and the horizontal pass of every row they complete =====
+    uint32_t bar32 = smem_u32(&sm.full[0]); // full[s] at bar32 + 8 s, empty[s] kEmptyOff further on (see mbar_wait_a)
+    asm volatile("" : "+r"(bar32));
+    constexpr uint32_t kEmptyOff = (uint32_t)(offsetof(Smem, empty) - offsetof(Smem, full));
     VCtx C;
     C.tile = tile; C.cx0 = cx0; C.vtid = tid; C.slot = slot;
     C.c = c; C.W = W; C.ys1 = ys1;
@@ -1629,7 +1658,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
                 // copy was issued a whole group ago)
                 if (wm_tma && (g & 3) == warp) tma_store_wait_read<0>();
             }
-            mbar_arrive(&sm.empty[rs]);
+            mbar_arrive_a(bar32 + kEmptyOff + 8u * (uint32_t)rs);
             if constexpr (INLINE) {
                 if (atomicAdd(&sm.done[rs], 1u) == STREAM_THREADS / 32 - 1) { // the last of the four: refill the stage
                     sm.done[rs] = 0;
@@ -1668,7 +1697,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
                 A[9] = __dp2a_lo(m, q.w, A[9]); A[10] = __dp2a_lo(mh, q.w, A[10]); A[11] = __dp2a_hi(m, q.w, A[11]);
             };
             for (; g < ngroups; g++) {
-                mbar_wait(&sm.full[rs], rph);
+                mbar_wait_a(bar32 + 8u * (uint32_t)rs, rph);
                 if constexpr (INLINE) {
                     if (wm_tma && (g & 3) == warp && (tid & 31) == 0) store_group(g, rs);
                 }
@@ -1744,7 +1773,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
     constexpr bool FOLD = FAST && LEAN != 3;
     const bool check = NT > 0 && (!FAST || J.redo_flag != nullptr); // read once: the asm memory clobbers would reload it per group
     for (; g < ngroups; g++) {
-        mbar_wait(&sm.full[rs], rph);
+        mbar_wait_a(bar32 + 8u * (uint32_t)rs, rph);
         if constexpr (INLINE) {
             if (wm_tma && (g & 3) == warp && (tid & 31) == 0) store_group(g, rs);
         }
@@ -1799,7 +1828,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
             A[T].al[1][0] = A[T].al[1][1] = make_float2(s1, s1);
         }
         for (; g < ngroups; g++) {
-            mbar_wait(&sm.full[rs], rph); // (already complete for the group that triggered the switch)
+            mbar_wait_a(bar32 + 8u * (uint32_t)rs, rph); // (already complete for the group that triggered the switch)
             v_rows<NT, WM, true>(A, J, sm.stage[rs], sm, C, ys0 + g * STREAM_GROUP, yend - ys0 - g * STREAM_GROUP, fix);
             advance();
         }
@@ -1994,7 +2023,11 @@ k_stream_planar(const StreamJob *__restrict__ jobs, const StreamItem *__restrict
     using Smem = PlanarSmem<NRGBA, PLANAR_STAGES>;
     constexpr int STAGES = PLANAR_STAGES;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    uint32_t sm32 = smem_u32(smem_raw); // kept opaque: see k_stream (no S2R SR_CgaCtaId per group)
+    asm volatile("" : "+r"(sm32));
+    Smem *smp = reinterpret_cast<Smem *>(__cvta_shared_to_generic(sm32));
+    __builtin_assume(__isShared(smp));
+    Smem &sm = *smp;
 
     const StreamItem it = items[blockIdx.x];
     const StreamJob &J = jobs[it.job];
