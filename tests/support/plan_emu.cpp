@@ -73,6 +73,7 @@ static int run_impl(const SAMPLE *src, int stride, int W, int H, int n_targets, 
         const bool vint = g_vint && g->vint_ok && !WIDE && opaque_src; // (a non-opaque source is redone in the fp32 form)
         std::vector<uint32_t> iacc((size_t)STREAM_COLS * 4, 0u); // integer-moment form: M0 | M1 << 12 per byte column
         std::vector<float> irow((size_t)STREAM_COLS * 4, 0.f), carry((size_t)STREAM_COLS * 4, 0.f); // the kernel's cy / nx
+        int piece_rows = 0;  // rows in the integer-moment piece being walked
         bool act[2] = {false, false};
         for (int t = 0; t < n_targets; t++) {
             acc[t][0].assign((size_t)STREAM_COLS * 4, 0.f);
@@ -131,6 +132,19 @@ static int run_impl(const SAMPLE *src, int stride, int W, int H, int n_targets, 
                     if (vint) { // k_stream's v_rows_int: IDP.2A per channel and row, fp32 only when a segment ends
                         const GroupRecI &GI = *reinterpret_cast<const GroupRecI *>(&g->grec[((size_t)g->band_grec_off[band] + (size_t)gi) * (size_t)g->rec_slots + 1]);
                         if (ys >= yend && (GI.m[k] != 0 || GI.emit[k] != -1)) return -3;
+                        // the record as the kernel takes it: rows up to end_k before the flush, the rest after it -- that is
+                        // the row-by-row walk below iff end_k / end_e name the group's only end; and a piece never outgrows
+                        // its moment word (<= 16 rows, r <= 15, multiplier 1 + (r << 12))
+                        if (k == 0) {
+                            int ends = 0, ke = STREAM_GROUP - 1, ee = -1;
+                            for (int kk = 0; kk < STREAM_GROUP; kk++)
+                                if (GI.emit[kk] != -1) { ends++; ke = kk; ee = GI.emit[kk]; }
+                            if (ends > 1 || GI.end_k != ke || GI.end_e != ee) return -6;
+                        }
+                        if (GI.m[k] != 0) {
+                            if ((GI.m[k] & 0xfffu) != 1u || (GI.m[k] >> 12) > 15u || ++piece_rows > 16) return -7;
+                        } else if (GI.emit[k] != -1) return -7; // an end sits on a row that feeds the piece
+                        if (GI.emit[k] != -1) piece_rows = 0;
                         for (int e = 0; e < STREAM_COLS; e++) {
                             const int c = cx0 + e;
                             uint8_t px[4] = {0, 0, 0, 255};
@@ -191,6 +205,7 @@ static int run_impl(const SAMPLE *src, int stride, int W, int H, int n_targets, 
                 }
             }
         }
+        if (piece_rows != 0) return -8; // a band's last row closes its last piece
     }
     if (info) {
         info[0] = g->n_tiles; info[1] = g->n_bands; info[2] = g->tile_w;

@@ -516,3 +516,34 @@ def test_integer_moment_form_is_refused_where_it_does_not_apply(vint_emu, oracle
     R, s = samples16(oracle, "420", 1000, 750, 5)
     rc, d, f = run_emu16(vint_emu, s, (125, 0, 750, 750, 50, 50), 1)
     assert rc == 0 and np.array_equal(d[f != 1], oracle.crop_and_resize(R, 50)[f != 1])
+
+
+def test_integer_moment_form_random_geometries(vint_emu, oracle):
+    """Seeded sweep over crop sizes, offsets, scales 8.5:1 ... 33:1 and band counts: whatever geometry the planner gives
+    the integer form must be a partition of the outputs, keep its records consistent (one end per group, pieces of at
+    most 16 rows: the emulator returns an error otherwise) and be certified; above 32:1 it must fall back."""
+    rng = np.random.default_rng(2024)
+    taken = 0
+    for case in range(24):
+        size = int(rng.integers(16, 72))
+        scale = float(rng.uniform(8.6, 33.5))
+        cs = int(round(size * scale)) + int(rng.integers(-3, 4))
+        w, h = cs + int(rng.integers(0, 260)), cs + int(rng.integers(0, 40))
+        if case % 2:
+            w, h = h, w
+        a = rgba_random(w, h, 500 + case)
+        if case % 6 == 5:
+            a[..., :3] = 255
+        cx, cy, cs2 = oracle.crop_square(w, h)
+        spec = (cx, cy, cs2, cs2, size, size)
+        rc, d, f, info, cap = run_emu_capture(vint_emu, a, spec, 1, int(rng.integers(1, 9)))
+        assert rc == 0, f"emulator error {rc} for {spec} in {w}x{h}"
+        s = cs2 / size
+        assert info[7] == (1 if s <= 32.0 else 0), f"{spec}: scale {s:.2f}"
+        taken += int(info[7])
+        T, _, _ = exact_T(oracle, a, spec)
+        assert np.abs(cap.astype(np.float64) - T)[..., :3].max() <= info[5] - 2
+        ref = oracle.crop_and_resize(oracle.Raster.rgba(a), size)
+        assert np.all((f == 16) | (f == 1))
+        assert np.array_equal(d[f != 1], ref[f != 1]) and np.abs(d.astype(int) - ref.astype(int)).max() <= 1, spec
+    assert taken >= 18
