@@ -61,3 +61,45 @@ def test_quantiser_ambiguity_window():
         got = ((low - np.uint32(D)) & np.uint32(0xFFFFFFFF)) >= np.uint32(65536 - 2 * D)
         want = (low < D) | (low >= 65536 - D)
         assert np.array_equal(got, want)
+
+
+def _dp2a(a, b, c, hi):
+    """PTX dp2a.{lo,hi}.u32.u32 d, a, b, c: a = two 16-bit lanes, b = four bytes, of which .lo takes bytes 0, 1 and .hi
+    bytes 2, 3: d = c + a.lo16 * b[sel] + a.hi16 * b[sel + 1]  (mod 2^32)."""
+    a, b, c = a.astype(np.uint64), b.astype(np.uint64), c.astype(np.uint64)
+    sel = 16 if hi else 0
+    b0, b1 = (b >> sel) & 0xFF, (b >> (sel + 8)) & 0xFF
+    return ((c + (a & 0xFFFF) * b0 + (a >> 16) * b1) & 0xFFFFFFFF).astype(np.uint32)
+
+
+def test_integer_moment_word_by_dp2a():
+    # k_stream's integer-moment loop: one IDP.2A per channel and source row with m = 1 + (r << 12) adds x to bits 0..11
+    # (M0 = sum x) and r * x from bit 12 on (M1 = sum r * x) of the channel's word; [m, 0] picks byte 0 (.lo) or 2 (.hi)
+    # of the pixel word, [0, m] = m << 16 picks byte 1 (.lo) -- the alpha byte is never touched
+    rng = np.random.default_rng(0)
+    q = rng.integers(0, 2 ** 32, 4096, dtype=np.uint64).astype(np.uint32)
+    for r in range(16):
+        m = np.full(q.shape, 1 + (r << 12), np.uint32)
+        zero = np.zeros_like(q)
+        byte = lambda k: (q >> np.uint32(8 * k)) & np.uint32(0xFF)   # noqa: E731
+        assert np.array_equal(_dp2a(m, q, zero, False), byte(0) * m)
+        assert np.array_equal(_dp2a(m << np.uint32(16), q, zero, False), byte(1) * m)
+        assert np.array_equal(_dp2a(m, q, zero, True), byte(2) * m)
+        assert m.max() < 2 ** 16                                      # the multiplier fits its 16-bit lane
+    # a piece of 16 rows of the largest byte: M0 = 4080 stays below bit 12, the word below 2^32, and both moments come
+    # back out; the fp32 conversions of the flush are exact (both < 2^24)
+    acc = np.zeros(1, np.uint32)
+    px = np.full(1, 0xFFFFFFFF, np.uint32)
+    for r in range(16):
+        acc = _dp2a(np.full(1, 1 + (r << 12), np.uint32), px, acc, False)
+    assert int(acc[0] & 0xFFF) == 16 * 255 and int(acc[0] >> 12) == 255 * sum(range(16))
+    assert 16 * 255 < 2 ** 12 and (255 * 120 << 12) + 4080 < 2 ** 32
+    assert np.float32(acc[0] >> 12) == 255 * 120 and np.float32(acc[0] & 0xFFF) == 4080
+    # random pieces: the packed word equals the two sums computed apart
+    rows = rng.integers(0, 256, (200, 16), dtype=np.uint32)
+    n = rng.integers(1, 17, 200)
+    for x, k in zip(rows, n):
+        w = np.uint32(0)
+        for r in range(int(k)):
+            w = _dp2a(np.array([1 + (r << 12)], np.uint32), np.array([x[r]], np.uint32), np.array([w], np.uint32), False)[0]
+        assert int(w & 0xFFF) == int(x[:k].sum()) and int(w >> 12) == int((np.arange(k) * x[:k]).sum())
