@@ -1472,7 +1472,8 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
 {
     // LEAN 1: one local target (lane-per-output pass inline); 2: one wide target (split pass);
     // 3: a local and a wide target fused (the source is read once for resize + thumbnail);
-    // 4: one target, local or wide decided per CTA (both passes inline): CTAs of both kinds share the SMs
+    // 4: one target, local or wide decided per CTA (a row loop per horizontal-pass form, all inline, plus the
+    //    integer-moment loop of wide 8-bit targets): CTAs of every kind share the SMs
     constexpr bool FAST = LEAN != 0;
     constexpr bool VINT = LEAN == 2 || LEAN == 4; // these run a wide target's vertical pass in the integer-moment form when the job has one
     static_assert(!FAST || (LEAN == 3 ? NT == 2 : NT == 1), "lean instantiations: one target, or local + wide");
@@ -1800,7 +1801,7 @@ k_stream(const StreamJob *__restrict__ jobs, const StreamItem *__restrict__ item
         else if constexpr (FAST) {
             // The merged instantiation keeps one row loop per horizontal-pass form and picks per CTA: the lane-per-output
             // local pass (the 12 MP resize) never shares its loop body with the table forms' code, so what a batch of
-            // one kind executes fits the instruction cache (measured: 24.1 -> 23.5 us per 12 MP image, r+t+w).
+            // one kind executes fits the instruction cache (measured: 24.1 -> 23.7 us per 12 MP image, r+t+w).
             uint32_t opq;
             if constexpr (LEAN == 4) opq = C.x0_inline ? v_rows_fast<1>(S[0], J, stg, sm, C, fix) : v_rows_fast<4>(S[0], J, stg, sm, C, fix);
             else opq = v_rows_fast<LEAN>(S[0], J, stg, sm, C, fix);
